@@ -1,0 +1,170 @@
+"""Deterministic synthetic clouds and tokenizer weights.
+
+Everything here is a pure function of (seed, shape) built from a counter-based integer
+hash evaluated with numpy uint64 arithmetic, so the build container, the GPU box, the
+golden-vector generator and bench.py all see bit-identical inputs without shipping
+tensors around (torch's global RNG - what the reference draws FPS start indices from,
+src/data/sampler.py:20 - differs between CPU and CUDA generators).
+
+Cloud kinds follow SURVEY.md 8d: "uniform" in [-1,1)^3, "clustered" (8 blobs, centres in
+U(-0.8,0.8)^3, sigma ~= 0.05) and "duplicates" (uniform points sampled with replacement,
+the tie-stress case that mirrors src/data/scanobjectnn.py:171-181).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Tuple
+
+import numpy as np
+
+_M1 = np.uint64(0xBF58476D1CE4E5B9)
+_M2 = np.uint64(0x94D049BB133111EB)
+_G = np.uint64(0x9E3779B97F4A7C15)
+
+
+def _mix(z: np.ndarray) -> np.ndarray:
+    z = z.astype(np.uint64, copy=True)
+    with np.errstate(over="ignore"):
+        z ^= z >> np.uint64(30)
+        z *= _M1
+        z ^= z >> np.uint64(27)
+        z *= _M2
+        z ^= z >> np.uint64(31)
+    return z
+
+
+def hash_u64(seed: int, n: int, stream: int = 0) -> np.ndarray:
+    """n 64-bit hashes for counters 0..n-1 of (seed, stream)."""
+    with np.errstate(over="ignore"):
+        base = _mix(np.array([np.uint64(seed & 0xFFFFFFFFFFFFFFFF) * _G
+                              + np.uint64(stream) * _M2 + np.uint64(0x1234567)], dtype=np.uint64))[0]
+        i = np.arange(n, dtype=np.uint64)
+        return _mix(_mix(i * _G + base) + base)
+
+
+def uniform01(seed: int, n: int, stream: int = 0) -> np.ndarray:
+    """float32 uniforms m/2^24 in [0,1) - exactly representable, platform independent."""
+    return (hash_u64(seed, n, stream) >> np.uint64(40)).astype(np.float32) * np.float32(2.0 ** -24)
+
+
+def randint(seed: int, n: int, high: int, stream: int = 0) -> np.ndarray:
+    return (hash_u64(seed, n, stream) % np.uint64(high)).astype(np.int64)
+
+
+def make_cloud(kind: str, B: int, N: int, seed: int, channels: int = 3) -> np.ndarray:
+    """(B,N,channels) float32.  channels=4 appends the 'height' feature y - min(y)
+    (src/data/augment.py:247-248) as the 4th channel."""
+    if kind == "uniform":
+        xyz = (uniform01(seed, B * N * 3, 1) * np.float32(2) - np.float32(1)).reshape(B, N, 3)
+    elif kind == "clustered":
+        nb = 8
+        ctr = (uniform01(seed, B * nb * 3, 2).astype(np.float64) * 1.6 - 0.8).reshape(B, nb, 3)
+        which = randint(seed, B * N, nb, 3).reshape(B, N)
+        u = uniform01(seed, B * N * 3 * 4, 4).astype(np.float64).reshape(B, N, 3, 4)
+        # Irwin-Hall(4): mean 2, var 1/3 -> unit variance after *sqrt(3); exact in fp64
+        noise = (u.sum(-1) - 2.0) * math.sqrt(3.0) * 0.05
+        xyz = (np.take_along_axis(ctr, which[..., None].repeat(3, -1), axis=1) + noise).astype(np.float32)
+    elif kind == "duplicates":
+        base = make_cloud("uniform", B, N, seed, 3)
+        pick = randint(seed, B * N, N, 5).reshape(B, N)
+        xyz = np.take_along_axis(base, pick[..., None].repeat(3, -1), axis=1)
+    else:
+        raise ValueError(f"unknown cloud kind {kind!r}")
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    if channels == 3:
+        return xyz
+    if channels == 4:
+        h = xyz[..., 1:2] - xyz[..., 1:2].min(axis=1, keepdims=True)
+        return np.ascontiguousarray(np.concatenate([xyz, h], -1), dtype=np.float32)
+    raise ValueError("channels must be 3 or 4")
+
+
+def start_indices(B: int, N: int, seed: int, stage: int = 0) -> np.ndarray:
+    """FPS start index per cloud (stands in for torch.randint(0,N,(B,)), sampler.py:20)."""
+    return randint(seed, B, N, 100 + stage)
+
+
+class _WeightStream:
+    def __init__(self, seed: int):
+        self.seed = seed
+        self.stream = 1000
+
+    def uniform(self, shape, lo: float, hi: float) -> np.ndarray:
+        n = int(np.prod(shape))
+        self.stream += 1
+        u = uniform01(self.seed, n, self.stream).astype(np.float64)
+        return (lo + (hi - lo) * u).astype(np.float32).reshape(shape)
+
+
+def _conv(ws: _WeightStream, sd: Dict[str, np.ndarray], name: str, cout: int, cin: int,
+          bias: bool, ndim: int) -> None:
+    bound = 1.0 / math.sqrt(cin)
+    shape = (cout, cin) + (1,) * (ndim - 2)
+    sd[name + ".weight"] = ws.uniform(shape, -bound, bound)
+    if bias:
+        sd[name + ".bias"] = ws.uniform((cout,), -bound, bound)
+
+
+def _bn(ws: _WeightStream, sd: Dict[str, np.ndarray], name: str, c: int) -> None:
+    sd[name + ".weight"] = ws.uniform((c,), 0.5, 1.5)
+    sd[name + ".bias"] = ws.uniform((c,), -0.1, 0.1)
+    sd[name + ".running_mean"] = ws.uniform((c,), -0.1, 0.1)
+    sd[name + ".running_var"] = ws.uniform((c,), 0.5, 1.5)
+    sd[name + ".num_batches_tracked"] = np.array(0, dtype=np.int64)
+
+
+def apf_encoder_state(embed_dim: int, in_channel: int, seed: int = 0) -> Dict[str, np.ndarray]:
+    """state_dict (numpy) with the reference Encoder's keys (src/models/apf.py:129-143):
+    first_conv.{0,1,3,4,6}.*, second_conv.{0,1,3}.*; BN running stats non-trivial."""
+    ws = _WeightStream(seed)
+    sd: Dict[str, np.ndarray] = {}
+    E = embed_dim
+    _conv(ws, sd, "first_conv.0", 256, in_channel, True, 3)
+    _bn(ws, sd, "first_conv.1", 256)
+    _conv(ws, sd, "first_conv.3", 512, 256, True, 3)
+    _bn(ws, sd, "first_conv.4", 512)
+    _conv(ws, sd, "first_conv.6", E, 512, True, 3)
+    _conv(ws, sd, "second_conv.0", 2 * E, 2 * E, True, 3)
+    _bn(ws, sd, "second_conv.1", 2 * E)
+    _conv(ws, sd, "second_conv.3", E, 2 * E, True, 3)
+    return sd
+
+
+def p3embed_dims(in_channels: int = 3, sample_ratio: float = 0.25, scale: int = 4,
+                 layers: int = 4, embed_dim: int = 256) -> Tuple[int, list]:
+    """(stages, [(Cin, W), ...]) exactly as P3Embed.__init__ derives them
+    (src/models/pix4point.py:123-160)."""
+    stages = int(math.log(1 / sample_ratio, scale))
+    w = int(embed_dim // 2 ** (stages - 1))
+    dims = []
+    cin = in_channels
+    for _ in range(stages):
+        dims.append((cin + 3, w))
+        cin = w
+        w *= 2
+    return stages, dims
+
+
+def p3embed_state(in_channels: int = 3, sample_ratio: float = 0.25, scale: int = 4,
+                  layers: int = 4, embed_dim: int = 256, seed: int = 0) -> Dict[str, np.ndarray]:
+    """state_dict (numpy) with P3Embed's keys for layers=4: convs.{s}.0.{0,1,2}.*, convs.{s}.1.{0,1,3,4}.*"""
+    if layers != 4:
+        raise ValueError("only the reference's layers=4 layout is supported")
+    ws = _WeightStream(seed)
+    sd: Dict[str, np.ndarray] = {}
+    _, dims = p3embed_dims(in_channels, sample_ratio, scale, layers, embed_dim)
+    for s, (cin, w) in enumerate(dims):
+        p = f"convs.{s}"
+        _conv(ws, sd, f"{p}.0.0", w, cin, False, 4)
+        _conv(ws, sd, f"{p}.0.1", w, w, True, 4)
+        _bn(ws, sd, f"{p}.0.2", w)
+        _conv(ws, sd, f"{p}.1.0", 2 * w, 2 * w, False, 4)
+        _bn(ws, sd, f"{p}.1.1", 2 * w)
+        _conv(ws, sd, f"{p}.1.3", w, 2 * w, False, 4)
+        _bn(ws, sd, f"{p}.1.4", w)
+    return sd
+
+
+def to_torch_state(sd: Dict[str, np.ndarray]):
+    import torch
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}

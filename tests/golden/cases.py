@@ -1,0 +1,25 @@
+"""Golden-vector cases shared by make_golden.py (build container, imports the reference) and the
+tests (anywhere).  Inputs and weights are regenerated from seeds by p3tok.synth, so a fixture
+only stores what the REFERENCE returned."""
+
+APF_CASES = {
+    # name: dict(kind, B, N, C, G, k, E, seed)
+    "apf_uniform": dict(kind="uniform", B=2, N=256, C=3, G=16, k=8, E=64, seed=11),
+    "apf_height": dict(kind="clustered", B=2, N=512, C=4, G=24, k=16, E=48, seed=12),
+    "apf_dups": dict(kind="duplicates", B=2, N=256, C=3, G=16, k=8, E=32, seed=13),
+    "apf_k32": dict(kind="uniform", B=1, N=1024, C=3, G=64, k=32, E=96, seed=14),
+}
+
+P4P_CASES = {
+    # name: dict(kind, B, N, k, sample_ratio, embed_dim, seed)   (in_channels=3, scale=4, layers=4)
+    "p4p_2stage": dict(kind="uniform", B=2, N=256, k=8, sample_ratio=1.0 / 16, embed_dim=64, seed=21),
+    "p4p_1stage": dict(kind="clustered", B=2, N=128, k=16, sample_ratio=0.25, embed_dim=256, seed=22),
+    "p4p_2stage_k32": dict(kind="uniform", B=1, N=1024, k=32, sample_ratio=1.0 / 16, embed_dim=256, seed=23),
+}
+
+INDEX_CASES = {
+    # bare FPS / kNN at a BASELINE-like shape: name: dict(kind, B, N, G, k, seed)
+    "idx_c2like": dict(kind="uniform", B=2, N=2048, G=128, k=32, seed=31),
+    "idx_clustered": dict(kind="clustered", B=2, N=1024, G=256, k=32, seed=32),
+    "idx_dups": dict(kind="duplicates", B=2, N=512, G=64, k=16, seed=33),
+}

@@ -1,0 +1,185 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (build container only).
+
+Run:  python tests/golden/make_golden.py
+Needs /root/reference (read-only).  The reference's internal `torch.randint` draw for the
+first FPS index (src/data/sampler.py:20, src/models/pix4point.py:30) is substituted by the
+synthetic start indices for the duration of each call; nothing else is touched.
+While generating, the script also asserts that oracle/port.py is bit-identical to the
+reference on this host and that oracle/oracle.py agrees (indices up to exact ties, tokens
+to 1e-5), i.e. it is the script that pins the oracle.
+"""
+import contextlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "adapting-2d-vits-for-3d-point-cloud-understanding_b200"))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+from p3tok import synth  # noqa: E402
+from oracle import oracle, port, ref_loader  # noqa: E402
+import cases  # noqa: E402
+
+
+@contextlib.contextmanager
+def forced_randint(draws):
+    draws = [torch.as_tensor(d, dtype=torch.long) for d in draws]
+    real = torch.randint
+    it = iter(draws)
+
+    def fake(low, high, size, **kw):
+        d = next(it)
+        assert tuple(size) == tuple(d.shape) and int(d.max()) < high
+        return d.clone()
+
+    torch.randint = fake
+    try:
+        yield
+    finally:
+        torch.randint = real
+
+
+def apf_case(ref, name, c):
+    x = synth.make_cloud(c["kind"], c["B"], c["N"], c["seed"], c["C"])
+    start = synth.start_indices(c["B"], c["N"], c["seed"])
+    sd = synth.apf_encoder_state(c["E"], 2 * c["C"], c["seed"])
+    tsd = synth.to_torch_state(sd)
+    net = ref.PointNet(c["E"], c["G"], c["k"], 2 * c["C"]).eval()
+    net.encoder.load_state_dict(tsd, strict=True)
+    xt = torch.from_numpy(x)
+    with torch.no_grad():
+        with forced_randint([start]):
+            fidx = ref.furthest_point_sample(xt[:, :, :3].contiguous(), c["G"])
+        ctr = ref.index_points(xt[:, :, :3].contiguous(), fidx)
+        kidx = ref.knn_point(c["k"], xt[:, :, :3].contiguous(), ctr)
+        with forced_randint([start]):
+            neigh, center = net.group(xt, xt[:, :, :3])
+        tok = net.encoder(neigh)
+        with forced_randint([start]):
+            tok2 = net(xt)
+        assert torch.equal(tok, tok2)
+        # port == reference, bitwise, on this host
+        pn, pc = port.apf_group(xt, c["G"], c["k"], torch.from_numpy(start))
+        assert torch.equal(pn, neigh) and torch.equal(pc, center), name
+        assert torch.equal(port.apf_encode(tsd, pn), tok), name
+    # oracle vs reference
+    o_tok, grp = oracle.pointnet_apf(sd, x, start, c["G"], c["k"])
+    assert np.array_equal(grp["fps_idx"], fidx.numpy()), name
+    D = oracle.pair_dist(x, grp["center"] if False else oracle.gather_points(x[..., :3], grp["fps_idx"]), oracle.KNN_APF_SQ)
+    ok, msg = oracle.knn_tie_equivalent(grp["knn_idx"], kidx.numpy(), D, ulp=0)
+    assert ok, (name, msg)
+    ties = msg
+    ref_tok = tok.numpy()
+    # Morton order may differ only on equal codes
+    codes, perm = grp["codes"], grp["perm"]
+    ref_center = center.numpy()
+    same_order = np.array_equal(grp["center"], ref_center)
+    err = np.abs(o_tok - ref_tok).max() / np.abs(ref_tok).max()
+    print(f"{name}: fps exact, knn {ties}, morton-order-identical={same_order}, token rel-max-err {err:.2e}")
+    assert same_order and err < 2e-5, name
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), fps_idx=fidx.numpy().astype(np.int32),
+                        knn_idx=kidx.numpy().astype(np.int32), center=ref_center,
+                        neigh=neigh.numpy() if neigh.numel() < 70000 else np.zeros(0, np.float32),
+                        tokens=ref_tok)
+
+
+def p4p_case(ref, name, c):
+    x = synth.make_cloud(c["kind"], c["B"], c["N"], c["seed"], 3)
+    stages, dims = synth.p3embed_dims(3, c["sample_ratio"], 4, 4, c["embed_dim"])
+    starts, n = [], c["N"]
+    for s in range(stages):
+        starts.append(synth.start_indices(c["B"], n, c["seed"], s))
+        n //= 4
+    sd = synth.p3embed_state(3, c["sample_ratio"], 4, 4, c["embed_dim"], c["seed"])
+    tsd = synth.to_torch_state(sd)
+    mod = ref.P3Embed(in_channels=3, sample_ratio=c["sample_ratio"], k=c["k"], embed_dim=c["embed_dim"]).eval()
+    mod.load_state_dict(tsd, strict=True)
+    xt = torch.from_numpy(x)
+    ft = xt.clone().transpose(1, 2).contiguous()
+    rec = {"fps": [], "grp": []}
+    real_s, real_g = mod.sample_fn, mod.grouper
+    mod.sample_fn = lambda p, m: rec["fps"].append(real_s(p, m)) or rec["fps"][-1]
+    mod.grouper = lambda p, cc, f, k: rec["grp"].append(real_g(p, cc, f, k)) or rec["grp"][-1]
+    with torch.no_grad():
+        with forced_randint(starts):
+            rp, rf = mod(xt, ft)
+        pp, pf = port.p3embed(tsd, xt, ft, c["k"], stages, [torch.from_numpy(s) for s in starts])
+        for a, b in zip(rf, pf):
+            assert torch.equal(a, b), name
+        ref_knn = [torch.cdist(rp[s + 1], rp[s]).topk(k=c["k"], dim=-1, largest=False, sorted=True).indices
+                   for s in range(stages)]
+    for s in range(stages):  # the recorded grouper output is what those indices gather
+        bi = torch.arange(c["B"]).view(-1, 1, 1)
+        assert torch.equal(rec["grp"][s][0], rp[s][bi, ref_knn[s]]), name
+    # oracle: drive each stage with the REFERENCE's previous-stage features so one stage's
+    # tie-break differences cannot cascade
+    out = {}
+    for s in range(stages):
+        pts = rp[s].numpy()
+        feats = rf[s].transpose(1, 2).contiguous().numpy()
+        ctr, tok, fidx, kidx = oracle.p3embed_stage(sd, s, pts, feats, starts[s], c["k"])
+        assert np.array_equal(fidx, rec["fps"][s].numpy()), (name, s)
+        D = oracle.pair_dist(pts, ctr, oracle.KNN_P4P_CDIST)
+        ok, msg = oracle.knn_tie_equivalent(kidx, ref_knn[s].numpy(), D, ulp=1)
+        assert ok, (name, s, msg)
+        assert oracle.sorted_by_distance(ref_knn[s].numpy(), D, ulp=1), (name, s)
+        rtok = rf[s + 1].transpose(1, 2).numpy()
+        nbad = int((np.abs(tok - rtok).max(-1) > 2e-5 * np.abs(rtok).max()).sum())
+        print(f"{name} stage {s}: fps exact, knn {msg}, groups with token diff > 2e-5: {nbad}")
+        assert nbad == 0, name
+        out[f"fps_idx{s}"] = rec["fps"][s].numpy().astype(np.int32)
+        out[f"knn_idx{s}"] = ref_knn[s].numpy().astype(np.int32)
+        out[f"centres{s}"] = rp[s + 1].numpy()
+        out[f"tokens{s}"] = rtok
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+
+
+def index_case(ref, name, c):
+    x = synth.make_cloud(c["kind"], c["B"], c["N"], c["seed"], 3)
+    start = synth.start_indices(c["B"], c["N"], c["seed"])
+    xt = torch.from_numpy(x)
+    with torch.no_grad():
+        with forced_randint([start]):
+            f1 = ref.furthest_point_sample(xt, c["G"])
+        with forced_randint([start]):
+            f2 = ref.farthest_point_sampling(xt, c["G"])
+        assert torch.equal(f1, f2)
+        ctr = ref.index_points(xt, f1)
+        k_apf = ref.knn_point(c["k"], xt, ctr)
+        k_p4p = torch.cdist(ctr, xt).topk(k=c["k"], dim=-1, largest=False, sorted=True).indices
+        mperm = ref.MortonEncoder.points_to_morton(ctr)
+    assert np.array_equal(oracle.fps(x, start, c["G"]), f1.numpy()), name
+    cn = ctr.numpy()
+    for mode, r, ulp in ((oracle.KNN_APF_SQ, k_apf, 0), (oracle.KNN_P4P_CDIST, k_p4p, 1)):
+        D = oracle.pair_dist(x, cn, mode)
+        ok, msg = oracle.knn_tie_equivalent(oracle.knn(x, cn, c["k"], mode), r.numpy(), D, ulp=ulp)
+        assert ok, (name, mode, msg)
+        print(f"{name} mode {mode}: {msg}")
+    codes, perm = oracle.morton(cn)
+    rc = np.take_along_axis(codes, mperm.numpy(), 1)
+    assert (np.diff(rc, axis=1) >= 0).all() and np.array_equal(np.sort(mperm.numpy(), 1), np.sort(perm, 1)), name
+    print(f"{name}: fps exact; morton perm identical={np.array_equal(perm, mperm.numpy())}")
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), fps_idx=f1.numpy().astype(np.int32),
+                        knn_apf=k_apf.numpy().astype(np.int32), knn_p4p=k_p4p.numpy().astype(np.int32),
+                        morton_perm=mperm.numpy().astype(np.int32))
+
+
+def main():
+    assert ref_loader.available(), "reference tree not present"
+    ref = ref_loader.load()
+    torch.set_num_threads(os.cpu_count() or 1)
+    for name, c in cases.INDEX_CASES.items():
+        index_case(ref, name, c)
+    for name, c in cases.APF_CASES.items():
+        apf_case(ref, name, c)
+    for name, c in cases.P4P_CASES.items():
+        p4p_case(ref, name, c)
+
+
+if __name__ == "__main__":
+    main()

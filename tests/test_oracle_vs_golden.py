@@ -1,0 +1,84 @@
+"""The oracle against the committed golden vectors (outputs of the reference itself, made by
+tests/golden/make_golden.py).  Runs anywhere - no GPU, no reference tree."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import oracle
+from p3tok import synth
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+@pytest.mark.parametrize("name", list(cases.INDEX_CASES))
+def test_index_cases(golden_dir, name):
+    c = cases.INDEX_CASES[name]
+    g = _load(golden_dir, name)
+    x = synth.make_cloud(c["kind"], c["B"], c["N"], c["seed"], 3)
+    start = synth.start_indices(c["B"], c["N"], c["seed"])
+    fidx = oracle.fps(x, start, c["G"])
+    assert np.array_equal(fidx, g["fps_idx"])          # bit-exact incl. lowest-index ties
+    ctr = oracle.gather_points(x, fidx)
+    for mode, key, ulp in ((oracle.KNN_APF_SQ, "knn_apf", 0), (oracle.KNN_P4P_CDIST, "knn_p4p", 1)):
+        D = oracle.pair_dist(x, ctr, mode)
+        mine = oracle.knn(x, ctr, c["k"], mode)
+        ok, msg = oracle.knn_tie_equivalent(mine, g[key].astype(np.int64), D, ulp=ulp)
+        assert ok, msg
+        assert oracle.sorted_by_distance(mine, D, 0)
+    assert oracle.sorted_by_distance(g["knn_p4p"].astype(np.int64),
+                                     oracle.pair_dist(x, ctr, oracle.KNN_P4P_CDIST), 1)
+    codes, perm = oracle.morton(ctr)
+    ref_perm = g["morton_perm"].astype(np.int64)
+    assert np.array_equal(np.take_along_axis(codes, ref_perm, 1), np.take_along_axis(codes, perm, 1))
+
+
+@pytest.mark.parametrize("name", list(cases.APF_CASES))
+def test_apf_cases(golden_dir, name):
+    c = cases.APF_CASES[name]
+    g = _load(golden_dir, name)
+    x = synth.make_cloud(c["kind"], c["B"], c["N"], c["seed"], c["C"])
+    start = synth.start_indices(c["B"], c["N"], c["seed"])
+    sd = synth.apf_encoder_state(c["E"], 2 * c["C"], c["seed"])
+    tok, grp = oracle.pointnet_apf(sd, x, start, c["G"], c["k"])
+    assert np.array_equal(grp["fps_idx"], g["fps_idx"])
+    D = oracle.pair_dist(x, oracle.gather_points(x[..., :3], grp["fps_idx"]), oracle.KNN_APF_SQ)
+    ok, msg = oracle.knn_tie_equivalent(grp["knn_idx"], g["knn_idx"].astype(np.int64), D, 0)
+    assert ok, msg
+    assert np.array_equal(grp["center"], g["center"])
+    if g["neigh"].size:
+        # same multiset of rows per group (reference order is topk(sorted=False)-arbitrary)
+        a = np.sort(grp["neigh"].reshape(c["B"] * c["G"], c["k"], -1), axis=1)
+        b = np.sort(g["neigh"].reshape(c["B"] * c["G"], c["k"], -1), axis=1)
+        if "dups" not in name:
+            assert np.array_equal(np.sort(a.sum(-1), 1), np.sort(b.sum(-1), 1))
+    ref = g["tokens"].astype(np.float64)
+    assert np.abs(tok - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("name", list(cases.P4P_CASES))
+def test_p4p_cases(golden_dir, name):
+    c = cases.P4P_CASES[name]
+    g = _load(golden_dir, name)
+    stages, dims = synth.p3embed_dims(3, c["sample_ratio"], 4, 4, c["embed_dim"])
+    sd = synth.p3embed_state(3, c["sample_ratio"], 4, 4, c["embed_dim"], c["seed"])
+    pts = synth.make_cloud(c["kind"], c["B"], c["N"], c["seed"], 3)
+    feats = pts.copy()
+    n = c["N"]
+    for s in range(stages):
+        start = synth.start_indices(c["B"], n, c["seed"], s)
+        ctr, tok, fidx, kidx = oracle.p3embed_stage(sd, s, pts, feats, start, c["k"])
+        assert np.array_equal(fidx, g[f"fps_idx{s}"])
+        assert np.array_equal(ctr, g[f"centres{s}"])
+        D = oracle.pair_dist(pts, ctr, oracle.KNN_P4P_CDIST)
+        ok, msg = oracle.knn_tie_equivalent(kidx, g[f"knn_idx{s}"].astype(np.int64), D, 1)
+        assert ok, msg
+        ref = g[f"tokens{s}"].astype(np.float64)
+        assert tok.shape == ref.shape == (c["B"], n // 4, dims[s][1])
+        assert np.abs(tok - ref).max() <= 2e-5 * np.abs(ref).max()
+        # next stage consumes the reference's fp32 outputs (as make_golden.py did)
+        pts, feats = g[f"centres{s}"], g[f"tokens{s}"]
+        n //= 4
