@@ -1,0 +1,249 @@
+// fps.cu - farthest point sampling, one CTA (or one thread-block cluster) per cloud.
+//
+// Replaces furthest_point_sample (reference src/data/sampler.py:4-30) and
+// farthest_point_sampling (src/models/pix4point.py:8-53).
+//
+// Layout: the cloud's raw (N, pt_stride) fp32 rows are staged once into shared memory - with a
+// 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) when the slice is 16-byte aligned, plain loads
+// otherwise - and each thread then keeps PPT=8 points (x,y,z) and their running min-distance
+// in REGISTERS for the whole G-iteration chain.  Shared memory keeps the staged rows only so
+// that the winner's coordinates can be broadcast with one LDS per iteration.
+// Per iteration: 8 distance updates per thread in the reference's exact fp32 order
+// ((dx*dx)+(dy*dy))+(dz*dz) (no FMA contraction), a thread-local strict-> argmax (lowest index
+// wins), two redux.sync per warp (max of the distance bits, then min index among the maxima),
+// one __syncthreads, a second redux over the per-warp winners.  Clouds larger than 8192 points
+// use a cluster of 2/4/8/16 CTAs: each CTA owns a contiguous slice, pushes its candidate
+// (distance, index, xyz) into every peer's shared memory through DSMEM and the cluster barrier
+// orders the exchange.
+#include <cooperative_groups.h>
+#include <cuda/ptx>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace p3tok {
+
+constexpr int FPS_PPT = 8;           // points per thread (registers)
+constexpr int FPS_MAX_THREADS = 1024;
+constexpr int FPS_SLICE = FPS_PPT * FPS_MAX_THREADS;  // 8192 points per CTA
+
+struct __align__(16) FpsCand {
+  uint32_t key;   // float bits of the candidate's min-distance (>= 0 -> order preserving)
+  uint32_t idx;   // global point index
+  float x, y, z;
+  uint32_t pad[3];
+};
+
+__device__ __forceinline__ void warp_argmax(uint32_t& key, uint32_t& idx) {
+  const uint32_t m = __reduce_max_sync(0xffffffffu, key);
+  const uint32_t cand = (key == m) ? idx : 0xffffffffu;
+  idx = __reduce_min_sync(0xffffffffu, cand);
+  key = m;
+}
+
+template <int CL>
+__global__ void __launch_bounds__(FPS_MAX_THREADS, 1)
+fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __restrict__ start_idx,
+           int G, int64_t* __restrict__ out_idx, int slice) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // [rows: slice*pt_stride floats][mbarrier 8B][warp slots 2*32*8B][cluster cands 2*16*32B]
+  float* rows = reinterpret_cast<float*>(smem_raw);
+  const int rows_bytes = ((slice * pt_stride * 4 + 127) / 128) * 128;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + rows_bytes);
+  uint2* wslot = reinterpret_cast<uint2*>(smem_raw + rows_bytes + 16);
+  FpsCand* ccand = reinterpret_cast<FpsCand*>(smem_raw + rows_bytes + 16 + 2 * 32 * sizeof(uint2));
+
+  const int T = blockDim.x;
+  const int t = threadIdx.x;
+  const int lane = t & 31, warp = t >> 5, nwarps = T >> 5;
+  int cloud, rank;
+  if constexpr (CL > 1) {
+    rank = (int)cg::this_cluster().block_rank();
+    cloud = blockIdx.x / CL;
+  } else {
+    rank = 0;
+    cloud = blockIdx.x;
+  }
+  const int p0 = rank * slice;                    // first point of this CTA's slice
+  const int np = max(0, min(slice, N - p0));      // points in this slice
+  const float* src = x + ((size_t)cloud * N + p0) * pt_stride;
+
+  // ---- stage the slice into shared memory
+  const size_t bytes = (size_t)np * pt_stride * 4;
+  const bool tma_ok = (bytes > 0) && (bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  if (tma_ok) {
+    if (t == 0) {
+      cuda::ptx::mbarrier_init(mbar, 1);
+      cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
+    }
+    __syncthreads();
+    if (t == 0) {
+      cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta,
+                                           cuda::ptx::space_shared, mbar, (uint32_t)bytes);
+      // bulk copies are limited by the mbarrier tx-count (2^20-1): our slice is <= 128 KiB
+      cuda::ptx::cp_async_bulk(cuda::ptx::space_cluster, cuda::ptx::space_global, rows, src,
+                               (uint32_t)bytes, mbar);
+    }
+    while (!cuda::ptx::mbarrier_try_wait_parity(mbar, 0)) {
+    }
+  } else {
+    for (int i = t; i < np * pt_stride; i += T) rows[i] = src[i];
+    __syncthreads();
+  }
+
+  // ---- registers: PPT points per thread, local index j*T + t (so j ascending == index ascending)
+  float px[FPS_PPT], py[FPS_PPT], pz[FPS_PPT], md[FPS_PPT];
+#pragma unroll
+  for (int j = 0; j < FPS_PPT; ++j) {
+    const int i = j * T + t;
+    if (i < np) {
+      px[j] = rows[i * pt_stride + 0];
+      py[j] = rows[i * pt_stride + 1];
+      pz[j] = rows[i * pt_stride + 2];
+      md[j] = 1e10f;   // sampler.py:19
+    } else {
+      px[j] = py[j] = pz[j] = 0.f;
+      md[j] = -2.f;    // padding: never the maximum, never updated (fminf keeps -2)
+    }
+  }
+
+  int far = (int)start_idx[cloud];
+  float cx, cy, cz;
+  if constexpr (CL > 1) {
+    // the owner CTA publishes the start point's coordinates to every peer
+    cg::cluster_group cluster = cg::this_cluster();
+    if (t == 0 && far >= p0 && far < p0 + np) {
+      const int l = far - p0;
+      FpsCand c;
+      c.key = 0; c.idx = (uint32_t)far;
+      c.x = rows[l * pt_stride]; c.y = rows[l * pt_stride + 1]; c.z = rows[l * pt_stride + 2];
+      c.pad[0] = c.pad[1] = c.pad[2] = 0;
+      for (int r = 0; r < CL; ++r) *cluster.map_shared_rank(&ccand[0], r) = c;
+    }
+    cluster.sync();
+    cx = ccand[0].x; cy = ccand[0].y; cz = ccand[0].z;
+    cluster.sync();   // everyone has read slot 0 before iteration 0 may overwrite it
+  } else {
+    cx = rows[far * pt_stride]; cy = rows[far * pt_stride + 1]; cz = rows[far * pt_stride + 2];
+  }
+
+  for (int g = 0; g < G; ++g) {
+    if (t == 0 && rank == 0) out_idx[(size_t)cloud * G + g] = far;
+    if (g == G - 1) break;
+    float best = -1.f;
+    int besti = 0;
+#pragma unroll
+    for (int j = 0; j < FPS_PPT; ++j) {
+      const float dx = __fsub_rn(px[j], cx), dy = __fsub_rn(py[j], cy), dz = __fsub_rn(pz[j], cz);
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      md[j] = fminf(md[j], d);
+      if (md[j] > best) { best = md[j]; besti = j; }
+    }
+    uint32_t key = best >= 0.f ? __float_as_uint(best) : 0u;
+    uint32_t idx = best >= 0.f ? (uint32_t)(p0 + besti * T + t) : 0xffffffffu;
+    warp_argmax(key, idx);
+    const int buf = g & 1;
+    if (lane == 0) wslot[buf * 32 + warp] = make_uint2(key, idx);
+    __syncthreads();
+    {
+      const uint2 s = (lane < nwarps) ? wslot[buf * 32 + lane] : make_uint2(0u, 0xffffffffu);
+      key = s.x; idx = s.y;
+      warp_argmax(key, idx);
+    }
+    if constexpr (CL > 1) {
+      cg::cluster_group cluster = cg::this_cluster();
+      if (warp == 0 && lane < CL) {
+        FpsCand c;
+        c.key = key; c.idx = idx;
+        if (idx != 0xffffffffu) {
+          const int l = (int)idx - p0;
+          c.x = rows[l * pt_stride]; c.y = rows[l * pt_stride + 1]; c.z = rows[l * pt_stride + 2];
+        } else {
+          c.x = c.y = c.z = 0.f;
+        }
+        c.pad[0] = c.pad[1] = c.pad[2] = 0;
+        *cluster.map_shared_rank(&ccand[buf * 16 + rank], lane) = c;
+      }
+      cluster.sync();
+      uint32_t bk = 0, bi = 0xffffffffu;
+      int br = 0;
+#pragma unroll
+      for (int r = 0; r < CL; ++r) {
+        const uint32_t k2 = ccand[buf * 16 + r].key, i2 = ccand[buf * 16 + r].idx;
+        if (k2 > bk || (k2 == bk && i2 < bi)) { bk = k2; bi = i2; br = r; }
+      }
+      far = (int)bi;
+      cx = ccand[buf * 16 + br].x; cy = ccand[buf * 16 + br].y; cz = ccand[buf * 16 + br].z;
+    } else {
+      far = (int)idx;
+      cx = rows[far * pt_stride]; cy = rows[far * pt_stride + 1]; cz = rows[far * pt_stride + 2];
+    }
+  }
+  if constexpr (CL > 1) cg::this_cluster().sync();   // no CTA exits while peers may still write to it
+}
+
+static size_t fps_smem_bytes(int slice, int pt_stride) {
+  const size_t rows_bytes = (((size_t)slice * pt_stride * 4 + 127) / 128) * 128;
+  return rows_bytes + 16 + 2 * 32 * sizeof(uint2) + 2 * 16 * sizeof(FpsCand);
+}
+
+template <int CL>
+static int fps_launch(const float* x, int B, int N, int pt_stride, const int64_t* start, int G,
+                      int64_t* out, int slice, int threads, cudaStream_t stream) {
+  const size_t smem = fps_smem_bytes(slice, pt_stride);
+  static thread_local size_t configured[32] = {0};   // per device (cudaFuncSetAttribute is per-device state)
+  int dev = 0;
+  P3_CUDA(cudaGetDevice(&dev));
+  if (dev < 32 && configured[dev] < smem) {
+    P3_CUDA(cudaFuncSetAttribute(fps_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (CL > 8) P3_CUDA(cudaFuncSetAttribute(fps_kernel<CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    configured[dev] = 227 * 1024;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(B * CL));
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  P3_CUDA(cudaLaunchKernelEx(&cfg, fps_kernel<CL>, x, N, pt_stride, start, G, out, slice));
+  return P3TOK_OK;
+}
+
+}  // namespace p3tok
+
+using namespace p3tok;
+
+extern "C" int p3tok_fps(const float* x, int64_t B, int64_t N, int64_t pt_stride,
+                         const int64_t* start_idx, int64_t G, int64_t* out_idx, void* stream) {
+  P3_REQUIRE(B >= 0 && N > 0 && G >= 0 && pt_stride >= 3, P3TOK_ERR_INVALID,
+             "fps: bad shape B=%lld N=%lld G=%lld stride=%lld", (long long)B, (long long)N, (long long)G,
+             (long long)pt_stride);
+  if (B == 0 || G == 0) return P3TOK_OK;
+  P3_REQUIRE(x && start_idx && out_idx, P3TOK_ERR_INVALID, "fps: null pointer");
+  P3_REQUIRE(pt_stride <= 4, P3TOK_ERR_UNSUPPORTED, "fps: pt_stride %lld > 4 (pass xyz or xyz+height rows)",
+             (long long)pt_stride);
+  P3_REQUIRE(N <= (int64_t)FPS_SLICE * 16, P3TOK_ERR_UNSUPPORTED, "fps: N=%lld exceeds 131072", (long long)N);
+  P3_REQUIRE(B * 16 < (1ll << 31) && B * G < (1ll << 40), P3TOK_ERR_UNSUPPORTED, "fps: batch too large");
+  cudaStream_t s = as_stream(stream);
+  int cl = 1;
+  while ((int64_t)cl * FPS_SLICE < N) cl *= 2;
+  const int slice = (int)((N + cl - 1) / cl);
+  int threads = ((slice + FPS_PPT - 1) / FPS_PPT + 31) / 32 * 32;
+  if (threads < 32) threads = 32;
+  // a slice must be fully covered by threads*PPT registers
+  P3_REQUIRE(threads <= FPS_MAX_THREADS, P3TOK_ERR_UNSUPPORTED, "fps: internal slice error");
+  switch (cl) {
+    case 1: return fps_launch<1>(x, (int)B, (int)N, (int)pt_stride, start_idx, (int)G, out_idx, slice, threads, s);
+    case 2: return fps_launch<2>(x, (int)B, (int)N, (int)pt_stride, start_idx, (int)G, out_idx, slice, threads, s);
+    case 4: return fps_launch<4>(x, (int)B, (int)N, (int)pt_stride, start_idx, (int)G, out_idx, slice, threads, s);
+    case 8: return fps_launch<8>(x, (int)B, (int)N, (int)pt_stride, start_idx, (int)G, out_idx, slice, threads, s);
+    default: return fps_launch<16>(x, (int)B, (int)N, (int)pt_stride, start_idx, (int)G, out_idx, slice, threads, s);
+  }
+}

@@ -1,0 +1,126 @@
+"""Host-side weight preparation: fold eval-mode BatchNorm (and P3Embed's activation-free conv
+pair) into the per-layer matrices the kernels consume (struct p3tok_mlp).
+
+  BN(eval):  y = (x - mean) / sqrt(var + eps) * gamma + beta     (eps 1e-5, running stats)
+  conv+BN :  W' = diag(s) W,  b' = (b - mean) * s + beta,  s = gamma / sqrt(var + eps)
+
+APF Encoder (reference src/models/apf.py:129-143): first_conv.{0+1, 3+4, 6}, second_conv.{0+1, 3};
+the concat layer second_conv.0 acts on [global || local] (apf.py:162-163), so its matrix is split
+column-wise into the half applied once per group and the half applied per point.
+P3Embed stage (src/models/pix4point.py:135-156): conv1 = Conv(Cin->W, no bias) then
+Conv(W->W, bias)+BN+ReLU with nothing in between, so the two matrices multiply into one
+(W x Cin); conv2 = [Conv(2W->2W)+BN+ReLU, Conv(2W->W)+BN+ReLU] with input [pooled || local]
+(pix4point.py:184-186).  All folding is done in float64 and rounded once.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Sequence
+
+import torch
+
+BN_EPS = 1e-5
+
+
+@dataclass
+class PatchMLP:
+    """Folded weights of one patch-embedding block, on one device, in one dtype."""
+    cin: int
+    pre_dims: List[int]
+    pre_relu: List[int]
+    mid_dim: int
+    out_dim: int
+    out_relu: int
+    w_pre: List[torch.Tensor]
+    b_pre: List[torch.Tensor]
+    w_mid_g: torch.Tensor
+    w_mid_f: torch.Tensor
+    b_mid: torch.Tensor
+    w_out: torch.Tensor
+    b_out: torch.Tensor
+    _cast: Dict = field(default_factory=dict, repr=False)
+
+    def tensors(self) -> List[torch.Tensor]:
+        out: List[torch.Tensor] = []
+        for w, b in zip(self.w_pre, self.b_pre):
+            out += [w, b]
+        return out + [self.w_mid_g, self.w_mid_f, self.b_mid, self.w_out, self.b_out]
+
+    def meta(self) -> List[int]:
+        return [self.cin, len(self.pre_dims)] + list(self.pre_dims) + list(self.pre_relu) + [
+            self.mid_dim, self.out_dim, self.out_relu]
+
+    def to(self, device, wdtype: torch.dtype = torch.float32) -> "PatchMLP":
+        """Matrices in `wdtype` (float32 or bfloat16), biases always float32, contiguous on device."""
+        key = (str(device), wdtype)
+        if key not in self._cast:
+            def m(t):
+                return t.to(device=device, dtype=wdtype).contiguous()
+
+            def b(t):
+                return t.to(device=device, dtype=torch.float32).contiguous()
+            self._cast[key] = PatchMLP(
+                self.cin, list(self.pre_dims), list(self.pre_relu), self.mid_dim, self.out_dim, self.out_relu,
+                [m(w) for w in self.w_pre], [b(x) for x in self.b_pre], m(self.w_mid_g), m(self.w_mid_f),
+                b(self.b_mid), m(self.w_out), b(self.b_out))
+        return self._cast[key]
+
+
+def _mat(sd, name) -> torch.Tensor:
+    w = sd[name + ".weight"].detach().double().cpu()
+    return w.reshape(w.shape[0], w.shape[1])
+
+
+def _bias(sd, name, n) -> torch.Tensor:
+    b = sd.get(name + ".bias")
+    return b.detach().double().cpu() if b is not None else torch.zeros(n, dtype=torch.float64)
+
+
+def _bn_affine(sd, name):
+    g = sd[name + ".weight"].detach().double().cpu()
+    b = sd[name + ".bias"].detach().double().cpu()
+    m = sd[name + ".running_mean"].detach().double().cpu()
+    v = sd[name + ".running_var"].detach().double().cpu()
+    s = g / torch.sqrt(v + BN_EPS)
+    return s, b - m * s
+
+
+def _conv_bn(sd, conv, bn):
+    W = _mat(sd, conv)
+    b = _bias(sd, conv, W.shape[0])
+    s, t = _bn_affine(sd, bn)
+    return W * s[:, None], b * s + t
+
+
+def fold_apf_encoder(sd: Dict[str, torch.Tensor]) -> PatchMLP:
+    W1, b1 = _conv_bn(sd, "first_conv.0", "first_conv.1")
+    W2, b2 = _conv_bn(sd, "first_conv.3", "first_conv.4")
+    W3, b3 = _mat(sd, "first_conv.6"), _bias(sd, "first_conv.6", 0)
+    Wm, bm = _conv_bn(sd, "second_conv.0", "second_conv.1")
+    Wo = _mat(sd, "second_conv.3")
+    bo = _bias(sd, "second_conv.3", Wo.shape[0])
+    E = W3.shape[0]
+    assert Wm.shape == (2 * E, 2 * E) and Wo.shape == (E, 2 * E)
+    f = lambda t: t.float().contiguous()
+    return PatchMLP(cin=W1.shape[1], pre_dims=[W1.shape[0], W2.shape[0], E], pre_relu=[1, 1, 0],
+                    mid_dim=2 * E, out_dim=E, out_relu=0,
+                    w_pre=[f(W1), f(W2), f(W3)], b_pre=[f(b1), f(b2), f(b3)],
+                    w_mid_g=f(Wm[:, :E]), w_mid_f=f(Wm[:, E:]), b_mid=f(bm), w_out=f(Wo), b_out=f(bo))
+
+
+def fold_p3embed_stage(sd: Dict[str, torch.Tensor], s: int) -> PatchMLP:
+    p = f"convs.{s}"
+    A = _mat(sd, f"{p}.0.0")                       # (W, Cin), no bias, no BN, no activation
+    Bm = _mat(sd, f"{p}.0.1")                      # (W, W) + bias, then BN + ReLU
+    bb = _bias(sd, f"{p}.0.1", Bm.shape[0])
+    s1, t1 = _bn_affine(sd, f"{p}.0.2")
+    W1 = (Bm @ A) * s1[:, None]
+    b1 = bb * s1 + t1
+    Wm, bm = _conv_bn(sd, f"{p}.1.0", f"{p}.1.1")
+    Wo, bo = _conv_bn(sd, f"{p}.1.3", f"{p}.1.4")
+    W = W1.shape[0]
+    assert Wm.shape == (2 * W, 2 * W) and Wo.shape == (W, 2 * W)
+    f = lambda t: t.float().contiguous()
+    return PatchMLP(cin=W1.shape[1], pre_dims=[W], pre_relu=[1], mid_dim=2 * W, out_dim=W, out_relu=1,
+                    w_pre=[f(W1)], b_pre=[f(b1)], w_mid_g=f(Wm[:, :W]), w_mid_f=f(Wm[:, W:]), b_mid=f(bm),
+                    w_out=f(Wo), b_out=f(bo))

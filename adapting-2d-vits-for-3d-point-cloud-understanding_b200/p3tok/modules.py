@@ -1,0 +1,193 @@
+"""nn.Module drop-ins for the reference's tokenizer modules, same constructor and forward
+signatures and the same state_dict keys, running on the sm_100a kernels.
+
+  Group / Encoder / PointNet  <- reference src/models/apf.py:12-217
+  P3Embed                     <- reference src/models/pix4point.py:105-191
+
+The parameter containers (Conv1d/BatchNorm1d/... inside nn.Sequential at the reference's
+indices) exist so reference checkpoints load with strict=True; forward never calls them.
+BatchNorm is applied in eval mode (running statistics folded into the weights, p3tok/fold.py);
+calling forward in training mode raises - train-mode BN couples clouds and needs backward
+(SURVEY.md 8f "next" #4).  `precision`: "fp32" (CUDA-core FFMA, rtol 1e-4 contract) or "bf16"
+(tcgen05 tensor cores, rtol 1e-2 contract).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib, fold, ops
+from .functional import _start
+
+
+def _check_precision(p: str) -> bool:
+    if p not in ("fp32", "bf16"):
+        raise ValueError(f"precision must be 'fp32' or 'bf16', got {p!r}")
+    return p == "bf16"
+
+
+class _FoldedMixin:
+    """Caches the folded weights per (device, dtype); refolds when any parameter changes."""
+
+    def _folded(self, build, device, bf16: bool) -> fold.PatchMLP:
+        ver = tuple((t._version, t.data_ptr()) for t in list(self.parameters()) + list(self.buffers()))
+        cache = self.__dict__.setdefault("_fold_cache", {})
+        if cache.get("ver") != ver:
+            cache.clear()
+            cache["ver"] = ver
+            cache["host"] = build()
+        return cache["host"].to(device, torch.bfloat16 if bf16 else torch.float32)
+
+    def _require_eval(self):
+        if self.training:
+            raise RuntimeError(
+                f"{type(self).__name__}: p3tok implements the eval-mode (folded BatchNorm) forward only; "
+                "call .eval() first (training-mode batch statistics are out of scope, SURVEY.md 8f)")
+
+
+class Group(nn.Module):
+    """apf.py:12-112.  forward(x (B,N,C), xyz (B,N,3)) -> (neighborhood (B,G,k,2C), center (B,G,3)),
+    groups in Morton order of their centres.  The reference's dead cdist(center,center) work
+    (apf.py:38-39) is not reproduced."""
+
+    def __init__(self, num_group: int, group_size: int):
+        super().__init__()
+        self.num_group = num_group
+        self.group_size = group_size
+
+    def indices(self, x: torch.Tensor, start_idx: Optional[torch.Tensor] = None):
+        """(fps_idx (B,G), center (B,G,3), knn_idx (B,G,k), perm (B,G)) - the index half of forward."""
+        fps_idx = ops.fps(x, _start(x, start_idx), self.num_group)
+        center = ops.gather_points(x, fps_idx)[..., :3].contiguous() if x.shape[-1] != 3 else ops.gather_points(x, fps_idx)
+        knn_idx = ops.knn(x, center, self.group_size, _lib.KNN_APF_SQ, False, False)[0]
+        perm = ops.morton_order(center)[0]
+        return fps_idx, center, knn_idx, perm
+
+    def forward(self, x: torch.Tensor, xyz: torch.Tensor, start_idx: Optional[torch.Tensor] = None):
+        # xyz is x[:, :, :3] in the reference's only call site (apf.py:212-214); the kernels read
+        # the xyz channels of x in place, so the separate argument is only shape-checked.
+        if xyz.shape[:2] != x.shape[:2]:
+            raise RuntimeError("Group.forward: x and xyz disagree on (B,N)")
+        x = x.float().contiguous()
+        fps_idx, _, knn_idx, perm = self.indices(x, start_idx)
+        return ops.apf_group(x, fps_idx, knn_idx, perm)
+
+
+class Encoder(nn.Module, _FoldedMixin):
+    """apf.py:114-181.  forward(point_groups (B,G,k,Cin)) -> (B,G,E)."""
+
+    def __init__(self, encoder_channel: int, in_channel: int, precision: str = "fp32"):
+        super().__init__()
+        self.encoder_channel = encoder_channel
+        self.precision = precision
+        E = encoder_channel
+        self.first_conv = nn.Sequential(
+            nn.Conv1d(in_channel, 256, 1), nn.BatchNorm1d(256), nn.ReLU(inplace=True),
+            nn.Conv1d(256, 512, 1), nn.BatchNorm1d(512), nn.ReLU(inplace=True),
+            nn.Conv1d(512, E, 1))
+        self.second_conv = nn.Sequential(
+            nn.Conv1d(2 * E, 2 * E, 1), nn.BatchNorm1d(2 * E), nn.ReLU(inplace=True),
+            nn.Conv1d(2 * E, E, 1))
+
+    def folded(self, device) -> fold.PatchMLP:
+        return self._folded(lambda: fold.fold_apf_encoder(self.state_dict()), device, _check_precision(self.precision))
+
+    def forward(self, point_groups: torch.Tensor) -> torch.Tensor:
+        self._require_eval()
+        B, G, k, cin = point_groups.shape
+        m = self.folded(point_groups.device)
+        rows = point_groups.float().reshape(B * G * k, cin)
+        tok = ops.patch_embed(_lib.ROWS_DIRECT, rows, None, None, None, None, B * G, k, m.tensors(), m.meta(),
+                              _check_precision(self.precision))
+        return tok.view(B, G, self.encoder_channel)
+
+    get_features = forward
+
+
+class PointNet(nn.Module):
+    """apf.py:183-217.  forward(x (B,N,C)) -> (B,G,E).  Fused: the (B,G,k,2C) neighbourhood tensor
+    is never written - the embed kernels gather, centre-subtract and apply the Morton order as the
+    output row."""
+
+    def __init__(self, embed_dim: int, num_group: int, group_size: int, in_channel: int, precision: str = "fp32"):
+        super().__init__()
+        self.group = Group(num_group, group_size)
+        self.encoder = Encoder(embed_dim, in_channel, precision)
+
+    def forward(self, x: torch.Tensor, start_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+        self.encoder._require_eval()
+        x = x.float().contiguous()
+        B, N, C = x.shape
+        G, k = self.group.num_group, self.group.group_size
+        fps_idx, _, knn_idx, perm = self.group.indices(x, start_idx)
+        m = self.encoder.folded(x.device)
+        if m.cin != 2 * C:
+            raise RuntimeError(f"PointNet: in_channel={m.cin} but input has C={C} (expects in_channel == 2*C)")
+        tok = ops.patch_embed(_lib.ROWS_APF, x, None, fps_idx, knn_idx, perm, B * G, k, m.tensors(), m.meta(),
+                              _check_precision(self.encoder.precision))
+        return tok.view(B, G, -1)
+
+
+class P3Embed(nn.Module, _FoldedMixin):
+    """pix4point.py:105-191.  forward(p (B,N,3), f (B,D,N)) -> ([p, (B,N/4,3), ...], [f, (B,W0,N/4), ...]).
+    Features are kept channel-last internally; the returned feature tensors are (B,W,G) views."""
+
+    def __init__(self, in_channels: int = 3, sample_ratio: float = 0.25, scale: int = 4, k: int = 32,
+                 layers: int = 4, embed_dim: int = 256, precision: str = "fp32", **kwargs):
+        super().__init__()
+        if layers != 4:
+            raise ValueError("p3tok P3Embed supports the reference's layers=4 layout only")
+        self.sample_ratio = sample_ratio
+        self.k = k
+        self.precision = precision
+        stages = int(math.log(1 / sample_ratio, scale))
+        embed_dim = int(embed_dim // 2 ** (stages - 1))
+        self.convs = nn.ModuleList()
+        self.channel_list = [in_channels]
+        for _ in range(stages):
+            W = embed_dim
+            conv1 = nn.Sequential(nn.Conv2d(in_channels + 3, W, 1, bias=False), nn.Conv2d(W, W, 1, bias=True),
+                                  nn.BatchNorm2d(W), nn.ReLU())
+            conv2 = nn.Sequential(nn.Conv2d(2 * W, 2 * W, 1, bias=False), nn.BatchNorm2d(2 * W), nn.ReLU(),
+                                  nn.Conv2d(2 * W, W, 1, bias=False), nn.BatchNorm2d(W), nn.ReLU())
+            self.convs.append(nn.ModuleList([conv1, conv2]))
+            self.channel_list.append(W)
+            in_channels = W
+            embed_dim *= 2
+        self.out_channels = self.channel_list[-1]
+
+    def folded(self, device) -> List[fold.PatchMLP]:
+        bf16 = _check_precision(self.precision)
+        ver = tuple((t._version, t.data_ptr()) for t in list(self.parameters()) + list(self.buffers()))
+        cache = self.__dict__.setdefault("_fold_cache", {})
+        if cache.get("ver") != ver:
+            cache.clear()
+            cache["ver"] = ver
+            sd = self.state_dict()
+            cache["host"] = [fold.fold_p3embed_stage(sd, s) for s in range(len(self.convs))]
+        return [m.to(device, torch.bfloat16 if bf16 else torch.float32) for m in cache["host"]]
+
+    def forward(self, p: torch.Tensor, f: torch.Tensor, start_idx: Optional[List[torch.Tensor]] = None
+                ) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
+        self._require_eval()
+        bf16 = _check_precision(self.precision)
+        B, N = int(p.shape[0]), int(p.shape[1])
+        out_p, out_f = [p], [f]
+        pts = p.float().contiguous()
+        feat = f.float().transpose(1, 2).contiguous()            # channel-last (B,N,D)
+        for s, m in enumerate(self.folded(p.device)):
+            N = N // 4                                           # pix4point.py:174
+            G = min(N, int(pts.shape[1]))                        # clamp of farthest_point_sampling (line 23)
+            st = None if start_idx is None else start_idx[s]
+            cidx = ops.fps(pts, _start(pts, st), G)
+            ctr = ops.gather_points(pts, cidx)
+            kidx = ops.knn(pts, ctr, self.k, _lib.KNN_P4P_CDIST, True, False)[0]
+            tok = ops.patch_embed(_lib.ROWS_P4P, pts, feat, None, kidx, None, B * G, self.k, m.tensors(), m.meta(), bf16)
+            feat = tok.view(B, G, -1)
+            pts = ctr
+            out_p.append(ctr)
+            out_f.append(feat.transpose(1, 2))
+        return out_p, out_f

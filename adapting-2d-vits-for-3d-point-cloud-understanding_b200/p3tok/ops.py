@@ -1,0 +1,337 @@
+"""torch custom ops (`torch.ops.p3tok.*`) over the C ABI of libp3tok.so.
+
+Each op validates its tensors (CUDA, dtype, contiguity), allocates the outputs with torch (the
+library owns no memory), and enqueues the kernels on torch's current stream.  Shape-only "fake"
+implementations are registered so the ops trace under torch.export / FakeTensor; there is no
+autograd registration (forward / inference path; indices are not differentiable) and no
+implementation for any device but CUDA.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+_lib_handle = None
+
+
+def _L():
+    global _lib_handle
+    if _lib_handle is None:
+        _lib_handle = _lib.lib()
+    return _lib_handle
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(name: str, *tensors: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(f"p3tok::{name}: CUDA tensors only (got {t.device}); p3tok has no CPU fallback")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"p3tok::{name}: tensors on different devices ({dev} vs {t.device})")
+    return dev
+
+
+def _f32c(name: str, t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"p3tok::{name}: expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _point_stride(x: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    """Accept (B,N,C) rows with C in {3,4} in place (xyz are channels 0..2); anything else is
+    first reduced to a contiguous (B,N,3) copy like the reference's `.contiguous()` (apf.py:65)."""
+    if x.dim() != 3 or x.shape[-1] < 3:
+        raise RuntimeError(f"expected (B,N,C>=3) points, got {tuple(x.shape)}")
+    if x.is_contiguous() and x.shape[-1] in (3, 4):
+        return x, int(x.shape[-1])
+    # a [:, :, :3] view of a contiguous (B,N,4) tensor: read the parent rows in place
+    if x.shape[-1] == 3 and x.stride(-1) == 1 and x.stride(1) == 4 and x.stride(0) == 4 * x.shape[1]:
+        return x, 4
+    return x[..., :3].contiguous(), 3
+
+
+# --------------------------------------------------------------------------------------------- fps
+@torch.library.custom_op("p3tok::fps", mutates_args=(), device_types="cuda")
+def fps(x: torch.Tensor, start_idx: torch.Tensor, npoint: int) -> torch.Tensor:
+    _need_cuda("fps", x, start_idx)
+    x = x if x.dtype == torch.float32 else x.float()
+    x, stride = _point_stride(x)
+    B, N = int(x.shape[0]), int(x.shape[1])
+    start = start_idx.to(torch.int64).contiguous()
+    if start.shape != (B,):
+        raise RuntimeError(f"p3tok::fps: start_idx must have shape ({B},)")
+    out = torch.empty((B, npoint), dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_L().p3tok_fps(x.data_ptr(), B, N, stride, start.data_ptr(), npoint, out.data_ptr(), _stream()), "fps")
+    return out
+
+
+@fps.register_fake
+def _(x, start_idx, npoint):
+    return x.new_empty((x.shape[0], npoint), dtype=torch.int64)
+
+
+# ------------------------------------------------------------------------------------------- gather
+@torch.library.custom_op("p3tok::gather_points", mutates_args=(), device_types="cuda")
+def gather_points(x: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    _need_cuda("gather_points", x, idx)
+    x = _f32c("gather_points", x)
+    B, N, C = (int(v) for v in x.shape)
+    flat = idx.to(torch.int64).reshape(B, -1).contiguous()
+    S = int(flat.shape[1])
+    out = torch.empty((B, S, C), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_L().p3tok_gather_points(x.data_ptr(), B, N, C, flat.data_ptr(), S, out.data_ptr(), _stream()),
+              "gather_points")
+    return out.view(*idx.shape, C)
+
+
+@gather_points.register_fake
+def _(x, idx):
+    return x.new_empty((*idx.shape, x.shape[-1]))
+
+
+# --------------------------------------------------------------------------------------------- knn
+@torch.library.custom_op("p3tok::knn", mutates_args=(), device_types="cuda")
+def knn(x: torch.Tensor, centres: torch.Tensor, k: int, mode: int, int32_out: bool,
+        return_dist: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    _need_cuda("knn", x, centres)
+    x = x if x.dtype == torch.float32 else x.float()
+    x, stride = _point_stride(x)
+    c = _f32c("knn", centres[..., :3])
+    B, N = int(x.shape[0]), int(x.shape[1])
+    if c.dim() != 3 or c.shape[0] != B:
+        raise RuntimeError("p3tok::knn: centres must be (B,G,3)")
+    G = int(c.shape[1])
+    if k > N:
+        # same failure the reference hits in torch.topk (sampler.py:74)
+        raise RuntimeError(f"p3tok::knn: selected index k out of range (k={k} > N={N})")
+    idx = torch.empty((B, G, k), dtype=torch.int32 if int32_out else torch.int64, device=x.device)
+    dist = torch.empty((B, G, k) if return_dist else (0,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_L().p3tok_knn(x.data_ptr(), B, N, stride, c.data_ptr(), G, k, mode, idx.data_ptr(),
+                             _lib.I32 if int32_out else _lib.I64, dist.data_ptr() if return_dist else None,
+                             _stream()), "knn")
+    return idx, dist
+
+
+@knn.register_fake
+def _(x, centres, k, mode, int32_out, return_dist):
+    B, G = x.shape[0], centres.shape[1]
+    return (x.new_empty((B, G, k), dtype=torch.int32 if int32_out else torch.int64),
+            x.new_empty((B, G, k) if return_dist else (0,), dtype=torch.float32))
+
+
+# ------------------------------------------------------------------------------------------ morton
+@torch.library.custom_op("p3tok::morton_order", mutates_args=(), device_types="cuda")
+def morton_order(centres: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    _need_cuda("morton_order", centres)
+    c = _f32c("morton_order", centres)
+    B, G = int(c.shape[0]), int(c.shape[1])
+    perm = torch.empty((B, G), dtype=torch.int64, device=c.device)
+    codes = torch.empty((B, G), dtype=torch.int64, device=c.device)
+    with torch.cuda.device(c.device):
+        check(_L().p3tok_morton_order(c.data_ptr(), B, G, perm.data_ptr(), codes.data_ptr(), _stream()), "morton_order")
+    return perm, codes
+
+
+@morton_order.register_fake
+def _(centres):
+    s = (centres.shape[0], centres.shape[1])
+    return centres.new_empty(s, dtype=torch.int64), centres.new_empty(s, dtype=torch.int64)
+
+
+# --------------------------------------------------------------------------------------- apf group
+@torch.library.custom_op("p3tok::apf_group", mutates_args=(), device_types="cuda")
+def apf_group(x: torch.Tensor, fps_idx: torch.Tensor, knn_idx: torch.Tensor,
+              perm: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+    _need_cuda("apf_group", x, fps_idx, knn_idx, perm)
+    x = _f32c("apf_group", x)
+    B, N, C = (int(v) for v in x.shape)
+    G, k = int(knn_idx.shape[1]), int(knn_idx.shape[2])
+    f = fps_idx.to(torch.int64).contiguous()
+    kn = knn_idx.to(torch.int64).contiguous()
+    pm = perm.to(torch.int64).contiguous() if perm is not None else None
+    neigh = torch.empty((B, G, k, 2 * C), dtype=torch.float32, device=x.device)
+    center = torch.empty((B, G, 3), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_L().p3tok_apf_group(x.data_ptr(), B, N, C, f.data_ptr(), kn.data_ptr(), _ptr(pm), G, k,
+                                   neigh.data_ptr(), center.data_ptr(), _stream()), "apf_group")
+    return neigh, center
+
+
+@apf_group.register_fake
+def _(x, fps_idx, knn_idx, perm):
+    B, G, k = knn_idx.shape
+    return x.new_empty((B, G, k, 2 * x.shape[-1])), x.new_empty((B, G, 3))
+
+
+# ------------------------------------------------------------------------------------ group gather
+@torch.library.custom_op("p3tok::group_gather", mutates_args=(), device_types="cuda")
+def group_gather(pnts: torch.Tensor, feats: torch.Tensor, idx: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    _need_cuda("group_gather", pnts, feats, idx)
+    p = _f32c("group_gather", pnts)
+    f = _f32c("group_gather", feats)
+    B, N, _ = (int(v) for v in p.shape)
+    D = int(f.shape[-1])
+    G, k = int(idx.shape[1]), int(idx.shape[2])
+    i32 = idx.to(torch.int32).contiguous()
+    gp = torch.empty((B, G, k, 3), dtype=torch.float32, device=p.device)
+    gf = torch.empty((B, G, k, D), dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        check(_L().p3tok_group_gather(p.data_ptr(), f.data_ptr(), B, N, D, i32.data_ptr(), G, k, gp.data_ptr(),
+                                      gf.data_ptr(), _stream()), "group_gather")
+    return gp, gf
+
+
+@group_gather.register_fake
+def _(pnts, feats, idx):
+    B, G, k = idx.shape
+    return pnts.new_empty((B, G, k, 3)), pnts.new_empty((B, G, k, feats.shape[-1]))
+
+
+# ------------------------------------------------------------------------------------- patch embed
+def _mlp_struct(weights: Sequence[torch.Tensor], meta: Sequence[int], wdtype: int) -> _lib.MlpStruct:
+    m = _lib.MlpStruct()
+    cin, n_pre = int(meta[0]), int(meta[1])
+    m.cin, m.n_pre = cin, n_pre
+    dims = [int(v) for v in meta[2:2 + n_pre]]
+    relu = [int(v) for v in meta[2 + n_pre:2 + 2 * n_pre]]
+    m.mid_dim, m.out_dim, m.out_relu = (int(v) for v in meta[2 + 2 * n_pre:5 + 2 * n_pre])
+    m.wdtype = wdtype
+    want = torch.float32 if wdtype == _lib.F32 else torch.bfloat16
+    kin = cin
+    for i in range(n_pre):
+        w, b = weights[2 * i], weights[2 * i + 1]
+        if w.dtype != want or tuple(w.shape) != (dims[i], kin) or not w.is_contiguous():
+            raise RuntimeError(f"p3tok::patch_embed: layer {i} weight must be contiguous {want} ({dims[i]},{kin})")
+        if b.dtype != torch.float32 or tuple(b.shape) != (dims[i],):
+            raise RuntimeError(f"p3tok::patch_embed: layer {i} bias must be float32 ({dims[i]},)")
+        m.pre_dim[i], m.pre_relu[i] = dims[i], relu[i]
+        m.w_pre[i], m.b_pre[i] = w.data_ptr(), b.data_ptr()
+        kin = dims[i]
+    wg, wf, bm, wo, bo = weights[2 * n_pre:2 * n_pre + 5]
+    for t, shp, dt, nm in ((wg, (m.mid_dim, kin), want, "w_mid_g"), (wf, (m.mid_dim, kin), want, "w_mid_f"),
+                           (bm, (m.mid_dim,), torch.float32, "b_mid"), (wo, (m.out_dim, m.mid_dim), want, "w_out"),
+                           (bo, (m.out_dim,), torch.float32, "b_out")):
+        if t.dtype != dt or tuple(t.shape) != shp or not t.is_contiguous():
+            raise RuntimeError(f"p3tok::patch_embed: {nm} must be contiguous {dt} {shp}, got {t.dtype} {tuple(t.shape)}")
+    m.w_mid_g, m.w_mid_f, m.b_mid, m.w_out, m.b_out = (t.data_ptr() for t in (wg, wf, bm, wo, bo))
+    return m
+
+
+@torch.library.custom_op("p3tok::patch_embed", mutates_args=(), device_types="cuda")
+def patch_embed(kind: int, x: torch.Tensor, feats: Optional[torch.Tensor], ctr_idx: Optional[torch.Tensor],
+                knn_idx: Optional[torch.Tensor], perm: Optional[torch.Tensor], ngroups: int, k: int,
+                weights: Sequence[torch.Tensor], meta: Sequence[int], bf16: bool) -> torch.Tensor:
+    """kind 0: APF rows from x (B,N,C) + ctr_idx (B,G) + knn_idx (B,G,k) [+ perm];
+    kind 1: P4P rows from x=pnts (B,N,3) + feats (B,N,D) + knn_idx (B,G,k);
+    kind 2: x is the row matrix (ngroups*k, cin).  Returns tokens (ngroups, out_dim) float32."""
+    _need_cuda("patch_embed", x, feats, ctr_idx, knn_idx, perm, *weights)
+    x = _f32c("patch_embed", x)
+    prec = _lib.BF16 if bf16 else _lib.F32
+    m = _mlp_struct(weights, meta, prec)
+    r = _lib.RowsStruct()
+    r.kind = kind
+    keep = [x]
+    if kind == _lib.ROWS_DIRECT:
+        if x.dim() != 2 or x.shape[0] != ngroups * k or x.shape[1] != m.cin:
+            raise RuntimeError(f"p3tok::patch_embed: rows must be ({ngroups * k},{m.cin}), got {tuple(x.shape)}")
+        r.B, r.G, r.N, r.k, r.C, r.D = 1, ngroups, 0, k, 0, 0
+    else:
+        B, N, C = (int(v) for v in x.shape)
+        kn = knn_idx if knn_idx.dtype in (torch.int32, torch.int64) else knn_idx.to(torch.int64)
+        kn = kn.contiguous()
+        G = int(kn.shape[1])
+        if B * G != ngroups or int(kn.shape[2]) != k:
+            raise RuntimeError("p3tok::patch_embed: knn_idx shape does not match ngroups/k")
+        r.B, r.G, r.N, r.k, r.C = B, G, N, k, C
+        r.idx_dtype = _lib.I32 if kn.dtype == torch.int32 else _lib.I64
+        r.knn_idx = kn.data_ptr()
+        keep.append(kn)
+        if kind == _lib.ROWS_APF:
+            ci = ctr_idx.to(torch.int64).contiguous()
+            r.ctr_idx = ci.data_ptr()
+            keep.append(ci)
+            if perm is not None:
+                pm = perm.to(torch.int64).contiguous()
+                r.perm = pm.data_ptr()
+                keep.append(pm)
+        else:
+            f = _f32c("patch_embed", feats)
+            r.D = int(f.shape[-1])
+            r.feats = f.data_ptr()
+            keep.append(f)
+    r.x = x.data_ptr()
+    L = _L()
+    ws_bytes = L.p3tok_patch_embed_workspace_bytes(ctypes.byref(m), ngroups, k, prec)
+    if ws_bytes < 0:
+        raise RuntimeError("p3tok::patch_embed: bad descriptor")
+    ws = torch.empty((max(int(ws_bytes), 256),), dtype=torch.uint8, device=x.device)
+    tokens = torch.empty((ngroups, m.out_dim), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(L.p3tok_patch_embed(ctypes.byref(r), ctypes.byref(m), prec, ws.data_ptr(), int(ws.numel()),
+                                  tokens.data_ptr(), _stream()), "patch_embed")
+    del keep
+    return tokens
+
+
+@patch_embed.register_fake
+def _(kind, x, feats, ctr_idx, knn_idx, perm, ngroups, k, weights, meta, bf16):
+    n_pre = meta[1]
+    return x.new_empty((ngroups, meta[3 + 2 * n_pre]))
+
+
+# ------------------------------------------------------------------------------ exported building blocks
+@torch.library.custom_op("p3tok::linear_f32", mutates_args=(), device_types="cuda")
+def linear_f32(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], relu: bool) -> torch.Tensor:
+    _need_cuda("linear_f32", a, w, bias)
+    a2 = _f32c("linear_f32", a).reshape(-1, a.shape[-1])
+    w = _f32c("linear_f32", w)
+    b = _f32c("linear_f32", bias) if bias is not None else None
+    M, K = (int(v) for v in a2.shape)
+    N = int(w.shape[0])
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(_L().p3tok_linear_f32(a2.data_ptr(), M, K, w.data_ptr(), N, _ptr(b), None, 1, int(relu), out.data_ptr(),
+                                    _stream()), "linear_f32")
+    return out.view(*a.shape[:-1], N)
+
+
+@linear_f32.register_fake
+def _(a, w, bias, relu):
+    return a.new_empty((*a.shape[:-1], w.shape[0]))
+
+
+@torch.library.custom_op("p3tok::group_max", mutates_args=(), device_types="cuda")
+def group_max(x: torch.Tensor, k: int) -> torch.Tensor:
+    _need_cuda("group_max", x)
+    x = _f32c("group_max", x)
+    C = int(x.shape[-1])
+    ng = x.numel() // (C * k)
+    out = torch.empty((ng, C), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_L().p3tok_group_max(x.data_ptr(), ng, k, C, out.data_ptr(), _stream()), "group_max")
+    return out
+
+
+@group_max.register_fake
+def _(x, k):
+    return x.new_empty((x.numel() // (x.shape[-1] * k), x.shape[-1]))

@@ -1,0 +1,175 @@
+/*
+ * p3tok.h - C ABI of the B200-native point-patch tokenizer (libp3tok.so).
+ *
+ * The reference (Irish-77/adapting-2D-ViTs-for-3D-point-cloud-understanding) has no FFI layer:
+ * its boundary is plain Python callables.  Every entry point below names the
+ * reference callable it replaces (path:line relative to the reference tree); the Python side
+ * (p3tok/ops.py) binds these with ctypes and registers them as torch custom ops.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless said otherwise;
+ *   - the caller owns every buffer (inputs, outputs, workspace); the library allocates nothing
+ *     persistent and keeps no state besides per-process kernel attributes;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); the library never
+ *     synchronises the device;
+ *   - return value: P3TOK_OK or an error code; p3tok_last_error() (thread-local, host string)
+ *     describes the last failure of the calling thread;
+ *   - outputs are fully overwritten; row-major contiguous layouts as written in each comment.
+ */
+#ifndef P3TOK_H_
+#define P3TOK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P3TOK_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define P3TOK_API __attribute__((visibility("default")))
+#else
+#define P3TOK_API
+#endif
+
+enum p3tok_status {
+  P3TOK_OK = 0,
+  P3TOK_ERR_INVALID = 1,     /* bad shape / null pointer / index out of contract */
+  P3TOK_ERR_UNSUPPORTED = 2, /* valid request outside the implemented envelope (k, N, alignment) */
+  P3TOK_ERR_CUDA = 3,        /* a CUDA call or launch failed; see p3tok_last_error() */
+  P3TOK_ERR_WORKSPACE = 4    /* workspace too small; see the matching *_workspace_bytes() */
+};
+
+/* kNN distance flavour */
+enum p3tok_knn_mode {
+  P3TOK_KNN_APF_SQ = 0,   /* src/data/sampler.py:47-62  ((-2*dot)+|c|^2)+|p|^2, K=3 FMA chain */
+  P3TOK_KNN_P4P_CDIST = 1 /* src/models/pix4point.py:87  cdist mm path: K=5 FMA chain, clamp, sqrt */
+};
+
+enum p3tok_dtype { P3TOK_F32 = 0, P3TOK_BF16 = 1, P3TOK_I32 = 2, P3TOK_I64 = 3 };
+
+P3TOK_API int p3tok_abi_version(void);
+P3TOK_API const char* p3tok_last_error(void);
+
+/* ---- a1/a2: farthest point sampling ----------------------------------------------------------
+ * Replaces furthest_point_sample (src/data/sampler.py:4-30) and farthest_point_sampling
+ * (src/models/pix4point.py:8-53; its min(n_samples,N) clamp is applied by the Python wrapper).
+ * x: B clouds x N points, point p of cloud b at x[(b*N+p)*pt_stride + 0..2] (pt_stride >= 3, so
+ * an (B,N,4) xyz+height tensor is read in place, no .contiguous() copy).
+ * start_idx: (B) int64, first pick per cloud (the reference draws torch.randint, sampler.py:20).
+ * out_idx: (B,G) int64.  dist = ((dx*dx)+(dy*dy))+(dz*dz) unfused; argmax keeps the lowest index.
+ * N <= 131072.  G > N repeats index 0 once the cloud is exhausted, like the reference. */
+P3TOK_API int p3tok_fps(const float* x, int64_t B, int64_t N, int64_t pt_stride, const int64_t* start_idx,
+              int64_t G, int64_t* out_idx, void* stream);
+
+/* ---- a5: index_points (src/data/sampler.py:77-94) / torch.gather of centres (pix4point.py:176)
+ * x (B,N,C) f32, idx (B,S) int64 -> out (B,S,C).  S may be G or G*k. */
+P3TOK_API int p3tok_gather_points(const float* x, int64_t B, int64_t N, int64_t C, const int64_t* idx,
+                        int64_t S, float* out, void* stream);
+
+/* ---- a3/a4: kNN query -----------------------------------------------------------------------
+ * Replaces _square_distance + knn_point (src/data/sampler.py:47-75) and the cdist+topk inside
+ * group_knn (src/models/pix4point.py:79-89).  centres: (B,G,3) contiguous query points.
+ * idx_out: (B,G,k) of idx_dtype (P3TOK_I64 for the APF flavour, P3TOK_I32 for Pix4Point's
+ * `.int()`), ascending by (distance, index) - the canonical instance of torch.topk's
+ * implementation-defined tie order.  dist_out: optional (B,G,k) f32 distances (may be NULL).
+ * 1 <= k <= 128, k <= N. */
+P3TOK_API int p3tok_knn(const float* x, int64_t B, int64_t N, int64_t pt_stride, const float* centres,
+              int64_t G, int64_t k, int mode, void* idx_out, int idx_dtype, float* dist_out,
+              void* stream);
+
+/* ---- a7: Morton order of the centres (src/models/apf_utils.py:66-104, resolution 1024) -------
+ * centres (B,G,3) -> perm (B,G) int64 = stable ascending argsort of the 30-bit Z-order code;
+ * codes_out optional (B,G) int64.  G <= 8192. */
+P3TOK_API int p3tok_morton_order(const float* centres, int64_t B, int64_t G, int64_t* perm,
+                       int64_t* codes_out, void* stream);
+
+/* ---- a6: Group.forward materialised (src/models/apf.py:52-112) --------------------------------
+ * x (B,N,C) f32 contiguous; fps_idx (B,G) i64; knn_idx (B,G,k) i64; perm (B,G) i64 or NULL.
+ * neigh (B,G,k,2C) = [x[nbr]-x[centre] || x[centre]], center (B,G,3) = xyz of the centre, both
+ * in the permuted group order (output group j = input group perm[b,j]). */
+P3TOK_API int p3tok_apf_group(const float* x, int64_t B, int64_t N, int64_t C, const int64_t* fps_idx,
+                    const int64_t* knn_idx, const int64_t* perm, int64_t G, int64_t k,
+                    float* neigh, float* center, void* stream);
+
+/* ---- a4 (gather half of group_knn, src/models/pix4point.py:92-102) ---------------------------
+ * pnts (B,N,3), feats (B,N,D) channel-last, idx (B,G,k) int32 -> grouped_pnts (B,G,k,3),
+ * grouped_feats (B,G,k,D).  Absolute coordinates: Pix4Point does not centre-normalise. */
+P3TOK_API int p3tok_group_gather(const float* pnts, const float* feats, int64_t B, int64_t N, int64_t D,
+                       const int32_t* idx, int64_t G, int64_t k, float* grouped_pnts,
+                       float* grouped_feats, void* stream);
+
+/* ---- a8/a10: mini-PointNet patch embedding ---------------------------------------------------
+ * One descriptor covers both model families (eval-mode BatchNorm already folded into the
+ * weights by the host, p3tok/fold.py):
+ *   rows X (ngroups*k, cin)
+ *   -> n_pre per-point layers  h = act(W_i h + b_i)           (APF: 3, P3Embed: 1 [conv1 folded])
+ *   -> g = max over the k rows of a group                     (apf.py:160 / pix4point.py:185)
+ *   -> h = relu(W_mid_g g + W_mid_f h + b_mid)                (concat layer split, apf.py:162-163)
+ *   -> o = act_out(W_out h + b_out);  token = max over k      (apf.py:167 / pix4point.py:188)
+ * Matrices are row-major [out, in] in `wdtype` (P3TOK_F32 for the fp32 path, P3TOK_BF16 for the
+ * tcgen05 path); biases are always f32. */
+typedef struct p3tok_mlp {
+  int32_t cin;
+  int32_t n_pre;
+  int32_t pre_dim[4];
+  int32_t pre_relu[4];
+  int32_t mid_dim;
+  int32_t out_dim;
+  int32_t out_relu;
+  int32_t wdtype;
+  const void* w_pre[4];
+  const float* b_pre[4];
+  const void* w_mid_g;
+  const void* w_mid_f;
+  const float* b_mid;
+  const void* w_out;
+  const float* b_out;
+} p3tok_mlp;
+
+/* Where the rows come from (fused gather, no (B,G,k,2C) tensor in HBM):
+ *   kind 0 (APF):  row = [x[b,nbr,:C]-x[b,ctr,:C] || x[b,ctr,:C]]  (cin = 2C), groups emitted in
+ *                  `perm` order when perm != NULL (Morton order as the OUTPUT row, apf.py:99-110)
+ *   kind 1 (P4P):  row = [pnts[b,nbr,:3] || feats[b,nbr,:D]]        (cin = 3+D)
+ *   kind 2 (rows): X given directly as (ngroups*k, cin) f32 in `x` (Encoder.forward on a
+ *                  materialised (B,G,k,2C) tensor, apf.py:171-181) */
+typedef struct p3tok_rows {
+  int32_t kind;
+  int32_t C;              /* channels of x (APF: 3 or 4; P4P: 3) */
+  int32_t D;              /* feature channels (P4P) */
+  int32_t idx_dtype;      /* dtype of knn_idx: P3TOK_I64 or P3TOK_I32 */
+  int64_t B, N, G, k;
+  const float* x;         /* (B,N,C) or rows */
+  const float* feats;     /* (B,N,D) channel-last, P4P only */
+  const int64_t* ctr_idx; /* (B,G) APF only */
+  const void* knn_idx;    /* (B,G,k) */
+  const int64_t* perm;    /* (B,G) or NULL */
+} p3tok_rows;
+
+/* Workspace size in bytes for p3tok_patch_embed with these shapes (host computation only). */
+P3TOK_API int64_t p3tok_patch_embed_workspace_bytes(const p3tok_mlp* mlp, int64_t ngroups, int64_t k,
+                                          int precision);
+
+/* Replaces Encoder.forward (src/models/apf.py:145-181) and the conv/pool half of one
+ * P3Embed.forward iteration (src/models/pix4point.py:179-188).
+ * precision: P3TOK_F32 (CUDA-core FFMA, fp32 accumulate; rtol 1e-4 contract) or P3TOK_BF16
+ * (tcgen05 tensor cores, bf16 operands, fp32 accumulate in TMEM; rtol 1e-2 contract).
+ * tokens: (B*G, out_dim) f32, group order as described in p3tok_rows. */
+P3TOK_API int p3tok_patch_embed(const p3tok_rows* rows, const p3tok_mlp* mlp, int precision, void* workspace,
+                      int64_t workspace_bytes, float* tokens, void* stream);
+
+/* ---- building blocks exported for tests and for the "next" rows (pix4point.py:245 proj) -------
+ * C[M,N] = act(A[M,K] W[N,K]^T + bias[N] + gbias[m / rows_per_group, N]) in fp32 on CUDA cores.
+ * gbias may be NULL. */
+P3TOK_API int p3tok_linear_f32(const float* A, int64_t M, int64_t K, const float* W, int64_t N,
+                     const float* bias, const float* gbias, int64_t rows_per_group, int relu,
+                     float* C, void* stream);
+
+/* out[g, c] = max over r < k of in[(g*k + r), c]   (torch.max(..., dim=k-axis)) */
+P3TOK_API int p3tok_group_max(const float* in, int64_t ngroups, int64_t k, int64_t C, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P3TOK_H_ */

@@ -1,0 +1,152 @@
+"""GPU parity of the index kernels (FPS, kNN, Morton, grouping) through the C ABI: bit-exact against
+the oracle on seeded inputs, against the committed reference outputs (tests/golden), and through
+size-independent properties at BASELINE.json's full sizes."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from helpers import dev, to_dev
+from oracle import oracle
+from p3tok import _lib, ops, synth
+from p3tok import functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _golden(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+@pytest.mark.parametrize("name", list(cases.INDEX_CASES))
+def test_golden_index_cases(golden_dir, name):
+    c, g = cases.INDEX_CASES[name], _golden(golden_dir, name)
+    x = synth.make_cloud(c["kind"], c["B"], c["N"], c["seed"], 3)
+    st = synth.start_indices(c["B"], c["N"], c["seed"])
+    xt = to_dev(x)
+    f1 = F.furthest_point_sample(xt, c["G"], to_dev(st))
+    f2 = F.farthest_point_sampling(xt, c["G"], to_dev(st))
+    assert f1.dtype == torch.int64 and torch.equal(f1, f2)
+    assert np.array_equal(f1.cpu().numpy(), g["fps_idx"])                 # == the reference, bit-exact
+    ctr = F.index_points(xt, f1)
+    assert np.array_equal(ctr.cpu().numpy(), oracle.gather_points(x, g["fps_idx"].astype(np.int64)))
+    for mode, key, ulp, fn in ((oracle.KNN_APF_SQ, "knn_apf", 0, lambda: F.knn_point(c["k"], xt, ctr)),
+                               (oracle.KNN_P4P_CDIST, "knn_p4p", 1, lambda: F.knn_query(xt, ctr, c["k"]))):
+        mine = fn().cpu().numpy().astype(np.int64)
+        D = oracle.pair_dist(x, ctr.cpu().numpy(), mode)
+        assert np.array_equal(mine, oracle.knn(x, ctr.cpu().numpy(), c["k"], mode))      # canonical, bit-exact
+        ok, msg = oracle.knn_tie_equivalent(mine, g[key].astype(np.int64), D, ulp)       # vs the reference
+        assert ok, msg
+    perm = F.morton_order(ctr).cpu().numpy()
+    codes, operm = oracle.morton(ctr.cpu().numpy())
+    assert np.array_equal(perm, operm)
+    assert np.array_equal(np.take_along_axis(codes, perm, 1), np.take_along_axis(codes, g["morton_perm"].astype(np.int64), 1))
+
+
+@pytest.mark.parametrize("B,N,G,C,kind", [
+    (3, 1, 1, 3, "uniform"), (2, 31, 31, 3, "uniform"), (5, 100, 40, 3, "clustered"), (2, 257, 64, 4, "uniform"),
+    (4, 1024, 256, 3, "uniform"), (3, 2048, 128, 4, "clustered"), (2, 2050, 33, 3, "duplicates"),
+    (2, 8192, 96, 3, "uniform"), (2, 8193, 50, 3, "uniform"), (1, 20000, 40, 4, "clustered"),
+    (2, 65536, 24, 3, "uniform"), (1, 70001, 16, 3, "uniform"), (1, 131072, 8, 3, "uniform"),
+])
+def test_fps_matches_oracle(B, N, G, C, kind):
+    x = synth.make_cloud(kind, B, N, 100 + N % 97, C)
+    st = synth.start_indices(B, N, 5)
+    got = ops.fps(to_dev(x), to_dev(st), G).cpu().numpy()
+    assert np.array_equal(got, oracle.fps(x, st, G))
+
+
+def test_fps_edge_cases():
+    # exhausted cloud (G > N) repeats index 0; identical points tie -> lowest index; xyz view of (B,N,4)
+    x = synth.make_cloud("uniform", 2, 8, 1)
+    got = ops.fps(to_dev(x), to_dev(np.array([3, 7])), 12).cpu().numpy()
+    assert np.array_equal(got, oracle.fps(x, np.array([3, 7]), 12)) and (got[:, 8:] == 0).all()
+    z = np.zeros((1, 64, 3), np.float32)
+    assert ops.fps(to_dev(z), to_dev(np.array([9])), 5).cpu().numpy().tolist() == [[9, 0, 0, 0, 0]]
+    x4 = to_dev(synth.make_cloud("uniform", 2, 300, 2, 4))
+    st = to_dev(np.array([0, 299]))
+    assert torch.equal(ops.fps(x4[:, :, :3], st, 20), ops.fps(x4[:, :, :3].contiguous(), st, 20))
+    assert ops.fps(x4[:0], st[:0], 4).shape == (0, 4)
+    # fps(): gathers all channels (sampler.py:33-45)
+    d = F.fps(x4, 16, st)
+    assert d.shape == (2, 16, 4)
+
+
+@pytest.mark.parametrize("mode", [oracle.KNN_APF_SQ, oracle.KNN_P4P_CDIST])
+@pytest.mark.parametrize("B,N,G,k,kind", [
+    (2, 40, 7, 1, "uniform"), (2, 100, 33, 8, "uniform"), (3, 257, 20, 16, "clustered"), (2, 512, 64, 32, "duplicates"),
+    (1, 1000, 100, 33, "uniform"), (2, 2048, 128, 32, "uniform"), (1, 2100, 40, 64, "clustered"),
+    (1, 4096, 10, 100, "uniform"), (1, 5000, 5, 128, "duplicates"), (1, 128, 128, 128, "uniform"),
+])
+def test_knn_matches_oracle(mode, B, N, G, k, kind):
+    x = synth.make_cloud(kind, B, N, 7 + k, 3)
+    ctr = np.ascontiguousarray(x[:, :G] if kind != "clustered" else synth.make_cloud("uniform", B, G, 9, 3))
+    idx, dist = ops.knn(to_dev(x), to_dev(ctr), k, mode, mode == oracle.KNN_P4P_CDIST, True)
+    oi, od = oracle.knn(x, ctr, k, mode, return_dist=True)
+    assert idx.dtype == (torch.int32 if mode == oracle.KNN_P4P_CDIST else torch.int64)
+    assert np.array_equal(idx.cpu().numpy().astype(np.int64), oi)
+    assert np.array_equal(dist.cpu().numpy(), od)
+
+
+def test_knn_errors_and_strided_input():
+    x = to_dev(synth.make_cloud("uniform", 1, 16, 1, 4))
+    with pytest.raises(RuntimeError):
+        F.knn_point(17, x[..., :3], x[:, :2, :3])          # k > N, like torch.topk in the reference
+    a = F.knn_point(4, x[..., :3], x[:, :5, :3])
+    b = F.knn_point(4, x[..., :3].contiguous(), x[:, :5, :3].contiguous())
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name", list(cases.APF_CASES))
+def test_group_forward_matches_oracle_and_reference(golden_dir, name):
+    from p3tok.modules import Group
+    c, g = cases.APF_CASES[name], _golden(golden_dir, name)
+    x = synth.make_cloud(c["kind"], c["B"], c["N"], c["seed"], c["C"])
+    st = synth.start_indices(c["B"], c["N"], c["seed"])
+    xt = to_dev(x)
+    grp = Group(c["G"], c["k"])
+    neigh, center = grp(xt, xt[:, :, :3], to_dev(st))
+    o = oracle.group_apf(x, st, c["G"], c["k"])
+    assert np.array_equal(neigh.cpu().numpy(), o["neigh"]) and np.array_equal(center.cpu().numpy(), o["center"])
+    assert np.array_equal(center.cpu().numpy(), g["center"])              # reference's Morton-ordered centres
+    fidx, _, kidx, perm = grp.indices(xt, to_dev(st))
+    assert np.array_equal(fidx.cpu().numpy(), g["fps_idx"])
+
+
+def test_group_knn_gather_matches_oracle():
+    B, N, G, k, D = 2, 300, 20, 8, 5
+    p = synth.make_cloud("uniform", B, N, 3)
+    f = synth.uniform01(4, B * N * D).reshape(B, N, D)
+    ctr = np.ascontiguousarray(p[:, :G])
+    gp, gf = F.group_knn(to_dev(p), to_dev(ctr), to_dev(f), k)
+    idx = oracle.knn(p, ctr, k, oracle.KNN_P4P_CDIST)
+    assert np.array_equal(gp.cpu().numpy(), oracle.gather_points(p, idx))
+    assert np.array_equal(gf.cpu().numpy(), oracle.gather_points(f, idx))
+
+
+def test_full_size_properties_c2_and_c4():
+    """BASELINE configs 2 and 4 (index half) through properties that do not need the oracle."""
+    for (B, N, G, k, kind) in ((128, 2048, 128, 32, "uniform"), (2, 65536, 2048, 64, "clustered")):
+        x = synth.make_cloud(kind, B, N, 1234, 3)
+        xt = to_dev(x)
+        st = to_dev(synth.start_indices(B, N, 1234))
+        idx = ops.fps(xt, st, G)
+        assert torch.equal(idx[:, 0], st)
+        assert all(len(set(r.tolist())) == G for r in idx.cpu().numpy())          # distinct picks
+        assert torch.equal(idx, ops.fps(xt, st, G))                               # deterministic
+        # prefix property: FPS with fewer centres is a prefix of FPS with more
+        assert torch.equal(idx[:, : G // 2], ops.fps(xt, st, G // 2))
+        ctr = ops.gather_points(xt, idx)
+        nn_idx, dist = ops.knn(xt, ctr, k, _lib.KNN_APF_SQ, False, True)
+        assert bool((dist[..., 1:] >= dist[..., :-1]).all())                      # sortedness
+        assert bool((nn_idx == idx.unsqueeze(-1)).any(-1).all())                  # a group contains its centre
+        assert bool(((nn_idx >= 0) & (nn_idx < N)).all())
+        s = nn_idx.sort(-1)[0]
+        assert bool((s[..., 1:] != s[..., :-1]).all())                            # no repeated neighbour
+        # spot-check 4 clouds' worth of centres against the oracle at full size
+        sub = slice(0, 1)
+        assert np.array_equal(nn_idx[sub, :64].cpu().numpy(),
+                              oracle.knn(x[sub], ctr[sub, :64].cpu().numpy(), k, oracle.KNN_APF_SQ))
+        assert np.array_equal(idx[sub].cpu().numpy(), oracle.fps(x[sub], st[sub].cpu().numpy(), G))

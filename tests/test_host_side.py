@@ -1,0 +1,112 @@
+"""CPU-only checks of the host side: C-ABI library loads and exports what include/p3tok.h declares,
+struct layouts, weight folding algebra, module state_dict compatibility, error behaviour."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import folded_forward
+from oracle import oracle, ref_loader
+from p3tok import _build, _lib, fold, synth
+from p3tok.modules import Encoder, Group, P3Embed, PointNet
+
+
+@pytest.fixture(scope="module")
+def built():
+    return _build.build_library()
+
+
+def test_library_exports_every_declared_symbol(built):
+    L = ctypes.CDLL(built)
+    names = _lib.declared_symbols()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(L, n), n
+    assert sorted(_lib._SIGNATURES) == names      # the Python binding covers the whole header
+    L.p3tok_abi_version.restype = ctypes.c_int
+    assert L.p3tok_abi_version() == 1             # host-only call, no GPU needed
+
+
+def test_struct_layouts_match_header(tmp_path, built):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "p3tok.h"\nint main(){printf("%zu %zu %zu %zu\\n",'
+                   'sizeof(p3tok_mlp),sizeof(p3tok_rows),offsetof(p3tok_mlp,w_pre),offsetof(p3tok_rows,x));return 0;}')
+    exe = tmp_path / "sz"
+    inc = os.path.join(os.path.dirname(_lib.HEADER_PATH))
+    subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True)
+    a, b, c, d = (int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split())
+    assert ctypes.sizeof(_lib.MlpStruct) == a and ctypes.sizeof(_lib.RowsStruct) == b
+    assert _lib.MlpStruct.w_pre.offset == c and _lib.RowsStruct.x.offset == d
+
+
+def test_fold_apf_matches_oracle():
+    sd = synth.apf_encoder_state(40, 6, 3)
+    x = synth.make_cloud("uniform", 2, 96, 3)
+    grp = oracle.group_apf(x, np.zeros(2, np.int64), 6, 8)
+    ref = oracle.apf_encoder(sd, grp["neigh"])
+    m = fold.fold_apf_encoder(synth.to_torch_state(sd))
+    got = folded_forward(m, torch.from_numpy(grp["neigh"]).reshape(-1, 6), 8).numpy().reshape(ref.shape)
+    assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()   # fp32-rounded folded weights
+    assert m.meta() == [6, 3, 256, 512, 40, 1, 1, 0, 80, 40, 0]
+
+
+def test_fold_p3embed_matches_oracle():
+    sd = synth.p3embed_state(3, 1 / 16, 4, 4, 64, 4)
+    pts = synth.make_cloud("uniform", 2, 128, 4)
+    ctr, ref, fidx, kidx = oracle.p3embed_stage(sd, 0, pts, pts, np.zeros(2, np.int64), 8)
+    m = fold.fold_p3embed_stage(synth.to_torch_state(sd), 0)
+    rows = np.concatenate([oracle.gather_points(pts, kidx), oracle.gather_points(pts, kidx)], -1).reshape(-1, 6)
+    got = folded_forward(m, torch.from_numpy(rows), 8).numpy().reshape(ref.shape)
+    assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+    assert m.out_relu == 1 and m.pre_dims == [32]
+
+
+def test_state_dict_keys_match_reference_layout():
+    keys = set(PointNet(64, 8, 4, 6).state_dict())
+    assert keys == {"encoder." + k for k in synth.apf_encoder_state(64, 6)}
+    assert set(P3Embed(sample_ratio=1 / 16, embed_dim=64).state_dict()) == set(synth.p3embed_state(3, 1 / 16, 4, 4, 64))
+    e = P3Embed()
+    assert e.out_channels == 256 and e.channel_list == [3, 256] and len(e.convs) == 1
+    e2 = P3Embed(sample_ratio=1 / 16)
+    assert e2.channel_list == [3, 128, 256]
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+def test_state_dict_loads_from_reference_modules():
+    ref = ref_loader.load()
+    r = ref.PointNet(48, 8, 4, 8)
+    mine = PointNet(48, 8, 4, 8)
+    mine.load_state_dict(r.state_dict(), strict=True)
+    r2 = ref.P3Embed(sample_ratio=1 / 16, k=8, embed_dim=128)
+    mine2 = P3Embed(sample_ratio=1 / 16, k=8, embed_dim=128)
+    mine2.load_state_dict(r2.state_dict(), strict=True)
+    assert mine2.out_channels == r2.out_channels and mine2.channel_list == r2.channel_list
+
+
+def test_no_cpu_fallback():
+    from p3tok import functional as F
+    x = torch.zeros(1, 16, 3)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        F.furthest_point_sample(x, 4, torch.zeros(1, dtype=torch.long))
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        F.knn_point(4, x, x[:, :2])
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        PointNet(32, 4, 4, 6).eval()(x)
+
+
+def test_train_mode_is_rejected():
+    with pytest.raises(RuntimeError, match="eval"):
+        Encoder(32, 6).train()(torch.zeros(1, 2, 4, 6))
+    with pytest.raises(ValueError):
+        Encoder(32, 6, precision="fp16").eval()(torch.zeros(1, 2, 4, 6))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.dirname(_lib.__file__)
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert "oracle" not in src.replace("# oracle", ""), f
