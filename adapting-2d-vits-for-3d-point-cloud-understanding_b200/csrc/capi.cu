@@ -1,5 +1,6 @@
 // capi.cu - error plumbing and the precision dispatch of the C ABI (include/p3tok.h).
 #include <stdarg.h>
+#include <atomic>
 #include <string.h>
 
 #include "embed.cuh"
@@ -7,6 +8,9 @@
 namespace p3tok {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -47,6 +51,7 @@ using namespace p3tok;
 
 extern "C" int p3tok_abi_version(void) { return P3TOK_ABI_VERSION; }
 extern "C" const char* p3tok_last_error(void) { return g_err; }
+extern "C" int64_t p3tok_kernel_launches(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int64_t p3tok_patch_embed_workspace_bytes(const p3tok_mlp* mlp, int64_t ngroups, int64_t k, int precision) {
   if (!mlp || ngroups < 0 || k <= 0 || mlp->n_pre < 1 || mlp->n_pre > 4) return -1;

@@ -11,6 +11,7 @@ namespace p3tok {
 // thread-local error string surfaced by p3tok_last_error()
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+void count_launch(int n = 1);   // process-wide diagnostic counter (p3tok_kernel_launches)
 
 #define P3_REQUIRE(cond, code, ...)        \
   do {                                      \
@@ -30,6 +31,7 @@ int cuda_fail(cudaError_t e, const char* what);
   do {                                                              \
     cudaError_t _e = cudaGetLastError();                            \
     if (_e != cudaSuccess) return ::p3tok::cuda_fail(_e, name);     \
+    ::p3tok::count_launch();                                        \
   } while (0)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -213,6 +213,7 @@ static int fps_launch(const float* x, int B, int N, int pt_stride, const int64_t
   cfg.attrs = attr;
   cfg.numAttrs = CL > 1 ? 1 : 0;
   P3_CUDA(cudaLaunchKernelEx(&cfg, fps_kernel<CL>, x, N, pt_stride, start, G, out, slice));
+  count_launch();
   return P3TOK_OK;
 }
 

@@ -30,6 +30,39 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# Optional per-op device timing (bench.py's roofline leg): when a list is installed, every C-ABI call
+# is bracketed by CUDA events recorded on the launching stream.
+_PROFILE = None
+
+
+def set_profile(sink):
+    """sink: None (off) or a list that receives (op_name, start_event, end_event)."""
+    global _PROFILE
+    _PROFILE = sink
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream())
+
+    def __exit__(self, *a):
+        if _PROFILE is not None:
+            self.e1.record(torch.cuda.current_stream())
+            _PROFILE.append((self.name, self.e0, self.e1))
+        return False
+
+
+def kernel_launches() -> int:
+    """Kernels launched by libp3tok.so in this process so far."""
+    return int(_L().p3tok_kernel_launches())
+
+
 def _need_cuda(name: str, *tensors: Optional[torch.Tensor]) -> torch.device:
     dev = None
     for t in tensors:
@@ -78,7 +111,7 @@ def fps(x: torch.Tensor, start_idx: torch.Tensor, npoint: int) -> torch.Tensor:
     if start.shape != (B,):
         raise RuntimeError(f"p3tok::fps: start_idx must have shape ({B},)")
     out = torch.empty((B, npoint), dtype=torch.int64, device=x.device)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("fps"):
         check(_L().p3tok_fps(x.data_ptr(), B, N, stride, start.data_ptr(), npoint, out.data_ptr(), _stream()), "fps")
     return out
 
@@ -97,7 +130,7 @@ def gather_points(x: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     flat = idx.to(torch.int64).reshape(B, -1).contiguous()
     S = int(flat.shape[1])
     out = torch.empty((B, S, C), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("gather"):
         check(_L().p3tok_gather_points(x.data_ptr(), B, N, C, flat.data_ptr(), S, out.data_ptr(), _stream()),
               "gather_points")
     return out.view(*idx.shape, C)
@@ -125,7 +158,7 @@ def knn(x: torch.Tensor, centres: torch.Tensor, k: int, mode: int, int32_out: bo
         raise RuntimeError(f"p3tok::knn: selected index k out of range (k={k} > N={N})")
     idx = torch.empty((B, G, k), dtype=torch.int32 if int32_out else torch.int64, device=x.device)
     dist = torch.empty((B, G, k) if return_dist else (0,), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("knn"):
         check(_L().p3tok_knn(x.data_ptr(), B, N, stride, c.data_ptr(), G, k, mode, idx.data_ptr(),
                              _lib.I32 if int32_out else _lib.I64, dist.data_ptr() if return_dist else None,
                              _stream()), "knn")
@@ -147,7 +180,7 @@ def morton_order(centres: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     B, G = int(c.shape[0]), int(c.shape[1])
     perm = torch.empty((B, G), dtype=torch.int64, device=c.device)
     codes = torch.empty((B, G), dtype=torch.int64, device=c.device)
-    with torch.cuda.device(c.device):
+    with torch.cuda.device(c.device), _timed("morton"):
         check(_L().p3tok_morton_order(c.data_ptr(), B, G, perm.data_ptr(), codes.data_ptr(), _stream()), "morton_order")
     return perm, codes
 
@@ -171,7 +204,7 @@ def apf_group(x: torch.Tensor, fps_idx: torch.Tensor, knn_idx: torch.Tensor,
     pm = perm.to(torch.int64).contiguous() if perm is not None else None
     neigh = torch.empty((B, G, k, 2 * C), dtype=torch.float32, device=x.device)
     center = torch.empty((B, G, 3), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("apf_group"):
         check(_L().p3tok_apf_group(x.data_ptr(), B, N, C, f.data_ptr(), kn.data_ptr(), _ptr(pm), G, k,
                                    neigh.data_ptr(), center.data_ptr(), _stream()), "apf_group")
     return neigh, center
@@ -195,7 +228,7 @@ def group_gather(pnts: torch.Tensor, feats: torch.Tensor, idx: torch.Tensor) -> 
     i32 = idx.to(torch.int32).contiguous()
     gp = torch.empty((B, G, k, 3), dtype=torch.float32, device=p.device)
     gf = torch.empty((B, G, k, D), dtype=torch.float32, device=p.device)
-    with torch.cuda.device(p.device):
+    with torch.cuda.device(p.device), _timed("group_gather"):
         check(_L().p3tok_group_gather(p.data_ptr(), f.data_ptr(), B, N, D, i32.data_ptr(), G, k, gp.data_ptr(),
                                       gf.data_ptr(), _stream()), "group_gather")
     return gp, gf
@@ -286,7 +319,7 @@ def patch_embed(kind: int, x: torch.Tensor, feats: Optional[torch.Tensor], ctr_i
         raise RuntimeError("p3tok::patch_embed: bad descriptor")
     ws = torch.empty((max(int(ws_bytes), 256),), dtype=torch.uint8, device=x.device)
     tokens = torch.empty((ngroups, m.out_dim), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("embed"):
         check(L.p3tok_patch_embed(ctypes.byref(r), ctypes.byref(m), prec, ws.data_ptr(), int(ws.numel()),
                                   tokens.data_ptr(), _stream()), "patch_embed")
     del keep
@@ -309,7 +342,7 @@ def linear_f32(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], r
     M, K = (int(v) for v in a2.shape)
     N = int(w.shape[0])
     out = torch.empty((M, N), dtype=torch.float32, device=a.device)
-    with torch.cuda.device(a.device):
+    with torch.cuda.device(a.device), _timed("linear_f32"):
         check(_L().p3tok_linear_f32(a2.data_ptr(), M, K, w.data_ptr(), N, _ptr(b), None, 1, int(relu), out.data_ptr(),
                                     _stream()), "linear_f32")
     return out.view(*a.shape[:-1], N)
@@ -327,7 +360,7 @@ def group_max(x: torch.Tensor, k: int) -> torch.Tensor:
     C = int(x.shape[-1])
     ng = x.numel() // (C * k)
     out = torch.empty((ng, C), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("group_max"):
         check(_L().p3tok_group_max(x.data_ptr(), ng, k, C, out.data_ptr(), _stream()), "group_max")
     return out
 

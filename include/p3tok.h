@@ -51,6 +51,8 @@ enum p3tok_dtype { P3TOK_F32 = 0, P3TOK_BF16 = 1, P3TOK_I32 = 2, P3TOK_I64 = 3 }
 
 P3TOK_API int p3tok_abi_version(void);
 P3TOK_API const char* p3tok_last_error(void);
+/* number of kernels this library has launched in this process (diagnostic; bench.py reports it) */
+P3TOK_API int64_t p3tok_kernel_launches(void);
 
 /* ---- a1/a2: farthest point sampling ----------------------------------------------------------
  * Replaces furthest_point_sample (src/data/sampler.py:4-30) and farthest_point_sampling
