@@ -353,6 +353,33 @@ def _(a, w, bias, relu):
     return a.new_empty((*a.shape[:-1], w.shape[0]))
 
 
+@torch.library.custom_op("p3tok::linear_bf16", mutates_args=(), device_types="cuda")
+def linear_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], relu: bool,
+                want_max32: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """tcgen05 GEMM building block: a (M,K) bf16, w (N,K) bf16 -> (bf16 out, f32 out, f32 max over 32-row blocks)."""
+    _need_cuda("linear_bf16", a, w, bias)
+    if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
+        raise RuntimeError("p3tok::linear_bf16: operands must be bfloat16")
+    a, w = a.contiguous(), w.contiguous()
+    b = _f32c("linear_bf16", bias) if bias is not None else None
+    M, K = (int(v) for v in a.shape)
+    N = int(w.shape[0])
+    ob = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    of = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    om = torch.empty(((M + 31) // 32 if want_max32 else 0, N), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device), _timed("linear_bf16"):
+        check(_L().p3tok_linear_bf16(a.data_ptr(), M, K, w.data_ptr(), N, _ptr(b), None, 1, int(relu), ob.data_ptr(),
+                                     of.data_ptr(), om.data_ptr() if want_max32 else None, _stream()), "linear_bf16")
+    return ob, of, om
+
+
+@linear_bf16.register_fake
+def _(a, w, bias, relu, want_max32):
+    M, N = a.shape[0], w.shape[0]
+    return (a.new_empty((M, N)), a.new_empty((M, N), dtype=torch.float32),
+            a.new_empty(((M + 31) // 32 if want_max32 else 0, N), dtype=torch.float32))
+
+
 @torch.library.custom_op("p3tok::group_max", mutates_args=(), device_types="cuda")
 def group_max(x: torch.Tensor, k: int) -> torch.Tensor:
     _need_cuda("group_max", x)

@@ -168,6 +168,13 @@ P3TOK_API int p3tok_linear_f32(const float* A, int64_t M, int64_t K, const float
                      const float* bias, const float* gbias, int64_t rows_per_group, int relu,
                      float* C, void* stream);
 
+/* Tensor-core version (tcgen05, bf16 operands A[M,K], W[N,K]; K % 8 == 0, N % 8 == 0; fp32 accumulate).
+ * Any subset of the outputs may be requested: out_bf16 [M,N] bf16, out_f32 [M,N] f32, out_max32
+ * [ceil(M/32), N] f32 = max over each 32 consecutive rows (the fused patch max-pool for k = 32). */
+P3TOK_API int p3tok_linear_bf16(const void* A, int64_t M, int64_t K, const void* W, int64_t N, const float* bias,
+                      const float* gbias, int64_t rows_per_group, int relu, void* out_bf16,
+                      float* out_f32, float* out_max32, void* stream);
+
 /* out[g, c] = max over r < k of in[(g*k + r), c]   (torch.max(..., dim=k-axis)) */
 P3TOK_API int p3tok_group_max(const float* in, int64_t ngroups, int64_t k, int64_t C, float* out, void* stream);
 

@@ -136,3 +136,22 @@ def test_token_properties_full_c2(prec):
     t1 = net.encoder(neigh)
     t2 = net.encoder(neigh.flip(2))
     assert torch.equal(t1, t2) or rel_err(t1.cpu().numpy(), t2.cpu().numpy()) < 1e-6
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 64, 64), (128, 256, 256), (300, 48, 40), (1000, 512, 384), (4096, 768, 384),
+                                   (37888, 384, 768), (33, 136, 256), (64, 8, 8)])
+def test_tc_linear_building_block(M, K, N):
+    """tcgen05 GEMM against torch on the same bf16 operands (fp32 accumulate on both sides)."""
+    torch.manual_seed(M + K + N)
+    a = (torch.randn(M, K, device=dev()) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=dev()) * 0.1).bfloat16()
+    b = torch.randn(N, device=dev())
+    ob, of, om = ops.linear_bf16(a, w, b, True, True)
+    ref = torch.relu(a.float() @ w.float().T + b)
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    assert float((of - ref).abs().max()) <= 2e-5 * max(scale, 1.0) + 1e-5 * K ** 0.5
+    assert float((ob.float() - ref).abs().max()) <= 8e-3 * max(scale, 1.0)
+    pad = (32 - M % 32) % 32
+    refm = torch.cat([ref, ref.new_full((pad, N), -1.0)]).view(-1, 32, N).max(1)[0]
+    assert float((om - refm).abs().max()) <= 2e-5 * max(scale, 1.0) + 1e-5 * K ** 0.5
