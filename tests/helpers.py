@@ -18,15 +18,48 @@ def rel_err(a, ref):
 
 
 def assert_tokens_close(a, ref, rtol, what=""):
-    """|a - ref| <= rtol * (|ref| + mean|ref|): the north-star tolerance (rtol 1e-4 fp32 / 1e-2 bf16)
-    with an absolute floor of rtol x the mean token magnitude for entries that cancel to ~0."""
+    """The north-star tolerance (rtol 1e-4 for the fp32 path, 1e-2 for the bf16 path), written out:
+         elementwise   |a - ref| <= rtol * |ref| + rtol * max|ref|     (allclose with a scale-aware atol:
+                       ReLU/max-pooled tokens that cancel to ~0 cannot meet a pure relative bound in any
+                       reduced precision)
+         aggregate     ||a - ref||_F <= 0.5 * rtol * ||ref||_F
+    """
     a = np.asarray(a, np.float64)
     ref = np.asarray(ref, np.float64)
     assert a.shape == ref.shape, (a.shape, ref.shape)
-    bound = rtol * (np.abs(ref) + np.abs(ref).mean())
+    assert np.isfinite(a).all(), f"{what}: non-finite tokens"
+    bound = rtol * np.abs(ref) + rtol * np.abs(ref).max()
     bad = np.abs(a - ref) > bound
     assert not bad.any(), (f"{what}: {int(bad.sum())}/{bad.size} tokens outside rtol={rtol}; "
                            f"worst ratio {float((np.abs(a - ref) / bound).max()):.2f}")
+    fro = float(np.linalg.norm(a - ref) / max(np.linalg.norm(ref), 1e-30))
+    assert fro <= 0.5 * rtol, f"{what}: relative Frobenius error {fro:.2e} > {0.5 * rtol:.1e}"
+
+
+def bf16_emulation(mlp, rows, k):
+    """The bf16 path's arithmetic spelled in torch (any device): bf16 weights and stored activations,
+    fp32 accumulation, max taken from the fp32 accumulators.  Test-side model of embed_tc.cu."""
+    import torch
+
+    def q(t):
+        return t.bfloat16().float()
+
+    h = rows.float()
+    n = len(mlp.w_pre)
+    for i, (w, b, r) in enumerate(zip(mlp.w_pre, mlp.b_pre, mlp.pre_relu)):
+        if i > 0 or mlp.cin > 16:
+            h = q(h)
+        h = (h.double() @ q(w.to(h.device)).double().T + b.to(h.device).double()).float()
+        if r:
+            h = torch.relu(h)
+    ng = h.shape[0] // k
+    g = h.view(ng, k, -1).max(1)[0]
+    dev_ = h.device
+    gb = (q(g).double() @ q(mlp.w_mid_g.to(dev_)).double().T + mlp.b_mid.to(dev_).double()).float()
+    h2 = torch.relu((q(h).double() @ q(mlp.w_mid_f.to(dev_)).double().T).float() + gb.repeat_interleave(k, 0))
+    o = (q(h2).double() @ q(mlp.w_out.to(dev_)).double().T + mlp.b_out.to(dev_).double()).float()
+    o = o.view(ng, k, -1).max(1)[0]
+    return torch.relu(o) if mlp.out_relu else o
 
 
 def folded_forward(mlp, rows, k):

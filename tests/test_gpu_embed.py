@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import cases
-from helpers import assert_tokens_close, dev, rel_err, to_dev
+from helpers import assert_tokens_close, bf16_emulation, dev, rel_err, to_dev
 from oracle import oracle
 from p3tok import _lib, ops, synth
 from p3tok.modules import Encoder, P3Embed, PointNet
@@ -155,3 +155,21 @@ def test_tc_linear_building_block(M, K, N):
     pad = (32 - M % 32) % 32
     refm = torch.cat([ref, ref.new_full((pad, N), -1.0)]).view(-1, 32, N).max(1)[0]
     assert float((om - refm).abs().max()) <= 2e-5 * max(scale, 1.0) + 1e-5 * K ** 0.5
+
+
+@pytest.mark.parametrize("E,k,cin", [(64, 32, 6), (384, 32, 6), (48, 16, 8), (96, 64, 6)])
+def test_bf16_path_matches_its_arithmetic_model(E, k, cin):
+    """Tight check of the tensor-core path: against a torch model of exactly its arithmetic (bf16 operands,
+    fp32 accumulate) the only differences are accumulation order and bf16 ties -> 2e-3 of max."""
+    _skip_if_unbuilt("bf16")
+    from p3tok import fold
+    torch.manual_seed(E)
+    ng = 300
+    rows = torch.randn(ng * k, cin, device=dev()) * 0.3
+    sd = synth.to_torch_state(synth.apf_encoder_state(E, cin, 5))
+    enc = Encoder(E, cin, precision="bf16").eval().to(dev())
+    enc.load_state_dict(sd)
+    tok = enc(rows.view(1, ng, k, cin))[0]
+    model = bf16_emulation(fold.fold_apf_encoder(sd), rows, k)
+    err = float((tok - model).abs().max() / model.abs().max())
+    assert err < 2e-3, err
