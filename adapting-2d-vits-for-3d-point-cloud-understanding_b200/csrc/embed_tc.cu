@@ -116,10 +116,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM
-constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4, TC_MAX_BN = 256, TC_THREADS = 192;
-constexpr int TC_A_STAGE = TC_BM * TC_BK * 2;       // 16 KB
-constexpr int TC_B_STAGE = TC_MAX_BN * TC_BK * 2;   // 32 KB
-constexpr int TC_SMEM = TC_STAGES * (TC_A_STAGE + TC_B_STAGE) + 256 + 1024;
+constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 3, TC_MAX_BN = 256;
+constexpr int TC_EPI_WARPS = 8;                      // two warps per TMEM lane quarter, alternating 64-column groups
+constexpr int TC_THREADS = 64 + TC_EPI_WARPS * 32;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int TC_A_STAGE = TC_BM * TC_BK * 2;        // 16 KB
+constexpr int TC_B_STAGE = TC_MAX_BN * TC_BK * 2;    // 32 KB
+constexpr int TC_STAGING = 32 * 128;                 // one 32-row x 64-column bf16 store box (4 KB, 128B-swizzled)
+constexpr int TC_SMEM_PIPE = TC_STAGES * (TC_A_STAGE + TC_B_STAGE);
+constexpr int TC_SMEM = TC_SMEM_PIPE + TC_EPI_WARPS * 2 * TC_STAGING + 256 + 1024;
 
 struct TcParams {
   int M, N, K, BN;
@@ -128,20 +132,63 @@ struct TcParams {
   const float* gbias;      // [ceil(M/rows_per_group), N] or null
   int rows_per_group;
   int relu;
-  __nv_bfloat16* out_bf16; // [M,N] or null
+  int store_bf16;          // write bf16 [M,N] through tmC (TMA store)
   float* out_f32;          // [M,N] or null
   float* out_max;          // [ceil(M/32), N] max over each 32 consecutive rows, or null
   __nv_bfloat16* out_max_bf16;
   int max_relu;            // apply ReLU to the max (out_relu of the block)
 };
 
+// bias / per-group bias / ReLU on 32 accumulator columns starting at global column n0
+__device__ __forceinline__ void epilogue_affine(float (&v)[32], const TcParams& p, const float* gb, int n0) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    if (n0 + j < p.N) {              // N % 8 == 0 -> a whole float4 is in range
+      if (p.bias) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      }
+      if (gb) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gb + n0 + j));
+        v[j] += g4.x; v[j + 1] += g4.y; v[j + 2] += g4.z; v[j + 3] += g4.w;
+      }
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+}
+
+// max over the warp's 32 rows (lane = row): lane-transpose reduction, lane l returns column l
+__device__ __forceinline__ float warp_rows_max(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      const float send = hi ? v[j] : v[j + off];
+      const float keep = hi ? v[j + off] : v[j];
+      v[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, off));
+    }
+  }
+  return v[0];
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + TC_STAGES * TC_A_STAGE;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * (TC_A_STAGE + TC_B_STAGE));
+  uint8_t* sC = smem + TC_SMEM_PIPE;                  // per-epilogue-warp store staging, 2 x 4 KB each
+  uint64_t* full = reinterpret_cast<uint64_t*>(sC + TC_EPI_WARPS * 2 * TC_STAGING);
   uint64_t* empty = full + TC_STAGES;
   uint64_t* tfull = empty + TC_STAGES;
   uint64_t* tempty = tfull + 2;
@@ -154,13 +201,14 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    if (p.store_bf16) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], 4);
+      mbar_init(&tempty[b], TC_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -214,84 +262,85 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_commit(&tfull[buf]);       // accumulator complete
       }
     }
-  } else {             // ---------------- epilogue warps 2..5: TMEM lane quarter = warp % 4
-    const int q = warp & 3;
+  } else {             // ---------------- epilogue warps: TMEM lane quarter q, column-group parity h
+    const int ew = warp - 2;
+    const int q = warp & 3, h = ew >> 2;
+    uint8_t* stg = sC + ew * 2 * TC_STAGING;
+    int sbuf = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
       const int buf = it & 1;
       mbar_wait(&tfull[buf], (uint32_t)(it >> 1) & 1);
       tc_fence_after();
-      const int row = mt * TC_BM + q * 32 + lane;
+      const int row0 = mt * TC_BM + q * 32;
+      const int row = row0 + lane;
       const bool row_ok = row < p.M;
       const float* gb = (p.gbias && row_ok) ? p.gbias + (size_t)(row / p.rows_per_group) * p.N : nullptr;
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
-        const int n0 = nt * p.BN + c0;
-        if (n0 >= p.N) break;            // warp-uniform
-        float v[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + c0), v);
+      for (int gi = h; gi * 64 < p.BN; gi += 2) {
+        const int n0 = nt * p.BN + gi * 64;
+        if (n0 >= p.N || row0 >= p.M) break;     // warp-uniform
+        float v0[32], v1[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + gi * 64);
+        tc_ld32(taddr, v0);
+        tc_ld32(taddr + 32, v1);
+        epilogue_affine(v0, p, gb, n0);
+        epilogue_affine(v1, p, gb, n0 + 32);
+        if (p.store_bf16) {
+          // stage the 32 x 64 bf16 box in the 128B-swizzled layout the store tensor map expects, then one
+          // TMA store (clips rows >= M and columns >= N); double-buffered per warp
+          uint8_t* sb = stg + sbuf * TC_STAGING;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+          const uint32_t rbase = smem_u32(sb) + lane * 128;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (n0 + j < p.N) {            // N % 8 == 0 -> whole float4 in range
-            if (p.bias) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
-            if (gb) {
-              const float4 g4 = __ldg(reinterpret_cast<const float4*>(gb + n0 + j));
-              v[j] += g4.x; v[j + 1] += g4.y; v[j + 2] += g4.z; v[j + 3] += g4.w;
-            }
+          for (int pc = 0; pc < 4; ++pc) {
+            const uint32_t a0 = rbase + (((uint32_t)pc ^ (lane & 7)) << 4);
+            const uint32_t a1 = rbase + (((uint32_t)(pc + 4) ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(pack_bf16x2(v0[pc * 8], v0[pc * 8 + 1])),
+                         "r"(pack_bf16x2(v0[pc * 8 + 2], v0[pc * 8 + 3])), "r"(pack_bf16x2(v0[pc * 8 + 4], v0[pc * 8 + 5])),
+                         "r"(pack_bf16x2(v0[pc * 8 + 6], v0[pc * 8 + 7]))
+                         : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(pack_bf16x2(v1[pc * 8], v1[pc * 8 + 1])),
+                         "r"(pack_bf16x2(v1[pc * 8 + 2], v1[pc * 8 + 3])), "r"(pack_bf16x2(v1[pc * 8 + 4], v1[pc * 8 + 5])),
+                         "r"(pack_bf16x2(v1[pc * 8 + 6], v1[pc * 8 + 7]))
+                         : "memory");
           }
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (row_ok) {
-          if (p.out_bf16) {
-            __nv_bfloat16* o = p.out_bf16 + (size_t)row * p.N + n0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (n0 + j < p.N) {
-                uint4 pk;
-                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                *reinterpret_cast<uint4*>(o + j) = pk;
-              }
-            }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmC)),
+                         "r"(smem_u32(sb)), "r"(n0), "r"(row0)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          if (p.out_f32) {
-            float* o = p.out_f32 + (size_t)row * p.N + n0;
+          sbuf ^= 1;
+        }
+        if (p.out_f32 && row_ok) {
+          float* o = p.out_f32 + (size_t)row * p.N + n0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (n0 + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int j = 0; j < 32; j += 4) {
+            if (n0 + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
+            if (n0 + 32 + j < p.N) *reinterpret_cast<float4*>(o + 32 + j) = make_float4(v1[j], v1[j + 1], v1[j + 2], v1[j + 3]);
           }
         }
         if (p.out_max || p.out_max_bf16) {
-          // max over the warp's 32 rows: lane-transpose reduction, lane l ends with column l
           if (!row_ok) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = -3.0e38f;
+            for (int j = 0; j < 32; ++j) { v0[j] = -3.0e38f; v1[j] = -3.0e38f; }
           }
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool hi = (lane & off) != 0;
-#pragma unroll
-            for (int j = 0; j < off; ++j) {
-              const float send = hi ? v[j] : v[j + off];
-              const float keep = hi ? v[j + off] : v[j];
-              v[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, off));
-            }
+          float m0 = warp_rows_max(v0, lane), m1 = warp_rows_max(v1, lane);
+          if (p.max_relu) { m0 = fmaxf(m0, 0.f); m1 = fmaxf(m1, 0.f); }
+          const size_t grow = (size_t)(row0 >> 5) * p.N;
+          const int na = n0 + lane, nb = n0 + 32 + lane;
+          if (p.out_max) {
+            if (na < p.N) p.out_max[grow + na] = m0;
+            if (nb < p.N) p.out_max[grow + nb] = m1;
           }
-          float mx = v[0];
-          if (p.max_relu) mx = fmaxf(mx, 0.f);
-          const int n = n0 + lane;
-          const int grow = (mt * TC_BM + q * 32) >> 5;
-          if (n < p.N && mt * TC_BM + q * 32 < p.M) {
-            if (p.out_max) p.out_max[(size_t)grow * p.N + n] = mx;
-            if (p.out_max_bf16) p.out_max_bf16[(size_t)grow * p.N + n] = __float2bfloat16_rn(mx);
+          if (p.out_max_bf16) {
+            if (na < p.N) p.out_max_bf16[grow + na] = __float2bfloat16_rn(m0);
+            if (nb < p.N) p.out_max_bf16[grow + nb] = __float2bfloat16_rn(m1);
           }
         }
       }
@@ -299,6 +348,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores of this warp are complete
   }
   tc_fence_before();
   __syncthreads();
@@ -327,6 +377,7 @@ static EncodeTiledFn encode_fn() {
 
 // bf16 row-major [rows, cols] (row pitch = cols*2 bytes), box = 64 cols x box_rows, 128B swizzle, OOB -> 0
 static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int box_rows) {
+  P3_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, P3TOK_ERR_UNSUPPORTED, "tensor map: base must be 16-byte aligned");
   EncodeTiledFn fn = encode_fn();
   P3_REQUIRE(fn, P3TOK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -353,9 +404,9 @@ static int num_sms() {
 }
 
 static int pick_bn(int N) {
-  // widest tile <= 256 (multiple of 32) that wastes the least padded columns
-  int best = 32, best_waste = 1 << 30;
-  for (int bn = 256; bn >= 32; bn -= 32) {
+  // widest tile <= 256 (multiple of 64: the epilogue works in 64-column store boxes) with the least padding
+  int best = 64, best_waste = 1 << 30;
+  for (int bn = 256; bn >= 64; bn -= 64) {
     const int tiles = (N + bn - 1) / bn;
     const int waste = tiles * bn - N;
     if (waste < best_waste) { best_waste = waste; best = bn; }
@@ -375,12 +426,18 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
   p.num_m_tiles = (int)((M + TC_BM - 1) / TC_BM);
   p.num_n_tiles = (N + p.BN - 1) / p.BN;
   p.bias = bias; p.gbias = gbias; p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1; p.relu = relu;
-  p.out_bf16 = out_bf16; p.out_f32 = out_f32; p.out_max = out_max; p.out_max_bf16 = out_max_bf16; p.max_relu = max_relu;
-  CUtensorMap ta, tb;
+  p.store_bf16 = out_bf16 != nullptr; p.out_f32 = out_f32; p.out_max = out_max; p.out_max_bf16 = out_max_bf16; p.max_relu = max_relu;
+  CUtensorMap ta, tb, tc;
   int rc = make_map(&ta, A, M, K, TC_BM);
   if (rc) return rc;
   rc = make_map(&tb, W, N, K, p.BN);
   if (rc) return rc;
+  if (out_bf16) {
+    rc = make_map(&tc, out_bf16, M, N, 32);     // store boxes: 64 columns x 32 rows
+    if (rc) return rc;
+  } else {
+    tc = ta;                                     // unused by the kernel
+  }
   static thread_local bool configured[32] = {false};
   int dev = 0;
   P3_CUDA(cudaGetDevice(&dev));
@@ -390,22 +447,22 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  tc_linear_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(ta, tb, p);
+  tc_linear_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(ta, tb, tc, p);
   P3_LAUNCH_CHECK("tc_linear_kernel");
   return P3TOK_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ first layer
 // Narrow input: one CTA = 32 rows (one k=32 patch when aligned), 128 threads x 2 output channels per pass.
-template <typename IdxT>
+template <typename IdxT, int CP>   // CP = padded input width (8 or 16)
 __global__ void __launch_bounds__(128)
 rows_first_layer_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, const __nv_bfloat16* __restrict__ W,
                         const float* __restrict__ bias, int cin, int nout, int relu, __nv_bfloat16* __restrict__ out) {
-  __shared__ float xin[32][16];
+  __shared__ __align__(16) float xin[32][CP];
   const int64_t r0 = (int64_t)blockIdx.x * 32;
   const IdxT* knn = reinterpret_cast<const IdxT*>(R.knn_idx);
-  for (int e = threadIdx.x; e < 32 * 16; e += 128) {
-    const int rr = e >> 4, c = e & 15;
+  for (int e = threadIdx.x; e < 32 * CP; e += 128) {
+    const int rr = e / CP, c = e % CP;
     const int64_t r = r0 + rr;
     float v = 0.f;          // columns >= cin and rows >= nrows stay zero
     if (r < nrows && c < cin) {
@@ -429,9 +486,9 @@ rows_first_layer_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, const __nv
   }
   __syncthreads();
   for (int n0 = threadIdx.x * 2; n0 < nout; n0 += 256) {
-    float w0[16], w1[16];
+    float w0[CP], w1[CP];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
+    for (int c = 0; c < CP; ++c) {
       w0[c] = c < cin ? __bfloat162float(W[(size_t)n0 * cin + c]) : 0.f;
       w1[c] = (c < cin && n0 + 1 < nout) ? __bfloat162float(W[(size_t)(n0 + 1) * cin + c]) : 0.f;
     }
@@ -441,10 +498,12 @@ rows_first_layer_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, const __nv
       if (r >= nrows) break;
       float a0 = b0, a1 = b1;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const float xv = xin[rr][c];
-        a0 = fmaf(w0[c], xv, a0);
-        a1 = fmaf(w1[c], xv, a1);
+      for (int c4 = 0; c4 < CP; c4 += 4) {
+        const float4 xv = *reinterpret_cast<const float4*>(&xin[rr][c4]);   // warp-wide broadcast
+        a0 = fmaf(w0[c4], xv.x, a0); a1 = fmaf(w1[c4], xv.x, a1);
+        a0 = fmaf(w0[c4 + 1], xv.y, a0); a1 = fmaf(w1[c4 + 1], xv.y, a1);
+        a0 = fmaf(w0[c4 + 2], xv.z, a0); a1 = fmaf(w1[c4 + 2], xv.z, a1);
+        a0 = fmaf(w0[c4 + 3], xv.w, a0); a1 = fmaf(w1[c4 + 3], xv.w, a1);
       }
       if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
       *reinterpret_cast<__nv_bfloat162*>(out + r * nout + n0) = __floats2bfloat162_rn(a0, a1);
@@ -618,12 +677,12 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
     int kin;
     if (!L.kpad0) {
       const unsigned blocks = (unsigned)((rows + 31) / 32);
-      if (i64)
-        rows_first_layer_kernel<int64_t><<<blocks, 128, 0, s>>>(*R, g0, rows, (const __nv_bfloat16*)m->w_pre[0], m->b_pre[0],
-                                                               m->cin, m->pre_dim[0], m->pre_relu[0], act[cur]);
-      else
-        rows_first_layer_kernel<int32_t><<<blocks, 128, 0, s>>>(*R, g0, rows, (const __nv_bfloat16*)m->w_pre[0], m->b_pre[0],
-                                                               m->cin, m->pre_dim[0], m->pre_relu[0], act[cur]);
+#define P3_L1(IDX, CPV)                                                                                        \
+  rows_first_layer_kernel<IDX, CPV><<<blocks, 128, 0, s>>>(*R, g0, rows, (const __nv_bfloat16*)m->w_pre[0],    \
+                                                           m->b_pre[0], m->cin, m->pre_dim[0], m->pre_relu[0], act[cur])
+      if (m->cin <= 8) { if (i64) P3_L1(int64_t, 8); else P3_L1(int32_t, 8); }
+      else             { if (i64) P3_L1(int64_t, 16); else P3_L1(int32_t, 16); }
+#undef P3_L1
       P3_LAUNCH_CHECK("rows_first_layer_kernel");
       first_tc = 1;
       kin = m->pre_dim[0];
