@@ -23,6 +23,7 @@
 // processed in chunks of groups sized to stay L2-resident between consecutive layers.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "embed.cuh"
 
@@ -88,7 +89,8 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+// issue only: the registers are valid after tc_ld_wait()
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -99,10 +101,10 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, rows of 128 B, 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
@@ -123,7 +125,8 @@ constexpr int TC_A_STAGE = TC_BM * TC_BK * 2;        // 16 KB
 constexpr int TC_B_STAGE = TC_MAX_BN * TC_BK * 2;    // 32 KB
 constexpr int TC_STAGING = 32 * 128;                 // one 32-row x 64-column bf16 store box (4 KB, 128B-swizzled)
 constexpr int TC_SMEM_PIPE = TC_STAGES * (TC_A_STAGE + TC_B_STAGE);
-constexpr int TC_SMEM = TC_SMEM_PIPE + TC_EPI_WARPS * 2 * TC_STAGING + 256 + 1024;
+constexpr int TC_MAX_N = 2048;                      // bias vector staged in shared memory (8 KB)
+constexpr int TC_SMEM = TC_SMEM_PIPE + TC_EPI_WARPS * 2 * TC_STAGING + TC_MAX_N * 4 + 256 + 1024;
 
 struct TcParams {
   int M, N, K, BN;
@@ -139,19 +142,24 @@ struct TcParams {
   int max_relu;            // apply ReLU to the max (out_relu of the block)
 };
 
-// bias / per-group bias / ReLU on 32 accumulator columns starting at global column n0
-__device__ __forceinline__ void epilogue_affine(float (&v)[32], const TcParams& p, const float* gb, int n0) {
+// bias / per-group bias / ReLU on 32 accumulator columns starting at global column n0.  `sbias` is the
+// bias vector staged in shared memory (zeros when the layer has none); all loads are issued before use.
+__device__ __forceinline__ void epilogue_affine(float (&v)[32], const TcParams& p, const float* sbias, const float* gb, int n0) {
+  const int nmax = p.N - 4;                                  // N % 8 == 0: clamped float4 loads stay in range
+  float4 g4[8];
+  if (gb) {
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    if (n0 + j < p.N) {              // N % 8 == 0 -> a whole float4 is in range
-      if (p.bias) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-      }
-      if (gb) {
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gb + n0 + j));
-        v[j] += g4.x; v[j + 1] += g4.y; v[j + 2] += g4.z; v[j + 3] += g4.w;
-      }
+    for (int j = 0; j < 8; ++j) g4[j] = __ldg(reinterpret_cast<const float4*>(gb + min(n0 + 4 * j, nmax)));
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 b4 = *reinterpret_cast<const float4*>(sbias + min(n0 + 4 * j, nmax));
+    v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+  }
+  if (gb) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[4 * j] += g4[j].x; v[4 * j + 1] += g4[j].y; v[4 * j + 2] += g4[j].z; v[4 * j + 3] += g4[j].w;
     }
   }
   if (p.relu) {
@@ -188,7 +196,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sA = smem;
   uint8_t* sB = smem + TC_STAGES * TC_A_STAGE;
   uint8_t* sC = smem + TC_SMEM_PIPE;                  // per-epilogue-warp store staging, 2 x 4 KB each
-  uint64_t* full = reinterpret_cast<uint64_t*>(sC + TC_EPI_WARPS * 2 * TC_STAGING);
+  float* sbias = reinterpret_cast<float*>(sC + TC_EPI_WARPS * 2 * TC_STAGING);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sC + TC_EPI_WARPS * 2 * TC_STAGING + TC_MAX_N * 4);
   uint64_t* empty = full + TC_STAGES;
   uint64_t* tfull = empty + TC_STAGES;
   uint64_t* tempty = tfull + 2;
@@ -212,6 +221,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < p.N; i += TC_THREADS) sbias[i] = p.bias ? p.bias[i] : 0.f;
   if (warp == 1) {   // TMEM: 512 columns = two 128 x BN fp32 accumulators
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -282,10 +292,11 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (n0 >= p.N || row0 >= p.M) break;     // warp-uniform
         float v0[32], v1[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + gi * 64);
-        tc_ld32(taddr, v0);
-        tc_ld32(taddr + 32, v1);
-        epilogue_affine(v0, p, gb, n0);
-        epilogue_affine(v1, p, gb, n0 + 32);
+        tc_ld32_issue(taddr, v0);
+        tc_ld32_issue(taddr + 32, v1);
+        tc_ld_wait();
+        epilogue_affine(v0, p, sbias, gb, n0);
+        epilogue_affine(v1, p, sbias, gb, n0 + 32);
         if (p.store_bf16) {
           // stage the 32 x 64 bf16 box in the 128B-swizzled layout the store tensor map expects, then one
           // TMA store (clips rows >= M and columns >= N); double-buffered per warp
@@ -419,6 +430,7 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
                      const float* gbias, int rows_per_group, int relu, __nv_bfloat16* out_bf16, float* out_f32,
                      float* out_max, __nv_bfloat16* out_max_bf16, int max_relu, cudaStream_t s) {
   P3_REQUIRE(K % 8 == 0 && N % 8 == 0, P3TOK_ERR_UNSUPPORTED, "tc_linear: K=%d and N=%d must be multiples of 8", K, N);
+  P3_REQUIRE(N <= TC_MAX_N, P3TOK_ERR_UNSUPPORTED, "tc_linear: N=%d > %d", N, TC_MAX_N);
   P3_REQUIRE(M < (1ll << 31) - 256, P3TOK_ERR_UNSUPPORTED, "tc_linear: too many rows");
   if (M == 0) return P3TOK_OK;
   TcParams p;
@@ -600,11 +612,18 @@ static inline unsigned grid_1d(int64_t total, int threads) {
 }
 
 // ------------------------------------------------------------------------------------------------ orchestration
-// Chunk = as many groups as give ~2 full waves of 128-row tiles per layer, which also keeps the widest
-// bf16 activation of a chunk (<= 768 columns, ~58 MB) inside the 126 MB L2 between the layer that
-// writes it and the layer that reads it.
+// Chunking: one chunk of rows goes through all layers before the next starts.  Measured on B200 (C2,
+// 524288 rows): per-launch fixed cost (prologue, pipeline fill, last-tile epilogue) outweighs keeping a
+// chunk's activations L2-resident - 2-wave chunks 1.91 ms, 16-wave chunks 1.35 ms - so chunks are as
+// large as a bounded workspace allows (default 2^20 rows: <= 1.6 GB per bf16 activation buffer at 768
+// columns).  P3TOK_CHUNK_ROWS overrides for experiments.
 static int64_t chunk_groups(int64_t ngroups, int64_t k) {
-  const int64_t rows_target = (int64_t)148 * TC_BM * 2;
+  static int64_t rows_target = 0;
+  if (!rows_target) {
+    const char* e = getenv("P3TOK_CHUNK_ROWS");
+    rows_target = e ? atoll(e) : (1ll << 20);
+    if (rows_target < 128) rows_target = 128;
+  }
   int64_t cg = rows_target / k;
   if (cg < 1) cg = 1;
   return ngroups < cg ? ngroups : cg;
