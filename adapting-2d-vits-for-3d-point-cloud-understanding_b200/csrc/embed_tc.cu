@@ -25,6 +25,8 @@
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "embed.cuh"
 
 namespace p3tok {
@@ -73,6 +75,82 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// multicast variant: the box lands at the same smem offset in every CTA of `mask`, and each destination's
+// mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// L2 prefetch of a tensor box (no shared memory, no barrier): turns the later TMA load into an L2 hit
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+// ---- CTA-pair (cta_group::2) forms: one MMA spans both SMs of the pair (M = 256), each CTA holds its 128
+// rows of A, half of the weight tile and its half of the accumulator; barriers live in the leader (rank 0)
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> leader's copy
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(leader_bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {   // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {   // arrive on `bar` of CTA `cta` of the cluster
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {   // one lane of the (converged) warp
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -118,29 +196,45 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM
-constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 3, TC_MAX_BN = 256;
-constexpr int TC_EPI_WARPS = 8;                      // two warps per TMEM lane quarter, alternating 64-column groups
-constexpr int TC_THREADS = 64 + TC_EPI_WARPS * 32;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int TC_BM = 128, TC_BK = 64, TC_MAX_STAGES = 8, TC_MAX_BN = 256;
+#ifndef P3TOK_EPI_WARPS
+#define P3TOK_EPI_WARPS 8
+#endif
+constexpr int TC_EPI_WARPS = P3TOK_EPI_WARPS;        // 2 (or 4) warps per TMEM lane quarter, interleaved 64-column groups
+constexpr int TC_EPI_PER_Q = TC_EPI_WARPS / 4;
+constexpr int TC_THREADS = 64 + TC_EPI_WARPS * 32;   // warp 0 TMA, warp 1 MMA, the rest epilogue
 constexpr int TC_A_STAGE = TC_BM * TC_BK * 2;        // 16 KB
-constexpr int TC_B_STAGE = TC_MAX_BN * TC_BK * 2;    // 32 KB
 constexpr int TC_STAGING = 32 * 128;                 // one 32-row x 64-column bf16 store box (4 KB, 128B-swizzled)
-constexpr int TC_SMEM_PIPE = TC_STAGES * (TC_A_STAGE + TC_B_STAGE);
-constexpr int TC_MAX_N = 2048;                      // bias vector staged in shared memory (8 KB)
-constexpr int TC_SMEM = TC_SMEM_PIPE + TC_EPI_WARPS * 2 * TC_STAGING + TC_MAX_N * 4 + 256 + 1024;
+constexpr int TC_MAX_N = 2048;                       // bias vector staged in shared memory (8 KB)
+// Shared memory: [pipeline stages][per-warp store staging 8 x 4 KB][bias 8 KB][barriers].  The TMA->MMA ring
+// is sized at launch to fill what is left: a stage round trip (TMA latency ~1500 cycles + MMA drain) needs
+// >= ingest_rate x latency bytes in flight, so the pair mode (32 KB stages) runs 5-6 stages deep.
+constexpr int TC_SMEM = 227 * 1024;
+constexpr int TC_WARP_SCRATCH = TC_STAGING + 256;    // store box + 64-float group-bias slice
+constexpr int TC_SMEM_FIXED = TC_EPI_WARPS * TC_WARP_SCRATCH + TC_MAX_N * 4 + 512 + 1024;
 
 struct TcParams {
   int M, N, K, BN;
   int num_m_tiles, num_n_tiles;
+  int CL;                  // cluster size (1, 2 or 4): CTAs of a cluster take consecutive M tiles of the same
+                           // N tile and share the weight tile by TMA multicast (each loads BN/CL rows of it)
   const float* bias;       // [N] or null
   const float* gbias;      // [ceil(M/rows_per_group), N] or null
   int rows_per_group;
   int relu;
-  int store_bf16;          // write bf16 [M,N] through tmC (TMA store)
+  __nv_bfloat16* out_bf16; // [M,N] or null
   float* out_f32;          // [M,N] or null
   float* out_max;          // [ceil(M/32), N] max over each 32 consecutive rows, or null
   __nv_bfloat16* out_max_bf16;
   int max_relu;            // apply ReLU to the max (out_relu of the block)
+  int stages, stage_bytes; // TMA->MMA ring depth and bytes per stage (A tile 16 KB + this CTA's part of the weight tile)
+  int prefetch;            // L2-prefetch the next item's activation tile
+  unsigned long long* trace;  // debug (P3TOK_TC_TRACE=1): per-CTA clock stamps, 16 words per tile per role
 };
+// trace layout: trace[((cta * 64 + tile_it) * 3 + role) * 4 + {0..3}]
+__device__ __forceinline__ void tc_trace(const TcParams& p, int it, int role, int slot, long long v) {
+  if (p.trace && it < 64) p.trace[(((size_t)blockIdx.x * 64 + it) * 3 + role) * 4 + slot] = (unsigned long long)v;
+}
 
 // bias / per-group bias / ReLU on 32 accumulator columns starting at global column n0.  `sbias` is the
 // bias vector staged in shared memory (zeros when the layer has none); all loads are issued before use.
@@ -188,184 +282,292 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// 32 accumulator columns (lane = row) starting at global column n0: bias / group bias / ReLU, then any of
+//   - pack to bf16 into this warp's 32 x 128 B staging box (4 x 16-byte pieces, XOR-swizzled by row: conflict-free),
+//   - fp32 store, - max over the warp's 32 rows.
+__device__ __forceinline__ void epilogue_half(const TcParams& p, const float* sbias, const float* gb, const float* sgb,
+                                              uint32_t sbox, int half, int row0, int row, bool row_ok, int lane, int n0,
+                                              float (&v)[32]) {
+  if (sgb) {   // this warp's group-bias slice (64 floats for the whole column group), staged in shared memory
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 g = *reinterpret_cast<const float4*>(sgb + 32 * half + 4 * j);
+      v[4 * j] += g.x; v[4 * j + 1] += g.y; v[4 * j + 2] += g.z; v[4 * j + 3] += g.w;
+    }
+  }
+  epilogue_affine(v, p, sbias, gb, n0);
+  if (p.out_bf16) {
+    const uint32_t rbase = sbox + lane * 128;
+#pragma unroll
+    for (int pc = 0; pc < 4; ++pc) {
+      const uint32_t a = rbase + (((uint32_t)(pc + 4 * half) ^ (lane & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(v[pc * 8], v[pc * 8 + 1])),
+                   "r"(pack_bf16x2(v[pc * 8 + 2], v[pc * 8 + 3])), "r"(pack_bf16x2(v[pc * 8 + 4], v[pc * 8 + 5])),
+                   "r"(pack_bf16x2(v[pc * 8 + 6], v[pc * 8 + 7]))
+                   : "memory");
+    }
+  }
+  if (p.out_f32 && row_ok) {
+    float* o = p.out_f32 + (size_t)row * p.N + n0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      if (n0 + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  }
+  if (p.out_max || p.out_max_bf16) {
+    if (!row_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = -3.0e38f;
+    }
+    float m = warp_rows_max(v, lane);
+    if (p.max_relu) m = fmaxf(m, 0.f);
+    const size_t o = (size_t)(row0 >> 5) * p.N + n0 + lane;
+    if (n0 + lane < p.N) {
+      if (p.out_max) p.out_max[o] = m;
+      if (p.out_max_bf16) p.out_max_bf16[o] = __float2bfloat16_rn(m);
+    }
+  }
+}
+
+// the staged 32 x 64 bf16 box -> global, 4 whole 128-byte row segments per st.global.v4 instruction
+__device__ __forceinline__ void store_box(const TcParams& p, uint32_t sbox, int row0, int lane, int n0) {
+  const int pc = lane & 7, rsub = lane >> 3;
+  const int gcol = n0 + pc * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + rsub;
+    uint4 val;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                 : "r"(sbox + r * 128 + (((uint32_t)pc ^ (r & 7)) << 4)));
+    const int grow = row0 + r;
+    if (grow < p.M && gcol < p.N) *reinterpret_cast<uint4*>(p.out_bf16 + (size_t)grow * p.N + gcol) = val;
+  }
+}
+
+template <bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const TcParams p) {
+tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int TC_STAGES = p.stages, STAGE_BYTES = p.stage_bytes;   // stage s starts at s*STAGE_BYTES: A tile (16 KB), then the weight rows
   uint8_t* sA = smem;
-  uint8_t* sB = smem + TC_STAGES * TC_A_STAGE;
-  uint8_t* sC = smem + TC_SMEM_PIPE;                  // per-epilogue-warp store staging, 2 x 4 KB each
-  float* sbias = reinterpret_cast<float*>(sC + TC_EPI_WARPS * 2 * TC_STAGING);
-  uint64_t* full = reinterpret_cast<uint64_t*>(sC + TC_EPI_WARPS * 2 * TC_STAGING + TC_MAX_N * 4);
-  uint64_t* empty = full + TC_STAGES;
-  uint64_t* tfull = empty + TC_STAGES;
+  uint8_t* sB = smem + TC_A_STAGE;
+  uint8_t* sC = smem + TC_STAGES * p.stage_bytes;     // per-epilogue-warp store staging, 4 KB each
+  float* sbias = reinterpret_cast<float*>(sC + TC_EPI_WARPS * TC_WARP_SCRATCH);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sC + TC_EPI_WARPS * TC_WARP_SCRATCH + TC_MAX_N * 4);
+  uint64_t* empty = full + TC_MAX_STAGES;
+  uint64_t* tfull = empty + TC_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform role index
+  const int lane = threadIdx.x & 31;
+  const int CL = p.CL;
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
+  const int num_items = ((p.num_m_tiles + CL - 1) / CL) * p.num_n_tiles;   // (group of CL M tiles) x N tile
   const int num_kb = (p.K + TC_BK - 1) / TC_BK;
+  const uint16_t mc_mask = (uint16_t)((1u << CL) - 1);
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-    if (p.store_bf16) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], PAIR ? 1 : CL);   // multicast: every CTA of the cluster must have consumed the slot
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], TC_EPI_WARPS);
+      mbar_init(&tempty[b], PAIR ? 2 * TC_EPI_WARPS : TC_EPI_WARPS);   // pair: both CTAs' epilogues report to the leader
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < p.N; i += TC_THREADS) sbias[i] = p.bias ? p.bias[i] : 0.f;
-  if (warp == 1) {   // TMEM: 512 columns = two 128 x BN fp32 accumulators
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  if (warp == 1) {   // TMEM: 512 columns = two 128 x BN fp32 accumulators (this CTA's 128 rows)
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {   // ---------------- TMA producer
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx = TC_A_STAGE + (uint32_t)p.BN * TC_BK * 2;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], tx);
-          tma_load_2d(sA + stage * TC_A_STAGE, &tmA, &full[stage], kb * TC_BK, mt * TC_BM);
-          tma_load_2d(sB + stage * TC_B_STAGE, &tmB, &full[stage], kb * TC_BK, nt * p.BN);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+    // ---------------- TMA producer.  The whole warp runs the (warp-uniform) loop so that addresses and
+    // counters live in uniform registers; one elected lane issues the asynchronous copies.
+    const bool issuer = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    // bytes landing on this CTA's (pair: the leader's) full barrier per stage
+    const uint32_t tx = PAIR ? 2u * (TC_A_STAGE + (uint32_t)(p.BN / 2) * TC_BK * 2) : TC_A_STAGE + (uint32_t)p.BN * TC_BK * 2;
+    const int brows = p.BN / CL;     // rows of the weight tile this CTA fetches (and multicasts)
+    for (int item = cluster_id; item < num_items; item += num_clusters) {
+      const int mg = item / p.num_n_tiles, nt = item - mg * p.num_n_tiles;
+      const int mt = mg * CL + rank;   // may be a dummy tile past the end: TMA zero-fills, stores are clipped
+      if (p.prefetch && issuer) {
+        // pull the NEXT item's activation tile (streamed from HBM exactly once) into L2 ahead of its loads
+        const int nitem = item + num_clusters;
+        if (nitem < num_items) {
+          const int nmt = (nitem / p.num_n_tiles) * CL + rank;
+          if (nmt < p.num_m_tiles)
+            for (int kb = 0; kb < num_kb; ++kb) tma_prefetch_2d(&tmA, kb * TC_BK, nmt * TC_BM);
         }
+      }
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (issuer) {
+          if (kb == 0) tc_trace(p, (item - cluster_id) / num_clusters, 0, 0, clock64());
+          if (kb == num_kb - 1) tc_trace(p, (item - cluster_id) / num_clusters, 0, 1, clock64());
+          uint8_t* a_dst = sA + stage * STAGE_BYTES;
+          uint8_t* b_dst = sB + stage * STAGE_BYTES;
+          if (PAIR) {
+            if (rank == 0) mbar_expect_tx(&full[stage], tx);
+            tma_load_2d_pair(a_dst, &tmA, &full[stage], kb * TC_BK, mt * TC_BM);
+            tma_load_2d_pair(b_dst, &tmB, &full[stage], kb * TC_BK, nt * p.BN + rank * brows);
+          } else {
+            mbar_expect_tx(&full[stage], tx);
+            tma_load_2d(a_dst, &tmA, &full[stage], kb * TC_BK, mt * TC_BM);
+            if (CL == 1) tma_load_2d(b_dst, &tmB, &full[stage], kb * TC_BK, nt * p.BN);
+            else tma_load_2d_mc(b_dst + rank * brows * 128, &tmB, &full[stage], kb * TC_BK, nt * p.BN + rank * brows, mc_mask);
+          }
+        }
+        __syncwarp();
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {   // ---------------- MMA issuer
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    if (!PAIR || rank == 0) {
+      // ---------------- MMA issuer (pair: the leader issues for both SMs); warp-uniform loop, one elected lane
+      const bool issuer = elect_one();
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128 (256 across a pair)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
+                             ((uint32_t)((PAIR ? 2 * TC_BM : TC_BM) >> 4) << 24);
+      const uint64_t dconst = umma_desc_sw128(0);                 // everything but the start address
+      const uint32_t a_base = smem_u32(sA) >> 4, b_base = smem_u32(sB) >> 4, stage_step = (uint32_t)STAGE_BYTES >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
         const int buf = it & 1;
+        if (issuer) tc_trace(p, it, 1, 0, clock64());
         mbar_wait(&tempty[buf], ((uint32_t)(it >> 1) & 1) ^ 1);
+        if (issuer) tc_trace(p, it, 1, 1, clock64());
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.BN);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a0 = smem_u32(sA + stage * TC_A_STAGE), b0 = smem_u32(sB + stage * TC_B_STAGE);
+          if (issuer) {
+            if (kb == 0) tc_trace(p, it, 1, 2, clock64());
+            const uint64_t adesc = dconst | (uint64_t)(a_base + stage * stage_step);
+            const uint64_t bdesc = dconst | (uint64_t)(b_base + stage * stage_step);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k)
-            tc_mma(tmem_d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (uint32_t)((kb | k) != 0));
-          tc_commit(&empty[stage]);   // frees the smem stage once these MMAs have read it
+            for (int k = 0; k < TC_BK / 16; ++k) {   // +32 bytes (2 x 16 B units) per 16-wide K step inside the swizzle atom
+              if (PAIR) tc_mma_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+              else tc_mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+            }
+            if (PAIR) tc_commit_pair(&empty[stage]);      // frees the stage in both CTAs of the pair
+            else if (CL == 1) tc_commit(&empty[stage]);   // frees the smem stage once these MMAs have read it
+            else tc_commit_mc(&empty[stage], mc_mask);    // ... in every CTA that multicasts into it
+          }
+          __syncwarp();
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull[buf]);       // accumulator complete
+        if (issuer) {
+          if (PAIR) tc_commit_pair(&tfull[buf]);   // accumulator halves complete in both CTAs
+          else tc_commit(&tfull[buf]);             // accumulator complete
+          tc_trace(p, it, 1, 3, clock64());
+        }
+        __syncwarp();
       }
     }
   } else {             // ---------------- epilogue warps: TMEM lane quarter q, column-group parity h
     const int ew = warp - 2;
     const int q = warp & 3, h = ew >> 2;
-    uint8_t* stg = sC + ew * 2 * TC_STAGING;
-    int sbuf = 0;
+    uint8_t* stg = sC + ew * TC_WARP_SCRATCH;   // 128-byte aligned; the box swizzle is by row index, not by address
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
+    for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
+      const int mg = item / p.num_n_tiles, nt = item - mg * p.num_n_tiles;
+      const int mt = mg * CL + rank;
       const int buf = it & 1;
+      if (ew == 0 && lane == 0) tc_trace(p, it, 2, 0, clock64());
       mbar_wait(&tfull[buf], (uint32_t)(it >> 1) & 1);
+      if (ew == 0 && lane == 0) tc_trace(p, it, 2, 1, clock64());
       tc_fence_after();
       const int row0 = mt * TC_BM + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
       const float* gb = (p.gbias && row_ok) ? p.gbias + (size_t)(row / p.rows_per_group) * p.N : nullptr;
-      for (int gi = h; gi * 64 < p.BN; gi += 2) {
+      bool released = false;
+      // per-warp group-bias slice: when a patch (rows_per_group rows) covers whole warps, all 32 rows of this
+      // warp share one group-bias row, so the 64 values of a column group are fetched once, coalesced, BEFORE
+      // the accumulator load (latency overlaps it) and re-read from shared memory as broadcasts
+      const bool gb_shared = p.gbias && (p.rows_per_group % 32 == 0) && (row0 < p.M);
+      const float* gb_row = gb_shared ? p.gbias + (size_t)(row0 / p.rows_per_group) * p.N : nullptr;
+      float* sgb = reinterpret_cast<float*>(stg + TC_STAGING) ;   // 256 B per warp, right behind its staging box
+      for (int gi = h; gi * 64 < p.BN; gi += TC_EPI_PER_Q) {
         const int n0 = nt * p.BN + gi * 64;
         if (n0 >= p.N || row0 >= p.M) break;     // warp-uniform
-        float v0[32], v1[32];
+        float2 gpre = make_float2(0.f, 0.f);
+        if (gb_shared) {
+          const int c = min(n0 + 2 * lane, p.N - 2);
+          gpre = __ldg(reinterpret_cast<const float2*>(gb_row + c));
+        }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + gi * 64);
-        tc_ld32_issue(taddr, v0);
-        tc_ld32_issue(taddr + 32, v1);
-        tc_ld_wait();
-        epilogue_affine(v0, p, sbias, gb, n0);
-        epilogue_affine(v1, p, sbias, gb, n0 + 32);
-        if (p.store_bf16) {
-          // stage the 32 x 64 bf16 box in the 128B-swizzled layout the store tensor map expects, then one
-          // TMA store (clips rows >= M and columns >= N); double-buffered per warp
-          uint8_t* sb = stg + sbuf * TC_STAGING;
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        const uint32_t sbox = smem_u32(stg);
+        const bool last = (gi + TC_EPI_PER_Q >= (p.BN >> 6)) || (n0 + 64 * TC_EPI_PER_Q >= p.N);
+        float v[32];
+        tc_ld32_issue(taddr, v);
+        if (gb_shared) {
+          *reinterpret_cast<float2*>(sgb + 2 * lane) = gpre;
           __syncwarp();
-          const uint32_t rbase = smem_u32(sb) + lane * 128;
-#pragma unroll
-          for (int pc = 0; pc < 4; ++pc) {
-            const uint32_t a0 = rbase + (((uint32_t)pc ^ (lane & 7)) << 4);
-            const uint32_t a1 = rbase + (((uint32_t)(pc + 4) ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(pack_bf16x2(v0[pc * 8], v0[pc * 8 + 1])),
-                         "r"(pack_bf16x2(v0[pc * 8 + 2], v0[pc * 8 + 3])), "r"(pack_bf16x2(v0[pc * 8 + 4], v0[pc * 8 + 5])),
-                         "r"(pack_bf16x2(v0[pc * 8 + 6], v0[pc * 8 + 7]))
-                         : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(pack_bf16x2(v1[pc * 8], v1[pc * 8 + 1])),
-                         "r"(pack_bf16x2(v1[pc * 8 + 2], v1[pc * 8 + 3])), "r"(pack_bf16x2(v1[pc * 8 + 4], v1[pc * 8 + 5])),
-                         "r"(pack_bf16x2(v1[pc * 8 + 6], v1[pc * 8 + 7]))
-                         : "memory");
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        tc_ld_wait();
+        epilogue_half(p, sbias, gb_shared ? nullptr : gb, gb_shared ? sgb : nullptr, sbox, 0, row0, row, row_ok, lane, n0, v);
+        tc_ld32_issue(taddr + 32, v);
+        tc_ld_wait();
+        if (last) {
+          // this warp has read its last accumulator columns of the tile: hand the TMEM buffer back to the MMA
+          // warp now, before the remaining bias / convert / store work
+          tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                             reinterpret_cast<uint64_t>(&tmC)),
-                         "r"(smem_u32(sb)), "r"(n0), "r"(row0)
-                         : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (PAIR) mbar_arrive_cta(&tempty[buf], 0);
+            else mbar_arrive(&tempty[buf]);
           }
-          sbuf ^= 1;
+          released = true;
         }
-        if (p.out_f32 && row_ok) {
-          float* o = p.out_f32 + (size_t)row * p.N + n0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (n0 + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
-            if (n0 + 32 + j < p.N) *reinterpret_cast<float4*>(o + 32 + j) = make_float4(v1[j], v1[j + 1], v1[j + 2], v1[j + 3]);
-          }
+        epilogue_half(p, sbias, gb_shared ? nullptr : gb, gb_shared ? sgb : nullptr, sbox, 1, row0, row, row_ok, lane, n0 + 32, v);
+        if (p.out_bf16) {
+          __syncwarp();
+          store_box(p, sbox, row0, lane, n0);
         }
-        if (p.out_max || p.out_max_bf16) {
-          if (!row_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { v0[j] = -3.0e38f; v1[j] = -3.0e38f; }
-          }
-          float m0 = warp_rows_max(v0, lane), m1 = warp_rows_max(v1, lane);
-          if (p.max_relu) { m0 = fmaxf(m0, 0.f); m1 = fmaxf(m1, 0.f); }
-          const size_t grow = (size_t)(row0 >> 5) * p.N;
-          const int na = n0 + lane, nb = n0 + 32 + lane;
-          if (p.out_max) {
-            if (na < p.N) p.out_max[grow + na] = m0;
-            if (nb < p.N) p.out_max[grow + nb] = m1;
-          }
-          if (p.out_max_bf16) {
-            if (na < p.N) p.out_max_bf16[grow + na] = __float2bfloat16_rn(m0);
-            if (nb < p.N) p.out_max_bf16[grow + nb] = __float2bfloat16_rn(m1);
-          }
+        __syncwarp();   // staging box and group-bias slice are free for the next group
+      }
+      if (!released) {   // this warp had no group in the tile (narrow N tile or rows past M)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cta(&tempty[buf], 0);
+          else mbar_arrive(&tempty[buf]);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (ew == 0 && lane == 0) tc_trace(p, it, 2, 2, clock64());
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores of this warp are complete
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -435,32 +637,91 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
   if (M == 0) return P3TOK_OK;
   TcParams p;
   p.M = (int)M; p.N = N; p.K = K; p.BN = pick_bn(N);
+  // P3TOK_TC_CLUSTER: 1 = one CTA per tile; 2/4 = TMA multicast of the weight tile across a cluster;
+  // P3TOK_TC_PAIR=1 (default): CTA pairs with cta_group::2 MMAs (M = 256 per pair, weight tile split)
+  static int want_cl = 0, want_pair = -1;
+  if (!want_cl) {
+    const char* e = getenv("P3TOK_TC_CLUSTER");
+    want_cl = e ? atoi(e) : 1;
+    if (want_cl != 1 && want_cl != 2 && want_cl != 4) want_cl = 1;
+    const char* e2 = getenv("P3TOK_TC_PAIR");
+    want_pair = e2 ? atoi(e2) : 1;
+  }
+  const bool pair = want_pair && ((M + TC_BM - 1) / TC_BM) >= 2;
   p.num_m_tiles = (int)((M + TC_BM - 1) / TC_BM);
   p.num_n_tiles = (N + p.BN - 1) / p.BN;
   p.bias = bias; p.gbias = gbias; p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1; p.relu = relu;
-  p.store_bf16 = out_bf16 != nullptr; p.out_f32 = out_f32; p.out_max = out_max; p.out_max_bf16 = out_max_bf16; p.max_relu = max_relu;
-  CUtensorMap ta, tb, tc;
+  p.out_bf16 = out_bf16; p.out_f32 = out_f32; p.out_max = out_max; p.out_max_bf16 = out_max_bf16; p.max_relu = max_relu;
+  CUtensorMap ta, tb;
   int rc = make_map(&ta, A, M, K, TC_BM);
   if (rc) return rc;
-  rc = make_map(&tb, W, N, K, p.BN);
+  p.CL = pair ? 2 : want_cl;
+  while (p.CL > 1 && p.num_m_tiles < p.CL) p.CL /= 2;
+  rc = make_map(&tb, W, N, K, p.BN / p.CL);     // each CTA of a cluster fetches BN/CL rows of the weight tile
   if (rc) return rc;
-  if (out_bf16) {
-    rc = make_map(&tc, out_bf16, M, N, 32);     // store boxes: 64 columns x 32 rows
-    if (rc) return rc;
-  } else {
-    tc = ta;                                     // unused by the kernel
-  }
   static thread_local bool configured[32] = {false};
   int dev = 0;
   P3_CUDA(cudaGetDevice(&dev));
   if (dev < 32 && !configured[dev]) {
-    P3_CUDA(cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    P3_CUDA(cudaFuncSetAttribute(tc_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    P3_CUDA(cudaFuncSetAttribute(tc_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     configured[dev] = true;
   }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  tc_linear_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(ta, tb, tc, p);
-  P3_LAUNCH_CHECK("tc_linear_kernel");
+  {
+    const int wrows = pair ? p.BN / 2 : p.BN;
+    p.stage_bytes = TC_A_STAGE + wrows * TC_BK * 2;
+    p.stages = (TC_SMEM - TC_SMEM_FIXED) / p.stage_bytes;
+    if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+    static int cap = -1;
+    if (cap < 0) { const char* e = getenv("P3TOK_TC_STAGES"); cap = e ? atoi(e) : 0; }
+    if (cap > 1 && p.stages > cap) p.stages = cap;
+  }
+  static int prefetch_on = -1;
+  if (prefetch_on < 0) { const char* e = getenv("P3TOK_TC_PREFETCH"); prefetch_on = e ? atoi(e) : 1; }
+  p.prefetch = prefetch_on;
+  static int trace_on = -1;
+  if (trace_on < 0) trace_on = getenv("P3TOK_TC_TRACE") ? 1 : 0;
+  p.trace = nullptr;
+  const size_t trace_words = (size_t)num_sms() * 64 * 3 * 4;
+  if (trace_on) {
+    P3_CUDA(cudaMalloc(&p.trace, trace_words * 8));
+    P3_CUDA(cudaMemsetAsync(p.trace, 0, trace_words * 8, s));
+  }
+  const int items = ((p.num_m_tiles + p.CL - 1) / p.CL) * p.num_n_tiles;
+  const int max_clusters = num_sms() / p.CL;
+  const int clusters = items < max_clusters ? items : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * p.CL));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TC_SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)p.CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.CL > 1 ? 1 : 0;
+  if (pair) P3_CUDA(cudaLaunchKernelEx(&cfg, tc_linear_kernel<true>, ta, tb, p));
+  else P3_CUDA(cudaLaunchKernelEx(&cfg, tc_linear_kernel<false>, ta, tb, p));
+  count_launch();
+  if (trace_on) {   // debug only: synchronises and prints CTA 0's per-tile timeline (cycles relative to its first stamp)
+    std::vector<unsigned long long> h(trace_words);
+    P3_CUDA(cudaStreamSynchronize(s));
+    P3_CUDA(cudaMemcpy(h.data(), p.trace, trace_words * 8, cudaMemcpyDeviceToHost));
+    P3_CUDA(cudaFree(p.trace));
+    fprintf(stderr, "[tc_trace] M=%d N=%d K=%d BN=%d CL=%d grid=%d\n", p.M, p.N, p.K, p.BN, p.CL, clusters * p.CL);
+    for (int cta = 0; cta < 2; ++cta) {
+      const unsigned long long t0 = h[(((size_t)cta * 64 + 0) * 3 + 1) * 4 + 0];
+      for (int it = 0; it < 8; ++it) {
+        const unsigned long long* q = &h[(((size_t)cta * 64 + it) * 3) * 4];
+        if (!q[4]) break;
+        auto rel = [&](unsigned long long v) { return v ? (long long)(v - t0) : -1ll; };
+        fprintf(stderr, "[tc_trace] cta%d tile%d  tma[first=%lld last=%lld]  mma[start=%lld tempty_ok=%lld data_ok=%lld done_issue=%lld]  epi[wait=%lld tfull_ok=%lld released=%lld end=%lld]\n",
+                cta, it, rel(q[0]), rel(q[1]), rel(q[4]), rel(q[5]), rel(q[6]), rel(q[7]), rel(q[8]), rel(q[9]), rel(q[10]), rel(q[11]));
+      }
+    }
+  }
   return P3TOK_OK;
 }
 

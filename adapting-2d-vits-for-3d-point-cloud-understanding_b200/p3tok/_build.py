@@ -39,6 +39,10 @@ def _newer(target: str, deps: List[str]) -> bool:
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
+    extra = []
+    if os.environ.get("P3TOK_EPI_WARPS"):          # experiment knob: epilogue warps of tc_linear_kernel (8 or 16)
+        extra = ["-DP3TOK_EPI_WARPS=" + os.environ["P3TOK_EPI_WARPS"]]
+        force = True
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers += [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
     nvcc = _nvcc()
@@ -49,7 +53,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _newer(o, [s] + headers):
-            jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+            jobs.append([nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
