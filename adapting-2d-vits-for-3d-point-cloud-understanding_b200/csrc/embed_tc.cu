@@ -210,8 +210,9 @@ constexpr int TC_MAX_N = 2048;                       // bias vector staged in sh
 // is sized at launch to fill what is left: a stage round trip (TMA latency ~1500 cycles + MMA drain) needs
 // >= ingest_rate x latency bytes in flight, so the pair mode (32 KB stages) runs 5-6 stages deep.
 constexpr int TC_SMEM = 227 * 1024;
-constexpr int TC_WARP_SCRATCH = TC_STAGING + 256;    // store box + 64-float group-bias slice
-constexpr int TC_SMEM_FIXED = TC_EPI_WARPS * TC_WARP_SCRATCH + TC_MAX_N * 4 + 512 + 1024;
+constexpr int TC_WARP_SCRATCH = 2 * TC_STAGING;      // two 1024-aligned store boxes (double-buffered TMA stores)
+constexpr int TC_SGB_BYTES = 256;                    // per-warp 64-float group-bias slice
+constexpr int TC_SMEM_FIXED = TC_EPI_WARPS * (TC_WARP_SCRATCH + TC_SGB_BYTES) + TC_MAX_N * 4 + 512 + 1024;
 
 struct TcParams {
   int M, N, K, BN;
@@ -328,33 +329,19 @@ __device__ __forceinline__ void epilogue_half(const TcParams& p, const float* sb
   }
 }
 
-// the staged 32 x 64 bf16 box -> global, 4 whole 128-byte row segments per st.global.v4 instruction
-__device__ __forceinline__ void store_box(const TcParams& p, uint32_t sbox, int row0, int lane, int n0) {
-  const int pc = lane & 7, rsub = lane >> 3;
-  const int gcol = n0 + pc * 8;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + rsub;
-    uint4 val;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
-                 : "r"(sbox + r * 128 + (((uint32_t)pc ^ (r & 7)) << 4)));
-    const int grow = row0 + r;
-    if (grow < p.M && gcol < p.N) *reinterpret_cast<uint4*>(p.out_bf16 + (size_t)grow * p.N + gcol) = val;
-  }
-}
-
 template <bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int TC_STAGES = p.stages, STAGE_BYTES = p.stage_bytes;   // stage s starts at s*STAGE_BYTES: A tile (16 KB), then the weight rows
   uint8_t* sA = smem;
   uint8_t* sB = smem + TC_A_STAGE;
   uint8_t* sC = smem + TC_STAGES * p.stage_bytes;     // per-epilogue-warp store staging, 4 KB each
-  float* sbias = reinterpret_cast<float*>(sC + TC_EPI_WARPS * TC_WARP_SCRATCH);
-  uint64_t* full = reinterpret_cast<uint64_t*>(sC + TC_EPI_WARPS * TC_WARP_SCRATCH + TC_MAX_N * 4);
+  float* sgb_all = reinterpret_cast<float*>(sC + TC_EPI_WARPS * TC_WARP_SCRATCH);
+  float* sbias = reinterpret_cast<float*>(sC + TC_EPI_WARPS * (TC_WARP_SCRATCH + TC_SGB_BYTES));
+  uint64_t* full = reinterpret_cast<uint64_t*>(sC + TC_EPI_WARPS * (TC_WARP_SCRATCH + TC_SGB_BYTES) + TC_MAX_N * 4);
   uint64_t* empty = full + TC_MAX_STAGES;
   uint64_t* tfull = empty + TC_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
@@ -490,7 +477,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {             // ---------------- epilogue warps: TMEM lane quarter q, column-group parity h
     const int ew = warp - 2;
     const int q = warp & 3, h = ew >> 2;
-    uint8_t* stg = sC + ew * TC_WARP_SCRATCH;   // 128-byte aligned; the box swizzle is by row index, not by address
+    uint8_t* stg = sC + ew * TC_WARP_SCRATCH;   // 1024-aligned: the TMA store un-swizzles by address bits
+    int sbuf = 0;
     int it = 0;
     for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
       const int mg = item / p.num_n_tiles, nt = item - mg * p.num_n_tiles;
@@ -510,7 +498,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // the accumulator load (latency overlaps it) and re-read from shared memory as broadcasts
       const bool gb_shared = p.gbias && (p.rows_per_group % 32 == 0) && (row0 < p.M);
       const float* gb_row = gb_shared ? p.gbias + (size_t)(row0 / p.rows_per_group) * p.N : nullptr;
-      float* sgb = reinterpret_cast<float*>(stg + TC_STAGING) ;   // 256 B per warp, right behind its staging box
+      float* sgb = sgb_all + ew * (TC_SGB_BYTES / 4);
       for (int gi = h; gi * 64 < p.BN; gi += TC_EPI_PER_Q) {
         const int n0 = nt * p.BN + gi * 64;
         if (n0 >= p.N || row0 >= p.M) break;     // warp-uniform
@@ -520,7 +508,11 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           gpre = __ldg(reinterpret_cast<const float2*>(gb_row + c));
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + gi * 64);
-        const uint32_t sbox = smem_u32(stg);
+        const uint32_t sbox = smem_u32(stg + sbuf * TC_STAGING);
+        if (p.out_bf16) {   // the TMA store issued two groups ago has finished reading this box
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+        }
         const bool last = (gi + TC_EPI_PER_Q >= (p.BN >> 6)) || (n0 + 64 * TC_EPI_PER_Q >= p.N);
         float v[32];
         tc_ld32_issue(taddr, v);
@@ -545,10 +537,19 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         epilogue_half(p, sbias, gb_shared ? nullptr : gb, gb_shared ? sgb : nullptr, sbox, 1, row0, row, row_ok, lane, n0 + 32, v);
         if (p.out_bf16) {
+          // one TMA store of the 32 x 64 bf16 box (clips rows >= M / columns >= N)
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          store_box(p, sbox, row0, lane, n0);
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmC)),
+                         "r"(sbox), "r"(n0), "r"(row0)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          sbuf ^= 1;
         }
-        __syncwarp();   // staging box and group-bias slice are free for the next group
+        __syncwarp();   // group-bias slice is free for the next group
       }
       if (!released) {   // this warp had no group in the tile (narrow N tile or rows past M)
         tc_fence_before();
@@ -560,6 +561,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (ew == 0 && lane == 0) tc_trace(p, it, 2, 2, clock64());
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this warp's stores are complete
   }
   tc_fence_before();
   __syncthreads();
@@ -652,13 +654,19 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
   p.num_n_tiles = (N + p.BN - 1) / p.BN;
   p.bias = bias; p.gbias = gbias; p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1; p.relu = relu;
   p.out_bf16 = out_bf16; p.out_f32 = out_f32; p.out_max = out_max; p.out_max_bf16 = out_max_bf16; p.max_relu = max_relu;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc;
   int rc = make_map(&ta, A, M, K, TC_BM);
   if (rc) return rc;
   p.CL = pair ? 2 : want_cl;
   while (p.CL > 1 && p.num_m_tiles < p.CL) p.CL /= 2;
   rc = make_map(&tb, W, N, K, p.BN / p.CL);     // each CTA of a cluster fetches BN/CL rows of the weight tile
   if (rc) return rc;
+  if (out_bf16) {
+    rc = make_map(&tc, out_bf16, M, N, 32);     // store boxes: 64 columns x 32 rows
+    if (rc) return rc;
+  } else {
+    tc = ta;                                     // unused by the kernel
+  }
   static thread_local bool configured[32] = {false};
   int dev = 0;
   P3_CUDA(cudaGetDevice(&dev));
@@ -702,8 +710,8 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = p.CL > 1 ? 1 : 0;
-  if (pair) P3_CUDA(cudaLaunchKernelEx(&cfg, tc_linear_kernel<true>, ta, tb, p));
-  else P3_CUDA(cudaLaunchKernelEx(&cfg, tc_linear_kernel<false>, ta, tb, p));
+  if (pair) P3_CUDA(cudaLaunchKernelEx(&cfg, tc_linear_kernel<true>, ta, tb, tc, p));
+  else P3_CUDA(cudaLaunchKernelEx(&cfg, tc_linear_kernel<false>, ta, tb, tc, p));
   count_launch();
   if (trace_on) {   // debug only: synchronises and prints CTA 0's per-tile timeline (cycles relative to its first stamp)
     std::vector<unsigned long long> h(trace_words);
