@@ -262,29 +262,37 @@ def run_p3tok(args, w, rank, world, local_rank):
         dev_ms = e0.elapsed_time(e1)
         launches = ops.kernel_launches() - launches0
 
-        # ---- e2e: host buffers in, host tokens out, through the public module call.  Serving-style pipeline:
-        # step i's token D2H (copy stream) overlaps step i+1's H2D + kernels (compute stream); both copies are
-        # inside the timed region every step, from / to pinned host memory.
+        # ---- e2e: host buffers in, host tokens out, through the public serving API (p3tok.graph.GraphedTokenizer:
+        # the module call captured once into a CUDA graph).  Every step copies the clouds and start indices from
+        # pinned host memory into the graph's input buffers, replays, and copies the tokens back to pinned host
+        # memory; the D2H of step i (copy stream) overlaps the H2D + kernels of step i+1 (two graph instances so
+        # that an output buffer is not overwritten while it is being copied out).
+        from p3tok.graph import GraphedTokenizer
         copy_stream = torch.cuda.Stream(device=device)
-        out_host = [torch.empty(out.shape, dtype=out.dtype).pin_memory() for _ in range(2)]
-        x_dev = [torch.empty_like(base) for _ in range(2)]
-        st_dev = [[torch.empty_like(s, device=device) for s in st_host] for _ in range(2)]
+        graphs = [GraphedTokenizer(lambda x, *st: run(x, list(st)), [base] + st_pool[0]) for _ in range(2)]
+        out_host = [torch.empty(graphs[0].output.shape, dtype=graphs[0].output.dtype).pin_memory() for _ in range(2)]
+        copied = [torch.cuda.Event() for _ in range(2)]
 
         def e2e_step(i):
             b = i & 1
-            x_dev[b].copy_(x_host, non_blocking=True)
-            for d, s in zip(st_dev[b], st_host):
+            g = graphs[b]
+            torch.cuda.current_stream().wait_event(copied[b])      # output buffer b has been copied out
+            g.inputs[0].copy_(x_host, non_blocking=True)
+            for d, s in zip(g.inputs[1:], st_host):
                 d.copy_(s, non_blocking=True)
-            o = run(x_dev[b], st_dev[b])
+            o = g.replay()
             done = torch.cuda.Event()
             done.record()
-            o.record_stream(copy_stream)
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(done)
-                out_host[b].copy_(o, non_blocking=True)     # in order on the copy stream: buffer b is reused 2 steps later
+                out_host[b].copy_(o, non_blocking=True)
+                copied[b].record()
 
-        for i in range(2):
+        for b in range(2):
+            copied[b].record()
+        for i in range(4):
             e2e_step(i)
+        copy_stream.synchronize()
         barrier()
         t0 = time.perf_counter()
         for i in range(args.steps):
@@ -292,6 +300,8 @@ def run_p3tok(args, w, rank, world, local_rank):
         copy_stream.synchronize()
         barrier()
         e2e_ms = 1e3 * (time.perf_counter() - t0)
+        # the graph path returns the same tokens as the eager path
+        assert torch.equal(graphs[0](pool[0], *st_pool[0]), run(pool[0], st_pool[0])), "graph replay != eager"
         clocks = sampler.stop() if rank == 0 else None
 
         # ---- per-stage device times (separate pass, not part of the timed region)

@@ -173,3 +173,18 @@ def test_bf16_path_matches_its_arithmetic_model(E, k, cin):
     model = bf16_emulation(fold.fold_apf_encoder(sd), rows, k)
     err = float((tok - model).abs().max() / model.abs().max())
     assert err < 2e-3, err
+
+
+def test_cuda_graph_replay_matches_eager():
+    """The serving wrapper: one tokenizer call captured into a CUDA graph returns the eager result bit-for-bit,
+    also after the inputs change."""
+    from p3tok.graph import GraphedTokenizer
+    B, N, G, k, E = 8, 1024, 64, 32, 128
+    net = PointNet(E, G, k, 6, precision="bf16" if _bf16_ready() else "fp32").eval().to(dev())
+    net.encoder.load_state_dict(synth.to_torch_state(synth.apf_encoder_state(E, 6, 3)))
+    x0, x1 = (to_dev(synth.make_cloud("uniform", B, N, s, 3)) for s in (1, 2))
+    s0, s1 = (to_dev(synth.start_indices(B, N, s)) for s in (1, 2))
+    g = GraphedTokenizer(lambda x, st: net(x, st), [x0, s0])
+    assert torch.equal(g(x0, s0), net(x0, s0))
+    assert torch.equal(g(x1, s1), net(x1, s1))
+    assert torch.equal(g(x0, s0), net(x0, s0))
