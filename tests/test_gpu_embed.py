@@ -188,3 +188,26 @@ def test_cuda_graph_replay_matches_eager():
     assert torch.equal(g(x0, s0), net(x0, s0))
     assert torch.equal(g(x1, s1), net(x1, s1))
     assert torch.equal(g(x0, s0), net(x0, s0))
+
+
+def test_fused_pair_kernel_matches_layerwise(monkeypatch):
+    """embed_fused.cu (two layers per kernel, hidden activation kept on-chip; opt-in via P3TOK_FUSED=1) against the
+    default layer-by-layer tensor-core path: same bf16 arithmetic, different accumulation grouping."""
+    _skip_if_unbuilt("bf16")
+    import subprocess, sys, os
+    code = (
+        "import sys, os; sys.path.insert(0, os.path.join(os.getcwd(), 'adapting-2d-vits-for-3d-point-cloud-understanding_b200'));"
+        "import torch; from p3tok import synth; from p3tok.modules import PointNet;"
+        "net = PointNet(384, 64, 32, 6, precision='bf16').eval().cuda();"
+        "net.encoder.load_state_dict(synth.to_torch_state(synth.apf_encoder_state(384, 6, 9)));"
+        "x = torch.from_numpy(synth.make_cloud('clustered', 4, 1024, 9, 3)).cuda();"
+        "st = torch.from_numpy(synth.start_indices(4, 1024, 9)).cuda();"
+        "torch.save(net(x, st).cpu(), sys.argv[1])")
+    outs = []
+    for flag in ("0", "1"):
+        path = f"/tmp/p3tok_fused_{flag}.pt"
+        env = dict(os.environ, P3TOK_FUSED=flag)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        outs.append(torch.load(path))
+    err = float((outs[0] - outs[1]).abs().max() / outs[0].abs().max())
+    assert err < 3e-3, err
