@@ -559,6 +559,67 @@ rows_first_layer_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, const __nv
   }
 }
 
+// APF rows whose 32-row block lies inside one patch (k % 32 == 0): the input is [nbr - ctr || ctr], and the centre
+// half is the same for all 32 rows, so its contribution W[:, C:2C].ctr + bias is formed once per block and each
+// row costs C (3 or 4) FMAs per output channel instead of 2C (apf.py:83-95 feeding apf.py:130).
+template <typename IdxT>
+__global__ void __launch_bounds__(128)
+rows_first_layer_apf_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, const __nv_bfloat16* __restrict__ W,
+                            const float* __restrict__ bias, int nout, int relu, __nv_bfloat16* __restrict__ out) {
+  __shared__ __align__(16) float rel[32][4];
+  __shared__ float ctr[4];
+  const int C = R.C, cin = 2 * C;
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const IdxT* knn = reinterpret_cast<const IdxT*>(R.knn_idx);
+  const int64_t bj = g_begin + r0 / R.k;               // output group of the whole block
+  const int64_t b = bj / R.G;
+  const int64_t g = R.perm ? R.perm[bj] : (bj - b * R.G);
+  const float* crow = R.x + (b * R.N + R.ctr_idx[b * R.G + g]) * C;
+  if (threadIdx.x < 32) {
+    const int64_t r = r0 + threadIdx.x;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < nrows) {
+      const int64_t ni = (int64_t)knn[(b * R.G + g) * R.k + (r % R.k)];
+      const float* prow = R.x + (b * R.N + ni) * C;
+      v.x = __fsub_rn(prow[0], crow[0]);
+      v.y = __fsub_rn(prow[1], crow[1]);
+      v.z = __fsub_rn(prow[2], crow[2]);
+      if (C == 4) v.w = __fsub_rn(prow[3], crow[3]);
+    }
+    *reinterpret_cast<float4*>(&rel[threadIdx.x][0]) = v;
+  } else if (threadIdx.x < 36) {
+    const int c = threadIdx.x - 32;
+    ctr[c] = c < C ? crow[c] : 0.f;
+  }
+  __syncthreads();
+  for (int n0 = threadIdx.x * 2; n0 < nout; n0 += 256) {
+    float w0[4], w1[4];
+    float base0 = bias ? bias[n0] : 0.f, base1 = bias ? bias[n0 + 1] : 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const bool ok = c < C;
+      w0[c] = ok ? __bfloat162float(W[(size_t)n0 * cin + c]) : 0.f;
+      w1[c] = ok ? __bfloat162float(W[(size_t)(n0 + 1) * cin + c]) : 0.f;
+      if (ok) {
+        base0 = fmaf(__bfloat162float(W[(size_t)n0 * cin + C + c]), ctr[c], base0);
+        base1 = fmaf(__bfloat162float(W[(size_t)(n0 + 1) * cin + C + c]), ctr[c], base1);
+      }
+    }
+#pragma unroll 4
+    for (int rr = 0; rr < 32; ++rr) {
+      const int64_t r = r0 + rr;
+      if (r >= nrows) break;
+      const float4 xv = *reinterpret_cast<const float4*>(&rel[rr][0]);   // warp-wide broadcast
+      float a0 = fmaf(w0[0], xv.x, base0), a1 = fmaf(w1[0], xv.x, base1);
+      a0 = fmaf(w0[1], xv.y, a0); a1 = fmaf(w1[1], xv.y, a1);
+      a0 = fmaf(w0[2], xv.z, a0); a1 = fmaf(w1[2], xv.z, a1);
+      a0 = fmaf(w0[3], xv.w, a0); a1 = fmaf(w1[3], xv.w, a1);
+      if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+      *reinterpret_cast<__nv_bfloat162*>(out + r * nout + n0) = __floats2bfloat162_rn(a0, a1);
+    }
+  }
+}
+
 // Wide input: gather rows to bf16 [nrows, kpad], zero padded
 template <typename IdxT>
 __global__ void rows_gather_bf16_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, int cin, int kpad,
@@ -735,7 +796,14 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
 #define P3_L1(IDX, CPV)                                                                                        \
   rows_first_layer_kernel<IDX, CPV><<<blocks, 128, 0, s>>>(*R, g0, rows, (const __nv_bfloat16*)m->w_pre[0],    \
                                                            m->b_pre[0], m->cin, m->pre_dim[0], m->pre_relu[0], act[cur])
-      if (m->cin <= 8) { if (i64) P3_L1(int64_t, 8); else P3_L1(int32_t, 8); }
+      static int apf_split = -1;
+      if (apf_split < 0) { const char* e = getenv("P3TOK_L1_SPLIT"); apf_split = e ? atoi(e) : 1; }
+      if (apf_split && R->kind == 0 && k % 32 == 0 && (R->C == 3 || R->C == 4) && m->pre_dim[0] % 2 == 0) {
+        if (i64) rows_first_layer_apf_kernel<int64_t><<<blocks, 128, 0, s>>>(*R, g0, rows, (const __nv_bfloat16*)m->w_pre[0],
+                                                                          m->b_pre[0], m->pre_dim[0], m->pre_relu[0], act[cur]);
+        else rows_first_layer_apf_kernel<int32_t><<<blocks, 128, 0, s>>>(*R, g0, rows, (const __nv_bfloat16*)m->w_pre[0],
+                                                                         m->b_pre[0], m->pre_dim[0], m->pre_relu[0], act[cur]);
+      } else if (m->cin <= 8) { if (i64) P3_L1(int64_t, 8); else P3_L1(int32_t, 8); }
       else             { if (i64) P3_L1(int64_t, 16); else P3_L1(int32_t, 16); }
 #undef P3_L1
       P3_LAUNCH_CHECK("rows_first_layer_kernel");
