@@ -167,7 +167,7 @@ class ClockSampler:
                     self.samples.append(f)
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05)
 
     def start(self):
         self.th = threading.Thread(target=self._loop, daemon=True)
@@ -359,7 +359,10 @@ def run_p3tok(args, w, rank, world, local_rank):
         "stage_ms_per_step": {k: round(v, 4) for k, v in sorted(stage_ms.items())},
         "roofline": {"bound": "tensor", "kernel": "patch embedding (p3tok_patch_embed)",
                      "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": (ach_tf / peak_tf) if ach_tf else None, "traffic": None,
+                     "frac": (ach_tf / peak_tf) if ach_tf else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of the embed launches of one step, from the ncu
+                     # --set full capture summarised in profiles/r01_c2_ncu_full.txt (c2 / bf16 only)
+                     "traffic": 3.72e9 if (args.workload == "c2" and precision == "bf16") else None,
                      "peak_source": f"{pk['source']} bf16 sustained (MEASURED_PEAKS.json)",
                      "algorithmic_flops_per_launch_group": work["embed_flops"] * B,
                      "as_written_flops": work["embed_flops_as_written"] * B, "duration_ms": embed_ms},
