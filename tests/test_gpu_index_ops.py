@@ -150,3 +150,38 @@ def test_full_size_properties_c2_and_c4():
         assert np.array_equal(nn_idx[sub, :64].cpu().numpy(),
                               oracle.knn(x[sub], ctr[sub, :64].cpu().numpy(), k, oracle.KNN_APF_SQ))
         assert np.array_equal(idx[sub].cpu().numpy(), oracle.fps(x[sub], st[sub].cpu().numpy(), G))
+
+
+def test_randomised_shapes_against_oracle():
+    """Seeded sweep over ragged shapes (N, G, k not multiples of the tile sizes; 3- and 4-channel rows; all three
+    cloud kinds): FPS, both kNN flavours, Morton order and APF grouping stay bit-exact against the oracle."""
+    rng = np.random.RandomState(20261018)
+    kinds = ["uniform", "clustered", "duplicates"]
+    for trial in range(24):
+        B = int(rng.randint(1, 5))
+        N = int(rng.choice([17, 63, 129, 500, 1025, 3000, 8200, 12345]))
+        G = int(rng.randint(1, min(N, 300) + 1))
+        k = int(rng.randint(1, min(N, 128) + 1))
+        C = int(rng.choice([3, 4]))
+        kind = kinds[trial % 3]
+        x = synth.make_cloud(kind, B, N, 1000 + trial, 3)
+        if C == 4:
+            x = np.concatenate([x, x[..., 1:2] - x[..., 1:2].min(1, keepdims=True)], -1).astype(np.float32)
+        st = synth.start_indices(B, N, trial)
+        xt = to_dev(x)
+        fidx = ops.fps(xt, to_dev(st), G)
+        assert np.array_equal(fidx.cpu().numpy(), oracle.fps(x, st, G)), (trial, "fps", B, N, G, C)
+        ctr = ops.gather_points(xt, fidx)[..., :3].contiguous()
+        for mode in (oracle.KNN_APF_SQ, oracle.KNN_P4P_CDIST):
+            idx, dist = ops.knn(xt, ctr, k, mode, mode == 1, True)
+            oi, od = oracle.knn(x, ctr.cpu().numpy(), k, mode, return_dist=True)
+            assert np.array_equal(idx.cpu().numpy().astype(np.int64), oi), (trial, "knn", mode, B, N, G, k, C)
+            assert np.array_equal(dist.cpu().numpy(), od), (trial, "dist", mode)
+        perm, codes = ops.morton_order(ctr)
+        oc, op_ = oracle.morton(ctr.cpu().numpy())
+        assert np.array_equal(perm.cpu().numpy(), op_) and np.array_equal(codes.cpu().numpy(), oc), (trial, "morton")
+        if k <= 32 and G <= 64:
+            kidx = ops.knn(xt, ctr, k, _lib.KNN_APF_SQ, False, False)[0]
+            neigh, center = ops.apf_group(xt.contiguous(), fidx, kidx, perm)
+            o = oracle.group_apf(x, st, G, k)
+            assert np.array_equal(neigh.cpu().numpy(), o["neigh"]) and np.array_equal(center.cpu().numpy(), o["center"]), (trial, "group")
