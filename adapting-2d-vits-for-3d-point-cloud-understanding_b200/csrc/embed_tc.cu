@@ -517,7 +517,8 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
 template <typename IdxT, int CP>   // CP = padded input width (8 or 16)
 __global__ void __launch_bounds__(128)
 rows_first_layer_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, const __nv_bfloat16* __restrict__ W,
-                        const float* __restrict__ bias, int cin, int nout, int relu, __nv_bfloat16* __restrict__ out) {
+                        const float* __restrict__ bias, int cin, int nout, int relu, __nv_bfloat16* __restrict__ out,
+                        __nv_bfloat16* __restrict__ gmax32) {   // gmax32: optional max over each block of 32 rows
   __shared__ __align__(16) float xin[32][CP];
   const int64_t r0 = (int64_t)blockIdx.x * 32;
   const IdxT* knn = reinterpret_cast<const IdxT*>(R.knn_idx);
@@ -553,6 +554,7 @@ rows_first_layer_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, const __nv
       w1[c] = (c < cin && n0 + 1 < nout) ? __bfloat162float(W[(size_t)(n0 + 1) * cin + c]) : 0.f;
     }
     const float b0 = bias ? bias[n0] : 0.f, b1 = (bias && n0 + 1 < nout) ? bias[n0 + 1] : 0.f;
+    float m0 = -3.0e38f, m1 = -3.0e38f;
     for (int rr = 0; rr < 32; ++rr) {
       const int64_t r = r0 + rr;
       if (r >= nrows) break;
@@ -566,8 +568,12 @@ rows_first_layer_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, const __nv
         a0 = fmaf(w0[c4 + 3], xv.w, a0); a1 = fmaf(w1[c4 + 3], xv.w, a1);
       }
       if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+      m0 = fmaxf(m0, a0); m1 = fmaxf(m1, a1);
       *reinterpret_cast<__nv_bfloat162*>(out + r * nout + n0) = __floats2bfloat162_rn(a0, a1);
     }
+    // the block is one k = 32 patch: its max-pool is thread-local (bf16 rounding is monotonic, so rounding the
+    // fp32 max equals the max of the rounded activations the next GEMM reads)
+    if (gmax32) *reinterpret_cast<__nv_bfloat162*>(gmax32 + (r0 >> 5) * nout + n0) = __floats2bfloat162_rn(m0, m1);
   }
 }
 
@@ -805,9 +811,11 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
     int kin;
     if (!L.kpad0) {
       const unsigned blocks = (unsigned)((rows + 31) / 32);
+      // single per-point layer (P3Embed stage 0) with k = 32: the first-layer kernel also emits the patch max
+      __nv_bfloat16* l1_gmax = (m->n_pre == 1 && k == 32 && m->pre_dim[0] % 2 == 0) ? gmax_bf16 : nullptr;
 #define P3_L1(IDX, CPV)                                                                                        \
   rows_first_layer_kernel<IDX, CPV><<<blocks, 128, 0, s>>>(*R, g0, rows, (const __nv_bfloat16*)m->w_pre[0],    \
-                                                           m->b_pre[0], m->cin, m->pre_dim[0], m->pre_relu[0], act[cur])
+                                                           m->b_pre[0], m->cin, m->pre_dim[0], m->pre_relu[0], act[cur], l1_gmax)
       static int apf_split = -1;
       if (apf_split < 0) { const char* e = getenv("P3TOK_L1_SPLIT"); apf_split = e ? atoi(e) : 1; }
       if (apf_split && R->kind == 0 && k % 32 == 0 && (R->C == 3 || R->C == 4) && m->pre_dim[0] % 2 == 0) {
@@ -882,6 +890,7 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
       cur ^= 1;
       kin = m->pre_dim[i];
     }
+    if (!have_gmax && !L.kpad0 && m->n_pre == 1 && k == 32 && m->pre_dim[0] % 2 == 0) have_gmax = true;   // emitted by the first-layer kernel
     if (!have_gmax) {
       // the block's only per-point layer ran on CUDA cores (P3Embed stage 0): reduce its bf16 output
       group_max_bf16_kernel<<<grid_1d(gc * L.F, 256), 256, 0, s>>>(act[cur], gc, (int)k, (int)L.F, gmax_bf16);
