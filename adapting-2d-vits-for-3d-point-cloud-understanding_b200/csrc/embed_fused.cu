@@ -50,7 +50,12 @@ struct FusedParams {
   float* out_max;                   // [M/32, N2] or null
   __nv_bfloat16* out_max_bf16;      // same, bf16, or null
   int max_relu;
+  unsigned long long* trace;        // debug (P3TOK_TC_TRACE=1): pair 0's timeline (leader MMA warp + one epilogue warp of each kind)
 };
+// trace[(it * 16 + j) * 16 + slot]; slots 0-7 MMA warp, 8-11 chunk-epilogue warp 2, 12-15 tile-epilogue warp 10 (leader CTA)
+__device__ __forceinline__ void fu_trace(const FusedParams& p, int it, int j, int slot, long long v) {
+  if (p.trace && blockIdx.x == 0 && it < 4 && j < 16) p.trace[((size_t)it * 16 + j) * 16 + slot] = (unsigned long long)v;
+}
 
 __global__ void __launch_bounds__(FU_THREADS, 1)
 tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWa,
@@ -202,18 +207,25 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         ++gc;
       };
       for (int tp = pair_id; tp < p.num_pairs; tp += pair_stride, ++it) {
+        if (issuer) fu_trace(p, it, 0, 4, clock64());             // tile start
         mbar_wait(a0_full, (uint32_t)(it & 1));
+        if (issuer) fu_trace(p, it, 0, 5, clock64());             // A0 present
         tc_fence_after();
         issue_A(NC == 1);
+        if (issuer) fu_trace(p, it, 0, 6, clock64());             // A(0) issued
         for (int j = 0; j < NC; ++j) {
           if (j + 1 < NC) issue_A(j + 1 == NC - 1);
           // B(j): output accumulator += chunk(j) . W_b[:, chunk j]^T, one MMA group per quarter of the output columns
           const uint32_t b = gcb & 1;
+          if (issuer) fu_trace(p, it, j, 0, clock64());           // A(j+1) issued
           mbar_wait(&ch_full[b], (gcb >> 1) & 1);
+          if (issuer) fu_trace(p, it, j, 1, clock64());           // chunk j operand ready
           if (j == 0) mbar_wait(acc3_empty, (uint32_t)(it & 1) ^ 1);
           tc_fence_after();
           for (int qd = 0; qd < NQ; ++qd) {
             mbar_wait(&rb_full[rbs], rbph);
+            if (issuer && qd == 0) fu_trace(p, it, j, 2, clock64());   // first W_b box present
+            if (issuer && qd == 3) fu_trace(p, it, j, 3, clock64());   // last W_b box present
             tc_fence_after();
             if (issuer) {
               const uint64_t ad = dconst | (uint64_t)(ch_base + b * (16384 >> 4));
@@ -227,6 +239,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (++rbs == p.rb_slots) { rbs = 0; rbph ^= 1; }
           }
           if (issuer) {
+            fu_trace(p, it, j, 7, clock64());                       // B(j) issued
             tc_commit_pair(&ch_empty[b]);
             if (j == NC - 1) tc_commit_pair(acc3_full);
           }
@@ -243,7 +256,9 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int trow = q * 32 + lane;                 // row inside this CTA's 128-row tile
     float* my_sgb = sgb + ew * 32;
     uint32_t gc = 0;
-    for (int tp = pair_id; tp < p.num_pairs; tp += pair_stride) {
+    int itc = 0;
+    const bool tr = (warp == 2 && lane == 0);
+    for (int tp = pair_id; tp < p.num_pairs; tp += pair_stride, ++itc) {
       const int row0 = (2 * tp + rank) * TC_BM + q * 32;
       const float* gb_row = (p.gbias && row0 < p.M) ? p.gbias + (size_t)(row0 / p.rows_per_group) * p.N1 : nullptr;
       for (int j = 0; j < NC; ++j, ++gc) {
@@ -251,7 +266,9 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int c0 = j * FU_CHUNK + h * 32;
         float gpre = 0.f;
         if (gb_row) gpre = __ldg(gb_row + c0 + lane);   // coalesced 128 B, overlaps the wait below
+        if (tr) fu_trace(p, itc, j, 8, clock64());                // waiting for the chunk accumulator
         mbar_wait(&acc2_full[b], (gc >> 1) & 1);
+        if (tr) fu_trace(p, itc, j, 9, clock64());                // accumulator ready
         tc_fence_after();
         float v[32];
         tc_ld32_issue(tmem_base + lane_field + FU_ACC2_COL + b * FU_CHUNK + h * 32, v);
@@ -277,6 +294,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        if (tr) fu_trace(p, itc, j, 10, clock64());               // converted, waiting for the operand buffer
         mbar_wait(&ch_empty[b], ((gc >> 1) & 1) ^ 1);     // the B-GEMM that read this buffer two chunks ago is done
         const uint32_t rbase = smem_u32(sCH) + b * 16384 + trow * 128;
 #pragma unroll
@@ -290,6 +308,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive_cta(&ch_full[b], 0);
+        if (tr) fu_trace(p, itc, j, 11, clock64());               // operand published
       }
     }
   } else {
@@ -304,7 +323,10 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int row0 = (2 * tp + rank) * TC_BM + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
+      const bool tr = (warp == 2 + FU_CH_WARPS && lane == 0);
+      if (tr) fu_trace(p, it, 0, 12, clock64());
       mbar_wait(acc3_full, (uint32_t)(it & 1));
+      if (tr) fu_trace(p, it, 0, 13, clock64());
       tc_fence_after();
       bool released = false;
       for (int gi = h; gi < ngroups; gi += 2) {
@@ -319,6 +341,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cta(acc3_empty, 0);      // the next tile's B-GEMM may overwrite the accumulator
+            if (tr) fu_trace(p, it, 0, 14, clock64());
             released = true;
           }
 #pragma unroll
@@ -368,6 +391,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
         }
       }
+      if (tr) fu_trace(p, it, 0, 15, clock64());
       if (!released) {   // (N2 == 64: the h = 1 warps have no output group) still hand the accumulator back
         tc_fence_before();
         __syncwarp();
@@ -440,6 +464,14 @@ int tc_fused(const __nv_bfloat16* A0, int64_t M, int K0, const __nv_bfloat16* Wa
     P3_CUDA(cudaFuncSetAttribute(tc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM));
     configured[dev] = true;
   }
+  static int trace_on = -1;
+  if (trace_on < 0) trace_on = getenv("P3TOK_TC_TRACE") ? 1 : 0;
+  p.trace = nullptr;
+  const size_t tw = 4 * 16 * 16;
+  if (trace_on) {
+    P3_CUDA(cudaMalloc(&p.trace, tw * 8));
+    P3_CUDA(cudaMemsetAsync(p.trace, 0, tw * 8, s));
+  }
   const int max_pairs = num_sms() / 2;
   const int pairs = p.num_pairs < max_pairs ? p.num_pairs : max_pairs;
   cudaLaunchConfig_t cfg = {};
@@ -456,6 +488,24 @@ int tc_fused(const __nv_bfloat16* A0, int64_t M, int K0, const __nv_bfloat16* Wa
   cfg.numAttrs = 1;
   P3_CUDA(cudaLaunchKernelEx(&cfg, tc_fused_kernel, ta, twa, twb, tc, p));
   count_launch();
+  if (trace_on) {   // debug only: synchronises and prints pair 0's timeline (cycles relative to its first stamp)
+    std::vector<unsigned long long> h(tw);
+    P3_CUDA(cudaStreamSynchronize(s));
+    P3_CUDA(cudaMemcpy(h.data(), p.trace, tw * 8, cudaMemcpyDeviceToHost));
+    P3_CUDA(cudaFree(p.trace));
+    fprintf(stderr, "[fu_trace] M=%d K0=%d N1=%d N2=%d ra=%d rb=%d\n", p.M, p.K0, p.N1, p.N2, p.ra_slots, p.rb_slots);
+    const unsigned long long t0 = h[4];
+    auto rel = [&](unsigned long long v) { return v ? (long long)(v - t0) : -1ll; };
+    for (int it = 1; it < 3; ++it) {
+      const unsigned long long* q = &h[(size_t)it * 16 * 16];
+      fprintf(stderr, "[fu_trace] tile%d mma: start=%lld a0_ok=%lld A0_issued=%lld | out-epi: wait=%lld acc3_ok=%lld released=%lld end=%lld\n", it,
+              rel(q[4]), rel(q[5]), rel(q[6]), rel(q[12]), rel(q[13]), rel(q[14]), rel(q[15]));
+      for (int j = 0; j < 16 && q[j * 16 + 7]; ++j)
+        fprintf(stderr, "[fu_trace]   chunk%-2d mma: Anext=%lld ch_ok=%lld wb0=%lld wb3=%lld B=%lld | ch-epi: wait=%lld acc2_ok=%lld conv=%lld pub=%lld\n",
+                j, rel(q[j * 16 + 0]), rel(q[j * 16 + 1]), rel(q[j * 16 + 2]), rel(q[j * 16 + 3]), rel(q[j * 16 + 7]),
+                rel(q[j * 16 + 8]), rel(q[j * 16 + 9]), rel(q[j * 16 + 10]), rel(q[j * 16 + 11]));
+    }
+  }
   return P3TOK_OK;
 }
 

@@ -842,7 +842,8 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
     static int fuse_on = -1;
     // P3TOK_FUSED=1 routes layer pairs through tc_fused_kernel (embed_fused.cu).  Parity-green but OFF by default:
     // measured on B200 at C2 (same box, 30 steps): layer-by-layer 1.10 ms, fused single-CTA 1.29 ms (weight rings hold
-    // ~1 chunk next to the resident A0 tile: TMA-latency bound, profiles/r01_fused_trace.txt), fused CTA-pair 1.22 ms.
+    // ~1 chunk next to the resident A0 tile: TMA-latency bound, profiles/r01_fused_trace.txt), fused CTA-pair 1.22 ms:
+    // a tcgen05.mma costs ~90 tensor-pipe cycles however small N is, and the TMEM budget forces 64-column chunks.
     if (fuse_on < 0) { const char* e = getenv("P3TOK_FUSED"); fuse_on = e ? atoi(e) : 0; }
     const bool fuse_pre = fuse_on && fused_max && (m->n_pre - first_tc == 2) && m->pre_relu[m->n_pre - 2] == 1 &&
                           m->pre_relu[m->n_pre - 1] == 0 &&
