@@ -185,3 +185,26 @@ def test_randomised_shapes_against_oracle():
             neigh, center = ops.apf_group(xt.contiguous(), fidx, kidx, perm)
             o = oracle.group_apf(x, st, G, k)
             assert np.array_equal(neigh.cpu().numpy(), o["neigh"]) and np.array_equal(center.cpu().numpy(), o["center"]), (trial, "group")
+
+
+def test_dataset_level_fps_downsample():
+    """SURVEY 8f "next" #2: ScanObjectNN.__init__ with sampling_method='fps' (src/data/scanobjectnn.py:92-97) moves the
+    whole split to the GPU and calls fps(points, num_points) once: B = 2309 clouds, N = 2048, number = 1024."""
+    B, N, G = 2309, 2048, 1024
+    x = synth.make_cloud("clustered", B, N, 77, 3)
+    st = synth.start_indices(B, N, 77)
+    xt, stt = to_dev(x), to_dev(st)
+    F.fps(xt, G, stt)                                   # warm-up at full size: allocator growth / kernel load are not timed
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = F.fps(xt, G, stt)
+    e1.record()
+    torch.cuda.synchronize()
+    assert out.shape == (B, G, 3)
+    idx = F.furthest_point_sample(xt, G, stt)
+    assert torch.equal(out, torch.gather(xt, 1, idx.unsqueeze(-1).expand(-1, -1, 3)))
+    sub = slice(0, 24)                                  # oracle on a slice (the CPU loop is G x N per cloud)
+    assert np.array_equal(idx[sub].cpu().numpy(), oracle.fps(x[sub], st[sub], G))
+    assert all(len(set(r.tolist())) == G for r in idx[::97].cpu().numpy())
+    print(f"dataset-level fps: {B} clouds x {N} pts -> {G}: {e0.elapsed_time(e1):.1f} ms")
