@@ -18,7 +18,10 @@ constexpr int SG_BM = 128, SG_BN = 128, SG_BK = 8, SG_THREADS = 256;
 __global__ void __launch_bounds__(SG_THREADS)
 sgemm_bias_act_kernel(const float* __restrict__ A, int64_t M, int K, const float* __restrict__ W, int N,
                       const float* __restrict__ bias, const float* __restrict__ gbias, int rows_per_group,
-                      int relu, float* __restrict__ C) {
+                      int relu, float* __restrict__ C, int seg_rows, int seg_skip) {
+  // relu: 0 none, 1 ReLU, 2 exact GELU (nn.GELU default).  Output row of input row m is m + (m / seg_rows + 1) *
+  // seg_skip: with seg_skip = 1 every segment of seg_rows rows is preceded by one row left for the caller (the cls
+  // token of pix4point.py:248-252); seg_skip = 0 is the plain layout.
   __shared__ __align__(16) float As[2][SG_BK][SG_BM];
   __shared__ __align__(16) float Ws[2][SG_BK][SG_BN];
   const int t = threadIdx.x;
@@ -90,8 +93,9 @@ sgemm_bias_act_kernel(const float* __restrict__ A, int64_t M, int K, const float
       float v = acc[i][j];
       if (bias) v += bias[n];
       if (gb) v += gb[n];
-      if (relu) v = fmaxf(v, 0.f);
-      C[m * N + n] = v;
+      if (relu == 1) v = fmaxf(v, 0.f);
+      else if (relu == 2) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+      C[(m + (seg_skip ? (m / seg_rows + 1) * seg_skip : 0)) * N + n] = v;
     }
   }
 }
@@ -155,10 +159,11 @@ int build_rows_f32(const p3tok_rows* R, int64_t g_begin, int64_t g_count, float*
 }
 
 static int linear_f32(const float* A, int64_t M, int64_t K, const float* W, int64_t N, const float* bias,
-                      const float* gbias, int64_t rpg, int relu, float* C, cudaStream_t s) {
+                      const float* gbias, int64_t rpg, int relu, float* C, cudaStream_t s, int seg_rows = 1,
+                      int seg_skip = 0) {
   if (M == 0 || N == 0) return P3TOK_OK;
   dim3 grid((unsigned)((M + SG_BM - 1) / SG_BM), (unsigned)((N + SG_BN - 1) / SG_BN));
-  sgemm_bias_act_kernel<<<grid, SG_THREADS, 0, s>>>(A, M, (int)K, W, (int)N, bias, gbias, (int)rpg, relu, C);
+  sgemm_bias_act_kernel<<<grid, SG_THREADS, 0, s>>>(A, M, (int)K, W, (int)N, bias, gbias, (int)rpg, relu, C, seg_rows, seg_skip);
   P3_LAUNCH_CHECK("sgemm_bias_act_kernel");
   return P3TOK_OK;
 }
@@ -259,4 +264,39 @@ extern "C" int p3tok_group_max(const float* in, int64_t ngroups, int64_t k, int6
   if (ngroups == 0) return P3TOK_OK;
   P3_REQUIRE(in && out, P3TOK_ERR_INVALID, "group_max: null pointer");
   return group_max(in, ngroups, k, C, 0, out, as_stream(stream));
+}
+
+// cls rows of the token head: feats[b,0,:] = cls_token, pos[b,0,:] = cls_pos
+__global__ void cls_rows_kernel(const float* __restrict__ cls_token, const float* __restrict__ cls_pos, int64_t B, int64_t G,
+                                int E, float* __restrict__ feats, float* __restrict__ pos) {
+  const int64_t total = B * E;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = e / E;
+    const int c = (int)(e - b * E);
+    feats[b * (G + 1) * E + c] = cls_token[c];
+    pos[b * (G + 1) * E + c] = cls_pos[c];
+  }
+}
+
+extern "C" int p3tok_token_head_f32(const float* tokens, const float* centres, int64_t B, int64_t G, int64_t W, int64_t E,
+                                    int64_t H, const float* proj_w, const float* proj_b, const float* pos_w1,
+                                    const float* pos_b1, const float* pos_w2, const float* pos_b2, const float* cls_token,
+                                    const float* cls_pos, float* hidden_ws, float* feats_out, float* pos_out, void* stream) {
+  P3_REQUIRE(B >= 0 && G > 0 && W > 0 && E > 0 && H > 0 && G < (1ll << 30), P3TOK_ERR_INVALID, "token_head: bad shape");
+  if (B == 0) return P3TOK_OK;
+  P3_REQUIRE(tokens && centres && proj_w && pos_w1 && pos_w2 && cls_token && cls_pos && hidden_ws && feats_out && pos_out,
+             P3TOK_ERR_INVALID, "token_head: null pointer");
+  cudaStream_t s = as_stream(stream);
+  const int64_t M = B * G;
+  // x = proj(tokens) written behind each cloud's cls row (pix4point.py:245, 248)
+  int rc = linear_f32(tokens, M, W, proj_w, E, proj_b, nullptr, 1, 0, feats_out, s, (int)G, 1);
+  if (rc) return rc;
+  // pos_embed = Linear(H->E)(GELU(Linear(3->H)(centres)))  (pix4point.py:214-218, 246)
+  rc = linear_f32(centres, M, 3, pos_w1, H, pos_b1, nullptr, 1, 2, hidden_ws, s);
+  if (rc) return rc;
+  rc = linear_f32(hidden_ws, M, H, pos_w2, E, pos_b2, nullptr, 1, 0, pos_out, s, (int)G, 1);
+  if (rc) return rc;
+  cls_rows_kernel<<<grid_1d(B * E, 256), 256, 0, s>>>(cls_token, cls_pos, B, G, (int)E, feats_out, pos_out);
+  P3_LAUNCH_CHECK("cls_rows_kernel");
+  return P3TOK_OK;
 }

@@ -191,3 +191,32 @@ class P3Embed(nn.Module, _FoldedMixin):
             out_p.append(ctr)
             out_f.append(feat.transpose(1, 2))
         return out_p, out_f
+
+
+class PointViTTokens(nn.Module):
+    """The tokenizer half of the reference's PointViT (pix4point.py:194-258) - everything `PointViT.forward` does
+    before the timm blocks: P3Embed, `proj`, `pos_embed`, cls token / cls position concat.  Same attribute names and
+    state_dict keys (`patch_embed.*`, `proj.*`, `pos_embed.{0,2}.*`, `cls_token`, `cls_pos`), so the tokenizer part of
+    a PointViT checkpoint loads with strict=False.  forward(p, x=None) -> (p_list, x_list, feats (B,1+G,E),
+    pos_embed (B,1+G,E)); the ViT blocks (out of scope) consume `feats + pos_embed`."""
+
+    def __init__(self, in_channels: int = 3, embed_dim: int = 384, k_neighbors: int = 16, precision: str = "fp32",
+                 **p3embed_kwargs):
+        super().__init__()
+        self.num_features = self.embed_dim = embed_dim
+        self.patch_embed = P3Embed(in_channels=in_channels, k=k_neighbors, precision=precision, **p3embed_kwargs)
+        self.proj = nn.Linear(self.patch_embed.out_channels, embed_dim)
+        self.pos_embed = nn.Sequential(nn.Linear(3, 128, bias=True), nn.GELU(), nn.Linear(128, embed_dim))
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.cls_pos = nn.Parameter(torch.zeros(1, 1, embed_dim))
+
+    def forward(self, p: torch.Tensor, x: Optional[torch.Tensor] = None, start_idx: Optional[List[torch.Tensor]] = None):
+        if x is None:
+            x = p.transpose(1, 2)                          # pix4point.py:237-238: features := coordinates
+        p_list, x_list = self.patch_embed(p, x, start_idx)
+        tokens = x_list[-1].transpose(1, 2)                # channel-last view of the kernel's native layout
+        d = lambda t: t.detach()                           # inference-only op: parameters enter as plain tensors
+        feats, pos = ops.token_head(tokens, p_list[-1], d(self.proj.weight), d(self.proj.bias),
+                                    d(self.pos_embed[0].weight), d(self.pos_embed[0].bias), d(self.pos_embed[2].weight),
+                                    d(self.pos_embed[2].bias), d(self.cls_token), d(self.cls_pos))
+        return p_list, x_list, feats, pos

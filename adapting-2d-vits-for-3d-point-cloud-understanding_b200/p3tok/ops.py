@@ -380,6 +380,37 @@ def _(a, w, bias, relu, want_max32):
             a.new_empty(((M + 31) // 32 if want_max32 else 0, N), dtype=torch.float32))
 
 
+@torch.library.custom_op("p3tok::token_head", mutates_args=(), device_types="cuda")
+def token_head(tokens: torch.Tensor, centres: torch.Tensor, proj_w: torch.Tensor, proj_b: torch.Tensor,
+               pos_w1: torch.Tensor, pos_b1: torch.Tensor, pos_w2: torch.Tensor, pos_b2: torch.Tensor,
+               cls_token: torch.Tensor, cls_pos: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Pix4Point token head (pix4point.py:245-252): tokens (B,G,W), centres (B,G,3) -> feats, pos_embed (B,1+G,E)."""
+    ts = [_f32c("token_head", t) for t in (tokens, centres, proj_w, proj_b, pos_w1, pos_b1, pos_w2, pos_b2,
+                                           cls_token.reshape(-1), cls_pos.reshape(-1))]
+    _need_cuda("token_head", *ts)
+    tk, ct, pw, pb, w1, b1, w2, b2, cl, cp = ts
+    B, G, W = (int(v) for v in tk.shape)
+    E, H = int(pw.shape[0]), int(w1.shape[0])
+    if tuple(pw.shape) != (E, W) or tuple(w1.shape) != (H, 3) or tuple(w2.shape) != (E, H) or cl.numel() != E or cp.numel() != E:
+        raise RuntimeError("p3tok::token_head: weight shapes do not match tokens/centres")
+    feats = torch.empty((B, G + 1, E), dtype=torch.float32, device=tk.device)
+    pos = torch.empty((B, G + 1, E), dtype=torch.float32, device=tk.device)
+    hidden = torch.empty((B * G, H), dtype=torch.float32, device=tk.device)
+    with torch.cuda.device(tk.device), _timed("token_head"):
+        check(_L().p3tok_token_head_f32(tk.data_ptr(), ct.data_ptr(), B, G, W, E, H, pw.data_ptr(), pb.data_ptr(),
+                                        w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), cl.data_ptr(),
+                                        cp.data_ptr(), hidden.data_ptr(), feats.data_ptr(), pos.data_ptr(), _stream()),
+              "token_head")
+    return feats, pos
+
+
+@token_head.register_fake
+def _(tokens, centres, proj_w, proj_b, pos_w1, pos_b1, pos_w2, pos_b2, cls_token, cls_pos):
+    B, G = tokens.shape[0], tokens.shape[1]
+    E = proj_w.shape[0]
+    return tokens.new_empty((B, G + 1, E)), tokens.new_empty((B, G + 1, E))
+
+
 @torch.library.custom_op("p3tok::group_max", mutates_args=(), device_types="cuda")
 def group_max(x: torch.Tensor, k: int) -> torch.Tensor:
     _need_cuda("group_max", x)

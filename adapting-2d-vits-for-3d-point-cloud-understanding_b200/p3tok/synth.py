@@ -165,6 +165,19 @@ def p3embed_state(in_channels: int = 3, sample_ratio: float = 0.25, scale: int =
     return sd
 
 
+def token_head_state(width: int, embed_dim: int, seed: int = 0) -> Dict[str, np.ndarray]:
+    """proj / pos_embed / cls parameters of the reference's PointViT (src/models/pix4point.py:213-218, 229-230)."""
+    ws = _WeightStream(seed + 7919)
+    sd: Dict[str, np.ndarray] = {}
+    for name, cout, cin in (("proj", embed_dim, width), ("pos_embed.0", 128, 3), ("pos_embed.2", embed_dim, 128)):
+        bound = 1.0 / math.sqrt(cin)
+        sd[name + ".weight"] = ws.uniform((cout, cin), -bound, bound)
+        sd[name + ".bias"] = ws.uniform((cout,), -bound, bound)
+    sd["cls_token"] = ws.uniform((1, 1, embed_dim), -0.02, 0.02)
+    sd["cls_pos"] = ws.uniform((1, 1, embed_dim), -0.02, 0.02)
+    return sd
+
+
 def to_torch_state(sd: Dict[str, np.ndarray]):
     import torch
     return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}

@@ -175,6 +175,17 @@ P3TOK_API int p3tok_linear_bf16(const void* A, int64_t M, int64_t K, const void*
                       const float* gbias, int64_t rows_per_group, int relu, void* out_bf16,
                       float* out_f32, float* out_max32, void* stream);
 
+/* ---- "next" row 1: Pix4Point token head, src/models/pix4point.py:213-218 and 245-252 -----------
+ * feats_out (B,1+G,E): row 0 = cls_token, rows 1.. = proj(tokens) with proj = Linear(W->E);
+ * pos_out   (B,1+G,E): row 0 = cls_pos,   rows 1.. = Linear(H->E)(GELU(Linear(3->H)(centres))) (exact erf GELU).
+ * tokens (B,G,W) channel-last, centres (B,G,3); weights row-major [out,in] f32; hidden_ws: caller scratch of
+ * B*G*H floats.  fp32 on CUDA cores. */
+P3TOK_API int p3tok_token_head_f32(const float* tokens, const float* centres, int64_t B, int64_t G, int64_t W, int64_t E,
+                         int64_t H, const float* proj_w, const float* proj_b, const float* pos_w1,
+                         const float* pos_b1, const float* pos_w2, const float* pos_b2,
+                         const float* cls_token, const float* cls_pos, float* hidden_ws, float* feats_out,
+                         float* pos_out, void* stream);
+
 /* out[g, c] = max over r < k of in[(g*k + r), c]   (torch.max(..., dim=k-axis)) */
 P3TOK_API int p3tok_group_max(const float* in, int64_t ngroups, int64_t k, int64_t C, float* out, void* stream);
 

@@ -223,6 +223,26 @@ def p3embed(sd: Dict[str, np.ndarray], pts: np.ndarray, feats_cl: np.ndarray,
     return out_p, out_f, aux
 
 
+def token_head(sd: Dict[str, np.ndarray], tokens: np.ndarray, centres: np.ndarray):
+    """pix4point.py:245-252: proj Linear on the tokens, pos_embed MLP (exact erf GELU) on the centres, cls rows first.
+    tokens (B,G,W), centres (B,G,3) -> feats, pos (B,1+G,E) float64."""
+    from math import sqrt
+    try:
+        from scipy.special import erf
+    except Exception:                                   # pragma: no cover
+        erf = np.vectorize(__import__("math").erf)
+    f = lambda k: np.asarray(sd[k], np.float64)
+    B = tokens.shape[0]
+    x = tokens.astype(np.float64) @ f("proj.weight").T + f("proj.bias")
+    h = centres.astype(np.float64) @ f("pos_embed.0.weight").T + f("pos_embed.0.bias")
+    h = 0.5 * h * (1.0 + erf(h / sqrt(2.0)))
+    pe = h @ f("pos_embed.2.weight").T + f("pos_embed.2.bias")
+    E = x.shape[-1]
+    feats = np.concatenate([np.broadcast_to(f("cls_token").reshape(1, 1, E), (B, 1, E)), x], 1)
+    pos = np.concatenate([np.broadcast_to(f("cls_pos").reshape(1, 1, E), (B, 1, E)), pe], 1)
+    return feats, pos
+
+
 # ----------------------------------------------------------------------------- comparison helpers
 
 def knn_tie_equivalent(idx_a: np.ndarray, idx_b: np.ndarray, dist_full: np.ndarray,

@@ -23,3 +23,8 @@ INDEX_CASES = {
     "idx_clustered": dict(kind="clustered", B=2, N=1024, G=256, k=32, seed=32),
     "idx_dups": dict(kind="duplicates", B=2, N=512, G=64, k=16, seed=33),
 }
+
+HEAD_CASES = {
+    # Pix4Point token head (proj + pos_embed + cls concat): name: dict(B, G, W, E, seed)
+    "p4p_head": dict(B=2, G=16, W=64, E=96, seed=41),
+}

@@ -169,6 +169,32 @@ def index_case(ref, name, c):
                         morton_perm=mperm.numpy().astype(np.int32))
 
 
+def head_case(name, c):
+    """The reference builds these layers with plain torch.nn (pix4point.py:213-218) and applies them at 245-252; PointViT
+    itself cannot be constructed here (timm.create_model), so the same torch.nn modules are evaluated directly."""
+    import torch.nn as nn
+    sd = synth.token_head_state(c["W"], c["E"], c["seed"])
+    tsd = synth.to_torch_state(sd)
+    proj = nn.Linear(c["W"], c["E"])
+    pos = nn.Sequential(nn.Linear(3, 128, bias=True), nn.GELU(), nn.Linear(128, c["E"]))
+    proj.load_state_dict({"weight": tsd["proj.weight"], "bias": tsd["proj.bias"]})
+    pos.load_state_dict({"0.weight": tsd["pos_embed.0.weight"], "0.bias": tsd["pos_embed.0.bias"],
+                         "2.weight": tsd["pos_embed.2.weight"], "2.bias": tsd["pos_embed.2.bias"]})
+    tokens = synth.uniform01(c["seed"], c["B"] * c["G"] * c["W"], 9).reshape(c["B"], c["G"], c["W"])
+    centres = synth.make_cloud("uniform", c["B"], c["G"], c["seed"], 3)
+    with torch.no_grad():
+        x = proj(torch.from_numpy(tokens))
+        pe = pos(torch.from_numpy(centres))
+        feats = torch.cat([tsd["cls_token"].expand(c["B"], -1, -1), x], dim=1)
+        pemb = torch.cat([tsd["cls_pos"].expand(c["B"], -1, -1), pe], dim=1)
+    of, op = oracle.token_head(sd, tokens, centres)
+    e1 = np.abs(of - feats.numpy()).max() / np.abs(feats.numpy()).max()
+    e2 = np.abs(op - pemb.numpy()).max() / np.abs(pemb.numpy()).max()
+    print(f"{name}: oracle vs torch.nn head: feats {e1:.2e}, pos {e2:.2e}")
+    assert e1 < 2e-6 and e2 < 2e-6, name
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), feats=feats.numpy(), pos=pemb.numpy())
+
+
 def main():
     assert ref_loader.available(), "reference tree not present"
     ref = ref_loader.load()
@@ -179,6 +205,8 @@ def main():
         apf_case(ref, name, c)
     for name, c in cases.P4P_CASES.items():
         p4p_case(ref, name, c)
+    for name, c in cases.HEAD_CASES.items():
+        head_case(name, c)
 
 
 if __name__ == "__main__":

@@ -211,3 +211,40 @@ def test_fused_pair_kernel_matches_layerwise(monkeypatch):
         outs.append(torch.load(path))
     err = float((outs[0] - outs[1]).abs().max() / outs[0].abs().max())
     assert err < 3e-3, err
+
+
+def test_token_head_matches_oracle_and_golden(golden_dir):
+    """SURVEY 8f next #1: proj + pos_embed + cls concat of PointViT.forward (pix4point.py:245-252), fp32, rtol 1e-4."""
+    c = cases.HEAD_CASES["p4p_head"]
+    g = _golden(golden_dir, "p4p_head")
+    sd = synth.token_head_state(c["W"], c["E"], c["seed"])
+    tokens = synth.uniform01(c["seed"], c["B"] * c["G"] * c["W"], 9).reshape(c["B"], c["G"], c["W"])
+    centres = synth.make_cloud("uniform", c["B"], c["G"], c["seed"], 3)
+    t = {k: to_dev(v) for k, v in sd.items()}
+    feats, pos = ops.token_head(to_dev(tokens), to_dev(centres), t["proj.weight"], t["proj.bias"], t["pos_embed.0.weight"],
+                                t["pos_embed.0.bias"], t["pos_embed.2.weight"], t["pos_embed.2.bias"], t["cls_token"], t["cls_pos"])
+    of, op = oracle.token_head(sd, tokens, centres)
+    for got, ref, gold in ((feats, of, g["feats"]), (pos, op, g["pos"])):
+        assert_tokens_close(got.cpu().numpy(), ref, 1e-4, "token head vs oracle")
+        assert_tokens_close(got.cpu().numpy(), gold, 1e-4, "token head vs torch.nn golden")
+
+
+def test_pointvit_tokens_module():
+    """PointViTTokens = P3Embed + token head behind PointViT's attribute names; BASELINE C1 shapes (embed dim 384)."""
+    from p3tok.modules import PointViTTokens
+    B, N, k, E = 4, 1024, 32, 384
+    m = PointViTTokens(embed_dim=E, k_neighbors=k, sample_ratio=1 / 16).eval().to(dev())
+    sd_p = synth.to_torch_state(synth.p3embed_state(3, 1 / 16, 4, 4, 256, 5))
+    sd_h = synth.to_torch_state(synth.token_head_state(256, E, 5))
+    m.patch_embed.load_state_dict(sd_p, strict=True)
+    missing = m.load_state_dict(sd_h, strict=False)
+    assert not missing.unexpected_keys and all(k_.startswith("patch_embed.") for k_ in missing.missing_keys)
+    assert {"proj.weight", "pos_embed.0.weight", "pos_embed.2.bias", "cls_token", "cls_pos"} <= set(m.state_dict())
+    p = synth.make_cloud("uniform", B, N, 5, 3)
+    starts = [synth.start_indices(B, N, 5, 0), synth.start_indices(B, N // 4, 5, 1)]
+    p_list, x_list, feats, pos = m(to_dev(p), None, [to_dev(s) for s in starts])
+    assert feats.shape == pos.shape == (B, 1 + N // 16, E)
+    op, of, _ = oracle.p3embed(synth.p3embed_state(3, 1 / 16, 4, 4, 256, 5), p, p.copy(), starts, k, 2)
+    rf, rp = oracle.token_head(synth.token_head_state(256, E, 5), of[-1].astype(np.float32), op[-1])
+    assert_tokens_close(feats.cpu().numpy(), rf, 2e-4, "PointViTTokens feats")
+    assert_tokens_close(pos.cpu().numpy(), rp, 1e-4, "PointViTTokens pos_embed")

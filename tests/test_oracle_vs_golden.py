@@ -82,3 +82,18 @@ def test_p4p_cases(golden_dir, name):
         # next stage consumes the reference's fp32 outputs (as make_golden.py did)
         pts, feats = g[f"centres{s}"], g[f"tokens{s}"]
         n //= 4
+
+
+@pytest.mark.parametrize("name", list(cases.HEAD_CASES))
+def test_token_head_cases(golden_dir, name):
+    """Pix4Point token head (SURVEY 8f next #1): oracle against the torch.nn evaluation stored by make_golden.py."""
+    c = cases.HEAD_CASES[name]
+    g = _load(golden_dir, name)
+    sd = synth.token_head_state(c["W"], c["E"], c["seed"])
+    tokens = synth.uniform01(c["seed"], c["B"] * c["G"] * c["W"], 9).reshape(c["B"], c["G"], c["W"])
+    centres = synth.make_cloud("uniform", c["B"], c["G"], c["seed"], 3)
+    feats, pos = oracle.token_head(sd, tokens, centres)
+    assert feats.shape == g["feats"].shape == (c["B"], c["G"] + 1, c["E"])
+    assert np.abs(feats - g["feats"]).max() <= 2e-6 * np.abs(g["feats"]).max()
+    assert np.abs(pos - g["pos"]).max() <= 2e-6 * np.abs(g["pos"]).max()
+    assert np.array_equal(feats[:, 0], np.broadcast_to(sd["cls_token"].reshape(1, -1), (c["B"], c["E"])).astype(np.float64))
