@@ -913,6 +913,20 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
       }
       continue;
     }
+    // narrow blocks (P3Embed stage 0): concat layer + output layer + pool in one kernel with the weights resident in
+    // shared memory (embed_stage.cu); the hidden activation never reaches HBM.  P3TOK_STAGE=0 disables it.
+    static int stage_on = -1;
+    if (stage_on < 0) { const char* e = getenv("P3TOK_STAGE"); stage_on = e ? atoi(e) : 1; }
+    if (stage_on && fused_max && tc_stage_supported((int)L.F, m->mid_dim, m->out_dim, k)) {
+      rc = tc_stage(act[cur], rows, (int)L.F, (const __nv_bfloat16*)m->w_mid_f, m->mid_dim, nullptr, gbias, (int)k,
+                    (const __nv_bfloat16*)m->w_out, m->out_dim, m->b_out, parts == 1 ? tok : gmax_f32, parts == 1 ? m->out_relu : 0, s);
+      if (rc) return rc;
+      if (parts > 1) {
+        group_max_f32_kernel<<<grid_1d(gc * m->out_dim, 256), 256, 0, s>>>(gmax_f32, gc, parts, m->out_dim, m->out_relu, tok, nullptr);
+        P3_LAUNCH_CHECK("group_max_f32_kernel");
+      }
+      continue;
+    }
     rc = tc_linear(act[cur], rows, (int)L.F, (const __nv_bfloat16*)m->w_mid_f, m->mid_dim, nullptr, gbias, (int)k, 1, act[cur ^ 1],
                    nullptr, nullptr, nullptr, 0, s);
     if (rc) return rc;

@@ -248,3 +248,39 @@ def test_pointvit_tokens_module():
     rf, rp = oracle.token_head(synth.token_head_state(256, E, 5), of[-1].astype(np.float32), op[-1])
     assert_tokens_close(feats.cpu().numpy(), rf, 2e-4, "PointViTTokens feats")
     assert_tokens_close(pos.cpu().numpy(), rp, 1e-4, "PointViTTokens pos_embed")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,ng", [(128, 8), (128, 4099), (64, 777)])
+def test_stage_kernel_matches_arithmetic_model_and_layerwise(W, ng):
+    """embed_stage.cu (concat + output layer + pool of a narrow P3Embed stage in one kernel, weights resident in
+    shared memory) against a torch model of its arithmetic and against the layer-by-layer tensor-core path
+    (P3TOK_STAGE=0 in a subprocess); ragged tile counts (ng not a multiple of 8 patches = 256 rows)."""
+    _skip_if_unbuilt("bf16")
+    import os, subprocess, sys
+    from p3tok import fold
+    k, cin = 32, 6
+    sd = synth.p3embed_state(3, 0.25, 4, 4, W, 77)
+    mlp = fold.fold_p3embed_stage(synth.to_torch_state(sd), 0)
+    torch.manual_seed(W + ng)
+    rows = (torch.randn(ng * k, cin) * 0.5)
+    m = mlp.to(dev(), torch.bfloat16)
+    tok = ops.patch_embed(_lib.ROWS_DIRECT, rows.to(dev()), None, None, None, None, ng, k, m.tensors(), m.meta(), True)
+    model = bf16_emulation(mlp, rows.to(dev()), k)
+    err = float((tok - model).abs().max() / model.abs().max())
+    assert err < 2e-3, err
+    path_in, path_out = f"/tmp/p3tok_stage_in_{W}_{ng}.pt", f"/tmp/p3tok_stage_out_{W}_{ng}.pt"
+    torch.save(rows, path_in)
+    code = (
+        "import sys, os; sys.path.insert(0, os.path.join(os.getcwd(), 'adapting-2d-vits-for-3d-point-cloud-understanding_b200'));"
+        "import torch; from p3tok import synth, fold, ops, _lib;"
+        f"mlp = fold.fold_p3embed_stage(synth.to_torch_state(synth.p3embed_state(3, 0.25, 4, 4, {W}, 77)), 0).to(torch.device('cuda:0'), torch.bfloat16);"
+        "rows = torch.load(sys.argv[1]).cuda();"
+        f"tok = ops.patch_embed(_lib.ROWS_DIRECT, rows, None, None, None, None, {ng}, 32, mlp.tensors(), mlp.meta(), True);"
+        "torch.save(tok.cpu(), sys.argv[2])")
+    env = dict(os.environ, P3TOK_STAGE="0")
+    subprocess.run([sys.executable, "-c", code, path_in, path_out], check=True, env=env,
+                   cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    ref = torch.load(path_out)
+    err2 = float((tok.cpu() - ref).abs().max() / ref.abs().max())
+    assert err2 < 2e-3, err2
