@@ -23,7 +23,7 @@
 // TMEM (512 columns): two accumulators of 256 columns.  Tile t uses accumulator t&1: GEMM 1 fills columns [0,N1);
 // once the hidden epilogue has drained them, GEMM 2 of the same tile re-uses columns [0,N2) for the output.
 // Warps: 0 = a0 producer (TMA), 1 = MMA issuer (leader CTA only), 2-9 = hidden epilogue (row quarter q x column
-// half h), 10-17 = output epilogue (row quarter q x column half h: 32-row max, bias, ReLU, token store).
+// half h), 10-17 = output epilogue (row quarter q x column half: 32-row max, bias, ReLU, token store).
 // MMA issue order  G1(0) G1(1) | G2(0) G1(2) | G2(1) G1(3) ...: while the hidden epilogue of tile t+1 runs, the
 // tensor pipe executes G2(t) and G1(t+2).
 // Barriers the leader's MMA warp waits on live in the leader CTA (TMA loads of both CTAs signal them, epilogue warps
@@ -47,7 +47,37 @@ struct StageParams {
   const float* bias_b;              // [N2] or null
   float* out_max;                   // [ceil(M/32), N2]
   int max_relu;
+  unsigned long long* trace;        // debug (P3TOK_TC_TRACE=1): leader CTA of pair 0, 16 clock stamps per tile
 };
+// slots: MMA warp 0 g2-wait 1 h_full-ok 2 g2-issued 3 g1-wait 4 a0_full-ok 5 acc_free-ok 6 g1-issued | hidden epilogue (warp 2)
+// 7 wait 8 acc1_full-ok 9 h_empty-ok 10 published | output epilogue (warp 10) 11 wait 12 acc2_full-ok 13 released 14 done | 15 TMA issued
+__device__ __forceinline__ void st_trace(const StageParams& p, int it, int slot) {
+  if (p.trace && blockIdx.x == 0 && it < 32) p.trace[it * 16 + slot] = (unsigned long long)clock64();
+}
+
+// One 32-row x 32-column piece of the hidden tile: accumulator + group bias -> ReLU -> bf16x2 (16 registers) ...
+__device__ __forceinline__ void st_convert(const float (&v)[32], const float* gb32, uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 g4 = *reinterpret_cast<const float4*>(gb32 + 4 * i);
+    float a0, a1, a2, a3;
+    add2(a0, a1, v[4 * i], v[4 * i + 1], g4.x, g4.y);
+    add2(a2, a3, v[4 * i + 2], v[4 * i + 3], g4.z, g4.w);
+    pk[2 * i] = pack_bf16x2_relu(a0, a1);          // ReLU rides on the conversion
+    pk[2 * i + 1] = pack_bf16x2_relu(a2, a3);
+  }
+}
+// ... and its store into the swizzled K-major rows of the hidden tile (64 B of this thread's 128-byte row)
+__device__ __forceinline__ void st_store(const uint32_t (&pk)[16], uint32_t rbase, int h, int trow) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t a = rbase + (((uint32_t)(j + 4 * h) ^ (uint32_t)(trow & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]),
+                 "r"(pk[4 * j + 3])
+                 : "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+}
 
 __global__ void __launch_bounds__(ST_THREADS, 1)
 tc_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWa,
@@ -68,10 +98,10 @@ tc_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* a0_full = bars + 1;        // [2] leader
   uint64_t* a0_empty = bars + 3;       // [2] local, multicast commit
   uint64_t* acc1_full = bars + 5;      // [2] local, multicast commit
-  uint64_t* h_full = bars + 7;         // leader, 2 x ST_E1_WARPS arrivals
-  uint64_t* h_empty = bars + 8;        // local, multicast commit
-  uint64_t* acc2_full = bars + 9;      // [2] local, multicast commit
-  uint64_t* acc_free = bars + 11;      // [2] leader, 2 x ST_E2_WARPS arrivals
+  uint64_t* acc2_full = bars + 7;      // [2] local, multicast commit
+  uint64_t* acc_free = bars + 9;       // [2] leader, 2 x ST_E2_WARPS arrivals
+  uint64_t* h_full = bars + 11;        // leader, 2 x ST_E1_WARPS arrivals
+  uint64_t* h_empty = bars + 12;       // local, multicast commit
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -123,6 +153,7 @@ tc_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (issuer) {
         if (rank == 0) mbar_expect_tx(&a0_full[s], 2u * (uint32_t)a0_bytes);
         for (int kb = 0; kb < KB0; ++kb) tma_load_2d_pair(sA0 + s * a0_bytes + kb * 16384, &tmA, &a0_full[s], kb * 64, mt * TC_BM);
+        st_trace(p, it, 15);
       }
       __syncwarp();
     }
@@ -140,10 +171,13 @@ tc_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // G1(t): accumulator t&1, columns [0,N1) = a0(t) . W_a^T
       auto issue_g1 = [&](int t) {
         const int s = t & 1;
+        if (issuer) st_trace(p, t, 3);
         mbar_wait(&a0_full[s], (uint32_t)(t >> 1) & 1);
+        if (issuer) st_trace(p, t, 4);
         mbar_wait(&acc_free[s], ((uint32_t)(t >> 1) & 1) ^ 1);     // output epilogue of tile t-2 has drained this accumulator
         tc_fence_after();
         if (issuer) {
+          st_trace(p, t, 5);
           const uint32_t d = tmem_base + (uint32_t)(s * ST_ACC_COLS);
           for (int kb = 0; kb < KB0; ++kb) {
             const uint64_t ad = dconst | (uint64_t)(a0_base + ((s * a0_bytes + kb * 16384) >> 4));
@@ -153,15 +187,18 @@ tc_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           tc_commit_pair(&a0_empty[s]);
           tc_commit_pair(&acc1_full[s]);
+          st_trace(p, t, 6);
         }
         __syncwarp();
       };
       // G2(t): accumulator t&1, columns [0,N2) = hidden(t) . W_b^T   (hidden epilogue has drained GEMM 1's result)
       auto issue_g2 = [&](int t) {
         const int s = t & 1;
+        if (issuer) st_trace(p, t, 0);
         mbar_wait(h_full, (uint32_t)t & 1);
         tc_fence_after();
         if (issuer) {
+          st_trace(p, t, 1);
           const uint32_t d = tmem_base + (uint32_t)(s * ST_ACC_COLS);
           for (int kb = 0; kb < KB1; ++kb) {
             const uint64_t ad = dconst | (uint64_t)(h_base + ((kb * 16384) >> 4));
@@ -171,6 +208,7 @@ tc_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           tc_commit_pair(h_empty);
           tc_commit_pair(&acc2_full[s]);
+          st_trace(p, t, 2);
         }
         __syncwarp();
       };
@@ -185,6 +223,8 @@ tc_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp < 2 + ST_E1_WARPS) {
     // ---------------- hidden epilogue: GEMM 1 accumulator -> + group bias -> ReLU -> bf16 K-major operand of GEMM 2
+    // (row quarter q x column half h).  Finer hand-over (one barrier per 64-column K block, TMEM loads one block ahead,
+    // one warp per quarter) was built and measured no better - see the header.
     const int ew = warp - 2;
     const int q = warp & 3, h = ew >> 2;            // TMEM lane quarter, column half
     const uint32_t lane_field = (uint32_t)(q * 32) << 16;
@@ -192,61 +232,65 @@ tc_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int half_cols = p.N1 / 2, pieces = half_cols / 32;
     float* my_sgb = sgb + ew * 128;
     const uint32_t h_row = smem_u32(sH) + trow * 128;
-    int it = 0;
-    for (int tp = pair_id; tp < p.num_pairs; tp += pair_stride, ++it) {
-      const int s = it & 1;
+    // this warp's slice of the group-bias row of tile `tp`, one float4 per lane, fetched ONE TILE AHEAD (otherwise an L2
+    // round trip per tile sits on the critical path between the two GEMMs)
+    auto load_gb = [&](int tp) {
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tp >= p.num_pairs) return g;
       const int row0 = (2 * tp + rank) * TC_BM + q * 32;
       const float* src = nullptr;
       if (p.gbias) { if (row0 < p.M) src = p.gbias + (size_t)(row0 / p.rows_per_group) * p.N1 + h * half_cols; }
       else if (p.bias_a) src = p.bias_a + h * half_cols;
-      float4 gpre = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (src && 4 * lane < half_cols) gpre = __ldg(reinterpret_cast<const float4*>(src) + lane);   // overlaps the wait below
+      if (src && 4 * lane < half_cols) g = __ldg(reinterpret_cast<const float4*>(src) + lane);
+      return g;
+    };
+    float4 gnext = load_gb(pair_id);
+    int it = 0;
+    for (int tp = pair_id; tp < p.num_pairs; tp += pair_stride, ++it) {
+      const int s = it & 1;
+      const float4 gpre = gnext;
+      const bool tr = (warp == 2 && lane == 0);
+      if (tr) st_trace(p, it, 7);
       mbar_wait(&acc1_full[s], (uint32_t)(it >> 1) & 1);
+      if (tr) st_trace(p, it, 8);
       tc_fence_after();
       __syncwarp();                                  // previous tile's reads of the slice are done
       *reinterpret_cast<float4*>(my_sgb + 4 * lane) = gpre;
       __syncwarp();
+      gnext = load_gb(tp + pair_stride);
       for (int pc = 0; pc < pieces; ++pc) {
         const int c0 = h * half_cols + pc * 32;      // hidden column of v[0]
         float v[32];
+        uint32_t pk[16];
         tc_ld32_issue(tmem_base + lane_field + (uint32_t)(s * ST_ACC_COLS + c0), v);
         tc_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 g4 = *reinterpret_cast<const float4*>(my_sgb + pc * 32 + 4 * i);
-          v[4 * i] += g4.x; v[4 * i + 1] += g4.y; v[4 * i + 2] += g4.z; v[4 * i + 3] += g4.w;
+        st_convert(v, my_sgb + pc * 32, pk);
+        if (pc == 0) {
+          mbar_wait(h_empty, ((uint32_t)it & 1) ^ 1);   // GEMM 2 of the previous tile has read the hidden tile
+          if (tr) st_trace(p, it, 9);
         }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-        if (pc == 0) mbar_wait(h_empty, ((uint32_t)it & 1) ^ 1);   // GEMM 2 of the previous tile has read the hidden tile
-        const uint32_t rbase = h_row + (uint32_t)(c0 >> 6) * 16384u;
-        const int half = (c0 >> 5) & 1;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t a = rbase + (((uint32_t)(j + 4 * half) ^ (uint32_t)(trow & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(v[j * 8], v[j * 8 + 1])),
-                       "r"(pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3])), "r"(pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5])),
-                       "r"(pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]))
-                       : "memory");
-        }
+        st_store(pk, h_row + (uint32_t)(c0 >> 6) * 16384u, (c0 >> 5) & 1, trow);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cta(h_full, 0);
+      if (tr) st_trace(p, it, 10);
     }
   } else {
     // ---------------- output epilogue: GEMM 2 accumulator -> max over the warp's 32 rows -> + bias -> ReLU -> token
     const int ew = warp - 2 - ST_E1_WARPS;
     const int q = warp & 3, h = ew >> 2;
     const uint32_t lane_field = (uint32_t)(q * 32) << 16;
-    const int half_cols = p.N2 / 2, pieces = half_cols / 32;       // 1 or 2 (N2 = 64 / 128); up to 4 for N2 = 256
+    const int half_cols = p.N2 / (ST_E2_WARPS / 4), pieces = half_cols / 32;   // columns per warp of a row quarter
     int it = 0;
     for (int tp = pair_id; tp < p.num_pairs; tp += pair_stride, ++it) {
       const int s = it & 1;
       const int row0 = (2 * tp + rank) * TC_BM + q * 32;
       const bool row_ok = row0 + lane < p.M;
+      const bool tr = (warp == 2 + ST_E1_WARPS && lane == 0);
+      if (tr) st_trace(p, it, 11);
       mbar_wait(&acc2_full[s], (uint32_t)(it >> 1) & 1);
+      if (tr) st_trace(p, it, 12);
       tc_fence_after();
       for (int pc0 = 0; pc0 < pieces; pc0 += 2) {
         const bool two = pc0 + 1 < pieces;
@@ -259,6 +303,7 @@ tc_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cta(&acc_free[s], 0);
+          if (tr) st_trace(p, it, 13);
         }
         if (!row_ok) {
 #pragma unroll
@@ -273,6 +318,7 @@ tc_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (row0 < p.M) p.out_max[(size_t)(row0 >> 5) * p.N2 + c0 + 32 + lane] = m1;
         }
       }
+      if (tr) st_trace(p, it, 14);
     }
   }
   tc_fence_before();
@@ -341,8 +387,31 @@ int tc_stage(const __nv_bfloat16* A0, int64_t M, int K0, const __nv_bfloat16* Wa
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  static int trace_on = -1;
+  if (trace_on < 0) trace_on = getenv("P3TOK_TC_TRACE") ? 1 : 0;
+  p.trace = nullptr;
+  if (trace_on) {
+    P3_CUDA(cudaMalloc(&p.trace, 32 * 16 * 8));
+    P3_CUDA(cudaMemsetAsync(p.trace, 0, 32 * 16 * 8, s));
+  }
   P3_CUDA(cudaLaunchKernelEx(&cfg, tc_stage_kernel, ta, twa, twb, p));
   count_launch();
+  if (trace_on) {   // debug only: synchronises and prints the leader CTA of pair 0 (cycles relative to its first stamp)
+    unsigned long long h[32 * 16];
+    P3_CUDA(cudaStreamSynchronize(s));
+    P3_CUDA(cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost));
+    P3_CUDA(cudaFree(p.trace));
+    const unsigned long long t0 = h[3];
+    auto rel = [&](unsigned long long v) { return v ? (long long)(v - t0) : -1ll; };
+    fprintf(stderr, "[st_trace] M=%d K0=%d N1=%d N2=%d pairs=%d\n", p.M, K0, N1, N2, pairs);
+    for (int it = 0; it < 32 && h[it * 16 + 3]; ++it) {
+      const unsigned long long* q = &h[it * 16];
+      fprintf(stderr, "[st_trace] t%-2d g1[wait=%lld a0=%lld accfree=%lld issued=%lld] g2[wait=%lld hfull=%lld issued=%lld] "
+              "e1[wait=%lld acc1=%lld hempty=%lld pub=%lld] e2[wait=%lld acc2=%lld rel=%lld done=%lld] tma=%lld\n", it,
+              rel(q[3]), rel(q[4]), rel(q[5]), rel(q[6]), rel(q[0]), rel(q[1]), rel(q[2]), rel(q[7]), rel(q[8]), rel(q[9]),
+              rel(q[10]), rel(q[11]), rel(q[12]), rel(q[13]), rel(q[14]), rel(q[15]));
+    }
+  }
   return P3TOK_OK;
 }
 

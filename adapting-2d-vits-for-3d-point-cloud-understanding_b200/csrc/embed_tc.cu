@@ -83,7 +83,8 @@ __device__ __forceinline__ void tc_trace(const TcParams& p, int it, int role, in
 
 // bias / per-group bias / ReLU on 32 accumulator columns starting at global column n0.  `sbias` is the
 // bias vector staged in shared memory (zeros when the layer has none); all loads are issued before use.
-__device__ __forceinline__ void epilogue_affine(float (&v)[32], const TcParams& p, const float* sbias, const float* gb, int n0) {
+__device__ __forceinline__ void epilogue_affine(float (&v)[32], const TcParams& p, const float* sbias, const float* gb, int n0,
+                                                bool relu_now) {
   const int nmax = p.N - 4;                                  // N % 8 == 0: clamped float4 loads stay in range
   float4 g4[8];
   if (gb) {
@@ -93,15 +94,17 @@ __device__ __forceinline__ void epilogue_affine(float (&v)[32], const TcParams& 
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float4 b4 = *reinterpret_cast<const float4*>(sbias + min(n0 + 4 * j, nmax));
-    v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+    add2(v[4 * j], v[4 * j + 1], v[4 * j], v[4 * j + 1], b4.x, b4.y);
+    add2(v[4 * j + 2], v[4 * j + 3], v[4 * j + 2], v[4 * j + 3], b4.z, b4.w);
   }
   if (gb) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      v[4 * j] += g4[j].x; v[4 * j + 1] += g4[j].y; v[4 * j + 2] += g4[j].z; v[4 * j + 3] += g4[j].w;
+      add2(v[4 * j], v[4 * j + 1], v[4 * j], v[4 * j + 1], g4[j].x, g4[j].y);
+      add2(v[4 * j + 2], v[4 * j + 3], v[4 * j + 2], v[4 * j + 3], g4[j].z, g4[j].w);
     }
   }
-  if (p.relu) {
+  if (relu_now) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   }
@@ -117,19 +120,33 @@ __device__ __forceinline__ void epilogue_half(const TcParams& p, const float* sb
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 g = *reinterpret_cast<const float4*>(sgb + 32 * half + 4 * j);
-      v[4 * j] += g.x; v[4 * j + 1] += g.y; v[4 * j + 2] += g.z; v[4 * j + 3] += g.w;
+      add2(v[4 * j], v[4 * j + 1], v[4 * j], v[4 * j + 1], g.x, g.y);
+      add2(v[4 * j + 2], v[4 * j + 3], v[4 * j + 2], v[4 * j + 3], g.z, g.w);
     }
   }
-  epilogue_affine(v, p, sbias, gb, n0);
+  // bf16-only outputs take their ReLU from the conversion instruction (F2FP.RELU) instead of 32 FMNMX
+  const bool relu_in_pack = p.relu && !p.out_f32 && !p.out_max && !p.out_max_bf16;
+  epilogue_affine(v, p, sbias, gb, n0, p.relu && !relu_in_pack);
   if (p.out_bf16) {
     const uint32_t rbase = sbox + lane * 128;
+    if (relu_in_pack) {
 #pragma unroll
-    for (int pc = 0; pc < 4; ++pc) {
-      const uint32_t a = rbase + (((uint32_t)(pc + 4 * half) ^ (lane & 7)) << 4);
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(v[pc * 8], v[pc * 8 + 1])),
-                   "r"(pack_bf16x2(v[pc * 8 + 2], v[pc * 8 + 3])), "r"(pack_bf16x2(v[pc * 8 + 4], v[pc * 8 + 5])),
-                   "r"(pack_bf16x2(v[pc * 8 + 6], v[pc * 8 + 7]))
-                   : "memory");
+      for (int pc = 0; pc < 4; ++pc) {
+        const uint32_t a = rbase + (((uint32_t)(pc + 4 * half) ^ (lane & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2_relu(v[pc * 8], v[pc * 8 + 1])),
+                     "r"(pack_bf16x2_relu(v[pc * 8 + 2], v[pc * 8 + 3])), "r"(pack_bf16x2_relu(v[pc * 8 + 4], v[pc * 8 + 5])),
+                     "r"(pack_bf16x2_relu(v[pc * 8 + 6], v[pc * 8 + 7]))
+                     : "memory");
+      }
+    } else {
+#pragma unroll
+      for (int pc = 0; pc < 4; ++pc) {
+        const uint32_t a = rbase + (((uint32_t)(pc + 4 * half) ^ (lane & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(v[pc * 8], v[pc * 8 + 1])),
+                     "r"(pack_bf16x2(v[pc * 8 + 2], v[pc * 8 + 3])), "r"(pack_bf16x2(v[pc * 8 + 4], v[pc * 8 + 5])),
+                     "r"(pack_bf16x2(v[pc * 8 + 6], v[pc * 8 + 7]))
+                     : "memory");
+      }
     }
   }
   if (p.out_f32 && row_ok) {
@@ -669,11 +686,45 @@ __global__ void rows_gather_bf16_kernel(p3tok_rows R, int64_t g_begin, int64_t n
   }
 }
 
-__global__ void pad_weight_kernel(const __nv_bfloat16* __restrict__ W, int N, int K, int kpad, __nv_bfloat16* __restrict__ out) {
+// P3Embed rows with D % 4 == 0 (stage >= 1: D = previous stage width): one warp per row, the feature row is one
+// coalesced float4 sweep.  Column order is ROTATED to [feats (D) | xyz (3) | zero pad] so that the 8-byte bf16 stores
+// stay aligned; pad_weight_kernel rotates the weight columns the same way (rot = 3).
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+rows_gather_p4p_bf16_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, int kpad, __nv_bfloat16* __restrict__ out) {
+  const IdxT* knn = reinterpret_cast<const IdxT*>(R.knn_idx);
+  const int lane = threadIdx.x & 31;
+  const int D = R.D, d4 = D >> 2, tail4 = (kpad - D) >> 2;       // kpad % 8 == 0, D % 4 == 0
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = warp0; r < nrows; r += nwarps) {
+    const int64_t bj = g_begin + r / R.k;
+    const int n = (int)(r - (r / R.k) * R.k);
+    const int64_t b = bj / R.G;
+    const int64_t ni = (int64_t)knn[bj * R.k + n];
+    const float4* src = reinterpret_cast<const float4*>(R.feats + (b * R.N + ni) * D);
+    uint2* dst = reinterpret_cast<uint2*>(out + r * kpad);
+    for (int c = lane; c < d4; c += 32) {
+      const float4 v = __ldg(src + c);
+      dst[c] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+    if (lane < tail4) {
+      uint2 t = make_uint2(0u, 0u);
+      if (lane == 0) {
+        const float* pr = R.x + (b * R.N + ni) * 3;
+        t = make_uint2(pack_bf16x2(pr[0], pr[1]), pack_bf16x2(pr[2], 0.f));
+      }
+      dst[d4 + lane] = t;
+    }
+  }
+}
+
+// out[n][c] = W[n][(c + rot) % K] for c < K, zero padding up to kpad (rot = 3 with the rotated P3Embed row layout)
+__global__ void pad_weight_kernel(const __nv_bfloat16* __restrict__ W, int N, int K, int kpad, int rot, __nv_bfloat16* __restrict__ out) {
   const int total = N * kpad;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int c = e % kpad, n = e / kpad;
-    out[e] = c < K ? W[(size_t)n * K + c] : __float2bfloat16_rn(0.f);
+    out[e] = c < K ? W[(size_t)n * K + (c + rot) % K] : __float2bfloat16_rn(0.f);
   }
 }
 
@@ -795,9 +846,12 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
   const int parts = fused_max ? (int)(k / 32) : 0;
   const bool i64 = (R->kind == 2) || R->idx_dtype == P3TOK_I64;
 
+  // P3Embed rows with a float4-aligned feature width use the rotated [feats | xyz] column order
+  const bool rot_rows = L.kpad0 && R->kind == 1 && R->D % 4 == 0 && R->D >= 4 &&
+                        (reinterpret_cast<uintptr_t>(R->feats) & 15) == 0;
   if (L.kpad0) {
     pad_weight_kernel<<<grid_1d((int64_t)m->pre_dim[0] * L.kpad0, 256), 256, 0, s>>>(
-        (const __nv_bfloat16*)m->w_pre[0], m->pre_dim[0], m->cin, (int)L.kpad0, wpad);
+        (const __nv_bfloat16*)m->w_pre[0], m->pre_dim[0], m->cin, (int)L.kpad0, rot_rows ? 3 : 0, wpad);
     P3_LAUNCH_CHECK("pad_weight_kernel");
   }
 
@@ -829,6 +883,12 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
       P3_LAUNCH_CHECK("rows_first_layer_kernel");
       first_tc = 1;
       kin = m->pre_dim[0];
+    } else if (rot_rows) {
+      const unsigned blocks = grid_1d(rows * 32, 256);
+      if (i64) rows_gather_p4p_bf16_kernel<int64_t><<<blocks, 256, 0, s>>>(*R, g0, rows, (int)L.kpad0, act[cur]);
+      else rows_gather_p4p_bf16_kernel<int32_t><<<blocks, 256, 0, s>>>(*R, g0, rows, (int)L.kpad0, act[cur]);
+      P3_LAUNCH_CHECK("rows_gather_p4p_bf16_kernel");
+      kin = (int)L.kpad0;
     } else {
       if (i64)
         rows_gather_bf16_kernel<int64_t><<<grid_1d(rows * L.kpad0, 256), 256, 0, s>>>(*R, g0, rows, m->cin, (int)L.kpad0, act[cur]);

@@ -175,8 +175,25 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return d;
 }
 
-// max over the warp's 32 rows (lane = row): lane-transpose reduction, lane l returns column l
+// max over the warp's 32 rows (lane = row), lane l returns column l.  One redux.sync.max.f32 per column (SASS
+// CREDUX.MAX.F32, result in a uniform register) instead of the 31-shuffle lane-transpose reduction (kept below for
+// warp_rows_max_shfl): a third of the instructions and nothing on the shuffle/shared-memory pipe.
+// Measured (profiles/microbench/redux_bench.cu, one SM): redux 565 cycles per 32x32 block per warp and ~12 cycles per
+// CREDUX per SM sub-partition however many warps; shuffle transpose 363 cycles per block per warp, 61 per block per SM
+// with 8 warps.  redux wins where the shuffle/shared-memory pipe is the contended resource (tc_linear epilogues with
+// swizzled stores), the shuffle version where one warp per sub-partition must finish several blocks per tile
+// (embed_stage.cu output epilogue).
 __device__ __forceinline__ float warp_rows_max(float (&v)[32], int lane) {
+  float m = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v[j]));
+    if (lane == j) m = r;
+  }
+  return m;
+}
+__device__ __forceinline__ float warp_rows_max_shfl(float (&v)[32], int lane) {
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
     const bool hi = (lane & off) != 0;
@@ -188,6 +205,19 @@ __device__ __forceinline__ float warp_rows_max(float (&v)[32], int lane) {
     }
   }
   return v[0];
+}
+
+// (o0, o1) = (a0 + b0, a1 + b1) as one packed FADD2
+__device__ __forceinline__ void add2(float& o0, float& o1, float a0, float a1, float b0, float b1) {
+  asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd; }"
+      : "=f"(o0), "=f"(o1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// bf16x2 {lo = relu(a), hi = relu(b)}: ReLU fused into the conversion (F2FP.RELU.BF16.F32.PACK_AB)
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
