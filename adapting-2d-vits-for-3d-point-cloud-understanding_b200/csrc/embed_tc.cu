@@ -33,6 +33,7 @@
 // activation tile were tried and measured neutral (kept behind P3TOK_TC_CLUSTER / P3TOK_TC_PREFETCH).
 // The concat layer W.[g||f] is evaluated as W_g.g (tensor-core GEMM over groups, becomes the per-group bias)
 // + W_f.f, so no (rows, 2E) tensor exists.
+#include <algorithm>
 #include <vector>
 
 #include "tc_common.cuh"
@@ -594,6 +595,103 @@ rows_first_layer_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, const __nv
   }
 }
 
+// Narrow P3Embed / direct rows (kind 1 or 2, cin <= 8) with nout = 32 * NPL.  One WARP owns a 32-row block at a time
+// (lane = row for the gather, lane = NPL consecutive output channels for the layer), walks several blocks and has the
+// next block's gathered inputs in registers while it computes the current one: no block-level barrier, the two
+// dependent global loads (neighbour index -> point) of block i+1 overlap the FMAs of block i.  The generic kernel above
+// left half of its threads idle at nout = 128, paid three 64-bit divisions per gathered element and exposed the gather
+// latency once per CTA (133 us per 2^20 rows).
+template <typename IdxT, int NPL>
+__global__ void __launch_bounds__(128)
+rows_first_layer_narrow_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, const __nv_bfloat16* __restrict__ W,
+                               const float* __restrict__ bias, int cin, int relu, __nv_bfloat16* __restrict__ out,
+                               __nv_bfloat16* __restrict__ gmax32) {
+  constexpr int NOUT = 32 * NPL;
+  __shared__ __align__(16) float xin_all[4][32][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float (*xin)[8] = xin_all[warp];
+  const int64_t nblocks = (nrows + 31) >> 5;
+  const int64_t wstride = (int64_t)gridDim.x * 4;
+  // gathered input of row (blk*32 + lane): 8 floats, zero beyond cin / nrows
+  auto gather = [&](int64_t blk, float (&v)[8]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = 0.f;
+    const int64_t r = blk * 32 + lane;
+    if (blk >= nblocks || r >= nrows) return;
+    if (R.kind == 2) {
+      const float* src = R.x + (g_begin * R.k + r) * cin;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) if (c < cin) v[c] = src[c];
+    } else {
+      const int64_t gq = r / R.k;
+      const int n = (int)(r - gq * R.k);
+      const int64_t bj = g_begin + gq;
+      const int64_t b = bj / R.G;
+      const int64_t ni = (int64_t)reinterpret_cast<const IdxT*>(R.knn_idx)[bj * R.k + n];
+      const float* pr = R.x + (b * R.N + ni) * 3;
+      const float* fr = R.feats + (b * R.N + ni) * R.D;
+      v[0] = pr[0]; v[1] = pr[1]; v[2] = pr[2];
+#pragma unroll
+      for (int c = 3; c < 8; ++c) if (c < cin) v[c] = fr[c - 3];
+    }
+  };
+  float w[NPL][8], b[NPL];
+#pragma unroll
+  for (int j = 0; j < NPL; ++j) {
+    const int n = lane * NPL + j;
+    b[j] = bias ? bias[n] : 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) w[j][c] = c < cin ? __bfloat162float(W[(size_t)n * cin + c]) : 0.f;
+  }
+  int64_t blk = (int64_t)blockIdx.x * 4 + warp;
+  float nxt[8];
+  gather(blk, nxt);
+  for (; blk < nblocks; blk += wstride) {
+    __syncwarp();                                    // the previous block's broadcasts are done
+    *reinterpret_cast<float4*>(&xin[lane][0]) = make_float4(nxt[0], nxt[1], nxt[2], nxt[3]);
+    *reinterpret_cast<float4*>(&xin[lane][4]) = make_float4(nxt[4], nxt[5], nxt[6], nxt[7]);
+    __syncwarp();
+    gather(blk + wstride, nxt);                      // in flight during the loop below
+    const int64_t r0 = blk * 32;
+    const int nr = (int)((nrows - r0) < 32 ? (nrows - r0) : 32);
+    float m[NPL];
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) m[j] = -3.0e38f;
+#pragma unroll 4
+    for (int row = 0; row < nr; ++row) {
+      const float4 x0 = *reinterpret_cast<const float4*>(&xin[row][0]);   // warp-wide broadcasts
+      const float4 x1 = *reinterpret_cast<const float4*>(&xin[row][4]);
+      float a[NPL];
+#pragma unroll
+      for (int j = 0; j < NPL; ++j) {
+        float t = fmaf(w[j][0], x0.x, b[j]);
+        t = fmaf(w[j][1], x0.y, t); t = fmaf(w[j][2], x0.z, t); t = fmaf(w[j][3], x0.w, t);
+        t = fmaf(w[j][4], x1.x, t); t = fmaf(w[j][5], x1.y, t); t = fmaf(w[j][6], x1.z, t); t = fmaf(w[j][7], x1.w, t);
+        if (relu) t = fmaxf(t, 0.f);
+        a[j] = t;
+        m[j] = fmaxf(m[j], t);
+      }
+      uint32_t pk[NPL / 2];
+#pragma unroll
+      for (int j = 0; j < NPL / 2; ++j) pk[j] = pack_bf16x2(a[2 * j], a[2 * j + 1]);
+      __nv_bfloat16* o = out + (r0 + row) * NOUT + lane * NPL;
+      if (NPL == 2) *reinterpret_cast<uint32_t*>(o) = pk[0];
+      else if (NPL == 4) *reinterpret_cast<uint2*>(o) = make_uint2(pk[0], pk[1 % (NPL / 2)]);
+      else *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1 % (NPL / 2)], pk[2 % (NPL / 2)], pk[3 % (NPL / 2)]);
+    }
+    if (gmax32) {
+      // bf16 rounding is monotonic: rounding the fp32 max equals the max of the rounded activations the next GEMM reads
+      uint32_t pm[NPL / 2];
+#pragma unroll
+      for (int j = 0; j < NPL / 2; ++j) pm[j] = pack_bf16x2(m[2 * j], m[2 * j + 1]);
+      __nv_bfloat16* o = gmax32 + blk * NOUT + lane * NPL;
+      if (NPL == 2) *reinterpret_cast<uint32_t*>(o) = pm[0];
+      else if (NPL == 4) *reinterpret_cast<uint2*>(o) = make_uint2(pm[0], pm[1 % (NPL / 2)]);
+      else *reinterpret_cast<uint4*>(o) = make_uint4(pm[0], pm[1 % (NPL / 2)], pm[2 % (NPL / 2)], pm[3 % (NPL / 2)]);
+    }
+  }
+}
+
 // APF rows whose 32-row block lies inside one patch (k % 32 == 0): the input is [nbr - ctr || ctr], and the centre
 // half is the same for all 32 rows, so its contribution W[:, C:2C].ctr + bias is formed once per block and each
 // row costs C (3 or 4) FMAs per output channel instead of 2C (apf.py:83-95 feeding apf.py:130).
@@ -697,24 +795,37 @@ rows_gather_p4p_bf16_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, int kp
   const int D = R.D, d4 = D >> 2, tail4 = (kpad - D) >> 2;       // kpad % 8 == 0, D % 4 == 0
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t r = warp0; r < nrows; r += nwarps) {
-    const int64_t bj = g_begin + r / R.k;
-    const int n = (int)(r - (r / R.k) * R.k);
-    const int64_t b = bj / R.G;
-    const int64_t ni = (int64_t)knn[bj * R.k + n];
-    const float4* src = reinterpret_cast<const float4*>(R.feats + (b * R.N + ni) * D);
-    uint2* dst = reinterpret_cast<uint2*>(out + r * kpad);
-    for (int c = lane; c < d4; c += 32) {
-      const float4 v = __ldg(src + c);
-      dst[c] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  // four rows per warp iteration: the four neighbour indices, then the four feature rows, are independent loads in flight
+  // together (one row per iteration was bound by two dependent round trips: 305 us per 2^20 rows)
+  for (int64_t r4 = warp0 * 4; r4 < nrows; r4 += nwarps * 4) {
+    const float4* src[4];
+    const float* pr[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = (r4 + u < nrows) ? r4 + u : nrows - 1;
+      const int64_t gq = r / R.k;
+      const int64_t bj = g_begin + gq;
+      const int64_t b = bj / R.G;
+      const int64_t ni = (int64_t)knn[bj * R.k + (r - gq * R.k)];
+      src[u] = reinterpret_cast<const float4*>(R.feats + (b * R.N + ni) * D);
+      pr[u] = R.x + (b * R.N + ni) * 3;
     }
-    if (lane < tail4) {
-      uint2 t = make_uint2(0u, 0u);
-      if (lane == 0) {
-        const float* pr = R.x + (b * R.N + ni) * 3;
-        t = make_uint2(pack_bf16x2(pr[0], pr[1]), pack_bf16x2(pr[2], 0.f));
+    for (int c = lane; c < d4; c += 32) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(src[u] + c);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r4 + u < nrows)
+          reinterpret_cast<uint2*>(out + (r4 + u) * kpad)[c] = make_uint2(pack_bf16x2(v[u].x, v[u].y), pack_bf16x2(v[u].z, v[u].w));
+    }
+    if (lane < 4 * tail4) {                          // [xyz, 0 | zeros] tail of row u = lane / tail4
+      const int u = lane / tail4, piece = lane - u * tail4;
+      if (r4 + u < nrows) {
+        uint2 t = make_uint2(0u, 0u);
+        if (piece == 0) t = make_uint2(pack_bf16x2(pr[u][0], pr[u][1]), pack_bf16x2(pr[u][2], 0.f));
+        reinterpret_cast<uint2*>(out + (r4 + u) * kpad)[d4 + piece] = t;
       }
-      dst[d4 + lane] = t;
     }
   }
 }
@@ -877,6 +988,16 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
                                                                           m->b_pre[0], m->pre_dim[0], m->pre_relu[0], act[cur]);
         else rows_first_layer_apf_kernel<int32_t><<<blocks, 128, 0, s>>>(*R, g0, rows, (const __nv_bfloat16*)m->w_pre[0],
                                                                          m->b_pre[0], m->pre_dim[0], m->pre_relu[0], act[cur]);
+      } else if (R->kind != 0 && m->cin <= 8 && (m->pre_dim[0] == 64 || m->pre_dim[0] == 128 || m->pre_dim[0] == 256)) {
+#define P3_L1N(IDX, NPL)                                                                                          \
+  rows_first_layer_narrow_kernel<IDX, NPL><<<nblk_narrow, 128, 0, s>>>(*R, g0, rows, (const __nv_bfloat16*)m->w_pre[0], \
+                                                                  m->b_pre[0], m->cin, m->pre_relu[0], act[cur], l1_gmax)
+        const int npl = m->pre_dim[0] / 32;
+        // ~6 row blocks per warp: enough to amortise the weight loads and to keep one gather in flight per warp
+        const unsigned nblk_narrow = (unsigned)std::min<int64_t>((blocks + 3) / 4, (int64_t)num_sms() * 10);
+        if (i64) { if (npl == 2) P3_L1N(int64_t, 2); else if (npl == 4) P3_L1N(int64_t, 4); else P3_L1N(int64_t, 8); }
+        else     { if (npl == 2) P3_L1N(int32_t, 2); else if (npl == 4) P3_L1N(int32_t, 4); else P3_L1N(int32_t, 8); }
+#undef P3_L1N
       } else if (m->cin <= 8) { if (i64) P3_L1(int64_t, 8); else P3_L1(int32_t, 8); }
       else             { if (i64) P3_L1(int64_t, 16); else P3_L1(int32_t, 16); }
 #undef P3_L1

@@ -152,25 +152,35 @@ knn_kernel(const float* __restrict__ x, int N, int pt_stride, const float* __res
       const int i = i0 + lane;
       const bool valid = i < cnt;
       const float4 p = tile[valid ? i : 0];
+      // all CPW distance chains first (independent: instruction-level parallelism), ONE vote for the common case
+      // "no candidate for any of the warp's centres", then the per-centre handling
+      float dc[KNN_CPW];
+      bool pc[KNN_CPW];
+      bool any = false;
 #pragma unroll
       for (int c = 0; c < KNN_CPW; ++c) {
-        float d;
-        bool pass;
         if (MODE == P3TOK_KNN_APF_SQ) {
           const float dot = __fmaf_rn(c2[c], p.z, __fmaf_rn(c1[c], p.y, __fmul_rn(c0[c], p.x)));
           float tt = __fmul_rn(-2.f, dot);
           tt = __fadd_rn(tt, cn[c]);
-          d = __fadd_rn(__fadd_rn(tt, p.w), 0.f);
-          pass = valid && (d < thr[c]);
+          dc[c] = __fadd_rn(__fadd_rn(tt, p.w), 0.f);
+          pc[c] = valid && (dc[c] < thr[c]);
         } else {
           float tt = __fmul_rn(c0[c], p.x);
           tt = __fmaf_rn(c1[c], p.y, tt);
           tt = __fmaf_rn(c2[c], p.z, tt);
           tt = __fadd_rn(tt, cn[c]);      // fma(|c|^2, 1, t)
           tt = __fadd_rn(tt, p.w);        // fma(1, |p|^2, t)
-          d = tt;
-          pass = valid && (tt <= thr[c]); // conservative: exact sqrt test below
+          dc[c] = tt;
+          pc[c] = valid && (tt <= thr[c]); // conservative: exact sqrt test below
         }
+        any = any || pc[c];
+      }
+      if (!__any_sync(0xffffffffu, any)) continue;
+#pragma unroll
+      for (int c = 0; c < KNN_CPW; ++c) {
+        float d = dc[c];
+        bool pass = pc[c];
         uint32_t ball = __ballot_sync(0xffffffffu, pass);
         if (ball == 0) continue;
         if (MODE == P3TOK_KNN_P4P_CDIST) {
