@@ -72,6 +72,18 @@ __device__ __forceinline__ void fps_wait_cands(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// packed fp32 pairs: one instruction, two independent IEEE operations (round-to-nearest each)
+__device__ __forceinline__ void fps_add2(float& o0, float& o1, float a0, float a1, float b0, float b1) {
+  asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd; }"
+      : "=f"(o0), "=f"(o1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fps_mul2(float& o0, float& o1, float a0, float a1, float b0, float b1) {
+  asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd; }"
+      : "=f"(o0), "=f"(o1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 template <int CL>
 __global__ void __launch_bounds__(FPS_MAX_THREADS, 1)
 fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __restrict__ start_idx,
@@ -169,18 +181,41 @@ fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __r
   for (int g = 0; g < G; ++g) {
     if (t == 0 && rank == 0) out_idx[(size_t)cloud * G + g] = far;
     if (g == G - 1) break;
-    float best = -1.f;
-    int besti = 0;
+    // Distance updates two points per instruction (FADD2 / FMUL2: each half is an IEEE fp32 op, so the reference's
+    // ((dx*dx)+(dy*dy))+(dz*dz) rounding sequence is unchanged; x - c is computed as x + (-c), bit-identical).
+    const float ncx = -cx, ncy = -cy, ncz = -cz;
 #pragma unroll
-    for (int j = 0; j < FPS_PPT; ++j) {
-      const float dx = __fsub_rn(px[j], cx), dy = __fsub_rn(py[j], cy), dz = __fsub_rn(pz[j], cz);
-      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-      md[j] = fminf(md[j], d);
-      if (md[j] > best) { best = md[j]; besti = j; }
+    for (int j = 0; j < FPS_PPT; j += 2) {
+      float dx0, dx1, dy0, dy1, dz0, dz1;
+      fps_add2(dx0, dx1, px[j], px[j + 1], ncx, ncx);
+      fps_add2(dy0, dy1, py[j], py[j + 1], ncy, ncy);
+      fps_add2(dz0, dz1, pz[j], pz[j + 1], ncz, ncz);
+      fps_mul2(dx0, dx1, dx0, dx1, dx0, dx1);
+      fps_mul2(dy0, dy1, dy0, dy1, dy0, dy1);
+      fps_mul2(dz0, dz1, dz0, dz1, dz0, dz1);
+      fps_add2(dx0, dx1, dx0, dx1, dy0, dy1);
+      fps_add2(dx0, dx1, dx0, dx1, dz0, dz1);
+      md[j] = fminf(md[j], dx0);
+      md[j + 1] = fminf(md[j + 1], dx1);
     }
+    // thread-local maximum first; the index of the maximum is only resolved by the threads that tie with the warp's
+    // maximum (usually one): lowest j == lowest point index inside a thread, lowest index wins across threads
+    float best = md[0];
+#pragma unroll
+    for (int j = 1; j < FPS_PPT; ++j) best = fmaxf(best, md[j]);
     uint32_t key = best >= 0.f ? __float_as_uint(best) : 0u;
-    uint32_t idx = best >= 0.f ? (uint32_t)(p0 + besti * T + t) : 0xffffffffu;
-    warp_argmax(key, idx);
+    uint32_t idx = 0xffffffffu;
+    {
+      const uint32_t wmax = __reduce_max_sync(0xffffffffu, key);
+      if (key == wmax && best >= 0.f) {
+        int besti = FPS_PPT - 1;
+#pragma unroll
+        for (int j = FPS_PPT - 2; j >= 0; --j) besti = (md[j] == best) ? j : besti;
+        idx = (uint32_t)(p0 + besti * T + t);
+      }
+      idx = __reduce_min_sync(0xffffffffu, idx);
+      key = wmax;
+    }
     const int buf = g & 1;
     if (lane == 0) wslot[buf * 32 + warp] = make_uint2(key, idx);
     __syncthreads();
