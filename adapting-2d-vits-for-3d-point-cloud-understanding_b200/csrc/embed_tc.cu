@@ -47,7 +47,9 @@ constexpr int TC_MAX_STAGES = 8, TC_MAX_BN = 256;
 #endif
 constexpr int TC_EPI_WARPS = P3TOK_EPI_WARPS;        // 2 (or 4) warps per TMEM lane quarter, interleaved 64-column groups
 constexpr int TC_EPI_PER_Q = TC_EPI_WARPS / 4;
-constexpr int TC_THREADS = 64 + TC_EPI_WARPS * 32;   // warp 0 TMA, warp 1 MMA, the rest epilogue
+constexpr int TC_THREADS = 64 + TC_EPI_WARPS * 32 + 32;   // warp 0 TMA, warp 1 MMA, epilogue warps, last warp = A producer (A-resident mode)
+constexpr int TC_ARES_WARP = 2 + TC_EPI_WARPS;
+constexpr int TC_MAX_KB = 8;                         // A-resident mode: K <= 512
 constexpr int TC_A_STAGE = TC_BM * TC_BK * 2;        // 16 KB
 constexpr int TC_STAGING = 32 * 128;                 // one 32-row x 64-column bf16 store box (4 KB, 128B-swizzled)
 constexpr int TC_MAX_N = 2048;                       // bias vector staged in shared memory (8 KB)
@@ -55,7 +57,11 @@ constexpr int TC_MAX_N = 2048;                       // bias vector staged in sh
 // is sized at launch to fill what is left: a stage round trip (TMA latency ~1500 cycles + MMA drain) needs
 // >= ingest_rate x latency bytes in flight, so the pair mode (32 KB stages) runs 5-6 stages deep.
 constexpr int TC_SMEM = 227 * 1024;
-constexpr int TC_WARP_SCRATCH = 2 * TC_STAGING;      // two 1024-aligned store boxes (double-buffered TMA stores)
+#ifndef P3TOK_EPI_BOXES
+#define P3TOK_EPI_BOXES (P3TOK_EPI_WARPS > 8 ? 1 : 2)
+#endif
+constexpr int TC_EPI_BOXES = P3TOK_EPI_BOXES;        // TMA-store boxes per epilogue warp (2 = double-buffered)
+constexpr int TC_WARP_SCRATCH = TC_EPI_BOXES * TC_STAGING;   // 1024-aligned store boxes
 constexpr int TC_SGB_BYTES = 256;                    // per-warp 64-float group-bias slice
 constexpr int TC_SMEM_FIXED = TC_EPI_WARPS * (TC_WARP_SCRATCH + TC_SGB_BYTES) + TC_MAX_N * 4 + 512 + 1024;
 
@@ -75,15 +81,30 @@ struct TcParams {
   int max_relu;            // apply ReLU to the max (out_relu of the block)
   int stages, stage_bytes; // TMA->MMA ring depth and bytes per stage (A tile 16 KB + this CTA's part of the weight tile)
   int prefetch;            // L2-prefetch the next item's activation tile
+  int ares;                // A-resident mode (pairs only): a pair walks ALL N tiles of its M group, the group's activation
+                           // rows stay in shared memory and only weight boxes stream through the ring
   unsigned long long* trace;  // debug (P3TOK_TC_TRACE=1): per-CTA clock stamps, 16 words per tile per role
+  unsigned long long* trace2; // debug: epilogue warp 0 of CTA 0, 8 stamps per (tile < 8, column group < 4)
 };
 // trace layout: trace[((cta * 64 + tile_it) * 3 + role) * 4 + {0..3}]
 __device__ __forceinline__ void tc_trace(const TcParams& p, int it, int role, int slot, long long v) {
   if (p.trace && it < 64) p.trace[(((size_t)blockIdx.x * 64 + it) * 3 + role) * 4 + slot] = (unsigned long long)v;
 }
+// stamps of one column group: 0 start, 1 store box free, 2 first TMEM load back, 3 first half converted, 4 second load back,
+// 5 second half converted, 6 store issued
+__device__ __forceinline__ void tc_trace2(const TcParams& p, bool on, int it, int g, int slot) {
+  if (on && it < 8 && g < 4) p.trace2[(it * 4 + g) * 8 + slot] = (unsigned long long)clock64();
+}
 
 // bias / per-group bias / ReLU on 32 accumulator columns starting at global column n0.  `sbias` is the
 // bias vector staged in shared memory (zeros when the layer has none); all loads are issued before use.
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {   // explicit shared-space load (the generic form costs an LD + address check)
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
+// `sbias` is staged zero-padded to a multiple of 64 columns, so the 32 columns starting at n0 are always readable.
 __device__ __forceinline__ void epilogue_affine(float (&v)[32], const TcParams& p, const float* sbias, const float* gb, int n0,
                                                 bool relu_now) {
   const int nmax = p.N - 4;                                  // N % 8 == 0: clamped float4 loads stay in range
@@ -92,11 +113,14 @@ __device__ __forceinline__ void epilogue_affine(float (&v)[32], const TcParams& 
 #pragma unroll
     for (int j = 0; j < 8; ++j) g4[j] = __ldg(reinterpret_cast<const float4*>(gb + min(n0 + 4 * j, nmax)));
   }
+  if (p.bias) {                                              // warp-uniform: layers whose bias rides in the group bias skip it
+    const uint32_t sb = smem_u32(sbias + n0);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 b4 = *reinterpret_cast<const float4*>(sbias + min(n0 + 4 * j, nmax));
-    add2(v[4 * j], v[4 * j + 1], v[4 * j], v[4 * j + 1], b4.x, b4.y);
-    add2(v[4 * j + 2], v[4 * j + 3], v[4 * j + 2], v[4 * j + 3], b4.z, b4.w);
+    for (int j = 0; j < 8; ++j) {
+      const float4 b4 = lds128(sb + 16 * j);
+      add2(v[4 * j], v[4 * j + 1], v[4 * j], v[4 * j + 1], b4.x, b4.y);
+      add2(v[4 * j + 2], v[4 * j + 3], v[4 * j + 2], v[4 * j + 3], b4.z, b4.w);
+    }
   }
   if (gb) {
 #pragma unroll
@@ -118,9 +142,10 @@ __device__ __forceinline__ void epilogue_half(const TcParams& p, const float* sb
                                               uint32_t sbox, int half, int row0, int row, bool row_ok, int lane, int n0,
                                               float (&v)[32]) {
   if (sgb) {   // this warp's group-bias slice (64 floats for the whole column group), staged in shared memory
+    const uint32_t sg = smem_u32(sgb + 32 * half);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float4 g = *reinterpret_cast<const float4*>(sgb + 32 * half + 4 * j);
+      const float4 g = lds128(sg + 16 * j);
       add2(v[4 * j], v[4 * j + 1], v[4 * j], v[4 * j + 1], g.x, g.y);
       add2(v[4 * j + 2], v[4 * j + 3], v[4 * j + 2], v[4 * j + 3], g.z, g.w);
     }
@@ -178,24 +203,44 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int TC_STAGES = p.stages, STAGE_BYTES = p.stage_bytes;   // stage s starts at s*STAGE_BYTES: A tile (16 KB), then the weight rows
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + TC_A_STAGE;
-  uint8_t* sC = smem + TC_STAGES * p.stage_bytes;     // per-epilogue-warp store staging, 4 KB each
+  const int num_kb = (p.K + TC_BK - 1) / TC_BK;
+  const int ARES = PAIR ? p.ares : 0;
+  const int ares_bytes = ARES ? num_kb * TC_A_STAGE : 0;   // resident activation K blocks in front of the ring
+  uint8_t* sAres = smem;
+  uint8_t* sA = smem + ares_bytes;
+  uint8_t* sB = sA + (ARES ? 0 : TC_A_STAGE);
+  uint8_t* sC = sA + TC_STAGES * p.stage_bytes;       // per-epilogue-warp store staging, 4 KB each
   float* sgb_all = reinterpret_cast<float*>(sC + TC_EPI_WARPS * TC_WARP_SCRATCH);
   float* sbias = reinterpret_cast<float*>(sC + TC_EPI_WARPS * (TC_WARP_SCRATCH + TC_SGB_BYTES));
   uint64_t* full = reinterpret_cast<uint64_t*>(sC + TC_EPI_WARPS * (TC_WARP_SCRATCH + TC_SGB_BYTES) + TC_MAX_N * 4);
   uint64_t* empty = full + TC_MAX_STAGES;
   uint64_t* tfull = empty + TC_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* a_full = tempty + 2;                      // [TC_MAX_KB] leader (A-resident mode)
+  uint64_t* a_empty = a_full + TC_MAX_KB;             // [TC_MAX_KB] local, multicast commit
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + TC_MAX_KB);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform role index
   const int lane = threadIdx.x & 31;
   const int CL = p.CL;
   const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
-  const int num_items = ((p.num_m_tiles + CL - 1) / CL) * p.num_n_tiles;   // (group of CL M tiles) x N tile
-  const int num_kb = (p.K + TC_BK - 1) / TC_BK;
+  const int num_mg = (p.num_m_tiles + CL - 1) / CL;
+  const int num_items = num_mg * p.num_n_tiles;   // (group of CL M tiles) x N tile
+  // local work list: entry li of this cluster is (M group mg, N tile nt).  Default: items round-robin over clusters;
+  // A-resident: whole M groups round-robin, their N tiles back to back.
+  auto decode = [&](int li, int& mg, int& nt) -> bool {
+    if (ARES) {
+      const int g = li / p.num_n_tiles;
+      nt = li - g * p.num_n_tiles;
+      mg = cluster_id + g * num_clusters;
+      return mg < num_mg;
+    }
+    const int item = cluster_id + li * num_clusters;
+    mg = item / p.num_n_tiles;
+    nt = item - mg * p.num_n_tiles;
+    return item < num_items;
+  };
   const uint16_t mc_mask = (uint16_t)((1u << CL) - 1);
 
   if (threadIdx.x == 0) {
@@ -209,9 +254,13 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tfull[b], 1);
       mbar_init(&tempty[b], PAIR ? 2 * TC_EPI_WARPS : TC_EPI_WARPS);   // pair: both CTAs' epilogues report to the leader
     }
+    for (int b = 0; b < TC_MAX_KB; ++b) {
+      mbar_init(&a_full[b], 1);
+      mbar_init(&a_empty[b], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < p.N; i += TC_THREADS) sbias[i] = p.bias ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < ((p.N + 63) & ~63); i += TC_THREADS) sbias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;   // zero-padded to 64
   if (warp == 1) {   // TMEM: 512 columns = two 128 x BN fp32 accumulators (this CTA's 128 rows)
     if (PAIR) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
@@ -234,16 +283,17 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     // bytes landing on this CTA's (pair: the leader's) full barrier per stage
-    const uint32_t tx = PAIR ? 2u * (TC_A_STAGE + (uint32_t)(p.BN / 2) * TC_BK * 2) : TC_A_STAGE + (uint32_t)p.BN * TC_BK * 2;
+    const uint32_t tx = PAIR ? 2u * ((ARES ? 0u : (uint32_t)TC_A_STAGE) + (uint32_t)(p.BN / 2) * TC_BK * 2)
+                             : TC_A_STAGE + (uint32_t)p.BN * TC_BK * 2;
     const int brows = p.BN / CL;     // rows of the weight tile this CTA fetches (and multicasts)
-    for (int item = cluster_id; item < num_items; item += num_clusters) {
-      const int mg = item / p.num_n_tiles, nt = item - mg * p.num_n_tiles;
+    int mg, nt;
+    for (int li = 0; decode(li, mg, nt); ++li) {
       const int mt = mg * CL + rank;   // may be a dummy tile past the end: TMA zero-fills, stores are clipped
-      if (p.prefetch && issuer) {
+      if (p.prefetch && issuer && !ARES) {
         // pull the NEXT item's activation tile (streamed from HBM exactly once) into L2 ahead of its loads
-        const int nitem = item + num_clusters;
-        if (nitem < num_items) {
-          const int nmt = (nitem / p.num_n_tiles) * CL + rank;
+        int nmg, nnt;
+        if (decode(li + 1, nmg, nnt)) {
+          const int nmt = nmg * CL + rank;
           if (nmt < p.num_m_tiles)
             for (int kb = 0; kb < num_kb; ++kb) tma_prefetch_2d(&tmA, kb * TC_BK, nmt * TC_BM);
         }
@@ -251,13 +301,13 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (issuer) {
-          if (kb == 0) tc_trace(p, (item - cluster_id) / num_clusters, 0, 0, clock64());
-          if (kb == num_kb - 1) tc_trace(p, (item - cluster_id) / num_clusters, 0, 1, clock64());
+          if (kb == 0) tc_trace(p, li, 0, 0, clock64());
+          if (kb == num_kb - 1) tc_trace(p, li, 0, 1, clock64());
           uint8_t* a_dst = sA + stage * STAGE_BYTES;
           uint8_t* b_dst = sB + stage * STAGE_BYTES;
           if (PAIR) {
             if (rank == 0) mbar_expect_tx(&full[stage], tx);
-            tma_load_2d_pair(a_dst, &tmA, &full[stage], kb * TC_BK, mt * TC_BM);
+            if (!ARES) tma_load_2d_pair(a_dst, &tmA, &full[stage], kb * TC_BK, mt * TC_BM);
             tma_load_2d_pair(b_dst, &tmB, &full[stage], kb * TC_BK, nt * p.BN + rank * brows);
           } else {
             mbar_expect_tx(&full[stage], tx);
@@ -270,6 +320,23 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
       }
     }
+  } else if (warp == TC_ARES_WARP) {
+    // ---------------- A producer (A-resident mode): the M group's activation rows, one 64-column K block at a time.
+    // K block kb of the next group is fetched as soon as the last N tile of the current group has consumed it.
+    if (ARES) {
+      const bool issuer = elect_one();
+      for (int g = 0, mg = cluster_id; mg < num_mg; mg += num_clusters, ++g) {
+        const int mt = mg * CL + rank;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&a_empty[kb], ((uint32_t)g & 1) ^ 1);
+          if (issuer) {
+            if (rank == 0) mbar_expect_tx(&a_full[kb], 2u * (uint32_t)TC_A_STAGE);
+            tma_load_2d_pair(sAres + kb * TC_A_STAGE, &tmA, &a_full[kb], kb * TC_BK, mt * TC_BM);
+          }
+          __syncwarp();
+        }
+      }
+    }
   } else if (warp == 1) {
     if (!PAIR || rank == 0) {
       // ---------------- MMA issuer (pair: the leader issues for both SMs); warp-uniform loop, one elected lane
@@ -279,22 +346,25 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                              ((uint32_t)((PAIR ? 2 * TC_BM : TC_BM) >> 4) << 24);
       const uint64_t dconst = umma_desc_sw128(0);                 // everything but the start address
       const uint32_t a_base = smem_u32(sA) >> 4, b_base = smem_u32(sB) >> 4, stage_step = (uint32_t)STAGE_BYTES >> 4;
+      const uint32_t ares_base = smem_u32(sAres) >> 4;
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
+      int mg, nt;
+      for (int it = 0; decode(it, mg, nt); ++it) {
         const int buf = it & 1;
         if (issuer) tc_trace(p, it, 1, 0, clock64());
         mbar_wait(&tempty[buf], ((uint32_t)(it >> 1) & 1) ^ 1);
         if (issuer) tc_trace(p, it, 1, 1, clock64());
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.BN);
+        const uint32_t gpar = ARES ? (uint32_t)(it / p.num_n_tiles) & 1 : 0;   // parity of this M group's A barriers
         for (int kb = 0; kb < num_kb; ++kb) {
+          if (ARES && nt == 0) mbar_wait(&a_full[kb], gpar);      // this group's K block kb is resident (both CTAs)
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           if (issuer) {
             if (kb == 0) tc_trace(p, it, 1, 2, clock64());
-            const uint64_t adesc = dconst | (uint64_t)(a_base + stage * stage_step);
+            const uint64_t adesc = dconst | (uint64_t)(ARES ? ares_base + kb * (TC_A_STAGE >> 4) : a_base + stage * stage_step);
             const uint64_t bdesc = dconst | (uint64_t)(b_base + stage * stage_step);
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {   // +32 bytes (2 x 16 B units) per 16-wide K step inside the swizzle atom
@@ -304,6 +374,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (PAIR) tc_commit_pair(&empty[stage]);      // frees the stage in both CTAs of the pair
             else if (CL == 1) tc_commit(&empty[stage]);   // frees the smem stage once these MMAs have read it
             else tc_commit_mc(&empty[stage], mc_mask);    // ... in every CTA that multicasts into it
+            if (PAIR && ARES && nt == p.num_n_tiles - 1) tc_commit_pair(&a_empty[kb]);   // last reader of this group's K block
           }
           __syncwarp();
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -321,9 +392,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3, h = ew >> 2;
     uint8_t* stg = sC + ew * TC_WARP_SCRATCH;   // 1024-aligned: the TMA store un-swizzles by address bits
     int sbuf = 0;
-    int it = 0;
-    for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
-      const int mg = item / p.num_n_tiles, nt = item - mg * p.num_n_tiles;
+    // (Fetching the per-warp group-bias slice one column group ahead was measured twice: the 384->768 layer went from
+    // 338 to 376 us, the extra live registers and address arithmetic cost more than the hidden L2 round trip.)
+    int mg, nt;
+    for (int it = 0; decode(it, mg, nt); ++it) {
       const int mt = mg * CL + rank;
       const int buf = it & 1;
       if (ew == 0 && lane == 0) tc_trace(p, it, 2, 0, clock64());
@@ -344,6 +416,9 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int gi = h; gi * 64 < p.BN; gi += TC_EPI_PER_Q) {
         const int n0 = nt * p.BN + gi * 64;
         if (n0 >= p.N || row0 >= p.M) break;     // warp-uniform
+        const bool tr2 = p.trace2 && blockIdx.x == 0 && ew == 0 && lane == 0;
+        const int g2 = (gi - h) / TC_EPI_PER_Q;
+        tc_trace2(p, tr2, it, g2, 0);
         float2 gpre = make_float2(0.f, 0.f);
         if (gb_shared) {
           const int c = min(n0 + 2 * lane, p.N - 2);
@@ -352,9 +427,13 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + gi * 64);
         const uint32_t sbox = smem_u32(stg + sbuf * TC_STAGING);
         if (p.out_bf16) {   // the TMA store issued two groups ago has finished reading this box
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (lane == 0) {
+            if (TC_EPI_BOXES == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
           __syncwarp();
         }
+        tc_trace2(p, tr2, it, g2, 1);
         const bool last = (gi + TC_EPI_PER_Q >= (p.BN >> 6)) || (n0 + 64 * TC_EPI_PER_Q >= p.N);
         float v[32];
         tc_ld32_issue(taddr, v);
@@ -363,9 +442,12 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
         }
         tc_ld_wait();
+        tc_trace2(p, tr2, it, g2, 2);
         epilogue_half(p, sbias, gb_shared ? nullptr : gb, gb_shared ? sgb : nullptr, sbox, 0, row0, row, row_ok, lane, n0, v);
+        tc_trace2(p, tr2, it, g2, 3);
         tc_ld32_issue(taddr + 32, v);
         tc_ld_wait();
+        tc_trace2(p, tr2, it, g2, 4);
         if (last) {
           // this warp has read its last accumulator columns of the tile: hand the TMEM buffer back to the MMA
           // warp now, before the remaining bias / convert / store work
@@ -378,6 +460,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           released = true;
         }
         epilogue_half(p, sbias, gb_shared ? nullptr : gb, gb_shared ? sgb : nullptr, sbox, 1, row0, row, row_ok, lane, n0 + 32, v);
+        tc_trace2(p, tr2, it, g2, 5);
         if (p.out_bf16) {
           // one TMA store of the 32 x 64 bf16 box (clips rows >= M / columns >= N)
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -389,8 +472,9 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          sbuf ^= 1;
+          if (TC_EPI_BOXES == 2) sbuf ^= 1;
         }
+        tc_trace2(p, tr2, it, g2, 6);
         __syncwarp();   // group-bias slice is free for the next group
       }
       if (!released) {   // this warp had no group in the tile (narrow N tile or rows past M)
@@ -474,8 +558,20 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
   }
   {
     const int wrows = pair ? p.BN / 2 : p.BN;
-    p.stage_bytes = TC_A_STAGE + wrows * TC_BK * 2;
-    p.stages = (TC_SMEM - TC_SMEM_FIXED) / p.stage_bytes;
+    // A-resident mode (P3TOK_TC_ARES=0 disables): with several N tiles per M group the default walk re-fetches the same
+    // activation tile once per N tile, and at 128 rows per CTA the L2 -> shared-memory fill (activation tile + half a
+    // weight tile per MMA group, ~62 B/cycle/SM at BN = 256) outruns what TMA delivers (~42 B/cycle/SM) before the
+    // tensor pipe is busy.  Keeping the M group's rows resident halves the fill.
+    static int ares_on = -1;
+    if (ares_on < 0) { const char* e = getenv("P3TOK_TC_ARES"); ares_on = e ? atoi(e) : 1; }
+    const int num_kb = (K + TC_BK - 1) / TC_BK;
+    p.ares = 0;
+    if (ares_on && pair && p.num_n_tiles >= 2 && num_kb <= TC_MAX_KB) {
+      const int ring = TC_SMEM - TC_SMEM_FIXED - num_kb * TC_A_STAGE;
+      if (ring / (wrows * TC_BK * 2) >= 3) p.ares = 1;
+    }
+    p.stage_bytes = (p.ares ? 0 : TC_A_STAGE) + wrows * TC_BK * 2;
+    p.stages = (TC_SMEM - TC_SMEM_FIXED - (p.ares ? num_kb * TC_A_STAGE : 0)) / p.stage_bytes;
     if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
     static int cap = -1;
     if (cap < 0) { const char* e = getenv("P3TOK_TC_STAGES"); cap = e ? atoi(e) : 0; }
@@ -488,11 +584,14 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
   if (trace_on < 0) trace_on = getenv("P3TOK_TC_TRACE") ? 1 : 0;
   p.trace = nullptr;
   const size_t trace_words = (size_t)num_sms() * 64 * 3 * 4;
+  p.trace2 = nullptr;
   if (trace_on) {
     P3_CUDA(cudaMalloc(&p.trace, trace_words * 8));
     P3_CUDA(cudaMemsetAsync(p.trace, 0, trace_words * 8, s));
+    P3_CUDA(cudaMalloc(&p.trace2, 8 * 4 * 8 * 8));
+    P3_CUDA(cudaMemsetAsync(p.trace2, 0, 8 * 4 * 8 * 8, s));
   }
-  const int items = ((p.num_m_tiles + p.CL - 1) / p.CL) * p.num_n_tiles;
+  const int items = p.ares ? (p.num_m_tiles + p.CL - 1) / p.CL : ((p.num_m_tiles + p.CL - 1) / p.CL) * p.num_n_tiles;
   const int max_clusters = num_sms() / p.CL;
   const int clusters = items < max_clusters ? items : max_clusters;
   cudaLaunchConfig_t cfg = {};
@@ -515,7 +614,17 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
     P3_CUDA(cudaStreamSynchronize(s));
     P3_CUDA(cudaMemcpy(h.data(), p.trace, trace_words * 8, cudaMemcpyDeviceToHost));
     P3_CUDA(cudaFree(p.trace));
-    fprintf(stderr, "[tc_trace] M=%d N=%d K=%d BN=%d CL=%d grid=%d\n", p.M, p.N, p.K, p.BN, p.CL, clusters * p.CL);
+    unsigned long long h2[8 * 4 * 8];
+    P3_CUDA(cudaMemcpy(h2, p.trace2, sizeof(h2), cudaMemcpyDeviceToHost));
+    P3_CUDA(cudaFree(p.trace2));
+    for (int it = 2; it < 5; ++it)
+      for (int g = 0; g < 4 && h2[(it * 4 + g) * 8]; ++g) {
+        const unsigned long long* q = &h2[(it * 4 + g) * 8];
+        fprintf(stderr, "[tc_trace2] tile%d group%d: box_free=+%lld ld0=+%lld conv0=+%lld ld1=+%lld conv1=+%lld store=+%lld\n", it, g,
+                (long long)(q[1] - q[0]), (long long)(q[2] - q[1]), (long long)(q[3] - q[2]), (long long)(q[4] - q[3]),
+                (long long)(q[5] - q[4]), (long long)(q[6] - q[5]));
+      }
+    fprintf(stderr, "[tc_trace] M=%d N=%d K=%d BN=%d CL=%d grid=%d ares=%d stages=%d\n", p.M, p.N, p.K, p.BN, p.CL, clusters * p.CL, p.ares, p.stages);
     for (int cta = 0; cta < 2; ++cta) {
       const unsigned long long t0 = h[(((size_t)cta * 64 + 0) * 3 + 1) * 4 + 0];
       for (int it = 0; it < 8; ++it) {

@@ -12,7 +12,7 @@ import re
 from typing import List
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libp3tok.so")
+LIB_PATH = os.environ.get("P3TOK_LIB") or os.path.join(_PKG, "libp3tok.so")   # P3TOK_LIB: A/B builds of the same sources
 HEADER_PATH = os.path.join(os.path.dirname(os.path.dirname(_PKG)), "include", "p3tok.h")
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, 1, 2, 3, 4
