@@ -18,6 +18,9 @@
 // small shared-memory queue by ballot/popc and merged 32 at a time with a warp bitonic sort +
 // bitonic merges.  The result is ascending by (distance, index): the canonical instance of
 // torch.topk's implementation-defined tie order.
+// Measured and rejected: direct per-candidate insertion (0.196 vs 0.12 ms at C2); two points per lane with packed
+// f32x2 distance arithmetic (FFMA2/FADD2: c3 6.1 -> 7.7 ms, c5 0.59 -> 0.97 ms - twice the votes per active step and a
+// vote is true twice as often; the queue merges, not the distance arithmetic, are what the kernel spends its time on).
 #include "common.cuh"
 
 namespace p3tok {
@@ -246,6 +249,318 @@ static int knn_launch(const float* x, int B, int N, int pt_stride, const float* 
   return P3TOK_OK;
 }
 
+
+// ================================================================================================
+// Spatially sorted variant (clouds of up to 8192 points): the sweep above evaluates every (centre, point) pair and its
+// running threshold only tightens as fast as random-order points allow (~k(1+ln(N/k)) candidates, ~10 merges per centre
+// at N = 8192).  Here a preparation kernel sorts each cloud along a Z-order curve once, so that 32 consecutive points
+// are a compact block with a bounding box; a warp then owns ONE centre: it seeds its list from the blocks around the
+// centre's own position on the curve (tight threshold after ~96 points), tests all block boxes against the threshold
+// 32 at a time (one lane per block), and evaluates only the blocks that can still contribute.  Distances, keys and the
+// result are exactly those of the sweep: a block is skipped only if a lower bound of the COMPUTED distance (geometric
+// bound minus a margin far above the rounding error of the expansion formula) exceeds the current k-th distance, and
+// because points no longer arrive in index order the filter is non-strict (<=): ties at the k-th distance reach the
+// merge, which orders by (distance, index).
+constexpr int KNS_MAX_N = 8192;
+constexpr int KNS_CELLS = 512;                 // coarse Z-order cells (top 9 bits of the 30-bit code) for the start position
+
+struct KnsLayout {
+  int64_t off_pts, off_ids, off_bb, off_lut, off_meta, total;
+};
+static KnsLayout kns_layout(int64_t B, int64_t N) {
+  KnsLayout L;
+  const int64_t nblk = (N + 31) / 32;
+  int64_t o = 0;
+  L.off_pts = o; o += B * nblk * 32 * 16;       // float4 {x,y,z,|p|^2}, sorted, padded to whole blocks
+  L.off_ids = o; o += B * nblk * 32 * 4;        // int32 original index
+  L.off_bb = o; o += B * nblk * 32;             // 8 floats per block: min xyz, max xyz, -, -
+  L.off_lut = o; o += B * (KNS_CELLS + 1) * 4;  // int32 first sorted position of each coarse cell
+  L.off_meta = o; o += B * 32;                  // 8 floats per cloud: min xyz, 1/(max-min) * 1023 xyz, max |p|^2, -
+  L.total = o + 256;
+  return L;
+}
+
+__device__ __forceinline__ uint32_t kns_part1by2(uint32_t n) {
+  n &= 0x000003ff;
+  n = (n ^ (n << 16)) & 0xff0000ff;
+  n = (n ^ (n << 8)) & 0x0300f00f;
+  n = (n ^ (n << 4)) & 0x030c30c3;
+  n = (n ^ (n << 2)) & 0x09249249;
+  return n;
+}
+__device__ __forceinline__ uint32_t kns_code(float x, float y, float z, const float* meta) {
+  const int qx = min(1023, max(0, (int)((x - meta[0]) * meta[3])));
+  const int qy = min(1023, max(0, (int)((y - meta[1]) * meta[4])));
+  const int qz = min(1023, max(0, (int)((z - meta[2]) * meta[5])));
+  return (kns_part1by2((uint32_t)qz) << 2) | (kns_part1by2((uint32_t)qy) << 1) | kns_part1by2((uint32_t)qx);
+}
+
+// one CTA per cloud: bounding box, Z-order keys, bitonic sort in shared memory, sorted copies + block boxes + cell table
+__global__ void __launch_bounds__(1024)
+knn_prep_kernel(const float* __restrict__ x, int N, int pt_stride, int P2, float4* __restrict__ pts, int* __restrict__ ids,
+                float* __restrict__ bb, int* __restrict__ lut, float* __restrict__ meta_out) {
+  extern __shared__ uint64_t keys[];
+  __shared__ float red[7][32];
+  __shared__ float meta[8];
+  __shared__ int slut[KNS_CELLS + 1];
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5, T = blockDim.x;
+  const float* P = x + (size_t)b * N * pt_stride;
+  const int nblk = (N + 31) / 32;
+  float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f}, wmax = 0.f;
+  for (int i = t; i < N; i += T) {
+    const float px = P[(size_t)i * pt_stride], py = P[(size_t)i * pt_stride + 1], pz = P[(size_t)i * pt_stride + 2];
+    mn[0] = fminf(mn[0], px); mx[0] = fmaxf(mx[0], px);
+    mn[1] = fminf(mn[1], py); mx[1] = fmaxf(mx[1], py);
+    mn[2] = fminf(mn[2], pz); mx[2] = fmaxf(mx[2], pz);
+    wmax = fmaxf(wmax, sq3(px, py, pz));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+    wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { red[a][warp] = mn[a]; red[3 + a][warp] = mx[a]; }
+    red[6][warp] = wmax;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float v[7];
+#pragma unroll
+    for (int a = 0; a < 7; ++a) v[a] = lane < nw ? red[a][lane] : (a < 3 ? 3.4e38f : (a < 6 ? -3.4e38f : 0.f));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int a = 0; a < 7; ++a) {
+        const float u = __shfl_xor_sync(0xffffffffu, v[a], o);
+        v[a] = a < 3 ? fminf(v[a], u) : fmaxf(v[a], u);
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        meta[a] = v[a];
+        const float ext = v[3 + a] - v[a];
+        meta[3 + a] = ext > 0.f ? 1023.f / ext : 0.f;
+      }
+      meta[6] = v[6];
+      meta[7] = 0.f;
+    }
+  }
+  for (int c = t; c <= KNS_CELLS; c += T) slut[c] = N;
+  __syncthreads();
+  if (t < 8) meta_out[(size_t)b * 8 + t] = meta[t];
+  for (int i = t; i < P2; i += T) {
+    uint64_t key = 0xffffffffffffffffull;
+    if (i < N) key = ((uint64_t)kns_code(P[(size_t)i * pt_stride], P[(size_t)i * pt_stride + 1], P[(size_t)i * pt_stride + 2], meta) << 32) | (uint32_t)i;
+    keys[i] = key;
+  }
+  __syncthreads();
+  for (int kk = 2; kk <= P2; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int i = t; i < P2; i += T) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t a = keys[i], c = keys[ixj];
+          const bool up = (i & kk) == 0;
+          if ((a > c) == up) { keys[i] = c; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // sorted copies, block boxes (a warp = one block of 32 consecutive sorted points), coarse cell table
+  for (int j0 = warp * 32; j0 < nblk * 32; j0 += nw * 32) {
+    const int j = j0 + lane;
+    float4 pt = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fc00000));   // padding: |p|^2 = NaN never passes a comparison
+    int id = -1;
+    float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    if (j < N) {
+      const uint64_t key = keys[j];
+      id = (int)(uint32_t)key;
+      const float px = P[(size_t)id * pt_stride], py = P[(size_t)id * pt_stride + 1], pz = P[(size_t)id * pt_stride + 2];
+      pt = make_float4(px, py, pz, sq3(px, py, pz));
+      lo[0] = hi[0] = px; lo[1] = hi[1] = py; lo[2] = hi[2] = pz;
+      const int cell = (int)(key >> (32 + 21));
+      const int prev = j > 0 ? (int)(keys[j - 1] >> (32 + 21)) : -1;
+      if (cell != prev) slut[cell] = j;
+    }
+    pts[((size_t)b * nblk) * 32 + j] = pt;
+    ids[((size_t)b * nblk) * 32 + j] = id;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+        hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+      }
+    }
+    if (lane < 8) {
+      const float v = lane < 3 ? lo[lane] : (lane < 6 ? hi[lane - 3] : 0.f);
+      bb[(((size_t)b * nblk) + (j0 >> 5)) * 8 + lane] = v;
+    }
+  }
+  __syncthreads();
+  if (t == 0) {   // empty cells inherit the start of the next non-empty one
+    for (int c = KNS_CELLS - 1; c >= 0; --c) slut[c] = min(slut[c], slut[c + 1]);
+  }
+  __syncthreads();
+  for (int c = t; c <= KNS_CELLS; c += T) lut[(size_t)b * (KNS_CELLS + 1) + c] = slut[c];
+}
+
+template <int KPL, int MODE>
+__global__ void __launch_bounds__(KNN_WARPS * 32)
+knn_sorted_kernel(const float4* __restrict__ pts, const int* __restrict__ ids, const float* __restrict__ bb,
+                  const int* __restrict__ lut, const float* __restrict__ meta_all, int N, const float* __restrict__ centres,
+                  int G, int64_t total, int k, void* __restrict__ idx_out, int idx_is_i64, float* __restrict__ dist_out) {
+  __shared__ uint64_t queue[KNN_WARPS][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t cw = (int64_t)blockIdx.x * KNN_WARPS + warp;      // this warp's centre
+  if (cw >= total) return;
+  const int b = (int)(cw / G);
+  const int nblk = (N + 31) / 32;
+  const float* meta = meta_all + (size_t)b * 8;
+  const float4* P4 = pts + (size_t)b * nblk * 32;
+  const int* ID = ids + (size_t)b * nblk * 32;
+  const float* BB = bb + (size_t)b * nblk * 8;
+  const float* cp = centres + (size_t)cw * 3;
+  const float cx = cp[0], cy = cp[1], cz = cp[2];
+  const float cn = sq3(cx, cy, cz);
+  float c0, c1, c2;
+  if (MODE == P3TOK_KNN_APF_SQ) { c0 = cx; c1 = cy; c2 = cz; }
+  else { c0 = __fmul_rn(-2.f, cx); c1 = __fmul_rn(-2.f, cy); c2 = __fmul_rn(-2.f, cz); }
+  // margin of the block test: the expansion formula's rounding error is a few ulp of (|c|^2 + |p|^2 + 2|c||p|) <= 2(|c|^2+|p|^2)
+  const float margin = 1e-5f * (cn + meta[6]) + 1e-30f;
+
+  uint64_t L[KPL];
+#pragma unroll
+  for (int j = 0; j < KPL; ++j) L[j] = KNN_SENTINEL;
+  float thr = __int_as_float(0x7f800000);      // candidates need d <= thr  (P4P: t <= thr as the cheap pre-filter)
+  float thr_d = __int_as_float(0x7f800000);    // exact current k-th distance (P4P)
+  int qn = 0;
+  const int kth_lane = (k - 1) & 31, kth_j = (k - 1) >> 5;
+  uint64_t* q = queue[warp];
+
+  auto merge = [&](int cnt) {
+    uint64_t v = (lane < cnt) ? q[lane] : KNN_SENTINEL;
+    v = warp_sort_asc(v, lane);
+    list_insert_run<KPL>(L, v, lane);
+    uint64_t kth = 0;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j)
+      if (j == kth_j) kth = shfl_u64(L[j], kth_lane);
+    const uint32_t ko = (uint32_t)(kth >> 32);
+    const float kd = (ko == 0xffffffffu) ? __int_as_float(0x7f800000) : ord2f(ko);
+    if (MODE == P3TOK_KNN_APF_SQ) {
+      thr = kd;
+    } else {
+      thr_d = kd;
+      thr = (kd == __int_as_float(0x7f800000)) ? kd : __fmul_ru(__fmul_ru(kd, kd), 1.0000002384185791f);
+    }
+  };
+  // one block of 32 sorted points (p = this lane's point, id < 0 on padding)
+  auto process = [&](const float4 p, const int id) {
+    float d;
+    bool pass;
+    if (MODE == P3TOK_KNN_APF_SQ) {
+      const float dot = __fmaf_rn(c2, p.z, __fmaf_rn(c1, p.y, __fmul_rn(c0, p.x)));
+      float tt = __fmul_rn(-2.f, dot);
+      tt = __fadd_rn(tt, cn);
+      d = __fadd_rn(__fadd_rn(tt, p.w), 0.f);
+      pass = (id >= 0) && (d <= thr);
+    } else {
+      float tt = __fmul_rn(c0, p.x);
+      tt = __fmaf_rn(c1, p.y, tt);
+      tt = __fmaf_rn(c2, p.z, tt);
+      tt = __fadd_rn(tt, cn);
+      tt = __fadd_rn(tt, p.w);
+      d = tt;
+      pass = (id >= 0) && (tt <= thr);
+    }
+    uint32_t ball = __ballot_sync(0xffffffffu, pass);
+    if (ball == 0) return;
+    if (MODE == P3TOK_KNN_P4P_CDIST) {
+      d = __fadd_rn(__fsqrt_rn(fmaxf(d, 0.f)), 0.f);
+      pass = pass && (d <= thr_d);
+      ball = __ballot_sync(0xffffffffu, pass);
+      if (ball == 0) return;
+    }
+    if (pass) q[qn + __popc(ball & ((1u << lane) - 1u))] = ((uint64_t)f2ord(d) << 32) | (uint32_t)id;
+    qn += __popc(ball);
+    __syncwarp();
+    if (qn >= 32) {
+      merge(32);
+      __syncwarp();
+      if (lane + 32 < qn) q[lane] = q[lane + 32];
+      qn -= 32;
+      __syncwarp();
+    }
+  };
+
+  // ---- seed: the blocks around the centre's own position on the curve
+  const int cell = (int)(kns_code(cx, cy, cz, meta) >> 21);
+  const int pos = lut[(size_t)b * (KNS_CELLS + 1) + cell];
+  int s0 = (pos >> 5) - 1;
+  s0 = max(0, min(s0, nblk - 3));
+  const int s1 = min(nblk, s0 + 3);
+  for (int blk = s0; blk < s1; ++blk) process(P4[blk * 32 + lane], ID[blk * 32 + lane]);
+
+  // ---- all other blocks: box test 32 blocks at a time, evaluate the survivors
+  for (int r0 = 0; r0 < nblk; r0 += 32) {
+    const int blk = r0 + lane;
+    float lb = __int_as_float(0x7f800000);
+    const bool mine = blk < nblk && (blk < s0 || blk >= s1);   // (thr may still be +inf: validity is not encoded in lb)
+    if (mine) {
+      const float4 lo = *reinterpret_cast<const float4*>(BB + (size_t)blk * 8);       // min x,y,z, max x
+      const float4 hi = *reinterpret_cast<const float4*>(BB + (size_t)blk * 8 + 4);   // max y,z
+      const float dx = fmaxf(fmaxf(lo.x - cx, cx - lo.w), 0.f);
+      const float dy = fmaxf(fmaxf(lo.y - cy, cy - hi.x), 0.f);
+      const float dz = fmaxf(fmaxf(lo.z - cz, cz - hi.y), 0.f);
+      lb = (dx * dx + dy * dy + dz * dz) * 0.999999f - margin;
+    }
+    uint32_t todo = __ballot_sync(0xffffffffu, mine && lb <= thr);
+    while (todo) {
+      const int bit = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const float lbb = __shfl_sync(0xffffffffu, lb, bit);
+      if (lbb > thr) continue;                     // the threshold tightened since the vote
+      const int bk = r0 + bit;
+      process(P4[bk * 32 + lane], ID[bk * 32 + lane]);
+    }
+  }
+  if (qn > 0) merge(qn);
+  const int g = (int)(cw - (int64_t)b * G);
+  const size_t o = ((size_t)b * G + g) * k;
+#pragma unroll
+  for (int j = 0; j < KPL; ++j) {
+    const int r = j * 32 + lane;
+    if (r < k) {
+      const uint32_t id = (uint32_t)L[j];
+      if (idx_is_i64) reinterpret_cast<int64_t*>(idx_out)[o + r] = (int64_t)id;
+      else reinterpret_cast<int32_t*>(idx_out)[o + r] = (int32_t)id;
+      if (dist_out) dist_out[o + r] = ord2f((uint32_t)(L[j] >> 32));
+    }
+  }
+}
+
+template <int KPL>
+static int knn_sorted_launch(const float4* pts, const int* ids, const float* bb, const int* lut, const float* meta, int N,
+                             const float* centres, int G, int64_t total, int k, int mode, void* idx_out, int i64, float* dist_out,
+                             cudaStream_t s) {
+  const unsigned grid = (unsigned)((total + KNN_WARPS - 1) / KNN_WARPS);
+  if (mode == P3TOK_KNN_APF_SQ)
+    knn_sorted_kernel<KPL, P3TOK_KNN_APF_SQ><<<grid, KNN_WARPS * 32, 0, s>>>(pts, ids, bb, lut, meta, N, centres, G, total, k, idx_out, i64, dist_out);
+  else
+    knn_sorted_kernel<KPL, P3TOK_KNN_P4P_CDIST><<<grid, KNN_WARPS * 32, 0, s>>>(pts, ids, bb, lut, meta, N, centres, G, total, k, idx_out, i64, dist_out);
+  P3_LAUNCH_CHECK("knn_sorted_kernel");
+  return P3TOK_OK;
+}
+
 }  // namespace p3tok
 
 using namespace p3tok;
@@ -267,4 +582,51 @@ extern "C" int p3tok_knn(const float* x, int64_t B, int64_t N, int64_t pt_stride
   if (k <= 32) return knn_launch<1>(x, (int)B, (int)N, (int)pt_stride, centres, (int)G, (int)k, mode, idx_out, i64, dist_out, s);
   if (k <= 64) return knn_launch<2>(x, (int)B, (int)N, (int)pt_stride, centres, (int)G, (int)k, mode, idx_out, i64, dist_out, s);
   return knn_launch<4>(x, (int)B, (int)N, (int)pt_stride, centres, (int)G, (int)k, mode, idx_out, i64, dist_out, s);
+}
+
+extern "C" int64_t p3tok_knn_workspace_bytes(int64_t B, int64_t N) {
+  if (B < 0 || N <= 0 || N > KNS_MAX_N) return 0;       // 0: the sorted variant does not apply, use p3tok_knn
+  return kns_layout(B, N).total;
+}
+
+extern "C" int p3tok_knn_sorted(const float* x, int64_t B, int64_t N, int64_t pt_stride, const float* centres, int64_t G,
+                                int64_t k, int mode, void* idx_out, int idx_dtype, float* dist_out, void* workspace,
+                                int64_t workspace_bytes, void* stream) {
+  P3_REQUIRE(B >= 0 && N > 0 && G >= 0 && pt_stride >= 3, P3TOK_ERR_INVALID, "knn_sorted: bad shape");
+  P3_REQUIRE(mode == P3TOK_KNN_APF_SQ || mode == P3TOK_KNN_P4P_CDIST, P3TOK_ERR_INVALID, "knn_sorted: bad mode %d", mode);
+  P3_REQUIRE(idx_dtype == P3TOK_I64 || idx_dtype == P3TOK_I32, P3TOK_ERR_INVALID, "knn_sorted: idx dtype must be i32/i64");
+  P3_REQUIRE(k >= 1 && k <= N, P3TOK_ERR_INVALID, "knn_sorted: k=%lld out of range for N=%lld", (long long)k, (long long)N);
+  P3_REQUIRE(k <= 128, P3TOK_ERR_UNSUPPORTED, "knn_sorted: k=%lld > 128", (long long)k);
+  P3_REQUIRE(N <= KNS_MAX_N, P3TOK_ERR_UNSUPPORTED, "knn_sorted: N=%lld > %d (use p3tok_knn)", (long long)N, KNS_MAX_N);
+  P3_REQUIRE(B < 65536, P3TOK_ERR_UNSUPPORTED, "knn_sorted: B too large");
+  if (B == 0 || G == 0) return P3TOK_OK;
+  P3_REQUIRE(x && centres && idx_out && workspace, P3TOK_ERR_INVALID, "knn_sorted: null pointer");
+  const KnsLayout L = kns_layout(B, N);
+  P3_REQUIRE(workspace_bytes >= L.total, P3TOK_ERR_WORKSPACE, "knn_sorted: workspace %lld < %lld bytes", (long long)workspace_bytes,
+             (long long)L.total);
+  cudaStream_t s = as_stream(stream);
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  float4* pts = reinterpret_cast<float4*>(base + L.off_pts);
+  int* ids = reinterpret_cast<int*>(base + L.off_ids);
+  float* bb = reinterpret_cast<float*>(base + L.off_bb);
+  int* lut = reinterpret_cast<int*>(base + L.off_lut);
+  float* meta = reinterpret_cast<float*>(base + L.off_meta);
+  int P2 = 32;
+  while (P2 < N) P2 <<= 1;
+  const int threads = P2 > 1024 ? 1024 : P2;
+  const size_t smem = (size_t)P2 * 8;
+  static thread_local bool configured[32] = {false};
+  int dev = 0;
+  P3_CUDA(cudaGetDevice(&dev));
+  if (dev < 32 && !configured[dev]) {
+    P3_CUDA(cudaFuncSetAttribute(knn_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KNS_MAX_N * 8));
+    configured[dev] = true;
+  }
+  knn_prep_kernel<<<(unsigned)B, threads, smem, s>>>(x, (int)N, (int)pt_stride, P2, pts, ids, bb, lut, meta);
+  P3_LAUNCH_CHECK("knn_prep_kernel");
+  const int i64 = idx_dtype == P3TOK_I64;
+  const int64_t total = B * G;
+  if (k <= 32) return knn_sorted_launch<1>(pts, ids, bb, lut, meta, (int)N, centres, (int)G, total, (int)k, mode, idx_out, i64, dist_out, s);
+  if (k <= 64) return knn_sorted_launch<2>(pts, ids, bb, lut, meta, (int)N, centres, (int)G, total, (int)k, mode, idx_out, i64, dist_out, s);
+  return knn_sorted_launch<4>(pts, ids, bb, lut, meta, (int)N, centres, (int)G, total, (int)k, mode, idx_out, i64, dist_out, s);
 }

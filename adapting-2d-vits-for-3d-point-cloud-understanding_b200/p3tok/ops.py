@@ -9,6 +9,7 @@ implementation for any device but CUDA.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -142,6 +143,9 @@ def _(x, idx):
 
 
 # --------------------------------------------------------------------------------------------- knn
+_KNN_SORTED = os.environ.get("P3TOK_KNN_SORTED", "1") != "0"
+
+
 @torch.library.custom_op("p3tok::knn", mutates_args=(), device_types="cuda")
 def knn(x: torch.Tensor, centres: torch.Tensor, k: int, mode: int, int32_out: bool,
         return_dist: bool) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -158,10 +162,19 @@ def knn(x: torch.Tensor, centres: torch.Tensor, k: int, mode: int, int32_out: bo
         raise RuntimeError(f"p3tok::knn: selected index k out of range (k={k} > N={N})")
     idx = torch.empty((B, G, k), dtype=torch.int32 if int32_out else torch.int64, device=x.device)
     dist = torch.empty((B, G, k) if return_dist else (0,), dtype=torch.float32, device=x.device)
+    # clouds of up to 8192 points: Z-order sorted blocks + bounding-box culling (same results bit for bit);
+    # P3TOK_KNN_SORTED=0 forces the plain sweep
+    ws_bytes = int(_L().p3tok_knn_workspace_bytes(B, N)) if _KNN_SORTED and B * G > 0 else 0
     with torch.cuda.device(x.device), _timed("knn"):
-        check(_L().p3tok_knn(x.data_ptr(), B, N, stride, c.data_ptr(), G, k, mode, idx.data_ptr(),
-                             _lib.I32 if int32_out else _lib.I64, dist.data_ptr() if return_dist else None,
-                             _stream()), "knn")
+        if ws_bytes > 0:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+            check(_L().p3tok_knn_sorted(x.data_ptr(), B, N, stride, c.data_ptr(), G, k, mode, idx.data_ptr(),
+                                        _lib.I32 if int32_out else _lib.I64, dist.data_ptr() if return_dist else None,
+                                        ws.data_ptr(), ws_bytes, _stream()), "knn_sorted")
+        else:
+            check(_L().p3tok_knn(x.data_ptr(), B, N, stride, c.data_ptr(), G, k, mode, idx.data_ptr(),
+                                 _lib.I32 if int32_out else _lib.I64, dist.data_ptr() if return_dist else None,
+                                 _stream()), "knn")
     return idx, dist
 
 

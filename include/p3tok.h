@@ -81,6 +81,15 @@ P3TOK_API int p3tok_knn(const float* x, int64_t B, int64_t N, int64_t pt_stride,
               int64_t G, int64_t k, int mode, void* idx_out, int idx_dtype, float* dist_out,
               void* stream);
 
+/* Spatially sorted variant of p3tok_knn for clouds of at most 8192 points (same contract, same results bit for bit):
+ * a preparation kernel sorts every cloud along a Z-order curve into `workspace`, then one warp per centre evaluates only
+ * the 32-point blocks whose bounding box can still contain one of the k nearest neighbours.
+ * p3tok_knn_workspace_bytes returns the scratch size in bytes, or 0 when the variant does not apply (N > 8192). */
+P3TOK_API int64_t p3tok_knn_workspace_bytes(int64_t B, int64_t N);
+P3TOK_API int p3tok_knn_sorted(const float* x, int64_t B, int64_t N, int64_t pt_stride, const float* centres,
+                     int64_t G, int64_t k, int mode, void* idx_out, int idx_dtype, float* dist_out,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- a7: Morton order of the centres (src/models/apf_utils.py:66-104, resolution 1024) -------
  * centres (B,G,3) -> perm (B,G) int64 = stable ascending argsort of the 30-bit Z-order code;
  * codes_out optional (B,G) int64.  G <= 8192. */

@@ -208,3 +208,60 @@ def test_dataset_level_fps_downsample():
     assert np.array_equal(idx[sub].cpu().numpy(), oracle.fps(x[sub], st[sub], G))
     assert all(len(set(r.tolist())) == G for r in idx[::97].cpu().numpy())
     print(f"dataset-level fps: {B} clouds x {N} pts -> {G}: {e0.elapsed_time(e1):.1f} ms")
+
+
+def _knn_both(x, ctr, k, mode, i32):
+    """(idx, dist) from the plain sweep (p3tok_knn) and from the Z-order sorted / culled variant (p3tok_knn_sorted),
+    both through the C ABI."""
+    L = ops._L()
+    B, N, _ = x.shape
+    G = ctr.shape[1]
+    outs = []
+    for sorted_variant in (False, True):
+        idx = torch.empty((B, G, k), dtype=torch.int32 if i32 else torch.int64, device=x.device)
+        dist = torch.empty((B, G, k), dtype=torch.float32, device=x.device)
+        dt = _lib.I32 if i32 else _lib.I64
+        if sorted_variant:
+            nbytes = int(L.p3tok_knn_workspace_bytes(B, N))
+            assert nbytes > 0
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            _lib.check(L.p3tok_knn_sorted(x.data_ptr(), B, N, 3, ctr.data_ptr(), G, k, mode, idx.data_ptr(), dt,
+                                          dist.data_ptr(), ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream),
+                       "knn_sorted")
+        else:
+            _lib.check(L.p3tok_knn(x.data_ptr(), B, N, 3, ctr.data_ptr(), G, k, mode, idx.data_ptr(), dt, dist.data_ptr(),
+                                   torch.cuda.current_stream().cuda_stream), "knn")
+        torch.cuda.synchronize()
+        outs.append((idx.cpu(), dist.cpu()))
+    return outs
+
+
+@pytest.mark.parametrize("mode", [oracle.KNN_APF_SQ, oracle.KNN_P4P_CDIST])
+@pytest.mark.parametrize("B,N,G,k,kind", [
+    (3, 1000, 77, 32, "uniform"), (2, 8192, 300, 32, "clustered"), (2, 2048, 128, 64, "duplicates"),
+    (4, 100, 100, 100, "uniform"), (2, 33, 5, 16, "clustered"), (1, 4096, 64, 128, "duplicates"),
+])
+def test_sorted_knn_is_bit_identical_to_the_sweep(mode, B, N, G, k, kind):
+    """The culled variant must return exactly the sweep's (distance, index) lists: ragged N, k = N, duplicated points
+    (ties at the k-th distance), and query points that are NOT cloud points (outside the cloud's bounding box too)."""
+    x = to_dev(synth.make_cloud(kind, B, N, 900 + N, 3))
+    g = torch.Generator().manual_seed(N + G)
+    pick = torch.randint(0, N, (B, G), generator=g)
+    ctr = torch.gather(x.cpu(), 1, pick[..., None].expand(B, G, 3)).clone()
+    ctr[:, ::3] += torch.randn(B, (G + 2) // 3, 3, generator=g) * 0.3          # every third centre is off-cloud
+    ctr[:, 1::7] *= 3.0                                                          # some far outside the bounding box
+    ctr = ctr.contiguous().to(dev())
+    (i0, d0), (i1, d1) = _knn_both(x, ctr, k, mode, mode == oracle.KNN_P4P_CDIST)
+    assert torch.equal(i0, i1)
+    assert torch.equal(d0.view(torch.int32), d1.view(torch.int32))
+
+
+def test_sorted_knn_workspace_contract():
+    L = ops._L()
+    assert int(L.p3tok_knn_workspace_bytes(4, 8193)) == 0          # too many points: use the sweep
+    x = to_dev(synth.make_cloud("uniform", 1, 64, 1, 3))
+    idx = torch.empty((1, 4, 8), dtype=torch.int64, device=dev())
+    ws = torch.empty(16, dtype=torch.uint8, device=dev())
+    rc = L.p3tok_knn_sorted(x.data_ptr(), 1, 64, 3, x.data_ptr(), 4, 8, 0, idx.data_ptr(), _lib.I64, None, ws.data_ptr(), 16,
+                            torch.cuda.current_stream().cuda_stream)
+    assert rc == _lib.ERR_WORKSPACE
