@@ -862,6 +862,90 @@ rows_first_layer_apf_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, const 
   }
 }
 
+// Warp-persistent form of the kernel above for nout = 32 * NPL (APF: 256): one warp owns a 32-row block at a time (lane =
+// row for the gather, lane = NPL consecutive output channels for the layer) and has the next block's gathered inputs in
+// registers while it computes the current one, so the dependent loads perm -> centre index -> centre row and neighbour
+// index -> neighbour row overlap the FMAs (82 us per 2^19 rows before, bound by that chain once per CTA).
+template <typename IdxT, int NPL>
+__global__ void __launch_bounds__(128)
+rows_first_layer_apf_warp_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, const __nv_bfloat16* __restrict__ W,
+                                 const float* __restrict__ bias, int relu, __nv_bfloat16* __restrict__ out) {
+  constexpr int NOUT = 32 * NPL;
+  __shared__ __align__(16) float rel_all[4][32][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float (*rel)[4] = rel_all[warp];
+  const int C = R.C, cin = 2 * C;
+  const IdxT* knn = reinterpret_cast<const IdxT*>(R.knn_idx);
+  const int64_t nblocks = (nrows + 31) >> 5;
+  const int64_t wstride = (int64_t)gridDim.x * 4;
+  // row (blk*32 + lane): v = neighbour - centre (zero beyond C / nrows), c = the block's centre row (same in every lane)
+  auto gather = [&](int64_t blk, float4& v, float4& c) {
+    v = make_float4(0.f, 0.f, 0.f, 0.f);
+    c = v;
+    if (blk >= nblocks) return;
+    const int64_t r0 = blk * 32;
+    const int64_t bj = g_begin + r0 / R.k;               // output group of the whole block (k % 32 == 0)
+    const int64_t b = bj / R.G;
+    const int64_t g = R.perm ? R.perm[bj] : (bj - b * R.G);
+    const float* crow = R.x + (b * R.N + R.ctr_idx[b * R.G + g]) * C;
+    c.x = crow[0]; c.y = crow[1]; c.z = crow[2];
+    if (C == 4) c.w = crow[3];
+    const int64_t r = r0 + lane;
+    if (r < nrows) {
+      const int64_t ni = (int64_t)knn[(b * R.G + g) * R.k + (r % R.k)];
+      const float* prow = R.x + (b * R.N + ni) * C;
+      v.x = __fsub_rn(prow[0], c.x);
+      v.y = __fsub_rn(prow[1], c.y);
+      v.z = __fsub_rn(prow[2], c.z);
+      if (C == 4) v.w = __fsub_rn(prow[3], c.w);
+    }
+  };
+  float wr[NPL][4], wc[NPL][4], b0[NPL];
+#pragma unroll
+  for (int j = 0; j < NPL; ++j) {
+    const int n = lane * NPL + j;
+    b0[j] = bias ? bias[n] : 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      wr[j][c] = c < C ? __bfloat162float(W[(size_t)n * cin + c]) : 0.f;
+      wc[j][c] = c < C ? __bfloat162float(W[(size_t)n * cin + C + c]) : 0.f;
+    }
+  }
+  int64_t blk = (int64_t)blockIdx.x * 4 + warp;
+  float4 nv, nc;
+  gather(blk, nv, nc);
+  for (; blk < nblocks; blk += wstride) {
+    const float4 cc = nc;
+    __syncwarp();                                    // the previous block's broadcasts are done
+    *reinterpret_cast<float4*>(&rel[lane][0]) = nv;
+    __syncwarp();
+    gather(blk + wstride, nv, nc);                   // in flight during the loop below
+    float base[NPL];
+#pragma unroll
+    for (int j = 0; j < NPL; ++j)
+      base[j] = fmaf(wc[j][3], cc.w, fmaf(wc[j][2], cc.z, fmaf(wc[j][1], cc.y, fmaf(wc[j][0], cc.x, b0[j]))));
+    const int64_t r0 = blk * 32;
+    const int nr = (int)((nrows - r0) < 32 ? (nrows - r0) : 32);
+#pragma unroll 2
+    for (int row = 0; row < nr; ++row) {
+      const float4 xv = *reinterpret_cast<const float4*>(&rel[row][0]);   // warp-wide broadcast
+      uint32_t pk[NPL / 2];
+#pragma unroll
+      for (int j = 0; j < NPL; j += 2) {
+        float a0 = fmaf(wr[j][0], xv.x, base[j]), a1 = fmaf(wr[j + 1][0], xv.x, base[j + 1]);
+        a0 = fmaf(wr[j][1], xv.y, a0); a1 = fmaf(wr[j + 1][1], xv.y, a1);
+        a0 = fmaf(wr[j][2], xv.z, a0); a1 = fmaf(wr[j + 1][2], xv.z, a1);
+        a0 = fmaf(wr[j][3], xv.w, a0); a1 = fmaf(wr[j + 1][3], xv.w, a1);
+        pk[j / 2] = relu ? pack_bf16x2_relu(a0, a1) : pack_bf16x2(a0, a1);
+      }
+      __nv_bfloat16* o = out + (r0 + row) * NOUT + lane * NPL;
+      if (NPL == 2) *reinterpret_cast<uint32_t*>(o) = pk[0];
+      else if (NPL == 4) *reinterpret_cast<uint2*>(o) = make_uint2(pk[0], pk[1 % (NPL / 2)]);
+      else *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1 % (NPL / 2)], pk[2 % (NPL / 2)], pk[3 % (NPL / 2)]);
+    }
+  }
+}
+
 // Wide input: gather rows to bf16 [nrows, kpad], zero padded
 template <typename IdxT>
 __global__ void rows_gather_bf16_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, int cin, int kpad,
@@ -1003,15 +1087,27 @@ static inline unsigned grid_1d(int64_t total, int threads) {
 // chunk's activations L2-resident - 2-wave chunks 1.91 ms, 16-wave chunks 1.35 ms - so chunks are as
 // large as a bounded workspace allows (default 2^20 rows: <= 1.6 GB per bf16 activation buffer at 768
 // columns).  P3TOK_CHUNK_ROWS overrides for experiments.
-static int64_t chunk_groups(int64_t ngroups, int64_t k) {
-  static int64_t rows_target = 0;
-  if (!rows_target) {
+// `wmax` = widest bf16 activation of the block: the default chunk keeps one activation buffer at <= 1.6 GB (2^20 rows
+// at 768 columns) but lets narrow blocks (P3Embed stage 0: 256 columns) run 3x larger chunks - fewer launches, fewer
+// pipeline fills and tails per row.
+static int64_t chunk_groups(int64_t ngroups, int64_t k, int64_t wmax) {
+  static int64_t rows_env = -1;
+  if (rows_env < 0) {
     const char* e = getenv("P3TOK_CHUNK_ROWS");
-    rows_target = e ? atoll(e) : (1ll << 20);
-    if (rows_target < 128) rows_target = 128;
+    rows_env = e ? atoll(e) : 0;
   }
+  int64_t rows_target = rows_env;
+  if (rows_target <= 0) {
+    rows_target = (1ll << 20) * 768 / (wmax > 0 ? wmax : 768);
+    if (rows_target < (1ll << 20)) rows_target = 1ll << 20;
+    if (rows_target > (1ll << 22)) rows_target = 1ll << 22;
+  }
+  if (rows_target < 128) rows_target = 128;
   int64_t cg = rows_target / k;
   if (cg < 1) cg = 1;
+  // equal chunks (the last one would otherwise be a short straggler)
+  const int64_t nchunks = (ngroups + cg - 1) / cg;
+  if (nchunks > 1) cg = ((ngroups + nchunks - 1) / nchunks + 7) / 8 * 8;   // whole 256-row pair tiles for k = 32
   return ngroups < cg ? ngroups : cg;
 }
 
@@ -1022,14 +1118,14 @@ struct BfLayout {
 
 static BfLayout bf_layout(const p3tok_mlp* m, int64_t ngroups, int64_t k) {
   BfLayout L;
-  L.cg = chunk_groups(ngroups, k);
-  L.rows = L.cg * k;
   L.F = m->pre_dim[m->n_pre - 1];
   L.kpad0 = m->cin <= 16 ? 0 : align_up(m->cin, 8);
   int64_t w = L.kpad0;
   for (int i = 0; i < m->n_pre; ++i) w = w > m->pre_dim[i] ? w : m->pre_dim[i];
   w = w > m->mid_dim ? w : m->mid_dim;
   L.wmax = w;
+  L.cg = chunk_groups(ngroups, k, w);
+  L.rows = L.cg * k;
   const int64_t wide = L.F > m->out_dim ? L.F : m->out_dim;
   int64_t o = 0;
   L.off_act0 = o; o += align_up(L.rows * w * 2, 1024);
@@ -1092,7 +1188,17 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
                                                            m->b_pre[0], m->cin, m->pre_dim[0], m->pre_relu[0], act[cur], l1_gmax)
       static int apf_split = -1;
       if (apf_split < 0) { const char* e = getenv("P3TOK_L1_SPLIT"); apf_split = e ? atoi(e) : 1; }
-      if (apf_split && R->kind == 0 && k % 32 == 0 && (R->C == 3 || R->C == 4) && m->pre_dim[0] % 2 == 0) {
+      if (apf_split && R->kind == 0 && k % 32 == 0 && (R->C == 3 || R->C == 4) &&
+          (m->pre_dim[0] == 64 || m->pre_dim[0] == 128 || m->pre_dim[0] == 256)) {
+        const unsigned nb = (unsigned)std::min<int64_t>((blocks + 3) / 4, (int64_t)num_sms() * 10);
+#define P3_L1A(IDX, NPL)                                                                                              \
+  rows_first_layer_apf_warp_kernel<IDX, NPL><<<nb, 128, 0, s>>>(*R, g0, rows, (const __nv_bfloat16*)m->w_pre[0], m->b_pre[0], \
+                                                                 m->pre_relu[0], act[cur])
+        const int npl = m->pre_dim[0] / 32;
+        if (i64) { if (npl == 2) P3_L1A(int64_t, 2); else if (npl == 4) P3_L1A(int64_t, 4); else P3_L1A(int64_t, 8); }
+        else     { if (npl == 2) P3_L1A(int32_t, 2); else if (npl == 4) P3_L1A(int32_t, 4); else P3_L1A(int32_t, 8); }
+#undef P3_L1A
+      } else if (apf_split && R->kind == 0 && k % 32 == 0 && (R->C == 3 || R->C == 4) && m->pre_dim[0] % 2 == 0) {
         if (i64) rows_first_layer_apf_kernel<int64_t><<<blocks, 128, 0, s>>>(*R, g0, rows, (const __nv_bfloat16*)m->w_pre[0],
                                                                           m->b_pre[0], m->pre_dim[0], m->pre_relu[0], act[cur]);
         else rows_first_layer_apf_kernel<int32_t><<<blocks, 128, 0, s>>>(*R, g0, rows, (const __nv_bfloat16*)m->w_pre[0],
