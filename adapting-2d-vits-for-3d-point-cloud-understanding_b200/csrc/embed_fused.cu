@@ -32,16 +32,20 @@ namespace p3tok {
 
 constexpr int FU_CH_WARPS = 8, FU_OUT_WARPS = 8;
 constexpr int FU_THREADS = (3 + FU_CH_WARPS + FU_OUT_WARPS) * 32;
-constexpr int FU_CHUNK = 64;                 // hidden columns per chunk
-constexpr int FU_ACC2_COL = 384;             // TMEM column of chunk accumulator 0
-constexpr int FU_RA_BOX = 32 * 128;          // 4 KB: this CTA's 32 of the chunk's 64 rows of W_a x 64 k
+constexpr int FU_CHUNK = 128;                // hidden columns per chunk: the narrowest N at which a tcgen05.mma still runs at
+                                             // its nominal rate (65 cycles; N = 64 costs 56 instead of 32: profiles/microbench)
+constexpr int FU_CH_BYTES = 2 * 16384;       // one chunk operand: 128 rows x 128 columns bf16 = two 64-column K blocks
+constexpr int FU_RA_BOX = 64 * 128;          // 8 KB: this CTA's 64 of the chunk's 128 rows of W_a x 64 k
 constexpr int FU_MAX_RA = 32, FU_MAX_RB = 16;
 constexpr int FU_SMEM = 227 * 1024;
 
 struct FusedParams {
   int M, K0, N1, N2;
   int num_pairs;                    // ceil(num_m_tiles / 2): one 256-row tile per CTA pair
-  int ra_slots, rb_slots, rb_box;   // ring depths; rb_box = (N2/8) * 128 bytes
+  int ra_slots, rb_slots, rb_box;   // ring depths; rb_box = (nq_rows/2) * 128 bytes
+  int nch;                          // chunk operand buffers in shared memory: 2, or 1 when the weight rings need the room
+  int nacc;                         // chunk accumulators in TMEM: 2 when N2 <= 256, else 1 (384 output + 128 chunk columns = 512)
+  int nq, nq_rows;                  // output columns per B-MMA: N2 (nq = 1) or N2/2 (nq = 2, N2 > 256)
   const float* bias_a;              // [N1] or null
   const float* gbias;               // [M / rows_per_group, N1] or null; rows_per_group % 32 == 0
   int rows_per_group;
@@ -62,16 +66,16 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmWb, const __grid_constant__ CUtensorMap tmC, const FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int KB0 = p.K0 / 64, NC = p.N1 / FU_CHUNK, NQ = 4;
+  const int KB0 = p.K0 / 64, NC = p.N1 / FU_CHUNK, NQ = p.nq;
   uint8_t* sA0 = smem;                                   // KB0 x 16 KB
-  uint8_t* sCH = sA0 + KB0 * 16384;                      // 2 x 16 KB
-  uint8_t* sRA = sCH + 2 * 16384;                        // ra_slots x 4 KB
+  uint8_t* sCH = sA0 + KB0 * 16384;                      // 2 x 32 KB chunk operands
+  uint8_t* sRA = sCH + p.nch * FU_CH_BYTES;              // ra_slots x 8 KB
   uint8_t* sRB = sRA + p.ra_slots * FU_RA_BOX;           // rb_slots x rb_box
   uint8_t* sST = sRB + p.rb_slots * p.rb_box;            // 8 x 4 KB store staging when store_out
   float* sba = reinterpret_cast<float*>(sST + (p.store_out ? FU_OUT_WARPS * 4096 : 0));   // N1 floats
   float* sbb = sba + p.N1;                               // N2 floats
-  float* sgb = sbb + p.N2;                               // chunk warps x 32 floats (group-bias slices)
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sgb + FU_CH_WARPS * 32) + 7) & ~(uintptr_t)7);
+  float* sgb = sbb + p.N2;                               // chunk warps x 64 floats (group-bias slices)
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sgb + FU_CH_WARPS * 64) + 7) & ~(uintptr_t)7);
   uint64_t* a0_full = bars;            // leader
   uint64_t* a0_empty = bars + 1;       // local, multicast commit
   uint64_t* acc3_full = bars + 2;      // local, multicast commit
@@ -120,7 +124,8 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();                       // the peer's barriers exist before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int nq_rows = p.N2 / NQ;            // output columns per B-MMA; each CTA holds nq_rows/2 rows of the W_b box
+  const int nq_rows = p.nq_rows;            // output columns per B-MMA; each CTA holds nq_rows/2 rows of the W_b box
+  const uint32_t acc_col0 = 512u - (uint32_t)p.nacc * FU_CHUNK;   // TMEM column of chunk accumulator 0
 
   if (warp == 0) {
     // ---------------- producer 0: this CTA's A0 rows, then its half of every W_a box, in consumption order
@@ -141,7 +146,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_wait(&ra_empty[rs], rph ^ 1);
           if (issuer) {
             if (rank == 0) mbar_expect_tx(&ra_full[rs], 2u * FU_RA_BOX);
-            tma_load_2d_pair(sRA + rs * FU_RA_BOX, &tmWa, &ra_full[rs], kb * 64, j * FU_CHUNK + rank * 32);
+            tma_load_2d_pair(sRA + rs * FU_RA_BOX, &tmWa, &ra_full[rs], kb * 64, j * FU_CHUNK + rank * (FU_CHUNK / 2));
           }
           __syncwarp();
           if (++rs == p.ra_slots) { rs = 0; rph ^= 1; }
@@ -155,11 +160,12 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t rph = 0;
     for (int tp = pair_id; tp < p.num_pairs; tp += pair_stride) {
       for (int j = 0; j < NC; ++j) {
-        for (int qd = 0; qd < NQ; ++qd) {
+        for (int kq = 0; kq < 2 * NQ; ++kq) {     // (64-column K block of the chunk) x (output column group)
+          const int kb2 = kq / NQ, qd = kq - kb2 * NQ;
           mbar_wait(&rb_empty[rs], rph ^ 1);
           if (issuer) {
             if (rank == 0) mbar_expect_tx(&rb_full[rs], 2u * (uint32_t)p.rb_box);
-            tma_load_2d_pair(sRB + rs * p.rb_box, &tmWb, &rb_full[rs], j * FU_CHUNK, qd * nq_rows + rank * (nq_rows / 2));
+            tma_load_2d_pair(sRB + rs * p.rb_box, &tmWb, &rb_full[rs], j * FU_CHUNK + kb2 * 64, qd * nq_rows + rank * (nq_rows / 2));
           }
           __syncwarp();
           if (++rs == p.rb_slots) { rs = 0; rph ^= 1; }
@@ -182,10 +188,11 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int it = 0;
       // A(j): chunk accumulator (gc & 1) = A0 . W_a[chunk j]^T
       auto issue_A = [&](bool last_of_tile) {
-        const uint32_t b = gc & 1;
-        mbar_wait(&acc2_empty[b], ((gc >> 1) & 1) ^ 1);
+        const uint32_t b = p.nacc == 2 ? (gc & 1) : 0u;                   // chunk accumulator and how often it was used
+        const uint32_t use = p.nacc == 2 ? (gc >> 1) : gc;
+        mbar_wait(&acc2_empty[b], (use & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem_base + FU_ACC2_COL + b * FU_CHUNK;
+        const uint32_t d = tmem_base + acc_col0 + b * FU_CHUNK;
         for (int kb = 0; kb < KB0; ++kb) {
           mbar_wait(&ra_full[ras], raph);
           tc_fence_after();
@@ -216,23 +223,25 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int j = 0; j < NC; ++j) {
           if (j + 1 < NC) issue_A(j + 1 == NC - 1);
           // B(j): output accumulator += chunk(j) . W_b[:, chunk j]^T, one MMA group per quarter of the output columns
-          const uint32_t b = gcb & 1;
+          const uint32_t b = p.nch == 2 ? (gcb & 1) : 0u;          // chunk operand buffer and how often it was used
+          const uint32_t cuse = p.nch == 2 ? (gcb >> 1) : gcb;
           if (issuer) fu_trace(p, it, j, 0, clock64());           // A(j+1) issued
-          mbar_wait(&ch_full[b], (gcb >> 1) & 1);
+          mbar_wait(&ch_full[b], cuse & 1);
           if (issuer) fu_trace(p, it, j, 1, clock64());           // chunk j operand ready
           if (j == 0) mbar_wait(acc3_empty, (uint32_t)(it & 1) ^ 1);
           tc_fence_after();
-          for (int qd = 0; qd < NQ; ++qd) {
+          for (int kq = 0; kq < 2 * NQ; ++kq) {
+            const int kb2 = kq / NQ, qd = kq - kb2 * NQ;
             mbar_wait(&rb_full[rbs], rbph);
-            if (issuer && qd == 0) fu_trace(p, it, j, 2, clock64());   // first W_b box present
-            if (issuer && qd == 3) fu_trace(p, it, j, 3, clock64());   // last W_b box present
+            if (issuer && kq == 0) fu_trace(p, it, j, 2, clock64());            // first W_b box present
+            if (issuer && kq == 2 * NQ - 1) fu_trace(p, it, j, 3, clock64());   // last W_b box present
             tc_fence_after();
             if (issuer) {
-              const uint64_t ad = dconst | (uint64_t)(ch_base + b * (16384 >> 4));
+              const uint64_t ad = dconst | (uint64_t)(ch_base + b * (FU_CH_BYTES >> 4) + kb2 * (16384 >> 4));
               const uint64_t bd = dconst | (uint64_t)(rb_base + rbs * (p.rb_box >> 4));
               const uint32_t d = tmem_base + (uint32_t)(qd * nq_rows);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) tc_mma_pair(d, ad + 2 * k, bd + 2 * k, idesc_b, (uint32_t)((j | k) != 0));
+              for (int k = 0; k < 4; ++k) tc_mma_pair(d, ad + 2 * k, bd + 2 * k, idesc_b, (uint32_t)((j | kb2 | k) != 0));
               tc_commit_pair(&rb_empty[rbs]);
             }
             __syncwarp();
@@ -251,10 +260,10 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp < 2 + FU_CH_WARPS) {
     // ---------------- chunk epilogue warps: chunk accumulator -> bias (+group bias) -> ReLU -> bf16 K-major operand
     const int ew = warp - 2;
-    const int q = warp & 3, h = ew >> 2;            // row quarter, 32-column half of every chunk
+    const int q = warp & 3, h = ew >> 2;            // row quarter, 64-column half (= K block) of every chunk
     const uint32_t lane_field = (uint32_t)(q * 32) << 16;
     const int trow = q * 32 + lane;                 // row inside this CTA's 128-row tile
-    float* my_sgb = sgb + ew * 32;
+    float* my_sgb = sgb + ew * 64;
     uint32_t gc = 0;
     int itc = 0;
     const bool tr = (warp == 2 && lane == 0);
@@ -262,52 +271,62 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int row0 = (2 * tp + rank) * TC_BM + q * 32;
       const float* gb_row = (p.gbias && row0 < p.M) ? p.gbias + (size_t)(row0 / p.rows_per_group) * p.N1 : nullptr;
       for (int j = 0; j < NC; ++j, ++gc) {
-        const uint32_t b = gc & 1;
-        const int c0 = j * FU_CHUNK + h * 32;
-        float gpre = 0.f;
-        if (gb_row) gpre = __ldg(gb_row + c0 + lane);   // coalesced 128 B, overlaps the wait below
+        const uint32_t ba = p.nacc == 2 ? (gc & 1) : 0u, use = p.nacc == 2 ? (gc >> 1) : gc;   // accumulator / its use count
+        const uint32_t bc = p.nch == 2 ? (gc & 1) : 0u, cuse = p.nch == 2 ? (gc >> 1) : gc;      // chunk operand buffer / use count
+        const int c0 = j * FU_CHUNK + h * 64;
+        float2 gpre = make_float2(0.f, 0.f);
+        if (gb_row) gpre = __ldg(reinterpret_cast<const float2*>(gb_row + c0) + lane);   // coalesced 256 B, overlaps the wait below
         if (tr) fu_trace(p, itc, j, 8, clock64());                // waiting for the chunk accumulator
-        mbar_wait(&acc2_full[b], (gc >> 1) & 1);
+        mbar_wait(&acc2_full[ba], use & 1);
         if (tr) fu_trace(p, itc, j, 9, clock64());                // accumulator ready
         tc_fence_after();
+        const uint32_t taddr = tmem_base + lane_field + acc_col0 + ba * FU_CHUNK + h * 64;
         float v[32];
-        tc_ld32_issue(tmem_base + lane_field + FU_ACC2_COL + b * FU_CHUNK + h * 32, v);
+        uint32_t pk[32];
+        tc_ld32_issue(taddr, v);
         if (gb_row) {
-          my_sgb[lane] = gpre;
+          *reinterpret_cast<float2*>(my_sgb + 2 * lane) = gpre;
           __syncwarp();
         }
-        tc_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cta(&acc2_empty[b], 0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b4 = *reinterpret_cast<const float4*>(sba + c0 + 4 * i);
-          v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
-        }
-        if (gb_row) {
+        for (int half = 0; half < 2; ++half) {
+          tc_ld_wait();
+          if (half == 1) {             // last TMEM read of this warp: hand the accumulator back before the conversion
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta(&acc2_empty[ba], 0);
+          }
+          const uint32_t sb = smem_u32(sba + c0 + 32 * half), sg = smem_u32(my_sgb + 32 * half);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 g4 = *reinterpret_cast<const float4*>(my_sgb + 4 * i);
-            v[4 * i] += g4.x; v[4 * i + 1] += g4.y; v[4 * i + 2] += g4.z; v[4 * i + 3] += g4.w;
+            float4 b4;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(sb + 16 * i));
+            add2(v[4 * i], v[4 * i + 1], v[4 * i], v[4 * i + 1], b4.x, b4.y);
+            add2(v[4 * i + 2], v[4 * i + 3], v[4 * i + 2], v[4 * i + 3], b4.z, b4.w);
+            if (gb_row) {
+              float4 g4;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g4.x), "=f"(g4.y), "=f"(g4.z), "=f"(g4.w) : "r"(sg + 16 * i));
+              add2(v[4 * i], v[4 * i + 1], v[4 * i], v[4 * i + 1], g4.x, g4.y);
+              add2(v[4 * i + 2], v[4 * i + 3], v[4 * i + 2], v[4 * i + 3], g4.z, g4.w);
+            }
+            pk[16 * half + 2 * i] = pack_bf16x2_relu(v[4 * i], v[4 * i + 1]);        // ReLU rides on the conversion
+            pk[16 * half + 2 * i + 1] = pack_bf16x2_relu(v[4 * i + 2], v[4 * i + 3]);
           }
+          if (half == 0) tc_ld32_issue(taddr + 32, v);
         }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         if (tr) fu_trace(p, itc, j, 10, clock64());               // converted, waiting for the operand buffer
-        mbar_wait(&ch_empty[b], ((gc >> 1) & 1) ^ 1);     // the B-GEMM that read this buffer two chunks ago is done
-        const uint32_t rbase = smem_u32(sCH) + b * 16384 + trow * 128;
+        mbar_wait(&ch_empty[bc], (cuse & 1) ^ 1);          // the B-GEMM that last read this buffer is done
+        const uint32_t rbase = smem_u32(sCH) + bc * FU_CH_BYTES + h * 16384 + trow * 128;
 #pragma unroll
-        for (int pc = 0; pc < 4; ++pc) {
-          const uint32_t a = rbase + (((uint32_t)(pc + 4 * h) ^ (trow & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(v[pc * 8], v[pc * 8 + 1])),
-                       "r"(pack_bf16x2(v[pc * 8 + 2], v[pc * 8 + 3])), "r"(pack_bf16x2(v[pc * 8 + 4], v[pc * 8 + 5])),
-                       "r"(pack_bf16x2(v[pc * 8 + 6], v[pc * 8 + 7]))
+        for (int pc = 0; pc < 8; ++pc) {
+          const uint32_t a = rbase + (((uint32_t)pc ^ (uint32_t)(trow & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk[4 * pc]), "r"(pk[4 * pc + 1]), "r"(pk[4 * pc + 2]),
+                       "r"(pk[4 * pc + 3])
                        : "memory");
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive_cta(&ch_full[b], 0);
+        if (lane == 0) mbar_arrive_cta(&ch_full[bc], 0);
         if (tr) fu_trace(p, itc, j, 11, clock64());               // operand published
       }
     }
@@ -410,11 +429,42 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------ host
+// ring depths for these shapes: what is left of shared memory after the resident operands is split between the two weight
+// rings in proportion to the bytes a chunk needs from each (a chunk = K0/64 RA boxes and 2*nq RB boxes)
+static bool fused_rings_n(int K0, int N1, int N2, bool store_out, int nch, int& ra_slots, int& rb_slots, int& rb_box) {
+  const int nq = N2 > 256 ? 2 : 1;
+  rb_box = (N2 / nq / 2) * 128;
+  const int fixed = (K0 / 64) * 16384 + nch * FU_CH_BYTES + (store_out ? FU_OUT_WARPS * 4096 : 0) +
+                    (N1 + N2 + FU_CH_WARPS * 64) * 4 + 112 * 8 + 64 + 1024;
+  const int left = FU_SMEM - fixed;
+  const int chunk_a = (K0 / 64) * FU_RA_BOX, chunk_b = 2 * nq * rb_box;
+  if (left < 2 * FU_RA_BOX + 2 * rb_box) return false;
+  ra_slots = (int)((int64_t)left * chunk_a / (chunk_a + chunk_b)) / FU_RA_BOX;
+  if (ra_slots < 2) ra_slots = 2;
+  if (ra_slots > FU_MAX_RA) ra_slots = FU_MAX_RA;
+  rb_slots = (left - ra_slots * FU_RA_BOX) / rb_box;
+  if (rb_slots > FU_MAX_RB) rb_slots = FU_MAX_RB;
+  return rb_slots >= 2;
+}
+
+// Two chunk operand buffers let the chunk epilogue of chunk j+1 store while the B-GEMM of chunk j still reads; but a TMA
+// round trip is ~1000-1500 cycles and a 12 KB weight box is consumed in ~390, so rings of 2-3 slots starve the MMAs
+// (measured: chunk period 5200 cycles against 3100 of MMA work at E = 384).  When the rings would be that shallow the
+// second operand buffer (32 KB) goes to the rings instead.
+static bool fused_rings(int K0, int N1, int N2, bool store_out, int& nch, int& ra_slots, int& rb_slots, int& rb_box) {
+  nch = 2;
+  if (fused_rings_n(K0, N1, N2, store_out, 2, ra_slots, rb_slots, rb_box) && ra_slots >= 4 && rb_slots >= 3) return true;
+  nch = 1;
+  return fused_rings_n(K0, N1, N2, store_out, 1, ra_slots, rb_slots, rb_box);
+}
+
 bool tc_fused_supported(int K0, int N1, int N2, int64_t rows_per_group, bool has_gbias) {
-  if (K0 % 64 || N1 % 64 || N2 % 64) return false;
-  if (K0 < 64 || K0 > 384 || N2 < 64 || N2 > 384 || N1 < 64 || N1 > 2048) return false;
+  if (K0 % 64 || N1 % FU_CHUNK || N2 % 64) return false;
+  if (K0 < 64 || K0 > 384 || N2 < 64 || N2 > 384 || N1 < FU_CHUNK || N1 > 2048) return false;
+  if (N2 > 256 && (N2 / 2) % 16) return false;          // two B-MMAs of N2/2 columns each
   if (has_gbias && (rows_per_group % 32 != 0)) return false;
-  return true;
+  int nch, ra, rb, box;
+  return fused_rings(K0, N1, N2, !has_gbias, nch, ra, rb, box);   // the "pre" pair (no group bias) also stores its output
 }
 
 // out = W_b relu(W_a A0 + bias_a + gbias) + bias_b.  A0 [M,K0] bf16, W_a [N1,K0], W_b [N2,N1] bf16.
@@ -431,25 +481,18 @@ int tc_fused(const __nv_bfloat16* A0, int64_t M, int K0, const __nv_bfloat16* Wa
   p.num_pairs = (num_m_tiles + 1) / 2;
   p.bias_a = bias_a; p.gbias = gbias; p.rows_per_group = rows_per_group > 0 ? rows_per_group : 32; p.bias_b = bias_b;
   p.store_out = out_bf16 != nullptr; p.out_max = out_max; p.out_max_bf16 = out_max_bf16; p.max_relu = max_relu;
-  p.rb_box = (N2 / 8) * 128;
-  // shared-memory budget: what is left after the resident operands is split between the two weight rings so that
-  // both hold the same number of chunks (a chunk = K0/64 RA boxes and 4 RB boxes)
-  const int fixed = (K0 / 64) * 16384 + 2 * 16384 + (p.store_out ? FU_OUT_WARPS * 4096 : 0) +
-                    (N1 + N2 + FU_CH_WARPS * 32) * 4 + 112 * 8 + 64 + 1024;
-  const int left = FU_SMEM - fixed;
-  const int chunk_a = (K0 / 64) * FU_RA_BOX, chunk_b = 4 * p.rb_box;
-  P3_REQUIRE(left >= chunk_a + chunk_b, P3TOK_ERR_UNSUPPORTED, "tc_fused: shapes do not fit shared memory");
-  p.ra_slots = (int)((int64_t)left * chunk_a / (chunk_a + chunk_b)) / FU_RA_BOX;
-  if (p.ra_slots > FU_MAX_RA) p.ra_slots = FU_MAX_RA;
-  p.rb_slots = (left - p.ra_slots * FU_RA_BOX) / p.rb_box;
-  if (p.rb_slots > FU_MAX_RB) p.rb_slots = FU_MAX_RB;
-  P3_REQUIRE(p.ra_slots >= 2 && p.rb_slots >= 2, P3TOK_ERR_UNSUPPORTED, "tc_fused: shapes do not fit shared memory");
+  p.nacc = N2 <= 256 ? 2 : 1;
+  p.nq = N2 > 256 ? 2 : 1;
+  p.nq_rows = N2 / p.nq;
+  p.rb_box = (p.nq_rows / 2) * 128;
+  P3_REQUIRE(fused_rings(K0, N1, N2, p.store_out != 0, p.nch, p.ra_slots, p.rb_slots, p.rb_box), P3TOK_ERR_UNSUPPORTED,
+             "tc_fused: shapes do not fit shared memory");
   CUtensorMap ta, twa, twb, tc;
   int rc = make_map(&ta, A0, M, K0, TC_BM);
   if (rc) return rc;
-  rc = make_map(&twa, Wa, N1, K0, 32);           // each CTA of the pair fetches 32 of a chunk's 64 rows
+  rc = make_map(&twa, Wa, N1, K0, FU_CHUNK / 2);  // each CTA of the pair fetches 64 of a chunk's 128 rows
   if (rc) return rc;
-  rc = make_map(&twb, Wb, N2, N1, N2 / 8);       // ... and half of a quarter of the output rows of W_b
+  rc = make_map(&twb, Wb, N2, N1, p.nq_rows / 2); // ... and half of the output rows of one B-MMA of W_b
   if (rc) return rc;
   if (out_bf16) {
     rc = make_map(&tc, out_bf16, M, N2, 32);
@@ -493,7 +536,7 @@ int tc_fused(const __nv_bfloat16* A0, int64_t M, int K0, const __nv_bfloat16* Wa
     P3_CUDA(cudaStreamSynchronize(s));
     P3_CUDA(cudaMemcpy(h.data(), p.trace, tw * 8, cudaMemcpyDeviceToHost));
     P3_CUDA(cudaFree(p.trace));
-    fprintf(stderr, "[fu_trace] M=%d K0=%d N1=%d N2=%d ra=%d rb=%d\n", p.M, p.K0, p.N1, p.N2, p.ra_slots, p.rb_slots);
+    fprintf(stderr, "[fu_trace] M=%d K0=%d N1=%d N2=%d ra=%d rb=%d nch=%d nacc=%d\n", p.M, p.K0, p.N1, p.N2, p.ra_slots, p.rb_slots, p.nch, p.nacc);
     const unsigned long long t0 = h[4];
     auto rel = [&](unsigned long long v) { return v ? (long long)(v - t0) : -1ll; };
     for (int it = 1; it < 3; ++it) {

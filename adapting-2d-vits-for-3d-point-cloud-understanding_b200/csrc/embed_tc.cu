@@ -1236,11 +1236,11 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
     // ---- remaining per-point layers on the tensor cores; the last one also emits the patch max
     bool have_gmax = false;
     static int fuse_on = -1;
-    // P3TOK_FUSED=1 routes layer pairs through tc_fused_kernel (embed_fused.cu).  Parity-green but OFF by default:
-    // measured on B200 at C2 (same box, 30 steps): layer-by-layer 1.10 ms, fused single-CTA 1.29 ms (weight rings hold
-    // ~1 chunk next to the resident A0 tile: TMA-latency bound, profiles/r01_fused_trace.txt), fused CTA-pair 1.22 ms:
-    // a tcgen05.mma costs ~90 tensor-pipe cycles however small N is, and the TMEM budget forces 64-column chunks.
-    if (fuse_on < 0) { const char* e = getenv("P3TOK_FUSED"); fuse_on = e ? atoi(e) : 0; }
+    // Layer pairs go through tc_fused_kernel (embed_fused.cu): the hidden activation of each pair never reaches HBM.
+    // P3TOK_FUSED=0 selects the layer-by-layer path.  History (same-box A/B, bench.py, ms per step): with 64-column
+    // chunks the fused path lost (c2 1.22 vs 1.10); with 128-column chunks - every MMA at its nominal rate - and rings
+    // deep enough to cover a TMA round trip it wins: c2 1.017 vs 1.166, c4 10.11 vs 10.72, c5 2.31 vs 2.50, c3 11.99 vs 12.73.
+    if (fuse_on < 0) { const char* e = getenv("P3TOK_FUSED"); fuse_on = e ? atoi(e) : 1; }
     const bool fuse_pre = fuse_on && fused_max && (m->n_pre - first_tc == 2) && m->pre_relu[m->n_pre - 2] == 1 &&
                           m->pre_relu[m->n_pre - 1] == 0 &&
                           tc_fused_supported(kin, m->pre_dim[m->n_pre - 2], m->pre_dim[m->n_pre - 1], k, false);
@@ -1297,18 +1297,6 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
                    nullptr, nullptr, 0, s);
     if (rc) return rc;
     float* tok = tokens + g0 * m->out_dim;
-    if (fuse_on && fused_max && tc_fused_supported((int)L.F, m->mid_dim, m->out_dim, k, true)) {
-      // concat layer (per-point half + group bias, ReLU) and output layer in one kernel; only the patch max is written
-      rc = tc_fused(act[cur], rows, (int)L.F, (const __nv_bfloat16*)m->w_mid_f, m->mid_dim, nullptr, gbias, (int)k,
-                    (const __nv_bfloat16*)m->w_out, m->out_dim, m->b_out, nullptr, parts == 1 ? tok : gmax_f32, nullptr,
-                    parts == 1 ? m->out_relu : 0, s);
-      if (rc) return rc;
-      if (parts > 1) {
-        group_max_f32_kernel<<<grid_1d(gc * m->out_dim, 256), 256, 0, s>>>(gmax_f32, gc, parts, m->out_dim, m->out_relu, tok, nullptr);
-        P3_LAUNCH_CHECK("group_max_f32_kernel");
-      }
-      continue;
-    }
     // narrow blocks (P3Embed stage 0): concat layer + output layer + pool in one kernel with the weights resident in
     // shared memory (embed_stage.cu); the hidden activation never reaches HBM.  P3TOK_STAGE=0 disables it.
     static int stage_on = -1;
@@ -1316,6 +1304,18 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
     if (stage_on && fused_max && tc_stage_supported((int)L.F, m->mid_dim, m->out_dim, k)) {
       rc = tc_stage(act[cur], rows, (int)L.F, (const __nv_bfloat16*)m->w_mid_f, m->mid_dim, nullptr, gbias, (int)k,
                     (const __nv_bfloat16*)m->w_out, m->out_dim, m->b_out, parts == 1 ? tok : gmax_f32, parts == 1 ? m->out_relu : 0, s);
+      if (rc) return rc;
+      if (parts > 1) {
+        group_max_f32_kernel<<<grid_1d(gc * m->out_dim, 256), 256, 0, s>>>(gmax_f32, gc, parts, m->out_dim, m->out_relu, tok, nullptr);
+        P3_LAUNCH_CHECK("group_max_f32_kernel");
+      }
+      continue;
+    }
+    if (fuse_on && fused_max && tc_fused_supported((int)L.F, m->mid_dim, m->out_dim, k, true)) {
+      // concat layer (per-point half + group bias, ReLU) and output layer in one kernel; only the patch max is written
+      rc = tc_fused(act[cur], rows, (int)L.F, (const __nv_bfloat16*)m->w_mid_f, m->mid_dim, nullptr, gbias, (int)k,
+                    (const __nv_bfloat16*)m->w_out, m->out_dim, m->b_out, nullptr, parts == 1 ? tok : gmax_f32, nullptr,
+                    parts == 1 ? m->out_relu : 0, s);
       if (rc) return rc;
       if (parts > 1) {
         group_max_f32_kernel<<<grid_1d(gc * m->out_dim, 256), 256, 0, s>>>(gmax_f32, gc, parts, m->out_dim, m->out_relu, tok, nullptr);
