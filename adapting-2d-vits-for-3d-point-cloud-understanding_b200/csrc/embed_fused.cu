@@ -6,21 +6,26 @@
 //   "pre"  pair  h1 -> 256->512 (ReLU) -> 512->E        emits f (bf16) and the per-patch max g
 //   "post" pair  f  -> E->2E (+W_g.g as group bias, ReLU) -> 2E->E   emits the patch tokens (max over the patch)
 // The hidden activation (rows x 512 / rows x 768, the widest tensors of the block) never leaves the SM:
-// per row tile the first GEMM is evaluated in 64-column chunks into a small TMEM accumulator, epilogue warps
-// turn each chunk into a bf16 K-major shared-memory operand (bias, ReLU), and the second GEMM consumes it at
-// once, accumulating the tile's full output row block in TMEM (<= 384 columns).
+// per row tile the first GEMM is evaluated in 128-column chunks into a TMEM chunk accumulator, epilogue warps
+// turn each chunk into a bf16 K-major shared-memory operand (bias / group bias, ReLU), and the second GEMM consumes it
+// at once, accumulating the tile's full output row block in TMEM (<= 384 columns).  128 columns is the narrowest N
+// at which a tcgen05.mma runs at its nominal rate (65 cycles; N = 64 costs 56 instead of 32, profiles/microbench):
+// the first version of this kernel used 64-column chunks and N2/4-column B-MMAs and lost to the layer-by-layer path.
 //
 // Two CTAs of a cluster work as a pair (tcgen05 cta_group::2): one MMA spans both SMs (M = 256 rows), each CTA
-// keeps its own 128 rows of A0 / chunk operands / accumulators and only HALF of every weight box.  With the
-// A0 tile (64-96 KB) and the chunk buffers resident, a single CTA's weight rings held ~1 chunk of weights and the
-// kernel was TMA-latency bound (profiles/r01_fused_trace.txt); halving the weight bytes per CTA doubles the
-// number of chunks in flight.
+// keeps its own 128 rows of A0 / chunk operands / accumulators and only HALF of every weight box.
 //
-// Per CTA shared memory: A0 (K0/64 x 16 KB) | 2 chunk operands (16 KB) | ring RA of 4 KB boxes [32 n x 64 k]
-// of W_a | ring RB of boxes [N2/8 n x 64 k] of W_b | 8 x 4 KB store staging ("pre" only) | biases.
-// TMEM (per CTA, its 128 rows): columns [0,N2) output accumulator, [384,448) / [448,512) chunk accumulators.
+// Per CTA shared memory: A0 (K0/64 x 16 KB) | 1 or 2 chunk operands (32 KB each) | ring RA of 8 KB boxes [64 n x 64 k]
+// of W_a | ring RB of boxes [nq_rows/2 n x 64 k] of W_b | 8 x 4 KB store staging ("pre" only) | biases.  A TMA round
+// trip is 1000-1500 cycles and a 12 KB W_b box is consumed in ~390, so ring DEPTH decides whether the MMAs starve: when
+// two chunk operands would leave fewer than 4 + 3 ring slots (E = 384: 3 + 2), the second operand buffer goes to the
+// rings (5 + 4) and the chunk epilogue waits for the previous chunk's B-GEMM before it stores (measured: chunk period
+// 5200 -> 4270 cycles against 3112 of MMA work; what is left is shared-memory bandwidth - MMA operand fetch 256 KB +
+// ring fills 96 KB + operand stores 32 KB per chunk is ~3000 cycles at 128 B/cycle).
+// TMEM (per CTA, its 128 rows): columns [0,N2) output accumulator; chunk accumulators in the last 128 (N2 > 256:
+// single-buffered) or 256 columns.
 // Warps: 0 = TMA producer (A0 + RA), 1 = MMA issuer (leader CTA only), 2..9 = chunk epilogue (row quarter q,
-// 32-column half h of each chunk), 10..17 = tile epilogue (row quarter q, alternating 64-column output groups),
+// 64-column half h of each chunk), 10..17 = tile epilogue (row quarter q, alternating 64-column output groups),
 // 18 = TMA producer (RB).  Barriers that the leader's MMA warp waits on live in the leader CTA: TMA loads of
 // both CTAs signal them (cta_group::2 loads), epilogue warps of the peer arrive remotely; barriers that
 // producers / epilogue warps wait on are local and released by multicast tcgen05.commit.

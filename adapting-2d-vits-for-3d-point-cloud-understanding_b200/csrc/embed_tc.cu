@@ -4,33 +4,38 @@
 // half of a P3Embed stage (src/models/pix4point.py:179-188), eval-mode BatchNorm folded on the
 // host, in the rtol-1e-2 precision mode: bf16 operands, fp32 accumulation in tensor memory.
 //
-// Kernels
-//   rows_first_layer_kernel  gather + centre-subtract + first layer on CUDA cores when the input is narrow
-//   rows_first_layer_apf_    (cin <= 16: APF 2C = 6/8, P3Embed stage 0 = 6): fp32 math from fp32 coordinates,
-//   kernel                   bf16 out.  The APF variant folds the centre half of [nbr-ctr || ctr] into a
-//                            per-patch bias.  Wide inputs (P3Embed stage 1, cin = 131) are gathered to a
-//                            zero-padded bf16 row matrix (rows_gather_bf16_kernel) and use the tensor cores.
+// Kernels in this file
+//   rows_first_layer_apf_warp_kernel / rows_first_layer_narrow_kernel
+//                            gather + centre-subtract + first layer on CUDA cores when the input is narrow (cin <= 8: APF
+//                            2C = 6/8, P3Embed stage 0 = 6): fp32 math from fp32 coordinates, bf16 out; one warp per
+//                            32-row block, the next block's gather in flight while the current one is computed.  The APF
+//                            variant folds the centre half of [nbr-ctr || ctr] into a per-block bias.
+//                            (rows_first_layer_kernel / rows_first_layer_apf_kernel: the generic CTA-per-block forms.)
+//   rows_gather_p4p_bf16_kernel / rows_gather_bf16_kernel
+//                            wide inputs (P3Embed stage >= 1, cin = 131) are gathered to a zero-padded bf16 row matrix
+//                            for the tensor cores.
 //   tc_linear_kernel<PAIR>   C = act(A W^T + bias + group_bias).  Persistent, warp-specialised:
 //                              warp 0   TMA producer (warp-uniform loop, one elected lane issues)
 //                              warp 1   tcgen05.mma issuer, descriptors in uniform registers
-//                              warps 2-9 epilogue, two per TMEM lane quarter
-//                            PAIR = cta_group::2: two CTAs of a cluster share one 256 x BN tile - each holds its
-//                            128 rows of A, HALF of the weight tile and its half of the accumulator; the leader
-//                            issues the MMAs, TMA loads of both CTAs signal the leader's barrier, tcgen05.commit
-//                            multicasts the slot release.  Stage = A tile 16 KB + weight rows in the 128B-swizzled
-//                            K-major UMMA layout; ring depth fills the 227 KB left by the epilogue scratch (4-5
-//                            stages).  Two 128 x BN fp32 accumulators in TMEM overlap the epilogue of tile i with
-//                            the MMAs of tile i+1; the epilogue works in 32-column tcgen05.ld pieces (register
-//                            budget), fuses bias (staged in smem) / per-group bias (staged per warp, coalesced) /
-//                            ReLU, packs bf16 into a swizzled 32x64 box and hands it to a double-buffered TMA
-//                            store; the fused patch max-pool is a lane-transpose reduction (31 shuffles per 32
-//                            columns).  The accumulator is released right after a warp's last TMEM read.
-// What bounded it, in the order found (traces via P3TOK_TC_TRACE=1, ncu in profiles/): direct per-row global
+//                              warps 2-9 epilogue, two per TMEM lane quarter;  warp 10  A producer (A-resident mode)
+//                            PAIR = cta_group::2: two CTAs of a cluster share one 256 x BN tile - each holds its 128
+//                            rows of A, HALF of the weight tile and its half of the accumulator; the leader issues the
+//                            MMAs, TMA loads of both CTAs signal the leader's barrier, tcgen05.commit multicasts the slot
+//                            release.  Two 128 x BN fp32 accumulators in TMEM overlap the epilogue of tile i with the
+//                            MMAs of tile i+1; the epilogue works in 32-column tcgen05.ld pieces, fuses bias (smem) /
+//                            per-group bias / ReLU (F2FP.RELU), packs bf16 into a swizzled 32x64 box for a TMA store; the
+//                            fused patch max-pool is one redux.sync.max.f32 per column.
+//   patch_embed_bf16         orchestration: which kernel runs which layers.  Default: first layer (CUDA cores) ->
+//                            tc_fused_kernel (embed_fused.cu) for the two remaining per-point layers -> tc_linear for the
+//                            pooled half of the concat layer (per-group bias) -> tc_fused_kernel for concat + output
+//                            layer + pool; narrow P3Embed stages use tc_stage_kernel (embed_stage.cu) instead.
+// What bounded tc_linear, in the order found (traces via P3TOK_TC_TRACE=1, ncu in profiles/): direct per-row global
 // stores (620 GB/s) -> TMA stores; dependent bias loads in the epilogue -> smem staging; per-launch fixed
-// cost -> 2^20-row chunks instead of L2-sized ones; the single-thread MMA loop (21 SASS instructions between
-// MMAs because every operand had to be moved to uniform registers) -> warp-uniform loops + elect_one;
-// weight-tile bytes per stage -> CTA pairs.  TMA multicast of the weight tile and L2 prefetch of the next
-// activation tile were tried and measured neutral (kept behind P3TOK_TC_CLUSTER / P3TOK_TC_PREFETCH).
+// cost -> large row chunks; the single-thread MMA loop -> warp-uniform loops + elect_one; weight-tile bytes per
+// stage -> CTA pairs; then the epilogue itself (500-1000 cycles per 32x32 piece: ~140 dependent instructions in one
+// warp) and the HBM round trip of every activation -> the fused kernels.  TMA multicast of the weight tile, L2
+// prefetch of the next activation tile, 16 epilogue warps and a prefetched group-bias slice were measured neutral
+// or worse.
 // The concat layer W.[g||f] is evaluated as W_g.g (tensor-core GEMM over groups, becomes the per-group bias)
 // + W_f.f, so no (rows, 2E) tensor exists.
 #include <algorithm>
