@@ -51,6 +51,7 @@ struct FusedParams {
   int nch;                          // chunk operand buffers in shared memory: 2, or 1 when the weight rings need the room
   int nacc;                         // chunk accumulators in TMEM: 2 when N2 <= 256, else 1 (384 output + 128 chunk columns = 512)
   int nq, nq_rows;                  // output columns per B-MMA: N2 (nq = 1) or N2/2 (nq = 2, N2 > 256)
+  int a_reuse;                      // nq = 2: second MMA of a K step re-uses the A operand from the collector (P3TOK_FUSED_AREUSE)
   const float* bias_a;              // [N1] or null
   const float* gbias;               // [M / rows_per_group, N1] or null; rows_per_group % 32 == 0
   int rows_per_group;
@@ -235,6 +236,37 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (issuer) fu_trace(p, it, j, 1, clock64());           // chunk j operand ready
           if (j == 0) mbar_wait(acc3_empty, (uint32_t)(it & 1) ^ 1);
           tc_fence_after();
+          if (NQ == 2 && p.a_reuse) {
+            // two output column groups: both MMAs of a K step read the same chunk operand - the second one takes it from
+            // the A collector instead of shared memory (this kernel is bound by shared-memory bandwidth)
+            for (int kb2 = 0; kb2 < 2; ++kb2) {
+              const int s0 = rbs;
+              const uint32_t ph0 = rbph;
+              if (++rbs == p.rb_slots) { rbs = 0; rbph ^= 1; }
+              const int s1 = rbs;
+              const uint32_t ph1 = rbph;
+              if (++rbs == p.rb_slots) { rbs = 0; rbph ^= 1; }
+              mbar_wait(&rb_full[s0], ph0);
+              if (issuer && kb2 == 0) fu_trace(p, it, j, 2, clock64());   // first W_b box present
+              mbar_wait(&rb_full[s1], ph1);
+              if (issuer && kb2 == 1) fu_trace(p, it, j, 3, clock64());   // last W_b box present
+              tc_fence_after();
+              if (issuer) {
+                const uint64_t ad = dconst | (uint64_t)(ch_base + b * (FU_CH_BYTES >> 4) + kb2 * (16384 >> 4));
+                const uint64_t bd0 = dconst | (uint64_t)(rb_base + s0 * (p.rb_box >> 4));
+                const uint64_t bd1 = dconst | (uint64_t)(rb_base + s1 * (p.rb_box >> 4));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t acc = (uint32_t)((j | kb2 | k) != 0);
+                  tc_mma_pair_a<1>(tmem_base, ad + 2 * k, bd0 + 2 * k, idesc_b, acc);
+                  tc_mma_pair_a<0>(tmem_base + (uint32_t)nq_rows, ad + 2 * k, bd1 + 2 * k, idesc_b, acc);
+                }
+                tc_commit_pair(&rb_empty[s0]);
+                tc_commit_pair(&rb_empty[s1]);
+              }
+              __syncwarp();
+            }
+          } else
           for (int kq = 0; kq < 2 * NQ; ++kq) {
             const int kb2 = kq / NQ, qd = kq - kb2 * NQ;
             mbar_wait(&rb_full[rbs], rbph);
@@ -489,6 +521,9 @@ int tc_fused(const __nv_bfloat16* A0, int64_t M, int K0, const __nv_bfloat16* Wa
   p.nacc = N2 <= 256 ? 2 : 1;
   p.nq = N2 > 256 ? 2 : 1;
   p.nq_rows = N2 / p.nq;
+  static int areuse_on = -1;
+  if (areuse_on < 0) { const char* e = getenv("P3TOK_FUSED_AREUSE"); areuse_on = e ? atoi(e) : 1; }
+  p.a_reuse = areuse_on && p.nq == 2;
   p.rb_box = (p.nq_rows / 2) * 128;
   P3_REQUIRE(fused_rings(K0, N1, N2, p.store_out != 0, p.nch, p.ra_slots, p.rb_slots, p.rb_box), P3TOK_ERR_UNSUPPORTED,
              "tc_fused: shapes do not fit shared memory");
