@@ -81,6 +81,7 @@ struct TcParams {
   int relu;
   __nv_bfloat16* out_bf16; // [M,N] or null
   float* out_f32;          // [M,N] or null
+  int f32_tma;             // out_f32 goes through swizzled 32x32 fp32 boxes + TMA stores (tmC is the fp32 map; no out_bf16)
   float* out_max;          // [ceil(M/32), N] max over each 32 consecutive rows, or null
   __nv_bfloat16* out_max_bf16;
   int max_relu;            // apply ReLU to the max (out_relu of the block)
@@ -180,7 +181,19 @@ __device__ __forceinline__ void epilogue_half(const TcParams& p, const float* sb
       }
     }
   }
-  if (p.out_f32 && row_ok) {
+  if (p.out_f32 && p.f32_tma) {
+    // this half's 32 rows x 32 columns as one 4 KB box (rows of 128 B, 16-byte pieces XOR-swizzled by row): the direct
+    // per-thread stores below touch 32 different cache lines per instruction (the group-bias GEMM spent most of its
+    // 38 us in them)
+    const uint32_t rbase = sbox + (uint32_t)half * TC_STAGING + lane * 128;
+#pragma unroll
+    for (int pc = 0; pc < 8; ++pc) {
+      const uint32_t a = rbase + (((uint32_t)pc ^ (lane & 7)) << 4);
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * pc]), "f"(v[4 * pc + 1]), "f"(v[4 * pc + 2]),
+                   "f"(v[4 * pc + 3])
+                   : "memory");
+    }
+  } else if (p.out_f32 && row_ok) {
     float* o = p.out_f32 + (size_t)row * p.N + n0;
 #pragma unroll
     for (int j = 0; j < 32; j += 4)
@@ -430,8 +443,9 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           gpre = __ldg(reinterpret_cast<const float2*>(gb_row + c));
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + gi * 64);
-        const uint32_t sbox = smem_u32(stg + sbuf * TC_STAGING);
-        if (p.out_bf16) {   // the TMA store issued two groups ago has finished reading this box
+        const bool f32_tma = p.out_f32 && p.f32_tma;   // fp32 output: box 0 / box 1 of this warp = the two 32-column halves
+        const uint32_t sbox = f32_tma ? smem_u32(stg) : smem_u32(stg + sbuf * TC_STAGING);
+        if (p.out_bf16 || f32_tma) {   // the TMA store issued two groups (fp32: two halves) ago has finished reading this box
           if (lane == 0) {
             if (TC_EPI_BOXES == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -451,6 +465,19 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         epilogue_half(p, sbias, gb_shared ? nullptr : gb, gb_shared ? sgb : nullptr, sbox, 0, row0, row, row_ok, lane, n0, v);
         tc_trace2(p, tr2, it, g2, 3);
         tc_ld32_issue(taddr + 32, v);
+        if (f32_tma) {   // store half 0, then make sure box 1 (the previous group's half 1) has been read
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmC)),
+                         "r"(sbox), "r"(n0), "r"(row0)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          }
+          __syncwarp();
+        }
         tc_ld_wait();
         tc_trace2(p, tr2, it, g2, 4);
         if (last) {
@@ -478,6 +505,16 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           if (TC_EPI_BOXES == 2) sbuf ^= 1;
+        } else if (f32_tma) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0 && n0 + 32 < p.N) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmC)),
+                         "r"(sbox + (uint32_t)TC_STAGING), "r"(n0 + 32), "r"(row0)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
         }
         tc_trace2(p, tr2, it, g2, 6);
         __syncwarp();   // group-bias slice is free for the next group
@@ -547,9 +584,14 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
   while (p.CL > 1 && p.num_m_tiles < p.CL) p.CL /= 2;
   rc = make_map(&tb, W, N, K, p.BN / p.CL);     // each CTA of a cluster fetches BN/CL rows of the weight tile
   if (rc) return rc;
+  p.f32_tma = 0;
   if (out_bf16) {
     rc = make_map(&tc, out_bf16, M, N, 32);     // store boxes: 64 columns x 32 rows
     if (rc) return rc;
+  } else if (out_f32 && TC_EPI_BOXES == 2 && N % 4 == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0) {
+    rc = make_map_f32(&tc, out_f32, M, N, 32);  // fp32 store boxes: 32 columns x 32 rows
+    if (rc) return rc;
+    p.f32_tma = 1;
   } else {
     tc = ta;                                     // unused by the kernel
   }

@@ -283,6 +283,24 @@ static inline int make_map(CUtensorMap* m, const void* base, int64_t rows, int64
   return P3TOK_OK;
 }
 
+// fp32 row-major [rows, cols] (row pitch = cols*4 bytes), box = 32 cols (128 B) x box_rows, 128B swizzle
+static inline int make_map_f32(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int box_rows) {
+  P3_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && cols % 4 == 0, P3TOK_ERR_UNSUPPORTED,
+             "tensor map (f32): base must be 16-byte aligned and the row pitch a multiple of 16 bytes");
+  EncodeTiledFn fn = encode_fn();
+  P3_REQUIRE(fn, P3TOK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  P3_REQUIRE(r == CUDA_SUCCESS, P3TOK_ERR_CUDA, "cuTensorMapEncodeTiled (f32) failed (%d) rows=%lld cols=%lld", (int)r,
+             (long long)rows, (long long)cols);
+  return P3TOK_OK;
+}
+
 static inline int num_sms() {
   static int n = 0;
   if (!n) {
