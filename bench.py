@@ -385,7 +385,7 @@ def run_p3tok(args, w, rank, world, local_rank):
                      "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (ach_tf / peak_tf) if ach_tf else None,
                      # dram__bytes_read.sum + dram__bytes_write.sum of the embed launches of one step (first layer 216 MB,
-                     # fused 256->512->384 pair 631 MB, group-bias GEMM 16 MB, fused 384->768->384 pair 481 MB), from the
+                     # fused 256->512->384 pair 631 MB, group-bias GEMM 14 MB, fused 384->768->384 pair 483 MB), from the
                      # ncu --set full capture summarised in profiles/r01_c2_ncu_full.txt (c2 / bf16 only; the
                      # layer-by-layer path of the first session moved 3.72 GB)
                      "traffic": 1.344e9 if (args.workload == "c2" and precision == "bf16") else None,
