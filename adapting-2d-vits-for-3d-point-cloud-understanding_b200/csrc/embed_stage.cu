@@ -33,7 +33,10 @@
 
 namespace p3tok {
 
-constexpr int ST_E1_WARPS = 8, ST_E2_WARPS = 8;
+#ifndef P3TOK_ST_E1_WARPS
+#define P3TOK_ST_E1_WARPS 8
+#endif
+constexpr int ST_E1_WARPS = P3TOK_ST_E1_WARPS, ST_E2_WARPS = 8;
 constexpr int ST_THREADS = (2 + ST_E1_WARPS + ST_E2_WARPS) * 32;
 constexpr int ST_SMEM = 227 * 1024;
 constexpr int ST_ACC_COLS = 256;            // TMEM columns per accumulator
@@ -224,12 +227,13 @@ tc_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp < 2 + ST_E1_WARPS) {
     // ---------------- hidden epilogue: GEMM 1 accumulator -> + group bias -> ReLU -> bf16 K-major operand of GEMM 2
     // (row quarter q x column half h).  Finer hand-over (one barrier per 64-column K block, TMEM loads one block ahead,
-    // one warp per quarter) was built and measured no better - see the header.
+    // one warp per quarter) was built and measured no better - see the header; 16 hidden-epilogue warps
+    // (-DP3TOK_ST_E1_WARPS=16) measured 6 % slower: the kernel is bound by shared-memory bandwidth, not by warp latency.
     const int ew = warp - 2;
     const int q = warp & 3, h = ew >> 2;            // TMEM lane quarter, column half
     const uint32_t lane_field = (uint32_t)(q * 32) << 16;
     const int trow = q * 32 + lane;                 // row inside this CTA's 128-row tile
-    const int half_cols = p.N1 / 2, pieces = half_cols / 32;
+    const int half_cols = p.N1 / (ST_E1_WARPS / 4), pieces = half_cols / 32;   // columns per warp of a row quarter
     float* my_sgb = sgb + ew * 128;
     const uint32_t h_row = smem_u32(sH) + trow * 128;
     // this warp's slice of the group-bias row of tile `tp`, one float4 per lane, fetched ONE TILE AHEAD (otherwise an L2

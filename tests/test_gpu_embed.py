@@ -157,7 +157,8 @@ def test_tc_linear_building_block(M, K, N):
     assert float((om - refm).abs().max()) <= 2e-5 * max(scale, 1.0) + 1e-5 * K ** 0.5
 
 
-@pytest.mark.parametrize("E,k,cin", [(64, 32, 6), (384, 32, 6), (48, 16, 8), (96, 64, 6)])
+@pytest.mark.parametrize("E,k,cin", [(64, 32, 6), (384, 32, 6), (48, 16, 8), (96, 64, 6), (384, 64, 6), (128, 32, 8),
+                                     (128, 64, 6), (256, 32, 6), (320, 32, 6)])
 def test_bf16_path_matches_its_arithmetic_model(E, k, cin):
     """Tight check of the tensor-core path: against a torch model of exactly its arithmetic (bf16 operands,
     fp32 accumulate) the only differences are accumulation order and bf16 ties -> 2e-3 of max."""
