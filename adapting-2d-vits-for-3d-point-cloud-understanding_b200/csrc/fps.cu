@@ -42,20 +42,25 @@ __device__ __forceinline__ void warp_argmax(uint32_t& key, uint32_t& idx) {
   key = m;
 }
 
-// ---- cluster candidate exchange without barrier.cluster: each CTA pushes its 32-byte candidate into every
-// peer's shared memory and then arrives (release, cluster scope) on that peer's mbarrier; a CTA waits (acquire,
-// cluster scope) until all CL candidates of the iteration are in.  Measured: barrier.cluster per iteration cost
-// 3.4 us at 8 x 1024 threads (C4); this exchange is one DSMEM store + one remote arrive per peer.
+// ---- cluster candidate exchange without barrier.cluster: each CTA sends its 32-byte candidate into every peer's shared
+// memory as two st.async (STAS.128) - a remote store that also counts its bytes on the peer's mbarrier (complete_tx), so
+// data and signal travel as one message - and every CTA arms its own barrier with the CL*32 bytes it expects and waits
+// (acquire, cluster scope) until all candidates of the iteration are in.  History: barrier.cluster per iteration 3.4 us at
+// 8 x 1024 threads (C4); DSMEM store + separate remote mbarrier.arrive(release) 2.4 us; this form: see DESIGN.md.
 __device__ __forceinline__ uint32_t fps_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void fps_push_cand(const FpsCand* local_slot, uint64_t* local_bar, uint32_t dst_cta, const FpsCand& c) {
   uint32_t ra, rb;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(fps_smem_u32(local_slot)), "r"(dst_cta));
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(fps_smem_u32(local_bar)), "r"(dst_cta));
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "r"(c.key), "r"(c.idx), "r"(__float_as_uint(c.x)),
-               "r"(__float_as_uint(c.y))
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%2, %3, %4, %5}, [%1];" ::"r"(ra), "r"(rb),
+               "r"(c.key), "r"(c.idx), "r"(__float_as_uint(c.x)), "r"(__float_as_uint(c.y))
                : "memory");
-  asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(ra + 16), "r"(__float_as_uint(c.z)) : "memory");
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rb) : "memory");
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%2, %3, %4, %5}, [%1];" ::"r"(ra + 16), "r"(rb),
+               "r"(__float_as_uint(c.z)), "r"(0u), "r"(0u), "r"(0u)
+               : "memory");
+}
+__device__ __forceinline__ void fps_expect_cands(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fps_smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void fps_wait_cands(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
@@ -159,8 +164,8 @@ fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __r
     // the owner CTA publishes the start point's coordinates to every peer
     cg::cluster_group cluster = cg::this_cluster();
     if (t == 0) {
-      cuda::ptx::mbarrier_init(&cbar[0], CL);
-      cuda::ptx::mbarrier_init(&cbar[1], CL);
+      cuda::ptx::mbarrier_init(&cbar[0], 1);   // one local arrive (expect_tx) per phase; the peers contribute bytes
+      cuda::ptx::mbarrier_init(&cbar[1], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (t == 0 && far >= p0 && far < p0 + np) {
@@ -238,6 +243,7 @@ fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __r
             c.x = c.y = c.z = 0.f;
           }
           c.pad[0] = c.pad[1] = c.pad[2] = 0;
+          if (lane == 0) fps_expect_cands(&cbar[buf], (uint32_t)CL * 32u);
           fps_push_cand(&ccand[buf * 16 + rank], &cbar[buf], (uint32_t)lane, c);
         }
         // buffer `buf` is reused every second iteration; a peer can be at most one iteration ahead (it needs this
