@@ -1,5 +1,7 @@
 // embed.cuh - internal interfaces shared by the patch-embedding paths.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace p3tok {
@@ -15,6 +17,19 @@ int patch_embed_f32(const p3tok_rows* rows, const p3tok_mlp* mlp, void* ws, int6
 int64_t patch_embed_bf16_workspace(const p3tok_mlp* mlp, int64_t ngroups, int64_t k);
 int patch_embed_bf16(const p3tok_rows* rows, const p3tok_mlp* mlp, void* ws, int64_t ws_bytes, float* tokens,
                      cudaStream_t s);
+
+// extra epilogue of tc_linear for the ViT blocks (vit.cu): GELU, fp32 residual stream, column-slice outputs
+struct TcExtra {
+  int gelu = 0;                    // exact GELU after the bias
+  const float* residual = nullptr; // out_f32 = res_mul * residual + out_scale * value
+  float res_mul = 1.f, out_scale = 1.f;
+  int64_t ldc = 0;                 // row pitch of out_bf16 in elements (0 = N)
+};
+int tc_linear_ex(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat16* W, int N, const float* bias, int relu,
+                 const TcExtra& ex, __nv_bfloat16* out_bf16, float* out_f32, cudaStream_t s);
+
+// vit.cu
+int64_t apf_vit_workspace(int64_t B, int64_t G, int64_t D, int64_t H, int64_t R);
 
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 

@@ -85,6 +85,9 @@ struct TcParams {
   float* out_max;          // [ceil(M/32), N] max over each 32 consecutive rows, or null
   __nv_bfloat16* out_max_bf16;
   int max_relu;            // apply ReLU to the max (out_relu of the block)
+  int gelu;                // exact (erf) GELU after bias (ViT mlp.fc1, embed.cuh TcExtra)
+  const float* residual;   // [M,N] f32 or null: out_f32 = res_mul * residual + out_scale * value (may alias out_f32:
+  float res_mul, out_scale; // every element is read by the thread that produces it, before its store box leaves)
   int stages, stage_bytes; // TMA->MMA ring depth and bytes per stage (A tile 16 KB + this CTA's part of the weight tile)
   int prefetch;            // L2-prefetch the next item's activation tile
   int ares;                // A-resident mode (pairs only): a pair walks ALL N tiles of its M group, the group's activation
@@ -108,6 +111,20 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {   // explicit shared-
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
   return v;
+}
+
+// exact GELU x * Phi(x) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32 rounding level): one
+// MUFU.RCP + one MUFU.EX2 + 9 FMA-pipe instructions instead of erff()'s branchy ~25
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = exp2f(-1.4426950408889634f * z * z);
+  const float erf_abs = fmaf(-poly * t, e, 1.f);           // erf(|x|/sqrt 2)
+  return 0.5f * x + 0.5f * fabsf(x) * erf_abs;             // x/2 * (1 + sign(x) erf(|x|/sqrt 2))
 }
 
 // `sbias` is staged zero-padded to a multiple of 64 columns, so the 32 columns starting at n0 are always readable.
@@ -159,6 +176,24 @@ __device__ __forceinline__ void epilogue_half(const TcParams& p, const float* sb
   // bf16-only outputs take their ReLU from the conversion instruction (F2FP.RELU) instead of 32 FMNMX
   const bool relu_in_pack = p.relu && !p.out_f32 && !p.out_max && !p.out_max_bf16;
   epilogue_affine(v, p, sbias, gb, n0, p.relu && !relu_in_pack);
+  if (p.gelu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  }
+  if (p.residual) {   // fp32 residual stream of the ViT blocks: 128 contiguous bytes per lane (whole sectors)
+    const int nmax = p.N - 4;
+    const float* rr = p.residual + (size_t)(row_ok ? row : 0) * p.N;
+    float4 r4[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r4[j] = *reinterpret_cast<const float4*>(rr + min(n0 + 4 * j, nmax));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[4 * j] = fmaf(p.res_mul, r4[j].x, p.out_scale * v[4 * j]);
+      v[4 * j + 1] = fmaf(p.res_mul, r4[j].y, p.out_scale * v[4 * j + 1]);
+      v[4 * j + 2] = fmaf(p.res_mul, r4[j].z, p.out_scale * v[4 * j + 2]);
+      v[4 * j + 3] = fmaf(p.res_mul, r4[j].w, p.out_scale * v[4 * j + 3]);
+    }
+  }
   if (p.out_bf16) {
     const uint32_t rbase = sbox + lane * 128;
     if (relu_in_pack) {
@@ -555,7 +590,7 @@ static int pick_bn(int N) {
 // C = act(A[M,K] W[N,K]^T + bias + gbias), bf16 operands.  K % 8 == 0, N % 8 == 0.
 static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat16* W, int N, const float* bias,
                      const float* gbias, int rows_per_group, int relu, __nv_bfloat16* out_bf16, float* out_f32,
-                     float* out_max, __nv_bfloat16* out_max_bf16, int max_relu, cudaStream_t s) {
+                     float* out_max, __nv_bfloat16* out_max_bf16, int max_relu, cudaStream_t s, const TcExtra* ex = nullptr) {
   P3_REQUIRE(K % 8 == 0 && N % 8 == 0, P3TOK_ERR_UNSUPPORTED, "tc_linear: K=%d and N=%d must be multiples of 8", K, N);
   P3_REQUIRE(N <= TC_MAX_N, P3TOK_ERR_UNSUPPORTED, "tc_linear: N=%d > %d", N, TC_MAX_N);
   P3_REQUIRE(M < (1ll << 31) - 256, P3TOK_ERR_UNSUPPORTED, "tc_linear: too many rows");
@@ -577,6 +612,12 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
   p.num_n_tiles = (N + p.BN - 1) / p.BN;
   p.bias = bias; p.gbias = gbias; p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1; p.relu = relu;
   p.out_bf16 = out_bf16; p.out_f32 = out_f32; p.out_max = out_max; p.out_max_bf16 = out_max_bf16; p.max_relu = max_relu;
+  p.gelu = ex ? ex->gelu : 0;
+  p.residual = ex ? ex->residual : nullptr;
+  p.res_mul = ex ? ex->res_mul : 0.f;
+  p.out_scale = ex ? ex->out_scale : 1.f;
+  const int64_t ldc = (ex && ex->ldc > 0) ? ex->ldc : N;   // row pitch of out_bf16 (column slices of a wider matrix)
+  P3_REQUIRE(ldc == N || (out_bf16 && !out_f32 && ldc % 8 == 0), P3TOK_ERR_UNSUPPORTED, "tc_linear: ldc only for bf16 outputs");
   CUtensorMap ta, tb, tc;
   int rc = make_map(&ta, A, M, K, TC_BM);
   if (rc) return rc;
@@ -586,7 +627,7 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
   if (rc) return rc;
   p.f32_tma = 0;
   if (out_bf16) {
-    rc = make_map(&tc, out_bf16, M, N, 32);     // store boxes: 64 columns x 32 rows
+    rc = make_map(&tc, out_bf16, M, N, 32, ldc);     // store boxes: 64 columns x 32 rows
     if (rc) return rc;
   } else if (out_f32 && TC_EPI_BOXES == 2 && N % 4 == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0) {
     rc = make_map_f32(&tc, out_f32, M, N, 32);  // fp32 store boxes: 32 columns x 32 rows
@@ -684,6 +725,11 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
     }
   }
   return P3TOK_OK;
+}
+
+int tc_linear_ex(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat16* W, int N, const float* bias, int relu,
+                 const TcExtra& ex, __nv_bfloat16* out_bf16, float* out_f32, cudaStream_t s) {
+  return tc_linear(A, M, K, W, N, bias, nullptr, 1, relu, out_bf16, out_f32, nullptr, nullptr, 0, s, &ex);
 }
 
 // ------------------------------------------------------------------------------------------------ first layer

@@ -267,12 +267,12 @@ static inline EncodeTiledFn encode_fn() {
 }
 
 // bf16 row-major [rows, cols] (row pitch = cols*2 bytes), box = 64 cols x box_rows, 128B swizzle, OOB -> 0
-static inline int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int box_rows) {
+static inline int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int box_rows, int64_t ld = 0) {
   P3_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, P3TOK_ERR_UNSUPPORTED, "tensor map: base must be 16-byte aligned");
   EncodeTiledFn fn = encode_fn();
   P3_REQUIRE(fn, P3TOK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)(ld > 0 ? ld : cols) * 2};   // ld: row pitch in elements when the matrix is a column slice
   cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,

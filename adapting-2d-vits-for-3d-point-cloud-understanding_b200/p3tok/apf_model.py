@@ -1,0 +1,196 @@
+"""Drop-ins for the consumer of the APF tokens (SURVEY.md 8f "next" #3): the reference's ViT block stack.
+
+  AttentionLayer / AdapterLayer / APFViTLayer  <- reference src/models/apf_utils.py:106-293
+  ClassificationHead / AdaptPointFormer        <- reference src/models/apf.py:219-373
+
+Same constructor arguments, attribute names and state_dict keys (`blocks.{i}.norm1`, `.attention.qkv`, `.mlp.fc1`,
+`.adapter.down_proj`, `encoder_norm`, `point_encoder.encoder.first_conv.0`, `head.mlp_head.0`, ...), so a reference
+checkpoint loads with strict=True.  The torch submodules are parameter containers; forward runs the sm_100a kernels
+(`p3tok::apf_vit`: LayerNorm -> tcgen05 GEMMs with GELU / residual epilogues -> attention, fp32 residual stream) and is
+eval-mode only (DropPath, dropout = identity; BatchNorm of the head folded).  Differences from the reference
+constructor: no timm / no network here, so `pretrained=True` raises - load a state_dict instead.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from .modules import PointNet
+
+
+class _Mlp(nn.Module):
+    """timm.models.layers.Mlp's parameter layout (fc1 -> GELU -> fc2); container only."""
+
+    def __init__(self, in_features: int, hidden_features: int):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.fc2 = nn.Linear(hidden_features, in_features)
+
+
+class AttentionLayer(nn.Module):
+    """apf_utils.py:106-160 (container; evaluated inside p3tok::apf_vit)."""
+
+    def __init__(self, dim: int, num_heads: int):
+        super().__init__()
+        self.num_heads = num_heads
+        self.scale = (dim // num_heads) ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=True)
+        self.proj = nn.Linear(dim, dim)
+
+
+class AdapterLayer(nn.Module):
+    """apf_utils.py:162-233 (container).  Same initialisation: kaiming down_proj, zero up_proj / biases."""
+
+    def __init__(self, model_dimension: int = 768, bottleneck: int = 64, dropout: float = 0.0):
+        super().__init__()
+        self.n_embd, self.down_size, self.dropout = model_dimension, bottleneck, dropout
+        self.adapter_norm = nn.LayerNorm(self.n_embd)
+        self.scale = nn.Parameter(torch.ones(1))
+        self.down_proj = nn.Linear(self.n_embd, self.down_size)
+        self.relu = nn.ReLU()
+        self.up_proj = nn.Linear(self.down_size, self.n_embd)
+        with torch.no_grad():
+            nn.init.kaiming_uniform_(self.down_proj.weight, a=math.sqrt(5))
+            nn.init.zeros_(self.up_proj.weight)
+            nn.init.zeros_(self.down_proj.bias)
+            nn.init.zeros_(self.up_proj.bias)
+
+
+class APFViTLayer(nn.Module):
+    """apf_utils.py:236-293.  forward(x (B,G,D)) -> (B,G,D); a single layer is a 1-layer stack."""
+
+    def __init__(self, dim: int = 768, num_heads: int = 12, drop_path: float = 0.0, dropout: float = 0.1):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.norm2 = nn.LayerNorm(dim)
+        self.drop_path = nn.Identity()                     # eval mode: DropPath is the identity
+        self.mlp = _Mlp(dim, dim * 4)
+        self.attention = AttentionLayer(dim=dim, num_heads=num_heads)
+        self.adapter = AdapterLayer(model_dimension=dim, dropout=dropout)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return run_blocks([self], x, None)[0]
+
+
+def _layer_params(layer: APFViTLayer, cache: dict) -> List[torch.Tensor]:
+    """The 18 tensors of ops.VIT_LAYER_TENSORS for one layer; bf16 copies of the matrices are cached per parameter
+    version."""
+    src = {
+        "norm1_w": layer.norm1.weight, "norm1_b": layer.norm1.bias, "norm2_w": layer.norm2.weight, "norm2_b": layer.norm2.bias,
+        "adnorm_w": layer.adapter.adapter_norm.weight, "adnorm_b": layer.adapter.adapter_norm.bias,
+        "qkv_w": layer.attention.qkv.weight, "qkv_b": layer.attention.qkv.bias,
+        "proj_w": layer.attention.proj.weight, "proj_b": layer.attention.proj.bias,
+        "fc1_w": layer.mlp.fc1.weight, "fc1_b": layer.mlp.fc1.bias, "fc2_w": layer.mlp.fc2.weight, "fc2_b": layer.mlp.fc2.bias,
+        "down_w": layer.adapter.down_proj.weight, "down_b": layer.adapter.down_proj.bias,
+        "up_w": layer.adapter.up_proj.weight, "up_b": layer.adapter.up_proj.bias,
+    }
+    out = []
+    for name in ops.VIT_LAYER_TENSORS:
+        t = src[name].detach()
+        if name in ops._VIT_BF16:
+            key = (id(layer), name)
+            ver = (t._version, t.data_ptr(), t.device)
+            hit = cache.get(key)
+            if hit is None or hit[0] != ver:
+                hit = (ver, t.to(torch.bfloat16).contiguous())
+                cache[key] = hit
+            t = hit[1]
+        else:
+            t = t.float().contiguous()
+        out.append(t)
+    return out
+
+
+def run_blocks(layers, x: torch.Tensor, final_norm: Optional[nn.LayerNorm], cache: Optional[dict] = None):
+    """(x after the last layer, pooled = max over tokens of final_norm(x) or None)."""
+    layers = list(layers)
+    if any(l.training for l in layers):
+        raise RuntimeError("APFViTLayer: p3tok implements the eval-mode forward only; call .eval() first")
+    cache = {} if cache is None else cache
+    params: List[torch.Tensor] = []
+    scales: List[float] = []
+    for l in layers:
+        params += _layer_params(l, cache)
+        key = (id(l), "scale")
+        sv = l.adapter.scale
+        ver = (sv._version, sv.data_ptr())
+        hit = cache.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, float(sv.detach().float().cpu().item()))   # one host read per parameter version
+            cache[key] = hit
+        scales.append(hit[1])
+    heads = layers[0].attention.num_heads
+    D = x.shape[-1]
+    if final_norm is None:
+        fw, fb = torch.ones(D, device=x.device), torch.zeros(D, device=x.device)
+    else:
+        fw, fb = final_norm.weight.detach().float(), final_norm.bias.detach().float()
+    y, pooled = ops.apf_vit(x.float(), params, scales, heads, fw, fb)
+    return y, (pooled if final_norm is not None else None)
+
+
+class ClassificationHead(nn.Module):
+    """apf.py:219-252.  Linear -> BN -> ReLU -> Dropout -> Linear -> BN -> ReLU -> Dropout -> Linear; eval mode: the
+    BatchNorms fold into the linears (p3tok::linear_f32, fp32 on CUDA cores - a (B,E) problem)."""
+
+    def __init__(self, in_channels: int, num_classes: int):
+        super().__init__()
+        self.mlp_head = nn.Sequential(
+            nn.Linear(in_channels, 512), nn.BatchNorm1d(512), nn.ReLU(inplace=True), nn.Dropout(p=0.4),
+            nn.Linear(512, 256), nn.BatchNorm1d(256), nn.ReLU(inplace=True), nn.Dropout(p=0.4),
+            nn.Linear(256, num_classes))
+
+    def _fold(self, lin: nn.Linear, bn: Optional[nn.BatchNorm1d]):
+        w, b = lin.weight.detach().double(), lin.bias.detach().double()
+        if bn is not None:
+            s = bn.weight.detach().double() / torch.sqrt(bn.running_var.double() + bn.eps)
+            w = w * s[:, None]
+            b = (b - bn.running_mean.double()) * s + bn.bias.detach().double()
+        return w.float().contiguous(), b.float().contiguous()
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.training:
+            raise RuntimeError("ClassificationHead: eval-mode forward only; call .eval() first")
+        m = self.mlp_head
+        x = x.float().contiguous()
+        for lin, bn, relu in ((m[0], m[1], True), (m[4], m[5], True), (m[8], None, False)):
+            w, b = self._fold(lin, bn)
+            x = ops.linear_f32(x, w, b, relu)
+        return x
+
+
+class AdaptPointFormer(nn.Module):
+    """apf.py:254-373.  forward(x (B,N,C)) -> (B,num_classes) logits: PointNet tokenizer -> 12 APFViTLayers ->
+    encoder_norm -> max over tokens -> classification head.  `precision` selects the tokenizer's embed path; the block
+    stack always runs bf16 GEMMs on tcgen05 with an fp32 residual stream."""
+
+    def __init__(self, num_classes: int = 15, embedding_dim: int = 768, vit_name: str = "vit_base_patch16_224",
+                 pretrained: bool = False, npoint: int = 196, nsample: int = 32, in_channels: int = 3,
+                 dropout_rate: float = 0.1, dropout_path_rate: float = 0.1, precision: str = "bf16"):
+        super().__init__()
+        if pretrained:
+            raise RuntimeError("AdaptPointFormer: no timm / network in this build - construct with pretrained=False and "
+                               "load_state_dict() a reference checkpoint (keys are identical)")
+        in_channels = in_channels * 2                      # apf.py:293: [rel || centre] concat
+        depth = 12
+        self.dropout = nn.Dropout(dropout_rate)
+        self.encoder_norm = nn.LayerNorm(embedding_dim)
+        self.point_encoder = PointNet(embedding_dim, npoint, nsample, in_channels, precision=precision)
+        self.head = ClassificationHead(in_channels=embedding_dim, num_classes=num_classes)
+        self.blocks = nn.Sequential(*[APFViTLayer(dim=embedding_dim, num_heads=12, drop_path=0.0, dropout=dropout_rate)
+                                      for _ in range(depth)])
+
+    def features(self, x: torch.Tensor, start_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(B,D) pooled features: everything before the classification head (apf.py:358-366)."""
+        if self.training:
+            raise RuntimeError("AdaptPointFormer: eval-mode forward only; call .eval() first")
+        tok = self.point_encoder(x, start_idx)
+        cache = self.__dict__.setdefault("_vit_cache", {})
+        return run_blocks(self.blocks, tok, self.encoder_norm, cache)[1]
+
+    def forward(self, x: torch.Tensor, start_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self.head(self.features(x, start_idx))

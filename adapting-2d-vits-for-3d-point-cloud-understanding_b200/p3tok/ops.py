@@ -439,3 +439,119 @@ def group_max(x: torch.Tensor, k: int) -> torch.Tensor:
 @group_max.register_fake
 def _(x, k):
     return x.new_empty((x.numel() // (x.shape[-1] * k), x.shape[-1]))
+
+
+# --------------------------------------------------------------------------------------------- ViT block stack
+# ("next" row 3): APFViTLayer stack + encoder_norm + token max of AdaptPointFormer.forward
+VIT_LAYER_TENSORS = ("norm1_w", "norm1_b", "norm2_w", "norm2_b", "adnorm_w", "adnorm_b", "qkv_w", "qkv_b", "proj_w", "proj_b",
+                     "fc1_w", "fc1_b", "fc2_w", "fc2_b", "down_w", "down_b", "up_w", "up_b")
+_VIT_BF16 = {"qkv_w", "proj_w", "fc1_w", "fc2_w", "down_w", "up_w"}
+
+
+@torch.library.custom_op("p3tok::apf_vit", mutates_args=(), device_types="cuda")
+def apf_vit(tokens: torch.Tensor, params: Sequence[torch.Tensor], adapter_scales: Sequence[float], heads: int,
+            final_w: torch.Tensor, final_b: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """tokens (B,G,D) f32 -> (x (B,G,D) f32 after the last block, pooled (B,D) f32 = max_G encoder_norm(x)).
+    params: 18 tensors per layer in VIT_LAYER_TENSORS order (matrices bf16 [out,in], vectors f32)."""
+    nl = len(adapter_scales)
+    if len(params) != nl * len(VIT_LAYER_TENSORS):
+        raise RuntimeError("p3tok::apf_vit: expected 18 tensors per layer")
+    _need_cuda("apf_vit", tokens, final_w, final_b, *params)
+    x = _f32c("apf_vit", tokens).clone()                  # the residual stream is updated in place
+    B, G, D = (int(v) for v in x.shape)
+    fw, fb = _f32c("apf_vit", final_w), _f32c("apf_vit", final_b)
+    keep = []
+    layers = (_lib.VitLayerStruct * max(nl, 1))()
+    H = R = 8
+    for li in range(nl):
+        for j, name in enumerate(VIT_LAYER_TENSORS):
+            t = params[li * len(VIT_LAYER_TENSORS) + j]
+            want = torch.bfloat16 if name in _VIT_BF16 else torch.float32
+            if t.dtype != want:
+                raise RuntimeError(f"p3tok::apf_vit: layer {li} {name} must be {want}, got {t.dtype}")
+            t = t.contiguous()
+            keep.append(t)
+            setattr(layers[li], name, t.data_ptr())
+        layers[li].adapter_scale = float(adapter_scales[li])
+        qkv, fc1, dn = (params[li * 18 + VIT_LAYER_TENSORS.index(n)] for n in ("qkv_w", "fc1_w", "down_w"))
+        if tuple(qkv.shape) != (3 * D, D) or fc1.shape[1] != D or dn.shape[1] != D:
+            raise RuntimeError("p3tok::apf_vit: weight shapes do not match the token width")
+        H, R = int(fc1.shape[0]), int(dn.shape[0])
+    pooled = torch.empty((B, D), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        nbytes = int(_L().p3tok_apf_vit_workspace_bytes(B, G, D, H, R))
+        ws = torch.empty((max(nbytes, 1024),), dtype=torch.uint8, device=x.device)
+        with _timed("apf_vit"):
+            check(_L().p3tok_apf_vit_forward(x.data_ptr(), B, G, D, int(heads), H, R, layers, nl, fw.data_ptr(), fb.data_ptr(),
+                                             pooled.data_ptr(), ws.data_ptr(), nbytes, _stream()), "apf_vit")
+    return x, pooled
+
+
+@apf_vit.register_fake
+def _(tokens, params, adapter_scales, heads, final_w, final_b):
+    return tokens.new_empty(tokens.shape), tokens.new_empty((tokens.shape[0], tokens.shape[2]))
+
+
+@torch.library.custom_op("p3tok::layernorm_bf16", mutates_args=(), device_types="cuda")
+def layernorm_bf16(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float) -> torch.Tensor:
+    """bf16(LayerNorm(x)) over the last dimension of x (M,D) f32 (building block of p3tok::apf_vit)."""
+    _need_cuda("layernorm_bf16", x, w, b)
+    x, w, b = _f32c("layernorm_bf16", x), _f32c("layernorm_bf16", w), _f32c("layernorm_bf16", b)
+    M, D = int(x.shape[0]), int(x.shape[1])
+    out = torch.empty((M, D), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device), _timed("layernorm_bf16"):
+        check(_L().p3tok_layernorm_bf16(x.data_ptr(), M, D, float(eps), w.data_ptr(), b.data_ptr(), out.data_ptr(), None, None,
+                                        None, _stream()), "layernorm_bf16")
+    return out
+
+
+@layernorm_bf16.register_fake
+def _(x, w, b, eps):
+    return x.new_empty(x.shape, dtype=torch.bfloat16)
+
+
+@torch.library.custom_op("p3tok::attention_bf16", mutates_args=(), device_types="cuda")
+def attention_bf16(qkv: torch.Tensor, B: int, G: int, heads: int) -> torch.Tensor:
+    """qkv (B*G, 3D) bf16 in AttentionLayer's column order -> softmax(q k^T / sqrt(hd)) v as (B*G, D) bf16."""
+    _need_cuda("attention_bf16", qkv)
+    if qkv.dtype != torch.bfloat16 or qkv.dim() != 2 or qkv.shape[0] != B * G or qkv.shape[1] % 3:
+        raise RuntimeError("p3tok::attention_bf16: expected (B*G, 3D) bf16")
+    qkv = qkv.contiguous()
+    D = int(qkv.shape[1]) // 3
+    out = torch.empty((B * G, D), dtype=torch.bfloat16, device=qkv.device)
+    with torch.cuda.device(qkv.device), _timed("attention_bf16"):
+        check(_L().p3tok_attention_bf16(qkv.data_ptr(), B, G, D, int(heads), out.data_ptr(), _stream()), "attention_bf16")
+    return out
+
+
+@attention_bf16.register_fake
+def _(qkv, B, G, heads):
+    return qkv.new_empty((qkv.shape[0], qkv.shape[1] // 3))
+
+
+@torch.library.custom_op("p3tok::linear_bf16_ex", mutates_args=(), device_types="cuda")
+def linear_bf16_ex(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, act: int, residual: Optional[torch.Tensor],
+                   res_mul: float, out_scale: float) -> torch.Tensor:
+    """act(a w^T + bias) on tcgen05 with the ViT epilogues: act 0/1/2 = none/ReLU/exact GELU -> bf16 (M,N); with a
+    residual (M,N) f32 the result is res_mul * residual + out_scale * (a w^T + bias) as f32."""
+    _need_cuda("linear_bf16_ex", a, w, bias, residual)
+    if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
+        raise RuntimeError("p3tok::linear_bf16_ex: bf16 operands expected")
+    a, w, bias = a.contiguous(), w.contiguous(), _f32c("linear_bf16_ex", bias)
+    M, K, N = int(a.shape[0]), int(a.shape[1]), int(w.shape[0])
+    with torch.cuda.device(a.device), _timed("linear_bf16_ex"):
+        if residual is None:
+            out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+            check(_L().p3tok_linear_bf16_ex(a.data_ptr(), M, K, w.data_ptr(), N, bias.data_ptr(), int(act), None, 0.0, 1.0,
+                                            out.data_ptr(), None, _stream()), "linear_bf16_ex")
+        else:
+            res = _f32c("linear_bf16_ex", residual)
+            out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+            check(_L().p3tok_linear_bf16_ex(a.data_ptr(), M, K, w.data_ptr(), N, bias.data_ptr(), int(act), res.data_ptr(),
+                                            float(res_mul), float(out_scale), None, out.data_ptr(), _stream()), "linear_bf16_ex")
+    return out
+
+
+@linear_bf16_ex.register_fake
+def _(a, w, bias, act, residual, res_mul, out_scale):
+    return a.new_empty((a.shape[0], w.shape[0]), dtype=torch.bfloat16 if residual is None else torch.float32)

@@ -178,6 +178,49 @@ def token_head_state(width: int, embed_dim: int, seed: int = 0) -> Dict[str, np.
     return sd
 
 
+def apf_vit_state(dim: int, depth: int, num_classes: int = 15, seed: int = 0, bottleneck: int = 64) -> Dict[str, np.ndarray]:
+    """state_dict (numpy) of the token consumer of the reference's AdaptPointFormer (src/models/apf.py:296-317): `blocks.{i}.*`
+    (APFViTLayer, src/models/apf_utils.py:236-266), `encoder_norm.*`, `head.mlp_head.*`.  Unlike the reference's initialisation
+    the adapter's up-projection and scale are non-trivial, so every term of the layer is exercised."""
+    ws = _WeightStream(seed + 104729)
+    sd: Dict[str, np.ndarray] = {}
+
+    def lin(name, cout, cin, scale=1.0):
+        bound = scale / math.sqrt(cin)
+        sd[name + ".weight"] = ws.uniform((cout, cin), -bound, bound)
+        sd[name + ".bias"] = ws.uniform((cout,), -bound, bound)
+
+    def ln(name):
+        sd[name + ".weight"] = ws.uniform((dim,), 0.5, 1.5)
+        sd[name + ".bias"] = ws.uniform((dim,), -0.1, 0.1)
+
+    for i in range(depth):
+        b = f"blocks.{i}."
+        ln(b + "norm1")
+        ln(b + "norm2")
+        lin(b + "mlp.fc1", 4 * dim, dim)
+        lin(b + "mlp.fc2", dim, 4 * dim)
+        lin(b + "attention.qkv", 3 * dim, dim, 2.0)
+        lin(b + "attention.proj", dim, dim)
+        ln(b + "adapter.adapter_norm")
+        sd[b + "adapter.scale"] = ws.uniform((1,), 0.5, 0.9)
+        lin(b + "adapter.down_proj", bottleneck, dim)
+        lin(b + "adapter.up_proj", dim, bottleneck)
+    ln("encoder_norm")
+    lin("head.mlp_head.0", 512, dim)
+    _bn(ws, sd, "head.mlp_head.1", 512)
+    lin("head.mlp_head.4", 256, 512)
+    _bn(ws, sd, "head.mlp_head.5", 256)
+    lin("head.mlp_head.8", num_classes, 256)
+    return sd
+
+
+def vit_tokens(B: int, G: int, D: int, seed: int) -> np.ndarray:
+    """Synthetic (B,G,D) token batch in [-1,1) for the ViT block-stack cases."""
+    u = uniform01(seed, B * G * D, 17).reshape(B, G, D)
+    return ((u - 0.5) * 2.0).astype(np.float32)
+
+
 def to_torch_state(sd: Dict[str, np.ndarray]):
     import torch
     return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}

@@ -243,6 +243,61 @@ def token_head(sd: Dict[str, np.ndarray], tokens: np.ndarray, centres: np.ndarra
     return feats, pos
 
 
+def _erf(x):
+    try:
+        from scipy.special import erf
+    except Exception:                                   # pragma: no cover
+        erf = np.vectorize(__import__("math").erf)
+    return erf(x)
+
+
+def _layer_norm(sd, name, x, eps=1e-5):
+    """nn.LayerNorm over the last axis: biased variance, eps inside the root."""
+    mu = x.mean(-1, keepdims=True)
+    var = ((x - mu) ** 2).mean(-1, keepdims=True)
+    return (x - mu) / np.sqrt(var + eps) * np.asarray(sd[name + ".weight"], np.float64) + np.asarray(sd[name + ".bias"], np.float64)
+
+
+def apf_vit_layer(sd: Dict[str, np.ndarray], prefix: str, x: np.ndarray, heads: int) -> np.ndarray:
+    """One APFViTLayer in eval mode, float64 (src/models/apf_utils.py:268-293): x (B,G,D) -> (B,G,D).
+    attention = AttentionLayer.forward (apf_utils.py:133-160), adapter = AdapterLayer.forward (197-233; returns
+    scale*up + x), mlp = fc1 -> exact GELU -> fc2; out = mlp(norm2(x)) + adapter(x) + x (line 292)."""
+    f = lambda k: np.asarray(sd[prefix + k], np.float64)
+    B, G, D = x.shape
+    hd = D // heads
+    a = _layer_norm(sd, prefix + "norm1", x)
+    qkv = (a @ f("attention.qkv.weight").T + f("attention.qkv.bias")).reshape(B, G, 3, heads, hd).transpose(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    att = (q @ k.transpose(0, 1, 3, 2)) * hd ** -0.5
+    att = np.exp(att - att.max(-1, keepdims=True))
+    att = att / att.sum(-1, keepdims=True)
+    o = (att @ v).transpose(0, 2, 1, 3).reshape(B, G, D)
+    x = x + (o @ f("attention.proj.weight").T + f("attention.proj.bias"))
+    an = _layer_norm(sd, prefix + "adapter.adapter_norm", x)
+    down = np.maximum(an @ f("adapter.down_proj.weight").T + f("adapter.down_proj.bias"), 0.0)
+    adapt = (down @ f("adapter.up_proj.weight").T + f("adapter.up_proj.bias")) * float(np.asarray(sd[prefix + "adapter.scale"]).reshape(-1)[0]) + x
+    h = _layer_norm(sd, prefix + "norm2", x) @ f("mlp.fc1.weight").T + f("mlp.fc1.bias")
+    h = 0.5 * h * (1.0 + _erf(h / np.sqrt(2.0)))
+    return (h @ f("mlp.fc2.weight").T + f("mlp.fc2.bias")) + adapt + x
+
+
+def apf_vit(sd: Dict[str, np.ndarray], tokens: np.ndarray, depth: int, heads: int):
+    """Block loop + encoder_norm + max over tokens + classification head of AdaptPointFormer.forward
+    (src/models/apf.py:361-371), eval mode, float64.  Returns (x (B,G,D), pooled (B,D), logits (B,classes))."""
+    x = tokens.astype(np.float64)
+    for i in range(depth):
+        x = apf_vit_layer(sd, f"blocks.{i}.", x, heads)
+    pooled = _layer_norm(sd, "encoder_norm", x).max(1)
+    f = lambda k: np.asarray(sd[k], np.float64)
+    h = pooled
+    for lin, bn in (("head.mlp_head.0", "head.mlp_head.1"), ("head.mlp_head.4", "head.mlp_head.5")):
+        h = h @ f(lin + ".weight").T + f(lin + ".bias")
+        h = (h - f(bn + ".running_mean")) / np.sqrt(f(bn + ".running_var") + BN_EPS) * f(bn + ".weight") + f(bn + ".bias")
+        h = np.maximum(h, 0.0)
+    logits = h @ f("head.mlp_head.8.weight").T + f("head.mlp_head.8.bias")
+    return x, pooled, logits
+
+
 # ----------------------------------------------------------------------------- comparison helpers
 
 def knn_tie_equivalent(idx_a: np.ndarray, idx_b: np.ndarray, dist_full: np.ndarray,

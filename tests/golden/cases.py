@@ -28,3 +28,10 @@ HEAD_CASES = {
     # Pix4Point token head (proj + pos_embed + cls concat): name: dict(B, G, W, E, seed)
     "p4p_head": dict(B=2, G=16, W=64, E=96, seed=41),
 }
+
+VIT_CASES = {
+    # APF ViT block stack + encoder_norm + max + head on synthetic tokens: name: dict(B, G, D, heads, depth, classes, seed)
+    "vit_small": dict(B=2, G=50, D=64, heads=2, depth=2, classes=15, seed=51),      # head dim 32, ragged G
+    "vit_hd64": dict(B=1, G=70, D=128, heads=2, depth=3, classes=15, seed=52),      # head dim 64
+    "vit_s12": dict(B=1, G=128, D=384, heads=12, depth=12, classes=15, seed=53),    # ViT-S geometry of BASELINE config 2
+}

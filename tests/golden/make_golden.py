@@ -195,6 +195,35 @@ def head_case(name, c):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), feats=feats.numpy(), pos=pemb.numpy())
 
 
+def vit_case(ref, name, c):
+    """The reference's AdaptPointFormer cannot be constructed here (its constructor downloads timm weights,
+    src/models/apf.py:319-327), so its forward tail (apf.py:361-371) is evaluated on the reference's own modules:
+    apf_utils.APFViTLayer x depth, nn.LayerNorm, max over tokens, apf.ClassificationHead."""
+    import torch.nn as nn
+    sd = synth.apf_vit_state(c["D"], c["depth"], c["classes"], c["seed"])
+    tsd = synth.to_torch_state(sd)
+    blocks = nn.Sequential(*[ref.apf_utils.APFViTLayer(dim=c["D"], num_heads=c["heads"], drop_path=0.0, dropout=0.1)
+                             for _ in range(c["depth"])]).eval()
+    norm = nn.LayerNorm(c["D"]).eval()
+    head = ref.apf.ClassificationHead(c["D"], c["classes"]).eval()
+    blocks.load_state_dict({k[len("blocks."):]: v for k, v in tsd.items() if k.startswith("blocks.")})
+    norm.load_state_dict({k[len("encoder_norm."):]: v for k, v in tsd.items() if k.startswith("encoder_norm.")})
+    head.load_state_dict({k[len("head."):]: v for k, v in tsd.items() if k.startswith("head.")})
+    tok = synth.vit_tokens(c["B"], c["G"], c["D"], c["seed"])
+    with torch.no_grad():
+        x = torch.from_numpy(tok)
+        for i in range(len(blocks)):
+            x = blocks[i](x)
+        pooled = norm(x).max(-2)[0]
+        logits = head(pooled)
+    ox, op, ol = oracle.apf_vit(sd, tok, c["depth"], c["heads"])
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+    e = (rel(ox, x.numpy()), rel(op, pooled.numpy()), rel(ol, logits.numpy()))
+    print(f"{name}: oracle vs reference blocks: x {e[0]:.2e}, pooled {e[1]:.2e}, logits {e[2]:.2e}")
+    assert max(e) < 2e-5, name
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), x=x.numpy(), pooled=pooled.numpy(), logits=logits.numpy())
+
+
 def main():
     assert ref_loader.available(), "reference tree not present"
     ref = ref_loader.load()
@@ -207,6 +236,8 @@ def main():
         p4p_case(ref, name, c)
     for name, c in cases.HEAD_CASES.items():
         head_case(name, c)
+    for name, c in cases.VIT_CASES.items():
+        vit_case(ref, name, c)
 
 
 if __name__ == "__main__":

@@ -75,3 +75,38 @@ def folded_forward(mlp, rows, k):
     h = torch.relu(h @ mlp.w_mid_f.double().T + gb.repeat_interleave(k, dim=0))
     o = (h @ mlp.w_out.double().T + mlp.b_out.double()).view(ng, k, -1).max(dim=1)[0]
     return torch.relu(o) if mlp.out_relu else o
+
+
+def vit_bf16_emulation(sd, tokens, depth, heads):
+    """The ViT block stack's arithmetic (csrc/vit.cu) spelled in torch on any device: bf16 weights and stored
+    activations (LayerNorm outputs, qkv, softmax probabilities, attention output, adapter bottleneck, GELU output),
+    fp32 accumulation, fp32 residual stream.  Returns (x (B,G,D), pooled (B,D)) float32."""
+    import torch
+    import torch.nn.functional as F
+
+    def q(t):
+        return t.bfloat16().float()
+
+    T = lambda k: torch.as_tensor(sd[k]).float().to(tokens.device)
+    mm = lambda a, w: (a.double() @ q(w).double().T).float()
+    x = tokens.float()
+    B, G, D = x.shape
+    hd = D // heads
+    for i in range(depth):
+        p = f"blocks.{i}."
+        a = q(F.layer_norm(x, (D,), T(p + "norm1.weight"), T(p + "norm1.bias"), 1e-5))
+        qkv = q(mm(a, T(p + "attention.qkv.weight")) + T(p + "attention.qkv.bias"))
+        qkv = qkv.reshape(B, G, 3, heads, hd).permute(2, 0, 3, 1, 4)
+        s = (qkv[0].double() @ qkv[1].double().transpose(-2, -1)).float() * hd ** -0.5
+        e = torch.exp(s - s.max(-1, keepdim=True)[0])
+        o = (q(e).double() @ qkv[2].double()).float() / e.sum(-1, keepdim=True)     # P rounded to bf16, row sum in fp32
+        o = q(o.transpose(1, 2).reshape(B, G, D))
+        x = x + (mm(o, T(p + "attention.proj.weight")) + T(p + "attention.proj.bias"))
+        n2 = q(F.layer_norm(x, (D,), T(p + "norm2.weight"), T(p + "norm2.bias"), 1e-5))
+        an = q(F.layer_norm(x, (D,), T(p + "adapter.adapter_norm.weight"), T(p + "adapter.adapter_norm.bias"), 1e-5))
+        dn = q(torch.relu(mm(an, T(p + "adapter.down_proj.weight")) + T(p + "adapter.down_proj.bias")))
+        x = 2.0 * x + float(T(p + "adapter.scale").reshape(-1)[0]) * (mm(dn, T(p + "adapter.up_proj.weight")) + T(p + "adapter.up_proj.bias"))
+        h = q(F.gelu(mm(n2, T(p + "mlp.fc1.weight")) + T(p + "mlp.fc1.bias")))
+        x = x + (mm(h, T(p + "mlp.fc2.weight")) + T(p + "mlp.fc2.bias"))
+    pooled = F.layer_norm(x, (D,), T("encoder_norm.weight"), T("encoder_norm.bias"), 1e-5).max(1)[0]
+    return x, pooled

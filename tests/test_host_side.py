@@ -33,13 +33,17 @@ def test_library_exports_every_declared_symbol(built):
 def test_struct_layouts_match_header(tmp_path, built):
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "p3tok.h"\nint main(){printf("%zu %zu %zu %zu\\n",'
-                   'sizeof(p3tok_mlp),sizeof(p3tok_rows),offsetof(p3tok_mlp,w_pre),offsetof(p3tok_rows,x));return 0;}')
+                   'sizeof(p3tok_mlp),sizeof(p3tok_rows),offsetof(p3tok_mlp,w_pre),offsetof(p3tok_rows,x));'
+                   'printf("%zu %zu %zu\\n",sizeof(p3tok_vit_layer),offsetof(p3tok_vit_layer,up_b),'
+                   'offsetof(p3tok_vit_layer,adapter_scale));return 0;}')
     exe = tmp_path / "sz"
     inc = os.path.join(os.path.dirname(_lib.HEADER_PATH))
     subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True)
-    a, b, c, d = (int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split())
+    a, b, c, d, e, f, g = (int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split())
     assert ctypes.sizeof(_lib.MlpStruct) == a and ctypes.sizeof(_lib.RowsStruct) == b
     assert _lib.MlpStruct.w_pre.offset == c and _lib.RowsStruct.x.offset == d
+    assert ctypes.sizeof(_lib.VitLayerStruct) == e and _lib.VitLayerStruct.up_b.offset == f
+    assert _lib.VitLayerStruct.adapter_scale.offset == g
 
 
 def test_fold_apf_matches_oracle():
@@ -110,3 +114,27 @@ def test_product_never_imports_oracle():
         if f.endswith(".py"):
             src = open(os.path.join(pkg, f)).read()
             assert "oracle" not in src.replace("# oracle", ""), f
+
+
+def test_apf_model_state_dict_keys():
+    """AdaptPointFormer drop-in: parameter names of the reference (src/models/apf.py:296-317, apf_utils.py:236-266)."""
+    from p3tok.apf_model import AdaptPointFormer
+    m = AdaptPointFormer(num_classes=15, embedding_dim=64, npoint=8, nsample=4, in_channels=3)
+    keys = set(m.state_dict())
+    want = set(synth.apf_vit_state(64, 12, 15)) | {"point_encoder.encoder." + k for k in synth.apf_encoder_state(64, 6)}
+    assert keys == want, (sorted(keys - want)[:5], sorted(want - keys)[:5])
+    m.load_state_dict(synth.to_torch_state(synth.apf_vit_state(64, 12, 15)), strict=False)
+    with pytest.raises(RuntimeError):
+        m.train()(torch.zeros(1, 16, 3))
+    with pytest.raises(RuntimeError):
+        AdaptPointFormer(pretrained=True)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+def test_apf_model_keys_match_reference_modules():
+    from p3tok.apf_model import APFViTLayer, ClassificationHead
+    ref = ref_loader.load()
+    assert set(APFViTLayer(64, 2).state_dict()) == set(ref.apf_utils.APFViTLayer(dim=64, num_heads=2).state_dict())
+    assert set(ClassificationHead(64, 15).state_dict()) == set(ref.apf.ClassificationHead(64, 15).state_dict())
+    sd = ref.apf_utils.APFViTLayer(dim=64, num_heads=2).state_dict()
+    APFViTLayer(64, 2).load_state_dict(sd, strict=True)

@@ -97,3 +97,16 @@ def test_token_head_cases(golden_dir, name):
     assert np.abs(feats - g["feats"]).max() <= 2e-6 * np.abs(g["feats"]).max()
     assert np.abs(pos - g["pos"]).max() <= 2e-6 * np.abs(g["pos"]).max()
     assert np.array_equal(feats[:, 0], np.broadcast_to(sd["cls_token"].reshape(1, -1), (c["B"], c["E"])).astype(np.float64))
+
+
+@pytest.mark.parametrize("name", list(cases.VIT_CASES))
+def test_vit_cases(golden_dir, name):
+    """oracle.apf_vit against the reference's own APFViTLayer / LayerNorm / ClassificationHead outputs."""
+    c = cases.VIT_CASES[name]
+    g = _load(golden_dir, name)
+    sd = synth.apf_vit_state(c["D"], c["depth"], c["classes"], c["seed"])
+    tok = synth.vit_tokens(c["B"], c["G"], c["D"], c["seed"])
+    x, pooled, logits = oracle.apf_vit(sd, tok, c["depth"], c["heads"])
+    for mine, key in ((x, "x"), (pooled, "pooled"), (logits, "logits")):
+        ref = g[key].astype(np.float64)
+        assert np.abs(mine - ref).max() <= 2e-5 * np.abs(ref).max(), key
