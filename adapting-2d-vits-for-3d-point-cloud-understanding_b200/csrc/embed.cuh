@@ -20,7 +20,9 @@ int patch_embed_bf16(const p3tok_rows* rows, const p3tok_mlp* mlp, void* ws, int
 
 // extra epilogue of tc_linear for the ViT blocks (vit.cu): GELU, fp32 residual stream, column-slice outputs
 struct TcExtra {
-  int gelu = 0;                    // exact GELU after the bias
+  int gelu = 0;                    // exact GELU after the bias ...
+  int gelu_cols = 0;               // ... on columns < gelu_cols (0 = all); `relu` then applies to the remaining columns
+  int bn = 0;                      // N-tile width override (multiple of 64, <= 256); 0 = least padding
   const float* residual = nullptr; // out_f32 = res_mul * residual + out_scale * value
   float res_mul = 1.f, out_scale = 1.f;
   int64_t ldc = 0;                 // row pitch of out_bf16 in elements (0 = N)

@@ -85,7 +85,8 @@ struct TcParams {
   float* out_max;          // [ceil(M/32), N] max over each 32 consecutive rows, or null
   __nv_bfloat16* out_max_bf16;
   int max_relu;            // apply ReLU to the max (out_relu of the block)
-  int gelu;                // exact (erf) GELU after bias (ViT mlp.fc1, embed.cuh TcExtra)
+  int gelu, gelu_cols;     // exact (erf) GELU after the bias on columns < gelu_cols (ViT mlp.fc1; ReLU, if set, applies to the
+                           // columns from gelu_cols on: the adapter bottleneck rides in the same GEMM, embed.cuh TcExtra)
   const float* residual;   // [M,N] f32 or null: out_f32 = res_mul * residual + out_scale * value (may alias out_f32:
   float res_mul, out_scale; // every element is read by the thread that produces it, before its store box leaves)
   int stages, stage_bytes; // TMA->MMA ring depth and bytes per stage (A tile 16 KB + this CTA's part of the weight tile)
@@ -113,18 +114,35 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {   // explicit shared-
   return v;
 }
 
-// exact GELU x * Phi(x) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32 rounding level): one
-// MUFU.RCP + one MUFU.EX2 + 9 FMA-pipe instructions instead of erff()'s branchy ~25
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float e = exp2f(-1.4426950408889634f * z * z);
-  const float erf_abs = fmaf(-poly * t, e, 1.f);           // erf(|x|/sqrt 2)
-  return 0.5f * x + 0.5f * fabsf(x) * erf_abs;             // x/2 * (1 + sign(x) erf(|x|/sqrt 2))
+// exact (erf) GELU without the erf: with q(t) = log2(erfc(t / sqrt 2)), t = |x|,
+//   gelu(x) = x Phi(x) = max(x, 0) - |x|/2 * 2^q(|x|)
+// (x < 0: x/2 erfc(|x|/sqrt 2); x > 0: x - x/2 erfc(x/sqrt 2)) - no cancellation in either tail.  q is smooth; its
+// degree-8 least-squares Chebyshev fit on [0, 10] (fitted and checked against scipy in fp32 arithmetic: |error| <=
+// 2.4e-6 absolute, <= 2.2e-5 relative where |gelu| > 1e-6 - a hundredth of a bf16 rounding) costs 8 FMAs + ONE MUFU
+// (EX2): the epilogue of the fc1 GEMM is MUFU- and issue-bound (erff(): ~25 instructions, the A&S 7.1.26 form 2 MUFUs),
+// and |x| beyond 10 is clamped (2^q(10) < 2e-23).  Two elements per call: the Horner chain runs as packed FFMA2.
+__device__ __forceinline__ void fma2(float& o0, float& o1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; fma.rn.f32x2 rd, ra, rb, rc; "
+      "mov.b64 {%0,%1}, rd; }"
+      : "=f"(o0), "=f"(o1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const float t0 = fminf(fabsf(x0), 10.f), t1 = fminf(fabsf(x1), 10.f);
+  float r0 = 6.171978522e-08f, r1 = 6.171978522e-08f;
+  fma2(r0, r1, r0, r1, t0, t1, -3.191675725e-06f, -3.191675725e-06f);
+  fma2(r0, r1, r0, r1, t0, t1, 7.265022928e-05f, 7.265022928e-05f);
+  fma2(r0, r1, r0, r1, t0, t1, -9.681803689e-04f, -9.681803689e-04f);
+  fma2(r0, r1, r0, r1, t0, t1, 8.529751658e-03f, 8.529751658e-03f);
+  fma2(r0, r1, r0, r1, t0, t1, -5.378560319e-02f, -5.378560319e-02f);
+  fma2(r0, r1, r0, r1, t0, t1, -4.588579945e-01f, -4.588579945e-01f);
+  fma2(r0, r1, r0, r1, t0, t1, -1.150993949e+00f, -1.150993949e+00f);
+  fma2(r0, r1, r0, r1, t0, t1, -3.042118848e-05f, -3.042118848e-05f);
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(r0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(r1));
+  x0 = fmaf(-0.5f * fabsf(x0), e0, fmaxf(x0, 0.f));
+  x1 = fmaf(-0.5f * fabsf(x1), e1, fmaxf(x1, 0.f));
 }
 
 // `sbias` is staged zero-padded to a multiple of 64 columns, so the 32 columns starting at n0 are always readable.
@@ -174,11 +192,13 @@ __device__ __forceinline__ void epilogue_half(const TcParams& p, const float* sb
     }
   }
   // bf16-only outputs take their ReLU from the conversion instruction (F2FP.RELU) instead of 32 FMNMX
-  const bool relu_in_pack = p.relu && !p.out_f32 && !p.out_max && !p.out_max_bf16;
-  epilogue_affine(v, p, sbias, gb, n0, p.relu && !relu_in_pack);
-  if (p.gelu) {
+  const bool gelu_here = p.gelu && n0 < p.gelu_cols;        // warp-uniform (gelu_cols is a multiple of 32)
+  const bool relu_here = p.relu && !gelu_here;
+  const bool relu_in_pack = relu_here && !p.out_f32 && !p.out_max && !p.out_max_bf16;
+  epilogue_affine(v, p, sbias, gb, n0, relu_here && !relu_in_pack);
+  if (gelu_here) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    for (int j = 0; j < 32; j += 2) gelu_erf2(v[j], v[j + 1]);
   }
   if (p.residual) {   // fp32 residual stream of the ViT blocks: 128 contiguous bytes per lane (whole sectors)
     const int nmax = p.N - 4;
@@ -597,6 +617,10 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
   if (M == 0) return P3TOK_OK;
   TcParams p;
   p.M = (int)M; p.N = N; p.K = K; p.BN = pick_bn(N);
+  if (ex && ex->bn > 0) {
+    P3_REQUIRE(ex->bn % 64 == 0 && ex->bn <= 256, P3TOK_ERR_INVALID, "tc_linear: tile width %d", ex->bn);
+    p.BN = ex->bn;
+  }
   // P3TOK_TC_CLUSTER: 1 = one CTA per tile; 2/4 = TMA multicast of the weight tile across a cluster;
   // P3TOK_TC_PAIR=1 (default): CTA pairs with cta_group::2 MMAs (M = 256 per pair, weight tile split)
   static int want_cl = 0, want_pair = -1;
@@ -613,6 +637,8 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
   p.bias = bias; p.gbias = gbias; p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1; p.relu = relu;
   p.out_bf16 = out_bf16; p.out_f32 = out_f32; p.out_max = out_max; p.out_max_bf16 = out_max_bf16; p.max_relu = max_relu;
   p.gelu = ex ? ex->gelu : 0;
+  p.gelu_cols = (ex && ex->gelu_cols > 0) ? ex->gelu_cols : N;
+  P3_REQUIRE(p.gelu_cols % 32 == 0 || p.gelu_cols == N, P3TOK_ERR_UNSUPPORTED, "tc_linear: gelu_cols must be a multiple of 32");
   p.residual = ex ? ex->residual : nullptr;
   p.res_mul = ex ? ex->res_mul : 0.f;
   p.out_scale = ex ? ex->out_scale : 1.f;

@@ -3,22 +3,26 @@
 // Replaces the block loop, encoder_norm and token max of AdaptPointFormer.forward (reference src/models/apf.py:361-366)
 // with APFViTLayer = attention + bottleneck adapter + MLP (src/models/apf_utils.py:106-293), eval mode.
 //
-// Data flow per layer (M = B*G token rows, fp32 residual stream x updated in place, bf16 activations in the workspace):
-//   ln_rows_kernel        a  = bf16(norm1(x))                                           warp per row
-//   tc_linear             qkv = a Wqkv^T + b                   (tcgen05, bf16 out)      embed_tc.cu
-//   attention_kernel      o  = softmax(q k^T / sqrt(hd)) v     per (cloud, head, 64 query rows)
-//   tc_linear             x  = x + (o Wproj^T + b)             (fp32 residual epilogue)
-//   ln_rows_kernel        n2 = bf16(norm2(x)),  an = bf16(adapter_norm(x))              one pass, shared statistics
-//   tc_linear             dn = relu(an Wdown^T + b)
-//   tc_linear             x  = 2 x + scale (dn Wup^T + b)      (adapter output + the layer's own residual, as the
-//                                                               reference adds them: apf_utils.py:233 and :292)
-//   tc_linear             h  = gelu(n2 Wfc1^T + b)             (exact GELU in the epilogue)
-//   tc_linear             x  = x + (h Wfc2^T + b)
+// At BASELINE config 2 (B = 128 clouds x G = 128 tokens = 16384 rows, D = 384) every GEMM of a layer is 7-14 us of tensor
+// work, so a layer is bound by the NUMBER of kernels (each has ~10 us of launch / pipeline fill / drain) and by the GEMM
+// epilogues, not by the MMAs.  The host therefore folds a layer (p3tok/apf_model.py::fold_vit_layer) into four GEMMs:
+//   LayerNorm affines move into the weights that consume them (W' = W diag(gamma), b' = b + W beta), so norm2 and
+//   adapter_norm (same statistics, different affine) become ONE affine-free normalisation feeding ONE GEMM
+//   [fc1 ; down_proj] (N = H + R) whose epilogue applies GELU to the first H columns and ReLU to the last R, and
+//   [fc2 | scale * up_proj] (K = H + R) consumes that matrix whole: x_out = 2 x + [h | dn] [Wfc2 | s Wup]^T + b.
+// Data flow per layer (M = B*G rows, fp32 residual stream x updated in place, bf16 activations in the workspace):
+//   ln_rows_kernel        xh = bf16((x - mean) / std)
+//   tc_linear             qkv = xh Wqkv'^T + b'                       (tcgen05, bf16 out)      embed_tc.cu
+//   attention_kernel      o  = softmax(q k^T / sqrt(hd)) v            per (cloud, head, 128 query rows)
+//   tc_linear             x  = x + (o Wproj^T + b)                    (fp32 residual epilogue)          apf_utils.py:279-283
+//   ln_rows_kernel        xh = bf16((x - mean) / std)
+//   tc_linear             hd = [gelu | relu](xh [Wfc1' ; Wdown']^T + b')                                :217-225, :288
+//   tc_linear             x  = 2 x + (hd [Wfc2 | s Wup]^T + b)        (adapter's own "+ x" and the layer's, :233 and :292)
 // then norm_max_kernel: pooled[b] = max over tokens of encoder_norm(x[b]).
 //
-// The GEMMs (95 % of the FLOPs) run on the tcgen05 kernel of embed_tc.cu; attention (sequence 128-196, head dim 32/64:
-// 5 % of the FLOPs, exp-bound) is a flash-style kernel on warp-level bf16 mma with fp32 online softmax, K and V^T of
-// one (cloud, head) staged in shared memory per 64-key block.
+// Attention (sequence 128-196, head dim 32/64: 5 % of the FLOPs, bound by the exp / element-wise work on the scores)
+// is a flash-style kernel on warp-level bf16 mma (ldmatrix fragments, fp32 online softmax in the log2 domain with the
+// scale folded into one FFMA per score).
 #include <math.h>
 
 #include "embed.cuh"
@@ -30,11 +34,9 @@ namespace p3tok {
 // variance - what torch computes up to rounding), biased variance, eps inside the square root.
 constexpr int LN_MAX_V4 = 8;
 
-template <bool DUAL>
 __global__ void __launch_bounds__(256)
-ln_rows_kernel(const float* __restrict__ x, int64_t M, int D, float eps, const float* __restrict__ w1,
-               const float* __restrict__ b1, __nv_bfloat16* __restrict__ o1, const float* __restrict__ w2,
-               const float* __restrict__ b2, __nv_bfloat16* __restrict__ o2) {
+ln_rows_kernel(const float* __restrict__ x, int64_t M, int D, float eps, const float* __restrict__ w,
+               const float* __restrict__ bvec, __nv_bfloat16* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -67,39 +69,26 @@ ln_rows_kernel(const float* __restrict__ x, int64_t M, int D, float eps, const f
   for (int i = 0; i < LN_MAX_V4; ++i) {
     const int j = lane + 32 * i;
     if (j < nv) {
-      const float a = (v[i].x - mean) * rstd, b = (v[i].y - mean) * rstd, c = (v[i].z - mean) * rstd,
-                  d = (v[i].w - mean) * rstd;
-      {
-        const float4 w = reinterpret_cast<const float4*>(w1)[j], bb = reinterpret_cast<const float4*>(b1)[j];
-        __nv_bfloat162 lo = __floats2bfloat162_rn(fmaf(a, w.x, bb.x), fmaf(b, w.y, bb.y));
-        __nv_bfloat162 hi = __floats2bfloat162_rn(fmaf(c, w.z, bb.z), fmaf(d, w.w, bb.w));
-        uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-        reinterpret_cast<uint2*>(o1 + row * D)[j] = pk;
+      float a = (v[i].x - mean) * rstd, b = (v[i].y - mean) * rstd, c = (v[i].z - mean) * rstd, d = (v[i].w - mean) * rstd;
+      if (w) {   // warp-uniform
+        const float4 ww = reinterpret_cast<const float4*>(w)[j], bb = reinterpret_cast<const float4*>(bvec)[j];
+        a = fmaf(a, ww.x, bb.x); b = fmaf(b, ww.y, bb.y); c = fmaf(c, ww.z, bb.z); d = fmaf(d, ww.w, bb.w);
       }
-      if (DUAL) {
-        const float4 w = reinterpret_cast<const float4*>(w2)[j], bb = reinterpret_cast<const float4*>(b2)[j];
-        __nv_bfloat162 lo = __floats2bfloat162_rn(fmaf(a, w.x, bb.x), fmaf(b, w.y, bb.y));
-        __nv_bfloat162 hi = __floats2bfloat162_rn(fmaf(c, w.z, bb.z), fmaf(d, w.w, bb.w));
-        uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-        reinterpret_cast<uint2*>(o2 + row * D)[j] = pk;
-      }
+      __nv_bfloat162 lo = __floats2bfloat162_rn(a, b);
+      __nv_bfloat162 hi = __floats2bfloat162_rn(c, d);
+      reinterpret_cast<uint2*>(out + row * D)[j] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
     }
   }
 }
 
-static int layernorm_bf16(const float* x, int64_t M, int D, float eps, const float* w1, const float* b1, __nv_bfloat16* o1,
-                          const float* w2, const float* b2, __nv_bfloat16* o2, cudaStream_t s) {
+// w == nullptr: plain normalisation (the affine lives in the consuming GEMM's weights)
+static int layernorm_bf16(const float* x, int64_t M, int D, float eps, const float* w, const float* b, __nv_bfloat16* out,
+                          cudaStream_t s) {
   P3_REQUIRE(D % 4 == 0 && D > 0 && D <= 128 * LN_MAX_V4, P3TOK_ERR_UNSUPPORTED, "layernorm: D=%d must be a multiple of 4, <= %d", D,
              128 * LN_MAX_V4);
-  P3_REQUIRE(x && w1 && b1 && o1, P3TOK_ERR_INVALID, "layernorm: null pointer");
+  P3_REQUIRE(x && out && (!w == !b), P3TOK_ERR_INVALID, "layernorm: null pointer");
   if (M == 0) return P3TOK_OK;
-  const unsigned blocks = (unsigned)((M + 7) / 8);
-  if (o2) {
-    P3_REQUIRE(w2 && b2, P3TOK_ERR_INVALID, "layernorm: second affine missing");
-    ln_rows_kernel<true><<<blocks, 256, 0, s>>>(x, M, D, eps, w1, b1, o1, w2, b2, o2);
-  } else {
-    ln_rows_kernel<false><<<blocks, 256, 0, s>>>(x, M, D, eps, w1, b1, o1, nullptr, nullptr, nullptr);
-  }
+  ln_rows_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(x, M, D, eps, w, b, out);
   P3_LAUNCH_CHECK("ln_rows_kernel");
   return P3TOK_OK;
 }
@@ -177,84 +166,101 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-constexpr int AT_Q = 64, AT_KV = 64;   // query rows per CTA (4 warps x 16), keys per block
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr int AT_Q = 128, AT_KV = 64, AT_THREADS = 256;   // query rows per CTA (8 warps x 16), keys per block
 
 // qkv (B*G, 3D) bf16: column which*D + head*HD + d (AttentionLayer's reshape(B,N,3,heads,hd), apf_utils.py:143).
 // out (B*G, D) bf16: column head*HD + d ((attn @ v).transpose(1,2).reshape(B,N,C), apf_utils.py:155).
-// grid (ceil(G/64), heads, B), 128 threads.  Lane (g = lane/4, t = lane%4) of a warp owns query rows g and g+8 of
-// the warp's 16: the m16n8k16 accumulator layout, so row maxima / sums need only the two quad shuffles.
+// grid (ceil(G/128), heads, B).  Q, K, V tiles are staged row-major in padded shared memory by coalesced 16-byte copies;
+// fragments come from ldmatrix (V through .trans: the [key][d] tile is already the k-major B operand of P V).
+// Lane (g = lane/4, t = lane%4) of a warp owns query rows g and g+8 of the warp's 16 (the m16n8k16 accumulator layout),
+// so row maxima / sums need only the two quad shuffles.  Scores stay raw; p = 2^(s*c - m*c) with c = log2(e)/sqrt(hd).
 template <int HD>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(AT_THREADS)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int G, int D, float scale_log2e) {
   constexpr int KS = HD / 16;          // k steps of q k^T
   constexpr int DT = HD / 8;           // n tiles of the output
-  constexpr int KP = HD + 8;           // padded row of sK (conflict-free fragment loads)
-  constexpr int VP = AT_KV + 8;        // padded row of sVt
-  __shared__ __align__(16) __nv_bfloat16 sK[AT_KV * KP];
-  __shared__ __align__(16) __nv_bfloat16 sVt[HD * VP];
+  constexpr int RP = HD + 8;           // padded row (16-byte aligned, conflict-free ldmatrix)
+  constexpr int CPR = HD / 8;          // 16-byte chunks per row
+  __shared__ __align__(16) __nv_bfloat16 sQ[AT_Q * RP];
+  __shared__ __align__(16) __nv_bfloat16 sK[AT_KV * RP];
+  __shared__ __align__(16) __nv_bfloat16 sV[AT_KV * RP];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int head = blockIdx.y, b = blockIdx.z;
-  const int q0 = blockIdx.x * AT_Q + warp * 16;
+  const int qb = blockIdx.x * AT_Q;
+  const int q0 = qb + warp * 16;
   const size_t ld = (size_t)3 * D;
   const __nv_bfloat16* base = qkv + (size_t)b * G * ld + (size_t)head * HD;
 
-  // Q fragments straight from global memory (rows past G are clamped; their results are never stored)
-  uint32_t qa[KS][4];
-  {
-    const int r0 = min(q0 + g, G - 1), r1 = min(q0 + g + 8, G - 1);
-    const __nv_bfloat16* p0 = base + (size_t)r0 * ld;
-    const __nv_bfloat16* p1 = base + (size_t)r1 * ld;
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      qa[ks][0] = *reinterpret_cast<const uint32_t*>(p0 + ks * 16 + 2 * t);
-      qa[ks][1] = *reinterpret_cast<const uint32_t*>(p1 + ks * 16 + 2 * t);
-      qa[ks][2] = *reinterpret_cast<const uint32_t*>(p0 + ks * 16 + 8 + 2 * t);
-      qa[ks][3] = *reinterpret_cast<const uint32_t*>(p1 + ks * 16 + 8 + 2 * t);
-    }
+  for (int c = tid; c < AT_Q * CPR; c += AT_THREADS) {
+    const int r = c / CPR, ch = c % CPR;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (qb + r < G) v = *reinterpret_cast<const uint4*>(base + (size_t)(qb + r) * ld + ch * 8);
+    *reinterpret_cast<uint4*>(&sQ[r * RP + ch * 8]) = v;
   }
+  __syncthreads();
+  uint32_t qa[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)   // lanes 0-15: rows 0-15 at column ks*16; lanes 16-31: the same rows at column ks*16 + 8
+    ldsm_x4(qa[ks], (uint32_t)__cvta_generic_to_shared(&sQ[(warp * 16 + (lane & 15)) * RP + ks * 16 + (lane >> 4) * 8]));
+  const bool active = q0 < G;   // warps whose 16 rows lie past G only help with the copies
   float o[DT][4];
 #pragma unroll
   for (int i = 0; i < DT; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // running maxima of the RAW scores, running sums
 
   for (int kv0 = 0; kv0 < G; kv0 += AT_KV) {
     __syncthreads();   // previous block's fragments have been read
-    for (int c = tid; c < AT_KV * (HD / 8); c += 128) {
-      const int r = c / (HD / 8), ch = c % (HD / 8);
+    for (int c = tid; c < AT_KV * CPR; c += AT_THREADS) {
+      const int r = c / CPR, ch = c % CPR;
       uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
       if (kv0 + r < G) {
         const __nv_bfloat16* rowp = base + (size_t)(kv0 + r) * ld + ch * 8;
         kk = *reinterpret_cast<const uint4*>(rowp + D);
         vv = *reinterpret_cast<const uint4*>(rowp + 2 * D);
       }
-      *reinterpret_cast<uint4*>(&sK[r * KP + ch * 8]) = kk;
-      const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sVt[(ch * 8 + i) * VP + r] = ve[i];
+      *reinterpret_cast<uint4*>(&sK[r * RP + ch * 8]) = kk;
+      *reinterpret_cast<uint4*>(&sV[r * RP + ch * 8]) = vv;
     }
     __syncthreads();
+    if (!active) continue;
 
     float sc[AT_KV / 8][4];
 #pragma unroll
     for (int nt = 0; nt < AT_KV / 8; ++nt) {
       sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sK[(nt * 8 + g) * KP + ks * 16 + 2 * t]);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sK[(nt * 8 + g) * KP + ks * 16 + 8 + 2 * t]);
-        mma_bf16_16816(sc[nt], qa[ks], b0, b1);
+      for (int k2 = 0; k2 < KS; k2 += 2) {   // one x4: keys nt*8..+7, d chunks (k2*16, +8, +16, +24) = b0,b1 of two k steps
+        uint32_t kb[4];
+        ldsm_x4(kb, (uint32_t)__cvta_generic_to_shared(&sK[(nt * 8 + (lane & 7)) * RP + k2 * 16 + (lane >> 3) * 8]));
+        mma_bf16_16816(sc[nt], qa[k2], kb[0], kb[1]);
+        mma_bf16_16816(sc[nt], qa[k2 + 1], kb[2], kb[3]);
       }
     }
-    // scale (log2 domain), mask keys past G, block row maxima
+    if (kv0 + AT_KV > G) {   // ragged last block: keys past G never win the max and contribute 2^-inf = 0
+#pragma unroll
+      for (int nt = 0; nt < AT_KV / 8; ++nt) {
+        const int col = kv0 + nt * 8 + 2 * t;
+        if (col >= G) sc[nt][0] = sc[nt][2] = -INFINITY;
+        if (col + 1 >= G) sc[nt][1] = sc[nt][3] = -INFINITY;
+      }
+    }
     float bm0 = -INFINITY, bm1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < AT_KV / 8; ++nt) {
-      const int col = kv0 + nt * 8 + 2 * t;
-      const bool ok0 = col < G, ok1 = col + 1 < G;
-      sc[nt][0] = ok0 ? sc[nt][0] * scale_log2e : -INFINITY;
-      sc[nt][1] = ok1 ? sc[nt][1] * scale_log2e : -INFINITY;
-      sc[nt][2] = ok0 ? sc[nt][2] * scale_log2e : -INFINITY;
-      sc[nt][3] = ok1 ? sc[nt][3] * scale_log2e : -INFINITY;
       bm0 = fmaxf(bm0, fmaxf(sc[nt][0], sc[nt][1]));
       bm1 = fmaxf(bm1, fmaxf(sc[nt][2], sc[nt][3]));
     }
@@ -263,15 +269,16 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
     bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
     const float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);   // finite: every block holds at least one valid key
-    const float c0 = exp2f(m0 - n0), c1 = exp2f(m1 - n1);   // 0 on the first block (m = -inf)
+    const float c0 = ex2f((m0 - n0) * scale_log2e), c1 = ex2f((m1 - n1) * scale_log2e);   // 0 on the first block (m = -inf)
     m0 = n0; m1 = n1;
+    const float ms0 = -n0 * scale_log2e, ms1 = -n1 * scale_log2e;
     l0 *= c0; l1 *= c1;
 #pragma unroll
     for (int i = 0; i < DT; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
 #pragma unroll
     for (int nt = 0; nt < AT_KV / 8; ++nt) {
-      sc[nt][0] = exp2f(sc[nt][0] - n0); sc[nt][1] = exp2f(sc[nt][1] - n0);
-      sc[nt][2] = exp2f(sc[nt][2] - n1); sc[nt][3] = exp2f(sc[nt][3] - n1);
+      sc[nt][0] = ex2f(fmaf(sc[nt][0], scale_log2e, ms0)); sc[nt][1] = ex2f(fmaf(sc[nt][1], scale_log2e, ms0));
+      sc[nt][2] = ex2f(fmaf(sc[nt][2], scale_log2e, ms1)); sc[nt][3] = ex2f(fmaf(sc[nt][3], scale_log2e, ms1));
       l0 += sc[nt][0] + sc[nt][1];
       l1 += sc[nt][2] + sc[nt][3];
     }
@@ -284,13 +291,16 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
       pa[2] = pack2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
       pa[3] = pack2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
 #pragma unroll
-      for (int dt = 0; dt < DT; ++dt) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sVt[(dt * 8 + g) * VP + kk * 16 + 2 * t]);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sVt[(dt * 8 + g) * VP + kk * 16 + 8 + 2 * t]);
-        mma_bf16_16816(o[dt], pa, b0, b1);
+      for (int dt = 0; dt < DT; dt += 2) {   // one x4.trans: keys kk*16 (+8), d tiles dt and dt+1 -> b0,b1 of each
+        uint32_t vb[4];
+        ldsm_x4_t(vb, (uint32_t)__cvta_generic_to_shared(
+                          &sV[(kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * RP + (dt + (lane >> 4)) * 8]));
+        mma_bf16_16816(o[dt], pa, vb[0], vb[1]);
+        mma_bf16_16816(o[dt + 1], pa, vb[2], vb[3]);
       }
     }
   }
+  if (!active) return;
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
   l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
@@ -315,42 +325,47 @@ static int attention_bf16(const __nv_bfloat16* qkv, int64_t B, int64_t G, int D,
   if (B * G == 0) return P3TOK_OK;
   const float scale_log2e = (float)((1.0 / sqrt((double)hd)) * 1.4426950408889634);
   dim3 grid((unsigned)((G + AT_Q - 1) / AT_Q), (unsigned)heads, (unsigned)B);
-  if (hd == 32) attention_kernel<32><<<grid, 128, 0, s>>>(qkv, out, (int)G, D, scale_log2e);
-  else attention_kernel<64><<<grid, 128, 0, s>>>(qkv, out, (int)G, D, scale_log2e);
+  if (hd == 32) attention_kernel<32><<<grid, AT_THREADS, 0, s>>>(qkv, out, (int)G, D, scale_log2e);
+  else attention_kernel<64><<<grid, AT_THREADS, 0, s>>>(qkv, out, (int)G, D, scale_log2e);
   P3_LAUNCH_CHECK("attention_kernel");
   return P3TOK_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ orchestration
 struct VitWs {
-  int64_t a, a2, qkv, h, dn, total;
+  int64_t a, qkv, h, total;
 };
 static VitWs vit_layout(int64_t M, int64_t D, int64_t H, int64_t R) {
   VitWs w;
   int64_t off = 0;
   auto take = [&](int64_t bytes) { int64_t o = off; off += align_up(bytes, 1024); return o; };
-  w.a = take(M * D * 2);
-  w.a2 = take(M * D * 2);
+  w.a = take(M * D * 2);            // normalised rows / attention output
   w.qkv = take(M * 3 * D * 2);
-  w.h = take(M * H * 2);
-  w.dn = take(M * R * 2);
+  w.h = take(M * (H + R) * 2);      // [gelu(fc1) | relu(down)]
   w.total = off + 1024;
   return w;
 }
 int64_t apf_vit_workspace(int64_t B, int64_t G, int64_t D, int64_t H, int64_t R) { return vit_layout(B * G, D, H, R).total; }
 
 // bf16-output GEMM whose N may exceed what one tc_linear launch stages (2048 columns): column slices of the weight
-// matrix write column slices of the output (ViT-B: 3D = 2304, H = 3072)
-static int linear_wide(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat16* W, int N, const float* bias, int relu, int gelu,
-                       __nv_bfloat16* out, cudaStream_t s) {
+// matrix write column slices of the output (ViT-B: 3D = 2304, H + R = 3136).  Slices are multiples of 256 columns, so a
+// GELU/ReLU boundary (gelu_cols, a multiple of 64) falls inside at most one slice and is passed relative to it.
+static int linear_wide(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat16* W, int N, const float* bias, int relu,
+                       int gelu_cols, __nv_bfloat16* out, cudaStream_t s) {
   const int parts = (N + 2047) / 2048;
-  int per = ((N + parts - 1) / parts + 63) / 64 * 64;
+  const int per = parts == 1 ? N : ((N + parts - 1) / parts + 255) / 256 * 256;
   for (int n0 = 0; n0 < N; n0 += per) {
     const int n = N - n0 < per ? N - n0 : per;
     TcExtra ex;
-    ex.gelu = gelu;
     ex.ldc = N;
-    int rc = tc_linear_ex(A, M, K, W + (size_t)n0 * K, n, bias + n0, relu, ex, out + n0, nullptr, s);
+    int do_relu = relu;
+    if (gelu_cols > n0) {             // this slice starts with GELU columns
+      ex.gelu = 1;
+      ex.gelu_cols = gelu_cols - n0 < n ? gelu_cols - n0 : n;
+      if (ex.gelu_cols == n) do_relu = 0;
+    }
+    if (n > 1024) ex.bn = 256;        // wide layers: full-rate 256-column tiles, a partly empty last tile costs less than narrow ones
+    int rc = tc_linear_ex(A, M, K, W + (size_t)n0 * K, n, bias + n0, do_relu, ex, out + n0, nullptr, s);
     if (rc) return rc;
   }
   return P3TOK_OK;
@@ -365,10 +380,10 @@ extern "C" int64_t p3tok_apf_vit_workspace_bytes(int64_t B, int64_t G, int64_t D
   return apf_vit_workspace(B, G, D, H, R);
 }
 
-extern "C" int p3tok_layernorm_bf16(const float* x, int64_t M, int64_t D, float eps, const float* w1, const float* b1, void* out1,
-                                    const float* w2, const float* b2, void* out2, void* stream) {
+extern "C" int p3tok_layernorm_bf16(const float* x, int64_t M, int64_t D, float eps, const float* w, const float* b, void* out,
+                                    void* stream) {
   P3_REQUIRE(M >= 0 && D > 0, P3TOK_ERR_INVALID, "layernorm: bad shape");
-  return layernorm_bf16(x, M, (int)D, eps, w1, b1, (__nv_bfloat16*)out1, w2, b2, (__nv_bfloat16*)out2, as_stream(stream));
+  return layernorm_bf16(x, M, (int)D, eps, w, b, (__nv_bfloat16*)out, as_stream(stream));
 }
 
 extern "C" int p3tok_attention_bf16(const void* qkv, int64_t B, int64_t G, int64_t D, int64_t heads, void* out, void* stream) {
@@ -377,19 +392,22 @@ extern "C" int p3tok_attention_bf16(const void* qkv, int64_t B, int64_t G, int64
 }
 
 extern "C" int p3tok_linear_bf16_ex(const void* A, int64_t M, int64_t K, const void* W, int64_t N, const float* bias, int act,
-                                    const float* residual, float res_mul, float out_scale, void* out_bf16, float* out_f32,
-                                    void* stream) {
+                                    int64_t gelu_cols, const float* residual, float res_mul, float out_scale, void* out_bf16,
+                                    float* out_f32, void* stream) {
   P3_REQUIRE(M >= 0 && K > 0 && N > 0 && K < (1 << 24) && N < (1 << 24), P3TOK_ERR_INVALID, "linear_bf16_ex: bad shape");
-  P3_REQUIRE(act >= 0 && act <= 2, P3TOK_ERR_INVALID, "linear_bf16_ex: act %d", act);
+  P3_REQUIRE(act >= 0 && act <= 3, P3TOK_ERR_INVALID, "linear_bf16_ex: act %d", act);
   if (M == 0) return P3TOK_OK;
   P3_REQUIRE(A && W && (out_bf16 || out_f32), P3TOK_ERR_INVALID, "linear_bf16_ex: null pointer");
   P3_REQUIRE(!residual || out_f32, P3TOK_ERR_INVALID, "linear_bf16_ex: a residual needs the f32 output");
+  P3_REQUIRE(act != 3 || (gelu_cols > 0 && gelu_cols < N && gelu_cols % 64 == 0), P3TOK_ERR_INVALID,
+             "linear_bf16_ex: act 3 needs 0 < gelu_cols < N, a multiple of 64");
   TcExtra ex;
-  ex.gelu = act == 2;
+  ex.gelu = act >= 2;
+  ex.gelu_cols = act == 3 ? (int)gelu_cols : 0;
   ex.residual = residual;
   ex.res_mul = res_mul;
   ex.out_scale = residual ? out_scale : 1.f;
-  return tc_linear_ex((const __nv_bfloat16*)A, M, (int)K, (const __nv_bfloat16*)W, (int)N, bias, act == 1, ex,
+  return tc_linear_ex((const __nv_bfloat16*)A, M, (int)K, (const __nv_bfloat16*)W, (int)N, bias, act == 1 || act == 3, ex,
                       (__nv_bfloat16*)out_bf16, out_f32, as_stream(stream));
 }
 
@@ -398,7 +416,7 @@ extern "C" int p3tok_apf_vit_forward(float* x, int64_t B, int64_t G, int64_t D, 
                                      const float* final_norm_b, float* pooled_out, void* workspace, int64_t workspace_bytes,
                                      void* stream) {
   P3_REQUIRE(B >= 0 && G >= 0 && D > 0 && H > 0 && R > 0 && heads > 0 && n_layers >= 0, P3TOK_ERR_INVALID, "apf_vit: bad shape");
-  P3_REQUIRE(D % 8 == 0 && H % 8 == 0 && R % 8 == 0, P3TOK_ERR_UNSUPPORTED, "apf_vit: D, H, R must be multiples of 8");
+  P3_REQUIRE(D % 8 == 0 && H % 64 == 0 && R % 8 == 0, P3TOK_ERR_UNSUPPORTED, "apf_vit: D, R must be multiples of 8, H of 64");
   P3_REQUIRE(D <= 128 * LN_MAX_V4, P3TOK_ERR_UNSUPPORTED, "apf_vit: D=%lld > %d", (long long)D, 128 * LN_MAX_V4);
   P3_REQUIRE(D % heads == 0 && (D / heads == 32 || D / heads == 64), P3TOK_ERR_UNSUPPORTED,
              "apf_vit: head dim %lld (supported: 32, 64)", (long long)(D / heads));
@@ -413,19 +431,17 @@ extern "C" int p3tok_apf_vit_forward(float* x, int64_t B, int64_t G, int64_t D, 
   cudaStream_t s = as_stream(stream);
   uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
   __nv_bfloat16* a = reinterpret_cast<__nv_bfloat16*>(ws + L.a);
-  __nv_bfloat16* a2 = reinterpret_cast<__nv_bfloat16*>(ws + L.a2);
   __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(ws + L.qkv);
   __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(ws + L.h);
-  __nv_bfloat16* dn = reinterpret_cast<__nv_bfloat16*>(ws + L.dn);
   const float eps = 1e-5f;
+  const int HR = (int)(H + R);
   int rc;
   for (int64_t li = 0; li < n_layers; ++li) {
     const p3tok_vit_layer& w = layers[li];
-    P3_REQUIRE(w.norm1_w && w.norm1_b && w.norm2_w && w.norm2_b && w.adnorm_w && w.adnorm_b && w.qkv_w && w.qkv_b && w.proj_w &&
-                   w.proj_b && w.fc1_w && w.fc1_b && w.fc2_w && w.fc2_b && w.down_w && w.down_b && w.up_w && w.up_b,
-               P3TOK_ERR_INVALID, "apf_vit: layer %lld has a null parameter", (long long)li);
+    P3_REQUIRE(w.qkv_w && w.qkv_b && w.proj_w && w.proj_b && w.fc1d_w && w.fc1d_b && w.fc2u_w && w.fc2u_b, P3TOK_ERR_INVALID,
+               "apf_vit: layer %lld has a null parameter", (long long)li);
     // attention branch: x += proj(attention(norm1(x)))                                    (apf_utils.py:279-283)
-    if ((rc = layernorm_bf16(x, M, (int)D, eps, w.norm1_w, w.norm1_b, a, nullptr, nullptr, nullptr, s))) return rc;
+    if ((rc = layernorm_bf16(x, M, (int)D, eps, nullptr, nullptr, a, s))) return rc;
     if ((rc = linear_wide(a, M, (int)D, (const __nv_bfloat16*)w.qkv_w, (int)(3 * D), w.qkv_b, 0, 0, qkv, s))) return rc;
     if ((rc = attention_bf16(qkv, B, G, (int)D, (int)heads, a, s))) return rc;
     {
@@ -434,21 +450,12 @@ extern "C" int p3tok_apf_vit_forward(float* x, int64_t B, int64_t G, int64_t D, 
       if ((rc = tc_linear_ex(a, M, (int)D, (const __nv_bfloat16*)w.proj_w, (int)D, w.proj_b, 0, ex, nullptr, x, s))) return rc;
     }
     // adapter + MLP on the same x: out = mlp(norm2(x)) + [scale * up(relu(down(adapter_norm(x)))) + x] + x   (:284-292)
-    if ((rc = layernorm_bf16(x, M, (int)D, eps, w.norm2_w, w.norm2_b, a, w.adnorm_w, w.adnorm_b, a2, s))) return rc;
+    if ((rc = layernorm_bf16(x, M, (int)D, eps, nullptr, nullptr, a, s))) return rc;
+    if ((rc = linear_wide(a, M, (int)D, (const __nv_bfloat16*)w.fc1d_w, HR, w.fc1d_b, 1, (int)H, h, s))) return rc;
     {
       TcExtra ex;
-      if ((rc = tc_linear_ex(a2, M, (int)D, (const __nv_bfloat16*)w.down_w, (int)R, w.down_b, 1, ex, dn, nullptr, s))) return rc;
-    }
-    {
-      TcExtra ex;
-      ex.residual = x; ex.res_mul = 2.f; ex.out_scale = w.adapter_scale;
-      if ((rc = tc_linear_ex(dn, M, (int)R, (const __nv_bfloat16*)w.up_w, (int)D, w.up_b, 0, ex, nullptr, x, s))) return rc;
-    }
-    if ((rc = linear_wide(a, M, (int)D, (const __nv_bfloat16*)w.fc1_w, (int)H, w.fc1_b, 0, 1, h, s))) return rc;
-    {
-      TcExtra ex;
-      ex.residual = x; ex.res_mul = 1.f; ex.out_scale = 1.f;
-      if ((rc = tc_linear_ex(h, M, (int)H, (const __nv_bfloat16*)w.fc2_w, (int)D, w.fc2_b, 0, ex, nullptr, x, s))) return rc;
+      ex.residual = x; ex.res_mul = 2.f; ex.out_scale = 1.f;
+      if ((rc = tc_linear_ex(h, M, HR, (const __nv_bfloat16*)w.fc2u_w, (int)D, w.fc2u_b, 0, ex, nullptr, x, s))) return rc;
     }
   }
   if (pooled_out) {

@@ -43,11 +43,8 @@ class RowsStruct(ctypes.Structure):
 
 
 class VitLayerStruct(ctypes.Structure):
-    """struct p3tok_vit_layer (include/p3tok.h)."""
-    _fields_ = [(n, _vp) for n in (
-        "norm1_w", "norm1_b", "norm2_w", "norm2_b", "adnorm_w", "adnorm_b", "qkv_w", "qkv_b", "proj_w", "proj_b",
-        "fc1_w", "fc1_b", "fc2_w", "fc2_b", "down_w", "down_b", "up_w", "up_b")] + [
-        ("adapter_scale", ctypes.c_float), ("pad_", _i32)]
+    """struct p3tok_vit_layer (include/p3tok.h): one APFViTLayer folded by apf_model.fold_vit_layer."""
+    _fields_ = [(n, _vp) for n in ("qkv_w", "qkv_b", "proj_w", "proj_b", "fc1d_w", "fc1d_b", "fc2u_w", "fc2u_b")]
 
 
 _f32 = ctypes.c_float
@@ -73,9 +70,9 @@ _SIGNATURES = {
     "p3tok_apf_vit_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64, _i64]),
     "p3tok_apf_vit_forward": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, ctypes.POINTER(VitLayerStruct), _i64, _vp, _vp,
                                      _vp, _vp, _i64, _vp]),
-    "p3tok_layernorm_bf16": (_int, [_vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "p3tok_layernorm_bf16": (_int, [_vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp]),
     "p3tok_attention_bf16": (_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
-    "p3tok_linear_bf16_ex": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _int, _vp, _f32, _f32, _vp, _vp, _vp]),
+    "p3tok_linear_bf16_ex": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _int, _i64, _vp, _f32, _f32, _vp, _vp, _vp]),
 }
 
 

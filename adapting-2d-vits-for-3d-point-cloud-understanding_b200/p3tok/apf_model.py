@@ -76,33 +76,42 @@ class APFViTLayer(nn.Module):
         return run_blocks([self], x, None)[0]
 
 
-def _layer_params(layer: APFViTLayer, cache: dict) -> List[torch.Tensor]:
-    """The 18 tensors of ops.VIT_LAYER_TENSORS for one layer; bf16 copies of the matrices are cached per parameter
-    version."""
-    src = {
-        "norm1_w": layer.norm1.weight, "norm1_b": layer.norm1.bias, "norm2_w": layer.norm2.weight, "norm2_b": layer.norm2.bias,
-        "adnorm_w": layer.adapter.adapter_norm.weight, "adnorm_b": layer.adapter.adapter_norm.bias,
-        "qkv_w": layer.attention.qkv.weight, "qkv_b": layer.attention.qkv.bias,
-        "proj_w": layer.attention.proj.weight, "proj_b": layer.attention.proj.bias,
-        "fc1_w": layer.mlp.fc1.weight, "fc1_b": layer.mlp.fc1.bias, "fc2_w": layer.mlp.fc2.weight, "fc2_b": layer.mlp.fc2.bias,
-        "down_w": layer.adapter.down_proj.weight, "down_b": layer.adapter.down_proj.bias,
-        "up_w": layer.adapter.up_proj.weight, "up_b": layer.adapter.up_proj.bias,
-    }
-    out = []
-    for name in ops.VIT_LAYER_TENSORS:
-        t = src[name].detach()
-        if name in ops._VIT_BF16:
-            key = (id(layer), name)
-            ver = (t._version, t.data_ptr(), t.device)
-            hit = cache.get(key)
-            if hit is None or hit[0] != ver:
-                hit = (ver, t.to(torch.bfloat16).contiguous())
-                cache[key] = hit
-            t = hit[1]
-        else:
-            t = t.float().contiguous()
-        out.append(t)
+def fold_vit_layer(layer: "APFViTLayer") -> List[torch.Tensor]:
+    """One APFViTLayer folded into the four GEMMs of struct p3tok_vit_layer (include/p3tok.h), float64 algebra, then bf16
+    matrices / f32 biases in ops.VIT_LAYER_TENSORS order:
+      LayerNorm affines move into the weights that consume the normalised rows (W diag(g), b + W beta);
+      norm2 and adapter_norm share their statistics, so [fc1 ; down_proj] is one GEMM on one normalised matrix;
+      [fc2 | scale * up_proj] consumes [gelu(fc1) | relu(down)] whole (apf_utils.py:217-233, 284-292)."""
+    d = lambda t: t.detach().double()
+    g1, b1 = d(layer.norm1.weight), d(layer.norm1.bias)
+    g2, b2 = d(layer.norm2.weight), d(layer.norm2.bias)
+    ga, ba = d(layer.adapter.adapter_norm.weight), d(layer.adapter.adapter_norm.bias)
+    sc = d(layer.adapter.scale).reshape(())
+    qw, qb = d(layer.attention.qkv.weight), d(layer.attention.qkv.bias)
+    f1w, f1b = d(layer.mlp.fc1.weight), d(layer.mlp.fc1.bias)
+    dw, db = d(layer.adapter.down_proj.weight), d(layer.adapter.down_proj.bias)
+    f2w, f2b = d(layer.mlp.fc2.weight), d(layer.mlp.fc2.bias)
+    uw, ub = d(layer.adapter.up_proj.weight), d(layer.adapter.up_proj.bias)
+    mats = [
+        (qw * g1[None, :], qb + qw @ b1),
+        (d(layer.attention.proj.weight), d(layer.attention.proj.bias)),
+        (torch.cat([f1w * g2[None, :], dw * ga[None, :]], 0), torch.cat([f1b + f1w @ b2, db + dw @ ba], 0)),
+        (torch.cat([f2w, sc * uw], 1), f2b + sc * ub),
+    ]
+    out: List[torch.Tensor] = []
+    for w, b in mats:
+        out += [w.to(torch.bfloat16).contiguous(), b.float().contiguous()]
     return out
+
+
+def _layer_params(layer: "APFViTLayer", cache: dict) -> List[torch.Tensor]:
+    """fold_vit_layer, cached per parameter version (no host synchronisation on the steady-state path)."""
+    ver = tuple((t._version, t.data_ptr()) for t in layer.parameters())
+    hit = cache.get(id(layer))
+    if hit is None or hit[0] != ver:
+        hit = (ver, fold_vit_layer(layer))
+        cache[id(layer)] = hit
+    return hit[1]
 
 
 def run_blocks(layers, x: torch.Tensor, final_norm: Optional[nn.LayerNorm], cache: Optional[dict] = None):
@@ -112,24 +121,15 @@ def run_blocks(layers, x: torch.Tensor, final_norm: Optional[nn.LayerNorm], cach
         raise RuntimeError("APFViTLayer: p3tok implements the eval-mode forward only; call .eval() first")
     cache = {} if cache is None else cache
     params: List[torch.Tensor] = []
-    scales: List[float] = []
     for l in layers:
         params += _layer_params(l, cache)
-        key = (id(l), "scale")
-        sv = l.adapter.scale
-        ver = (sv._version, sv.data_ptr())
-        hit = cache.get(key)
-        if hit is None or hit[0] != ver:
-            hit = (ver, float(sv.detach().float().cpu().item()))   # one host read per parameter version
-            cache[key] = hit
-        scales.append(hit[1])
     heads = layers[0].attention.num_heads
     D = x.shape[-1]
     if final_norm is None:
         fw, fb = torch.ones(D, device=x.device), torch.zeros(D, device=x.device)
     else:
         fw, fb = final_norm.weight.detach().float(), final_norm.bias.detach().float()
-    y, pooled = ops.apf_vit(x.float(), params, scales, heads, fw, fb)
+    y, pooled = ops.apf_vit(x.float(), params, heads, layers[0].adapter.down_size, fw, fb)
     return y, (pooled if final_norm is not None else None)
 
 

@@ -443,40 +443,44 @@ def _(x, k):
 
 # --------------------------------------------------------------------------------------------- ViT block stack
 # ("next" row 3): APFViTLayer stack + encoder_norm + token max of AdaptPointFormer.forward
-VIT_LAYER_TENSORS = ("norm1_w", "norm1_b", "norm2_w", "norm2_b", "adnorm_w", "adnorm_b", "qkv_w", "qkv_b", "proj_w", "proj_b",
-                     "fc1_w", "fc1_b", "fc2_w", "fc2_b", "down_w", "down_b", "up_w", "up_b")
-_VIT_BF16 = {"qkv_w", "proj_w", "fc1_w", "fc2_w", "down_w", "up_w"}
+VIT_LAYER_TENSORS = ("qkv_w", "qkv_b", "proj_w", "proj_b", "fc1d_w", "fc1d_b", "fc2u_w", "fc2u_b")   # struct p3tok_vit_layer
+_NVT = len(VIT_LAYER_TENSORS)
 
 
 @torch.library.custom_op("p3tok::apf_vit", mutates_args=(), device_types="cuda")
-def apf_vit(tokens: torch.Tensor, params: Sequence[torch.Tensor], adapter_scales: Sequence[float], heads: int,
-            final_w: torch.Tensor, final_b: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+def apf_vit(tokens: torch.Tensor, params: Sequence[torch.Tensor], heads: int, bottleneck: int, final_w: torch.Tensor,
+            final_b: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """tokens (B,G,D) f32 -> (x (B,G,D) f32 after the last block, pooled (B,D) f32 = max_G encoder_norm(x)).
-    params: 18 tensors per layer in VIT_LAYER_TENSORS order (matrices bf16 [out,in], vectors f32)."""
-    nl = len(adapter_scales)
-    if len(params) != nl * len(VIT_LAYER_TENSORS):
-        raise RuntimeError("p3tok::apf_vit: expected 18 tensors per layer")
+    params: 8 tensors per layer in VIT_LAYER_TENSORS order - the layer as folded by apf_model.fold_vit_layer
+    (matrices bf16 [out,in], biases f32)."""
+    if len(params) % _NVT:
+        raise RuntimeError(f"p3tok::apf_vit: expected {_NVT} tensors per layer")
+    nl = len(params) // _NVT
     _need_cuda("apf_vit", tokens, final_w, final_b, *params)
     x = _f32c("apf_vit", tokens).clone()                  # the residual stream is updated in place
     B, G, D = (int(v) for v in x.shape)
     fw, fb = _f32c("apf_vit", final_w), _f32c("apf_vit", final_b)
     keep = []
     layers = (_lib.VitLayerStruct * max(nl, 1))()
-    H = R = 8
+    R = int(bottleneck)
+    H = 64
     for li in range(nl):
         for j, name in enumerate(VIT_LAYER_TENSORS):
-            t = params[li * len(VIT_LAYER_TENSORS) + j]
-            want = torch.bfloat16 if name in _VIT_BF16 else torch.float32
+            t = params[li * _NVT + j]
+            want = torch.bfloat16 if name.endswith("_w") else torch.float32
             if t.dtype != want:
                 raise RuntimeError(f"p3tok::apf_vit: layer {li} {name} must be {want}, got {t.dtype}")
             t = t.contiguous()
             keep.append(t)
             setattr(layers[li], name, t.data_ptr())
-        layers[li].adapter_scale = float(adapter_scales[li])
-        qkv, fc1, dn = (params[li * 18 + VIT_LAYER_TENSORS.index(n)] for n in ("qkv_w", "fc1_w", "down_w"))
-        if tuple(qkv.shape) != (3 * D, D) or fc1.shape[1] != D or dn.shape[1] != D:
+        qkv, proj, fc1d, fc2u = (params[li * _NVT + j] for j in (0, 2, 4, 6))
+        HR = int(fc1d.shape[0])
+        if tuple(qkv.shape) != (3 * D, D) or tuple(proj.shape) != (D, D) or fc1d.shape[1] != D or tuple(fc2u.shape) != (D, HR):
             raise RuntimeError("p3tok::apf_vit: weight shapes do not match the token width")
-        H, R = int(fc1.shape[0]), int(dn.shape[0])
+        H = HR - R                                        # [fc1 ; down_proj]: the adapter bottleneck is the tail
+        for j in (1, 3, 5, 7):
+            if params[li * _NVT + j].numel() != params[li * _NVT + j - 1].shape[0]:
+                raise RuntimeError("p3tok::apf_vit: bias length does not match its matrix")
     pooled = torch.empty((B, D), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         nbytes = int(_L().p3tok_apf_vit_workspace_bytes(B, G, D, H, R))
@@ -488,20 +492,22 @@ def apf_vit(tokens: torch.Tensor, params: Sequence[torch.Tensor], adapter_scales
 
 
 @apf_vit.register_fake
-def _(tokens, params, adapter_scales, heads, final_w, final_b):
+def _(tokens, params, heads, bottleneck, final_w, final_b):
     return tokens.new_empty(tokens.shape), tokens.new_empty((tokens.shape[0], tokens.shape[2]))
 
 
 @torch.library.custom_op("p3tok::layernorm_bf16", mutates_args=(), device_types="cuda")
-def layernorm_bf16(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float) -> torch.Tensor:
-    """bf16(LayerNorm(x)) over the last dimension of x (M,D) f32 (building block of p3tok::apf_vit)."""
+def layernorm_bf16(x: torch.Tensor, w: Optional[torch.Tensor], b: Optional[torch.Tensor], eps: float) -> torch.Tensor:
+    """bf16(LayerNorm(x)) over the last dimension of x (M,D) f32; w = b = None: normalisation without affine."""
     _need_cuda("layernorm_bf16", x, w, b)
-    x, w, b = _f32c("layernorm_bf16", x), _f32c("layernorm_bf16", w), _f32c("layernorm_bf16", b)
+    x = _f32c("layernorm_bf16", x)
+    w = None if w is None else _f32c("layernorm_bf16", w)
+    b = None if b is None else _f32c("layernorm_bf16", b)
     M, D = int(x.shape[0]), int(x.shape[1])
     out = torch.empty((M, D), dtype=torch.bfloat16, device=x.device)
     with torch.cuda.device(x.device), _timed("layernorm_bf16"):
-        check(_L().p3tok_layernorm_bf16(x.data_ptr(), M, D, float(eps), w.data_ptr(), b.data_ptr(), out.data_ptr(), None, None,
-                                        None, _stream()), "layernorm_bf16")
+        check(_L().p3tok_layernorm_bf16(x.data_ptr(), M, D, float(eps), _ptr(w), _ptr(b), out.data_ptr(), _stream()),
+              "layernorm_bf16")
     return out
 
 
@@ -530,10 +536,11 @@ def _(qkv, B, G, heads):
 
 
 @torch.library.custom_op("p3tok::linear_bf16_ex", mutates_args=(), device_types="cuda")
-def linear_bf16_ex(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, act: int, residual: Optional[torch.Tensor],
-                   res_mul: float, out_scale: float) -> torch.Tensor:
-    """act(a w^T + bias) on tcgen05 with the ViT epilogues: act 0/1/2 = none/ReLU/exact GELU -> bf16 (M,N); with a
-    residual (M,N) f32 the result is res_mul * residual + out_scale * (a w^T + bias) as f32."""
+def linear_bf16_ex(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, act: int, gelu_cols: int,
+                   residual: Optional[torch.Tensor], res_mul: float, out_scale: float) -> torch.Tensor:
+    """act(a w^T + bias) on tcgen05 with the ViT epilogues: act 0/1/2 = none/ReLU/exact GELU, 3 = GELU on columns
+    < gelu_cols and ReLU on the rest -> bf16 (M,N); with a residual (M,N) f32 the result is
+    res_mul * residual + out_scale * (a w^T + bias) as f32."""
     _need_cuda("linear_bf16_ex", a, w, bias, residual)
     if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
         raise RuntimeError("p3tok::linear_bf16_ex: bf16 operands expected")
@@ -542,16 +549,17 @@ def linear_bf16_ex(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, act: in
     with torch.cuda.device(a.device), _timed("linear_bf16_ex"):
         if residual is None:
             out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
-            check(_L().p3tok_linear_bf16_ex(a.data_ptr(), M, K, w.data_ptr(), N, bias.data_ptr(), int(act), None, 0.0, 1.0,
-                                            out.data_ptr(), None, _stream()), "linear_bf16_ex")
+            check(_L().p3tok_linear_bf16_ex(a.data_ptr(), M, K, w.data_ptr(), N, bias.data_ptr(), int(act), int(gelu_cols), None,
+                                            0.0, 1.0, out.data_ptr(), None, _stream()), "linear_bf16_ex")
         else:
             res = _f32c("linear_bf16_ex", residual)
             out = torch.empty((M, N), dtype=torch.float32, device=a.device)
-            check(_L().p3tok_linear_bf16_ex(a.data_ptr(), M, K, w.data_ptr(), N, bias.data_ptr(), int(act), res.data_ptr(),
-                                            float(res_mul), float(out_scale), None, out.data_ptr(), _stream()), "linear_bf16_ex")
+            check(_L().p3tok_linear_bf16_ex(a.data_ptr(), M, K, w.data_ptr(), N, bias.data_ptr(), int(act), int(gelu_cols),
+                                            res.data_ptr(), float(res_mul), float(out_scale), None, out.data_ptr(), _stream()),
+                  "linear_bf16_ex")
     return out
 
 
 @linear_bf16_ex.register_fake
-def _(a, w, bias, act, residual, res_mul, out_scale):
+def _(a, w, bias, act, gelu_cols, residual, res_mul, out_scale):
     return a.new_empty((a.shape[0], w.shape[0]), dtype=torch.bfloat16 if residual is None else torch.float32)

@@ -200,19 +200,19 @@ P3TOK_API int p3tok_token_head_f32(const float* tokens, const float* centres, in
  * adapter(x) + x with adapter(x) = scale * up(relu(down(adapter_norm(x)))) + x (apf_utils.py:197-233) - so the
  * layer output carries 2*x, as the reference computes it.  Attention is the explicit softmax(q k^T / sqrt(hd)) v of
  * AttentionLayer (apf_utils.py:133-160); mlp = fc1 -> exact (erf) GELU -> fc2 (timm Mlp).  Eval mode: DropPath and
- * dropout are the identity.  LayerNorm eps 1e-5.  Weights row-major [out,in] bf16, biases / norm affines f32. */
+ * dropout are the identity.  LayerNorm eps 1e-5.
+ * The descriptor holds the layer FOLDED by the host (p3tok/apf_model.py::fold_vit_layer, like the BatchNorm folding of
+ * p3tok_mlp), matrices row-major [out,in] bf16, biases f32; g1/b1, g2/b2, ga/ba = affine of norm1, norm2, adapter_norm:
+ *   qkv_w  [3D, D]   = qkv.weight * diag(g1)                       qkv_b  = qkv.bias + qkv.weight b1
+ *   proj_w [D, D]    = proj.weight                                 proj_b = proj.bias
+ *   fc1d_w [H+R, D]  = [fc1.weight diag(g2) ; down_proj.weight diag(ga)]
+ *   fc1d_b [H+R]     = [fc1.bias + fc1.weight b2 ; down_proj.bias + down_proj.weight ba]
+ *   fc2u_w [D, H+R]  = [fc2.weight | scale * up_proj.weight]       fc2u_b = fc2.bias + scale * up_proj.bias */
 typedef struct p3tok_vit_layer {
-  const float* norm1_w; const float* norm1_b;      /* [D] */
-  const float* norm2_w; const float* norm2_b;      /* [D] */
-  const float* adnorm_w; const float* adnorm_b;    /* [D]  adapter.adapter_norm */
-  const void* qkv_w; const float* qkv_b;           /* [3D,D], [3D] */
-  const void* proj_w; const float* proj_b;         /* [D,D],  [D]  */
-  const void* fc1_w; const float* fc1_b;           /* [H,D],  [H]  */
-  const void* fc2_w; const float* fc2_b;           /* [D,H],  [D]  */
-  const void* down_w; const float* down_b;         /* [R,D],  [R]  adapter.down_proj */
-  const void* up_w; const float* up_b;             /* [D,R],  [D]  adapter.up_proj */
-  float adapter_scale;                             /* adapter.scale (a 1-element parameter), host value */
-  int32_t pad_;
+  const void* qkv_w; const float* qkv_b;
+  const void* proj_w; const float* proj_b;
+  const void* fc1d_w; const float* fc1d_b;
+  const void* fc2u_w; const float* fc2u_b;
 } p3tok_vit_layer;
 
 /* Workspace bytes for p3tok_apf_vit_forward (host computation only). */
@@ -221,25 +221,27 @@ P3TOK_API int64_t p3tok_apf_vit_workspace_bytes(int64_t B, int64_t G, int64_t D,
 /* Replaces the block loop + encoder_norm + token max of AdaptPointFormer.forward (src/models/apf.py:361-366).
  * x (B,G,D) f32: the tokens; overwritten IN PLACE by the output of the last block (the fp32 residual stream).
  * layers: HOST array of n_layers descriptors (device pointers inside).  heads: D/heads must be 32 or 64.
+ * H = mlp hidden width (multiple of 64), R = adapter bottleneck (multiple of 8).
  * final_norm_w/b [D] + pooled_out (B,D) f32: pooled = max over the G tokens of LayerNorm(x) (apf.py:364-366);
  * pass pooled_out = NULL to skip.  GEMMs on tcgen05 (bf16 operands, fp32 accumulate), attention on bf16 mma with
- * fp32 softmax; rtol 2e-2 contract on the pooled features (12 layers of bf16 GEMMs), see tests/test_gpu_vit.py. */
+ * fp32 softmax; the bf16 contract of the tokenizer (rtol 1e-2) holds after 12 layers, see tests/test_gpu_vit.py. */
 P3TOK_API int p3tok_apf_vit_forward(float* x, int64_t B, int64_t G, int64_t D, int64_t heads, int64_t H, int64_t R,
                           const p3tok_vit_layer* layers, int64_t n_layers, const float* final_norm_w,
                           const float* final_norm_b, float* pooled_out, void* workspace, int64_t workspace_bytes,
                           void* stream);
 
 /* Building blocks of the above, exported for tests.
- * p3tok_layernorm_bf16: out1 = bf16(LN(x; w1,b1)), optionally out2 = bf16(LN(x; w2,b2)) (same statistics). x (M,D) f32.
+ * p3tok_layernorm_bf16: out = bf16(LN(x; w, b)) over the rows of x (M,D) f32; w = b = NULL: normalisation only.
  * p3tok_attention_bf16: qkv (B*G, 3D) bf16 laid out as AttentionLayer's reshape(B,N,3,heads,hd) -> out (B*G, D) bf16. */
-P3TOK_API int p3tok_layernorm_bf16(const float* x, int64_t M, int64_t D, float eps, const float* w1, const float* b1,
-                         void* out1, const float* w2, const float* b2, void* out2, void* stream);
+P3TOK_API int p3tok_layernorm_bf16(const float* x, int64_t M, int64_t D, float eps, const float* w, const float* b,
+                         void* out, void* stream);
 P3TOK_API int p3tok_attention_bf16(const void* qkv, int64_t B, int64_t G, int64_t D, int64_t heads, void* out, void* stream);
-/* p3tok_linear_bf16 with the ViT epilogues: act 0 none / 1 ReLU / 2 exact GELU; then, if residual != NULL,
- * out_f32 = res_mul * residual + out_scale * act(A W^T + bias) (residual may alias out_f32). */
+/* p3tok_linear_bf16 with the ViT epilogues: act 0 none / 1 ReLU / 2 exact GELU / 3 GELU on columns < gelu_cols and ReLU on
+ * the rest; then, if residual != NULL, out_f32 = res_mul * residual + out_scale * act(A W^T + bias) (residual may alias
+ * out_f32).  N <= 2048 per call. */
 P3TOK_API int p3tok_linear_bf16_ex(const void* A, int64_t M, int64_t K, const void* W, int64_t N, const float* bias, int act,
-                         const float* residual, float res_mul, float out_scale, void* out_bf16, float* out_f32,
-                         void* stream);
+                         int64_t gelu_cols, const float* residual, float res_mul, float out_scale, void* out_bf16,
+                         float* out_f32, void* stream);
 
 /* out[g, c] = max over r < k of in[(g*k + r), c]   (torch.max(..., dim=k-axis)) */
 P3TOK_API int p3tok_group_max(const float* in, int64_t ngroups, int64_t k, int64_t C, float* out, void* stream);

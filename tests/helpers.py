@@ -77,36 +77,33 @@ def folded_forward(mlp, rows, k):
     return torch.relu(o) if mlp.out_relu else o
 
 
-def vit_bf16_emulation(sd, tokens, depth, heads):
-    """The ViT block stack's arithmetic (csrc/vit.cu) spelled in torch on any device: bf16 weights and stored
-    activations (LayerNorm outputs, qkv, softmax probabilities, attention output, adapter bottleneck, GELU output),
-    fp32 accumulation, fp32 residual stream.  Returns (x (B,G,D), pooled (B,D)) float32."""
+def vit_bf16_emulation(folded, tokens, heads, bottleneck, final_w, final_b):
+    """The ViT block stack's arithmetic (csrc/vit.cu) spelled in torch on any device, from the FOLDED layers
+    (p3tok.apf_model.fold_vit_layer: 8 tensors per layer): bf16 weights and stored activations (normalised rows, qkv,
+    softmax probabilities, attention output, [gelu | relu] hidden matrix), fp32 accumulation, fp32 residual stream.
+    Returns (x (B,G,D), pooled (B,D)) float32."""
     import torch
     import torch.nn.functional as F
 
     def q(t):
         return t.bfloat16().float()
 
-    T = lambda k: torch.as_tensor(sd[k]).float().to(tokens.device)
-    mm = lambda a, w: (a.double() @ q(w).double().T).float()
+    mm = lambda a, w: (a.double() @ w.double().T).float()
     x = tokens.float()
     B, G, D = x.shape
     hd = D // heads
-    for i in range(depth):
-        p = f"blocks.{i}."
-        a = q(F.layer_norm(x, (D,), T(p + "norm1.weight"), T(p + "norm1.bias"), 1e-5))
-        qkv = q(mm(a, T(p + "attention.qkv.weight")) + T(p + "attention.qkv.bias"))
-        qkv = qkv.reshape(B, G, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    for qkv_w, qkv_b, proj_w, proj_b, fc1d_w, fc1d_b, fc2u_w, fc2u_b in folded:
+        a = q(F.layer_norm(x, (D,), None, None, 1e-5))
+        qkv = q(mm(a, qkv_w) + qkv_b).reshape(B, G, 3, heads, hd).permute(2, 0, 3, 1, 4)
         s = (qkv[0].double() @ qkv[1].double().transpose(-2, -1)).float() * hd ** -0.5
         e = torch.exp(s - s.max(-1, keepdim=True)[0])
         o = (q(e).double() @ qkv[2].double()).float() / e.sum(-1, keepdim=True)     # P rounded to bf16, row sum in fp32
         o = q(o.transpose(1, 2).reshape(B, G, D))
-        x = x + (mm(o, T(p + "attention.proj.weight")) + T(p + "attention.proj.bias"))
-        n2 = q(F.layer_norm(x, (D,), T(p + "norm2.weight"), T(p + "norm2.bias"), 1e-5))
-        an = q(F.layer_norm(x, (D,), T(p + "adapter.adapter_norm.weight"), T(p + "adapter.adapter_norm.bias"), 1e-5))
-        dn = q(torch.relu(mm(an, T(p + "adapter.down_proj.weight")) + T(p + "adapter.down_proj.bias")))
-        x = 2.0 * x + float(T(p + "adapter.scale").reshape(-1)[0]) * (mm(dn, T(p + "adapter.up_proj.weight")) + T(p + "adapter.up_proj.bias"))
-        h = q(F.gelu(mm(n2, T(p + "mlp.fc1.weight")) + T(p + "mlp.fc1.bias")))
-        x = x + (mm(h, T(p + "mlp.fc2.weight")) + T(p + "mlp.fc2.bias"))
-    pooled = F.layer_norm(x, (D,), T("encoder_norm.weight"), T("encoder_norm.bias"), 1e-5).max(1)[0]
+        x = x + (mm(o, proj_w) + proj_b)
+        a = q(F.layer_norm(x, (D,), None, None, 1e-5))
+        h = mm(a, fc1d_w) + fc1d_b
+        H = h.shape[-1] - bottleneck
+        h = q(torch.cat([F.gelu(h[..., :H]), torch.relu(h[..., H:])], -1))
+        x = 2.0 * x + (mm(h, fc2u_w) + fc2u_b)
+    pooled = F.layer_norm(x, (D,), final_w.float(), final_b.float(), 1e-5).max(1)[0]
     return x, pooled

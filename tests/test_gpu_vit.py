@@ -12,7 +12,7 @@ import cases
 from helpers import assert_tokens_close, dev, rel_err, to_dev, vit_bf16_emulation
 from oracle import oracle
 from p3tok import ops, synth
-from p3tok.apf_model import AdaptPointFormer, APFViTLayer, ClassificationHead, run_blocks
+from p3tok.apf_model import AdaptPointFormer, APFViTLayer, ClassificationHead, fold_vit_layer, run_blocks
 
 pytestmark = pytest.mark.gpu
 
@@ -25,6 +25,9 @@ def test_layernorm_block(M, D):
     got = ops.layernorm_bf16(x, w, b, 1e-5).float()
     ref = torch.nn.functional.layer_norm(x.double(), (D,), w.double(), b.double(), 1e-5)
     assert (got.double() - ref).abs().max() <= 2 ** -8 * ref.abs().max() + 1e-6      # one bf16 rounding
+    got = ops.layernorm_bf16(x, None, None, 1e-5).float()                             # the stack's form: no affine
+    ref = torch.nn.functional.layer_norm(x.double(), (D,), None, None, 1e-5)
+    assert (got.double() - ref).abs().max() <= 2 ** -8 * ref.abs().max() + 1e-6
 
 
 @pytest.mark.parametrize("B,G,heads,hd", [(2, 128, 12, 32), (3, 50, 2, 32), (1, 196, 12, 64), (2, 7, 1, 64), (1, 300, 3, 32)])
@@ -41,7 +44,8 @@ def test_attention_block(B, G, heads, hd):
     assert torch.linalg.norm(got.double() - ref) <= 5e-3 * torch.linalg.norm(ref)
 
 
-@pytest.mark.parametrize("M,K,N", [(256, 384, 1536), (1000, 64, 384), (300, 1536, 384), (130, 384, 64), (128, 768, 2304)])
+@pytest.mark.parametrize("M,K,N", [(256, 384, 1536), (1000, 64, 384), (300, 1600, 384), (130, 384, 64), (128, 768, 2304),
+                                   (700, 384, 1600)])
 def test_linear_epilogues(M, K, N):
     torch.manual_seed(K + N)
     a = torch.randn(M, K, device=dev()).bfloat16()
@@ -50,16 +54,23 @@ def test_linear_epilogues(M, K, N):
     acc = a.double() @ w.double().T + b.double()
     if N <= 2048:
         for act, f in ((0, lambda t: t), (1, torch.relu), (2, lambda t: torch.nn.functional.gelu(t))):
-            got = ops.linear_bf16_ex(a, w, b, act, None, 0.0, 1.0).double()
+            got = ops.linear_bf16_ex(a, w, b, act, 0, None, 0.0, 1.0).double()
             ref = f(acc)
             assert (got - ref).abs().max() <= 2 ** -8 * ref.abs().max() + 1e-3, act
+            # elementwise to one bf16 rounding of the fp32 result (GELU: the erfc-exponent polynomial is 2e-5 relative)
+            assert ((got - ref).abs() <= 2 ** -8 * ref.abs() + 2e-5 * acc.abs().max()).all(), act
+        if N > 64:                                             # [gelu | relu] column split (fc1 + adapter bottleneck GEMM)
+            split = (N // 2 + 63) // 64 * 64
+            got = ops.linear_bf16_ex(a, w, b, 3, split, None, 0.0, 1.0).double()
+            ref = torch.cat([torch.nn.functional.gelu(acc[:, :split]), torch.relu(acc[:, split:])], 1)
+            assert ((got - ref).abs() <= 2 ** -8 * ref.abs() + 2e-5 * acc.abs().max()).all()
         res = torch.randn(M, N, device=dev()) * 4
-        got = ops.linear_bf16_ex(a, w, b, 0, res, 2.0, 0.7).double()
+        got = ops.linear_bf16_ex(a, w, b, 0, 0, res, 2.0, 0.7).double()
         ref = 2.0 * res.double() + 0.7 * acc
         assert (got - ref).abs().max() <= 2e-5 * ref.abs().max()
     else:
         with pytest.raises(RuntimeError):                      # one launch stages at most 2048 bias columns; the stack
-            ops.linear_bf16_ex(a, w, b, 0, None, 0.0, 1.0)     # slices wider layers (checked by test_vit_b_width)
+            ops.linear_bf16_ex(a, w, b, 0, 0, None, 0.0, 1.0)  # slices wider layers (checked by test_vit_b_width)
 
 
 def _stack(c, sd):
@@ -87,7 +98,8 @@ def test_vit_stack_golden(golden_dir, name):
         assert_tokens_close(got.cpu().numpy(), orc, 1e-2, f"{name}:{key} vs oracle")
         assert_tokens_close(got.cpu().numpy(), g[key], 1e-2, f"{name}:{key} vs reference golden")
     # against a torch model of the kernels' own arithmetic the error is accumulation order + exp2/GELU approximations
-    ex, ep = vit_bf16_emulation(sd, to_dev(tok), c["depth"], c["heads"])
+    folded = [fold_vit_layer(blk) for blk in blocks]
+    ex, ep = vit_bf16_emulation(folded, to_dev(tok), c["heads"], 64, norm.weight.detach(), norm.bias.detach())
     assert rel_err(x.cpu().numpy(), ex.cpu().numpy()) < 4e-3
     assert rel_err(pooled.cpu().numpy(), ep.cpu().numpy()) < 4e-3
     # a single layer called as a module (APFViTLayer.forward) is the first step of the stack

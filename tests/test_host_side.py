@@ -34,16 +34,16 @@ def test_struct_layouts_match_header(tmp_path, built):
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "p3tok.h"\nint main(){printf("%zu %zu %zu %zu\\n",'
                    'sizeof(p3tok_mlp),sizeof(p3tok_rows),offsetof(p3tok_mlp,w_pre),offsetof(p3tok_rows,x));'
-                   'printf("%zu %zu %zu\\n",sizeof(p3tok_vit_layer),offsetof(p3tok_vit_layer,up_b),'
-                   'offsetof(p3tok_vit_layer,adapter_scale));return 0;}')
+                   'printf("%zu %zu %zu\\n",sizeof(p3tok_vit_layer),offsetof(p3tok_vit_layer,fc1d_w),'
+                   'offsetof(p3tok_vit_layer,fc2u_b));return 0;}')
     exe = tmp_path / "sz"
     inc = os.path.join(os.path.dirname(_lib.HEADER_PATH))
     subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True)
     a, b, c, d, e, f, g = (int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split())
     assert ctypes.sizeof(_lib.MlpStruct) == a and ctypes.sizeof(_lib.RowsStruct) == b
     assert _lib.MlpStruct.w_pre.offset == c and _lib.RowsStruct.x.offset == d
-    assert ctypes.sizeof(_lib.VitLayerStruct) == e and _lib.VitLayerStruct.up_b.offset == f
-    assert _lib.VitLayerStruct.adapter_scale.offset == g
+    assert ctypes.sizeof(_lib.VitLayerStruct) == e and _lib.VitLayerStruct.fc1d_w.offset == f
+    assert _lib.VitLayerStruct.fc2u_b.offset == g
 
 
 def test_fold_apf_matches_oracle():
@@ -138,3 +138,24 @@ def test_apf_model_keys_match_reference_modules():
     assert set(ClassificationHead(64, 15).state_dict()) == set(ref.apf.ClassificationHead(64, 15).state_dict())
     sd = ref.apf_utils.APFViTLayer(dim=64, num_heads=2).state_dict()
     APFViTLayer(64, 2).load_state_dict(sd, strict=True)
+
+
+def test_fold_vit_layer_matches_oracle():
+    """The four folded GEMMs of a layer (p3tok.apf_model.fold_vit_layer) evaluated in float64 equal the oracle's layer."""
+    from p3tok.apf_model import APFViTLayer, fold_vit_layer
+    D, heads, R = 64, 2, 64
+    sd = synth.apf_vit_state(D, 1, 15, 9)
+    blk = APFViTLayer(D, heads).eval()
+    blk.load_state_dict({k[len("blocks.0."):]: v for k, v in synth.to_torch_state(sd).items() if k.startswith("blocks.0.")})
+    x = torch.from_numpy(synth.vit_tokens(2, 10, D, 9)).double()
+    ref = oracle.apf_vit_layer(sd, "blocks.0.", x.numpy(), heads)
+    qw, qb, pw, pb, f1w, f1b, f2w, f2b = [t.double() for t in fold_vit_layer(blk)]
+    ln = lambda t: torch.nn.functional.layer_norm(t, (D,), None, None, 1e-5)
+    qkv = (ln(x) @ qw.T + qb).reshape(2, 10, 3, heads, D // heads).permute(2, 0, 3, 1, 4)
+    att = ((qkv[0] @ qkv[1].transpose(-2, -1)) * (D // heads) ** -0.5).softmax(-1)
+    x = x + ((att @ qkv[2]).transpose(1, 2).reshape(2, 10, D) @ pw.T + pb)
+    h = ln(x) @ f1w.T + f1b
+    h = torch.cat([torch.nn.functional.gelu(h[..., :-R]), torch.relu(h[..., -R:])], -1)
+    got = 2 * x + (h @ f2w.T + f2b)
+    assert np.abs(got.numpy() - ref).max() <= 1e-2 * np.abs(ref).max()      # bf16-rounded folded weights
+    assert np.linalg.norm(got.numpy() - ref) <= 5e-3 * np.linalg.norm(ref)
