@@ -114,13 +114,14 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {   // explicit shared-
   return v;
 }
 
-// exact (erf) GELU without the erf: with q(t) = log2(erfc(t / sqrt 2)), t = |x|,
-//   gelu(x) = x Phi(x) = max(x, 0) - |x|/2 * 2^q(|x|)
+// exact (erf) GELU without the erf: with q(t) = log2(erfc(t / sqrt 2) / 2), t = |x|,
+//   gelu(x) = x Phi(x) = max(x, 0) - |x| * 2^q(|x|)
 // (x < 0: x/2 erfc(|x|/sqrt 2); x > 0: x - x/2 erfc(x/sqrt 2)) - no cancellation in either tail.  q is smooth; its
-// degree-8 least-squares Chebyshev fit on [0, 10] (fitted and checked against scipy in fp32 arithmetic: |error| <=
-// 2.4e-6 absolute, <= 2.2e-5 relative where |gelu| > 1e-6 - a hundredth of a bf16 rounding) costs 8 FMAs + ONE MUFU
-// (EX2): the epilogue of the fc1 GEMM is MUFU- and issue-bound (erff(): ~25 instructions, the A&S 7.1.26 form 2 MUFUs),
-// and |x| beyond 10 is clamped (2^q(10) < 2e-23).  Two elements per call: the Horner chain runs as packed FFMA2.
+// degree-7 least-squares Chebyshev fit on [0, 6.5] (fitted and checked against scipy in fp32 arithmetic: <= 7e-6 relative
+// where |gelu| > 1e-6, absolute error at fp32 rounding level - 1/280 of a bf16 rounding) has a negative leading
+// coefficient, so beyond the interval it only falls (q < -34 for t > 6.5, -inf for huge t: 2^q = 0, no clamp needed).
+// 7 FMAs + ONE MUFU (EX2) + FMNMX + FFMA per element: the epilogue of the fc1 GEMM is issue- and MUFU-bound (erff():
+// ~25 instructions; the A&S 7.1.26 form: 2 MUFUs).  Two elements per call: the Horner chain runs as packed FFMA2.
 __device__ __forceinline__ void fma2(float& o0, float& o1, float a0, float a1, float b0, float b1, float c0, float c1) {
   asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; fma.rn.f32x2 rd, ra, rb, rc; "
       "mov.b64 {%0,%1}, rd; }"
@@ -128,21 +129,20 @@ __device__ __forceinline__ void fma2(float& o0, float& o1, float a0, float a1, f
       : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
 }
 __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
-  const float t0 = fminf(fabsf(x0), 10.f), t1 = fminf(fabsf(x1), 10.f);
-  float r0 = 6.171978522e-08f, r1 = 6.171978522e-08f;
-  fma2(r0, r1, r0, r1, t0, t1, -3.191675725e-06f, -3.191675725e-06f);
-  fma2(r0, r1, r0, r1, t0, t1, 7.265022928e-05f, 7.265022928e-05f);
-  fma2(r0, r1, r0, r1, t0, t1, -9.681803689e-04f, -9.681803689e-04f);
-  fma2(r0, r1, r0, r1, t0, t1, 8.529751658e-03f, 8.529751658e-03f);
-  fma2(r0, r1, r0, r1, t0, t1, -5.378560319e-02f, -5.378560319e-02f);
-  fma2(r0, r1, r0, r1, t0, t1, -4.588579945e-01f, -4.588579945e-01f);
-  fma2(r0, r1, r0, r1, t0, t1, -1.150993949e+00f, -1.150993949e+00f);
-  fma2(r0, r1, r0, r1, t0, t1, -3.042118848e-05f, -3.042118848e-05f);
+  const float t0 = fabsf(x0), t1 = fabsf(x1);
+  float r0 = -1.808829734e-06f, r1 = -1.808829734e-06f;
+  fma2(r0, r1, r0, r1, t0, t1, 6.107435026e-05f, 6.107435026e-05f);
+  fma2(r0, r1, r0, r1, t0, t1, -9.264088059e-04f, -9.264088059e-04f);
+  fma2(r0, r1, r0, r1, t0, t1, 8.492039891e-03f, 8.492039891e-03f);
+  fma2(r0, r1, r0, r1, t0, t1, -5.392931550e-02f, -5.392931550e-02f);
+  fma2(r0, r1, r0, r1, t0, t1, -4.584916519e-01f, -4.584916519e-01f);
+  fma2(r0, r1, r0, r1, t0, t1, -1.151243301e+00f, -1.151243301e+00f);
+  fma2(r0, r1, r0, r1, t0, t1, -9.999950370e-01f, -9.999950370e-01f);
   float e0, e1;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(r0));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(r1));
-  x0 = fmaf(-0.5f * fabsf(x0), e0, fmaxf(x0, 0.f));
-  x1 = fmaf(-0.5f * fabsf(x1), e1, fmaxf(x1, 0.f));
+  x0 = fmaf(-t0, e0, fmaxf(x0, 0.f));
+  x1 = fmaf(-t1, e1, fmaxf(x1, 0.f));
 }
 
 // `sbias` is staged zero-padded to a multiple of 64 columns, so the 32 columns starting at n0 are always readable.

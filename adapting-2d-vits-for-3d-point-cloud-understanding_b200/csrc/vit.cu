@@ -182,123 +182,151 @@ __device__ __forceinline__ float ex2f(float x) {
 
 constexpr int AT_Q = 128, AT_KV = 64, AT_THREADS = 256;   // query rows per CTA (8 warps x 16), keys per block
 
+// 16-byte asynchronous global -> shared copy; `ok` false zero-fills (rows past the end of the cloud)
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool ok) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int n = ok ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int HD>
+constexpr int attention_smem_bytes() { return (AT_Q + 4 * AT_KV) * (HD + 8) * 2; }
+
 // qkv (B*G, 3D) bf16: column which*D + head*HD + d (AttentionLayer's reshape(B,N,3,heads,hd), apf_utils.py:143).
 // out (B*G, D) bf16: column head*HD + d ((attn @ v).transpose(1,2).reshape(B,N,C), apf_utils.py:155).
-// grid (ceil(G/128), heads, B).  Q, K, V tiles are staged row-major in padded shared memory by coalesced 16-byte copies;
+// grid (ceil(G/128), heads, B).  Q and the K / V blocks are staged row-major in padded shared memory by cp.async, two key
+// blocks in flight (for G <= 128 the whole (cloud, head) is requested up front: one exposed memory latency per CTA
+// instead of three - the first version, load -> barrier -> compute per block, was latency-bound at 32 us per 16 k rows);
 // fragments come from ldmatrix (V through .trans: the [key][d] tile is already the k-major B operand of P V).
 // Lane (g = lane/4, t = lane%4) of a warp owns query rows g and g+8 of the warp's 16 (the m16n8k16 accumulator layout),
 // so row maxima / sums need only the two quad shuffles.  Scores stay raw; p = 2^(s*c - m*c) with c = log2(e)/sqrt(hd).
 template <int HD>
-__global__ void __launch_bounds__(AT_THREADS)
+__global__ void __launch_bounds__(AT_THREADS, HD == 32 ? 3 : 2)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int G, int D, float scale_log2e) {
   constexpr int KS = HD / 16;          // k steps of q k^T
   constexpr int DT = HD / 8;           // n tiles of the output
   constexpr int RP = HD + 8;           // padded row (16-byte aligned, conflict-free ldmatrix)
   constexpr int CPR = HD / 8;          // 16-byte chunks per row
-  __shared__ __align__(16) __nv_bfloat16 sQ[AT_Q * RP];
-  __shared__ __align__(16) __nv_bfloat16 sK[AT_KV * RP];
-  __shared__ __align__(16) __nv_bfloat16 sV[AT_KV * RP];
+  extern __shared__ __align__(16) uint8_t at_smem[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(at_smem);
+  __nv_bfloat16* sKV = sQ + AT_Q * RP;   // buffer j: K at sKV + j * 2 * AT_KV * RP, V right behind it
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int head = blockIdx.y, b = blockIdx.z;
   const int qb = blockIdx.x * AT_Q;
   const int q0 = qb + warp * 16;
   const size_t ld = (size_t)3 * D;
   const __nv_bfloat16* base = qkv + (size_t)b * G * ld + (size_t)head * HD;
+  const int nblk = (G + AT_KV - 1) / AT_KV;
 
+  auto load_kv = [&](int blk) {
+    __nv_bfloat16* k = sKV + (size_t)(blk & 1) * 2 * AT_KV * RP;
+    __nv_bfloat16* v = k + AT_KV * RP;
+    const int kv0 = blk * AT_KV;
+    for (int c = tid; c < AT_KV * CPR; c += AT_THREADS) {
+      const int r = c / CPR, ch = c % CPR;
+      const bool ok = kv0 + r < G;
+      const __nv_bfloat16* rowp = base + (size_t)(ok ? kv0 + r : 0) * ld + ch * 8;
+      cp_async16(&k[r * RP + ch * 8], rowp + D, ok);
+      cp_async16(&v[r * RP + ch * 8], rowp + 2 * D, ok);
+    }
+  };
   for (int c = tid; c < AT_Q * CPR; c += AT_THREADS) {
     const int r = c / CPR, ch = c % CPR;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (qb + r < G) v = *reinterpret_cast<const uint4*>(base + (size_t)(qb + r) * ld + ch * 8);
-    *reinterpret_cast<uint4*>(&sQ[r * RP + ch * 8]) = v;
+    const bool ok = qb + r < G;
+    cp_async16(&sQ[r * RP + ch * 8], base + (size_t)(ok ? qb + r : 0) * ld + ch * 8, ok);
   }
-  __syncthreads();
+  load_kv(0);
+  cp_async_commit();                   // group: Q + block 0
+  if (nblk > 1) load_kv(1);
+  cp_async_commit();                   // group: block 1 (possibly empty)
+
+  const bool active = q0 < G;          // warps whose 16 rows lie past G only help with the copies
   uint32_t qa[KS][4];
-#pragma unroll
-  for (int ks = 0; ks < KS; ++ks)   // lanes 0-15: rows 0-15 at column ks*16; lanes 16-31: the same rows at column ks*16 + 8
-    ldsm_x4(qa[ks], (uint32_t)__cvta_generic_to_shared(&sQ[(warp * 16 + (lane & 15)) * RP + ks * 16 + (lane >> 4) * 8]));
-  const bool active = q0 < G;   // warps whose 16 rows lie past G only help with the copies
   float o[DT][4];
 #pragma unroll
   for (int i = 0; i < DT; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // running maxima of the RAW scores, running sums
 
-  for (int kv0 = 0; kv0 < G; kv0 += AT_KV) {
-    __syncthreads();   // previous block's fragments have been read
-    for (int c = tid; c < AT_KV * CPR; c += AT_THREADS) {
-      const int r = c / CPR, ch = c % CPR;
-      uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-      if (kv0 + r < G) {
-        const __nv_bfloat16* rowp = base + (size_t)(kv0 + r) * ld + ch * 8;
-        kk = *reinterpret_cast<const uint4*>(rowp + D);
-        vv = *reinterpret_cast<const uint4*>(rowp + 2 * D);
-      }
-      *reinterpret_cast<uint4*>(&sK[r * RP + ch * 8]) = kk;
-      *reinterpret_cast<uint4*>(&sV[r * RP + ch * 8]) = vv;
-    }
+  for (int blk = 0; blk < nblk; ++blk) {
+    cp_async_wait<1>();                // everything but the most recent group has landed: this block (and Q)
     __syncthreads();
-    if (!active) continue;
-
-    float sc[AT_KV / 8][4];
+    const int kv0 = blk * AT_KV;
+    const __nv_bfloat16* sK = sKV + (size_t)(blk & 1) * 2 * AT_KV * RP;
+    const __nv_bfloat16* sV = sK + AT_KV * RP;
+    if (blk == 0) {
 #pragma unroll
-    for (int nt = 0; nt < AT_KV / 8; ++nt) {
-      sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
-#pragma unroll
-      for (int k2 = 0; k2 < KS; k2 += 2) {   // one x4: keys nt*8..+7, d chunks (k2*16, +8, +16, +24) = b0,b1 of two k steps
-        uint32_t kb[4];
-        ldsm_x4(kb, (uint32_t)__cvta_generic_to_shared(&sK[(nt * 8 + (lane & 7)) * RP + k2 * 16 + (lane >> 3) * 8]));
-        mma_bf16_16816(sc[nt], qa[k2], kb[0], kb[1]);
-        mma_bf16_16816(sc[nt], qa[k2 + 1], kb[2], kb[3]);
-      }
+      for (int ks = 0; ks < KS; ++ks)   // lanes 0-15: rows 0-15 at column ks*16; lanes 16-31: the same rows at column ks*16 + 8
+        ldsm_x4(qa[ks], (uint32_t)__cvta_generic_to_shared(&sQ[(warp * 16 + (lane & 15)) * RP + ks * 16 + (lane >> 4) * 8]));
     }
-    if (kv0 + AT_KV > G) {   // ragged last block: keys past G never win the max and contribute 2^-inf = 0
+    if (active) {
+      float sc[AT_KV / 8][4];
 #pragma unroll
       for (int nt = 0; nt < AT_KV / 8; ++nt) {
-        const int col = kv0 + nt * 8 + 2 * t;
-        if (col >= G) sc[nt][0] = sc[nt][2] = -INFINITY;
-        if (col + 1 >= G) sc[nt][1] = sc[nt][3] = -INFINITY;
+        sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+#pragma unroll
+        for (int k2 = 0; k2 < KS; k2 += 2) {   // one x4: keys nt*8..+7, d chunks (k2*16, +8, +16, +24) = b0,b1 of two k steps
+          uint32_t kb[4];
+          ldsm_x4(kb, (uint32_t)__cvta_generic_to_shared(&sK[(nt * 8 + (lane & 7)) * RP + k2 * 16 + (lane >> 3) * 8]));
+          mma_bf16_16816(sc[nt], qa[k2], kb[0], kb[1]);
+          mma_bf16_16816(sc[nt], qa[k2 + 1], kb[2], kb[3]);
+        }
+      }
+      if (kv0 + AT_KV > G) {   // ragged last block: keys past G never win the max and contribute 2^-inf = 0
+#pragma unroll
+        for (int nt = 0; nt < AT_KV / 8; ++nt) {
+          const int col = kv0 + nt * 8 + 2 * t;
+          if (col >= G) sc[nt][0] = sc[nt][2] = -INFINITY;
+          if (col + 1 >= G) sc[nt][1] = sc[nt][3] = -INFINITY;
+        }
+      }
+      float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < AT_KV / 8; ++nt) {
+        bm0 = fmaxf(bm0, fmaxf(sc[nt][0], sc[nt][1]));
+        bm1 = fmaxf(bm1, fmaxf(sc[nt][2], sc[nt][3]));
+      }
+      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+      const float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);   // finite: every block holds at least one valid key
+      const float c0 = ex2f((m0 - n0) * scale_log2e), c1 = ex2f((m1 - n1) * scale_log2e);   // 0 on the first block (m = -inf)
+      m0 = n0; m1 = n1;
+      const float ms0 = -n0 * scale_log2e, ms1 = -n1 * scale_log2e;
+      l0 *= c0; l1 *= c1;
+#pragma unroll
+      for (int i = 0; i < DT; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+#pragma unroll
+      for (int nt = 0; nt < AT_KV / 8; ++nt) {
+        sc[nt][0] = ex2f(fmaf(sc[nt][0], scale_log2e, ms0)); sc[nt][1] = ex2f(fmaf(sc[nt][1], scale_log2e, ms0));
+        sc[nt][2] = ex2f(fmaf(sc[nt][2], scale_log2e, ms1)); sc[nt][3] = ex2f(fmaf(sc[nt][3], scale_log2e, ms1));
+        l0 += sc[nt][0] + sc[nt][1];
+        l1 += sc[nt][2] + sc[nt][3];
+      }
+      // O += P V: the score accumulators of two adjacent key tiles are exactly one A fragment
+#pragma unroll
+      for (int kk = 0; kk < AT_KV / 16; ++kk) {
+        uint32_t pa[4];
+        pa[0] = pack2(sc[2 * kk][0], sc[2 * kk][1]);
+        pa[1] = pack2(sc[2 * kk][2], sc[2 * kk][3]);
+        pa[2] = pack2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+        pa[3] = pack2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+#pragma unroll
+        for (int dt = 0; dt < DT; dt += 2) {   // one x4.trans: keys kk*16 (+8), d tiles dt and dt+1 -> b0,b1 of each
+          uint32_t vb[4];
+          ldsm_x4_t(vb, (uint32_t)__cvta_generic_to_shared(
+                            &sV[(kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * RP + (dt + (lane >> 4)) * 8]));
+          mma_bf16_16816(o[dt], pa, vb[0], vb[1]);
+          mma_bf16_16816(o[dt + 1], pa, vb[2], vb[3]);
+        }
       }
     }
-    float bm0 = -INFINITY, bm1 = -INFINITY;
-#pragma unroll
-    for (int nt = 0; nt < AT_KV / 8; ++nt) {
-      bm0 = fmaxf(bm0, fmaxf(sc[nt][0], sc[nt][1]));
-      bm1 = fmaxf(bm1, fmaxf(sc[nt][2], sc[nt][3]));
-    }
-    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
-    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
-    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
-    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-    const float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);   // finite: every block holds at least one valid key
-    const float c0 = ex2f((m0 - n0) * scale_log2e), c1 = ex2f((m1 - n1) * scale_log2e);   // 0 on the first block (m = -inf)
-    m0 = n0; m1 = n1;
-    const float ms0 = -n0 * scale_log2e, ms1 = -n1 * scale_log2e;
-    l0 *= c0; l1 *= c1;
-#pragma unroll
-    for (int i = 0; i < DT; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
-#pragma unroll
-    for (int nt = 0; nt < AT_KV / 8; ++nt) {
-      sc[nt][0] = ex2f(fmaf(sc[nt][0], scale_log2e, ms0)); sc[nt][1] = ex2f(fmaf(sc[nt][1], scale_log2e, ms0));
-      sc[nt][2] = ex2f(fmaf(sc[nt][2], scale_log2e, ms1)); sc[nt][3] = ex2f(fmaf(sc[nt][3], scale_log2e, ms1));
-      l0 += sc[nt][0] + sc[nt][1];
-      l1 += sc[nt][2] + sc[nt][3];
-    }
-    // O += P V: the score accumulators of two adjacent key tiles are exactly one A fragment
-#pragma unroll
-    for (int kk = 0; kk < AT_KV / 16; ++kk) {
-      uint32_t pa[4];
-      pa[0] = pack2(sc[2 * kk][0], sc[2 * kk][1]);
-      pa[1] = pack2(sc[2 * kk][2], sc[2 * kk][3]);
-      pa[2] = pack2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
-      pa[3] = pack2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
-#pragma unroll
-      for (int dt = 0; dt < DT; dt += 2) {   // one x4.trans: keys kk*16 (+8), d tiles dt and dt+1 -> b0,b1 of each
-        uint32_t vb[4];
-        ldsm_x4_t(vb, (uint32_t)__cvta_generic_to_shared(
-                          &sV[(kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * RP + (dt + (lane >> 4)) * 8]));
-        mma_bf16_16816(o[dt], pa, vb[0], vb[1]);
-        mma_bf16_16816(o[dt + 1], pa, vb[2], vb[3]);
-      }
-    }
+    __syncthreads();                   // every warp is done with buffer blk & 1
+    if (blk + 2 < nblk) load_kv(blk + 2);
+    cp_async_commit();                 // one group per iteration keeps the wait_group<1> accounting uniform
   }
   if (!active) return;
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
@@ -325,8 +353,16 @@ static int attention_bf16(const __nv_bfloat16* qkv, int64_t B, int64_t G, int D,
   if (B * G == 0) return P3TOK_OK;
   const float scale_log2e = (float)((1.0 / sqrt((double)hd)) * 1.4426950408889634);
   dim3 grid((unsigned)((G + AT_Q - 1) / AT_Q), (unsigned)heads, (unsigned)B);
-  if (hd == 32) attention_kernel<32><<<grid, AT_THREADS, 0, s>>>(qkv, out, (int)G, D, scale_log2e);
-  else attention_kernel<64><<<grid, AT_THREADS, 0, s>>>(qkv, out, (int)G, D, scale_log2e);
+  static thread_local bool configured[32] = {false};   // attention_kernel<64> needs 55 KB of dynamic shared memory
+  int dev = 0;
+  P3_CUDA(cudaGetDevice(&dev));
+  if (dev < 32 && !configured[dev]) {
+    P3_CUDA(cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, attention_smem_bytes<32>()));
+    P3_CUDA(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attention_smem_bytes<64>()));
+    configured[dev] = true;
+  }
+  if (hd == 32) attention_kernel<32><<<grid, AT_THREADS, attention_smem_bytes<32>(), s>>>(qkv, out, (int)G, D, scale_log2e);
+  else attention_kernel<64><<<grid, AT_THREADS, attention_smem_bytes<64>(), s>>>(qkv, out, (int)G, D, scale_log2e);
   P3_LAUNCH_CHECK("attention_kernel");
   return P3TOK_OK;
 }

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - tokenized clouds/sec of the point-patch tokenizer (FPS + kNN + gather/normalise + embed).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl p3tok|reference] [--workload c2|c1|c3|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl p3tok|reference] [--workload c2|c2v|c1|c3|c4|c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one pass of the hot path over one batch of synthetic clouds.  Default workload = BASELINE.json
@@ -43,6 +43,9 @@ WORKLOADS = {
                desc="Pix4Point P3Embed 2-stage 1024->256->64, k=32 (BASELINE configs[0])"),
     "c2": dict(family="apf", B=128, N=2048, G=128, k=32, E=384, C=3,
                desc="APF PointNet tokenizer E=384 G=128 k=32 (BASELINE configs[1])"),
+    "c2v": dict(family="apf", vit=True, B=128, N=2048, G=128, k=32, E=384, C=3,
+                desc="APF tokenizer + ViT-S forward: PointNet E=384 G=128 k=32 -> 12 APFViTLayers (12 heads) -> encoder_norm -> "
+                     "token max (BASELINE configs[1] with its ViT tail, SURVEY 8f next #3)"),
     "c3": dict(family="p4p", B=256, N=8192, k=32, embed_dim=256, sample_ratio=1 / 16,
                desc="Pix4Point P3Embed 2-stage 8192->2048->512, k=32 (BASELINE configs[2])"),
     "c4": dict(family="apf", B=16, N=65536, G=2048, k=64, E=384, C=3,
@@ -63,6 +66,10 @@ def algorithmic_work(w):
         as_written = G * k * (2 * C * 256 + 256 * 512 + 512 * E + 6 * E * E)
         pairs = G * N
         byts = 4 * C * N + 4 * G * E
+        if w.get("vit"):      # 12 x (qkv + proj + fc1 + fc2 + adapter down/up) per token + the two attention products per head
+            vit_macs = 12 * (G * (3 * E * E + E * E + 8 * E * E + 2 * E * 64) + 2 * G * G * E)
+            return dict(embed_flops=2 * macs, embed_flops_as_written=2 * as_written, fps_pairs=pairs, knn_pairs=pairs,
+                        compulsory_bytes=4 * C * N + 4 * E, vit_flops=2 * vit_macs)
         return dict(embed_flops=2 * macs, embed_flops_as_written=2 * as_written, fps_pairs=pairs, knn_pairs=pairs,
                     compulsory_bytes=byts)
     n, cin, wd = w["N"], 6, int(w["embed_dim"] // 2)
@@ -99,6 +106,11 @@ def make_inputs(w, seed):
     return x, starts
 
 
+def make_vit_state(w):
+    from p3tok import synth
+    return synth.apf_vit_state(w["E"], 12, 15, 0)
+
+
 def make_state(w):
     from p3tok import synth
     if w["family"] == "apf":
@@ -110,6 +122,13 @@ def build_gpu_model(w, precision, device):
     from p3tok import synth
     from p3tok.modules import P3Embed, PointNet
     sd = synth.to_torch_state(make_state(w))
+    if w.get("vit"):
+        from p3tok.apf_model import AdaptPointFormer
+        net = AdaptPointFormer(num_classes=15, embedding_dim=w["E"], npoint=w["G"], nsample=w["k"], in_channels=w["C"],
+                               precision=precision).eval().to(device)
+        net.point_encoder.encoder.load_state_dict(sd, strict=True)
+        net.load_state_dict(synth.to_torch_state(make_vit_state(w)), strict=False)
+        return net, (lambda x, st: net.features(x, st[0]))
     if w["family"] == "apf":
         net = PointNet(w["E"], w["G"], w["k"], 2 * w["C"], precision=precision).eval().to(device)
         net.encoder.load_state_dict(sd, strict=True)
@@ -128,6 +147,9 @@ def cpu_port_runner(w):
     from oracle import port
     from p3tok import synth
     sd = synth.to_torch_state(make_state(w))
+    if w.get("vit"):
+        vsd = synth.to_torch_state(make_vit_state(w))
+        return lambda x, st: port.apf_vit_features(vsd, port.apf_pointnet(sd, x, w["G"], w["k"], st[0]), 12, 12)
     if w["family"] == "apf":
         return lambda x, st: port.apf_pointnet(sd, x, w["G"], w["k"], st[0])
     return lambda x, st: port.p3embed(sd, x, x.transpose(1, 2).contiguous(), w["k"], 2, st)[1][-1]
@@ -191,7 +213,7 @@ def run_reference(args, w, rank, world):
     """--impl reference: the reference's own CPU implementation of the path (torch-CPU port), rank 0 only."""
     if rank != 0:
         return
-    sample = min(w["B"], {"c2": 16, "c1": 16, "c5": 16, "c3": 2, "c4": 1}[args.workload])
+    sample = min(w["B"], {"c2": 16, "c2v": 16, "c1": 16, "c5": 16, "c3": 2, "c4": 1}[args.workload])
     torch.set_num_threads(os.cpu_count() or 1)
     ww = dict(w, B=sample)
     x, st = make_inputs(ww, 4321)
@@ -397,10 +419,14 @@ def run_p3tok(args, w, rank, world, local_rank):
             "knn_pairs_per_s": (work["knn_pairs"] * B / (stage_ms["knn"] / 1e3)) if stage_ms.get("knn") else None,
             "compulsory_bytes_per_step": work["compulsory_bytes"] * B, "peak_GBps": pk["hbm_gbs"]},
     }
+    if w.get("vit") and stage_ms.get("apf_vit"):
+        line["vit"] = {"ms_per_step": stage_ms["apf_vit"], "algorithmic_flops": work["vit_flops"] * B,
+                       "achieved_tflops": work["vit_flops"] * B / (stage_ms["apf_vit"] / 1e3) / 1e12,
+                       "frac_of_bf16_peak": work["vit_flops"] * B / (stage_ms["apf_vit"] / 1e3) / 1e12 / peak_tf}
     if allgather_ms is not None:
         line["token_allgather_ms"] = allgather_ms
     if world == 1 and not args.no_cpu_baseline:
-        sample = {"c2": 32, "c1": 32, "c5": 32, "c3": 4, "c4": 1}[args.workload]
+        sample = {"c2": 32, "c2v": 32, "c1": 32, "c5": 32, "c3": 4, "c4": 1}[args.workload]
         v, secs = time_cpu_port(w, sample, 2)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"{sample} clouds of the {args.workload} workload, best of 2 after 1 warm-up ({secs:.2f} s per pass)"}

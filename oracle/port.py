@@ -137,6 +137,41 @@ def apf_pointnet(sd: Dict[str, torch.Tensor], x: torch.Tensor, G: int, k: int, s
     return apf_encode(sd, neigh)
 
 
+# --- APF token consumer ----------------------------------------------------
+
+def apf_vit_layer(sd: Dict[str, torch.Tensor], p: str, x: torch.Tensor, heads: int) -> torch.Tensor:
+    """apf_utils.py:268-293 APFViTLayer.forward (eval: DropPath / dropout are the identity), the reference's torch calls in
+    its order: norm1 -> AttentionLayer (133-160) -> residual; AdapterLayer (197-233); norm2 -> Mlp -> sum."""
+    B, N, C = x.shape
+    a = F.layer_norm(x, (C,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], 1e-5)
+    qkv = F.linear(a, sd[p + "attention.qkv.weight"], sd[p + "attention.qkv.bias"])
+    qkv = qkv.reshape(B, N, 3, heads, C // heads).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    attn = (q @ k.transpose(-2, -1)) * (C // heads) ** -0.5
+    attn = attn.softmax(dim=-1)
+    o = (attn @ v).transpose(1, 2).reshape(B, N, C)
+    x = x + F.linear(o, sd[p + "attention.proj.weight"], sd[p + "attention.proj.bias"])
+    residual = x
+    an = F.layer_norm(x, (C,), sd[p + "adapter.adapter_norm.weight"], sd[p + "adapter.adapter_norm.bias"], 1e-5)
+    down = F.relu(F.linear(an, sd[p + "adapter.down_proj.weight"], sd[p + "adapter.down_proj.bias"]))
+    up = F.linear(down, sd[p + "adapter.up_proj.weight"], sd[p + "adapter.up_proj.bias"]) * sd[p + "adapter.scale"]
+    adapt = up + x
+    m = F.layer_norm(x, (C,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-5)
+    m = F.linear(F.gelu(F.linear(m, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"])), sd[p + "mlp.fc2.weight"],
+                 sd[p + "mlp.fc2.bias"])
+    return m + adapt + residual
+
+
+def apf_vit_features(sd: Dict[str, torch.Tensor], tokens: torch.Tensor, depth: int, heads: int) -> torch.Tensor:
+    """apf.py:361-366: the block loop, encoder_norm and the max over tokens -> (B, D)."""
+    x = tokens
+    for i in range(depth):
+        x = apf_vit_layer(sd, f"blocks.{i}.", x, heads)
+    C = x.shape[-1]
+    x = F.layer_norm(x, (C,), sd["encoder_norm.weight"], sd["encoder_norm.bias"], 1e-5)
+    return x.max(-2)[0]
+
+
 # --- Pix4Point tokenizer -----------------------------------------------------------------------
 
 def _bn2(sd, bn: str, h: torch.Tensor) -> torch.Tensor:

@@ -110,3 +110,17 @@ def test_vit_cases(golden_dir, name):
     for mine, key in ((x, "x"), (pooled, "pooled"), (logits, "logits")):
         ref = g[key].astype(np.float64)
         assert np.abs(mine - ref).max() <= 2e-5 * np.abs(ref).max(), key
+
+
+@pytest.mark.parametrize("name", ["vit_small", "vit_hd64"])
+def test_vit_port_matches_golden(golden_dir, name):
+    """oracle/port.py's torch-CPU restatement of the block stack (the timed CPU baseline of bench.py --workload c2v)."""
+    import torch
+    from oracle import port
+    c = cases.VIT_CASES[name]
+    g = _load(golden_dir, name)
+    sd = synth.to_torch_state(synth.apf_vit_state(c["D"], c["depth"], c["classes"], c["seed"]))
+    tok = torch.from_numpy(synth.vit_tokens(c["B"], c["G"], c["D"], c["seed"]))
+    with torch.no_grad():
+        pooled = port.apf_vit_features(sd, tok, c["depth"], c["heads"]).numpy()
+    assert np.abs(pooled - g["pooled"]).max() <= 1e-5 * np.abs(g["pooled"]).max()
