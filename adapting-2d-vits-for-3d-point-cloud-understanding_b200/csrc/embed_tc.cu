@@ -82,6 +82,8 @@ struct TcParams {
   __nv_bfloat16* out_bf16; // [M,N] or null
   float* out_f32;          // [M,N] or null
   int f32_tma;             // out_f32 goes through swizzled 32x32 fp32 boxes + TMA stores (tmC is the fp32 map; no out_bf16)
+  int res_add;             // f32_tma only: the boxes are ADDED to out_f32 by TMA reduce stores (cp.reduce.async.bulk.tensor .add)
+                           // - the in-place residual x += out_scale * value with no load of x in the epilogue
   float* out_max;          // [ceil(M/32), N] max over each 32 consecutive rows, or null
   __nv_bfloat16* out_max_bf16;
   int max_relu;            // apply ReLU to the max (out_relu of the block)
@@ -200,7 +202,11 @@ __device__ __forceinline__ void epilogue_half(const TcParams& p, const float* sb
 #pragma unroll
     for (int j = 0; j < 32; j += 2) gelu_erf2(v[j], v[j + 1]);
   }
-  if (p.residual) {   // fp32 residual stream of the ViT blocks: 128 contiguous bytes per lane (whole sectors)
+  if (p.res_add && p.out_scale != 1.f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
+  }
+  if (p.residual) {   // general residual (not in place): 128 contiguous bytes per lane; the load latency is exposed
     const int nmax = p.N - 4;
     const float* rr = p.residual + (size_t)(row_ok ? row : 0) * p.N;
     float4 r4[8];
@@ -524,10 +530,16 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
-            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                             reinterpret_cast<uint64_t>(&tmC)),
-                         "r"(sbox), "r"(n0), "r"(row0)
-                         : "memory");
+            if (p.res_add)
+              asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                               reinterpret_cast<uint64_t>(&tmC)),
+                           "r"(sbox), "r"(n0), "r"(row0)
+                           : "memory");
+            else
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                               reinterpret_cast<uint64_t>(&tmC)),
+                           "r"(sbox), "r"(n0), "r"(row0)
+                           : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           }
@@ -564,10 +576,16 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0 && n0 + 32 < p.N) {
-            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                             reinterpret_cast<uint64_t>(&tmC)),
-                         "r"(sbox + (uint32_t)TC_STAGING), "r"(n0 + 32), "r"(row0)
-                         : "memory");
+            if (p.res_add)
+              asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                               reinterpret_cast<uint64_t>(&tmC)),
+                           "r"(sbox + (uint32_t)TC_STAGING), "r"(n0 + 32), "r"(row0)
+                           : "memory");
+            else
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                               reinterpret_cast<uint64_t>(&tmC)),
+                           "r"(sbox + (uint32_t)TC_STAGING), "r"(n0 + 32), "r"(row0)
+                           : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
@@ -652,6 +670,7 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
   rc = make_map(&tb, W, N, K, p.BN / p.CL);     // each CTA of a cluster fetches BN/CL rows of the weight tile
   if (rc) return rc;
   p.f32_tma = 0;
+  p.res_add = 0;
   if (out_bf16) {
     rc = make_map(&tc, out_bf16, M, N, 32, ldc);     // store boxes: 64 columns x 32 rows
     if (rc) return rc;
@@ -659,6 +678,11 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
     rc = make_map_f32(&tc, out_f32, M, N, 32);  // fp32 store boxes: 32 columns x 32 rows
     if (rc) return rc;
     p.f32_tma = 1;
+    // in-place residual with unit multiplier: let the TMA unit add the boxes into x instead of loading x in the epilogue
+    if (p.residual && p.residual == out_f32 && p.res_mul == 1.f) {
+      p.res_add = 1;
+      p.residual = nullptr;
+    }
   } else {
     tc = ta;                                     // unused by the kernel
   }

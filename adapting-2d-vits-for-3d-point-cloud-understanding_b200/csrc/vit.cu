@@ -15,9 +15,12 @@
 //   tc_linear             qkv = xh Wqkv'^T + b'                       (tcgen05, bf16 out)      embed_tc.cu
 //   attention_kernel      o  = softmax(q k^T / sqrt(hd)) v            per (cloud, head, 128 query rows)
 //   tc_linear             x  = x + (o Wproj^T + b)                    (fp32 residual epilogue)          apf_utils.py:279-283
-//   ln_rows_kernel        xh = bf16((x - mean) / std)
+//   ln_rows_kernel        xh = bf16((x - mean) / std);  x = 2 x       (adapter's own "+ x" and the layer's, :233 and :292)
 //   tc_linear             hd = [gelu | relu](xh [Wfc1' ; Wdown']^T + b')                                :217-225, :288
-//   tc_linear             x  = 2 x + (hd [Wfc2 | s Wup]^T + b)        (adapter's own "+ x" and the layer's, :233 and :292)
+//   tc_linear             x += hd [Wfc2 | s Wup]^T + b
+// Both residual GEMMs add into x with TMA reduce stores (cp.reduce.async.bulk.tensor .add.f32): the first version loaded
+// x in the epilogue (32 lanes x 128 B rows), and that load's latency - exposed once per 32x32 piece - was most of the
+// kernel (proj: 25 us for 3.4 us of MMA work).
 // then norm_max_kernel: pooled[b] = max over tokens of encoder_norm(x[b]).
 //
 // Attention (sequence 128-196, head dim 32/64: 5 % of the FLOPs, bound by the exp / element-wise work on the scores)
@@ -35,13 +38,13 @@ namespace p3tok {
 constexpr int LN_MAX_V4 = 8;
 
 __global__ void __launch_bounds__(256)
-ln_rows_kernel(const float* __restrict__ x, int64_t M, int D, float eps, const float* __restrict__ w,
-               const float* __restrict__ bvec, __nv_bfloat16* __restrict__ out) {
+ln_rows_kernel(float* __restrict__ x, int64_t M, int D, float eps, const float* __restrict__ w,
+               const float* __restrict__ bvec, __nv_bfloat16* __restrict__ out, float rescale) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int nv = D >> 2;
-  const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+  float4* xr = reinterpret_cast<float4*>(x + row * D);
   float4 v[LN_MAX_V4];
   float s = 0.f;
 #pragma unroll
@@ -49,6 +52,13 @@ ln_rows_kernel(const float* __restrict__ x, int64_t M, int D, float eps, const f
     const int j = lane + 32 * i;
     v[i] = j < nv ? xr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  if (rescale != 1.f) {   // the residual stream leaves this kernel multiplied (the layer's "2 x", see the header comment)
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i) {
+      const int j = lane + 32 * i;
+      if (j < nv) xr[j] = make_float4(v[i].x * rescale, v[i].y * rescale, v[i].z * rescale, v[i].w * rescale);
+    }
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -82,13 +92,14 @@ ln_rows_kernel(const float* __restrict__ x, int64_t M, int D, float eps, const f
 }
 
 // w == nullptr: plain normalisation (the affine lives in the consuming GEMM's weights)
-static int layernorm_bf16(const float* x, int64_t M, int D, float eps, const float* w, const float* b, __nv_bfloat16* out,
-                          cudaStream_t s) {
+// rescale != 1: x is also multiplied in place (x <- rescale * x) after it has been read
+static int layernorm_bf16(float* x, int64_t M, int D, float eps, const float* w, const float* b, __nv_bfloat16* out,
+                          float rescale, cudaStream_t s) {
   P3_REQUIRE(D % 4 == 0 && D > 0 && D <= 128 * LN_MAX_V4, P3TOK_ERR_UNSUPPORTED, "layernorm: D=%d must be a multiple of 4, <= %d", D,
              128 * LN_MAX_V4);
   P3_REQUIRE(x && out && (!w == !b), P3TOK_ERR_INVALID, "layernorm: null pointer");
   if (M == 0) return P3TOK_OK;
-  ln_rows_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(x, M, D, eps, w, b, out);
+  ln_rows_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(x, M, D, eps, w, b, out, rescale);
   P3_LAUNCH_CHECK("ln_rows_kernel");
   return P3TOK_OK;
 }
@@ -419,7 +430,7 @@ extern "C" int64_t p3tok_apf_vit_workspace_bytes(int64_t B, int64_t G, int64_t D
 extern "C" int p3tok_layernorm_bf16(const float* x, int64_t M, int64_t D, float eps, const float* w, const float* b, void* out,
                                     void* stream) {
   P3_REQUIRE(M >= 0 && D > 0, P3TOK_ERR_INVALID, "layernorm: bad shape");
-  return layernorm_bf16(x, M, (int)D, eps, w, b, (__nv_bfloat16*)out, as_stream(stream));
+  return layernorm_bf16(const_cast<float*>(x), M, (int)D, eps, w, b, (__nv_bfloat16*)out, 1.f, as_stream(stream));
 }
 
 extern "C" int p3tok_attention_bf16(const void* qkv, int64_t B, int64_t G, int64_t D, int64_t heads, void* out, void* stream) {
@@ -477,7 +488,7 @@ extern "C" int p3tok_apf_vit_forward(float* x, int64_t B, int64_t G, int64_t D, 
     P3_REQUIRE(w.qkv_w && w.qkv_b && w.proj_w && w.proj_b && w.fc1d_w && w.fc1d_b && w.fc2u_w && w.fc2u_b, P3TOK_ERR_INVALID,
                "apf_vit: layer %lld has a null parameter", (long long)li);
     // attention branch: x += proj(attention(norm1(x)))                                    (apf_utils.py:279-283)
-    if ((rc = layernorm_bf16(x, M, (int)D, eps, nullptr, nullptr, a, s))) return rc;
+    if ((rc = layernorm_bf16(x, M, (int)D, eps, nullptr, nullptr, a, 1.f, s))) return rc;
     if ((rc = linear_wide(a, M, (int)D, (const __nv_bfloat16*)w.qkv_w, (int)(3 * D), w.qkv_b, 0, 0, qkv, s))) return rc;
     if ((rc = attention_bf16(qkv, B, G, (int)D, (int)heads, a, s))) return rc;
     {
@@ -486,11 +497,12 @@ extern "C" int p3tok_apf_vit_forward(float* x, int64_t B, int64_t G, int64_t D, 
       if ((rc = tc_linear_ex(a, M, (int)D, (const __nv_bfloat16*)w.proj_w, (int)D, w.proj_b, 0, ex, nullptr, x, s))) return rc;
     }
     // adapter + MLP on the same x: out = mlp(norm2(x)) + [scale * up(relu(down(adapter_norm(x)))) + x] + x   (:284-292)
-    if ((rc = layernorm_bf16(x, M, (int)D, eps, nullptr, nullptr, a, s))) return rc;
+    // the normalisation pass also leaves 2 x behind, so that the last GEMM, like proj, only ADDS into the stream
+    if ((rc = layernorm_bf16(x, M, (int)D, eps, nullptr, nullptr, a, 2.f, s))) return rc;
     if ((rc = linear_wide(a, M, (int)D, (const __nv_bfloat16*)w.fc1d_w, HR, w.fc1d_b, 1, (int)H, h, s))) return rc;
     {
       TcExtra ex;
-      ex.residual = x; ex.res_mul = 2.f; ex.out_scale = 1.f;
+      ex.residual = x; ex.res_mul = 1.f; ex.out_scale = 1.f;
       if ((rc = tc_linear_ex(h, M, HR, (const __nv_bfloat16*)w.fc2u_w, (int)D, w.fc2u_b, 0, ex, nullptr, x, s))) return rc;
     }
   }

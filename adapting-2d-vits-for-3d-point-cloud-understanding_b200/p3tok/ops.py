@@ -553,7 +553,12 @@ def linear_bf16_ex(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, act: in
                                             0.0, 1.0, out.data_ptr(), None, _stream()), "linear_bf16_ex")
         else:
             res = _f32c("linear_bf16_ex", residual)
-            out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+            if float(res_mul) == 1.0:
+                # the in-place form the ViT stack uses: residual aliases the output, the kernel ADDS into it (TMA reduce)
+                out = res.clone()
+                res = out
+            else:
+                out = torch.empty((M, N), dtype=torch.float32, device=a.device)
             check(_L().p3tok_linear_bf16_ex(a.data_ptr(), M, K, w.data_ptr(), N, bias.data_ptr(), int(act), int(gelu_cols),
                                             res.data_ptr(), float(res_mul), float(out_scale), None, out.data_ptr(), _stream()),
                   "linear_bf16_ex")

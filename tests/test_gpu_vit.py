@@ -65,8 +65,11 @@ def test_linear_epilogues(M, K, N):
             ref = torch.cat([torch.nn.functional.gelu(acc[:, :split]), torch.relu(acc[:, split:])], 1)
             assert ((got - ref).abs() <= 2 ** -8 * ref.abs() + 2e-5 * acc.abs().max()).all()
         res = torch.randn(M, N, device=dev()) * 4
-        got = ops.linear_bf16_ex(a, w, b, 0, 0, res, 2.0, 0.7).double()
+        got = ops.linear_bf16_ex(a, w, b, 0, 0, res, 2.0, 0.7).double()       # general form: the epilogue loads the residual
         ref = 2.0 * res.double() + 0.7 * acc
+        assert (got - ref).abs().max() <= 2e-5 * ref.abs().max()
+        got = ops.linear_bf16_ex(a, w, b, 0, 0, res, 1.0, 0.7).double()       # in-place form: TMA reduce-add into the stream
+        ref = res.double() + 0.7 * acc
         assert (got - ref).abs().max() <= 2e-5 * ref.abs().max()
     else:
         with pytest.raises(RuntimeError):                      # one launch stages at most 2048 bias columns; the stack
