@@ -394,6 +394,10 @@ static VitWs vit_layout(int64_t M, int64_t D, int64_t H, int64_t R) {
 }
 int64_t apf_vit_workspace(int64_t B, int64_t G, int64_t D, int64_t H, int64_t R) { return vit_layout(B * G, D, H, R).total; }
 
+// wide layers whose width is no multiple of 192 or 256 (fc1 + bottleneck: 1600): the least-padding rule of tc_linear would
+// pick 64-column tiles; full-rate 256-column tiles with a partly empty last tile cost less
+static int wide_tile(int n) { return (n > 1024 && n % 192 != 0 && n % 256 != 0) ? 256 : 0; }
+
 // bf16-output GEMM whose N may exceed what one tc_linear launch stages (2048 columns): column slices of the weight
 // matrix write column slices of the output (ViT-B: 3D = 2304, H + R = 3136).  Slices are multiples of 256 columns, so a
 // GELU/ReLU boundary (gelu_cols, a multiple of 64) falls inside at most one slice and is passed relative to it.
@@ -411,7 +415,7 @@ static int linear_wide(const __nv_bfloat16* A, int64_t M, int K, const __nv_bflo
       ex.gelu_cols = gelu_cols - n0 < n ? gelu_cols - n0 : n;
       if (ex.gelu_cols == n) do_relu = 0;
     }
-    if (n > 1024) ex.bn = 256;        // wide layers: full-rate 256-column tiles, a partly empty last tile costs less than narrow ones
+    ex.bn = wide_tile(n);
     int rc = tc_linear_ex(A, M, K, W + (size_t)n0 * K, n, bias + n0, do_relu, ex, out + n0, nullptr, s);
     if (rc) return rc;
   }
@@ -454,6 +458,7 @@ extern "C" int p3tok_linear_bf16_ex(const void* A, int64_t M, int64_t K, const v
   ex.residual = residual;
   ex.res_mul = res_mul;
   ex.out_scale = residual ? out_scale : 1.f;
+  ex.bn = wide_tile((int)N);
   return tc_linear_ex((const __nv_bfloat16*)A, M, (int)K, (const __nv_bfloat16*)W, (int)N, bias, act == 1 || act == 3, ex,
                       (__nv_bfloat16*)out_bf16, out_f32, as_stream(stream));
 }
