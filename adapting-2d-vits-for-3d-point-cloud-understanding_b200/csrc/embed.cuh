@@ -22,6 +22,7 @@ int patch_embed_bf16(const p3tok_rows* rows, const p3tok_mlp* mlp, void* ws, int
 struct TcExtra {
   int gelu = 0;                    // exact GELU after the bias ...
   int gelu_cols = 0;               // ... on columns < gelu_cols (0 = all); `relu` then applies to the remaining columns
+  int epi16 = 0;                   // 16 epilogue warps instead of 8 (bf16-only outputs; small-M GEMMs whose tiles are epilogue-bound)
   int bn = 0;                      // N-tile width override (multiple of 64, <= 256); 0 = least padding
   const float* residual = nullptr; // out_f32 = res_mul * residual + out_scale * value
   float res_mul = 1.f, out_scale = 1.f;

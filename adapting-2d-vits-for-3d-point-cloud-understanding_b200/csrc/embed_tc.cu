@@ -69,6 +69,18 @@ constexpr int TC_EPI_BOXES = P3TOK_EPI_BOXES;        // TMA-store boxes per epil
 constexpr int TC_WARP_SCRATCH = TC_EPI_BOXES * TC_STAGING;   // 1024-aligned store boxes
 constexpr int TC_SGB_BYTES = 256;                    // per-warp 64-float group-bias slice
 constexpr int TC_SMEM_FIXED = TC_EPI_WARPS * (TC_WARP_SCRATCH + TC_SGB_BYTES) + TC_MAX_N * 4 + 512 + 1024;
+// The epilogue-warp count is a template parameter of the kernel: EW = TC_EPI_WARPS (8) for the tokenizer's layers, whose
+// tiles are MMA-bound (16 warps measured -12 % there: registers), EW = 16 for the small-M bf16-output GEMMs of the ViT
+// blocks (vit.cu), whose tile period is the epilogue's (two warps per scheduler issue ~1 instruction per 4-14 cycles).
+template <int EW>
+struct TcCfg {
+  static constexpr int PER_Q = EW / 4;
+  static constexpr int THREADS = 64 + EW * 32 + 32;
+  static constexpr int ARES_WARP = 2 + EW;
+  static constexpr int BOXES = EW > 8 ? 1 : TC_EPI_BOXES;
+  static constexpr int WARP_SCRATCH = BOXES * TC_STAGING;
+  static constexpr int SMEM_FIXED = EW * (WARP_SCRATCH + TC_SGB_BYTES) + TC_MAX_N * 4 + 512 + 1024;
+};
 
 struct TcParams {
   int M, N, K, BN;
@@ -181,6 +193,7 @@ __device__ __forceinline__ void epilogue_affine(float (&v)[32], const TcParams& 
 // 32 accumulator columns (lane = row) starting at global column n0: bias / group bias / ReLU, then any of
 //   - pack to bf16 into this warp's 32 x 128 B staging box (4 x 16-byte pieces, XOR-swizzled by row: conflict-free),
 //   - fp32 store, - max over the warp's 32 rows.
+template <bool LEAN>   // LEAN (16 epilogue warps, ~100 registers): bf16 output only - no fp32 / max / residual / per-row group-bias paths
 __device__ __forceinline__ void epilogue_half(const TcParams& p, const float* sbias, const float* gb, const float* sgb,
                                               uint32_t sbox, int half, int row0, int row, bool row_ok, int lane, int n0,
                                               float (&v)[32]) {
@@ -196,17 +209,17 @@ __device__ __forceinline__ void epilogue_half(const TcParams& p, const float* sb
   // bf16-only outputs take their ReLU from the conversion instruction (F2FP.RELU) instead of 32 FMNMX
   const bool gelu_here = p.gelu && n0 < p.gelu_cols;        // warp-uniform (gelu_cols is a multiple of 32)
   const bool relu_here = p.relu && !gelu_here;
-  const bool relu_in_pack = relu_here && !p.out_f32 && !p.out_max && !p.out_max_bf16;
+  const bool relu_in_pack = relu_here && (LEAN || (!p.out_f32 && !p.out_max && !p.out_max_bf16));
   epilogue_affine(v, p, sbias, gb, n0, relu_here && !relu_in_pack);
   if (gelu_here) {
 #pragma unroll
     for (int j = 0; j < 32; j += 2) gelu_erf2(v[j], v[j + 1]);
   }
-  if (p.res_add && p.out_scale != 1.f) {
+  if (!LEAN && p.res_add && p.out_scale != 1.f) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
   }
-  if (p.residual) {   // general residual (not in place): 128 contiguous bytes per lane; the load latency is exposed
+  if (!LEAN && p.residual) {   // general residual (not in place): 128 contiguous bytes per lane; the load latency is exposed
     const int nmax = p.N - 4;
     const float* rr = p.residual + (size_t)(row_ok ? row : 0) * p.N;
     float4 r4[8];
@@ -242,6 +255,7 @@ __device__ __forceinline__ void epilogue_half(const TcParams& p, const float* sb
       }
     }
   }
+  if (LEAN) return;
   if (p.out_f32 && p.f32_tma) {
     // this half's 32 rows x 32 columns as one 4 KB box (rows of 128 B, 16-byte pieces XOR-swizzled by row): the direct
     // per-thread stores below touch 32 different cache lines per instruction (the group-bias GEMM spent most of its
@@ -275,10 +289,11 @@ __device__ __forceinline__ void epilogue_half(const TcParams& p, const float* sb
   }
 }
 
-template <bool PAIR>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <bool PAIR, int EW>
+__global__ void __launch_bounds__(TcCfg<EW>::THREADS, 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const TcParams p) {
+  using Cfg = TcCfg<EW>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int TC_STAGES = p.stages, STAGE_BYTES = p.stage_bytes;   // stage s starts at s*STAGE_BYTES: A tile (16 KB), then the weight rows
@@ -289,9 +304,9 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sA = smem + ares_bytes;
   uint8_t* sB = sA + (ARES ? 0 : TC_A_STAGE);
   uint8_t* sC = sA + TC_STAGES * p.stage_bytes;       // per-epilogue-warp store staging, 4 KB each
-  float* sgb_all = reinterpret_cast<float*>(sC + TC_EPI_WARPS * TC_WARP_SCRATCH);
-  float* sbias = reinterpret_cast<float*>(sC + TC_EPI_WARPS * (TC_WARP_SCRATCH + TC_SGB_BYTES));
-  uint64_t* full = reinterpret_cast<uint64_t*>(sC + TC_EPI_WARPS * (TC_WARP_SCRATCH + TC_SGB_BYTES) + TC_MAX_N * 4);
+  float* sgb_all = reinterpret_cast<float*>(sC + EW * Cfg::WARP_SCRATCH);
+  float* sbias = reinterpret_cast<float*>(sC + EW * (Cfg::WARP_SCRATCH + TC_SGB_BYTES));
+  uint64_t* full = reinterpret_cast<uint64_t*>(sC + EW * (Cfg::WARP_SCRATCH + TC_SGB_BYTES) + TC_MAX_N * 4);
   uint64_t* empty = full + TC_MAX_STAGES;
   uint64_t* tfull = empty + TC_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
@@ -331,7 +346,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], PAIR ? 2 * TC_EPI_WARPS : TC_EPI_WARPS);   // pair: both CTAs' epilogues report to the leader
+      mbar_init(&tempty[b], PAIR ? 2 * EW : EW);   // pair: both CTAs' epilogues report to the leader
     }
     for (int b = 0; b < TC_MAX_KB; ++b) {
       mbar_init(&a_full[b], 1);
@@ -339,7 +354,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < ((p.N + 63) & ~63); i += TC_THREADS) sbias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;   // zero-padded to 64
+  for (int i = threadIdx.x; i < ((p.N + 63) & ~63); i += Cfg::THREADS) sbias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;   // zero-padded to 64
   if (warp == 1) {   // TMEM: 512 columns = two 128 x BN fp32 accumulators (this CTA's 128 rows)
     if (PAIR) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
@@ -399,7 +414,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == TC_ARES_WARP) {
+  } else if (warp == Cfg::ARES_WARP) {
     // ---------------- A producer (A-resident mode): the M group's activation rows, one 64-column K block at a time.
     // K block kb of the next group is fetched as soon as the last N tile of the current group has consumed it.
     if (ARES) {
@@ -469,7 +484,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {             // ---------------- epilogue warps: TMEM lane quarter q, column-group parity h
     const int ew = warp - 2;
     const int q = warp & 3, h = ew >> 2;
-    uint8_t* stg = sC + ew * TC_WARP_SCRATCH;   // 1024-aligned: the TMA store un-swizzles by address bits
+    uint8_t* stg = sC + ew * Cfg::WARP_SCRATCH;   // 1024-aligned: the TMA store un-swizzles by address bits
     int sbuf = 0;
     // (Fetching the per-warp group-bias slice one column group ahead was measured twice: the 384->768 layer went from
     // 338 to 376 us, the extra live registers and address arithmetic cost more than the hidden L2 round trip.)
@@ -484,19 +499,19 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row0 = mt * TC_BM + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
-      const float* gb = (p.gbias && row_ok) ? p.gbias + (size_t)(row / p.rows_per_group) * p.N : nullptr;
+      const float* gb = (EW <= 8 && p.gbias && row_ok) ? p.gbias + (size_t)(row / p.rows_per_group) * p.N : nullptr;
       bool released = false;
       // per-warp group-bias slice: when a patch (rows_per_group rows) covers whole warps, all 32 rows of this
       // warp share one group-bias row, so the 64 values of a column group are fetched once, coalesced, BEFORE
       // the accumulator load (latency overlaps it) and re-read from shared memory as broadcasts
-      const bool gb_shared = p.gbias && (p.rows_per_group % 32 == 0) && (row0 < p.M);
+      const bool gb_shared = EW <= 8 && p.gbias && (p.rows_per_group % 32 == 0) && (row0 < p.M);
       const float* gb_row = gb_shared ? p.gbias + (size_t)(row0 / p.rows_per_group) * p.N : nullptr;
       float* sgb = sgb_all + ew * (TC_SGB_BYTES / 4);
-      for (int gi = h; gi * 64 < p.BN; gi += TC_EPI_PER_Q) {
+      for (int gi = h; gi * 64 < p.BN; gi += Cfg::PER_Q) {
         const int n0 = nt * p.BN + gi * 64;
         if (n0 >= p.N || row0 >= p.M) break;     // warp-uniform
         const bool tr2 = p.trace2 && blockIdx.x == 0 && ew == 0 && lane == 0;
-        const int g2 = (gi - h) / TC_EPI_PER_Q;
+        const int g2 = (gi - h) / Cfg::PER_Q;
         tc_trace2(p, tr2, it, g2, 0);
         float2 gpre = make_float2(0.f, 0.f);
         if (gb_shared) {
@@ -504,17 +519,17 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           gpre = __ldg(reinterpret_cast<const float2*>(gb_row + c));
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + gi * 64);
-        const bool f32_tma = p.out_f32 && p.f32_tma;   // fp32 output: box 0 / box 1 of this warp = the two 32-column halves
+        const bool f32_tma = EW <= 8 && p.out_f32 && p.f32_tma;   // fp32 output: box 0 / box 1 of this warp = the two 32-column halves
         const uint32_t sbox = f32_tma ? smem_u32(stg) : smem_u32(stg + sbuf * TC_STAGING);
         if (p.out_bf16 || f32_tma) {   // the TMA store issued two groups (fp32: two halves) ago has finished reading this box
           if (lane == 0) {
-            if (TC_EPI_BOXES == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (Cfg::BOXES == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           }
           __syncwarp();
         }
         tc_trace2(p, tr2, it, g2, 1);
-        const bool last = (gi + TC_EPI_PER_Q >= (p.BN >> 6)) || (n0 + 64 * TC_EPI_PER_Q >= p.N);
+        const bool last = (gi + Cfg::PER_Q >= (p.BN >> 6)) || (n0 + 64 * Cfg::PER_Q >= p.N);
         float v[32];
         tc_ld32_issue(taddr, v);
         if (gb_shared) {
@@ -523,7 +538,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         tc_ld_wait();
         tc_trace2(p, tr2, it, g2, 2);
-        epilogue_half(p, sbias, gb_shared ? nullptr : gb, gb_shared ? sgb : nullptr, sbox, 0, row0, row, row_ok, lane, n0, v);
+        epilogue_half<(EW > 8)>(p, sbias, gb_shared ? nullptr : gb, gb_shared ? sgb : nullptr, sbox, 0, row0, row, row_ok, lane, n0, v);
         tc_trace2(p, tr2, it, g2, 3);
         tc_ld32_issue(taddr + 32, v);
         if (f32_tma) {   // store half 0, then make sure box 1 (the previous group's half 1) has been read
@@ -558,7 +573,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           released = true;
         }
-        epilogue_half(p, sbias, gb_shared ? nullptr : gb, gb_shared ? sgb : nullptr, sbox, 1, row0, row, row_ok, lane, n0 + 32, v);
+        epilogue_half<(EW > 8)>(p, sbias, gb_shared ? nullptr : gb, gb_shared ? sgb : nullptr, sbox, 1, row0, row, row_ok, lane, n0 + 32, v);
         tc_trace2(p, tr2, it, g2, 5);
         if (p.out_bf16) {
           // one TMA store of the 32 x 64 bf16 box (clips rows >= M / columns >= N)
@@ -571,7 +586,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          if (TC_EPI_BOXES == 2) sbuf ^= 1;
+          if (Cfg::BOXES == 2) sbuf ^= 1;
         } else if (f32_tma) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
@@ -674,7 +689,7 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
   if (out_bf16) {
     rc = make_map(&tc, out_bf16, M, N, 32, ldc);     // store boxes: 64 columns x 32 rows
     if (rc) return rc;
-  } else if (out_f32 && TC_EPI_BOXES == 2 && N % 4 == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0) {
+  } else if (out_f32 && TcCfg<TC_EPI_WARPS>::BOXES == 2 && N % 4 == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0) {
     rc = make_map_f32(&tc, out_f32, M, N, 32);  // fp32 store boxes: 32 columns x 32 rows
     if (rc) return rc;
     p.f32_tma = 1;
@@ -690,10 +705,17 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
   int dev = 0;
   P3_CUDA(cudaGetDevice(&dev));
   if (dev < 32 && !configured[dev]) {
-    P3_CUDA(cudaFuncSetAttribute(tc_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    P3_CUDA(cudaFuncSetAttribute(tc_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    P3_CUDA(cudaFuncSetAttribute(tc_linear_kernel<false, TC_EPI_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    P3_CUDA(cudaFuncSetAttribute(tc_linear_kernel<true, TC_EPI_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    P3_CUDA(cudaFuncSetAttribute(tc_linear_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    P3_CUDA(cudaFuncSetAttribute(tc_linear_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     configured[dev] = true;
   }
+  // 16 epilogue warps: bf16-only outputs of the ViT blocks (one store box per warp, so no fp32 / max outputs)
+  static int epi16_on = -1;
+  if (epi16_on < 0) { const char* e = getenv("P3TOK_TC_EPI16"); epi16_on = e ? atoi(e) : 1; }
+  const bool ew16 = epi16_on && ex && ex->epi16 && out_bf16 && !out_f32 && !out_max && !out_max_bf16 && !gbias;
+  const int smem_fixed = ew16 ? TcCfg<16>::SMEM_FIXED : TcCfg<TC_EPI_WARPS>::SMEM_FIXED;
   {
     const int wrows = pair ? p.BN / 2 : p.BN;
     // A-resident mode (P3TOK_TC_ARES=0 disables): with several N tiles per M group the default walk re-fetches the same
@@ -705,11 +727,11 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
     const int num_kb = (K + TC_BK - 1) / TC_BK;
     p.ares = 0;
     if (ares_on && pair && p.num_n_tiles >= 2 && num_kb <= TC_MAX_KB) {
-      const int ring = TC_SMEM - TC_SMEM_FIXED - num_kb * TC_A_STAGE;
+      const int ring = TC_SMEM - smem_fixed - num_kb * TC_A_STAGE;
       if (ring / (wrows * TC_BK * 2) >= 3) p.ares = 1;
     }
     p.stage_bytes = (p.ares ? 0 : TC_A_STAGE) + wrows * TC_BK * 2;
-    p.stages = (TC_SMEM - TC_SMEM_FIXED - (p.ares ? num_kb * TC_A_STAGE : 0)) / p.stage_bytes;
+    p.stages = (TC_SMEM - smem_fixed - (p.ares ? num_kb * TC_A_STAGE : 0)) / p.stage_bytes;
     if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
     static int cap = -1;
     if (cap < 0) { const char* e = getenv("P3TOK_TC_STAGES"); cap = e ? atoi(e) : 0; }
@@ -734,7 +756,7 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
   const int clusters = items < max_clusters ? items : max_clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * p.CL));
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3(ew16 ? TcCfg<16>::THREADS : TcCfg<TC_EPI_WARPS>::THREADS);
   cfg.dynamicSmemBytes = TC_SMEM;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -744,8 +766,13 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = p.CL > 1 ? 1 : 0;
-  if (pair) P3_CUDA(cudaLaunchKernelEx(&cfg, tc_linear_kernel<true>, ta, tb, tc, p));
-  else P3_CUDA(cudaLaunchKernelEx(&cfg, tc_linear_kernel<false>, ta, tb, tc, p));
+  if (ew16) {
+    if (pair) P3_CUDA(cudaLaunchKernelEx(&cfg, tc_linear_kernel<true, 16>, ta, tb, tc, p));
+    else P3_CUDA(cudaLaunchKernelEx(&cfg, tc_linear_kernel<false, 16>, ta, tb, tc, p));
+  } else {
+    if (pair) P3_CUDA(cudaLaunchKernelEx(&cfg, tc_linear_kernel<true, TC_EPI_WARPS>, ta, tb, tc, p));
+    else P3_CUDA(cudaLaunchKernelEx(&cfg, tc_linear_kernel<false, TC_EPI_WARPS>, ta, tb, tc, p));
+  }
   count_launch();
   if (trace_on) {   // debug only: synchronises and prints CTA 0's per-tile timeline (cycles relative to its first stamp)
     std::vector<unsigned long long> h(trace_words);

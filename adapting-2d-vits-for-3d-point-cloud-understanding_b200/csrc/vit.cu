@@ -416,6 +416,7 @@ static int linear_wide(const __nv_bfloat16* A, int64_t M, int K, const __nv_bflo
       if (ex.gelu_cols == n) do_relu = 0;
     }
     ex.bn = wide_tile(n);
+    ex.epi16 = 1;
     int rc = tc_linear_ex(A, M, K, W + (size_t)n0 * K, n, bias + n0, do_relu, ex, out + n0, nullptr, s);
     if (rc) return rc;
   }
