@@ -255,12 +255,11 @@ __device__ __forceinline__ void epilogue_half(const TcParams& p, const float* sb
       }
     }
   }
-  if (LEAN) return;
   if (p.out_f32 && p.f32_tma) {
     // this half's 32 rows x 32 columns as one 4 KB box (rows of 128 B, 16-byte pieces XOR-swizzled by row): the direct
     // per-thread stores below touch 32 different cache lines per instruction (the group-bias GEMM spent most of its
     // 38 us in them)
-    const uint32_t rbase = sbox + (uint32_t)half * TC_STAGING + lane * 128;
+    const uint32_t rbase = sbox + (LEAN ? 0u : (uint32_t)half * TC_STAGING) + lane * 128;   // LEAN: one box per warp, both halves
 #pragma unroll
     for (int pc = 0; pc < 8; ++pc) {
       const uint32_t a = rbase + (((uint32_t)pc ^ (lane & 7)) << 4);
@@ -268,13 +267,13 @@ __device__ __forceinline__ void epilogue_half(const TcParams& p, const float* sb
                    "f"(v[4 * pc + 3])
                    : "memory");
     }
-  } else if (p.out_f32 && row_ok) {
+  } else if (!LEAN && p.out_f32 && row_ok) {
     float* o = p.out_f32 + (size_t)row * p.N + n0;
 #pragma unroll
     for (int j = 0; j < 32; j += 4)
       if (n0 + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
   }
-  if (p.out_max || p.out_max_bf16) {
+  if (!LEAN && (p.out_max || p.out_max_bf16)) {
     if (!row_ok) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = -3.0e38f;
@@ -519,7 +518,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           gpre = __ldg(reinterpret_cast<const float2*>(gb_row + c));
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + gi * 64);
-        const bool f32_tma = EW <= 8 && p.out_f32 && p.f32_tma;   // fp32 output: box 0 / box 1 of this warp = the two 32-column halves
+        const bool f32_tma = p.out_f32 && p.f32_tma;   // fp32 output: box 0 / box 1 of this warp = the two 32-column halves
         const uint32_t sbox = f32_tma ? smem_u32(stg) : smem_u32(stg + sbuf * TC_STAGING);
         if (p.out_bf16 || f32_tma) {   // the TMA store issued two groups (fp32: two halves) ago has finished reading this box
           if (lane == 0) {
@@ -556,7 +555,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                            "r"(sbox), "r"(n0), "r"(row0)
                            : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (Cfg::BOXES == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // one box: half 1 overwrites what half 0 just sent
           }
           __syncwarp();
         }
@@ -594,12 +594,12 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (p.res_add)
               asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                                reinterpret_cast<uint64_t>(&tmC)),
-                           "r"(sbox + (uint32_t)TC_STAGING), "r"(n0 + 32), "r"(row0)
+                           "r"(sbox + (Cfg::BOXES == 2 ? (uint32_t)TC_STAGING : 0u)), "r"(n0 + 32), "r"(row0)
                            : "memory");
             else
               asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                                reinterpret_cast<uint64_t>(&tmC)),
-                           "r"(sbox + (uint32_t)TC_STAGING), "r"(n0 + 32), "r"(row0)
+                           "r"(sbox + (Cfg::BOXES == 2 ? (uint32_t)TC_STAGING : 0u)), "r"(n0 + 32), "r"(row0)
                            : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -677,6 +677,10 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
   p.out_scale = ex ? ex->out_scale : 1.f;
   const int64_t ldc = (ex && ex->ldc > 0) ? ex->ldc : N;   // row pitch of out_bf16 (column slices of a wider matrix)
   P3_REQUIRE(ldc == N || (out_bf16 && !out_f32 && ldc % 8 == 0), P3TOK_ERR_UNSUPPORTED, "tc_linear: ldc only for bf16 outputs");
+  // 16 epilogue warps (lean epilogue: bf16 or TMA-stored / TMA-added fp32 outputs only), asked for by the ViT blocks
+  static int epi16_on = -1;
+  if (epi16_on < 0) { const char* e = getenv("P3TOK_TC_EPI16"); epi16_on = e ? atoi(e) : 1; }
+  const bool want16 = epi16_on && ex && ex->epi16 && !out_max && !out_max_bf16 && !gbias && !(out_bf16 && out_f32);
   CUtensorMap ta, tb, tc;
   int rc = make_map(&ta, A, M, K, TC_BM);
   if (rc) return rc;
@@ -689,7 +693,7 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
   if (out_bf16) {
     rc = make_map(&tc, out_bf16, M, N, 32, ldc);     // store boxes: 64 columns x 32 rows
     if (rc) return rc;
-  } else if (out_f32 && TcCfg<TC_EPI_WARPS>::BOXES == 2 && N % 4 == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0) {
+  } else if (out_f32 && (TcCfg<TC_EPI_WARPS>::BOXES == 2 || want16) && N % 4 == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0) {
     rc = make_map_f32(&tc, out_f32, M, N, 32);  // fp32 store boxes: 32 columns x 32 rows
     if (rc) return rc;
     p.f32_tma = 1;
@@ -711,10 +715,7 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
     P3_CUDA(cudaFuncSetAttribute(tc_linear_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     configured[dev] = true;
   }
-  // 16 epilogue warps: bf16-only outputs of the ViT blocks (one store box per warp, so no fp32 / max outputs)
-  static int epi16_on = -1;
-  if (epi16_on < 0) { const char* e = getenv("P3TOK_TC_EPI16"); epi16_on = e ? atoi(e) : 1; }
-  const bool ew16 = epi16_on && ex && ex->epi16 && out_bf16 && !out_f32 && !out_max && !out_max_bf16 && !gbias;
+  const bool ew16 = want16 && (out_bf16 || (p.f32_tma && !p.residual));
   const int smem_fixed = ew16 ? TcCfg<16>::SMEM_FIXED : TcCfg<TC_EPI_WARPS>::SMEM_FIXED;
   {
     const int wrows = pair ? p.BN / 2 : p.BN;

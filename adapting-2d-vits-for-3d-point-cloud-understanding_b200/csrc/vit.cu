@@ -499,7 +499,7 @@ extern "C" int p3tok_apf_vit_forward(float* x, int64_t B, int64_t G, int64_t D, 
     if ((rc = attention_bf16(qkv, B, G, (int)D, (int)heads, a, s))) return rc;
     {
       TcExtra ex;
-      ex.residual = x; ex.res_mul = 1.f; ex.out_scale = 1.f;
+      ex.residual = x; ex.res_mul = 1.f; ex.out_scale = 1.f; ex.epi16 = 1;
       if ((rc = tc_linear_ex(a, M, (int)D, (const __nv_bfloat16*)w.proj_w, (int)D, w.proj_b, 0, ex, nullptr, x, s))) return rc;
     }
     // adapter + MLP on the same x: out = mlp(norm2(x)) + [scale * up(relu(down(adapter_norm(x)))) + x] + x   (:284-292)
@@ -508,7 +508,7 @@ extern "C" int p3tok_apf_vit_forward(float* x, int64_t B, int64_t G, int64_t D, 
     if ((rc = linear_wide(a, M, (int)D, (const __nv_bfloat16*)w.fc1d_w, HR, w.fc1d_b, 1, (int)H, h, s))) return rc;
     {
       TcExtra ex;
-      ex.residual = x; ex.res_mul = 1.f; ex.out_scale = 1.f;
+      ex.residual = x; ex.res_mul = 1.f; ex.out_scale = 1.f; ex.epi16 = 1;
       if ((rc = tc_linear_ex(h, M, HR, (const __nv_bfloat16*)w.fc2u_w, (int)D, w.fc2u_b, 0, ex, nullptr, x, s))) return rc;
     }
   }
