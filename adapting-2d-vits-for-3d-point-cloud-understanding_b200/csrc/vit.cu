@@ -37,56 +37,83 @@ namespace p3tok {
 // variance - what torch computes up to rounding), biased variance, eps inside the square root.
 constexpr int LN_MAX_V4 = 8;
 
+// NV4 = float4 slots per lane (3 for D = 384, 6 for 768, 8 generic); every warp normalises TWO rows per pass, all loads of
+// both rows issued before the first reduction (the kernel is a chain of exposed latencies: load, 2 x 5 shuffles, store).
+template <int NV4>
 __global__ void __launch_bounds__(256)
 ln_rows_kernel(float* __restrict__ x, int64_t M, int D, float eps, const float* __restrict__ w,
                const float* __restrict__ bvec, __nv_bfloat16* __restrict__ out, float rescale) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
+  const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2;
+  if (row0 >= M) return;
   const int nv = D >> 2;
-  float4* xr = reinterpret_cast<float4*>(x + row * D);
-  float4 v[LN_MAX_V4];
-  float s = 0.f;
+  const bool two = row0 + 1 < M;   // warp-uniform
+  float4 v[2][NV4];
+  float s[2] = {0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < LN_MAX_V4; ++i) {
-    const int j = lane + 32 * i;
-    v[i] = j < nv ? xr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  }
-  if (rescale != 1.f) {   // the residual stream leaves this kernel multiplied (the layer's "2 x", see the header comment)
+  for (int r = 0; r < 2; ++r) {
+    float4* xr = reinterpret_cast<float4*>(x + (row0 + (two ? r : 0)) * D);
 #pragma unroll
-    for (int i = 0; i < LN_MAX_V4; ++i) {
+    for (int i = 0; i < NV4; ++i) {
       const int j = lane + 32 * i;
-      if (j < nv) xr[j] = make_float4(v[i].x * rescale, v[i].y * rescale, v[i].z * rescale, v[i].w * rescale);
+      v[r][i] = j < nv ? xr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
 #pragma unroll
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / (float)D;
-  float q = 0.f;
+  for (int r = 0; r < 2; ++r) {
 #pragma unroll
-  for (int i = 0; i < LN_MAX_V4; ++i) {
-    const int j = lane + 32 * i;
-    if (j < nv) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      q += (a * a + b * b) + (c * c + d * d);
-    }
-  }
+    for (int i = 0; i < NV4; ++i) s[r] += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+    if (rescale != 1.f && (r == 0 || two)) {   // the residual stream leaves this kernel multiplied (the layer's "2 x")
+      float4* xr = reinterpret_cast<float4*>(x + (row0 + r) * D);
 #pragma unroll
-  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = 1.f / sqrtf(q / (float)D + eps);
-#pragma unroll
-  for (int i = 0; i < LN_MAX_V4; ++i) {
-    const int j = lane + 32 * i;
-    if (j < nv) {
-      float a = (v[i].x - mean) * rstd, b = (v[i].y - mean) * rstd, c = (v[i].z - mean) * rstd, d = (v[i].w - mean) * rstd;
-      if (w) {   // warp-uniform
-        const float4 ww = reinterpret_cast<const float4*>(w)[j], bb = reinterpret_cast<const float4*>(bvec)[j];
-        a = fmaf(a, ww.x, bb.x); b = fmaf(b, ww.y, bb.y); c = fmaf(c, ww.z, bb.z); d = fmaf(d, ww.w, bb.w);
+      for (int i = 0; i < NV4; ++i) {
+        const int j = lane + 32 * i;
+        if (j < nv) xr[j] = make_float4(v[r][i].x * rescale, v[r][i].y * rescale, v[r][i].z * rescale, v[r][i].w * rescale);
       }
-      __nv_bfloat162 lo = __floats2bfloat162_rn(a, b);
-      __nv_bfloat162 hi = __floats2bfloat162_rn(c, d);
-      reinterpret_cast<uint2*>(out + row * D)[j] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    s[0] += __shfl_xor_sync(0xffffffffu, s[0], o);
+    s[1] += __shfl_xor_sync(0xffffffffu, s[1], o);
+  }
+  const float mean[2] = {s[0] / (float)D, s[1] / (float)D};
+  float q[2] = {0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int j = lane + 32 * i;
+      if (j < nv) {
+        const float a = v[r][i].x - mean[r], b = v[r][i].y - mean[r], c = v[r][i].z - mean[r], d = v[r][i].w - mean[r];
+        q[r] += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    q[0] += __shfl_xor_sync(0xffffffffu, q[0], o);
+    q[1] += __shfl_xor_sync(0xffffffffu, q[1], o);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    if (r == 1 && !two) break;
+    const float rstd = 1.f / sqrtf(q[r] / (float)D + eps);
+    __nv_bfloat16* orow = out + (row0 + r) * D;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int j = lane + 32 * i;
+      if (j < nv) {
+        float a = (v[r][i].x - mean[r]) * rstd, b = (v[r][i].y - mean[r]) * rstd, c = (v[r][i].z - mean[r]) * rstd,
+              d = (v[r][i].w - mean[r]) * rstd;
+        if (w) {   // warp-uniform
+          const float4 ww = reinterpret_cast<const float4*>(w)[j], bb = reinterpret_cast<const float4*>(bvec)[j];
+          a = fmaf(a, ww.x, bb.x); b = fmaf(b, ww.y, bb.y); c = fmaf(c, ww.z, bb.z); d = fmaf(d, ww.w, bb.w);
+        }
+        __nv_bfloat162 lo = __floats2bfloat162_rn(a, b);
+        __nv_bfloat162 hi = __floats2bfloat162_rn(c, d);
+        reinterpret_cast<uint2*>(orow)[j] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      }
     }
   }
 }
@@ -99,7 +126,10 @@ static int layernorm_bf16(float* x, int64_t M, int D, float eps, const float* w,
              128 * LN_MAX_V4);
   P3_REQUIRE(x && out && (!w == !b), P3TOK_ERR_INVALID, "layernorm: null pointer");
   if (M == 0) return P3TOK_OK;
-  ln_rows_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(x, M, D, eps, w, b, out, rescale);
+  const unsigned blocks = (unsigned)((M + 15) / 16);   // 8 warps x 2 rows
+  if (D <= 384) ln_rows_kernel<3><<<blocks, 256, 0, s>>>(x, M, D, eps, w, b, out, rescale);
+  else if (D <= 768) ln_rows_kernel<6><<<blocks, 256, 0, s>>>(x, M, D, eps, w, b, out, rescale);
+  else ln_rows_kernel<LN_MAX_V4><<<blocks, 256, 0, s>>>(x, M, D, eps, w, b, out, rescale);
   P3_LAUNCH_CHECK("ln_rows_kernel");
   return P3TOK_OK;
 }
