@@ -612,28 +612,34 @@ extern "C" int64_t p3tok_knn_workspace_bytes(int64_t B, int64_t N) {
   return kns_layout(B, N).total;
 }
 
-extern "C" int p3tok_knn_sorted(const float* x, int64_t B, int64_t N, int64_t pt_stride, const float* centres, int64_t G,
-                                int64_t k, int mode, void* idx_out, int idx_dtype, float* dist_out, void* workspace,
-                                int64_t workspace_bytes, void* stream) {
-  P3_REQUIRE(B >= 0 && N > 0 && G >= 0 && pt_stride >= 3, P3TOK_ERR_INVALID, "knn_sorted: bad shape");
-  P3_REQUIRE(mode == P3TOK_KNN_APF_SQ || mode == P3TOK_KNN_P4P_CDIST, P3TOK_ERR_INVALID, "knn_sorted: bad mode %d", mode);
-  P3_REQUIRE(idx_dtype == P3TOK_I64 || idx_dtype == P3TOK_I32, P3TOK_ERR_INVALID, "knn_sorted: idx dtype must be i32/i64");
-  P3_REQUIRE(k >= 1 && k <= N, P3TOK_ERR_INVALID, "knn_sorted: k=%lld out of range for N=%lld", (long long)k, (long long)N);
-  P3_REQUIRE(k <= 128, P3TOK_ERR_UNSUPPORTED, "knn_sorted: k=%lld > 128", (long long)k);
-  P3_REQUIRE(N <= KNS_MAX_N, P3TOK_ERR_UNSUPPORTED, "knn_sorted: N=%lld > %d (use p3tok_knn)", (long long)N, KNS_MAX_N);
-  P3_REQUIRE(B < 65536, P3TOK_ERR_UNSUPPORTED, "knn_sorted: B too large");
-  if (B == 0 || G == 0) return P3TOK_OK;
-  P3_REQUIRE(x && centres && idx_out && workspace, P3TOK_ERR_INVALID, "knn_sorted: null pointer");
+// workspace pieces of the sorted variant
+struct KnsPtrs {
+  float4* pts; int* ids; float* bb; int* lut; float* meta;
+};
+static KnsPtrs kns_ptrs(void* workspace, int64_t B, int64_t N) {
   const KnsLayout L = kns_layout(B, N);
-  P3_REQUIRE(workspace_bytes >= L.total, P3TOK_ERR_WORKSPACE, "knn_sorted: workspace %lld < %lld bytes", (long long)workspace_bytes,
-             (long long)L.total);
-  cudaStream_t s = as_stream(stream);
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
-  float4* pts = reinterpret_cast<float4*>(base + L.off_pts);
-  int* ids = reinterpret_cast<int*>(base + L.off_ids);
-  float* bb = reinterpret_cast<float*>(base + L.off_bb);
-  int* lut = reinterpret_cast<int*>(base + L.off_lut);
-  float* meta = reinterpret_cast<float*>(base + L.off_meta);
+  KnsPtrs p;
+  p.pts = reinterpret_cast<float4*>(base + L.off_pts);
+  p.ids = reinterpret_cast<int*>(base + L.off_ids);
+  p.bb = reinterpret_cast<float*>(base + L.off_bb);
+  p.lut = reinterpret_cast<int*>(base + L.off_lut);
+  p.meta = reinterpret_cast<float*>(base + L.off_meta);
+  return p;
+}
+
+// The preparation half (depends on the clouds only, not on the centres: a caller can run it on a second stream while
+// FPS picks the centres) ...
+extern "C" int p3tok_knn_prepare(const float* x, int64_t B, int64_t N, int64_t pt_stride, void* workspace, int64_t workspace_bytes,
+                                 void* stream) {
+  P3_REQUIRE(B >= 0 && N > 0 && pt_stride >= 3, P3TOK_ERR_INVALID, "knn_prepare: bad shape");
+  P3_REQUIRE(N <= KNS_MAX_N, P3TOK_ERR_UNSUPPORTED, "knn_prepare: N=%lld > %d (use p3tok_knn)", (long long)N, KNS_MAX_N);
+  P3_REQUIRE(B < 65536, P3TOK_ERR_UNSUPPORTED, "knn_prepare: B too large");
+  if (B == 0) return P3TOK_OK;
+  P3_REQUIRE(x && workspace, P3TOK_ERR_INVALID, "knn_prepare: null pointer");
+  P3_REQUIRE(workspace_bytes >= kns_layout(B, N).total, P3TOK_ERR_WORKSPACE, "knn_prepare: workspace %lld < %lld bytes",
+             (long long)workspace_bytes, (long long)kns_layout(B, N).total);
+  const KnsPtrs w = kns_ptrs(workspace, B, N);
   int P2 = 32;
   while (P2 < N) P2 <<= 1;
   const int threads = P2 > 1024 ? 1024 : P2;
@@ -645,11 +651,39 @@ extern "C" int p3tok_knn_sorted(const float* x, int64_t B, int64_t N, int64_t pt
     P3_CUDA(cudaFuncSetAttribute(knn_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KNS_MAX_N * 8));
     configured[dev] = true;
   }
-  knn_prep_kernel<<<(unsigned)B, threads, smem, s>>>(x, (int)N, (int)pt_stride, P2, pts, ids, bb, lut, meta);
+  knn_prep_kernel<<<(unsigned)B, threads, smem, as_stream(stream)>>>(x, (int)N, (int)pt_stride, P2, w.pts, w.ids, w.bb, w.lut, w.meta);
   P3_LAUNCH_CHECK("knn_prep_kernel");
+  return P3TOK_OK;
+}
+
+// ... and the query half on a workspace p3tok_knn_prepare has filled for the same (B, N) clouds.
+extern "C" int p3tok_knn_query(const void* workspace, int64_t workspace_bytes, int64_t B, int64_t N, const float* centres, int64_t G,
+                               int64_t k, int mode, void* idx_out, int idx_dtype, float* dist_out, void* stream) {
+  P3_REQUIRE(B >= 0 && N > 0 && G >= 0, P3TOK_ERR_INVALID, "knn_query: bad shape");
+  P3_REQUIRE(mode == P3TOK_KNN_APF_SQ || mode == P3TOK_KNN_P4P_CDIST, P3TOK_ERR_INVALID, "knn_query: bad mode %d", mode);
+  P3_REQUIRE(idx_dtype == P3TOK_I64 || idx_dtype == P3TOK_I32, P3TOK_ERR_INVALID, "knn_query: idx dtype must be i32/i64");
+  P3_REQUIRE(k >= 1 && k <= N, P3TOK_ERR_INVALID, "knn_query: k=%lld out of range for N=%lld", (long long)k, (long long)N);
+  P3_REQUIRE(k <= 128, P3TOK_ERR_UNSUPPORTED, "knn_query: k=%lld > 128", (long long)k);
+  P3_REQUIRE(N <= KNS_MAX_N, P3TOK_ERR_UNSUPPORTED, "knn_query: N=%lld > %d (use p3tok_knn)", (long long)N, KNS_MAX_N);
+  if (B == 0 || G == 0) return P3TOK_OK;
+  P3_REQUIRE(centres && idx_out && workspace, P3TOK_ERR_INVALID, "knn_query: null pointer");
+  P3_REQUIRE(workspace_bytes >= kns_layout(B, N).total, P3TOK_ERR_WORKSPACE, "knn_query: workspace %lld < %lld bytes",
+             (long long)workspace_bytes, (long long)kns_layout(B, N).total);
+  const KnsPtrs w = kns_ptrs(const_cast<void*>(workspace), B, N);
+  cudaStream_t s = as_stream(stream);
   const int i64 = idx_dtype == P3TOK_I64;
   const int64_t total = B * G;
-  if (k <= 32) return knn_sorted_launch<1>(pts, ids, bb, lut, meta, (int)N, centres, (int)G, total, (int)k, mode, idx_out, i64, dist_out, s);
-  if (k <= 64) return knn_sorted_launch<2>(pts, ids, bb, lut, meta, (int)N, centres, (int)G, total, (int)k, mode, idx_out, i64, dist_out, s);
-  return knn_sorted_launch<4>(pts, ids, bb, lut, meta, (int)N, centres, (int)G, total, (int)k, mode, idx_out, i64, dist_out, s);
+  if (k <= 32) return knn_sorted_launch<1>(w.pts, w.ids, w.bb, w.lut, w.meta, (int)N, centres, (int)G, total, (int)k, mode, idx_out, i64, dist_out, s);
+  if (k <= 64) return knn_sorted_launch<2>(w.pts, w.ids, w.bb, w.lut, w.meta, (int)N, centres, (int)G, total, (int)k, mode, idx_out, i64, dist_out, s);
+  return knn_sorted_launch<4>(w.pts, w.ids, w.bb, w.lut, w.meta, (int)N, centres, (int)G, total, (int)k, mode, idx_out, i64, dist_out, s);
+}
+
+extern "C" int p3tok_knn_sorted(const float* x, int64_t B, int64_t N, int64_t pt_stride, const float* centres, int64_t G,
+                                int64_t k, int mode, void* idx_out, int idx_dtype, float* dist_out, void* workspace,
+                                int64_t workspace_bytes, void* stream) {
+  P3_REQUIRE(k >= 1 && k <= N, P3TOK_ERR_INVALID, "knn_sorted: k=%lld out of range for N=%lld", (long long)k, (long long)N);
+  if (B == 0 || G == 0) return P3TOK_OK;
+  int rc = p3tok_knn_prepare(x, B, N, pt_stride, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  return p3tok_knn_query(workspace, workspace_bytes, B, N, centres, G, k, mode, idx_out, idx_dtype, dist_out, stream);
 }

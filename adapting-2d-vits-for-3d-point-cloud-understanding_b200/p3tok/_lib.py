@@ -58,6 +58,8 @@ _SIGNATURES = {
     "p3tok_knn": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _int, _vp, _int, _vp, _vp]),
     "p3tok_knn_workspace_bytes": (_i64, [_i64, _i64]),
     "p3tok_knn_sorted": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _int, _vp, _int, _vp, _vp, _i64, _vp]),
+    "p3tok_knn_prepare": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp]),
+    "p3tok_knn_query": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _int, _vp, _int, _vp, _vp]),
     "p3tok_morton_order": (_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
     "p3tok_apf_group": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "p3tok_group_gather": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp]),

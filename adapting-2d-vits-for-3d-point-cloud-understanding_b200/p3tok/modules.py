@@ -60,9 +60,9 @@ class Group(nn.Module):
 
     def indices(self, x: torch.Tensor, start_idx: Optional[torch.Tensor] = None):
         """(fps_idx (B,G), center (B,G,3), knn_idx (B,G,k), perm (B,G)) - the index half of forward."""
-        fps_idx = ops.fps(x, _start(x, start_idx), self.num_group)
+        fps_idx, ws = ops.fps_with_knn_prepare(x, _start(x, start_idx), self.num_group)   # kNN preparation overlaps FPS
         center = ops.gather_points(x, fps_idx)[..., :3].contiguous() if x.shape[-1] != 3 else ops.gather_points(x, fps_idx)
-        knn_idx = ops.knn(x, center, self.group_size, _lib.KNN_APF_SQ, False, False)[0]
+        knn_idx = ops.knn_query(x, ws, center, self.group_size, _lib.KNN_APF_SQ, False)
         perm = ops.morton_order(center)[0]
         return fps_idx, center, knn_idx, perm
 
@@ -182,9 +182,9 @@ class P3Embed(nn.Module, _FoldedMixin):
             N = N // 4                                           # pix4point.py:174
             G = min(N, int(pts.shape[1]))                        # clamp of farthest_point_sampling (line 23)
             st = None if start_idx is None else start_idx[s]
-            cidx = ops.fps(pts, _start(pts, st), G)
+            cidx, ws = ops.fps_with_knn_prepare(pts, _start(pts, st), G)                   # kNN preparation overlaps FPS
             ctr = ops.gather_points(pts, cidx)
-            kidx = ops.knn(pts, ctr, self.k, _lib.KNN_P4P_CDIST, True, False)[0]
+            kidx = ops.knn_query(pts, ws, ctr, self.k, _lib.KNN_P4P_CDIST, True)
             tok = ops.patch_embed(_lib.ROWS_P4P, pts, feat, None, kidx, None, B * G, self.k, m.tensors(), m.meta(), bf16)
             feat = tok.view(B, G, -1)
             pts = ctr

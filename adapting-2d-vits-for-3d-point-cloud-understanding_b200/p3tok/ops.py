@@ -144,6 +144,7 @@ def _(x, idx):
 
 # --------------------------------------------------------------------------------------------- knn
 _KNN_SORTED = os.environ.get("P3TOK_KNN_SORTED", "1") != "0"
+_OVERLAP = os.environ.get("P3TOK_OVERLAP", "1") != "0"     # FPS and the kNN preparation on two streams (fps_with_knn_prepare)
 
 
 @torch.library.custom_op("p3tok::knn", mutates_args=(), device_types="cuda")
@@ -183,6 +184,80 @@ def _(x, centres, k, mode, int32_out, return_dist):
     B, G = x.shape[0], centres.shape[1]
     return (x.new_empty((B, G, k), dtype=torch.int32 if int32_out else torch.int64),
             x.new_empty((B, G, k) if return_dist else (0,), dtype=torch.float32))
+
+
+@torch.library.custom_op("p3tok::knn_prepare", mutates_args=(), device_types="cuda")
+def knn_prepare(x: torch.Tensor) -> torch.Tensor:
+    """The centre-independent half of the sorted kNN (Z-order sort + block boxes of every cloud) -> workspace bytes;
+    empty when the sorted variant does not apply (N > 8192 or P3TOK_KNN_SORTED=0).  Enqueued on the CURRENT stream:
+    modules run it on a side stream next to FPS."""
+    _need_cuda("knn_prepare", x)
+    x = x if x.dtype == torch.float32 else x.float()
+    x, stride = _point_stride(x)
+    B, N = int(x.shape[0]), int(x.shape[1])
+    ws_bytes = int(_L().p3tok_knn_workspace_bytes(B, N)) if _KNN_SORTED and B > 0 else 0
+    ws = torch.empty(max(ws_bytes, 0), dtype=torch.uint8, device=x.device)
+    if ws_bytes > 0:
+        with torch.cuda.device(x.device), _timed("knn"):
+            check(_L().p3tok_knn_prepare(x.data_ptr(), B, N, stride, ws.data_ptr(), ws_bytes, _stream()), "knn_prepare")
+    return ws
+
+
+@knn_prepare.register_fake
+def _(x):
+    return x.new_empty((0,), dtype=torch.uint8)
+
+
+@torch.library.custom_op("p3tok::knn_query", mutates_args=(), device_types="cuda")
+def knn_query(x: torch.Tensor, ws: torch.Tensor, centres: torch.Tensor, k: int, mode: int, int32_out: bool) -> torch.Tensor:
+    """kNN indices (B,G,k) from a workspace knn_prepare(x) filled (falls back to the plain sweep when it is empty)."""
+    if ws.numel() == 0:
+        return knn(x, centres, k, mode, int32_out, False)[0]
+    _need_cuda("knn_query", x, ws, centres)
+    c = _f32c("knn_query", centres[..., :3])
+    B, N, G = int(x.shape[0]), int(x.shape[1]), int(c.shape[1])
+    if c.dim() != 3 or c.shape[0] != B:
+        raise RuntimeError("p3tok::knn_query: centres must be (B,G,3)")
+    if k > N:
+        raise RuntimeError(f"p3tok::knn: selected index k out of range (k={k} > N={N})")
+    idx = torch.empty((B, G, k), dtype=torch.int32 if int32_out else torch.int64, device=x.device)
+    with torch.cuda.device(x.device), _timed("knn"):
+        check(_L().p3tok_knn_query(ws.data_ptr(), int(ws.numel()), B, N, c.data_ptr(), G, k, mode, idx.data_ptr(),
+                                   _lib.I32 if int32_out else _lib.I64, None, _stream()), "knn_query")
+    return idx
+
+
+@knn_query.register_fake
+def _(x, ws, centres, k, mode, int32_out):
+    return x.new_empty((x.shape[0], centres.shape[1], k), dtype=torch.int32 if int32_out else torch.int64)
+
+
+def fps_with_knn_prepare(x: torch.Tensor, start_idx: torch.Tensor, npoint: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(fps_idx, knn workspace): FPS on the current stream with the kNN preparation of the same clouds on a side stream
+    (both are one-CTA-per-cloud kernels that leave most of every SM idle; the preparation does not need the centres).
+    Fork / join by events, so the pair is capturable into a CUDA graph.  P3TOK_OVERLAP=0 runs them back to back."""
+    if not _OVERLAP:
+        return fps(x, start_idx, npoint), knn_prepare(x)
+    cur = torch.cuda.current_stream(x.device)
+    side = _side_stream(x.device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        ws = knn_prepare(x)
+    idx = fps(x, start_idx, npoint)
+    cur.wait_stream(side)
+    ws.record_stream(cur)
+    return idx, ws
+
+
+_SIDE = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    s = _SIDE.get(key)
+    if s is None:
+        s = _SIDE[key] = torch.cuda.Stream(device=device)
+    return s
 
 
 # ------------------------------------------------------------------------------------------ morton

@@ -90,6 +90,15 @@ P3TOK_API int p3tok_knn_sorted(const float* x, int64_t B, int64_t N, int64_t pt_
                      int64_t G, int64_t k, int mode, void* idx_out, int idx_dtype, float* dist_out,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The two halves of p3tok_knn_sorted as separate calls.  p3tok_knn_prepare depends only on the clouds, so a caller can
+ * enqueue it on a second stream while p3tok_fps picks the centres on the first (p3tok/modules.py does; the two kernels
+ * share the SMs), then p3tok_knn_query - after a stream dependency on the preparation - answers the query from the
+ * workspace.  Same contract and results as p3tok_knn / p3tok_knn_sorted. */
+P3TOK_API int p3tok_knn_prepare(const float* x, int64_t B, int64_t N, int64_t pt_stride, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+P3TOK_API int p3tok_knn_query(const void* workspace, int64_t workspace_bytes, int64_t B, int64_t N, const float* centres,
+                    int64_t G, int64_t k, int mode, void* idx_out, int idx_dtype, float* dist_out, void* stream);
+
 /* ---- a7: Morton order of the centres (src/models/apf_utils.py:66-104, resolution 1024) -------
  * centres (B,G,3) -> perm (B,G) int64 = stable ascending argsort of the 30-bit Z-order code;
  * codes_out optional (B,G) int64.  G <= 8192. */

@@ -265,3 +265,24 @@ def test_sorted_knn_workspace_contract():
     rc = L.p3tok_knn_sorted(x.data_ptr(), 1, 64, 3, x.data_ptr(), 4, 8, 0, idx.data_ptr(), _lib.I64, None, ws.data_ptr(), 16,
                             torch.cuda.current_stream().cuda_stream)
     assert rc == _lib.ERR_WORKSPACE
+
+
+@pytest.mark.parametrize("mode", [oracle.KNN_APF_SQ, oracle.KNN_P4P_CDIST])
+def test_knn_prepare_query_split_and_stream_overlap(mode):
+    """p3tok_knn_prepare + p3tok_knn_query (the halves modules run on two streams) == p3tok_knn, bit for bit; and the
+    overlapped FPS + preparation pair returns what the two calls return back to back."""
+    B, N, G, k = 5, 1500, 70, 24
+    x = to_dev(synth.make_cloud("clustered", B, N, 91, 3))
+    start = to_dev(synth.start_indices(B, N, 91))
+    fidx, ws = ops.fps_with_knn_prepare(x, start, G)
+    assert torch.equal(fidx, ops.fps(x, start, G))
+    ctr = ops.gather_points(x, fidx)
+    got = ops.knn_query(x, ws, ctr, k, mode, mode == oracle.KNN_P4P_CDIST)
+    ref = ops.knn(x, ctr, k, mode, mode == oracle.KNN_P4P_CDIST, False)[0]
+    assert torch.equal(got, ref)
+    assert np.array_equal(got.cpu().numpy().astype(np.int64), oracle.knn(x.cpu().numpy(), ctr.cpu().numpy(), k, mode))
+    big = to_dev(synth.make_cloud("uniform", 1, 9000, 92, 3))          # N > 8192: empty workspace, the sweep answers
+    ws2 = ops.knn_prepare(big)
+    assert ws2.numel() == 0
+    c2 = big[:, :10].contiguous()
+    assert torch.equal(ops.knn_query(big, ws2, c2, 8, mode, False), ops.knn(big, c2, 8, mode, False, False)[0])
