@@ -144,7 +144,7 @@ def _(x, idx):
 
 # --------------------------------------------------------------------------------------------- knn
 _KNN_SORTED = os.environ.get("P3TOK_KNN_SORTED", "1") != "0"
-_OVERLAP = os.environ.get("P3TOK_OVERLAP", "1") != "0"     # FPS and the kNN preparation on two streams (fps_with_knn_prepare)
+_OVERLAP = os.environ.get("P3TOK_OVERLAP", "auto")         # FPS and the kNN preparation on two streams: 0 / 1 / auto
 
 
 @torch.library.custom_op("p3tok::knn", mutates_args=(), device_types="cuda")
@@ -235,8 +235,12 @@ def _(x, ws, centres, k, mode, int32_out):
 def fps_with_knn_prepare(x: torch.Tensor, start_idx: torch.Tensor, npoint: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """(fps_idx, knn workspace): FPS on the current stream with the kNN preparation of the same clouds on a side stream
     (both are one-CTA-per-cloud kernels that leave most of every SM idle; the preparation does not need the centres).
-    Fork / join by events, so the pair is capturable into a CUDA graph.  P3TOK_OVERLAP=0 runs them back to back."""
-    if not _OVERLAP:
+    Fork / join by events, so the pair is capturable into a CUDA graph.  Measured (B200, same box): with one CTA per cloud
+    in each kernel the pair helps only while the two grids fit side by side - c1 (B = 32) 0.319 -> 0.293 ms per step; at
+    c2 (B = 128) the preparation's 1024-thread sort shares SMs with FPS, whose dependent iterations are the critical
+    path, and the step gets slower (0.972 -> 1.012 ms; c5 2.34 -> 2.38) - so "auto" overlaps only when 2 B <= #SMs.
+    P3TOK_OVERLAP=0 / 1 forces back-to-back / overlapped."""
+    if _OVERLAP == "0" or (_OVERLAP != "1" and 2 * int(x.shape[0]) > _sm_count(x.device)):
         return fps(x, start_idx, npoint), knn_prepare(x)
     cur = torch.cuda.current_stream(x.device)
     side = _side_stream(x.device)
@@ -250,6 +254,14 @@ def fps_with_knn_prepare(x: torch.Tensor, start_idx: torch.Tensor, npoint: int) 
 
 
 _SIDE = {}
+_SMS = {}
+
+
+def _sm_count(device) -> int:
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _SMS:
+        _SMS[key] = torch.cuda.get_device_properties(key).multi_processor_count
+    return _SMS[key]
 
 
 def _side_stream(device) -> torch.cuda.Stream:
