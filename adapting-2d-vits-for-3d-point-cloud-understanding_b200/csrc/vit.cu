@@ -27,6 +27,7 @@
 // is a flash-style kernel on warp-level bf16 mma (ldmatrix fragments, fp32 online softmax in the log2 domain with the
 // scale folded into one FFMA per score).
 #include <math.h>
+#include <stdlib.h>
 
 #include "embed.cuh"
 
@@ -384,6 +385,162 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   }
 }
 
+// Persistent form for short sequences (G <= 128: one query block, at most two key blocks - BASELINE config 2): a CTA walks
+// (cloud, head) items, and while it computes item i the whole of item i+1 (Q, K, V: 30 KB at head dim 32) is already in
+// flight into the other half of shared memory.  The non-persistent kernel above pays one exposed L2 round trip per CTA and
+// runs 3.5 rounds of CTAs per SM at config 2 (24 us per layer); here only the first item of a CTA waits.
+template <int HD>
+constexpr int attention_small_smem_bytes() { return 2 * 3 * AT_Q * (HD + 8) * 2; }
+
+template <int HD>
+__global__ void __launch_bounds__(AT_THREADS, HD == 32 ? 3 : 2)
+attention_small_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int G, int D, int heads, int items,
+                       float scale_log2e) {
+  constexpr int KS = HD / 16, DT = HD / 8, RP = HD + 8, CPR = HD / 8;
+  constexpr int BUF = 3 * AT_Q * RP;   // elements per item buffer: Q, K, V of 128 rows each
+  extern __shared__ __align__(16) uint8_t at_smem[];
+  __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(at_smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const size_t ld = (size_t)3 * D;
+  const int nblk = (G + AT_KV - 1) / AT_KV;   // 1 or 2
+  const int kv_rows = nblk * AT_KV;
+  const int q0 = warp * 16;
+  const bool active = q0 < G;
+
+  auto load_item = [&](int item, int buf) {
+    const int b = item / heads, head = item - b * heads;
+    const __nv_bfloat16* base = qkv + (size_t)b * G * ld + (size_t)head * HD;
+    __nv_bfloat16* q = sm + (size_t)buf * BUF;
+    __nv_bfloat16* k = q + AT_Q * RP;
+    __nv_bfloat16* v = k + AT_Q * RP;
+    for (int c = tid; c < AT_Q * CPR; c += AT_THREADS) {
+      const int r = c / CPR, ch = c % CPR;
+      const bool ok = r < G;
+      const __nv_bfloat16* rowp = base + (size_t)(ok ? r : 0) * ld + ch * 8;
+      cp_async16(&q[r * RP + ch * 8], rowp, ok);
+      if (r < kv_rows) {
+        cp_async16(&k[r * RP + ch * 8], rowp + D, ok);
+        cp_async16(&v[r * RP + ch * 8], rowp + 2 * D, ok);
+      }
+    }
+  };
+
+  int buf = 0;
+  if ((int)blockIdx.x < items) load_item(blockIdx.x, 0);
+  cp_async_commit();
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int next = item + gridDim.x;
+    if (next < items) load_item(next, buf ^ 1);   // the other buffer was released by the barrier that ended the previous item
+    cp_async_commit();
+    cp_async_wait<1>();                            // this item's group has landed
+    __syncthreads();
+    const __nv_bfloat16* sQ = sm + (size_t)buf * BUF;
+    const __nv_bfloat16* sKa = sQ + AT_Q * RP;
+    const __nv_bfloat16* sVa = sKa + AT_Q * RP;
+    if (active) {
+      uint32_t qa[KS][4];
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+        ldsm_x4(qa[ks], (uint32_t)__cvta_generic_to_shared(&sQ[(q0 + (lane & 15)) * RP + ks * 16 + (lane >> 4) * 8]));
+      float o[DT][4];
+#pragma unroll
+      for (int i = 0; i < DT; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+      float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+      for (int blk = 0; blk < nblk; ++blk) {
+        const int kv0 = blk * AT_KV;
+        const __nv_bfloat16* sK = sKa + kv0 * RP;
+        const __nv_bfloat16* sV = sVa + kv0 * RP;
+        float sc[AT_KV / 8][4];
+#pragma unroll
+        for (int nt = 0; nt < AT_KV / 8; ++nt) {
+          sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+#pragma unroll
+          for (int k2 = 0; k2 < KS; k2 += 2) {
+            uint32_t kb[4];
+            ldsm_x4(kb, (uint32_t)__cvta_generic_to_shared(&sK[(nt * 8 + (lane & 7)) * RP + k2 * 16 + (lane >> 3) * 8]));
+            mma_bf16_16816(sc[nt], qa[k2], kb[0], kb[1]);
+            mma_bf16_16816(sc[nt], qa[k2 + 1], kb[2], kb[3]);
+          }
+        }
+        if (kv0 + AT_KV > G) {
+#pragma unroll
+          for (int nt = 0; nt < AT_KV / 8; ++nt) {
+            const int col = kv0 + nt * 8 + 2 * t;
+            if (col >= G) sc[nt][0] = sc[nt][2] = -INFINITY;
+            if (col + 1 >= G) sc[nt][1] = sc[nt][3] = -INFINITY;
+          }
+        }
+        float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < AT_KV / 8; ++nt) {
+          bm0 = fmaxf(bm0, fmaxf(sc[nt][0], sc[nt][1]));
+          bm1 = fmaxf(bm1, fmaxf(sc[nt][2], sc[nt][3]));
+        }
+        bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+        bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+        bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+        bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+        const float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);
+        const float c0 = ex2f((m0 - n0) * scale_log2e), c1 = ex2f((m1 - n1) * scale_log2e);
+        m0 = n0; m1 = n1;
+        const float ms0 = -n0 * scale_log2e, ms1 = -n1 * scale_log2e;
+        l0 *= c0; l1 *= c1;
+#pragma unroll
+        for (int i = 0; i < DT; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+#pragma unroll
+        for (int nt = 0; nt < AT_KV / 8; ++nt) {
+          sc[nt][0] = ex2f(fmaf(sc[nt][0], scale_log2e, ms0)); sc[nt][1] = ex2f(fmaf(sc[nt][1], scale_log2e, ms0));
+          sc[nt][2] = ex2f(fmaf(sc[nt][2], scale_log2e, ms1)); sc[nt][3] = ex2f(fmaf(sc[nt][3], scale_log2e, ms1));
+          l0 += sc[nt][0] + sc[nt][1];
+          l1 += sc[nt][2] + sc[nt][3];
+        }
+#pragma unroll
+        for (int kk = 0; kk < AT_KV / 16; ++kk) {
+          uint32_t pa[4];
+          pa[0] = pack2(sc[2 * kk][0], sc[2 * kk][1]);
+          pa[1] = pack2(sc[2 * kk][2], sc[2 * kk][3]);
+          pa[2] = pack2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+          pa[3] = pack2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+#pragma unroll
+          for (int dt = 0; dt < DT; dt += 2) {
+            uint32_t vb[4];
+            ldsm_x4_t(vb, (uint32_t)__cvta_generic_to_shared(
+                              &sV[(kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * RP + (dt + (lane >> 4)) * 8]));
+            mma_bf16_16816(o[dt], pa, vb[0], vb[1]);
+            mma_bf16_16816(o[dt + 1], pa, vb[2], vb[3]);
+          }
+        }
+      }
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      const float i0 = 1.f / l0, i1 = 1.f / l1;
+      const int r0 = q0 + g, r1 = q0 + g + 8;
+      const int b = item / heads, head = item - b * heads;
+      __nv_bfloat16* ob = out + (size_t)b * G * D + (size_t)head * HD;
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) {
+        if (r0 < G) *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * D + dt * 8 + 2 * t) = pack2(o[dt][0] * i0, o[dt][1] * i0);
+        if (r1 < G) *reinterpret_cast<uint32_t*>(ob + (size_t)r1 * D + dt * 8 + 2 * t) = pack2(o[dt][2] * i1, o[dt][3] * i1);
+      }
+    }
+    __syncthreads();   // every warp is done with this buffer: the next iteration prefetches into it
+    buf ^= 1;
+  }
+}
+
+static int num_sms_vit() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 static int attention_bf16(const __nv_bfloat16* qkv, int64_t B, int64_t G, int D, int heads, __nv_bfloat16* out, cudaStream_t s) {
   P3_REQUIRE(heads > 0 && D % heads == 0, P3TOK_ERR_INVALID, "attention: D=%d not divisible by heads=%d", D, heads);
   const int hd = D / heads;
@@ -400,7 +557,22 @@ static int attention_bf16(const __nv_bfloat16* qkv, int64_t B, int64_t G, int D,
   if (dev < 32 && !configured[dev]) {
     P3_CUDA(cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, attention_smem_bytes<32>()));
     P3_CUDA(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attention_smem_bytes<64>()));
+    P3_CUDA(cudaFuncSetAttribute(attention_small_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, attention_small_smem_bytes<32>()));
+    P3_CUDA(cudaFuncSetAttribute(attention_small_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attention_small_smem_bytes<64>()));
     configured[dev] = true;
+  }
+  static int small_on = -1;
+  if (small_on < 0) { const char* e = getenv("P3TOK_ATTN_SMALL"); small_on = e ? atoi(e) : 1; }
+  if (small_on && G <= AT_Q) {   // persistent, next item prefetched
+    const int items = (int)(B * heads);
+    const int slots = num_sms_vit() * (hd == 32 ? 3 : 2);
+    const unsigned nblocks = (unsigned)(items < slots ? items : slots);
+    if (hd == 32)
+      attention_small_kernel<32><<<nblocks, AT_THREADS, attention_small_smem_bytes<32>(), s>>>(qkv, out, (int)G, D, heads, items, scale_log2e);
+    else
+      attention_small_kernel<64><<<nblocks, AT_THREADS, attention_small_smem_bytes<64>(), s>>>(qkv, out, (int)G, D, heads, items, scale_log2e);
+    P3_LAUNCH_CHECK("attention_small_kernel");
+    return P3TOK_OK;
   }
   if (hd == 32) attention_kernel<32><<<grid, AT_THREADS, attention_smem_bytes<32>(), s>>>(qkv, out, (int)G, D, scale_log2e);
   else attention_kernel<64><<<grid, AT_THREADS, attention_smem_bytes<64>(), s>>>(qkv, out, (int)G, D, scale_log2e);
