@@ -46,14 +46,11 @@
 namespace p3tok {
 
 // ------------------------------------------------------------------------------------------------ GEMM
-constexpr int TC_MAX_STAGES = 8, TC_MAX_BN = 256;
+constexpr int TC_MAX_STAGES = 8;
 #ifndef P3TOK_EPI_WARPS
 #define P3TOK_EPI_WARPS 8
 #endif
-constexpr int TC_EPI_WARPS = P3TOK_EPI_WARPS;        // 2 (or 4) warps per TMEM lane quarter, interleaved 64-column groups
-constexpr int TC_EPI_PER_Q = TC_EPI_WARPS / 4;
-constexpr int TC_THREADS = 64 + TC_EPI_WARPS * 32 + 32;   // warp 0 TMA, warp 1 MMA, epilogue warps, last warp = A producer (A-resident mode)
-constexpr int TC_ARES_WARP = 2 + TC_EPI_WARPS;
+constexpr int TC_EPI_WARPS = P3TOK_EPI_WARPS;        // default epilogue-warp count: 2 warps per TMEM lane quarter (see TcCfg below)
 constexpr int TC_MAX_KB = 8;                         // A-resident mode: K <= 512
 constexpr int TC_A_STAGE = TC_BM * TC_BK * 2;        // 16 KB
 constexpr int TC_STAGING = 32 * 128;                 // one 32-row x 64-column bf16 store box (4 KB, 128B-swizzled)
@@ -66,19 +63,17 @@ constexpr int TC_SMEM = 227 * 1024;
 #define P3TOK_EPI_BOXES (P3TOK_EPI_WARPS > 8 ? 1 : 2)
 #endif
 constexpr int TC_EPI_BOXES = P3TOK_EPI_BOXES;        // TMA-store boxes per epilogue warp (2 = double-buffered)
-constexpr int TC_WARP_SCRATCH = TC_EPI_BOXES * TC_STAGING;   // 1024-aligned store boxes
 constexpr int TC_SGB_BYTES = 256;                    // per-warp 64-float group-bias slice
-constexpr int TC_SMEM_FIXED = TC_EPI_WARPS * (TC_WARP_SCRATCH + TC_SGB_BYTES) + TC_MAX_N * 4 + 512 + 1024;
 // The epilogue-warp count is a template parameter of the kernel: EW = TC_EPI_WARPS (8) for the tokenizer's layers, whose
 // tiles are MMA-bound (16 warps measured -12 % there: registers), EW = 16 for the small-M bf16-output GEMMs of the ViT
 // blocks (vit.cu), whose tile period is the epilogue's (two warps per scheduler issue ~1 instruction per 4-14 cycles).
 template <int EW>
 struct TcCfg {
-  static constexpr int PER_Q = EW / 4;
-  static constexpr int THREADS = 64 + EW * 32 + 32;
+  static constexpr int PER_Q = EW / 4;                   // epilogue warps per TMEM lane quarter, interleaved 64-column groups
+  static constexpr int THREADS = 64 + EW * 32 + 32;      // warp 0 TMA, warp 1 MMA, epilogue warps, last warp = A producer (A-resident mode)
   static constexpr int ARES_WARP = 2 + EW;
   static constexpr int BOXES = EW > 8 ? 1 : TC_EPI_BOXES;
-  static constexpr int WARP_SCRATCH = BOXES * TC_STAGING;
+  static constexpr int WARP_SCRATCH = BOXES * TC_STAGING;   // 1024-aligned store boxes
   static constexpr int SMEM_FIXED = EW * (WARP_SCRATCH + TC_SGB_BYTES) + TC_MAX_N * 4 + 512 + 1024;
 };
 

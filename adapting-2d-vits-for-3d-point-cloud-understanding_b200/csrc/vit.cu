@@ -237,6 +237,95 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int HD>
 constexpr int attention_smem_bytes() { return (AT_Q + 4 * AT_KV) * (HD + 8) * 2; }
 
+// One 64-key block of the flash loop for a warp's 16 query rows: scores (raw), ragged-block mask, online softmax in the
+// log2 domain, O += P V.  sK / sV: the block's [key][d] tiles (padded rows of RP elements).  Shared by both kernels.
+template <int HD>
+__device__ __forceinline__ void attention_block(const uint32_t (&qa)[HD / 16][4], const __nv_bfloat16* sK, const __nv_bfloat16* sV,
+                                                int kv0, int G, float scale_log2e, int lane, float (&o)[HD / 8][4], float& m0,
+                                                float& m1, float& l0, float& l1) {
+  constexpr int KS = HD / 16, DT = HD / 8, RP = HD + 8;
+  const int t = lane & 3;
+  float sc[AT_KV / 8][4];
+#pragma unroll
+  for (int nt = 0; nt < AT_KV / 8; ++nt) {
+    sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+#pragma unroll
+    for (int k2 = 0; k2 < KS; k2 += 2) {   // one x4: keys nt*8..+7, d chunks (k2*16, +8, +16, +24) = b0,b1 of two k steps
+      uint32_t kb[4];
+      ldsm_x4(kb, (uint32_t)__cvta_generic_to_shared(&sK[(nt * 8 + (lane & 7)) * RP + k2 * 16 + (lane >> 3) * 8]));
+      mma_bf16_16816(sc[nt], qa[k2], kb[0], kb[1]);
+      mma_bf16_16816(sc[nt], qa[k2 + 1], kb[2], kb[3]);
+    }
+  }
+  if (kv0 + AT_KV > G) {   // ragged last block: keys past G never win the max and contribute 2^-inf = 0
+#pragma unroll
+    for (int nt = 0; nt < AT_KV / 8; ++nt) {
+      const int col = kv0 + nt * 8 + 2 * t;
+      if (col >= G) sc[nt][0] = sc[nt][2] = -INFINITY;
+      if (col + 1 >= G) sc[nt][1] = sc[nt][3] = -INFINITY;
+    }
+  }
+  float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < AT_KV / 8; ++nt) {
+    bm0 = fmaxf(bm0, fmaxf(sc[nt][0], sc[nt][1]));
+    bm1 = fmaxf(bm1, fmaxf(sc[nt][2], sc[nt][3]));
+  }
+  bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+  bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+  bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+  bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+  const float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);   // finite: every block holds at least one valid key
+  const float c0 = ex2f((m0 - n0) * scale_log2e), c1 = ex2f((m1 - n1) * scale_log2e);   // 0 on the first block (m = -inf)
+  m0 = n0; m1 = n1;
+  const float ms0 = -n0 * scale_log2e, ms1 = -n1 * scale_log2e;
+  l0 *= c0; l1 *= c1;
+#pragma unroll
+  for (int i = 0; i < DT; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+#pragma unroll
+  for (int nt = 0; nt < AT_KV / 8; ++nt) {
+    sc[nt][0] = ex2f(fmaf(sc[nt][0], scale_log2e, ms0)); sc[nt][1] = ex2f(fmaf(sc[nt][1], scale_log2e, ms0));
+    sc[nt][2] = ex2f(fmaf(sc[nt][2], scale_log2e, ms1)); sc[nt][3] = ex2f(fmaf(sc[nt][3], scale_log2e, ms1));
+    l0 += sc[nt][0] + sc[nt][1];
+    l1 += sc[nt][2] + sc[nt][3];
+  }
+  // O += P V: the score accumulators of two adjacent key tiles are exactly one A fragment
+#pragma unroll
+  for (int kk = 0; kk < AT_KV / 16; ++kk) {
+    uint32_t pa[4];
+    pa[0] = pack2(sc[2 * kk][0], sc[2 * kk][1]);
+    pa[1] = pack2(sc[2 * kk][2], sc[2 * kk][3]);
+    pa[2] = pack2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+    pa[3] = pack2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+#pragma unroll
+    for (int dt = 0; dt < DT; dt += 2) {   // one x4.trans: keys kk*16 (+8), d tiles dt and dt+1 -> b0,b1 of each
+      uint32_t vb[4];
+      ldsm_x4_t(vb, (uint32_t)__cvta_generic_to_shared(
+                        &sV[(kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * RP + (dt + (lane >> 4)) * 8]));
+      mma_bf16_16816(o[dt], pa, vb[0], vb[1]);
+      mma_bf16_16816(o[dt + 1], pa, vb[2], vb[3]);
+    }
+  }
+}
+
+// normalise by the row sums and store the warp's 16 rows (rows past G are skipped)
+template <int HD>
+__device__ __forceinline__ void attention_store(float (&o)[HD / 8][4], float l0, float l1, __nv_bfloat16* ob, int q0, int G, int D,
+                                                int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  const int r0 = q0 + g, r1 = q0 + g + 8;
+#pragma unroll
+  for (int dt = 0; dt < HD / 8; ++dt) {
+    if (r0 < G) *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * D + dt * 8 + 2 * t) = pack2(o[dt][0] * i0, o[dt][1] * i0);
+    if (r1 < G) *reinterpret_cast<uint32_t*>(ob + (size_t)r1 * D + dt * 8 + 2 * t) = pack2(o[dt][2] * i1, o[dt][3] * i1);
+  }
+}
+
 // qkv (B*G, 3D) bf16: column which*D + head*HD + d (AttentionLayer's reshape(B,N,3,heads,hd), apf_utils.py:143).
 // out (B*G, D) bf16: column head*HD + d ((attn @ v).transpose(1,2).reshape(B,N,C), apf_utils.py:155).
 // grid (ceil(G/128), heads, B).  Q and the K / V blocks are staged row-major in padded shared memory by cp.async, two key
@@ -255,7 +344,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   extern __shared__ __align__(16) uint8_t at_smem[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(at_smem);
   __nv_bfloat16* sKV = sQ + AT_Q * RP;   // buffer j: K at sKV + j * 2 * AT_KV * RP, V right behind it
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int head = blockIdx.y, b = blockIdx.z;
   const int qb = blockIdx.x * AT_Q;
   const int q0 = qb + warp * 16;
@@ -303,86 +392,12 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
       for (int ks = 0; ks < KS; ++ks)   // lanes 0-15: rows 0-15 at column ks*16; lanes 16-31: the same rows at column ks*16 + 8
         ldsm_x4(qa[ks], (uint32_t)__cvta_generic_to_shared(&sQ[(warp * 16 + (lane & 15)) * RP + ks * 16 + (lane >> 4) * 8]));
     }
-    if (active) {
-      float sc[AT_KV / 8][4];
-#pragma unroll
-      for (int nt = 0; nt < AT_KV / 8; ++nt) {
-        sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
-#pragma unroll
-        for (int k2 = 0; k2 < KS; k2 += 2) {   // one x4: keys nt*8..+7, d chunks (k2*16, +8, +16, +24) = b0,b1 of two k steps
-          uint32_t kb[4];
-          ldsm_x4(kb, (uint32_t)__cvta_generic_to_shared(&sK[(nt * 8 + (lane & 7)) * RP + k2 * 16 + (lane >> 3) * 8]));
-          mma_bf16_16816(sc[nt], qa[k2], kb[0], kb[1]);
-          mma_bf16_16816(sc[nt], qa[k2 + 1], kb[2], kb[3]);
-        }
-      }
-      if (kv0 + AT_KV > G) {   // ragged last block: keys past G never win the max and contribute 2^-inf = 0
-#pragma unroll
-        for (int nt = 0; nt < AT_KV / 8; ++nt) {
-          const int col = kv0 + nt * 8 + 2 * t;
-          if (col >= G) sc[nt][0] = sc[nt][2] = -INFINITY;
-          if (col + 1 >= G) sc[nt][1] = sc[nt][3] = -INFINITY;
-        }
-      }
-      float bm0 = -INFINITY, bm1 = -INFINITY;
-#pragma unroll
-      for (int nt = 0; nt < AT_KV / 8; ++nt) {
-        bm0 = fmaxf(bm0, fmaxf(sc[nt][0], sc[nt][1]));
-        bm1 = fmaxf(bm1, fmaxf(sc[nt][2], sc[nt][3]));
-      }
-      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
-      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
-      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
-      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-      const float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);   // finite: every block holds at least one valid key
-      const float c0 = ex2f((m0 - n0) * scale_log2e), c1 = ex2f((m1 - n1) * scale_log2e);   // 0 on the first block (m = -inf)
-      m0 = n0; m1 = n1;
-      const float ms0 = -n0 * scale_log2e, ms1 = -n1 * scale_log2e;
-      l0 *= c0; l1 *= c1;
-#pragma unroll
-      for (int i = 0; i < DT; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
-#pragma unroll
-      for (int nt = 0; nt < AT_KV / 8; ++nt) {
-        sc[nt][0] = ex2f(fmaf(sc[nt][0], scale_log2e, ms0)); sc[nt][1] = ex2f(fmaf(sc[nt][1], scale_log2e, ms0));
-        sc[nt][2] = ex2f(fmaf(sc[nt][2], scale_log2e, ms1)); sc[nt][3] = ex2f(fmaf(sc[nt][3], scale_log2e, ms1));
-        l0 += sc[nt][0] + sc[nt][1];
-        l1 += sc[nt][2] + sc[nt][3];
-      }
-      // O += P V: the score accumulators of two adjacent key tiles are exactly one A fragment
-#pragma unroll
-      for (int kk = 0; kk < AT_KV / 16; ++kk) {
-        uint32_t pa[4];
-        pa[0] = pack2(sc[2 * kk][0], sc[2 * kk][1]);
-        pa[1] = pack2(sc[2 * kk][2], sc[2 * kk][3]);
-        pa[2] = pack2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
-        pa[3] = pack2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
-#pragma unroll
-        for (int dt = 0; dt < DT; dt += 2) {   // one x4.trans: keys kk*16 (+8), d tiles dt and dt+1 -> b0,b1 of each
-          uint32_t vb[4];
-          ldsm_x4_t(vb, (uint32_t)__cvta_generic_to_shared(
-                            &sV[(kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * RP + (dt + (lane >> 4)) * 8]));
-          mma_bf16_16816(o[dt], pa, vb[0], vb[1]);
-          mma_bf16_16816(o[dt + 1], pa, vb[2], vb[3]);
-        }
-      }
-    }
+    if (active) attention_block<HD>(qa, sK, sV, kv0, G, scale_log2e, lane, o, m0, m1, l0, l1);
     __syncthreads();                   // every warp is done with buffer blk & 1
     if (blk + 2 < nblk) load_kv(blk + 2);
     cp_async_commit();                 // one group per iteration keeps the wait_group<1> accounting uniform
   }
-  if (!active) return;
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float i0 = 1.f / l0, i1 = 1.f / l1;
-  const int r0 = q0 + g, r1 = q0 + g + 8;
-  __nv_bfloat16* ob = out + (size_t)b * G * D + (size_t)head * HD;
-#pragma unroll
-  for (int dt = 0; dt < DT; ++dt) {
-    if (r0 < G) *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * D + dt * 8 + 2 * t) = pack2(o[dt][0] * i0, o[dt][1] * i0);
-    if (r1 < G) *reinterpret_cast<uint32_t*>(ob + (size_t)r1 * D + dt * 8 + 2 * t) = pack2(o[dt][2] * i1, o[dt][3] * i1);
-  }
+  if (active) attention_store<HD>(o, l0, l1, out + (size_t)b * G * D + (size_t)head * HD, q0, G, D, lane);
 }
 
 // Persistent form for short sequences (G <= 128: one query block, at most two key blocks - BASELINE config 2): a CTA walks
@@ -400,7 +415,7 @@ attention_small_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
   constexpr int BUF = 3 * AT_Q * RP;   // elements per item buffer: Q, K, V of 128 rows each
   extern __shared__ __align__(16) uint8_t at_smem[];
   __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(at_smem);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t ld = (size_t)3 * D;
   const int nblk = (G + AT_KV - 1) / AT_KV;   // 1 or 2
   const int kv_rows = nblk * AT_KV;
@@ -446,84 +461,10 @@ attention_small_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
 #pragma unroll
       for (int i = 0; i < DT; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
       float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-      for (int blk = 0; blk < nblk; ++blk) {
-        const int kv0 = blk * AT_KV;
-        const __nv_bfloat16* sK = sKa + kv0 * RP;
-        const __nv_bfloat16* sV = sVa + kv0 * RP;
-        float sc[AT_KV / 8][4];
-#pragma unroll
-        for (int nt = 0; nt < AT_KV / 8; ++nt) {
-          sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
-#pragma unroll
-          for (int k2 = 0; k2 < KS; k2 += 2) {
-            uint32_t kb[4];
-            ldsm_x4(kb, (uint32_t)__cvta_generic_to_shared(&sK[(nt * 8 + (lane & 7)) * RP + k2 * 16 + (lane >> 3) * 8]));
-            mma_bf16_16816(sc[nt], qa[k2], kb[0], kb[1]);
-            mma_bf16_16816(sc[nt], qa[k2 + 1], kb[2], kb[3]);
-          }
-        }
-        if (kv0 + AT_KV > G) {
-#pragma unroll
-          for (int nt = 0; nt < AT_KV / 8; ++nt) {
-            const int col = kv0 + nt * 8 + 2 * t;
-            if (col >= G) sc[nt][0] = sc[nt][2] = -INFINITY;
-            if (col + 1 >= G) sc[nt][1] = sc[nt][3] = -INFINITY;
-          }
-        }
-        float bm0 = -INFINITY, bm1 = -INFINITY;
-#pragma unroll
-        for (int nt = 0; nt < AT_KV / 8; ++nt) {
-          bm0 = fmaxf(bm0, fmaxf(sc[nt][0], sc[nt][1]));
-          bm1 = fmaxf(bm1, fmaxf(sc[nt][2], sc[nt][3]));
-        }
-        bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
-        bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
-        bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
-        bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-        const float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);
-        const float c0 = ex2f((m0 - n0) * scale_log2e), c1 = ex2f((m1 - n1) * scale_log2e);
-        m0 = n0; m1 = n1;
-        const float ms0 = -n0 * scale_log2e, ms1 = -n1 * scale_log2e;
-        l0 *= c0; l1 *= c1;
-#pragma unroll
-        for (int i = 0; i < DT; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
-#pragma unroll
-        for (int nt = 0; nt < AT_KV / 8; ++nt) {
-          sc[nt][0] = ex2f(fmaf(sc[nt][0], scale_log2e, ms0)); sc[nt][1] = ex2f(fmaf(sc[nt][1], scale_log2e, ms0));
-          sc[nt][2] = ex2f(fmaf(sc[nt][2], scale_log2e, ms1)); sc[nt][3] = ex2f(fmaf(sc[nt][3], scale_log2e, ms1));
-          l0 += sc[nt][0] + sc[nt][1];
-          l1 += sc[nt][2] + sc[nt][3];
-        }
-#pragma unroll
-        for (int kk = 0; kk < AT_KV / 16; ++kk) {
-          uint32_t pa[4];
-          pa[0] = pack2(sc[2 * kk][0], sc[2 * kk][1]);
-          pa[1] = pack2(sc[2 * kk][2], sc[2 * kk][3]);
-          pa[2] = pack2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
-          pa[3] = pack2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
-#pragma unroll
-          for (int dt = 0; dt < DT; dt += 2) {
-            uint32_t vb[4];
-            ldsm_x4_t(vb, (uint32_t)__cvta_generic_to_shared(
-                              &sV[(kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * RP + (dt + (lane >> 4)) * 8]));
-            mma_bf16_16816(o[dt], pa, vb[0], vb[1]);
-            mma_bf16_16816(o[dt + 1], pa, vb[2], vb[3]);
-          }
-        }
-      }
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-      const float i0 = 1.f / l0, i1 = 1.f / l1;
-      const int r0 = q0 + g, r1 = q0 + g + 8;
+      for (int blk = 0; blk < nblk; ++blk)
+        attention_block<HD>(qa, sKa + blk * AT_KV * RP, sVa + blk * AT_KV * RP, blk * AT_KV, G, scale_log2e, lane, o, m0, m1, l0, l1);
       const int b = item / heads, head = item - b * heads;
-      __nv_bfloat16* ob = out + (size_t)b * G * D + (size_t)head * HD;
-#pragma unroll
-      for (int dt = 0; dt < DT; ++dt) {
-        if (r0 < G) *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * D + dt * 8 + 2 * t) = pack2(o[dt][0] * i0, o[dt][1] * i0);
-        if (r1 < G) *reinterpret_cast<uint32_t*>(ob + (size_t)r1 * D + dt * 8 + 2 * t) = pack2(o[dt][2] * i1, o[dt][3] * i1);
-      }
+      attention_store<HD>(o, l0, l1, out + (size_t)b * G * D + (size_t)head * HD, q0, G, D, lane);
     }
     __syncthreads();   // every warp is done with this buffer: the next iteration prefetches into it
     buf ^= 1;
