@@ -41,3 +41,42 @@ class GraphedTokenizer:
         for dst, src in zip(self.inputs, inputs):
             dst.copy_(src, non_blocking=True)
         return self.replay()
+
+
+class GraphedHostTokenizer:
+    """The whole serving step as ONE CUDA graph on its own stream: pinned host inputs -> device (memcpy nodes) -> the
+    captured module call -> pinned host output.  A step then costs the host one graph launch; two instances replayed
+    alternately on their two streams overlap the copies of one step with the kernels of the other (what bench.py's `e2e`
+    measures).  `host_inputs` are read at every replay (refill them in place); `host_output` is overwritten by the next
+    replay of the same instance - call `synchronize()` (or wait on `done`) before reading it."""
+
+    def __init__(self, fn: Callable[..., torch.Tensor], host_inputs: Sequence[torch.Tensor], device, warmup: int = 3):
+        self.device = torch.device(device)
+        self.host_inputs = [t if t.is_pinned() else t.pin_memory() for t in host_inputs]
+        self.inputs = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in self.host_inputs]
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        self.done = torch.cuda.Event()
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream), torch.no_grad():
+            for _ in range(max(1, warmup)):            # lazy initialisation and the output shape, outside the capture
+                for d, h in zip(self.inputs, self.host_inputs):
+                    d.copy_(h, non_blocking=True)
+                out = fn(*self.inputs)
+        self.stream.synchronize()
+        self.host_output = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+        with torch.no_grad(), torch.cuda.graph(self.graph, stream=self.stream):
+            for d, h in zip(self.inputs, self.host_inputs):
+                d.copy_(h, non_blocking=True)
+            self.output = fn(*self.inputs)
+            self.host_output.copy_(self.output, non_blocking=True)
+
+    def replay(self) -> None:
+        """Enqueue one step on this instance's stream (asynchronous)."""
+        with torch.cuda.stream(self.stream):
+            self.graph.replay()
+            self.done.record()
+
+    def synchronize(self) -> torch.Tensor:
+        self.stream.synchronize()
+        return self.host_output

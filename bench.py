@@ -299,55 +299,29 @@ def run_p3tok(args, w, rank, world, local_rank):
         dev_ms = e0.elapsed_time(e1)
         launches = per_step_launches * args.steps       # kernels of libp3tok.so executed in the timed region
 
-        # ---- e2e: host buffers in, host tokens out, through the public serving API (p3tok.graph.GraphedTokenizer:
-        # the module call captured once into a CUDA graph).  Every step copies the clouds and start indices from
-        # pinned host memory into the graph's input buffers, replays, and copies the tokens back to pinned host
-        # memory; the D2H of step i (copy stream) overlaps the H2D + kernels of step i+1 (two graph instances so
-        # that an output buffer is not overwritten while it is being copied out).
-        copy_stream = torch.cuda.Stream(device=device)
-        h2d_stream = torch.cuda.Stream(device=device)
-        graphs = [GraphedTokenizer(lambda x, *st: run(x, list(st)), [base] + st_pool[0]) for _ in range(2)]
-        out_host = [torch.empty(graphs[0].output.shape, dtype=graphs[0].output.dtype).pin_memory() for _ in range(2)]
-        copied = [torch.cuda.Event() for _ in range(2)]
-        in_free = [torch.cuda.Event() for _ in range(2)]
-
-        def e2e_step(i):
-            # three streams: H2D of step i+1 and D2H of step i-1 overlap the kernels of step i
-            b = i & 1
-            g = graphs[b]
-            with torch.cuda.stream(h2d_stream):
-                h2d_stream.wait_event(in_free[b])                  # the replay that last read these input buffers is done
-                g.inputs[0].copy_(x_host, non_blocking=True)
-                for d, s in zip(g.inputs[1:], st_host):
-                    d.copy_(s, non_blocking=True)
-                ready = torch.cuda.Event()
-                ready.record()
-            cur = torch.cuda.current_stream()
-            cur.wait_event(ready)
-            cur.wait_event(copied[b])                              # output buffer b has been copied out
-            o = g.replay()
-            in_free[b].record()
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(in_free[b])
-                out_host[b].copy_(o, non_blocking=True)
-                copied[b].record()
-
-        for b in range(2):
-            copied[b].record()
-            in_free[b].record()
+        # ---- e2e: host buffers in, host tokens out, through the public serving API (p3tok.graph.GraphedHostTokenizer):
+        # one CUDA graph per step = pinned-host -> device copies of the clouds and start indices, the captured module call,
+        # device -> pinned-host copy of the tokens.  Two instances on two streams are replayed alternately, so the copies
+        # of step i+1 overlap the kernels of step i; the host pays one graph launch per step.
+        from p3tok.graph import GraphedHostTokenizer
+        graphs = [GraphedHostTokenizer(lambda x, *st: run(x, list(st)), [x_host] + st_host, device) for _ in range(2)]
+        out_host = [g.host_output for g in graphs]
         for i in range(4):
-            e2e_step(i)
-        copy_stream.synchronize()
+            graphs[i & 1].replay()
+        for g in graphs:
+            g.synchronize()
         barrier()
         t0 = time.perf_counter()
         for i in range(args.steps):
-            e2e_step(i)
-        copy_stream.synchronize()
+            graphs[i & 1].replay()
+        for g in graphs:
+            g.synchronize()
         barrier()
         e2e_ms = 1e3 * (time.perf_counter() - t0)
-        h2d_stream.synchronize()
+        # the host-to-host graph returns the same tokens as the eager module call on the same clouds
+        assert torch.equal(out_host[0].to(device), run(x_host.to(device), [s.to(device) for s in st_host])), "e2e graph != eager"
         # the graph path returns the same tokens as the eager path
-        assert torch.equal(graphs[0](pool[0], *st_pool[0]), run(pool[0], st_pool[0])), "graph replay != eager"
+        assert torch.equal(gdev(pool[0], *st_pool[0]), run(pool[0], st_pool[0])) if gdev is not None else True, "graph replay != eager"
         clocks = sampler.stop() if rank == 0 else None
 
         # ---- per-stage device times (separate pass, not part of the timed region)
