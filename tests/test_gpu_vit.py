@@ -153,3 +153,23 @@ def test_vit_errors():
         APFViTLayer(64, 2).train().to(dev())(torch.zeros(1, 4, 64, device=dev()))
     with pytest.raises(RuntimeError):
         ops.attention_bf16(torch.zeros(8, 192), 2, 4, 2)     # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("G", [1, 2, 63, 64, 65, 127, 129])
+def test_vit_edge_sequence_lengths(G):
+    """One token, block boundaries of the attention kernels (64-key blocks; 128-row persistent form vs the general one)."""
+    c = dict(B=2, G=G, D=64, heads=2, depth=1, classes=15, seed=70 + G)
+    sd = synth.apf_vit_state(c["D"], 1, 15, c["seed"])
+    tok = synth.vit_tokens(c["B"], G, c["D"], c["seed"])
+    blocks, norm, _ = _stack(c, sd)
+    x, pooled = run_blocks(blocks, to_dev(tok), norm)
+    ox, op, _ = oracle.apf_vit(sd, tok, 1, 2)
+    assert_tokens_close(x.cpu().numpy(), ox, 1e-2, f"G={G} x")
+    assert_tokens_close(pooled.cpu().numpy(), op, 1e-2, f"G={G} pooled")
+
+
+def test_vit_empty_batch():
+    c = dict(B=1, G=4, D=64, heads=2, depth=1, classes=15, seed=69)
+    blocks, norm, _ = _stack(c, synth.apf_vit_state(64, 1, 15, 69))
+    x, pooled = run_blocks(blocks, torch.zeros(0, 4, 64, device=dev()), norm)
+    assert tuple(x.shape) == (0, 4, 64) and tuple(pooled.shape) == (0, 64)
