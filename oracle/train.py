@@ -1,0 +1,102 @@
+"""Training-mode restatement of the APF Encoder (SURVEY.md 8f "next" #4) - TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Groundwork for the next row: float64 numpy forward with batch-statistics BatchNorm (reference src/models/apf.py:129-143 in
+train mode: nn.BatchNorm1d, eps 1e-5, momentum 0.1, biased variance for the normalisation, unbiased for the running
+estimate) and the backward of the whole mini-PointNet through both max-pools and the concat (apf.py:145-169), i.e. what
+autograd computes for `Encoder.forward`.  Pinned against the reference module's own autograd by tests/golden/make_golden.py
+(tests/golden/apf_train.npz) and re-checked against those fixtures by tests/test_oracle_vs_golden.py.  No kernel consumes
+this yet (next #4 "oracle pinned, kernels not started").
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import numpy as np
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def _w(sd, name):
+    w = np.asarray(sd[name + ".weight"], np.float64)
+    return w.reshape(w.shape[0], -1)
+
+
+def _bn_fwd(z, gamma, beta):
+    mu = z.mean(0)
+    var = z.var(0)                       # biased: what the normalisation uses
+    xhat = (z - mu) / np.sqrt(var + BN_EPS)
+    return gamma * xhat + beta, (xhat, var, mu)
+
+
+def _bn_bwd(dy, gamma, cache):
+    xhat, var, _ = cache
+    dgamma = (dy * xhat).sum(0)
+    dbeta = dy.sum(0)
+    dz = gamma / np.sqrt(var + BN_EPS) * (dy - dy.mean(0) - xhat * (dy * xhat).mean(0))
+    return dz, dgamma, dbeta
+
+
+def apf_encoder_train(sd: Dict[str, np.ndarray], neigh: np.ndarray, grad_tokens: np.ndarray):
+    """neigh (B,G,k,cin), grad_tokens (B,G,E) = dL/dtokens.
+    Returns (tokens (B,G,E), grads: dict name -> array incl. "input", running: dict of updated BN running statistics)."""
+    B, G, k, cin = neigh.shape
+    f = lambda n: np.asarray(sd[n], np.float64)
+    X = neigh.reshape(B * G * k, cin).astype(np.float64)
+    R = X.shape[0]
+    W1, W2, W3, W4, W5 = (_w(sd, n) for n in ("first_conv.0", "first_conv.3", "first_conv.6", "second_conv.0", "second_conv.3"))
+    b1, b2, b3, b4, b5 = (f(n + ".bias") for n in ("first_conv.0", "first_conv.3", "first_conv.6", "second_conv.0", "second_conv.3"))
+    g1, be1, g2, be2, g4, be4 = (f(n) for n in ("first_conv.1.weight", "first_conv.1.bias", "first_conv.4.weight", "first_conv.4.bias",
+                                                "second_conv.1.weight", "second_conv.1.bias"))
+    # ---- forward (apf.py:145-169)
+    z1 = X @ W1.T + b1
+    y1, c1 = _bn_fwd(z1, g1, be1)
+    h1 = np.maximum(y1, 0)
+    z2 = h1 @ W2.T + b2
+    y2, c2 = _bn_fwd(z2, g2, be2)
+    h2 = np.maximum(y2, 0)
+    ft = h2 @ W3.T + b3                                  # (R, E)
+    E = ft.shape[1]
+    ftg = ft.reshape(B * G, k, E)
+    arg_g = ftg.argmax(1)                                # first maximum, like torch.max(dim)
+    gl = np.take_along_axis(ftg, arg_g[:, None, :], 1)[:, 0]
+    cat = np.concatenate([np.repeat(gl, k, 0), ft], 1)   # (R, 2E): [global | per-point]
+    z4 = cat @ W4.T + b4
+    y4, c4 = _bn_fwd(z4, g4, be4)
+    h4 = np.maximum(y4, 0)
+    o = h4 @ W5.T + b5
+    og = o.reshape(B * G, k, E)
+    arg_o = og.argmax(1)
+    tokens = np.take_along_axis(og, arg_o[:, None, :], 1)[:, 0]
+    running = {}
+    for name, (_, var, mu) in (("first_conv.1", c1), ("first_conv.4", c2), ("second_conv.1", c4)):
+        running[name + ".running_mean"] = (1 - BN_MOMENTUM) * f(name + ".running_mean") + BN_MOMENTUM * mu
+        running[name + ".running_var"] = (1 - BN_MOMENTUM) * f(name + ".running_var") + BN_MOMENTUM * var * R / (R - 1)
+    # ---- backward
+    gt = grad_tokens.reshape(B * G, E).astype(np.float64)
+    do = np.zeros_like(og)
+    np.put_along_axis(do, arg_o[:, None, :], gt[:, None, :], 1)
+    do = do.reshape(R, E)
+    grads = {"second_conv.3.weight": do.T @ h4, "second_conv.3.bias": do.sum(0)}
+    dy4 = (do @ W5) * (y4 > 0)
+    dz4, grads["second_conv.1.weight"], grads["second_conv.1.bias"] = _bn_bwd(dy4, g4, c4)
+    grads["second_conv.0.weight"] = dz4.T @ cat
+    grads["second_conv.0.bias"] = dz4.sum(0)
+    dcat = dz4 @ W4
+    dgl = dcat[:, :E].reshape(B * G, k, E).sum(1)        # the expanded global feature collects its k copies
+    dftg = dcat[:, E:].reshape(B * G, k, E).copy()
+    add = np.zeros_like(dftg)
+    np.put_along_axis(add, arg_g[:, None, :], dgl[:, None, :], 1)
+    dft = (dftg + add).reshape(R, E)
+    grads["first_conv.6.weight"] = dft.T @ h2
+    grads["first_conv.6.bias"] = dft.sum(0)
+    dy2 = (dft @ W3) * (y2 > 0)
+    dz2, grads["first_conv.4.weight"], grads["first_conv.4.bias"] = _bn_bwd(dy2, g2, c2)
+    grads["first_conv.3.weight"] = dz2.T @ h1
+    grads["first_conv.3.bias"] = dz2.sum(0)
+    dy1 = (dz2 @ W2) * (y1 > 0)
+    dz1, grads["first_conv.1.weight"], grads["first_conv.1.bias"] = _bn_bwd(dy1, g1, c1)
+    grads["first_conv.0.weight"] = dz1.T @ X
+    grads["first_conv.0.bias"] = dz1.sum(0)
+    grads["input"] = (dz1 @ W1).reshape(B, G, k, cin)
+    return tokens.reshape(B, G, E), grads, running

@@ -35,3 +35,8 @@ VIT_CASES = {
     "vit_hd64": dict(B=1, G=70, D=128, heads=2, depth=3, classes=15, seed=52),      # head dim 64
     "vit_s12": dict(B=1, G=128, D=384, heads=12, depth=12, classes=15, seed=53),    # ViT-S geometry of BASELINE config 2
 }
+
+TRAIN_CASES = {
+    # training-mode APF Encoder (batch-statistics BN) + autograd through both max-pools: dict(B, N, C, G, k, E, seed)
+    "apf_train": dict(B=2, N=128, C=3, G=6, k=8, E=32, seed=95),
+}

@@ -224,6 +224,53 @@ def vit_case(ref, name, c):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), x=x.numpy(), pooled=pooled.numpy(), logits=logits.numpy())
 
 
+def train_inputs(c):
+    """(neigh (B,G,k,2C) f32, grad_tokens (B,G,E) f32, encoder state) of a TRAIN_CASES entry (shared with the tests)."""
+    x = synth.make_cloud("uniform", c["B"], c["N"], c["seed"], c["C"])
+    start = synth.start_indices(c["B"], c["N"], c["seed"])
+    sd = synth.apf_encoder_state(c["E"], 2 * c["C"], c["seed"])
+    neigh = oracle.group_apf(x, start, c["G"], c["k"])["neigh"].astype(np.float32)
+    gt = (synth.uniform01(c["seed"], c["B"] * c["G"] * c["E"], 31).reshape(c["B"], c["G"], c["E"]) - 0.5).astype(np.float32)
+    return neigh, gt, sd
+
+
+def train_case(ref, name, c):
+    """Reference Encoder in TRAIN mode (apf.py:114-181): forward with batch statistics, loss = sum(tokens * grad_tokens),
+    autograd.  Stores what the reference returned; asserts oracle/train.py against it."""
+    from oracle import train
+    neigh, gt, sd = train_inputs(c)
+    enc = ref.Encoder(c["E"], 2 * c["C"]).train()
+    enc.load_state_dict(synth.to_torch_state(sd))
+    xt = torch.from_numpy(neigh).requires_grad_(True)
+    tok = enc(xt)
+    (tok * torch.from_numpy(gt)).sum().backward()
+    out = {"tokens": tok.detach().numpy(), "grad.input": xt.grad.numpy()}
+    for n, p_ in enc.named_parameters():
+        out["grad." + n] = p_.grad.numpy()
+    for n, b in enc.named_buffers():
+        if "num_batches" not in n:
+            out["running." + n] = b.numpy()
+    tk, grads, running = train.apf_encoder_train(sd, neigh, gt)
+    scale = max(np.abs(v).max() for k_, v in out.items() if k_.startswith("grad.") and k_.endswith("weight"))
+    worst = np.abs(tk - out["tokens"]).max() / np.abs(out["tokens"]).max()
+    for n, v in grads.items():
+        worst = max(worst, np.abs(v.reshape(out["grad." + n].shape) - out["grad." + n]).max() / scale)
+    for n, v in running.items():
+        worst = max(worst, np.abs(v - out["running." + n]).max() / np.abs(out["running." + n]).max())
+    print(f"{name}: oracle/train.py vs reference autograd: worst error {worst:.2e}")
+    assert worst < 1e-5, name
+    # keep the fixture small: matrices above 20 k elements are stored as their row sums and column sums
+    small = {}
+    for k_, v in out.items():
+        if v.size > 20000:
+            m = v.reshape(v.shape[0], -1)
+            small[k_ + "#rowsum"] = m.sum(1)
+            small[k_ + "#colsum"] = m.sum(0)
+        else:
+            small[k_] = v
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **small)
+
+
 def main():
     assert ref_loader.available(), "reference tree not present"
     ref = ref_loader.load()
@@ -238,6 +285,8 @@ def main():
         head_case(name, c)
     for name, c in cases.VIT_CASES.items():
         vit_case(ref, name, c)
+    for name, c in cases.TRAIN_CASES.items():
+        train_case(ref, name, c)
 
 
 if __name__ == "__main__":

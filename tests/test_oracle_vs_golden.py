@@ -124,3 +124,31 @@ def test_vit_port_matches_golden(golden_dir, name):
     with torch.no_grad():
         pooled = port.apf_vit_features(sd, tok, c["depth"], c["heads"]).numpy()
     assert np.abs(pooled - g["pooled"]).max() <= 1e-5 * np.abs(g["pooled"]).max()
+
+
+@pytest.mark.parametrize("name", list(cases.TRAIN_CASES))
+def test_train_mode_oracle(golden_dir, name):
+    """Groundwork for SURVEY 8f next #4: oracle/train.py (batch-statistics BN forward + backward through both max-pools)
+    against what the reference Encoder's own autograd returned."""
+    from oracle import train
+    c = cases.TRAIN_CASES[name]
+    g = _load(golden_dir, name)
+    x = synth.make_cloud("uniform", c["B"], c["N"], c["seed"], c["C"])
+    start = synth.start_indices(c["B"], c["N"], c["seed"])
+    sd = synth.apf_encoder_state(c["E"], 2 * c["C"], c["seed"])
+    neigh = oracle.group_apf(x, start, c["G"], c["k"])["neigh"].astype(np.float32)
+    gt = (synth.uniform01(c["seed"], c["B"] * c["G"] * c["E"], 31).reshape(c["B"], c["G"], c["E"]) - 0.5).astype(np.float32)
+    tokens, grads, running = train.apf_encoder_train(sd, neigh, gt)
+    assert np.abs(tokens - g["tokens"]).max() <= 1e-5 * np.abs(g["tokens"]).max()
+    scale = max(np.abs(g[k_]).max() for k_ in g.files if k_.startswith("grad.") and k_.endswith("weight"))
+    for n, v in grads.items():                      # biases in front of a BatchNorm have (numerically) zero gradient
+        if "grad." + n in g.files:
+            ref = g["grad." + n]
+            assert np.abs(v.reshape(ref.shape) - ref).max() <= 1e-5 * scale, n
+        else:                                       # large matrices are stored as row sums and column sums
+            m = v.reshape(v.shape[0], -1)
+            for proj, mine in (("#rowsum", m.sum(1)), ("#colsum", m.sum(0))):
+                ref = g["grad." + n + proj]
+                assert np.abs(mine - ref).max() <= 1e-5 * max(np.abs(ref).max(), scale), n + proj
+    for n, v in running.items():
+        assert np.abs(v - g["running." + n]).max() <= 1e-5 * np.abs(g["running." + n]).max(), n
