@@ -100,3 +100,82 @@ def apf_encoder_train(sd: Dict[str, np.ndarray], neigh: np.ndarray, grad_tokens:
     grads["first_conv.0.bias"] = dz1.sum(0)
     grads["input"] = (dz1 @ W1).reshape(B, G, k, cin)
     return tokens.reshape(B, G, E), grads, running
+
+
+def p3embed_stage_train(sd: Dict[str, np.ndarray], s: int, rows: np.ndarray, grad_out: np.ndarray):
+    """One P3Embed stage in train mode on its gathered rows (reference src/models/pix4point.py:179-188 with the BatchNorm2d
+    layers of 135-156 on batch statistics).  rows (B,G,k,Cin) = [grouped xyz || grouped feats], grad_out (B,G,W) = dL/d(stage
+    output, channel-last).  Returns (out (B,G,W), grads: dict name -> array incl. "rows", running statistics).
+    conv1 = Conv2d(Cin,W, no bias) -> Conv2d(W,W, bias) -> BN -> ReLU;  conv2 = Conv2d(2W,2W, no bias) -> BN -> ReLU ->
+    Conv2d(2W,W, no bias) -> BN -> ReLU;  pools are max over k."""
+    B, G, k, cin = rows.shape
+    f = lambda n: np.asarray(sd[n], np.float64)
+    pre = f"convs.{s}."
+    Wa, Wb = _w(sd, pre + "0.0"), _w(sd, pre + "0.1")
+    bb = f(pre + "0.1.bias")
+    Wc, Wd = _w(sd, pre + "1.0"), _w(sd, pre + "1.3")
+    g1, be1 = f(pre + "0.2.weight"), f(pre + "0.2.bias")
+    g2, be2 = f(pre + "1.1.weight"), f(pre + "1.1.bias")
+    g3, be3 = f(pre + "1.4.weight"), f(pre + "1.4.bias")
+    X = rows.reshape(B * G * k, cin).astype(np.float64)
+    R = X.shape[0]
+    a = X @ Wa.T                                         # no bias, no activation (pix4point.py:139)
+    z1 = a @ Wb.T + bb
+    y1, c1 = _bn_fwd(z1, g1, be1)
+    f1 = np.maximum(y1, 0)
+    W = f1.shape[1]
+    f1g = f1.reshape(B * G, k, W)
+    arg_g = f1g.argmax(1)
+    gl = np.take_along_axis(f1g, arg_g[:, None, :], 1)[:, 0]
+    cat = np.concatenate([np.repeat(gl, k, 0), f1], 1)
+    z2 = cat @ Wc.T
+    y2, c2 = _bn_fwd(z2, g2, be2)
+    h2 = np.maximum(y2, 0)
+    z3 = h2 @ Wd.T
+    y3, c3 = _bn_fwd(z3, g3, be3)
+    h3 = np.maximum(y3, 0)
+    h3g = h3.reshape(B * G, k, W)
+    arg_o = h3g.argmax(1)
+    out = np.take_along_axis(h3g, arg_o[:, None, :], 1)[:, 0]
+    running = {}
+    for name, (_, var, mu) in ((pre + "0.2", c1), (pre + "1.1", c2), (pre + "1.4", c3)):
+        running[name + ".running_mean"] = (1 - BN_MOMENTUM) * f(name + ".running_mean") + BN_MOMENTUM * mu
+        running[name + ".running_var"] = (1 - BN_MOMENTUM) * f(name + ".running_var") + BN_MOMENTUM * var * R / (R - 1)
+    # ---- backward
+    go = grad_out.reshape(B * G, W).astype(np.float64)
+    dh3 = np.zeros_like(h3g)
+    np.put_along_axis(dh3, arg_o[:, None, :], go[:, None, :], 1)
+    dy3 = dh3.reshape(R, W) * (y3 > 0)
+    grads = {}
+    dz3, grads[pre + "1.4.weight"], grads[pre + "1.4.bias"] = _bn_bwd(dy3, g3, c3)
+    grads[pre + "1.3.weight"] = dz3.T @ h2
+    dy2 = (dz3 @ Wd) * (y2 > 0)
+    dz2, grads[pre + "1.1.weight"], grads[pre + "1.1.bias"] = _bn_bwd(dy2, g2, c2)
+    grads[pre + "1.0.weight"] = dz2.T @ cat
+    dcat = dz2 @ Wc
+    dgl = dcat[:, :W].reshape(B * G, k, W).sum(1)
+    df1 = dcat[:, W:].reshape(B * G, k, W).copy()
+    add = np.zeros_like(df1)
+    np.put_along_axis(add, arg_g[:, None, :], dgl[:, None, :], 1)
+    dy1 = (df1 + add).reshape(R, W) * (y1 > 0)
+    dz1, grads[pre + "0.2.weight"], grads[pre + "0.2.bias"] = _bn_bwd(dy1, g1, c1)
+    grads[pre + "0.1.weight"] = dz1.T @ a
+    grads[pre + "0.1.bias"] = dz1.sum(0)
+    da = dz1 @ Wb
+    grads[pre + "0.0.weight"] = da.T @ X
+    grads["rows"] = (da @ Wa).reshape(B, G, k, cin)
+    return out.reshape(B, G, W), grads, running
+
+
+def scatter_rows_grad(drows: np.ndarray, knn_idx: np.ndarray, N: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Gradient of the gather (pix4point.py:92-102): drows (B,G,k,3+D) -> (d points (B,N,3), d feats (B,N,D)), each point
+    collecting the gradients of every neighbourhood it appears in."""
+    B = drows.shape[0]
+    D = drows.shape[-1] - 3
+    dp, df = np.zeros((B, N, 3)), np.zeros((B, N, D))
+    for b in range(B):
+        idx = np.asarray(knn_idx[b]).reshape(-1)
+        flat = drows[b].reshape(-1, 3 + D)
+        np.add.at(dp[b], idx, flat[:, :3])
+        np.add.at(df[b], idx, flat[:, 3:])
+    return dp, df

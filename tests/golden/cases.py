@@ -36,6 +36,11 @@ VIT_CASES = {
     "vit_s12": dict(B=1, G=128, D=384, heads=12, depth=12, classes=15, seed=53),    # ViT-S geometry of BASELINE config 2
 }
 
+P4P_TRAIN_CASES = {
+    # training-mode P3Embed (1 stage) through the reference's own forward + autograd: dict(B, N, k, W, seed)
+    "p4p_train": dict(B=2, N=64, k=8, W=32, seed=96),
+}
+
 TRAIN_CASES = {
     # training-mode APF Encoder (batch-statistics BN) + autograd through both max-pools: dict(B, N, C, G, k, E, seed)
     "apf_train": dict(B=2, N=128, C=3, G=6, k=8, E=32, seed=95),

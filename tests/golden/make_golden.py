@@ -271,6 +271,49 @@ def train_case(ref, name, c):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **small)
 
 
+def p4p_train_inputs(c):
+    x = synth.make_cloud("uniform", c["B"], c["N"], c["seed"], 3)
+    start = synth.start_indices(c["B"], c["N"], c["seed"], 0)
+    sd = synth.p3embed_state(3, 0.25, 4, 4, c["W"], c["seed"])
+    G = c["N"] // 4
+    go = (synth.uniform01(c["seed"], c["B"] * G * c["W"], 33).reshape(c["B"], G, c["W"]) - 0.5).astype(np.float32)
+    return x, start, sd, go
+
+
+def p4p_train_case(ref, name, c):
+    """Reference P3Embed.forward in TRAIN mode (pix4point.py:166-191, 1 stage) + autograd; loss = sum(out * grad_out)."""
+    from oracle import train
+    x, start, sd, go = p4p_train_inputs(c)
+    m = ref.P3Embed(in_channels=3, sample_ratio=0.25, scale=4, k=c["k"], layers=4, embed_dim=c["W"]).train()
+    m.load_state_dict(synth.to_torch_state(sd))
+    p = torch.from_numpy(x).requires_grad_(True)
+    fe = torch.from_numpy(np.ascontiguousarray(x.transpose(0, 2, 1))).requires_grad_(True)
+    with forced_randint([start]):
+        _, fs = m(p, fe)
+    (fs[-1].transpose(1, 2) * torch.from_numpy(go)).sum().backward()
+    out = {"out": fs[-1].detach().transpose(1, 2).numpy(), "grad.p": p.grad.numpy(), "grad.f": fe.grad.transpose(1, 2).numpy()}
+    for n, q in m.named_parameters():
+        out["grad." + n] = q.grad.numpy()
+    for n, b in m.named_buffers():
+        if "num_batches" not in n:
+            out["running." + n] = b.numpy()
+    _, _, _, kidx = oracle.p3embed_stage(sd, 0, x, x.copy(), start, c["k"])
+    rows = np.concatenate([oracle.gather_points(x, kidx), oracle.gather_points(x, kidx)], -1)
+    o, grads, running = train.p3embed_stage_train(sd, 0, rows, go)
+    dp, df = train.scatter_rows_grad(grads["rows"], kidx, c["N"])
+    scale = max(np.abs(v).max() for k_, v in out.items() if k_.startswith("grad.convs") and k_.endswith("weight"))
+    worst = max(np.abs(o - out["out"]).max() / np.abs(out["out"]).max(), np.abs(dp - out["grad.p"]).max() / np.abs(out["grad.p"]).max(),
+                np.abs(df - out["grad.f"]).max() / np.abs(out["grad.f"]).max())
+    for n, v in grads.items():
+        if n != "rows":
+            worst = max(worst, np.abs(v.reshape(out["grad." + n].shape) - out["grad." + n]).max() / scale)
+    for n, v in running.items():
+        worst = max(worst, np.abs(v - out["running." + n]).max() / np.abs(out["running." + n]).max())
+    print(f"{name}: oracle/train.py vs reference P3Embed autograd: worst error {worst:.2e}")
+    assert worst < 1e-5, name
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+
+
 def main():
     assert ref_loader.available(), "reference tree not present"
     ref = ref_loader.load()
@@ -287,6 +330,8 @@ def main():
         vit_case(ref, name, c)
     for name, c in cases.TRAIN_CASES.items():
         train_case(ref, name, c)
+    for name, c in cases.P4P_TRAIN_CASES.items():
+        p4p_train_case(ref, name, c)
 
 
 if __name__ == "__main__":

@@ -152,3 +152,29 @@ def test_train_mode_oracle(golden_dir, name):
                 assert np.abs(mine - ref).max() <= 1e-5 * max(np.abs(ref).max(), scale), n + proj
     for n, v in running.items():
         assert np.abs(v - g["running." + n]).max() <= 1e-5 * np.abs(g["running." + n]).max(), n
+
+
+@pytest.mark.parametrize("name", list(cases.P4P_TRAIN_CASES))
+def test_p3embed_train_mode_oracle(golden_dir, name):
+    """oracle/train.py's P3Embed stage (train-mode BN, backward through both pools, the concat and the gather) against the
+    reference P3Embed.forward + autograd."""
+    from oracle import train
+    c = cases.P4P_TRAIN_CASES[name]
+    g = _load(golden_dir, name)
+    x = synth.make_cloud("uniform", c["B"], c["N"], c["seed"], 3)
+    start = synth.start_indices(c["B"], c["N"], c["seed"], 0)
+    sd = synth.p3embed_state(3, 0.25, 4, 4, c["W"], c["seed"])
+    G = c["N"] // 4
+    go = (synth.uniform01(c["seed"], c["B"] * G * c["W"], 33).reshape(c["B"], G, c["W"]) - 0.5).astype(np.float32)
+    _, _, _, kidx = oracle.p3embed_stage(sd, 0, x, x.copy(), start, c["k"])
+    rows = np.concatenate([oracle.gather_points(x, kidx), oracle.gather_points(x, kidx)], -1)
+    out, grads, running = train.p3embed_stage_train(sd, 0, rows, go)
+    dp, df = train.scatter_rows_grad(grads["rows"], kidx, c["N"])
+    for mine, key in ((out, "out"), (dp, "grad.p"), (df, "grad.f")):
+        assert np.abs(mine - g[key]).max() <= 1e-5 * np.abs(g[key]).max(), key
+    scale = max(np.abs(g[k_]).max() for k_ in g.files if k_.startswith("grad.convs") and k_.endswith("weight"))
+    for n, v in grads.items():
+        if n != "rows":
+            assert np.abs(v.reshape(g["grad." + n].shape) - g["grad." + n]).max() <= 1e-5 * scale, n
+    for n, v in running.items():
+        assert np.abs(v - g["running." + n]).max() <= 1e-5 * np.abs(g["running." + n]).max(), n
