@@ -11,21 +11,22 @@
 //   [fc1 ; down_proj] (N = H + R) whose epilogue applies GELU to the first H columns and ReLU to the last R, and
 //   [fc2 | scale * up_proj] (K = H + R) consumes that matrix whole: x_out = 2 x + [h | dn] [Wfc2 | s Wup]^T + b.
 // Data flow per layer (M = B*G rows, fp32 residual stream x updated in place, bf16 activations in the workspace):
-//   ln_rows_kernel        xh = bf16((x - mean) / std)
-//   tc_linear             qkv = xh Wqkv'^T + b'                       (tcgen05, bf16 out)      embed_tc.cu
-//   attention_kernel      o  = softmax(q k^T / sqrt(hd)) v            per (cloud, head, 128 query rows)
-//   tc_linear             x  = x + (o Wproj^T + b)                    (fp32 residual epilogue)          apf_utils.py:279-283
-//   ln_rows_kernel        xh = bf16((x - mean) / std);  x = 2 x       (adapter's own "+ x" and the layer's, :233 and :292)
-//   tc_linear             hd = [gelu | relu](xh [Wfc1' ; Wdown']^T + b')                                :217-225, :288
-//   tc_linear             x += hd [Wfc2 | s Wup]^T + b
+//   ln_rows_kernel          xh = bf16((x - mean) / std)
+//   tc_linear               qkv = xh Wqkv'^T + b'                     (tcgen05, bf16 out, 16 epilogue warps)   embed_tc.cu
+//   attention_small_kernel  o  = softmax(q k^T / sqrt(hd)) v          (G <= 128: persistent over (cloud, head) items;
+//   / attention_kernel                                                 longer sequences: one CTA per 128 query rows)
+//   tc_linear               x += o Wproj^T + b                        (TMA reduce-add epilogue)          apf_utils.py:279-283
+//   ln_rows_kernel          xh = bf16((x - mean) / std);  x = 2 x     (adapter's own "+ x" and the layer's, :233 and :292)
+//   tc_linear               hd = [gelu | relu](xh [Wfc1' ; Wdown']^T + b')                               :217-225, :288
+//   tc_linear               x += hd [Wfc2 | s Wup]^T + b
+// then norm_max_kernel: pooled[b] = max over tokens of encoder_norm(x[b]).
 // Both residual GEMMs add into x with TMA reduce stores (cp.reduce.async.bulk.tensor .add.f32): the first version loaded
 // x in the epilogue (32 lanes x 128 B rows), and that load's latency - exposed once per 32x32 piece - was most of the
 // kernel (proj: 25 us for 3.4 us of MMA work).
-// then norm_max_kernel: pooled[b] = max over tokens of encoder_norm(x[b]).
 //
 // Attention (sequence 128-196, head dim 32/64: 5 % of the FLOPs, bound by the exp / element-wise work on the scores)
 // is a flash-style kernel on warp-level bf16 mma (ldmatrix fragments, fp32 online softmax in the log2 domain with the
-// scale folded into one FFMA per score).
+// scale folded into one FFMA per score).  Measurements and what bounds each kernel: DESIGN.md 6c.
 #include <math.h>
 #include <stdlib.h>
 
