@@ -14,10 +14,14 @@
 //   rows_gather_p4p_bf16_kernel / rows_gather_bf16_kernel
 //                            wide inputs (P3Embed stage >= 1, cin = 131) are gathered to a zero-padded bf16 row matrix
 //                            for the tensor cores.
-//   tc_linear_kernel<PAIR>   C = act(A W^T + bias + group_bias).  Persistent, warp-specialised:
+//   tc_linear_kernel<PAIR, EW>  C = act(A W^T + bias + group_bias).  Persistent, warp-specialised:
 //                              warp 0   TMA producer (warp-uniform loop, one elected lane issues)
 //                              warp 1   tcgen05.mma issuer, descriptors in uniform registers
-//                              warps 2-9 epilogue, two per TMEM lane quarter;  warp 10  A producer (A-resident mode)
+//                              warps 2..EW+1 epilogue, EW/4 per TMEM lane quarter;  last warp  A producer (A-resident mode)
+//                            EW = 8 for the tokenizer's layers; EW = 16 with a lean epilogue (bf16 or TMA-stored fp32 only)
+//                            for the small-M GEMMs of the ViT blocks (vit.cu), whose extra epilogues live here too: exact
+//                            GELU (one MUFU), [gelu | relu] column split, fp32 residual as a TMA reduce-add, column-slice
+//                            outputs (TcExtra, embed.cuh).
 //                            PAIR = cta_group::2: two CTAs of a cluster share one 256 x BN tile - each holds its 128
 //                            rows of A, HALF of the weight tile and its half of the accumulator; the leader issues the
 //                            MMAs, TMA loads of both CTAs signal the leader's barrier, tcgen05.commit multicasts the slot
