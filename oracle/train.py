@@ -179,3 +179,93 @@ def scatter_rows_grad(drows: np.ndarray, knn_idx: np.ndarray, N: int) -> Tuple[n
         np.add.at(dp[b], idx, flat[:, :3])
         np.add.at(df[b], idx, flat[:, 3:])
     return dp, df
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Backward THROUGH the (frozen) ViT block stack: what the tokenizer's Encoder needs from the layers above it when the
+# reference trains (apf.py:335-346 keeps the blocks frozen but the gradient still flows through them).  dX only, plus the
+# trainable encoder_norm.  Dropout / DropPath are taken at p = 0 (they are random in the reference's train mode).
+
+def _erf(x):
+    from scipy.special import erf
+    return erf(x)
+
+
+def _ln_fwd(x, w, b, eps=1e-5):
+    mu = x.mean(-1, keepdims=True)
+    var = ((x - mu) ** 2).mean(-1, keepdims=True)
+    rstd = 1.0 / np.sqrt(var + eps)
+    xhat = (x - mu) * rstd
+    return xhat * w + b, (xhat, rstd)
+
+
+def _ln_bwd(dy, w, cache):
+    xhat, rstd = cache
+    dxhat = dy * w
+    dx = rstd * (dxhat - dxhat.mean(-1, keepdims=True) - xhat * (dxhat * xhat).mean(-1, keepdims=True))
+    return dx, (dy * xhat).reshape(-1, xhat.shape[-1]).sum(0), dy.reshape(-1, xhat.shape[-1]).sum(0)
+
+
+def apf_vit_layer_fwd_bwd(sd: Dict[str, np.ndarray], p: str, x: np.ndarray, heads: int):
+    """Forward of one APFViTLayer (apf_utils.py:268-293, dropout 0) returning the output and a closure dY -> dX."""
+    f = lambda k: np.asarray(sd[p + k], np.float64)
+    B, G, D = x.shape
+    hd = D // heads
+    a, c_n1 = _ln_fwd(x, f("norm1.weight"), f("norm1.bias"))
+    Wq, bq, Wp, bp = f("attention.qkv.weight"), f("attention.qkv.bias"), f("attention.proj.weight"), f("attention.proj.bias")
+    qkv = (a @ Wq.T + bq).reshape(B, G, 3, heads, hd).transpose(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    s = (q @ k.transpose(0, 1, 3, 2)) * hd ** -0.5
+    e = np.exp(s - s.max(-1, keepdims=True))
+    P = e / e.sum(-1, keepdims=True)
+    o = (P @ v).transpose(0, 2, 1, 3).reshape(B, G, D)
+    x1 = x + (o @ Wp.T + bp)
+    an, c_an = _ln_fwd(x1, f("adapter.adapter_norm.weight"), f("adapter.adapter_norm.bias"))
+    Wd, bd, Wu, bu = f("adapter.down_proj.weight"), f("adapter.down_proj.bias"), f("adapter.up_proj.weight"), f("adapter.up_proj.bias")
+    sc = float(np.asarray(sd[p + "adapter.scale"]).reshape(-1)[0])
+    zd = an @ Wd.T + bd
+    dn = np.maximum(zd, 0)
+    n2, c_n2 = _ln_fwd(x1, f("norm2.weight"), f("norm2.bias"))
+    W1, b1, W2, b2 = f("mlp.fc1.weight"), f("mlp.fc1.bias"), f("mlp.fc2.weight"), f("mlp.fc2.bias")
+    z1 = n2 @ W1.T + b1
+    cdf = 0.5 * (1.0 + _erf(z1 / np.sqrt(2.0)))
+    h = z1 * cdf
+    y = (h @ W2.T + b2) + ((dn @ Wu.T + bu) * sc + x1) + x1
+
+    def backward(dy):
+        dx1 = 2.0 * dy                                                    # adapter's "+ x" and the layer's
+        dh = dy @ W2
+        dz1 = dh * (cdf + z1 * np.exp(-0.5 * z1 * z1) / np.sqrt(2.0 * np.pi))
+        dx1 = dx1 + _ln_bwd(dz1 @ W1, f("norm2.weight"), c_n2)[0]
+        dzd = ((dy * sc) @ Wu) * (zd > 0)
+        dx1 = dx1 + _ln_bwd(dzd @ Wd, f("adapter.adapter_norm.weight"), c_an)[0]
+        do = (dx1 @ Wp).reshape(B, G, heads, hd).transpose(0, 2, 1, 3)    # (B,h,G,hd)
+        dP = do @ v.transpose(0, 1, 3, 2)
+        dv = P.transpose(0, 1, 3, 2) @ do
+        ds = P * (dP - (dP * P).sum(-1, keepdims=True)) * hd ** -0.5
+        dq = ds @ k
+        dk = ds.transpose(0, 1, 3, 2) @ q
+        dqkv = np.stack([dq, dk, dv], 0).transpose(1, 3, 0, 2, 4).reshape(B, G, 3 * D)
+        return dx1 + _ln_bwd(dqkv @ Wq, f("norm1.weight"), c_n1)[0]
+
+    return y, backward
+
+
+def apf_vit_backward(sd: Dict[str, np.ndarray], tokens: np.ndarray, depth: int, heads: int, grad_pooled: np.ndarray):
+    """Blocks (frozen) -> encoder_norm (trainable) -> max over tokens (apf.py:361-366): returns (pooled (B,D), d tokens (B,G,D),
+    {"encoder_norm.weight": ..., "encoder_norm.bias": ...}) for dL/dpooled = grad_pooled."""
+    x = tokens.astype(np.float64)
+    backs = []
+    for i in range(depth):
+        x, bw = apf_vit_layer_fwd_bwd(sd, f"blocks.{i}.", x, heads)
+        backs.append(bw)
+    w, b = np.asarray(sd["encoder_norm.weight"], np.float64), np.asarray(sd["encoder_norm.bias"], np.float64)
+    yn, c = _ln_fwd(x, w, b)
+    arg = yn.argmax(1)                                                    # (B, D)
+    pooled = np.take_along_axis(yn, arg[:, None, :], 1)[:, 0]
+    dyn = np.zeros_like(yn)
+    np.put_along_axis(dyn, arg[:, None, :], grad_pooled.astype(np.float64)[:, None, :], 1)
+    dx, dw, db = _ln_bwd(dyn, w, c)
+    for bw in reversed(backs):
+        dx = bw(dx)
+    return pooled, dx, {"encoder_norm.weight": dw, "encoder_norm.bias": db}

@@ -314,6 +314,36 @@ def p4p_train_case(ref, name, c):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
 
 
+def vit_train_case(ref, name, c):
+    """The reference's APFViTLayer stack (dropout / DropPath at 0: they are random in train mode) + nn.LayerNorm + max over
+    tokens (apf.py:361-366) under autograd: gradient of sum(pooled * grad_pooled) w.r.t. the tokens and the encoder_norm."""
+    import torch.nn as nn
+    from oracle import train
+    sd = synth.apf_vit_state(c["D"], c["depth"], 15, c["seed"])
+    tsd = synth.to_torch_state(sd)
+    blocks = nn.Sequential(*[ref.apf_utils.APFViTLayer(dim=c["D"], num_heads=c["heads"], drop_path=0.0, dropout=0.0)
+                             for _ in range(c["depth"])]).train()
+    blocks.load_state_dict({k[len("blocks."):]: v for k, v in tsd.items() if k.startswith("blocks.")})
+    norm = nn.LayerNorm(c["D"]).train()
+    norm.load_state_dict({"weight": tsd["encoder_norm.weight"], "bias": tsd["encoder_norm.bias"]})
+    tok = synth.vit_tokens(c["B"], c["G"], c["D"], c["seed"])
+    gp = (synth.uniform01(c["seed"], c["B"] * c["D"], 35).reshape(c["B"], c["D"]) - 0.5).astype(np.float32)
+    x = torch.from_numpy(tok).requires_grad_(True)
+    h = x
+    for i in range(c["depth"]):
+        h = blocks[i](h)
+    pooled = norm(h).max(-2)[0]
+    (pooled * torch.from_numpy(gp)).sum().backward()
+    po, dx, g = train.apf_vit_backward(sd, tok, c["depth"], c["heads"], gp)
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+    worst = max(rel(po, pooled.detach().numpy()), rel(dx, x.grad.numpy()), rel(g["encoder_norm.weight"], norm.weight.grad.numpy()),
+                rel(g["encoder_norm.bias"], norm.bias.grad.numpy()))
+    print(f"{name}: oracle/train.py vs reference autograd through the block stack: worst error {worst:.2e}")
+    assert worst < 1e-5, name
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), pooled=pooled.detach().numpy(), grad_tokens=x.grad.numpy(),
+                        grad_norm_w=norm.weight.grad.numpy(), grad_norm_b=norm.bias.grad.numpy())
+
+
 def main():
     assert ref_loader.available(), "reference tree not present"
     ref = ref_loader.load()
@@ -332,6 +362,8 @@ def main():
         train_case(ref, name, c)
     for name, c in cases.P4P_TRAIN_CASES.items():
         p4p_train_case(ref, name, c)
+    for name, c in cases.VIT_TRAIN_CASES.items():
+        vit_train_case(ref, name, c)
 
 
 if __name__ == "__main__":

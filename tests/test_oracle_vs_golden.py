@@ -178,3 +178,19 @@ def test_p3embed_train_mode_oracle(golden_dir, name):
             assert np.abs(v.reshape(g["grad." + n].shape) - g["grad." + n]).max() <= 1e-5 * scale, n
     for n, v in running.items():
         assert np.abs(v - g["running." + n]).max() <= 1e-5 * np.abs(g["running." + n]).max(), n
+
+
+@pytest.mark.parametrize("name", list(cases.VIT_TRAIN_CASES))
+def test_vit_backward_oracle(golden_dir, name):
+    """oracle/train.py::apf_vit_backward (dX through the frozen block stack, encoder_norm gradients) against the reference
+    modules' autograd."""
+    from oracle import train
+    c = cases.VIT_TRAIN_CASES[name]
+    g = _load(golden_dir, name)
+    sd = synth.apf_vit_state(c["D"], c["depth"], 15, c["seed"])
+    tok = synth.vit_tokens(c["B"], c["G"], c["D"], c["seed"])
+    gp = (synth.uniform01(c["seed"], c["B"] * c["D"], 35).reshape(c["B"], c["D"]) - 0.5).astype(np.float32)
+    pooled, dx, gn = train.apf_vit_backward(sd, tok, c["depth"], c["heads"], gp)
+    for mine, key in ((pooled, "pooled"), (dx, "grad_tokens"), (gn["encoder_norm.weight"], "grad_norm_w"),
+                      (gn["encoder_norm.bias"], "grad_norm_b")):
+        assert np.abs(mine - g[key]).max() <= 1e-5 * np.abs(g[key]).max(), key
