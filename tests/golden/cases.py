@@ -36,12 +36,7 @@ VIT_CASES = {
     "vit_s12": dict(B=1, G=128, D=384, heads=12, depth=12, classes=15, seed=53),    # ViT-S geometry of BASELINE config 2
 }
 
-P4P_VIT_TRAIN_CASES = {
-    # backward through the frozen APFViTLayer stack + trainable encoder_norm + token max: dict(B, G, D, heads, depth, seed)
-    "vit_train": dict(B=2, G=20, D=64, heads=2, depth=2, seed=97),
-}
-
-TRAIN_CASES = {
+P4P_TRAIN_CASES = {
     # training-mode P3Embed (1 stage) through the reference's own forward + autograd: dict(B, N, k, W, seed)
     "p4p_train": dict(B=2, N=64, k=8, W=32, seed=96),
 }
