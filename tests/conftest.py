@@ -34,3 +34,17 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Write the parity record (per-comparison error and pure-relative shares, tests/helpers.py) next to the GPU logs."""
+    try:
+        import json
+        import helpers
+        if helpers.PARITY_LOG and _has_cuda():
+            out = os.path.join(ROOT, "gpurun_out")
+            os.makedirs(out, exist_ok=True)
+            with open(os.path.join(out, "parity_report.json"), "w") as f:
+                json.dump(helpers.PARITY_LOG, f, indent=1)
+    except Exception:
+        pass

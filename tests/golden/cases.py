@@ -8,6 +8,8 @@ APF_CASES = {
     "apf_height": dict(kind="clustered", B=2, N=512, C=4, G=24, k=16, E=48, seed=12),
     "apf_dups": dict(kind="duplicates", B=2, N=256, C=3, G=16, k=8, E=32, seed=13),
     "apf_k32": dict(kind="uniform", B=1, N=1024, C=3, G=64, k=32, E=96, seed=14),
+    # BASELINE configs[3] ("c4") widths: k = 64 neighbours, E = 384, clustered scene (reduced N / G so the fixture stays small)
+    "apf_k64": dict(kind="clustered", B=1, N=8192, C=3, G=128, k=64, E=384, seed=15),
 }
 
 P4P_CASES = {
@@ -15,6 +17,8 @@ P4P_CASES = {
     "p4p_2stage": dict(kind="uniform", B=2, N=256, k=8, sample_ratio=1.0 / 16, embed_dim=64, seed=21),
     "p4p_1stage": dict(kind="clustered", B=2, N=128, k=16, sample_ratio=0.25, embed_dim=256, seed=22),
     "p4p_2stage_k32": dict(kind="uniform", B=1, N=1024, k=32, sample_ratio=1.0 / 16, embed_dim=256, seed=23),
+    # BASELINE configs[2] ("c3") shape for one cloud: 8192 -> 2048 -> 512, k = 32, widths 128 / 256
+    "p4p_c3": dict(kind="uniform", B=1, N=8192, k=32, sample_ratio=1.0 / 16, embed_dim=256, seed=24),
 }
 
 INDEX_CASES = {

@@ -345,25 +345,28 @@ def vit_train_case(ref, name, c):
 
 
 def main():
+    """python tests/golden/make_golden.py [case names ...]  (no names: every case)."""
     assert ref_loader.available(), "reference tree not present"
     ref = ref_loader.load()
     torch.set_num_threads(os.cpu_count() or 1)
+    only = set(sys.argv[1:])
+    want = lambda name: not only or name in only
     for name, c in cases.INDEX_CASES.items():
-        index_case(ref, name, c)
+        if want(name): index_case(ref, name, c)
     for name, c in cases.APF_CASES.items():
-        apf_case(ref, name, c)
+        if want(name): apf_case(ref, name, c)
     for name, c in cases.P4P_CASES.items():
-        p4p_case(ref, name, c)
+        if want(name): p4p_case(ref, name, c)
     for name, c in cases.HEAD_CASES.items():
-        head_case(name, c)
+        if want(name): head_case(name, c)
     for name, c in cases.VIT_CASES.items():
-        vit_case(ref, name, c)
+        if want(name): vit_case(ref, name, c)
     for name, c in cases.TRAIN_CASES.items():
-        train_case(ref, name, c)
+        if want(name): train_case(ref, name, c)
     for name, c in cases.P4P_TRAIN_CASES.items():
-        p4p_train_case(ref, name, c)
+        if want(name): p4p_train_case(ref, name, c)
     for name, c in cases.VIT_TRAIN_CASES.items():
-        vit_train_case(ref, name, c)
+        if want(name): vit_train_case(ref, name, c)
 
 
 if __name__ == "__main__":

@@ -285,3 +285,60 @@ def test_stage_kernel_matches_arithmetic_model_and_layerwise(W, ng):
     ref = torch.load(path_out)
     err2 = float((tok.cpu() - ref).abs().max() / ref.abs().max())
     assert err2 < 2e-3, err2
+
+
+# ------------------------------------------------------------------ BASELINE configs[2] / configs[3] shapes, end to end
+_C4_ORACLE = {}
+
+
+def _c4_oracle(kind):
+    """One cloud of BASELINE configs[3] (N = 65536, G = 2048, k = 64, E = 384) through the oracle (~10 s), cached per kind."""
+    if kind not in _C4_ORACLE:
+        B, N, G, k, E = 1, 65536, 2048, 64, 384
+        x = synth.make_cloud(kind, B, N, 4400 + len(kind), 3)
+        st = synth.start_indices(B, N, 4400)
+        sd = synth.apf_encoder_state(E, 6, 44)
+        tok, grp = oracle.pointnet_apf(sd, x, st, G, k)
+        _C4_ORACLE[kind] = (x, st, sd, tok, grp)
+    return _C4_ORACLE[kind]
+
+
+@pytest.mark.parametrize("prec,rtol", PRECISIONS)
+@pytest.mark.parametrize("kind", ["uniform", "clustered", "duplicates"])
+def test_c4_shape_pointnet_against_oracle(kind, prec, rtol):
+    """BASELINE configs[3] at its real per-cloud shape (cluster FPS over 65536 points -> sweep kNN with k = 64 -> fused
+    embed at E = 384): indices bit-exact, tokens in tolerance, all three cloud kinds (duplicates = exact distance ties)."""
+    _skip_if_unbuilt(prec)
+    x, st, sd, otok, grp = _c4_oracle(kind)
+    G, k, E = 2048, 64, 384
+    net = PointNet(E, G, k, 6, precision=prec).eval().to(dev())
+    net.encoder.load_state_dict(synth.to_torch_state(sd), strict=True)
+    xt, stt = to_dev(x), to_dev(st)
+    fidx, ctr, kidx, perm = net.group.indices(xt, stt)
+    assert np.array_equal(fidx.cpu().numpy(), grp["fps_idx"]), "FPS indices"
+    assert np.array_equal(kidx.cpu().numpy(), grp["knn_idx"]), "kNN indices"
+    assert np.array_equal(perm.cpu().numpy(), grp["perm"]), "Morton order"
+    tok = net(xt, stt)
+    assert tok.shape == (1, G, E)
+    assert_tokens_close(tok.cpu().numpy(), otok, rtol, f"c4 shape ({kind}, {prec}) vs oracle")
+
+
+@pytest.mark.parametrize("prec,rtol", PRECISIONS)
+@pytest.mark.parametrize("kind", ["uniform", "clustered"])
+def test_c3_shape_p3embed_against_oracle(kind, prec, rtol):
+    """BASELINE configs[2] at its real per-cloud shape: P3Embed 2-stage 8192 -> 2048 -> 512, k = 32, widths 128 / 256
+    (Z-order culled kNN at N = 8192, stage kernel, gathered stage-1 rows, fused pair), B = 2 clouds."""
+    _skip_if_unbuilt(prec)
+    B, N, k = 2, 8192, 32
+    p = synth.make_cloud(kind, B, N, 3300 + len(kind), 3)
+    starts = [synth.start_indices(B, N, 33, 0), synth.start_indices(B, N // 4, 33, 1)]
+    sd = synth.p3embed_state(3, 1 / 16, 4, 4, 256, 33)
+    mod = P3Embed(sample_ratio=1 / 16, k=k, embed_dim=256, precision=prec).eval().to(dev())
+    mod.load_state_dict(synth.to_torch_state(sd), strict=True)
+    pt = to_dev(p)
+    ps, fs = mod(pt, pt.transpose(1, 2).contiguous(), [to_dev(s) for s in starts])
+    op, of, aux = oracle.p3embed(sd, p, p.copy(), starts, k, 2)
+    assert [tuple(f.shape) for f in fs[1:]] == [(B, 128, N // 4), (B, 256, N // 16)]
+    for s in (1, 2):
+        assert np.array_equal(ps[s].cpu().numpy(), op[s]), f"centres of stage {s - 1}"
+        assert_tokens_close(fs[s].transpose(1, 2).cpu().numpy(), of[s], rtol * s, f"c3 shape ({kind}, {prec}) stage {s - 1} vs oracle")
