@@ -60,19 +60,22 @@ extern "C" int64_t p3tok_patch_embed_workspace_bytes(const p3tok_mlp* mlp, int64
   return -1;
 }
 
-extern "C" int p3tok_patch_embed(const p3tok_rows* rows, const p3tok_mlp* mlp, int precision, void* workspace,
-                                 int64_t workspace_bytes, float* tokens, void* stream) {
+extern "C" int p3tok_patch_embed(const p3tok_rows* rows, const p3tok_mlp* mlp, int precision, int tokens_dtype,
+                                 void* workspace, int64_t workspace_bytes, void* tokens, void* stream) {
   int rc = check_embed_args(rows, mlp);
   if (rc) return rc;
   if (rows->B * rows->G == 0) return P3TOK_OK;
   P3_REQUIRE(tokens && workspace, P3TOK_ERR_INVALID, "patch_embed: null output/workspace");
+  P3_REQUIRE(tokens_dtype == P3TOK_F32 || tokens_dtype == P3TOK_BF16, P3TOK_ERR_INVALID, "patch_embed: tokens_dtype %d", tokens_dtype);
+  P3_REQUIRE(tokens_dtype == P3TOK_F32 || precision == P3TOK_BF16, P3TOK_ERR_UNSUPPORTED,
+             "patch_embed: bf16 tokens are emitted by the bf16 path only");
   if (precision == P3TOK_F32) {
     P3_REQUIRE(mlp->wdtype == P3TOK_F32, P3TOK_ERR_INVALID, "patch_embed(f32): weights must be f32");
-    return patch_embed_f32(rows, mlp, workspace, workspace_bytes, tokens, as_stream(stream));
+    return patch_embed_f32(rows, mlp, workspace, workspace_bytes, (float*)tokens, as_stream(stream));
   }
   if (precision == P3TOK_BF16) {
     P3_REQUIRE(mlp->wdtype == P3TOK_BF16, P3TOK_ERR_INVALID, "patch_embed(bf16): weights must be bf16");
-    return patch_embed_bf16(rows, mlp, workspace, workspace_bytes, tokens, as_stream(stream));
+    return patch_embed_bf16(rows, mlp, workspace, workspace_bytes, tokens, tokens_dtype == P3TOK_BF16, as_stream(stream));
   }
   set_error("patch_embed: unknown precision %d", precision);
   return P3TOK_ERR_INVALID;

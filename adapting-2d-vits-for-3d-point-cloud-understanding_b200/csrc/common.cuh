@@ -29,7 +29,7 @@ void count_launch(int n = 1);   // process-wide diagnostic counter (p3tok_kernel
 
 #define P3_LAUNCH_CHECK(name)                                       \
   do {                                                              \
-    cudaError_t _e = cudaGetLastError();                            \
+    cudaError_t _e = cudaPeekAtLastError();   /* do not clear errors that belong to earlier, unrelated work */ \
     if (_e != cudaSuccess) return ::p3tok::cuda_fail(_e, name);     \
     ::p3tok::count_launch();                                        \
   } while (0)

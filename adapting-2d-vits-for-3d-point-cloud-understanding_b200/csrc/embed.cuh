@@ -15,7 +15,8 @@ int patch_embed_f32(const p3tok_rows* rows, const p3tok_mlp* mlp, void* ws, int6
                     cudaStream_t s);
 
 int64_t patch_embed_bf16_workspace(const p3tok_mlp* mlp, int64_t ngroups, int64_t k);
-int patch_embed_bf16(const p3tok_rows* rows, const p3tok_mlp* mlp, void* ws, int64_t ws_bytes, float* tokens,
+// tokens: f32 (tokens_bf16 = 0) or bf16 (tokens_bf16 = 1), [ngroups, out_dim]
+int patch_embed_bf16(const p3tok_rows* rows, const p3tok_mlp* mlp, void* ws, int64_t ws_bytes, void* tokens, int tokens_bf16,
                      cudaStream_t s);
 
 // extra epilogue of tc_linear for the ViT blocks (vit.cu): GELU, fp32 residual stream, column-slice outputs

@@ -48,7 +48,8 @@ struct StageParams {
   const float* bias_a;              // [N1] used when gbias is null, or null
   int rows_per_group;               // multiple of 32
   const float* bias_b;              // [N2] or null
-  float* out_max;                   // [ceil(M/32), N2]
+  float* out_max;                   // [ceil(M/32), N2] f32 and / or
+  __nv_bfloat16* out_max_bf16;      // the same rounded to bf16 (either may be null)
   int max_relu;
   unsigned long long* trace;        // debug (P3TOK_TC_TRACE=1): leader CTA of pair 0, 16 clock stamps per tile
 };
@@ -315,11 +316,17 @@ tc_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         float m = warp_rows_max(v0, lane) + sbb[c0 + lane];
         if (p.max_relu) m = fmaxf(m, 0.f);
-        if (row0 < p.M) p.out_max[(size_t)(row0 >> 5) * p.N2 + c0 + lane] = m;
+        if (row0 < p.M) {
+          if (p.out_max) p.out_max[(size_t)(row0 >> 5) * p.N2 + c0 + lane] = m;
+          if (p.out_max_bf16) p.out_max_bf16[(size_t)(row0 >> 5) * p.N2 + c0 + lane] = __float2bfloat16_rn(m);
+        }
         if (two) {
           float m1 = warp_rows_max(v1, lane) + sbb[c0 + 32 + lane];
           if (p.max_relu) m1 = fmaxf(m1, 0.f);
-          if (row0 < p.M) p.out_max[(size_t)(row0 >> 5) * p.N2 + c0 + 32 + lane] = m1;
+          if (row0 < p.M) {
+            if (p.out_max) p.out_max[(size_t)(row0 >> 5) * p.N2 + c0 + 32 + lane] = m1;
+            if (p.out_max_bf16) p.out_max_bf16[(size_t)(row0 >> 5) * p.N2 + c0 + 32 + lane] = __float2bfloat16_rn(m1);
+          }
         }
       }
       if (tr) st_trace(p, it, 14);
@@ -350,19 +357,19 @@ bool tc_stage_supported(int K0, int N1, int N2, int64_t rows_per_group) {
 // out_max[g] = max over each 32 rows of act(W_b relu(W_a A0 + gbias|bias_a) + bias_b).  A0 [M,K0] bf16, W_a [N1,K0], W_b [N2,N1].
 int tc_stage(const __nv_bfloat16* A0, int64_t M, int K0, const __nv_bfloat16* Wa, int N1, const float* bias_a,
              const float* gbias, int rows_per_group, const __nv_bfloat16* Wb, int N2, const float* bias_b, float* out_max,
-             int max_relu, cudaStream_t s) {
+             __nv_bfloat16* out_max_bf16, int max_relu, cudaStream_t s) {
   if (rows_per_group <= 0) rows_per_group = 32;
   P3_REQUIRE(tc_stage_supported(K0, N1, N2, rows_per_group), P3TOK_ERR_UNSUPPORTED, "tc_stage: unsupported shape K0=%d N1=%d N2=%d",
              K0, N1, N2);
   P3_REQUIRE(M < (1ll << 31) - 512, P3TOK_ERR_UNSUPPORTED, "tc_stage: too many rows");
-  P3_REQUIRE(out_max != nullptr, P3TOK_ERR_INVALID, "tc_stage: null output");
+  P3_REQUIRE(out_max != nullptr || out_max_bf16 != nullptr, P3TOK_ERR_INVALID, "tc_stage: null output");
   if (M == 0) return P3TOK_OK;
   StageParams p;
   p.M = (int)M; p.K0 = K0; p.N1 = N1; p.N2 = N2;
   const int num_m_tiles = (int)((M + TC_BM - 1) / TC_BM);
   p.num_pairs = (num_m_tiles + 1) / 2;
   p.gbias = gbias; p.bias_a = bias_a; p.rows_per_group = rows_per_group; p.bias_b = bias_b;
-  p.out_max = out_max; p.max_relu = max_relu;
+  p.out_max = out_max; p.out_max_bf16 = out_max_bf16; p.max_relu = max_relu;
   CUtensorMap ta, twa, twb;
   int rc = make_map(&ta, A0, M, K0, TC_BM);
   if (rc) return rc;

@@ -1312,7 +1312,8 @@ static BfLayout bf_layout(const p3tok_mlp* m, int64_t ngroups, int64_t k) {
 
 int64_t patch_embed_bf16_workspace(const p3tok_mlp* m, int64_t ngroups, int64_t k) { return bf_layout(m, ngroups, k).total; }
 
-int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t ws_bytes, float* tokens, cudaStream_t s) {
+int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t ws_bytes, void* tokens, int tokens_bf16,
+                     cudaStream_t s) {
   const int64_t ngroups = R->B * R->G, k = R->k;
   const BfLayout L = bf_layout(m, ngroups, k);
   P3_REQUIRE(ws_bytes >= L.total, P3TOK_ERR_WORKSPACE, "patch_embed(bf16): workspace %lld < %lld bytes", (long long)ws_bytes,
@@ -1466,17 +1467,20 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
     rc = tc_linear(gmax_bf16, gc, (int)L.F, (const __nv_bfloat16*)m->w_mid_g, m->mid_dim, m->b_mid, nullptr, 1, 0, nullptr, gbias,
                    nullptr, nullptr, 0, s);
     if (rc) return rc;
-    float* tok = tokens + g0 * m->out_dim;
+    // the patch tokens leave as f32 (reference dtype) or bf16: rounded once, by the epilogue / reduction that produces them
+    float* tok = tokens_bf16 ? nullptr : reinterpret_cast<float*>(tokens) + g0 * m->out_dim;
+    __nv_bfloat16* tokb = tokens_bf16 ? reinterpret_cast<__nv_bfloat16*>(tokens) + g0 * m->out_dim : nullptr;
     // narrow blocks (P3Embed stage 0): concat layer + output layer + pool in one kernel with the weights resident in
     // shared memory (embed_stage.cu); the hidden activation never reaches HBM.  P3TOK_STAGE=0 disables it.
     static int stage_on = -1;
     if (stage_on < 0) { const char* e = getenv("P3TOK_STAGE"); stage_on = e ? atoi(e) : 1; }
     if (stage_on && fused_max && tc_stage_supported((int)L.F, m->mid_dim, m->out_dim, k)) {
       rc = tc_stage(act[cur], rows, (int)L.F, (const __nv_bfloat16*)m->w_mid_f, m->mid_dim, nullptr, gbias, (int)k,
-                    (const __nv_bfloat16*)m->w_out, m->out_dim, m->b_out, parts == 1 ? tok : gmax_f32, parts == 1 ? m->out_relu : 0, s);
+                    (const __nv_bfloat16*)m->w_out, m->out_dim, m->b_out, parts == 1 ? tok : gmax_f32, parts == 1 ? tokb : nullptr,
+                    parts == 1 ? m->out_relu : 0, s);
       if (rc) return rc;
       if (parts > 1) {
-        group_max_f32_kernel<<<grid_1d(gc * m->out_dim, 256), 256, 0, s>>>(gmax_f32, gc, parts, m->out_dim, m->out_relu, tok, nullptr);
+        group_max_f32_kernel<<<grid_1d(gc * m->out_dim, 256), 256, 0, s>>>(gmax_f32, gc, parts, m->out_dim, m->out_relu, tok, tokb);
         P3_LAUNCH_CHECK("group_max_f32_kernel");
       }
       continue;
@@ -1484,11 +1488,11 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
     if (fuse_on && fused_max && tc_fused_supported((int)L.F, m->mid_dim, m->out_dim, k, true)) {
       // concat layer (per-point half + group bias, ReLU) and output layer in one kernel; only the patch max is written
       rc = tc_fused(act[cur], rows, (int)L.F, (const __nv_bfloat16*)m->w_mid_f, m->mid_dim, nullptr, gbias, (int)k,
-                    (const __nv_bfloat16*)m->w_out, m->out_dim, m->b_out, nullptr, parts == 1 ? tok : gmax_f32, nullptr,
-                    parts == 1 ? m->out_relu : 0, s);
+                    (const __nv_bfloat16*)m->w_out, m->out_dim, m->b_out, nullptr, parts == 1 ? tok : gmax_f32,
+                    parts == 1 ? tokb : nullptr, parts == 1 ? m->out_relu : 0, s);
       if (rc) return rc;
       if (parts > 1) {
-        group_max_f32_kernel<<<grid_1d(gc * m->out_dim, 256), 256, 0, s>>>(gmax_f32, gc, parts, m->out_dim, m->out_relu, tok, nullptr);
+        group_max_f32_kernel<<<grid_1d(gc * m->out_dim, 256), 256, 0, s>>>(gmax_f32, gc, parts, m->out_dim, m->out_relu, tok, tokb);
         P3_LAUNCH_CHECK("group_max_f32_kernel");
       }
       continue;
@@ -1500,18 +1504,18 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
     // ---- output layer + max over the patch
     if (fused_max) {
       rc = tc_linear(act[cur], rows, m->mid_dim, (const __nv_bfloat16*)m->w_out, m->out_dim, m->b_out, nullptr, 1, 0, nullptr, nullptr,
-                     parts == 1 ? tok : gmax_f32, nullptr, parts == 1 ? m->out_relu : 0, s);
+                     parts == 1 ? tok : gmax_f32, parts == 1 ? tokb : nullptr, parts == 1 ? m->out_relu : 0, s);
       if (rc) return rc;
       if (parts > 1) {
         // ReLU commutes with max: apply it after combining the partial maxima
-        group_max_f32_kernel<<<grid_1d(gc * m->out_dim, 256), 256, 0, s>>>(gmax_f32, gc, parts, m->out_dim, m->out_relu, tok, nullptr);
+        group_max_f32_kernel<<<grid_1d(gc * m->out_dim, 256), 256, 0, s>>>(gmax_f32, gc, parts, m->out_dim, m->out_relu, tok, tokb);
         P3_LAUNCH_CHECK("group_max_f32_kernel");
       }
     } else {
       rc = tc_linear(act[cur], rows, m->mid_dim, (const __nv_bfloat16*)m->w_out, m->out_dim, m->b_out, nullptr, 1, 0, nullptr, scratch,
                      nullptr, nullptr, 0, s);
       if (rc) return rc;
-      group_max_f32_kernel<<<grid_1d(gc * m->out_dim, 256), 256, 0, s>>>(scratch, gc, (int)k, m->out_dim, m->out_relu, tok, nullptr);
+      group_max_f32_kernel<<<grid_1d(gc * m->out_dim, 256), 256, 0, s>>>(scratch, gc, (int)k, m->out_dim, m->out_relu, tok, tokb);
       P3_LAUNCH_CHECK("group_max_f32_kernel");
     }
   }

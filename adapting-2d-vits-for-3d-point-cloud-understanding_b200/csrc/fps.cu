@@ -257,10 +257,10 @@ fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __r
         if (lane == (int)src) cwin[buf] = ccand[buf * 16 + lane];
       }
       __syncthreads();
-      far = (int)cwin[buf].idx;
+      far = (int)min(cwin[buf].idx, (uint32_t)(N - 1));   // no candidate anywhere (cannot happen for finite input): stay in range
       cx = cwin[buf].x; cy = cwin[buf].y; cz = cwin[buf].z;
     } else {
-      far = (int)idx;
+      far = (int)min(idx, (uint32_t)(N - 1));             // idx = 0xffffffff only if no thread had a candidate: stay in range
       cx = rows[far * pt_stride]; cy = rows[far * pt_stride + 1]; cz = rows[far * pt_stride + 2];
     }
   }

@@ -323,6 +323,6 @@ int tc_fused(const __nv_bfloat16* A0, int64_t M, int K0, const __nv_bfloat16* Wa
 bool tc_stage_supported(int K0, int N1, int N2, int64_t rows_per_group);
 int tc_stage(const __nv_bfloat16* A0, int64_t M, int K0, const __nv_bfloat16* Wa, int N1, const float* bias_a,
              const float* gbias, int rows_per_group, const __nv_bfloat16* Wb, int N2, const float* bias_b, float* out_max,
-             int max_relu, cudaStream_t s);
+             __nv_bfloat16* out_max_bf16, int max_relu, cudaStream_t s);
 
 }  // namespace p3tok

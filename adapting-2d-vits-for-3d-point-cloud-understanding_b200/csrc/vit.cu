@@ -610,8 +610,8 @@ extern "C" int p3tok_linear_bf16_ex(const void* A, int64_t M, int64_t K, const v
 
 extern "C" int p3tok_apf_vit_forward(float* x, int64_t B, int64_t G, int64_t D, int64_t heads, int64_t H, int64_t R,
                                      const p3tok_vit_layer* layers, int64_t n_layers, const float* final_norm_w,
-                                     const float* final_norm_b, float* pooled_out, void* workspace, int64_t workspace_bytes,
-                                     void* stream) {
+                                     const float* final_norm_b, float ln_eps, float* pooled_out, void* workspace,
+                                     int64_t workspace_bytes, void* stream) {
   P3_REQUIRE(B >= 0 && G >= 0 && D > 0 && H > 0 && R > 0 && heads > 0 && n_layers >= 0, P3TOK_ERR_INVALID, "apf_vit: bad shape");
   P3_REQUIRE(D % 8 == 0 && H % 64 == 0 && R % 8 == 0, P3TOK_ERR_UNSUPPORTED, "apf_vit: D, R must be multiples of 8, H of 64");
   P3_REQUIRE(D <= 128 * LN_MAX_V4, P3TOK_ERR_UNSUPPORTED, "apf_vit: D=%lld > %d", (long long)D, 128 * LN_MAX_V4);
@@ -630,7 +630,8 @@ extern "C" int p3tok_apf_vit_forward(float* x, int64_t B, int64_t G, int64_t D, 
   __nv_bfloat16* a = reinterpret_cast<__nv_bfloat16*>(ws + L.a);
   __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(ws + L.qkv);
   __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(ws + L.h);
-  const float eps = 1e-5f;
+  P3_REQUIRE(ln_eps > 0.f && ln_eps < 1.f, P3TOK_ERR_INVALID, "apf_vit: ln_eps %g", (double)ln_eps);
+  const float eps = ln_eps;
   const int HR = (int)(H + R);
   int rc;
   for (int64_t li = 0; li < n_layers; ++li) {

@@ -64,14 +64,14 @@ _SIGNATURES = {
     "p3tok_apf_group": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "p3tok_group_gather": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp]),
     "p3tok_patch_embed_workspace_bytes": (_i64, [ctypes.POINTER(MlpStruct), _i64, _i64, _int]),
-    "p3tok_patch_embed": (_int, [ctypes.POINTER(RowsStruct), ctypes.POINTER(MlpStruct), _int, _vp, _i64, _vp, _vp]),
+    "p3tok_patch_embed": (_int, [ctypes.POINTER(RowsStruct), ctypes.POINTER(MlpStruct), _int, _int, _vp, _i64, _vp, _vp]),
     "p3tok_linear_f32": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _int, _vp, _vp]),
     "p3tok_linear_bf16": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp]),
     "p3tok_token_head_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64] + [_vp] * 12),
     "p3tok_group_max": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "p3tok_apf_vit_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64, _i64]),
     "p3tok_apf_vit_forward": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, ctypes.POINTER(VitLayerStruct), _i64, _vp, _vp,
-                                     _vp, _vp, _i64, _vp]),
+                                     _f32, _vp, _vp, _i64, _vp]),
     "p3tok_layernorm_bf16": (_int, [_vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp]),
     "p3tok_attention_bf16": (_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "p3tok_linear_bf16_ex": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _int, _i64, _vp, _f32, _f32, _vp, _vp, _vp]),
@@ -99,7 +99,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.p3tok_abi_version() != 1:
+        if L.p3tok_abi_version() != 2:
             raise RuntimeError("libp3tok.so ABI version mismatch; rebuild")
         _lib = L
     return _lib

@@ -125,11 +125,17 @@ def run_blocks(layers, x: torch.Tensor, final_norm: Optional[nn.LayerNorm], cach
         params += _layer_params(l, cache)
     heads = layers[0].attention.num_heads
     D = x.shape[-1]
+    # one eps for every normalisation of the stack (norm2 and adapter_norm share their statistics in the folded layer)
+    norms = [n for l in layers for n in (l.norm1, l.norm2, l.adapter.adapter_norm)] + ([final_norm] if final_norm is not None else [])
+    eps = {float(n.eps) for n in norms}
+    if len(eps) != 1:
+        raise RuntimeError(f"APFViTLayer stack: all LayerNorms must share one eps, got {sorted(eps)}")
+    ln_eps = eps.pop()
     if final_norm is None:
         fw, fb = torch.ones(D, device=x.device), torch.zeros(D, device=x.device)
     else:
         fw, fb = final_norm.weight.detach().float(), final_norm.bias.detach().float()
-    y, pooled = ops.apf_vit(x.float(), params, heads, layers[0].adapter.down_size, fw, fb)
+    y, pooled = ops.apf_vit(x.float(), params, heads, layers[0].adapter.down_size, fw, fb, ln_eps)
     return y, (pooled if final_norm is not None else None)
 
 

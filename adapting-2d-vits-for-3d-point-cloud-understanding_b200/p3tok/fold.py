@@ -15,7 +15,7 @@ Conv(W->W, bias)+BN+ReLU with nothing in between, so the two matrices multiply i
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Dict, List, Sequence
+from typing import Dict, List, Optional, Sequence
 
 import torch
 
@@ -76,27 +76,28 @@ def _bias(sd, name, n) -> torch.Tensor:
     return b.detach().double().cpu() if b is not None else torch.zeros(n, dtype=torch.float64)
 
 
-def _bn_affine(sd, name):
+def _bn_affine(sd, name, eps=None):
+    """eps: {BatchNorm module name: eps} from the module (modules._bn_eps); the nn default 1e-5 when absent."""
     g = sd[name + ".weight"].detach().double().cpu()
     b = sd[name + ".bias"].detach().double().cpu()
     m = sd[name + ".running_mean"].detach().double().cpu()
     v = sd[name + ".running_var"].detach().double().cpu()
-    s = g / torch.sqrt(v + BN_EPS)
+    s = g / torch.sqrt(v + (eps or {}).get(name, BN_EPS))
     return s, b - m * s
 
 
-def _conv_bn(sd, conv, bn):
+def _conv_bn(sd, conv, bn, eps=None):
     W = _mat(sd, conv)
     b = _bias(sd, conv, W.shape[0])
-    s, t = _bn_affine(sd, bn)
+    s, t = _bn_affine(sd, bn, eps)
     return W * s[:, None], b * s + t
 
 
-def fold_apf_encoder(sd: Dict[str, torch.Tensor]) -> PatchMLP:
-    W1, b1 = _conv_bn(sd, "first_conv.0", "first_conv.1")
-    W2, b2 = _conv_bn(sd, "first_conv.3", "first_conv.4")
+def fold_apf_encoder(sd: Dict[str, torch.Tensor], eps: Optional[Dict[str, float]] = None) -> PatchMLP:
+    W1, b1 = _conv_bn(sd, "first_conv.0", "first_conv.1", eps)
+    W2, b2 = _conv_bn(sd, "first_conv.3", "first_conv.4", eps)
     W3, b3 = _mat(sd, "first_conv.6"), _bias(sd, "first_conv.6", 0)
-    Wm, bm = _conv_bn(sd, "second_conv.0", "second_conv.1")
+    Wm, bm = _conv_bn(sd, "second_conv.0", "second_conv.1", eps)
     Wo = _mat(sd, "second_conv.3")
     bo = _bias(sd, "second_conv.3", Wo.shape[0])
     E = W3.shape[0]
@@ -108,16 +109,16 @@ def fold_apf_encoder(sd: Dict[str, torch.Tensor]) -> PatchMLP:
                     w_mid_g=f(Wm[:, :E]), w_mid_f=f(Wm[:, E:]), b_mid=f(bm), w_out=f(Wo), b_out=f(bo))
 
 
-def fold_p3embed_stage(sd: Dict[str, torch.Tensor], s: int) -> PatchMLP:
+def fold_p3embed_stage(sd: Dict[str, torch.Tensor], s: int, eps: Optional[Dict[str, float]] = None) -> PatchMLP:
     p = f"convs.{s}"
     A = _mat(sd, f"{p}.0.0")                       # (W, Cin), no bias, no BN, no activation
     Bm = _mat(sd, f"{p}.0.1")                      # (W, W) + bias, then BN + ReLU
     bb = _bias(sd, f"{p}.0.1", Bm.shape[0])
-    s1, t1 = _bn_affine(sd, f"{p}.0.2")
+    s1, t1 = _bn_affine(sd, f"{p}.0.2", eps)
     W1 = (Bm @ A) * s1[:, None]
     b1 = bb * s1 + t1
-    Wm, bm = _conv_bn(sd, f"{p}.1.0", f"{p}.1.1")
-    Wo, bo = _conv_bn(sd, f"{p}.1.3", f"{p}.1.4")
+    Wm, bm = _conv_bn(sd, f"{p}.1.0", f"{p}.1.1", eps)
+    Wo, bo = _conv_bn(sd, f"{p}.1.3", f"{p}.1.4", eps)
     W = W1.shape[0]
     assert Wm.shape == (2 * W, 2 * W) and Wo.shape == (W, 2 * W)
     f = lambda t: t.float().contiguous()

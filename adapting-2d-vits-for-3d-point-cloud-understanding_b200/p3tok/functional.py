@@ -4,8 +4,12 @@ Drop-in for `from data.sampler import furthest_point_sample, fps, knn_point, ind
 (reference src/data/sampler.py:4-94) and for `farthest_point_sampling`, `group_knn`
 (src/models/pix4point.py:8-102).  Every function takes one optional extra keyword the
 reference does not have - `start_idx` - because the reference draws the first FPS index from
-torch's global RNG inside the call (sampler.py:20); when omitted the same draw is made here
-on the input's device.
+torch's global RNG inside the call (sampler.py:20).  When it is omitted the same draw is made
+here the way each reference function makes it, so `torch.manual_seed(s)` reproduces the
+reference's centres: furthest_point_sample / fps draw `torch.randint` on the global CPU
+generator and copy the result to the device (sampler.py:20); farthest_point_sampling draws on
+the input's device (pix4point.py:30).  (A host draw cannot be captured into a CUDA graph: pass
+`start_idx` when capturing, as p3tok.graph does.)
 """
 from __future__ import annotations
 
@@ -16,10 +20,12 @@ import torch
 from . import _lib, ops
 
 
-def _start(x: torch.Tensor, start_idx: Optional[torch.Tensor]) -> torch.Tensor:
+def _start(x: torch.Tensor, start_idx: Optional[torch.Tensor], device_draw: bool = False) -> torch.Tensor:
     B, N = x.shape[0], x.shape[1]
     if start_idx is None:
-        return torch.randint(0, N, (B,), dtype=torch.long, device=x.device)   # sampler.py:20
+        if device_draw:
+            return torch.randint(0, N, (B,), dtype=torch.long, device=x.device)   # pix4point.py:30
+        return torch.randint(0, N, (B,), dtype=torch.long).to(x.device)           # sampler.py:20: CPU generator, then .to(device)
     return start_idx.to(device=x.device, dtype=torch.long)
 
 
@@ -30,10 +36,18 @@ def furthest_point_sample(xyz: torch.Tensor, npoint: int, start_idx: Optional[to
 
 def farthest_point_sampling(points: torch.Tensor, n_samples: int,
                             start_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """pix4point.py:8-53: clamps n_samples to N (line 23)."""
-    if points.shape[-1] != 3:
-        raise RuntimeError("p3tok farthest_point_sampling: only D=3 coordinates are supported")
-    return ops.fps(points, _start(points, start_idx), min(int(n_samples), int(points.shape[1])))
+    """pix4point.py:8-53: clamps n_samples to N (line 23); distances sum over ALL D coordinates (line 44).
+    D = 3 (and D = 4 rows whose 4th channel is not a coordinate never reach this function in the reference) runs
+    the kernel in place; D < 3 is zero-padded to 3 columns - adding (0 - 0)^2 = +0 terms leaves every fp32 sum
+    bit-identical; D > 3 is outside the kernel's envelope (the reference only ever passes xyz, pix4point.py:175)."""
+    D = int(points.shape[-1])
+    if D > 3:
+        raise RuntimeError("p3tok farthest_point_sampling: D > 3 coordinates are not supported (the reference's only "
+                           "call site passes xyz, pix4point.py:175)")
+    start = _start(points, start_idx, device_draw=True)
+    if D < 3:
+        points = torch.cat([points.float(), points.new_zeros((*points.shape[:2], 3 - D), dtype=torch.float32)], -1)
+    return ops.fps(points, start, min(int(n_samples), int(points.shape[1])))
 
 
 def index_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:

@@ -29,6 +29,23 @@ def _check_precision(p: str) -> bool:
     return p == "bf16"
 
 
+def _check_token_dtype(token_dtype, precision: str) -> bool:
+    """True when the tokens leave as bfloat16 (bf16 path only); default float32 like the reference."""
+    if token_dtype in (None, torch.float32):
+        return False
+    if token_dtype != torch.bfloat16:
+        raise ValueError(f"token_dtype must be torch.float32 or torch.bfloat16, got {token_dtype!r}")
+    if precision != "bf16":
+        raise ValueError("token_dtype=torch.bfloat16 needs precision='bf16'")
+    return True
+
+
+def _bn_eps(module: nn.Module):
+    """{prefix of each BatchNorm in `module`: its eps} - the folding uses the module's eps, not a constant."""
+    return {name: float(m.eps) for name, m in module.named_modules()
+            if isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d))}
+
+
 class _FoldedMixin:
     """Caches the folded weights per (device, dtype); refolds when any parameter changes."""
 
@@ -59,30 +76,45 @@ class Group(nn.Module):
         self.group_size = group_size
 
     def indices(self, x: torch.Tensor, start_idx: Optional[torch.Tensor] = None):
-        """(fps_idx (B,G), center (B,G,3), knn_idx (B,G,k), perm (B,G)) - the index half of forward."""
+        """(fps_idx (B,G), center (B,G,3), knn_idx (B,G,k), perm (B,G)) - the index half of forward, computed on the
+        coordinates x[..., :3] (read in place when x has 3 or 4 channels)."""
         fps_idx, ws = ops.fps_with_knn_prepare(x, _start(x, start_idx), self.num_group)   # kNN preparation overlaps FPS
         center = ops.gather_points(x, fps_idx)[..., :3].contiguous() if x.shape[-1] != 3 else ops.gather_points(x, fps_idx)
         knn_idx = ops.knn_query(x, ws, center, self.group_size, _lib.KNN_APF_SQ, False)
         perm = ops.morton_order(center)[0]
         return fps_idx, center, knn_idx, perm
 
+    @staticmethod
+    def _xyz_is_prefix_of(x: torch.Tensor, xyz: torch.Tensor) -> bool:
+        """xyz is x[:, :, :3] itself (the reference's only call site, apf.py:212-214): same storage, same strides."""
+        return (xyz.shape[-1] == 3 and xyz.dtype == x.dtype and xyz.device == x.device and xyz.data_ptr() == x.data_ptr()
+                and xyz.stride() == x.stride())
+
     def forward(self, x: torch.Tensor, xyz: torch.Tensor, start_idx: Optional[torch.Tensor] = None):
-        # xyz is x[:, :, :3] in the reference's only call site (apf.py:212-214); the kernels read
-        # the xyz channels of x in place, so the separate argument is only shape-checked.
-        if xyz.shape[:2] != x.shape[:2]:
-            raise RuntimeError("Group.forward: x and xyz disagree on (B,N)")
+        """FPS, kNN and the Morton order run on `xyz`, the gather / centre-subtraction on `x` (apf.py:64-95).  When xyz
+        is the x[:, :, :3] view (apf.py:212-214) the kernels read it in place; any other xyz (normalised, augmented)
+        is honoured through a contiguous copy, and the returned centres are xyz rows as in the reference (apf.py:70)."""
+        if xyz.shape[:2] != x.shape[:2] or xyz.shape[-1] != 3:
+            raise RuntimeError("Group.forward: xyz must be (B,N,3) with x's B and N")
+        if x.dtype == torch.float32 and x.is_contiguous() and self._xyz_is_prefix_of(x, xyz):
+            fps_idx, _, knn_idx, perm = self.indices(x, start_idx)
+            return ops.apf_group(x, fps_idx, knn_idx, perm)
         x = x.float().contiguous()
-        fps_idx, _, knn_idx, perm = self.indices(x, start_idx)
-        return ops.apf_group(x, fps_idx, knn_idx, perm)
+        pts = xyz.float().contiguous()
+        fps_idx, center, knn_idx, perm = self.indices(pts, start_idx)
+        neigh, _ = ops.apf_group(x, fps_idx, knn_idx, perm)
+        center = torch.gather(center, 1, perm.unsqueeze(-1).expand(-1, -1, 3))      # Morton order of the xyz centres
+        return neigh, center
 
 
 class Encoder(nn.Module, _FoldedMixin):
     """apf.py:114-181.  forward(point_groups (B,G,k,Cin)) -> (B,G,E)."""
 
-    def __init__(self, encoder_channel: int, in_channel: int, precision: str = "fp32"):
+    def __init__(self, encoder_channel: int, in_channel: int, precision: str = "fp32", token_dtype=None):
         super().__init__()
         self.encoder_channel = encoder_channel
         self.precision = precision
+        self.token_dtype = token_dtype
         E = encoder_channel
         self.first_conv = nn.Sequential(
             nn.Conv1d(in_channel, 256, 1), nn.BatchNorm1d(256), nn.ReLU(inplace=True),
@@ -93,7 +125,8 @@ class Encoder(nn.Module, _FoldedMixin):
             nn.Conv1d(2 * E, E, 1))
 
     def folded(self, device) -> fold.PatchMLP:
-        return self._folded(lambda: fold.fold_apf_encoder(self.state_dict()), device, _check_precision(self.precision))
+        return self._folded(lambda: fold.fold_apf_encoder(self.state_dict(), _bn_eps(self)), device,
+                            _check_precision(self.precision))
 
     def forward(self, point_groups: torch.Tensor) -> torch.Tensor:
         self._require_eval()
@@ -101,7 +134,7 @@ class Encoder(nn.Module, _FoldedMixin):
         m = self.folded(point_groups.device)
         rows = point_groups.float().reshape(B * G * k, cin)
         tok = ops.patch_embed(_lib.ROWS_DIRECT, rows, None, None, None, None, B * G, k, m.tensors(), m.meta(),
-                              _check_precision(self.precision))
+                              _check_precision(self.precision), _check_token_dtype(self.token_dtype, self.precision))
         return tok.view(B, G, self.encoder_channel)
 
     get_features = forward
@@ -112,10 +145,11 @@ class PointNet(nn.Module):
     is never written - the embed kernels gather, centre-subtract and apply the Morton order as the
     output row."""
 
-    def __init__(self, embed_dim: int, num_group: int, group_size: int, in_channel: int, precision: str = "fp32"):
+    def __init__(self, embed_dim: int, num_group: int, group_size: int, in_channel: int, precision: str = "fp32",
+                 token_dtype=None):
         super().__init__()
         self.group = Group(num_group, group_size)
-        self.encoder = Encoder(embed_dim, in_channel, precision)
+        self.encoder = Encoder(embed_dim, in_channel, precision, token_dtype)
 
     def forward(self, x: torch.Tensor, start_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
         self.encoder._require_eval()
@@ -127,7 +161,8 @@ class PointNet(nn.Module):
         if m.cin != 2 * C:
             raise RuntimeError(f"PointNet: in_channel={m.cin} but input has C={C} (expects in_channel == 2*C)")
         tok = ops.patch_embed(_lib.ROWS_APF, x, None, fps_idx, knn_idx, perm, B * G, k, m.tensors(), m.meta(),
-                              _check_precision(self.encoder.precision))
+                              _check_precision(self.encoder.precision),
+                              _check_token_dtype(self.encoder.token_dtype, self.encoder.precision))
         return tok.view(B, G, -1)
 
 
@@ -136,13 +171,14 @@ class P3Embed(nn.Module, _FoldedMixin):
     Features are kept channel-last internally; the returned feature tensors are (B,W,G) views."""
 
     def __init__(self, in_channels: int = 3, sample_ratio: float = 0.25, scale: int = 4, k: int = 32,
-                 layers: int = 4, embed_dim: int = 256, precision: str = "fp32", **kwargs):
+                 layers: int = 4, embed_dim: int = 256, precision: str = "fp32", token_dtype=None, **kwargs):
         super().__init__()
         if layers != 4:
             raise ValueError("p3tok P3Embed supports the reference's layers=4 layout only")
         self.sample_ratio = sample_ratio
         self.k = k
         self.precision = precision
+        self.token_dtype = token_dtype          # dtype of the LAST stage's tokens (earlier stages feed the next gather in f32)
         stages = int(math.log(1 / sample_ratio, scale))
         embed_dim = int(embed_dim // 2 ** (stages - 1))
         self.convs = nn.ModuleList()
@@ -167,7 +203,8 @@ class P3Embed(nn.Module, _FoldedMixin):
             cache.clear()
             cache["ver"] = ver
             sd = self.state_dict()
-            cache["host"] = [fold.fold_p3embed_stage(sd, s) for s in range(len(self.convs))]
+            eps = _bn_eps(self)
+            cache["host"] = [fold.fold_p3embed_stage(sd, s, eps) for s in range(len(self.convs))]
         return [m.to(device, torch.bfloat16 if bf16 else torch.float32) for m in cache["host"]]
 
     def forward(self, p: torch.Tensor, f: torch.Tensor, start_idx: Optional[List[torch.Tensor]] = None
@@ -178,14 +215,17 @@ class P3Embed(nn.Module, _FoldedMixin):
         out_p, out_f = [p], [f]
         pts = p.float().contiguous()
         feat = f.float().transpose(1, 2).contiguous()            # channel-last (B,N,D)
-        for s, m in enumerate(self.folded(p.device)):
+        folded = self.folded(p.device)
+        bf16_last = _check_token_dtype(self.token_dtype, self.precision)
+        for s, m in enumerate(folded):
             N = N // 4                                           # pix4point.py:174
             G = min(N, int(pts.shape[1]))                        # clamp of farthest_point_sampling (line 23)
             st = None if start_idx is None else start_idx[s]
-            cidx, ws = ops.fps_with_knn_prepare(pts, _start(pts, st), G)                   # kNN preparation overlaps FPS
+            cidx, ws = ops.fps_with_knn_prepare(pts, _start(pts, st, device_draw=True), G)   # kNN preparation overlaps FPS
             ctr = ops.gather_points(pts, cidx)
             kidx = ops.knn_query(pts, ws, ctr, self.k, _lib.KNN_P4P_CDIST, True)
-            tok = ops.patch_embed(_lib.ROWS_P4P, pts, feat, None, kidx, None, B * G, self.k, m.tensors(), m.meta(), bf16)
+            tok = ops.patch_embed(_lib.ROWS_P4P, pts, feat, None, kidx, None, B * G, self.k, m.tensors(), m.meta(), bf16,
+                                  bf16_last and s == len(folded) - 1)
             feat = tok.view(B, G, -1)
             pts = ctr
             out_p.append(ctr)

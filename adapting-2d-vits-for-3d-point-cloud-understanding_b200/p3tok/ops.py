@@ -192,6 +192,7 @@ def knn_prepare(x: torch.Tensor) -> torch.Tensor:
     empty when the sorted variant does not apply (N > 8192 or P3TOK_KNN_SORTED=0).  Enqueued on the CURRENT stream:
     modules run it on a side stream next to FPS."""
     _need_cuda("knn_prepare", x)
+    x_in = x
     x = x if x.dtype == torch.float32 else x.float()
     x, stride = _point_stride(x)
     B, N = int(x.shape[0]), int(x.shape[1])
@@ -200,6 +201,7 @@ def knn_prepare(x: torch.Tensor) -> torch.Tensor:
     if ws_bytes > 0:
         with torch.cuda.device(x.device), _timed("knn"):
             check(_L().p3tok_knn_prepare(x.data_ptr(), B, N, stride, ws.data_ptr(), ws_bytes, _stream()), "knn_prepare")
+        _ws_bind(ws, x_in)
     return ws
 
 
@@ -214,6 +216,7 @@ def knn_query(x: torch.Tensor, ws: torch.Tensor, centres: torch.Tensor, k: int, 
     if ws.numel() == 0:
         return knn(x, centres, k, mode, int32_out, False)[0]
     _need_cuda("knn_query", x, ws, centres)
+    _ws_check(ws, x)
     c = _f32c("knn_query", centres[..., :3])
     B, N, G = int(x.shape[0]), int(x.shape[1]), int(c.shape[1])
     if c.dim() != 3 or c.shape[0] != B:
@@ -230,6 +233,29 @@ def knn_query(x: torch.Tensor, ws: torch.Tensor, centres: torch.Tensor, k: int, 
 @knn_query.register_fake
 def _(x, ws, centres, k, mode, int32_out):
     return x.new_empty((x.shape[0], centres.shape[1], k), dtype=torch.int32 if int32_out else torch.int64)
+
+
+# A prepared workspace answers queries for the clouds it was sorted from and nothing else; the C side can only check its
+# size.  knn_prepare records which tensor (storage address, shape, version counter) a workspace belongs to and knn_query
+# refuses a workspace prepared from other clouds or from an `x` that was modified in place since.
+_WS_OWNER = {}
+
+
+def _ws_key(x: torch.Tensor):
+    return (x.data_ptr(), tuple(x.shape), tuple(x.stride()), x._version)
+
+
+def _ws_bind(ws: torch.Tensor, x: torch.Tensor) -> None:
+    if len(_WS_OWNER) > 64:                           # stale entries of freed workspaces
+        _WS_OWNER.clear()
+    _WS_OWNER[ws.data_ptr()] = _ws_key(x)
+
+
+def _ws_check(ws: torch.Tensor, x: torch.Tensor) -> None:
+    owner = _WS_OWNER.get(ws.data_ptr())
+    if owner is not None and owner != _ws_key(x):
+        raise RuntimeError("p3tok::knn_query: this workspace was prepared from a different (or since modified) point tensor; "
+                           "call knn_prepare(x) again")
 
 
 def fps_with_knn_prepare(x: torch.Tensor, start_idx: torch.Tensor, npoint: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -373,10 +399,11 @@ def _mlp_struct(weights: Sequence[torch.Tensor], meta: Sequence[int], wdtype: in
 @torch.library.custom_op("p3tok::patch_embed", mutates_args=(), device_types="cuda")
 def patch_embed(kind: int, x: torch.Tensor, feats: Optional[torch.Tensor], ctr_idx: Optional[torch.Tensor],
                 knn_idx: Optional[torch.Tensor], perm: Optional[torch.Tensor], ngroups: int, k: int,
-                weights: Sequence[torch.Tensor], meta: Sequence[int], bf16: bool) -> torch.Tensor:
+                weights: Sequence[torch.Tensor], meta: Sequence[int], bf16: bool, bf16_tokens: bool = False) -> torch.Tensor:
     """kind 0: APF rows from x (B,N,C) + ctr_idx (B,G) + knn_idx (B,G,k) [+ perm];
     kind 1: P4P rows from x=pnts (B,N,3) + feats (B,N,D) + knn_idx (B,G,k);
-    kind 2: x is the row matrix (ngroups*k, cin).  Returns tokens (ngroups, out_dim) float32."""
+    kind 2: x is the row matrix (ngroups*k, cin).  Returns tokens (ngroups, out_dim) float32, or bfloat16 with
+    bf16_tokens (bf16 path only: the patch max is rounded once by the epilogue that produces it)."""
     _need_cuda("patch_embed", x, feats, ctr_idx, knn_idx, perm, *weights)
     x = _f32c("patch_embed", x)
     prec = _lib.BF16 if bf16 else _lib.F32
@@ -418,18 +445,20 @@ def patch_embed(kind: int, x: torch.Tensor, feats: Optional[torch.Tensor], ctr_i
     if ws_bytes < 0:
         raise RuntimeError("p3tok::patch_embed: bad descriptor")
     ws = torch.empty((max(int(ws_bytes), 256),), dtype=torch.uint8, device=x.device)
-    tokens = torch.empty((ngroups, m.out_dim), dtype=torch.float32, device=x.device)
+    if bf16_tokens and not bf16:
+        raise RuntimeError("p3tok::patch_embed: bfloat16 tokens are emitted by the bf16 path only")
+    tokens = torch.empty((ngroups, m.out_dim), dtype=torch.bfloat16 if bf16_tokens else torch.float32, device=x.device)
     with torch.cuda.device(x.device), _timed("embed"):
-        check(L.p3tok_patch_embed(ctypes.byref(r), ctypes.byref(m), prec, ws.data_ptr(), int(ws.numel()),
-                                  tokens.data_ptr(), _stream()), "patch_embed")
+        check(L.p3tok_patch_embed(ctypes.byref(r), ctypes.byref(m), prec, _lib.BF16 if bf16_tokens else _lib.F32, ws.data_ptr(),
+                                  int(ws.numel()), tokens.data_ptr(), _stream()), "patch_embed")
     del keep
     return tokens
 
 
 @patch_embed.register_fake
-def _(kind, x, feats, ctr_idx, knn_idx, perm, ngroups, k, weights, meta, bf16):
+def _(kind, x, feats, ctr_idx, knn_idx, perm, ngroups, k, weights, meta, bf16, bf16_tokens=False):
     n_pre = meta[1]
-    return x.new_empty((ngroups, meta[3 + 2 * n_pre]))
+    return x.new_empty((ngroups, meta[3 + 2 * n_pre]), dtype=torch.bfloat16 if bf16_tokens else torch.float32)
 
 
 # ------------------------------------------------------------------------------ exported building blocks
@@ -536,7 +565,7 @@ _NVT = len(VIT_LAYER_TENSORS)
 
 @torch.library.custom_op("p3tok::apf_vit", mutates_args=(), device_types="cuda")
 def apf_vit(tokens: torch.Tensor, params: Sequence[torch.Tensor], heads: int, bottleneck: int, final_w: torch.Tensor,
-            final_b: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+            final_b: torch.Tensor, ln_eps: float = 1e-5) -> Tuple[torch.Tensor, torch.Tensor]:
     """tokens (B,G,D) f32 -> (x (B,G,D) f32 after the last block, pooled (B,D) f32 = max_G encoder_norm(x)).
     params: 8 tensors per layer in VIT_LAYER_TENSORS order - the layer as folded by apf_model.fold_vit_layer
     (matrices bf16 [out,in], biases f32)."""
@@ -574,12 +603,12 @@ def apf_vit(tokens: torch.Tensor, params: Sequence[torch.Tensor], heads: int, bo
         ws = torch.empty((max(nbytes, 1024),), dtype=torch.uint8, device=x.device)
         with _timed("apf_vit"):
             check(_L().p3tok_apf_vit_forward(x.data_ptr(), B, G, D, int(heads), H, R, layers, nl, fw.data_ptr(), fb.data_ptr(),
-                                             pooled.data_ptr(), ws.data_ptr(), nbytes, _stream()), "apf_vit")
+                                             float(ln_eps), pooled.data_ptr(), ws.data_ptr(), nbytes, _stream()), "apf_vit")
     return x, pooled
 
 
 @apf_vit.register_fake
-def _(tokens, params, heads, bottleneck, final_w, final_b):
+def _(tokens, params, heads, bottleneck, final_w, final_b, ln_eps=1e-5):
     return tokens.new_empty(tokens.shape), tokens.new_empty((tokens.shape[0], tokens.shape[2]))
 
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define P3TOK_ABI_VERSION 1
+#define P3TOK_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define P3TOK_API __attribute__((visibility("default")))
@@ -175,9 +175,11 @@ P3TOK_API int64_t p3tok_patch_embed_workspace_bytes(const p3tok_mlp* mlp, int64_
  * P3Embed.forward iteration (src/models/pix4point.py:179-188).
  * precision: P3TOK_F32 (CUDA-core FFMA, fp32 accumulate; rtol 1e-4 contract) or P3TOK_BF16
  * (tcgen05 tensor cores, bf16 operands, fp32 accumulate in TMEM; rtol 1e-2 contract).
- * tokens: (B*G, out_dim) f32, group order as described in p3tok_rows. */
-P3TOK_API int p3tok_patch_embed(const p3tok_rows* rows, const p3tok_mlp* mlp, int precision, void* workspace,
-                      int64_t workspace_bytes, float* tokens, void* stream);
+ * tokens: (B*G, out_dim) of tokens_dtype, group order as described in p3tok_rows.  tokens_dtype: P3TOK_F32 (the
+ * reference's dtype) or, with precision P3TOK_BF16 only, P3TOK_BF16 - the patch max is rounded once, in the epilogue
+ * that produces it, so a bf16 consumer (the ViT blocks) or a host reader moves half the bytes. */
+P3TOK_API int p3tok_patch_embed(const p3tok_rows* rows, const p3tok_mlp* mlp, int precision, int tokens_dtype,
+                      void* workspace, int64_t workspace_bytes, void* tokens, void* stream);
 
 /* ---- building blocks exported for tests and for the "next" rows (pix4point.py:245 proj) -------
  * C[M,N] = act(A[M,K] W[N,K]^T + bias[N] + gbias[m / rows_per_group, N]) in fp32 on CUDA cores.
@@ -209,7 +211,7 @@ P3TOK_API int p3tok_token_head_f32(const float* tokens, const float* centres, in
  * adapter(x) + x with adapter(x) = scale * up(relu(down(adapter_norm(x)))) + x (apf_utils.py:197-233) - so the
  * layer output carries 2*x, as the reference computes it.  Attention is the explicit softmax(q k^T / sqrt(hd)) v of
  * AttentionLayer (apf_utils.py:133-160); mlp = fc1 -> exact (erf) GELU -> fc2 (timm Mlp).  Eval mode: DropPath and
- * dropout are the identity.  LayerNorm eps 1e-5.
+ * dropout are the identity.  ln_eps: the eps of norm1 / norm2 / adapter_norm / encoder_norm (nn.LayerNorm default 1e-5).
  * The descriptor holds the layer FOLDED by the host (p3tok/apf_model.py::fold_vit_layer, like the BatchNorm folding of
  * p3tok_mlp), matrices row-major [out,in] bf16, biases f32; g1/b1, g2/b2, ga/ba = affine of norm1, norm2, adapter_norm:
  *   qkv_w  [3D, D]   = qkv.weight * diag(g1)                       qkv_b  = qkv.bias + qkv.weight b1
@@ -236,8 +238,8 @@ P3TOK_API int64_t p3tok_apf_vit_workspace_bytes(int64_t B, int64_t G, int64_t D,
  * fp32 softmax; the bf16 contract of the tokenizer (rtol 1e-2) holds after 12 layers, see tests/test_gpu_vit.py. */
 P3TOK_API int p3tok_apf_vit_forward(float* x, int64_t B, int64_t G, int64_t D, int64_t heads, int64_t H, int64_t R,
                           const p3tok_vit_layer* layers, int64_t n_layers, const float* final_norm_w,
-                          const float* final_norm_b, float* pooled_out, void* workspace, int64_t workspace_bytes,
-                          void* stream);
+                          const float* final_norm_b, float ln_eps, float* pooled_out, void* workspace,
+                          int64_t workspace_bytes, void* stream);
 
 /* Building blocks of the above, exported for tests.
  * p3tok_layernorm_bf16: out = bf16(LN(x; w, b)) over the rows of x (M,D) f32; w = b = NULL: normalisation only.

@@ -342,3 +342,32 @@ def test_c3_shape_p3embed_against_oracle(kind, prec, rtol):
     for s in (1, 2):
         assert np.array_equal(ps[s].cpu().numpy(), op[s]), f"centres of stage {s - 1}"
         assert_tokens_close(fs[s].transpose(1, 2).cpu().numpy(), of[s], rtol * s, f"c3 shape ({kind}, {prec}) stage {s - 1} vs oracle")
+
+
+def test_bf16_token_output_is_the_rounded_fp32_output():
+    """token_dtype=torch.bfloat16 (bf16 path): the patch max is rounded once by the epilogue that produces it, so the
+    result equals the float32 tokens rounded to bf16 - for the APF tokenizer (fused pair epilogue, k = 32 and k = 64
+    partial-max reduction) and for the last P3Embed stage; the fp32 path refuses the option."""
+    _skip_if_unbuilt("bf16")
+    for (G, k) in ((64, 32), (32, 64)):
+        x = to_dev(synth.make_cloud("uniform", 3, 1024, 61, 3))
+        st = to_dev(synth.start_indices(3, 1024, 61))
+        sd = synth.to_torch_state(synth.apf_encoder_state(384, 6, 61))
+        nets = [PointNet(384, G, k, 6, precision="bf16", token_dtype=dt).eval().to(dev()) for dt in (None, torch.bfloat16)]
+        for n in nets:
+            n.encoder.load_state_dict(sd)
+        t32, t16 = nets[0](x, st), nets[1](x, st)
+        assert t16.dtype == torch.bfloat16 and t32.dtype == torch.float32
+        assert torch.equal(t16, t32.bfloat16())
+    p = to_dev(synth.make_cloud("uniform", 2, 1024, 62, 3))
+    starts = [to_dev(synth.start_indices(2, 1024, 62, 0)), to_dev(synth.start_indices(2, 256, 62, 1))]
+    sd = synth.to_torch_state(synth.p3embed_state(3, 1 / 16, 4, 4, 256, 62))
+    outs = []
+    for dt in (None, torch.bfloat16):
+        m = P3Embed(sample_ratio=1 / 16, k=32, precision="bf16", token_dtype=dt).eval().to(dev())
+        m.load_state_dict(sd)
+        outs.append(m(p, p.transpose(1, 2).contiguous(), starts)[1])
+    assert outs[1][1].dtype == torch.float32 and outs[1][2].dtype == torch.bfloat16     # only the last stage changes dtype
+    assert torch.equal(outs[1][1], outs[0][1]) and torch.equal(outs[1][2], outs[0][2].bfloat16())
+    with pytest.raises(ValueError):
+        PointNet(64, 8, 8, 6, precision="fp32", token_dtype=torch.bfloat16)(x, st)

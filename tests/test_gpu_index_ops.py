@@ -286,3 +286,79 @@ def test_knn_prepare_query_split_and_stream_overlap(mode):
     assert ws2.numel() == 0
     c2 = big[:, :10].contiguous()
     assert torch.equal(ops.knn_query(big, ws2, c2, 8, mode, False), ops.knn(big, c2, 8, mode, False, False)[0])
+
+
+# ------------------------------------------------------------------ round-1 advisor findings
+def test_fps_with_non_finite_points_stays_in_range():
+    """Non-finite coordinates are outside the contract (the reference assumes finite input), but every index the kernel
+    writes must stay inside the cloud - single-CTA and cluster paths."""
+    for N in (1000, 20000):
+        x = synth.make_cloud("uniform", 2, N, 9, 3)
+        x[0, 5] = np.nan
+        x[0, 7, 1] = np.inf
+        x[1] = np.nan                                     # a cloud with no finite point at all
+        idx = ops.fps(to_dev(x), to_dev(np.array([3, 0], np.int64)), 64)
+        torch.cuda.synchronize()
+        a = idx.cpu().numpy()
+        assert a.min() >= 0 and a.max() < N
+
+
+def test_group_forward_honours_the_xyz_argument():
+    """apf.py:64-71 runs FPS / kNN / Morton on the `xyz` argument; a caller passing coordinates that are not
+    x[:, :, :3] (e.g. normalised) must get the groups of THOSE coordinates, gathered from x."""
+    from p3tok.modules import Group
+    B, N, G, k = 2, 512, 16, 8
+    x = synth.make_cloud("uniform", B, N, 21, 4)
+    xyz = (x[..., :3] * np.array([1.0, 0.25, 2.0], np.float32)).astype(np.float32)     # anisotropic: different neighbours
+    st = synth.start_indices(B, N, 21)
+    neigh, center = Group(G, k)(to_dev(x), to_dev(xyz), to_dev(st))
+    fidx = oracle.fps(xyz, st, G)
+    ctr = oracle.gather_points(xyz, fidx)
+    kidx = oracle.knn(xyz, ctr, k, oracle.KNN_APF_SQ)
+    _, perm = oracle.morton(ctr)
+    cf = oracle.gather_points(x, fidx)                                                  # centre features come from x
+    nb = oracle.gather_points(x, kidx.reshape(B, -1)).reshape(B, G, k, 4) - cf[:, :, None, :]
+    ref = np.concatenate([nb, np.broadcast_to(cf[:, :, None, :], nb.shape)], -1)
+    ref = np.take_along_axis(ref, perm[:, :, None, None], 1)
+    assert np.array_equal(neigh.cpu().numpy(), ref.astype(np.float32))
+    assert np.array_equal(center.cpu().numpy(), np.take_along_axis(ctr, perm[:, :, None], 1))
+    # and the in-place fast path (xyz IS the view) still equals the oracle
+    xt = to_dev(x)
+    n2, c2 = Group(G, k)(xt, xt[:, :, :3], to_dev(st))
+    o = oracle.group_apf(x, st, G, k)
+    assert np.array_equal(n2.cpu().numpy(), o["neigh"]) and np.array_equal(c2.cpu().numpy(), o["center"])
+
+
+def test_knn_query_rejects_a_foreign_workspace():
+    B, N = 2, 1024
+    x0, x1 = (to_dev(synth.make_cloud("uniform", B, N, s, 3)) for s in (1, 2))
+    ws = ops.knn_prepare(x0)
+    ctr = x0[:, :8].contiguous()
+    ops.knn_query(x0, ws, ctr, 4, _lib.KNN_APF_SQ, False)
+    with pytest.raises(RuntimeError, match="prepared from a different"):
+        ops.knn_query(x1, ws, ctr, 4, _lib.KNN_APF_SQ, False)
+    x0.add_(1.0)                                           # modified in place since the preparation
+    with pytest.raises(RuntimeError, match="prepared from a different"):
+        ops.knn_query(x0, ws, ctr, 4, _lib.KNN_APF_SQ, False)
+
+
+def test_farthest_point_sampling_fewer_than_three_coordinates():
+    """pix4point.py:44 sums over all D coordinates; D < 3 runs zero-padded (adds exact +0 terms)."""
+    p2 = synth.make_cloud("uniform", 2, 300, 5, 3)[..., :2].copy()
+    st = synth.start_indices(2, 300, 5)
+    got = F.farthest_point_sampling(to_dev(p2), 40, to_dev(st)).cpu().numpy()
+    ref = oracle.fps(np.concatenate([p2, np.zeros((2, 300, 1), np.float32)], -1), st, 40)
+    assert np.array_equal(got, ref)
+    with pytest.raises(RuntimeError, match="D > 3"):
+        F.farthest_point_sampling(torch.zeros(1, 8, 5, device=dev()), 2)
+
+
+def test_seeded_draw_reproduces_reference_semantics():
+    """Without start_idx, furthest_point_sample takes its first index from torch's global CPU generator like
+    sampler.py:20, so the same manual_seed gives the same centres as passing that draw explicitly."""
+    x = to_dev(synth.make_cloud("uniform", 3, 256, 8, 3))
+    torch.manual_seed(77)
+    a = F.furthest_point_sample(x, 16)
+    torch.manual_seed(77)
+    st = torch.randint(0, 256, (3,), dtype=torch.long)
+    assert torch.equal(a, F.furthest_point_sample(x, 16, st.to(dev())))

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(built):
         assert hasattr(L, n), n
     assert sorted(_lib._SIGNATURES) == names      # the Python binding covers the whole header
     L.p3tok_abi_version.restype = ctypes.c_int
-    assert L.p3tok_abi_version() == 1             # host-only call, no GPU needed
+    assert L.p3tok_abi_version() == 2             # host-only call, no GPU needed
 
 
 def test_struct_layouts_match_header(tmp_path, built):
@@ -159,3 +159,36 @@ def test_fold_vit_layer_matches_oracle():
     got = 2 * x + (h @ f2w.T + f2b)
     assert np.abs(got.numpy() - ref).max() <= 1e-2 * np.abs(ref).max()      # bf16-rounded folded weights
     assert np.linalg.norm(got.numpy() - ref) <= 5e-3 * np.linalg.norm(ref)
+
+
+def test_fold_uses_the_modules_bn_eps():
+    """BatchNorm eps comes from the module, not a constant (a checkpoint built with eps = 1e-3 must fold with it)."""
+    from p3tok.modules import _bn_eps
+    enc = Encoder(32, 6).eval()
+    enc.load_state_dict(synth.to_torch_state(synth.apf_encoder_state(32, 6, 4)))
+    for m in enc.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.eps = 1e-3
+    eps = _bn_eps(enc)
+    assert set(eps) == {"first_conv.1", "first_conv.4", "second_conv.1"} and set(eps.values()) == {1e-3}
+    rows = torch.randn(4 * 8, 6)
+    with torch.no_grad():                     # the container modules ARE the reference arithmetic (same nn layers)
+        f = enc.first_conv(rows.view(4, 8, 6).transpose(1, 2))
+        g = f.max(2, keepdim=True)[0]
+        ref = enc.second_conv(torch.cat([g.expand(-1, -1, 8), f], 1)).max(2)[0]
+    got = folded_forward(fold.fold_apf_encoder(enc.state_dict(), eps), rows, 8)
+    assert float((got - ref.double()).abs().max()) <= 1e-5 * float(ref.abs().max())
+    wrong = folded_forward(fold.fold_apf_encoder(enc.state_dict()), rows, 8)       # default 1e-5: measurably different
+    assert float((wrong - ref.double()).abs().max()) > 1e-4 * float(ref.abs().max())
+
+
+def test_start_index_draws_mirror_the_reference():
+    """furthest_point_sample draws on the global CPU generator (sampler.py:20); an explicit start_idx is used as is."""
+    from p3tok.functional import _start
+    x = torch.zeros(5, 100, 3)
+    torch.manual_seed(123)
+    a = _start(x, None)
+    torch.manual_seed(123)
+    b = torch.randint(0, 100, (5,), dtype=torch.long)
+    assert torch.equal(a, b)
+    assert torch.equal(_start(x, torch.tensor([1, 2, 3, 4, 5], dtype=torch.int32)), torch.tensor([1, 2, 3, 4, 5]))
