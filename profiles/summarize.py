@@ -1,6 +1,8 @@
 """Turn gpurun_out ncu artefacts into the small text summaries committed under profiles/.
   python profiles/summarize.py launches gpurun_out/launches_X.csv > profiles/X_launches.txt
   python profiles/summarize.py full gpurun_out/prof_X.ncu-rep     > profiles/X_ncu_full.txt
+  python profiles/summarize.py traffic gpurun_out/traffic_c2.csv c2:bf16:128 1   (merges into profiles/r02_traffic.json)
+  python profiles/summarize.py sass adapting-.../p3tok/libp3tok.so           > profiles/r02_sass_opcodes.txt
 """
 import collections
 import csv
@@ -54,5 +56,88 @@ def full(path):
                 print(f"  {w:70s} {r[i]:>14s} {units[i]}")
 
 
+EMBED_KERNELS = ("tc_", "rows_", "pad_weight", "partial_max", "group_max", "sgemm", "build_rows", "embed_")
+
+
+def traffic(path, key, steps):
+    """ncu csv with dram__bytes_read.sum / dram__bytes_write.sum (+ gpu__time_duration.sum) of `steps` eager steps
+    (bench.py --ncu N under `ncu --profile-from-start off`): DRAM bytes of the patch-embedding launches per step ->
+    profiles/r02_traffic.json[key], the number bench.py prints as roofline.traffic."""
+    import json
+    import os
+    with open(path) as f:
+        lines = [l for l in f if not l.startswith("==")]
+    per_kernel = collections.OrderedDict()
+    tot = {"embed": 0.0, "other": 0.0}
+    us = {"embed": 0.0, "other": 0.0}
+    for row in csv.DictReader(lines):
+        name = row["Kernel Name"].split("(")[0].replace("void ", "").replace("p3tok::", "")
+        v = float(row["Metric Value"].replace(",", ""))
+        u = row["Metric Unit"]
+        m = row["Metric Name"]
+        cls = "embed" if name.startswith(EMBED_KERNELS) else "other"
+        if m.startswith("dram__bytes"):
+            v *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+            tot[cls] += v
+            per_kernel.setdefault(name, [0.0, 0.0, 0])
+            per_kernel[name][0] += v
+            if m.startswith("dram__bytes_read"):
+                per_kernel[name][2] += 1
+        elif m.startswith("gpu__time_duration"):
+            v = v / 1000 if u == "ns" else (v * 1000 if u == "ms" else v)
+            us[cls] += v
+            per_kernel.setdefault(name, [0.0, 0.0, 0])
+            per_kernel[name][1] += v
+    steps = int(steps)
+    out_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "r02_traffic.json")
+    d = json.load(open(out_path)) if os.path.isfile(out_path) else {}
+    d[key] = {"embed_dram_bytes_per_step": tot["embed"] / steps, "other_dram_bytes_per_step": tot["other"] / steps,
+              "embed_us_per_step_under_ncu": us["embed"] / steps,
+              "per_kernel": {k: {"dram_bytes_per_step": v[0] / steps, "us_per_step_under_ncu": v[1] / steps, "launches_per_step": v[2] / steps}
+                             for k, v in per_kernel.items()},
+              "source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum over the embed launches of {steps} eager step(s) ({os.path.basename(path)})"}
+    json.dump(d, open(out_path, "w"), indent=1, sort_keys=True)
+    print(f"{key}: embed {tot['embed'] / steps / 1e6:.1f} MB per step, other kernels {tot['other'] / steps / 1e6:.1f} MB")
+
+
+SASS_OPS = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UTMAPF", "UBLKCP", "STAS", "SYNCS",
+            "CREDUX", "HMMA", "FFMA2", "FADD2", "FMUL2", "F2FP", "MUFU.EX2", "LDSM", "LDGSTS", "UCGABAR"]
+
+
+def sass(lib):
+    """Per-kernel SASS opcode counts of the built library (cuobjdump -sass): the tcgen05 / TMEM / TMA evidence."""
+    import re
+    out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    counts = collections.OrderedDict()
+    cur = None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().split("(")[0]
+            cur = cur.replace("void ", "").replace("p3tok::", "")
+            counts.setdefault(cur, collections.Counter())
+            continue
+        if cur is None:
+            continue
+        m = re.search(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", line)
+        if m:
+            op = m.group(1)
+            counts[cur]["_all"] += 1
+            for want in SASS_OPS:
+                if op == want or op.startswith(want + "."):
+                    counts[cur][want] += 1
+    print(f"# {lib}: SASS opcode counts per kernel (cuobjdump -sass, sm_100a)")
+    print("# UTCHMMA = tcgen05.mma kind::f16 (.2CTA = cta_group::2), LDTM = tcgen05.ld, UTMALDG/UTMASTG/UTMAREDG = TMA tensor load / store / "
+          "reduce-add, UBLKCP = cp.async.bulk, STAS = st.async, CREDUX = redux.sync, HMMA = legacy mma.sync")
+    used = [o for o in SASS_OPS if any(c[o] for c in counts.values())]
+    print(f"{'kernel':70s} {'instrs':>7s} " + " ".join(f"{o:>8s}" for o in used))
+    for k, c in counts.items():
+        print(f"{k[:70]:70s} {c['_all']:7d} " + " ".join(f"{c[o]:8d}" for o in used))
+    tot = collections.Counter()
+    for c in counts.values():
+        tot.update(c)
+    print(f"{'TOTAL':70s} {tot['_all']:7d} " + " ".join(f"{tot[o]:8d}" for o in used))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic, "sass": sass}[sys.argv[1]](*sys.argv[2:])
