@@ -186,8 +186,12 @@ fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __r
   for (int g = 0; g < G; ++g) {
     if (t == 0 && rank == 0) out_idx[(size_t)cloud * G + g] = far;
     if (g == G - 1) break;
-    // Distance updates two points per instruction (FADD2 / FMUL2: each half is an IEEE fp32 op, so the reference's
-    // ((dx*dx)+(dy*dy))+(dz*dz) rounding sequence is unchanged; x - c is computed as x + (-c), bit-identical).
+    // Distance updates: the differences and the squares two points per instruction (FADD2 / FMUL2: each half is an IEEE
+    // fp32 op; x - c is computed as x + (-c), bit-identical), the two sums as SCALAR add.rn.  Round 1 also packed the sums
+    // (add.rn.f32x2): ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 despite the .rn (and -fmad=false) - a
+    // fused square differs from the reference's ((dx*dx)+(dy*dy))+(dz*dz) in the last bit for ~19 % of the pairs
+    // (profiles/microbench/f32x2_check.cu), which flips FPS picks on near-ties (found by the C3-shape parity test).  A
+    // scalar add.rn is never contracted; build() checks that the kernel's SASS holds no FFMA2.
     const float ncx = -cx, ncy = -cy, ncz = -cz;
 #pragma unroll
     for (int j = 0; j < FPS_PPT; j += 2) {
@@ -198,10 +202,10 @@ fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __r
       fps_mul2(dx0, dx1, dx0, dx1, dx0, dx1);
       fps_mul2(dy0, dy1, dy0, dy1, dy0, dy1);
       fps_mul2(dz0, dz1, dz0, dz1, dz0, dz1);
-      fps_add2(dx0, dx1, dx0, dx1, dy0, dy1);
-      fps_add2(dx0, dx1, dx0, dx1, dz0, dz1);
-      md[j] = fminf(md[j], dx0);
-      md[j + 1] = fminf(md[j + 1], dx1);
+      const float d0 = __fadd_rn(__fadd_rn(dx0, dy0), dz0);
+      const float d1 = __fadd_rn(__fadd_rn(dx1, dy1), dz1);
+      md[j] = fminf(md[j], d0);
+      md[j + 1] = fminf(md[j + 1], d1);
     }
     // thread-local maximum first; the index of the maximum is only resolved by the threads that tie with the warp's
     // maximum (usually one): lowest j == lowest point index inside a thread, lowest index wins across threads

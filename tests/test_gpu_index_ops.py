@@ -362,3 +362,16 @@ def test_seeded_draw_reproduces_reference_semantics():
     torch.manual_seed(77)
     st = torch.randint(0, 256, (3,), dtype=torch.long)
     assert torch.equal(a, F.furthest_point_sample(x, 16, st.to(dev())))
+
+
+def test_fps_many_iterations_bit_exact_near_ties():
+    """65536 dependent FPS iterations over full-mantissa coordinates: the running distances of the two best candidates
+    come within one ulp of each other about once per 10^4 iterations, so a single mis-rounded distance (round 1: a
+    contracted FFMA2) shows up as a flipped pick.  Single-CTA and cluster paths."""
+    for (B, N, G) in ((64, 2048, 1024), (4, 20000, 2048)):
+        x = synth.make_cloud("uniform", B, N, 777, 3)
+        st = synth.start_indices(B, N, 777)
+        got = ops.fps(to_dev(x), to_dev(st), G).cpu().numpy()
+        ref = oracle.fps(x, st, G)
+        bad = np.argwhere(got != ref)
+        assert bad.size == 0, f"{len(bad)} picks differ; first at cloud {bad[0][0]} iteration {bad[0][1]}"

@@ -192,3 +192,10 @@ def test_start_index_draws_mirror_the_reference():
     b = torch.randint(0, 100, (5,), dtype=torch.long)
     assert torch.equal(a, b)
     assert torch.equal(_start(x, torch.tensor([1, 2, 3, 4, 5], dtype=torch.int32)), torch.tensor([1, 2, 3, 4, 5]))
+
+
+def test_fps_kernel_sass_has_no_fused_multiply_add(built):
+    """Regression (round 2): ptxas contracted the packed distance arithmetic of fps_kernel into FFMA2, so ~19 % of the
+    squared distances differed from ((dx*dx)+(dy*dy))+(dz*dz) in the last bit and FPS picks flipped on near-ties."""
+    import __graft_entry__ as entry
+    assert entry.fps_fused_multiply_adds(built) == 0
