@@ -379,44 +379,80 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else {
-    // ---------------- tile epilogue warps: output accumulator -> bias -> bf16 store and/or 32-row max
+    // ---------------- tile epilogue warps: output accumulator -> bias -> bf16 store and/or 32-row max.
+    // The next tile's B-GEMM cannot start before these warps hand the accumulator back, so this epilogue is on the tile's
+    // critical path (round 1: 32 redux.sync per 32 columns = ~4500 cycles per tile at E = 384, 18 % of the tile).  Round 2:
+    //   "post" pair (only the patch max leaves): accumulator read as m16n8 fragments (tcgen05.ld.16x256b), 24 thread-local
+    //          FMNMX + 7 shuffles per 32 columns, bias added AFTER the max (max(x + b) == max(x) + b in fp32: rounding is
+    //          monotonic) - rows_max_frag, tc_common.cuh;
+    //   "pre" pair (bf16 store of f + bf16 patch max g): the max is read back from the swizzled store box the TMA store
+    //          reads anyway (32 LDS.32 + HMNMX2 per 64 columns) - box_rows_max_bf16x2.
     const int ew = warp - 2 - FU_CH_WARPS;
     const int q = warp & 3, h = ew >> 2;
     const uint32_t lane_field = (uint32_t)(q * 32) << 16;
     uint8_t* stg = sST + ew * 4096;
     const int ngroups = p.N2 / 64;
+    const int fcol = rows_max_frag_col(lane);
     int it = 0;
     for (int tp = pair_id; tp < p.num_pairs; tp += pair_stride, ++it) {
       const int row0 = (2 * tp + rank) * TC_BM + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
+      const int nvalid = p.M - row0 >= 32 ? 32 : (p.M - row0 > 0 ? p.M - row0 : 0);
       const bool tr = (warp == 2 + FU_CH_WARPS && lane == 0);
       if (tr) fu_trace(p, it, 0, 12, clock64());
       mbar_wait(acc3_full, (uint32_t)(it & 1));
       if (tr) fu_trace(p, it, 0, 13, clock64());
       tc_fence_after();
       bool released = false;
-      for (int gi = h; gi < ngroups; gi += 2) {
-        const int n0 = gi * 64;
-        const bool last = gi + 2 >= ngroups;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float v[32];
-          tc_ld32_issue(tmem_base + lane_field + (uint32_t)(n0 + half * 32), v);
+      if (!p.store_out) {
+        for (int gi = h; gi < ngroups; gi += 2) {
+          const int n0 = gi * 64;
+          const bool last = gi + 2 >= ngroups;
+          float a0[16], b0[16], a1[16], b1[16];
+          const uint32_t t0 = tmem_base + lane_field + (uint32_t)n0;
+          tc_ld16x256_x4_issue(t0, a0);
+          tc_ld16x256_x4_issue(t0 + (16u << 16), b0);
+          tc_ld16x256_x4_issue(t0 + 32u, a1);
+          tc_ld16x256_x4_issue(t0 + 32u + (16u << 16), b1);
           tc_ld_wait();
-          if (last && half == 1) {
+          if (last) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cta(acc3_empty, 0);      // the next tile's B-GEMM may overwrite the accumulator
             if (tr) fu_trace(p, it, 0, 14, clock64());
             released = true;
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sbb + n0 + half * 32 + 4 * i);
-            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+          float m0 = rows_max_frag(a0, b0, lane, nvalid) + sbb[n0 + fcol];
+          float m1 = rows_max_frag(a1, b1, lane, nvalid) + sbb[n0 + 32 + fcol];
+          if (p.max_relu) { m0 = fmaxf(m0, 0.f); m1 = fmaxf(m1, 0.f); }
+          if (row0 < p.M) {
+            const size_t o = (size_t)(row0 >> 5) * p.N2 + n0 + fcol;
+            if (p.out_max) { p.out_max[o] = m0; p.out_max[o + 32] = m1; }
+            if (p.out_max_bf16) { p.out_max_bf16[o] = __float2bfloat16_rn(m0); p.out_max_bf16[o + 32] = __float2bfloat16_rn(m1); }
           }
-          if (p.store_out) {
+        }
+      } else {
+        for (int gi = h; gi < ngroups; gi += 2) {
+          const int n0 = gi * 64;
+          const bool last = gi + 2 >= ngroups;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float v[32];
+            tc_ld32_issue(tmem_base + lane_field + (uint32_t)(n0 + half * 32), v);
+            tc_ld_wait();
+            if (last && half == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cta(acc3_empty, 0);
+              if (tr) fu_trace(p, it, 0, 14, clock64());
+              released = true;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sbb + n0 + half * 32 + 4 * i);
+              v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+            }
             if (half == 0) {   // the previous box of this warp has left shared memory
               if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
               __syncwarp();
@@ -430,22 +466,16 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                            "r"(pack_bf16x2(v[pc * 8 + 6], v[pc * 8 + 7]))
                            : "memory");
             }
-          }
-          if (p.out_max || p.out_max_bf16) {
-            if (!row_ok) {
+            if (p.out_max) {   // fp32 patch max next to the bf16 store (not used by the tokenizer's orchestration)
+              if (!row_ok) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = -3.0e38f;
-            }
-            float m = warp_rows_max(v, lane);
-            if (p.max_relu) m = fmaxf(m, 0.f);
-            const size_t o = (size_t)(row0 >> 5) * p.N2 + n0 + half * 32 + lane;
-            if (row0 < p.M) {
-              if (p.out_max) p.out_max[o] = m;
-              if (p.out_max_bf16) p.out_max_bf16[o] = __float2bfloat16_rn(m);
+                for (int i = 0; i < 32; ++i) v[i] = -3.0e38f;
+              }
+              float m = warp_rows_max(v, lane);
+              if (p.max_relu) m = fmaxf(m, 0.f);
+              if (row0 < p.M) p.out_max[(size_t)(row0 >> 5) * p.N2 + n0 + half * 32 + lane] = m;
             }
           }
-        }
-        if (p.store_out) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0 && row0 < p.M) {
@@ -454,6 +484,11 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                          "r"(smem_u32(stg)), "r"(n0), "r"(row0)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          if (p.out_max_bf16 && row0 < p.M) {   // the patch max of the values just staged (what the next GEMM reads, rounded once)
+            uint32_t m = box_rows_max_bf16x2(smem_u32(stg), lane, nvalid);
+            if (p.max_relu) asm("max.bf16x2 %0, %0, %1;" : "+r"(m) : "r"(0u));
+            *reinterpret_cast<uint32_t*>(p.out_max_bf16 + (size_t)(row0 >> 5) * p.N2 + n0 + 2 * lane) = m;
           }
           __syncwarp();
         }

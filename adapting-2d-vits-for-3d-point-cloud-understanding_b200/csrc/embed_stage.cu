@@ -291,18 +291,26 @@ tc_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int tp = pair_id; tp < p.num_pairs; tp += pair_stride, ++it) {
       const int s = it & 1;
       const int row0 = (2 * tp + rank) * TC_BM + q * 32;
-      const bool row_ok = row0 + lane < p.M;
       const bool tr = (warp == 2 + ST_E1_WARPS && lane == 0);
       if (tr) st_trace(p, it, 11);
       mbar_wait(&acc2_full[s], (uint32_t)(it >> 1) & 1);
       if (tr) st_trace(p, it, 12);
       tc_fence_after();
+      // 32-row max straight from the m16n8 accumulator fragments (rows_max_frag, tc_common.cuh: 7 shuffles per 32 columns
+      // instead of 32 redux.sync); the bias is added after the max (exactly the same value: fp32 rounding is monotonic)
+      const int nvalid = p.M - row0 >= 32 ? 32 : (p.M - row0 > 0 ? p.M - row0 : 0);
+      const int fcol = rows_max_frag_col(lane);
       for (int pc0 = 0; pc0 < pieces; pc0 += 2) {
         const bool two = pc0 + 1 < pieces;
         const int c0 = h * half_cols + pc0 * 32;
-        float v0[32], v1[32];
-        tc_ld32_issue(tmem_base + lane_field + (uint32_t)(s * ST_ACC_COLS + c0), v0);
-        if (two) tc_ld32_issue(tmem_base + lane_field + (uint32_t)(s * ST_ACC_COLS + c0 + 32), v1);
+        float a0[16], b0[16], a1[16], b1[16];
+        const uint32_t t0 = tmem_base + lane_field + (uint32_t)(s * ST_ACC_COLS + c0);
+        tc_ld16x256_x4_issue(t0, a0);
+        tc_ld16x256_x4_issue(t0 + (16u << 16), b0);
+        if (two) {
+          tc_ld16x256_x4_issue(t0 + 32u, a1);
+          tc_ld16x256_x4_issue(t0 + 32u + (16u << 16), b1);
+        }
         tc_ld_wait();
         if (pc0 + 2 >= pieces) {        // last accumulator read of this warp: GEMM 1 of tile t+2 may overwrite it
           tc_fence_before();
@@ -310,22 +318,20 @@ tc_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (lane == 0) mbar_arrive_cta(&acc_free[s], 0);
           if (tr) st_trace(p, it, 13);
         }
-        if (!row_ok) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) { v0[i] = -3.0e38f; v1[i] = -3.0e38f; }
-        }
-        float m = warp_rows_max(v0, lane) + sbb[c0 + lane];
+        float m = rows_max_frag(a0, b0, lane, nvalid) + sbb[c0 + fcol];
         if (p.max_relu) m = fmaxf(m, 0.f);
         if (row0 < p.M) {
-          if (p.out_max) p.out_max[(size_t)(row0 >> 5) * p.N2 + c0 + lane] = m;
-          if (p.out_max_bf16) p.out_max_bf16[(size_t)(row0 >> 5) * p.N2 + c0 + lane] = __float2bfloat16_rn(m);
+          const size_t o = (size_t)(row0 >> 5) * p.N2 + c0 + fcol;
+          if (p.out_max) p.out_max[o] = m;
+          if (p.out_max_bf16) p.out_max_bf16[o] = __float2bfloat16_rn(m);
         }
         if (two) {
-          float m1 = warp_rows_max(v1, lane) + sbb[c0 + 32 + lane];
+          float m1 = rows_max_frag(a1, b1, lane, nvalid) + sbb[c0 + 32 + fcol];
           if (p.max_relu) m1 = fmaxf(m1, 0.f);
           if (row0 < p.M) {
-            if (p.out_max) p.out_max[(size_t)(row0 >> 5) * p.N2 + c0 + 32 + lane] = m1;
-            if (p.out_max_bf16) p.out_max_bf16[(size_t)(row0 >> 5) * p.N2 + c0 + 32 + lane] = __float2bfloat16_rn(m1);
+            const size_t o = (size_t)(row0 >> 5) * p.N2 + c0 + 32 + fcol;
+            if (p.out_max) p.out_max[o] = m1;
+            if (p.out_max_bf16) p.out_max_bf16[o] = __float2bfloat16_rn(m1);
           }
         }
       }

@@ -1216,6 +1216,19 @@ __global__ void partial_max_kernel(const float* __restrict__ in, int64_t ngroups
   }
 }
 
+// the same for bf16 partial maxima (the fused "pre" pair emits its 32-row maxima in bf16, read back from its store boxes)
+__global__ void partial_max_bf16_kernel(const __nv_bfloat16* __restrict__ in, int64_t ngroups, int parts, int C,
+                                        __nv_bfloat16* __restrict__ out) {
+  const int64_t total = ngroups * C;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = e / C;
+    const int c = (int)(e - g * C);
+    float m = __bfloat162float(in[(g * parts) * C + c]);
+    for (int q = 1; q < parts; ++q) m = fmaxf(m, __bfloat162float(in[(g * parts + q) * C + c]));
+    out[e] = __float2bfloat16_rn(m);
+  }
+}
+
 // generic group max for k not a multiple of 32: in fp32 [ngroups*k, C]
 __global__ void group_max_f32_kernel(const float* __restrict__ in, int64_t ngroups, int k, int C, int relu, float* out_f32,
                                      __nv_bfloat16* out_bf16) {
@@ -1418,13 +1431,16 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
     if (fuse_pre) {
       // both tensor-core per-point layers in one kernel: the (rows x pre_dim[n-2]) hidden activation stays on-chip
       const int i0 = m->n_pre - 2, i1 = m->n_pre - 1;
+      // the pair's epilogue emits the max of every 32 rows in bf16 (read back from its store boxes); k = 32*parts rows
+      // per patch: the partial maxima go through the (otherwise unused) fp32 scratch and are combined below
+      __nv_bfloat16* part_bf16 = reinterpret_cast<__nv_bfloat16*>(gmax_f32);
       rc = tc_fused(act[cur], rows, kin, (const __nv_bfloat16*)m->w_pre[i0], m->pre_dim[i0], m->b_pre[i0], nullptr, 32,
                     (const __nv_bfloat16*)m->w_pre[i1], m->pre_dim[i1], m->b_pre[i1], act[cur ^ 1],
-                    parts == 1 ? nullptr : gmax_f32, parts == 1 ? gmax_bf16 : nullptr, 0, s);
+                    nullptr, parts == 1 ? gmax_bf16 : part_bf16, 0, s);
       if (rc) return rc;
       if (parts > 1) {
-        partial_max_kernel<<<grid_1d(gc * L.F, 256), 256, 0, s>>>(gmax_f32, gc, parts, (int)L.F, nullptr, gmax_bf16);
-        P3_LAUNCH_CHECK("partial_max_kernel");
+        partial_max_bf16_kernel<<<grid_1d(gc * L.F, 256), 256, 0, s>>>(part_bf16, gc, parts, (int)L.F, gmax_bf16);
+        P3_LAUNCH_CHECK("partial_max_bf16_kernel");
       }
       have_gmax = true;
       cur ^= 1;

@@ -231,6 +231,91 @@ __device__ __forceinline__ float warp_rows_max_shfl(float (&v)[32], int lane) {
   return v[0];
 }
 
+// ---- 32-row max straight from tensor memory --------------------------------------------------------------------------
+// tcgen05.ld.16x256b hands a thread the m16n8 accumulator fragment: registers 4s+{0,1} = (lane t/4, columns 8s + 2(t%4) +
+// {0,1}), registers 4s+{2,3} = (lane t/4 + 8, same columns) (mapping read back on a B200: profiles/microbench/
+// rowmax_bench.cu).  Two such loads (lanes +0..15 and +16..31 of the warp's quarter) put rows r, r+8, r+16, r+24 of a column
+// pair into ONE thread, so 24 thread-local FMNMX leave only 8 row classes to reduce across lanes: a halving butterfly of
+// 4 + 2 + 1 = 7 shuffles per 32 columns, against 32 redux.sync (~13 cycles each on the shared CREDUX unit: the 4500-cycle
+// tile epilogue of the fused pair, profiles/r02_fused_trace.txt) or 31 shuffles after a 32x32b load.
+__device__ __forceinline__ void tc_ld16x256_x4_issue(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// column (0..31) whose maximum lane t holds after rows_max_frag()
+__device__ __forceinline__ int rows_max_frag_col(int lane) {
+  return 8 * (2 * ((lane >> 4) & 1) + ((lane >> 3) & 1)) + 2 * (lane & 3) + ((lane >> 2) & 1);
+}
+// a = fragment of lanes +0..15, b = of lanes +16..31 (both already waited for); nvalid = rows of the 32 that exist (< 32 only
+// in the last, ragged row block: the others are masked out).  Returns in lane t the max of column rows_max_frag_col(t).
+__device__ __forceinline__ float rows_max_frag(float (&a)[16], float (&b)[16], int lane, int nvalid) {
+  if (nvalid < 32) {                                   // warp-uniform
+    const int r = lane >> 2;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (r >= nvalid) a[4 * s + e] = -3.0e38f;
+        if (r + 8 >= nvalid) a[4 * s + 2 + e] = -3.0e38f;
+        if (r + 16 >= nvalid) b[4 * s + e] = -3.0e38f;
+        if (r + 24 >= nvalid) b[4 * s + 2 + e] = -3.0e38f;
+      }
+    }
+  }
+  float m[8];                                          // m[2s+e]: column 8s + 2(t%4) + e over rows {t/4, +8, +16, +24}
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) m[2 * s + e] = fmaxf(fmaxf(a[4 * s + e], a[4 * s + 2 + e]), fmaxf(b[4 * s + e], b[4 * s + 2 + e]));
+  }
+  {
+    const bool hi = (lane & 16) != 0;                  // keep column sub-blocks {2,3} if hi else {0,1}
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float send = hi ? m[j] : m[j + 4];
+      const float keep = hi ? m[j + 4] : m[j];
+      m[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+    }
+  }
+  {
+    const bool hi = (lane & 8) != 0;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float send = hi ? m[j] : m[j + 2];
+      const float keep = hi ? m[j + 2] : m[j];
+      m[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+    }
+  }
+  {
+    const bool hi = (lane & 4) != 0;
+    const float send = hi ? m[0] : m[1];
+    const float keep = hi ? m[1] : m[0];
+    m[0] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+  }
+  return m[0];
+}
+// max over `nvalid` (<= 32) rows of a 32-row x 64-column bf16 store box (rows of 128 B, 16-byte chunks XOR-swizzled by row,
+// as the epilogues stage it for a TMA store): lane l reads its two columns (2l, 2l+1) of every row - 32 conflict-free
+// LDS.32 + 31 HMNMX2, nothing on the CREDUX unit and no second accumulator read.  bf16 rounding is monotonic, so this equals
+// the rounded fp32 max.  Returns bf16x2 {column 2l, column 2l+1}.
+__device__ __forceinline__ uint32_t box_rows_max_bf16x2(uint32_t sbox, int lane, int nvalid) {
+  const uint32_t chunk = (uint32_t)(lane >> 2), within = (uint32_t)(lane & 3) * 4u;
+  uint32_t m = 0xff80ff80u;                            // {-inf, -inf}
+#pragma unroll 8
+  for (int r = 0; r < nvalid; ++r) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(sbox + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4) + within));
+    asm("max.bf16x2 %0, %0, %1;" : "+r"(m) : "r"(v));
+  }
+  return m;
+}
+
 // (o0, o1) = (a0 + b0, a1 + b1) as one packed FADD2
 __device__ __forceinline__ void add2(float& o0, float& o1, float a0, float a1, float b0, float b1) {
   asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd; }"

@@ -370,4 +370,4 @@ def test_bf16_token_output_is_the_rounded_fp32_output():
     assert outs[1][1].dtype == torch.float32 and outs[1][2].dtype == torch.bfloat16     # only the last stage changes dtype
     assert torch.equal(outs[1][1], outs[0][1]) and torch.equal(outs[1][2], outs[0][2].bfloat16())
     with pytest.raises(ValueError):
-        PointNet(64, 8, 8, 6, precision="fp32", token_dtype=torch.bfloat16)(x, st)
+        PointNet(64, 8, 8, 6, precision="fp32", token_dtype=torch.bfloat16).eval().to(dev())(x, st)
