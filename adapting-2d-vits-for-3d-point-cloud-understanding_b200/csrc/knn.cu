@@ -628,8 +628,20 @@ static KnsPtrs kns_ptrs(void* workspace, int64_t B, int64_t N) {
   return p;
 }
 
-// The preparation half (depends on the clouds only, not on the centres: a caller can run it on a second stream while
-// FPS picks the centres) ...
+namespace p3tok {
+// views into a prepared workspace for the block-culled FPS (fps_culled.cu)
+int kns_workspace_views(const void* workspace, int64_t workspace_bytes, int64_t B, int64_t N, const float4** pts, const int** ids,
+                        const float** bb) {
+  P3_REQUIRE(N > 0 && N <= KNS_MAX_N && B >= 0, P3TOK_ERR_UNSUPPORTED, "sorted workspace: N=%lld outside (0, %d]", (long long)N, KNS_MAX_N);
+  P3_REQUIRE(workspace_bytes >= kns_layout(B, N).total, P3TOK_ERR_WORKSPACE, "sorted workspace %lld < %lld bytes",
+             (long long)workspace_bytes, (long long)kns_layout(B, N).total);
+  const KnsPtrs w = kns_ptrs(const_cast<void*>(workspace), B, N);
+  *pts = w.pts; *ids = w.ids; *bb = w.bb;
+  return P3TOK_OK;
+}
+}  // namespace p3tok
+
+// The preparation half (depends on the clouds only, not on the centres) ...
 extern "C" int p3tok_knn_prepare(const float* x, int64_t B, int64_t N, int64_t pt_stride, void* workspace, int64_t workspace_bytes,
                                  void* stream) {
   P3_REQUIRE(B >= 0 && N > 0 && pt_stride >= 3, P3TOK_ERR_INVALID, "knn_prepare: bad shape");
