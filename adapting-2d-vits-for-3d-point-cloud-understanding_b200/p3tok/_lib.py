@@ -70,6 +70,16 @@ _SIGNATURES = {
     "p3tok_linear_bf16": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp]),
     "p3tok_token_head_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64] + [_vp] * 12),
     "p3tok_group_max": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
+    "p3tok_linear_tn_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _vp]),
+    "p3tok_colstats_f32": (_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
+    "p3tok_bn_act_f32": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _int, _vp, _vp]),
+    "p3tok_bn_bwd_stats_f32": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp]),
+    "p3tok_bn_bwd_apply_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp]),
+    "p3tok_group_max_arg_f32": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "p3tok_group_max_bwd_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _vp, _vp]),
+    "p3tok_group_sum_f32": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
+    "p3tok_scatter_rows_add_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "p3tok_build_rows_f32": (_int, [ctypes.POINTER(RowsStruct), _vp, _vp]),
     "p3tok_apf_vit_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64, _i64]),
     "p3tok_apf_vit_forward": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, ctypes.POINTER(VitLayerStruct), _i64, _vp, _vp,
                                      _f32, _vp, _vp, _i64, _vp]),

@@ -6,10 +6,11 @@ signatures and the same state_dict keys, running on the sm_100a kernels.
 
 The parameter containers (Conv1d/BatchNorm1d/... inside nn.Sequential at the reference's
 indices) exist so reference checkpoints load with strict=True; forward never calls them.
-BatchNorm is applied in eval mode (running statistics folded into the weights, p3tok/fold.py);
-calling forward in training mode raises - train-mode BN couples clouds and needs backward
-(SURVEY.md 8f "next" #4).  `precision`: "fp32" (CUDA-core FFMA, rtol 1e-4 contract) or "bf16"
-(tcgen05 tensor cores, rtol 1e-2 contract).
+eval():  BatchNorm uses the running statistics, folded into the weights (p3tok/fold.py); `precision` selects
+         "fp32" (CUDA-core FFMA, rtol 1e-4 contract) or "bf16" (tcgen05 tensor cores, rtol 1e-2 contract).
+train(): batch-statistics BatchNorm (running estimates updated like nn.BatchNorm) and autograd through both
+         max-pools, the concat and the gather - p3tok/train.py over csrc/train.cu, fp32 (SURVEY.md 8f "next" #4);
+         `sync_bn=True` all-reduces the BatchNorm sums when the batch is sharded over ranks.
 """
 from __future__ import annotations
 
@@ -19,7 +20,7 @@ from typing import List, Optional, Tuple
 import torch
 from torch import nn
 
-from . import _lib, fold, ops
+from . import _lib, fold, ops, train
 from .functional import _start
 
 
@@ -110,11 +111,12 @@ class Group(nn.Module):
 class Encoder(nn.Module, _FoldedMixin):
     """apf.py:114-181.  forward(point_groups (B,G,k,Cin)) -> (B,G,E)."""
 
-    def __init__(self, encoder_channel: int, in_channel: int, precision: str = "fp32", token_dtype=None):
+    def __init__(self, encoder_channel: int, in_channel: int, precision: str = "fp32", token_dtype=None, sync_bn: bool = False):
         super().__init__()
         self.encoder_channel = encoder_channel
         self.precision = precision
         self.token_dtype = token_dtype
+        self.sync_bn = sync_bn                  # train mode: all-reduce the BatchNorm sums over torch.distributed ranks
         E = encoder_channel
         self.first_conv = nn.Sequential(
             nn.Conv1d(in_channel, 256, 1), nn.BatchNorm1d(256), nn.ReLU(inplace=True),
@@ -129,8 +131,10 @@ class Encoder(nn.Module, _FoldedMixin):
                             _check_precision(self.precision))
 
     def forward(self, point_groups: torch.Tensor) -> torch.Tensor:
-        self._require_eval()
         B, G, k, cin = point_groups.shape
+        if self.training:                       # batch-statistics BatchNorm + autograd (p3tok/train.py), fp32
+            rows = point_groups.float().reshape(B * G * k, cin)
+            return train.encoder_train(self, rows, k, self.sync_bn).view(B, G, self.encoder_channel)
         m = self.folded(point_groups.device)
         rows = point_groups.float().reshape(B * G * k, cin)
         tok = ops.patch_embed(_lib.ROWS_DIRECT, rows, None, None, None, None, B * G, k, m.tensors(), m.meta(),
@@ -146,17 +150,20 @@ class PointNet(nn.Module):
     output row."""
 
     def __init__(self, embed_dim: int, num_group: int, group_size: int, in_channel: int, precision: str = "fp32",
-                 token_dtype=None):
+                 token_dtype=None, sync_bn: bool = False):
         super().__init__()
         self.group = Group(num_group, group_size)
-        self.encoder = Encoder(embed_dim, in_channel, precision, token_dtype)
+        self.encoder = Encoder(embed_dim, in_channel, precision, token_dtype, sync_bn)
 
     def forward(self, x: torch.Tensor, start_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
-        self.encoder._require_eval()
         x = x.float().contiguous()
         B, N, C = x.shape
         G, k = self.group.num_group, self.group.group_size
-        fps_idx, _, knn_idx, perm = self.group.indices(x, start_idx)
+        with torch.no_grad():
+            fps_idx, _, knn_idx, perm = self.group.indices(x, start_idx)
+        if self.encoder.training:               # train mode: the gathered rows feed the batch-statistics Encoder (p3tok/train.py)
+            rows = train.apf_rows(x, fps_idx, knn_idx, perm)
+            return train.encoder_train(self.encoder, rows, k, self.encoder.sync_bn).view(B, G, -1)
         m = self.encoder.folded(x.device)
         if m.cin != 2 * C:
             raise RuntimeError(f"PointNet: in_channel={m.cin} but input has C={C} (expects in_channel == 2*C)")
@@ -171,7 +178,8 @@ class P3Embed(nn.Module, _FoldedMixin):
     Features are kept channel-last internally; the returned feature tensors are (B,W,G) views."""
 
     def __init__(self, in_channels: int = 3, sample_ratio: float = 0.25, scale: int = 4, k: int = 32,
-                 layers: int = 4, embed_dim: int = 256, precision: str = "fp32", token_dtype=None, **kwargs):
+                 layers: int = 4, embed_dim: int = 256, precision: str = "fp32", token_dtype=None, sync_bn: bool = False,
+                 **kwargs):
         super().__init__()
         if layers != 4:
             raise ValueError("p3tok P3Embed supports the reference's layers=4 layout only")
@@ -179,6 +187,7 @@ class P3Embed(nn.Module, _FoldedMixin):
         self.k = k
         self.precision = precision
         self.token_dtype = token_dtype          # dtype of the LAST stage's tokens (earlier stages feed the next gather in f32)
+        self.sync_bn = sync_bn                  # train mode: all-reduce the BatchNorm sums over torch.distributed ranks
         stages = int(math.log(1 / sample_ratio, scale))
         embed_dim = int(embed_dim // 2 ** (stages - 1))
         self.convs = nn.ModuleList()
@@ -209,7 +218,8 @@ class P3Embed(nn.Module, _FoldedMixin):
 
     def forward(self, p: torch.Tensor, f: torch.Tensor, start_idx: Optional[List[torch.Tensor]] = None
                 ) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
-        self._require_eval()
+        if self.training:
+            return self._forward_train(p, f, start_idx)
         bf16 = _check_precision(self.precision)
         B, N = int(p.shape[0]), int(p.shape[1])
         out_p, out_f = [p], [f]
@@ -231,6 +241,35 @@ class P3Embed(nn.Module, _FoldedMixin):
             out_p.append(ctr)
             out_f.append(feat.transpose(1, 2))
         return out_p, out_f
+
+
+def _p3embed_forward_train(self, p, f, start_idx=None):
+    """P3Embed.forward in train mode (pix4point.py:166-191): index ops without gradient, differentiable gather of the rows
+    (points and features collect the gradients of every neighbourhood they appear in), batch-statistics stage MLP."""
+    B, N = int(p.shape[0]), int(p.shape[1])
+    out_p, out_f = [p], [f]
+    pts = p.float()
+    feat = f.float().transpose(1, 2)                             # channel-last (B,N,D)
+    for s, (conv1, conv2) in enumerate(self.convs):
+        N = N // 4
+        G = min(N, int(pts.shape[1]))
+        st = None if start_idx is None else start_idx[s]
+        with torch.no_grad():
+            pd = pts.detach().contiguous()
+            cidx, ws = ops.fps_with_knn_prepare(pd, _start(pd, st, device_draw=True), G)
+            ctr_nd = ops.gather_points(pd, cidx)
+            kidx = ops.knn_query(pd, ws, ctr_nd, self.k, _lib.KNN_P4P_CDIST, True)
+        ctr = torch.gather(pts, 1, cidx.unsqueeze(-1).expand(-1, -1, 3))     # pix4point.py:176 (differentiable like the reference)
+        rows = train.GatherRowsFn.apply(pts.contiguous(), feat.contiguous(), kidx)
+        tok = train.p3stage_train(conv1, conv2, rows, self.k, self.sync_bn)
+        feat = tok.view(B, G, -1)
+        pts = ctr
+        out_p.append(ctr)
+        out_f.append(feat.transpose(1, 2))
+    return out_p, out_f
+
+
+P3Embed._forward_train = _p3embed_forward_train
 
 
 class PointViTTokens(nn.Module):

@@ -262,6 +262,45 @@ P3TOK_API int p3tok_linear_bf16_ex(const void* A, int64_t M, int64_t K, const vo
                          int64_t gelu_cols, const float* residual, float res_mul, float out_scale, void* out_bf16,
                          float* out_f32, void* stream);
 
+/* ---- "next" row 4: training-mode building blocks ------------------------------------------------------
+ * The reference trains the tokenizer (src/models/apf.py:335-346 keeps the "encoder" parameters trainable; Pix4Point
+ * trains everything): nn.BatchNorm1d/2d in TRAIN mode (batch statistics, biased variance for the normalisation, running
+ * estimates updated with the unbiased one; apf.py:129-143, pix4point.py:135-156) and autograd through Encoder.forward
+ * (apf.py:145-181) / P3Embed.forward (pix4point.py:171-189).  fp32 on CUDA cores, fp64 accumulation of per-channel sums.
+ * The host side (p3tok/train.py) strings these together as torch.autograd.Functions; dX = dY W reuses p3tok_linear_f32
+ * with the transposed matrix.  All matrices row-major; "M" = rows (groups * k), "N" = channels. */
+/* dW[N,K] (+)= dY[M,N]^T X[M,K]  (weight gradient of Y = X W^T); accumulate = 0 overwrites. */
+P3TOK_API int p3tok_linear_tn_f32(const float* dY, const float* X, int64_t M, int64_t N, int64_t K, float* dW, int accumulate,
+                        void* stream);
+/* sum[c] = sum_m X[m,c], sumsq[c] = sum_m X[m,c]^2 (both overwritten): the batch statistics of a BatchNorm; a sharded
+ * batch all-reduces these two vectors (and the row count) before the mean / variance are formed (SyncBN). */
+P3TOK_API int p3tok_colstats_f32(const float* X, int64_t M, int64_t N, double* sum, double* sumsq, void* stream);
+/* Y = act(gamma * (Z - mean) * rstd + beta), act = ReLU if relu else identity (nn.BatchNorm forward in train mode). */
+P3TOK_API int p3tok_bn_act_f32(const float* Z, int64_t M, int64_t N, const float* mean, const float* rstd, const float* gamma,
+                     const float* beta, int relu, float* Y, void* stream);
+/* Backward of the above for dY = dL/dY: with dy' = dY * [Y > 0] (ReLU) and xhat = (Z - mean) rstd,
+ *   stats: s1[c] = sum_m dy' (= dbeta), s2[c] = sum_m dy' xhat (= dgamma)   (overwritten; all-reduced when sharded)
+ *   apply: dZ = gamma rstd (dy' - s1/count - xhat s2/count),  count = rows of the whole (global) batch. */
+P3TOK_API int p3tok_bn_bwd_stats_f32(const float* dY, const float* Z, int64_t M, int64_t N, const float* mean, const float* rstd,
+                           const float* gamma, const float* beta, int relu, double* s1, double* s2, void* stream);
+P3TOK_API int p3tok_bn_bwd_apply_f32(const float* dY, const float* Z, int64_t M, int64_t N, int64_t count, const float* mean,
+                           const float* rstd, const float* gamma, const float* beta, int relu, const double* s1,
+                           const double* s2, float* dZ, void* stream);
+/* torch.max over the k rows of a group with its index (first maximum): X [G*k, C] -> out [G, C], arg [G, C] in [0,k). */
+P3TOK_API int p3tok_group_max_arg_f32(const float* X, int64_t G, int64_t k, int64_t C, float* out, int32_t* arg, void* stream);
+/* its backward: dX[(g*k + r), c] (+)= (r == arg[g,c]) ? dOut[g,c] : 0  (accumulate = 0 overwrites every element). */
+P3TOK_API int p3tok_group_max_bwd_f32(const float* dOut, const int32_t* arg, int64_t G, int64_t k, int64_t C, int accumulate,
+                            float* dX, void* stream);
+/* out[g,c] = sum over the k rows of group g (the gradient the expanded global feature collects, apf.py:162). */
+P3TOK_API int p3tok_group_sum_f32(const float* X, int64_t G, int64_t k, int64_t C, float* out, void* stream);
+/* Gradient of the kNN gather of group_knn (pix4point.py:92-102): dRows (B,G,k,3+D), idx (B,G,k) int32 ->
+ * dP (B,N,3) += xyz part, dF (B,N,D) += feature part (atomic adds; either output may be NULL). */
+P3TOK_API int p3tok_scatter_rows_add_f32(const float* dRows, const int32_t* idx, int64_t B, int64_t N, int64_t G, int64_t k,
+                               int64_t D, float* dP, float* dF, void* stream);
+/* The gathered row matrix a p3tok_rows descriptor (kind 0 or 1) stands for: X (B*G*k, cin) f32 - the training path's
+ * input (the inference path never materialises it). */
+P3TOK_API int p3tok_build_rows_f32(const p3tok_rows* rows, float* X, void* stream);
+
 /* out[g, c] = max over r < k of in[(g*k + r), c]   (torch.max(..., dim=k-axis)) */
 P3TOK_API int p3tok_group_max(const float* in, int64_t ngroups, int64_t k, int64_t C, float* out, void* stream);
 

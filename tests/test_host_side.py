@@ -101,8 +101,8 @@ def test_no_cpu_fallback():
         PointNet(32, 4, 4, 6).eval()(x)
 
 
-def test_train_mode_is_rejected():
-    with pytest.raises(RuntimeError, match="eval"):
+def test_train_mode_has_no_cpu_fallback_either():
+    with pytest.raises(RuntimeError, match="CUDA"):          # train mode runs csrc/train.cu: CPU tensors are refused, not emulated
         Encoder(32, 6).train()(torch.zeros(1, 2, 4, 6))
     with pytest.raises(ValueError):
         Encoder(32, 6, precision="fp16").eval()(torch.zeros(1, 2, 4, 6))
@@ -199,3 +199,19 @@ def test_fps_kernel_sass_has_no_fused_multiply_add(built):
     squared distances differed from ((dx*dx)+(dy*dy))+(dz*dz) in the last bit and FPS picks flipped on near-ties."""
     import __graft_entry__ as entry
     assert entry.fps_fused_multiply_adds(built) == 0
+
+
+def test_bn_statistics_combination_matches_batchnorm():
+    """Host logic of the train-mode BatchNorm (p3tok.train.combine_stats): (sum, sum of squares, rows) -> mean, rstd and the
+    unbiased variance nn.BatchNorm1d puts into running_var; summing the per-shard triples first (SyncBN) gives the same."""
+    from p3tok import train
+    torch.manual_seed(3)
+    x = torch.randn(200, 7, dtype=torch.float64) * 3 + 1
+    bn = torch.nn.BatchNorm1d(7).double().train()
+    y = bn(x)
+    mean, rstd, var_unb = train.combine_stats(x.sum(0), (x * x).sum(0), 200.0, bn.eps)
+    assert torch.allclose((x - mean) * rstd, y, atol=1e-10)
+    assert torch.allclose(bn.running_var, 0.9 * torch.ones(7, dtype=torch.float64) + 0.1 * var_unb, atol=1e-12)
+    a, b = x[:80], x[80:]
+    m2, r2, v2 = train.combine_stats(a.sum(0) + b.sum(0), (a * a).sum(0) + (b * b).sum(0), 200.0, bn.eps)
+    assert torch.allclose(m2, mean) and torch.allclose(r2, rstd) and torch.allclose(v2, var_unb)
