@@ -57,6 +57,7 @@ extern "C" int64_t p3tok_patch_embed_workspace_bytes(const p3tok_mlp* mlp, int64
   if (!mlp || ngroups < 0 || k <= 0 || mlp->n_pre < 1 || mlp->n_pre > 4) return -1;
   if (precision == P3TOK_F32) return patch_embed_f32_workspace(mlp, ngroups, k);
   if (precision == P3TOK_BF16) return patch_embed_bf16_workspace(mlp, ngroups, k);
+  if (precision == P3TOK_BF16X3) return patch_embed_x3_workspace(mlp, ngroups, k);
   return -1;
 }
 
@@ -76,6 +77,10 @@ extern "C" int p3tok_patch_embed(const p3tok_rows* rows, const p3tok_mlp* mlp, i
   if (precision == P3TOK_BF16) {
     P3_REQUIRE(mlp->wdtype == P3TOK_BF16, P3TOK_ERR_INVALID, "patch_embed(bf16): weights must be bf16");
     return patch_embed_bf16(rows, mlp, workspace, workspace_bytes, tokens, tokens_dtype == P3TOK_BF16, as_stream(stream));
+  }
+  if (precision == P3TOK_BF16X3) {
+    P3_REQUIRE(mlp->wdtype == P3TOK_BF16X3, P3TOK_ERR_INVALID, "patch_embed(bf16x3): weights must be the split [hi|hi|lo] form");
+    return patch_embed_x3(rows, mlp, workspace, workspace_bytes, (float*)tokens, as_stream(stream));
   }
   set_error("patch_embed: unknown precision %d", precision);
   return P3TOK_ERR_INVALID;

@@ -19,6 +19,10 @@ int64_t patch_embed_bf16_workspace(const p3tok_mlp* mlp, int64_t ngroups, int64_
 int patch_embed_bf16(const p3tok_rows* rows, const p3tok_mlp* mlp, void* ws, int64_t ws_bytes, void* tokens, int tokens_bf16,
                      cudaStream_t s);
 
+// bf16x3 (fp32-accurate tensor-core) mode, embed_tc.cu
+int64_t patch_embed_x3_workspace(const p3tok_mlp* mlp, int64_t ngroups, int64_t k);
+int patch_embed_x3(const p3tok_rows* rows, const p3tok_mlp* mlp, void* ws, int64_t ws_bytes, float* tokens, cudaStream_t s);
+
 // extra epilogue of tc_linear for the ViT blocks (vit.cu): GELU, fp32 residual stream, column-slice outputs
 struct TcExtra {
   int gelu = 0;                    // exact GELU after the bias ...
@@ -28,6 +32,8 @@ struct TcExtra {
   const float* residual = nullptr; // out_f32 = res_mul * residual + out_scale * value
   float res_mul = 1.f, out_scale = 1.f;
   int64_t ldc = 0;                 // row pitch of out_bf16 in elements (0 = N)
+  int x3 = 0;                      // bf16x3 split operands: A [M, 2Kp] = [hi | lo], W [N, 3Kp] = [W_hi | W_hi | W_lo], K = 3Kp
+  int out_split = 0;               // out_bf16 is [M, 2N] = [hi | lo] of the fp32 result
 };
 int tc_linear_ex(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat16* W, int N, const float* bias, int relu,
                  const TcExtra& ex, __nv_bfloat16* out_bf16, float* out_f32, cudaStream_t s);

@@ -103,6 +103,9 @@ struct TcParams {
   const float* residual;   // [M,N] f32 or null: out_f32 = res_mul * residual + out_scale * value (may alias out_f32:
   float res_mul, out_scale; // every element is read by the thread that produces it, before its store box leaves)
   int stages, stage_bytes; // TMA->MMA ring depth and bytes per stage (A tile 16 KB + this CTA's part of the weight tile)
+  int x3;                  // bf16x3 split mode (fp32-accurate on the tensor cores): A is [M, 2 Kp] = [hi | lo], W is [N, 3 Kp] =
+                           // [W_hi | W_hi | W_lo], K = 3 Kp: k-blocks of the third segment re-read the hi half of A
+  int out_split;           // out_bf16 is [M, 2 N] = [hi | lo] of the fp32 result (the next layer's split operand)
   int prefetch;            // L2-prefetch the next item's activation tile
   int ares;                // A-resident mode (pairs only): a pair walks ALL N tiles of its M group, the group's activation
                            // rows stay in shared memory and only weight boxes stream through the ring
@@ -208,7 +211,7 @@ __device__ __forceinline__ void epilogue_half(const TcParams& p, const float* sb
   // bf16-only outputs take their ReLU from the conversion instruction (F2FP.RELU) instead of 32 FMNMX
   const bool gelu_here = p.gelu && n0 < p.gelu_cols;        // warp-uniform (gelu_cols is a multiple of 32)
   const bool relu_here = p.relu && !gelu_here;
-  const bool relu_in_pack = relu_here && (LEAN || (!p.out_f32 && !p.out_max && !p.out_max_bf16));
+  const bool relu_in_pack = relu_here && (LEAN || (!p.out_f32 && !p.out_max && !p.out_max_bf16 && !p.out_split));
   epilogue_affine(v, p, sbias, gb, n0, relu_here && !relu_in_pack);
   if (gelu_here) {
 #pragma unroll
@@ -232,7 +235,25 @@ __device__ __forceinline__ void epilogue_half(const TcParams& p, const float* sb
       v[4 * j + 3] = fmaf(p.res_mul, r4[j].w, p.out_scale * v[4 * j + 3]);
     }
   }
-  if (p.out_bf16) {
+  if (!LEAN && p.out_bf16 && p.out_split) {
+    // bf16x3: the fp32 value leaves as hi = bf16(v) (box 0) and lo = bf16(v - hi) (box 1): hi + lo carries 16 mantissa bits
+    const uint32_t rbase = sbox + lane * 128;
+#pragma unroll
+    for (int pc = 0; pc < 4; ++pc) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = v[pc * 8 + 2 * e], b = v[pc * 8 + 2 * e + 1];
+        const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+        hi[e] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+        lo[e] = pack_bf16x2(a - __bfloat162float(ha), b - __bfloat162float(hb));
+      }
+      const uint32_t a = rbase + (((uint32_t)(pc + 4 * half) ^ (lane & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + (uint32_t)TC_STAGING), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3])
+                   : "memory");
+    }
+  } else if (p.out_bf16) {
     const uint32_t rbase = sbox + lane * 128;
     if (relu_in_pack) {
 #pragma unroll
@@ -378,10 +399,13 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tx = PAIR ? 2u * ((ARES ? 0u : (uint32_t)TC_A_STAGE) + (uint32_t)(p.BN / 2) * TC_BK * 2)
                              : TC_A_STAGE + (uint32_t)p.BN * TC_BK * 2;
     const int brows = p.BN / CL;     // rows of the weight tile this CTA fetches (and multicasts)
+    // A column of k-block kb: plain, or (bf16x3) [hi | lo | hi again] over the [hi | lo] operand
+    const int kb_seg = p.x3 ? num_kb / 3 : num_kb;
+    auto acol = [&](int kb) { return (p.x3 && kb >= 2 * kb_seg ? kb - 2 * kb_seg : kb) * TC_BK; };
     int mg, nt;
     for (int li = 0; decode(li, mg, nt); ++li) {
       const int mt = mg * CL + rank;   // may be a dummy tile past the end: TMA zero-fills, stores are clipped
-      if (p.prefetch && issuer && !ARES) {
+      if (p.prefetch && issuer && !ARES && !p.x3) {
         // pull the NEXT item's activation tile (streamed from HBM exactly once) into L2 ahead of its loads
         int nmg, nnt;
         if (decode(li + 1, nmg, nnt)) {
@@ -399,11 +423,11 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* b_dst = sB + stage * STAGE_BYTES;
           if (PAIR) {
             if (rank == 0) mbar_expect_tx(&full[stage], tx);
-            if (!ARES) tma_load_2d_pair(a_dst, &tmA, &full[stage], kb * TC_BK, mt * TC_BM);
+            if (!ARES) tma_load_2d_pair(a_dst, &tmA, &full[stage], acol(kb), mt * TC_BM);
             tma_load_2d_pair(b_dst, &tmB, &full[stage], kb * TC_BK, nt * p.BN + rank * brows);
           } else {
             mbar_expect_tx(&full[stage], tx);
-            tma_load_2d(a_dst, &tmA, &full[stage], kb * TC_BK, mt * TC_BM);
+            tma_load_2d(a_dst, &tmA, &full[stage], acol(kb), mt * TC_BM);
             if (CL == 1) tma_load_2d(b_dst, &tmB, &full[stage], kb * TC_BK, nt * p.BN);
             else tma_load_2d_mc(b_dst + rank * brows * 128, &tmB, &full[stage], kb * TC_BK, nt * p.BN + rank * brows, mc_mask);
           }
@@ -518,10 +542,11 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + gi * 64);
         const bool f32_tma = p.out_f32 && p.f32_tma;   // fp32 output: box 0 / box 1 of this warp = the two 32-column halves
-        const uint32_t sbox = f32_tma ? smem_u32(stg) : smem_u32(stg + sbuf * TC_STAGING);
+        const bool split = EW <= 8 && p.out_split;     // bf16x3: box 0 = hi, box 1 = lo of the same 64 columns (no double buffering)
+        const uint32_t sbox = (f32_tma || split) ? smem_u32(stg) : smem_u32(stg + sbuf * TC_STAGING);
         if (p.out_bf16 || f32_tma) {   // the TMA store issued two groups (fp32: two halves) ago has finished reading this box
           if (lane == 0) {
-            if (Cfg::BOXES == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (Cfg::BOXES == 2 && !split) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           }
           __syncwarp();
@@ -583,9 +608,14 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                              reinterpret_cast<uint64_t>(&tmC)),
                          "r"(sbox), "r"(n0), "r"(row0)
                          : "memory");
+            if (split)      // the lo half of the split output: columns [N, 2N) of the same row-major matrix
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                               reinterpret_cast<uint64_t>(&tmC)),
+                           "r"(sbox + (uint32_t)TC_STAGING), "r"(p.N + n0), "r"(row0)
+                           : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          if (Cfg::BOXES == 2) sbuf ^= 1;
+          if (Cfg::BOXES == 2 && !split) sbuf ^= 1;
         } else if (f32_tma) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
@@ -674,14 +704,18 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
   p.residual = ex ? ex->residual : nullptr;
   p.res_mul = ex ? ex->res_mul : 0.f;
   p.out_scale = ex ? ex->out_scale : 1.f;
-  const int64_t ldc = (ex && ex->ldc > 0) ? ex->ldc : N;   // row pitch of out_bf16 (column slices of a wider matrix)
-  P3_REQUIRE(ldc == N || (out_bf16 && !out_f32 && ldc % 8 == 0), P3TOK_ERR_UNSUPPORTED, "tc_linear: ldc only for bf16 outputs");
+  p.x3 = ex ? ex->x3 : 0;
+  p.out_split = ex ? ex->out_split : 0;
+  if (p.x3) P3_REQUIRE(K % (3 * TC_BK) == 0, P3TOK_ERR_UNSUPPORTED, "tc_linear(x3): K=%d must be 3 x a multiple of 64", K);
+  if (p.out_split) P3_REQUIRE(out_bf16 && N % 64 == 0 && !(ex && ex->epi16), P3TOK_ERR_UNSUPPORTED, "tc_linear(split): N=%d must be a multiple of 64", N);
+  const int64_t ldc = p.out_split ? 2 * (int64_t)N : ((ex && ex->ldc > 0) ? ex->ldc : N);   // row pitch of out_bf16
+  P3_REQUIRE(ldc == N || (out_bf16 && (!out_f32 || p.out_split) && ldc % 8 == 0), P3TOK_ERR_UNSUPPORTED, "tc_linear: ldc only for bf16 outputs");
   // 16 epilogue warps (lean epilogue: bf16 or TMA-stored / TMA-added fp32 outputs only), asked for by the ViT blocks
   static int epi16_on = -1;
   if (epi16_on < 0) { const char* e = getenv("P3TOK_TC_EPI16"); epi16_on = e ? atoi(e) : 1; }
   const bool want16 = epi16_on && ex && ex->epi16 && !out_max && !out_max_bf16 && !gbias && !(out_bf16 && out_f32);
   CUtensorMap ta, tb, tc;
-  int rc = make_map(&ta, A, M, K, TC_BM);
+  int rc = make_map(&ta, A, M, p.x3 ? K / 3 * 2 : K, TC_BM);    // x3: the operand holds [hi | lo], 2/3 of the reduction length
   if (rc) return rc;
   p.CL = pair ? 2 : want_cl;
   while (p.CL > 1 && p.num_m_tiles < p.CL) p.CL /= 2;
@@ -690,7 +724,7 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
   p.f32_tma = 0;
   p.res_add = 0;
   if (out_bf16) {
-    rc = make_map(&tc, out_bf16, M, N, 32, ldc);     // store boxes: 64 columns x 32 rows
+    rc = make_map(&tc, out_bf16, M, p.out_split ? 2 * N : N, 32, ldc);     // store boxes: 64 columns x 32 rows
     if (rc) return rc;
   } else if (out_f32 && (TcCfg<TC_EPI_WARPS>::BOXES == 2 || want16) && N % 4 == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0) {
     rc = make_map_f32(&tc, out_f32, M, N, 32);  // fp32 store boxes: 32 columns x 32 rows
@@ -726,7 +760,7 @@ static int tc_linear(const __nv_bfloat16* A, int64_t M, int K, const __nv_bfloat
     if (ares_on < 0) { const char* e = getenv("P3TOK_TC_ARES"); ares_on = e ? atoi(e) : 1; }
     const int num_kb = (K + TC_BK - 1) / TC_BK;
     p.ares = 0;
-    if (ares_on && pair && p.num_n_tiles >= 2 && num_kb <= TC_MAX_KB) {
+    if (ares_on && pair && !p.x3 && p.num_n_tiles >= 2 && num_kb <= TC_MAX_KB) {
       const int ring = TC_SMEM - smem_fixed - num_kb * TC_A_STAGE;
       if (ring / (wrows * TC_BK * 2) >= 3) p.ares = 1;
     }
@@ -1532,6 +1566,243 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
                      nullptr, nullptr, 0, s);
       if (rc) return rc;
       group_max_f32_kernel<<<grid_1d(gc * m->out_dim, 256), 256, 0, s>>>(scratch, gc, (int)k, m->out_dim, m->out_relu, tok, tokb);
+      P3_LAUNCH_CHECK("group_max_f32_kernel");
+    }
+  }
+  return P3TOK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ bf16x3 (fp32-accurate) mode
+// The rtol-1e-4 contract on the tensor cores: every fp32 operand is carried as hi = bf16(v), lo = bf16(v - hi) (16 mantissa
+// bits) and a product a.w is evaluated as a_hi.w_hi + a_lo.w_hi + a_hi.w_lo with fp32 accumulation in tensor memory - ONE
+// tcgen05 GEMM over a three-fold reduction length: activations are stored [rows, 2K] = [hi | lo], the host prepares
+// W' = [W_hi | W_hi | W_lo] (p3tok/fold.py), and the k-blocks of the third segment re-read the hi half (tc_linear x3).  The
+// epilogue splits its fp32 result into the next layer's [hi | lo].  Measured error against the float64 oracle ~7e-6 of max
+// (emulation: same figure), against 3e-7 for the CUDA-core fp32 path and 4e-3 for plain bf16.
+// Narrow first layers (cin <= 16: the coordinates) stay on CUDA cores in fp32, as in the bf16 mode.
+template <typename IdxT>
+__global__ void __launch_bounds__(128)
+rows_first_layer_split_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, const float* __restrict__ W, const float* __restrict__ bias,
+                              int cin, int nout, int relu, __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32) {
+  __shared__ __align__(16) float xin[32][16];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const IdxT* knn = reinterpret_cast<const IdxT*>(R.knn_idx);
+  for (int e = threadIdx.x; e < 32 * 16; e += 128) {
+    const int rr = e >> 4, c = e & 15;
+    const int64_t r = r0 + rr;
+    float v = 0.f;
+    if (r < nrows && c < cin) {
+      if (R.kind == 2) {
+        v = R.x[(g_begin * R.k + r) * cin + c];
+      } else {
+        const int n = (int)(r % R.k);
+        const int64_t bj = g_begin + r / R.k;
+        const int64_t b = bj / R.G;
+        const int64_t g = R.perm ? R.perm[bj] : (bj - b * R.G);
+        const int64_t ni = (int64_t)knn[(b * R.G + g) * R.k + n];
+        if (R.kind == 0) {
+          const float* crow = R.x + (b * R.N + R.ctr_idx[b * R.G + g]) * R.C;
+          v = c < R.C ? __fsub_rn(R.x[(b * R.N + ni) * R.C + c], crow[c]) : crow[c - R.C];
+        } else {
+          v = c < 3 ? R.x[(b * R.N + ni) * 3 + c] : R.feats[(b * R.N + ni) * R.D + (c - 3)];
+        }
+      }
+    }
+    xin[rr][c] = v;
+  }
+  __syncthreads();
+  for (int n0 = threadIdx.x; n0 < nout; n0 += 128) {
+    float w[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) w[c] = c < cin ? W[(size_t)n0 * cin + c] : 0.f;
+    const float b0 = bias ? bias[n0] : 0.f;
+    for (int rr = 0; rr < 32; ++rr) {
+      const int64_t r = r0 + rr;
+      if (r >= nrows) break;
+      float a = b0;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) a = fmaf(w[c], xin[rr][c], a);
+      if (relu) a = fmaxf(a, 0.f);
+      const __nv_bfloat16 hi = __float2bfloat16_rn(a);
+      out[r * 2 * nout + n0] = hi;
+      out[r * 2 * nout + nout + n0] = __float2bfloat16_rn(a - __bfloat162float(hi));
+      if (out_f32) out_f32[r * nout + n0] = a;
+    }
+  }
+}
+
+// wide inputs (P3Embed stage >= 1): gathered rows as split operands [rows, 2 kpad] = [hi | lo], zero padded
+template <typename IdxT>
+__global__ void rows_gather_split_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, int cin, int kpad, __nv_bfloat16* __restrict__ out) {
+  const IdxT* knn = reinterpret_cast<const IdxT*>(R.knn_idx);
+  const int64_t total = nrows * kpad;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % kpad);
+    const int64_t r = e / kpad;
+    float v = 0.f;
+    if (c < cin) {
+      if (R.kind == 2) {
+        v = R.x[(g_begin * R.k + r) * cin + c];
+      } else {
+        const int n = (int)(r % R.k);
+        const int64_t bj = g_begin + r / R.k;
+        const int64_t b = bj / R.G;
+        const int64_t g = R.perm ? R.perm[bj] : (bj - b * R.G);
+        const int64_t ni = (int64_t)knn[(b * R.G + g) * R.k + n];
+        if (R.kind == 0) {
+          const float* crow = R.x + (b * R.N + R.ctr_idx[b * R.G + g]) * R.C;
+          v = c < R.C ? __fsub_rn(R.x[(b * R.N + ni) * R.C + c], crow[c]) : crow[c - R.C];
+        } else {
+          v = c < 3 ? R.x[(b * R.N + ni) * 3 + c] : R.feats[(b * R.N + ni) * R.D + (c - 3)];
+        }
+      }
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    out[r * 2 * kpad + c] = hi;
+    out[r * 2 * kpad + kpad + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
+// fp32 [R, C] -> split bf16 [R, 2 cpad] = [hi | lo], zero padded to cpad columns
+__global__ void split_rows_kernel(const float* __restrict__ in, int64_t R_, int C, int cpad, __nv_bfloat16* __restrict__ out) {
+  const int64_t total = R_ * cpad;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % cpad);
+    const int64_t r = e / cpad;
+    const float v = c < C ? in[r * C + c] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    out[r * 2 * cpad + c] = hi;
+    out[r * 2 * cpad + cpad + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
+struct X3Layout {
+  int64_t cg, rows, wmax, F, wide;
+  int64_t off_act0, off_act1, off_max32, off_gmax, off_gsplit, off_gbias, off_scratch, total;
+};
+static inline int64_t pad64(int64_t v) { return (v + 63) / 64 * 64; }
+
+static X3Layout x3_layout(const p3tok_mlp* m, int64_t ngroups, int64_t k) {
+  X3Layout L;
+  L.F = m->pre_dim[m->n_pre - 1];
+  int64_t w = m->cin > 16 ? pad64(m->cin) : 0;
+  for (int i = 0; i < m->n_pre; ++i) w = w > m->pre_dim[i] ? w : m->pre_dim[i];
+  w = w > m->mid_dim ? w : m->mid_dim;
+  L.wmax = w;
+  L.cg = chunk_groups(ngroups, k, 2 * w);
+  L.rows = L.cg * k;
+  L.wide = L.F > m->out_dim ? L.F : m->out_dim;
+  int64_t o = 0;
+  L.off_act0 = o; o += align_up(L.rows * 2 * w * 2, 1024);
+  L.off_act1 = o; o += align_up(L.rows * 2 * w * 2, 1024);
+  L.off_max32 = o; o += align_up((L.rows / 32 + 1) * L.wide * 4, 1024);
+  L.off_gmax = o; o += align_up((L.cg + 1) * L.F * 4, 1024);
+  L.off_gsplit = o; o += align_up((L.cg + 1) * 2 * pad64(L.F) * 2, 1024);
+  L.off_gbias = o; o += align_up(L.cg * m->mid_dim * 4, 1024);
+  // fp32 scratch [rows, wide]: the unfused max (k not a multiple of 32) and the max of a CUDA-core-only pre stage
+  L.off_scratch = o; o += align_up(L.rows * L.wide * 4, 1024);
+  L.total = o + 1024;
+  return L;
+}
+
+int64_t patch_embed_x3_workspace(const p3tok_mlp* m, int64_t ngroups, int64_t k) { return x3_layout(m, ngroups, k).total; }
+
+// Weights (prepared by p3tok/fold.py, wdtype P3TOK_BF16X3): a first layer with cin <= 16 stays fp32 [N, cin]; every other
+// matrix is bf16 [N, 3 pad64(K)] = [W_hi | W_hi | W_lo].
+int patch_embed_x3(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t ws_bytes, float* tokens, cudaStream_t s) {
+  const int64_t ngroups = R->B * R->G, k = R->k;
+  const X3Layout L = x3_layout(m, ngroups, k);
+  P3_REQUIRE(ws_bytes >= L.total, P3TOK_ERR_WORKSPACE, "patch_embed(bf16x3): workspace %lld < %lld bytes", (long long)ws_bytes,
+             (long long)L.total);
+  for (int i = 0; i < m->n_pre; ++i)
+    P3_REQUIRE(m->pre_dim[i] % 64 == 0, P3TOK_ERR_UNSUPPORTED, "patch_embed(bf16x3): layer widths must be multiples of 64");
+  P3_REQUIRE(m->mid_dim % 64 == 0 && m->out_dim % 64 == 0, P3TOK_ERR_UNSUPPORTED, "patch_embed(bf16x3): layer widths must be multiples of 64");
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) / 1024 * 1024);
+  __nv_bfloat16* act[2] = {reinterpret_cast<__nv_bfloat16*>(base + L.off_act0), reinterpret_cast<__nv_bfloat16*>(base + L.off_act1)};
+  float* max32 = reinterpret_cast<float*>(base + L.off_max32);
+  float* gmax = reinterpret_cast<float*>(base + L.off_gmax);
+  __nv_bfloat16* gsplit = reinterpret_cast<__nv_bfloat16*>(base + L.off_gsplit);
+  float* gbias = reinterpret_cast<float*>(base + L.off_gbias);
+  float* scratch = reinterpret_cast<float*>(base + L.off_scratch);
+  const bool fused_max = (k % 32 == 0);
+  const int parts = fused_max ? (int)(k / 32) : 0;
+  const bool i64 = (R->kind == 2) || R->idx_dtype == P3TOK_I64;
+  TcExtra ex;
+  ex.x3 = 1;
+  TcExtra exs = ex;
+  exs.out_split = 1;
+  const int F = (int)L.F;
+  for (int64_t g0 = 0; g0 < ngroups; g0 += L.cg) {
+    const int64_t gc = (ngroups - g0) < L.cg ? (ngroups - g0) : L.cg;
+    const int64_t rows = gc * k;
+    int cur = 0, rc, first_tc, kin;
+    bool have_gmax = false;
+    if (m->cin <= 16) {
+      const bool only = (m->n_pre == 1);                 // the block's only per-point layer: also keep fp32 values for its max
+      const unsigned blocks = (unsigned)((rows + 31) / 32);
+      if (i64) rows_first_layer_split_kernel<int64_t><<<blocks, 128, 0, s>>>(*R, g0, rows, (const float*)m->w_pre[0], m->b_pre[0], m->cin,
+                                                                           m->pre_dim[0], m->pre_relu[0], act[cur], only ? scratch : nullptr);
+      else rows_first_layer_split_kernel<int32_t><<<blocks, 128, 0, s>>>(*R, g0, rows, (const float*)m->w_pre[0], m->b_pre[0], m->cin,
+                                                                         m->pre_dim[0], m->pre_relu[0], act[cur], only ? scratch : nullptr);
+      P3_LAUNCH_CHECK("rows_first_layer_split_kernel");
+      if (only) {
+        group_max_f32_kernel<<<grid_1d(gc * L.F, 256), 256, 0, s>>>(scratch, gc, (int)k, F, 0, gmax, nullptr);
+        P3_LAUNCH_CHECK("group_max_f32_kernel");
+        have_gmax = true;
+      }
+      first_tc = 1;
+      kin = m->pre_dim[0];
+    } else {
+      const int kp = (int)pad64(m->cin);
+      if (i64) rows_gather_split_kernel<int64_t><<<grid_1d(rows * kp, 256), 256, 0, s>>>(*R, g0, rows, m->cin, kp, act[cur]);
+      else rows_gather_split_kernel<int32_t><<<grid_1d(rows * kp, 256), 256, 0, s>>>(*R, g0, rows, m->cin, kp, act[cur]);
+      P3_LAUNCH_CHECK("rows_gather_split_kernel");
+      first_tc = 0;
+      kin = kp;
+    }
+    for (int i = first_tc; i < m->n_pre; ++i) {
+      const bool last = (i == m->n_pre - 1);
+      rc = tc_linear(act[cur], rows, 3 * kin, (const __nv_bfloat16*)m->w_pre[i], m->pre_dim[i], m->b_pre[i], nullptr, 1, m->pre_relu[i],
+                     act[cur ^ 1], (last && !fused_max) ? scratch : nullptr, (last && fused_max) ? max32 : nullptr, nullptr, 0, s, &exs);
+      if (rc) return rc;
+      cur ^= 1;
+      kin = m->pre_dim[i];
+      if (last) {
+        if (fused_max) {
+          partial_max_kernel<<<grid_1d(gc * L.F, 256), 256, 0, s>>>(max32, gc, parts, F, gmax, nullptr);
+          P3_LAUNCH_CHECK("partial_max_kernel");
+        } else {
+          group_max_f32_kernel<<<grid_1d(gc * L.F, 256), 256, 0, s>>>(scratch, gc, (int)k, F, 0, gmax, nullptr);
+          P3_LAUNCH_CHECK("group_max_f32_kernel");
+        }
+        have_gmax = true;
+      }
+    }
+    P3_REQUIRE(have_gmax, P3TOK_ERR_INVALID, "patch_embed(bf16x3): no per-point layer");
+    // ---- concat layer: pooled half once per group (fp32 group bias), then the per-point half
+    split_rows_kernel<<<grid_1d(gc * L.F, 256), 256, 0, s>>>(gmax, gc, F, F, gsplit);
+    P3_LAUNCH_CHECK("split_rows_kernel");
+    rc = tc_linear(gsplit, gc, 3 * F, (const __nv_bfloat16*)m->w_mid_g, m->mid_dim, m->b_mid, nullptr, 1, 0, nullptr, gbias, nullptr, nullptr,
+                   0, s, &ex);
+    if (rc) return rc;
+    rc = tc_linear(act[cur], rows, 3 * F, (const __nv_bfloat16*)m->w_mid_f, m->mid_dim, nullptr, gbias, (int)k, 1, act[cur ^ 1], nullptr, nullptr,
+                   nullptr, 0, s, &exs);
+    if (rc) return rc;
+    cur ^= 1;
+    float* tok = tokens + g0 * m->out_dim;
+    if (fused_max) {
+      rc = tc_linear(act[cur], rows, 3 * m->mid_dim, (const __nv_bfloat16*)m->w_out, m->out_dim, m->b_out, nullptr, 1, 0, nullptr, nullptr,
+                     parts == 1 ? tok : max32, nullptr, parts == 1 ? m->out_relu : 0, s, &ex);
+      if (rc) return rc;
+      if (parts > 1) {
+        group_max_f32_kernel<<<grid_1d(gc * m->out_dim, 256), 256, 0, s>>>(max32, gc, parts, m->out_dim, m->out_relu, tok, nullptr);
+        P3_LAUNCH_CHECK("group_max_f32_kernel");
+      }
+    } else {
+      rc = tc_linear(act[cur], rows, 3 * m->mid_dim, (const __nv_bfloat16*)m->w_out, m->out_dim, m->b_out, nullptr, 1, 0, nullptr, scratch,
+                     nullptr, nullptr, 0, s, &ex);
+      if (rc) return rc;
+      group_max_f32_kernel<<<grid_1d(gc * m->out_dim, 256), 256, 0, s>>>(scratch, gc, (int)k, m->out_dim, m->out_relu, tok, nullptr);
       P3_LAUNCH_CHECK("group_max_f32_kernel");
     }
   }

@@ -17,7 +17,7 @@ HEADER_PATH = os.path.join(os.path.dirname(os.path.dirname(_PKG)), "include", "p
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, 1, 2, 3, 4
 KNN_APF_SQ, KNN_P4P_CDIST = 0, 1
-F32, BF16, I32, I64 = 0, 1, 2, 3
+F32, BF16, I32, I64, BF16X3 = 0, 1, 2, 3, 4
 ROWS_APF, ROWS_P4P, ROWS_DIRECT = 0, 1, 2
 
 _i32, _i64, _vp, _int = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int

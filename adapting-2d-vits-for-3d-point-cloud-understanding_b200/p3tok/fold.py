@@ -50,6 +50,30 @@ class PatchMLP:
         return [self.cin, len(self.pre_dims)] + list(self.pre_dims) + list(self.pre_relu) + [
             self.mid_dim, self.out_dim, self.out_relu]
 
+    def to_x3(self, device) -> "PatchMLP":
+        """The bf16x3 (fp32-accurate tensor-core) form: a first layer with cin <= 16 stays float32 [out, cin] (CUDA cores, fp32
+        coordinates); every other matrix W [out, in] becomes bfloat16 [out, 3 * pad64(in)] = [W_hi | W_hi | W_lo] with
+        W_hi = bf16(W), W_lo = bf16(W - W_hi), matching activations stored as [hi | lo]: one GEMM over the tripled reduction
+        length evaluates a_hi.w_hi + a_lo.w_hi + a_hi.w_lo (csrc/embed_tc.cu).  Biases float32."""
+        key = (str(device), "x3")
+        if key not in self._cast:
+            def x3(w):
+                w = w.detach().float().cpu()
+                kp = (w.shape[1] + 63) // 64 * 64
+                wp = torch.zeros(w.shape[0], kp)
+                wp[:, :w.shape[1]] = w
+                hi = wp.bfloat16()
+                lo = (wp - hi.float()).bfloat16()
+                return torch.cat([hi, hi, lo], 1).contiguous().to(device)
+
+            def b(t):
+                return t.to(device=device, dtype=torch.float32).contiguous()
+            w_pre = [(b(w) if (i == 0 and self.cin <= 16) else x3(w)) for i, w in enumerate(self.w_pre)]
+            self._cast[key] = PatchMLP(
+                self.cin, list(self.pre_dims), list(self.pre_relu), self.mid_dim, self.out_dim, self.out_relu,
+                w_pre, [b(x) for x in self.b_pre], x3(self.w_mid_g), x3(self.w_mid_f), b(self.b_mid), x3(self.w_out), b(self.b_out))
+        return self._cast[key]
+
     def to(self, device, wdtype: torch.dtype = torch.float32) -> "PatchMLP":
         """Matrices in `wdtype` (float32 or bfloat16), biases always float32, contiguous on device."""
         key = (str(device), wdtype)

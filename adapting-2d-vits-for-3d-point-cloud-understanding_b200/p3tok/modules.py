@@ -25,8 +25,10 @@ from .functional import _start
 
 
 def _check_precision(p: str) -> bool:
-    if p not in ("fp32", "bf16"):
-        raise ValueError(f"precision must be 'fp32' or 'bf16', got {p!r}")
+    """True for the plain bf16 tensor-core path.  "fp32" = CUDA-core FFMA, "fp32tc" = the same rtol-1e-4 contract on the
+    tensor cores (bf16x3 split operands, csrc/embed_tc.cu patch_embed_x3)."""
+    if p not in ("fp32", "bf16", "fp32tc"):
+        raise ValueError(f"precision must be 'fp32', 'fp32tc' or 'bf16', got {p!r}")
     return p == "bf16"
 
 
@@ -57,6 +59,8 @@ class _FoldedMixin:
             cache.clear()
             cache["ver"] = ver
             cache["host"] = build()
+        if getattr(self, "precision", None) == "fp32tc":
+            return cache["host"].to_x3(device)
         return cache["host"].to(device, torch.bfloat16 if bf16 else torch.float32)
 
     def _require_eval(self):
@@ -138,7 +142,8 @@ class Encoder(nn.Module, _FoldedMixin):
         m = self.folded(point_groups.device)
         rows = point_groups.float().reshape(B * G * k, cin)
         tok = ops.patch_embed(_lib.ROWS_DIRECT, rows, None, None, None, None, B * G, k, m.tensors(), m.meta(),
-                              _check_precision(self.precision), _check_token_dtype(self.token_dtype, self.precision))
+                              _check_precision(self.precision), _check_token_dtype(self.token_dtype, self.precision),
+                              self.precision == "fp32tc")
         return tok.view(B, G, self.encoder_channel)
 
     get_features = forward
@@ -169,7 +174,7 @@ class PointNet(nn.Module):
             raise RuntimeError(f"PointNet: in_channel={m.cin} but input has C={C} (expects in_channel == 2*C)")
         tok = ops.patch_embed(_lib.ROWS_APF, x, None, fps_idx, knn_idx, perm, B * G, k, m.tensors(), m.meta(),
                               _check_precision(self.encoder.precision),
-                              _check_token_dtype(self.encoder.token_dtype, self.encoder.precision))
+                              _check_token_dtype(self.encoder.token_dtype, self.encoder.precision), self.encoder.precision == "fp32tc")
         return tok.view(B, G, -1)
 
 
@@ -214,6 +219,8 @@ class P3Embed(nn.Module, _FoldedMixin):
             sd = self.state_dict()
             eps = _bn_eps(self)
             cache["host"] = [fold.fold_p3embed_stage(sd, s, eps) for s in range(len(self.convs))]
+        if self.precision == "fp32tc":
+            return [m.to_x3(device) for m in cache["host"]]
         return [m.to(device, torch.bfloat16 if bf16 else torch.float32) for m in cache["host"]]
 
     def forward(self, p: torch.Tensor, f: torch.Tensor, start_idx: Optional[List[torch.Tensor]] = None
@@ -235,7 +242,7 @@ class P3Embed(nn.Module, _FoldedMixin):
             ctr = ops.gather_points(pts, cidx)
             kidx = ops.knn_query(pts, ws, ctr, self.k, _lib.KNN_P4P_CDIST, True)
             tok = ops.patch_embed(_lib.ROWS_P4P, pts, feat, None, kidx, None, B * G, self.k, m.tensors(), m.meta(), bf16,
-                                  bf16_last and s == len(folded) - 1)
+                                  bf16_last and s == len(folded) - 1, self.precision == "fp32tc")
             feat = tok.view(B, G, -1)
             pts = ctr
             out_p.append(ctr)

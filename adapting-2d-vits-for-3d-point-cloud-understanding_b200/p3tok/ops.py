@@ -430,20 +430,25 @@ def _mlp_struct(weights: Sequence[torch.Tensor], meta: Sequence[int], wdtype: in
     relu = [int(v) for v in meta[2 + n_pre:2 + 2 * n_pre]]
     m.mid_dim, m.out_dim, m.out_relu = (int(v) for v in meta[2 + 2 * n_pre:5 + 2 * n_pre])
     m.wdtype = wdtype
+    x3 = wdtype == _lib.BF16X3
     want = torch.float32 if wdtype == _lib.F32 else torch.bfloat16
+    kw = (lambda k_: 3 * ((k_ + 63) // 64 * 64)) if x3 else (lambda k_: k_)     # bf16x3: [W_hi | W_hi | W_lo] over the padded width
     kin = cin
     for i in range(n_pre):
         w, b = weights[2 * i], weights[2 * i + 1]
-        if w.dtype != want or tuple(w.shape) != (dims[i], kin) or not w.is_contiguous():
-            raise RuntimeError(f"p3tok::patch_embed: layer {i} weight must be contiguous {want} ({dims[i]},{kin})")
+        if x3 and i == 0 and cin <= 16:          # the narrow first layer stays float32 (CUDA cores)
+            if w.dtype != torch.float32 or tuple(w.shape) != (dims[i], kin) or not w.is_contiguous():
+                raise RuntimeError(f"p3tok::patch_embed: bf16x3 layer 0 weight must be contiguous float32 ({dims[i]},{kin})")
+        elif w.dtype != want or tuple(w.shape) != (dims[i], kw(kin)) or not w.is_contiguous():
+            raise RuntimeError(f"p3tok::patch_embed: layer {i} weight must be contiguous {want} ({dims[i]},{kw(kin)})")
         if b.dtype != torch.float32 or tuple(b.shape) != (dims[i],):
             raise RuntimeError(f"p3tok::patch_embed: layer {i} bias must be float32 ({dims[i]},)")
         m.pre_dim[i], m.pre_relu[i] = dims[i], relu[i]
         m.w_pre[i], m.b_pre[i] = w.data_ptr(), b.data_ptr()
         kin = dims[i]
     wg, wf, bm, wo, bo = weights[2 * n_pre:2 * n_pre + 5]
-    for t, shp, dt, nm in ((wg, (m.mid_dim, kin), want, "w_mid_g"), (wf, (m.mid_dim, kin), want, "w_mid_f"),
-                           (bm, (m.mid_dim,), torch.float32, "b_mid"), (wo, (m.out_dim, m.mid_dim), want, "w_out"),
+    for t, shp, dt, nm in ((wg, (m.mid_dim, kw(kin)), want, "w_mid_g"), (wf, (m.mid_dim, kw(kin)), want, "w_mid_f"),
+                           (bm, (m.mid_dim,), torch.float32, "b_mid"), (wo, (m.out_dim, kw(m.mid_dim)), want, "w_out"),
                            (bo, (m.out_dim,), torch.float32, "b_out")):
         if t.dtype != dt or tuple(t.shape) != shp or not t.is_contiguous():
             raise RuntimeError(f"p3tok::patch_embed: {nm} must be contiguous {dt} {shp}, got {t.dtype} {tuple(t.shape)}")
@@ -454,14 +459,15 @@ def _mlp_struct(weights: Sequence[torch.Tensor], meta: Sequence[int], wdtype: in
 @torch.library.custom_op("p3tok::patch_embed", mutates_args=(), device_types="cuda")
 def patch_embed(kind: int, x: torch.Tensor, feats: Optional[torch.Tensor], ctr_idx: Optional[torch.Tensor],
                 knn_idx: Optional[torch.Tensor], perm: Optional[torch.Tensor], ngroups: int, k: int,
-                weights: Sequence[torch.Tensor], meta: Sequence[int], bf16: bool, bf16_tokens: bool = False) -> torch.Tensor:
+                weights: Sequence[torch.Tensor], meta: Sequence[int], bf16: bool, bf16_tokens: bool = False,
+                x3: bool = False) -> torch.Tensor:
     """kind 0: APF rows from x (B,N,C) + ctr_idx (B,G) + knn_idx (B,G,k) [+ perm];
     kind 1: P4P rows from x=pnts (B,N,3) + feats (B,N,D) + knn_idx (B,G,k);
     kind 2: x is the row matrix (ngroups*k, cin).  Returns tokens (ngroups, out_dim) float32, or bfloat16 with
     bf16_tokens (bf16 path only: the patch max is rounded once by the epilogue that produces it)."""
     _need_cuda("patch_embed", x, feats, ctr_idx, knn_idx, perm, *weights)
     x = _f32c("patch_embed", x)
-    prec = _lib.BF16 if bf16 else _lib.F32
+    prec = _lib.BF16X3 if x3 else (_lib.BF16 if bf16 else _lib.F32)     # x3: fp32-accurate tensor-core mode (weights from PatchMLP.to_x3)
     m = _mlp_struct(weights, meta, prec)
     r = _lib.RowsStruct()
     r.kind = kind
@@ -511,7 +517,7 @@ def patch_embed(kind: int, x: torch.Tensor, feats: Optional[torch.Tensor], ctr_i
 
 
 @patch_embed.register_fake
-def _(kind, x, feats, ctr_idx, knn_idx, perm, ngroups, k, weights, meta, bf16, bf16_tokens=False):
+def _(kind, x, feats, ctr_idx, knn_idx, perm, ngroups, k, weights, meta, bf16, bf16_tokens=False, x3=False):
     n_pre = meta[1]
     return x.new_empty((ngroups, meta[3 + 2 * n_pre]), dtype=torch.bfloat16 if bf16_tokens else torch.float32)
 

@@ -577,7 +577,8 @@ def run_p3tok(args, w, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "strong" if w.get("strong") else "weak", "vs_baseline": None,
-        "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+        "dtype": {"bf16": "bf16", "fp32": "f32", "fp32tc": "bf16x3 (fp32-accurate split operands on the tensor cores)"}[precision],
+        "data": "synthetic",
         "config": {"workload": f"{args.workload}: {w['desc']}", "clouds": kinds[0], "clouds_per_gpu_per_step": B,
                    "global_clouds_per_step": B * world, "points": w["N"], "k": w["k"],
                    "parallelism": f"batch-shard x{world}, no collective on the path",
@@ -672,7 +673,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="p3tok", choices=["p3tok", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("P3TOK_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("P3TOK_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16", "fp32tc"])
     ap.add_argument("--token-dtype", default="bf16", choices=["bf16", "f32"],
                     help="dtype of the tokens the serving step returns (bf16 path: rounded once in the producing epilogue; f32 = the reference's dtype)")
     ap.add_argument("--clouds", default="both", choices=["uniform", "clustered", "both"],

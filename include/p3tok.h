@@ -47,7 +47,8 @@ enum p3tok_knn_mode {
   P3TOK_KNN_P4P_CDIST = 1 /* src/models/pix4point.py:87  cdist mm path: K=5 FMA chain, clamp, sqrt */
 };
 
-enum p3tok_dtype { P3TOK_F32 = 0, P3TOK_BF16 = 1, P3TOK_I32 = 2, P3TOK_I64 = 3 };
+enum p3tok_dtype { P3TOK_F32 = 0, P3TOK_BF16 = 1, P3TOK_I32 = 2, P3TOK_I64 = 3,
+                   P3TOK_BF16X3 = 4 /* precision mode / weight form of the fp32-accurate tensor-core path, see p3tok_patch_embed */ };
 
 P3TOK_API int p3tok_abi_version(void);
 P3TOK_API const char* p3tok_last_error(void);
@@ -181,8 +182,11 @@ P3TOK_API int64_t p3tok_patch_embed_workspace_bytes(const p3tok_mlp* mlp, int64_
 
 /* Replaces Encoder.forward (src/models/apf.py:145-181) and the conv/pool half of one
  * P3Embed.forward iteration (src/models/pix4point.py:179-188).
- * precision: P3TOK_F32 (CUDA-core FFMA, fp32 accumulate; rtol 1e-4 contract) or P3TOK_BF16
- * (tcgen05 tensor cores, bf16 operands, fp32 accumulate in TMEM; rtol 1e-2 contract).
+ * precision: P3TOK_F32 (CUDA-core FFMA, fp32 accumulate; rtol 1e-4 contract), P3TOK_BF16 (tcgen05 tensor cores, bf16
+ * operands, fp32 accumulate in TMEM; rtol 1e-2 contract) or P3TOK_BF16X3 - the rtol 1e-4 contract ON the tensor cores:
+ * every operand is carried as hi + lo bf16 halves and a.w = a_hi.w_hi + a_lo.w_hi + a_hi.w_lo accumulates in fp32; the
+ * descriptor then holds (wdtype P3TOK_BF16X3) a first layer with cin <= 16 as f32 [out, cin] and every other matrix as
+ * bf16 [out, 3 * pad64(in)] = [W_hi | W_hi | W_lo] (p3tok/fold.py prepares them); all widths multiples of 64.
  * tokens: (B*G, out_dim) of tokens_dtype, group order as described in p3tok_rows.  tokens_dtype: P3TOK_F32 (the
  * reference's dtype) or, with precision P3TOK_BF16 only, P3TOK_BF16 - the patch max is rounded once, in the epilogue
  * that produces it, so a bf16 consumer (the ViT blocks) or a host reader moves half the bytes. */

@@ -14,7 +14,13 @@ from p3tok.modules import Encoder, P3Embed, PointNet
 
 pytestmark = pytest.mark.gpu
 
-PRECISIONS = [("fp32", 1e-4), ("bf16", 1e-2)]
+PRECISIONS = [("fp32", 1e-4), ("bf16", 1e-2), ("fp32tc", 1e-4)]     # fp32tc: bf16x3 split operands on the tensor cores
+
+
+def _skip_unless_x3_widths(prec, *widths):
+    """The fp32tc mode needs every layer width to be a multiple of 64 (all BASELINE widths are); other widths raise."""
+    if prec == "fp32tc" and any(w % 64 for w in widths):
+        pytest.skip("fp32tc: widths not multiples of 64")
 
 
 def _bf16_ready():
@@ -53,6 +59,7 @@ def test_linear_and_group_max_blocks():
 def test_pointnet_golden(golden_dir, name, prec, rtol):
     _skip_if_unbuilt(prec)
     c, g = cases.APF_CASES[name], _golden(golden_dir, name)
+    _skip_unless_x3_widths(prec, c["E"])
     x = synth.make_cloud(c["kind"], c["B"], c["N"], c["seed"], c["C"])
     st = synth.start_indices(c["B"], c["N"], c["seed"])
     sd = synth.apf_encoder_state(c["E"], 2 * c["C"], c["seed"])
@@ -74,6 +81,7 @@ def test_p3embed_golden(golden_dir, name, prec, rtol):
     _skip_if_unbuilt(prec)
     c, g = cases.P4P_CASES[name], _golden(golden_dir, name)
     stages, dims = synth.p3embed_dims(3, c["sample_ratio"], 4, 4, c["embed_dim"])
+    _skip_unless_x3_widths(prec, *[d[1] for d in dims])
     sd = synth.p3embed_state(3, c["sample_ratio"], 4, 4, c["embed_dim"], c["seed"])
     mod = P3Embed(sample_ratio=c["sample_ratio"], k=c["k"], embed_dim=c["embed_dim"], precision=prec).eval().to(dev())
     mod.load_state_dict(synth.to_torch_state(sd), strict=True)
@@ -371,3 +379,29 @@ def test_bf16_token_output_is_the_rounded_fp32_output():
     assert torch.equal(outs[1][1], outs[0][1]) and torch.equal(outs[1][2], outs[0][2].bfloat16())
     with pytest.raises(ValueError):
         PointNet(64, 8, 8, 6, precision="fp32", token_dtype=torch.bfloat16).eval().to(dev())(x, st)
+
+
+def test_fp32tc_rejects_widths_it_cannot_tile():
+    """The bf16x3 mode has no fallback: widths that are not multiples of 64 raise instead of silently taking another path."""
+    _skip_if_unbuilt("bf16")
+    enc = Encoder(48, 6, precision="fp32tc").eval().to(dev())
+    with pytest.raises(RuntimeError, match="multiples of 64"):
+        enc(torch.zeros(1, 4, 32, 6, device=dev()))
+
+
+def test_fp32tc_is_close_to_the_cuda_core_fp32_path_at_c2():
+    """BASELINE configs[1] shapes: the tensor-core fp32-accurate mode against the CUDA-core fp32 mode on the same inputs
+    (both are held to rtol 1e-4 against the oracle; against each other the difference is the split's ~7e-6)."""
+    _skip_if_unbuilt("bf16")
+    B, N, G, k, E = 16, 2048, 128, 32, 384
+    x = to_dev(synth.make_cloud("uniform", B, N, 12, 3))
+    st = to_dev(synth.start_indices(B, N, 12))
+    sd = synth.to_torch_state(synth.apf_encoder_state(E, 6, 12))
+    toks = []
+    for prec in ("fp32", "fp32tc"):
+        net = PointNet(E, G, k, 6, precision=prec).eval().to(dev())
+        net.encoder.load_state_dict(sd)
+        toks.append(net(x, st))
+    err = float((toks[0] - toks[1]).abs().max() / toks[0].abs().max())
+    print(f"[parity] fp32tc vs fp32 at c2 shapes: {err:.2e} of max")
+    assert err < 5e-5, err
