@@ -44,7 +44,11 @@ constexpr int LN_MAX_V4 = 8;
 template <int NV4>
 __global__ void __launch_bounds__(256)
 ln_rows_kernel(float* __restrict__ x, int64_t M, int D, float eps, const float* __restrict__ w,
-               const float* __restrict__ bvec, __nv_bfloat16* __restrict__ out, float rescale) {
+               const float* __restrict__ bvec, __nv_bfloat16* __restrict__ out, float rescale, const float* __restrict__ add,
+               float* __restrict__ out_f32) {
+  // add != null: the rows are first replaced by x + add (Pix4Point re-adds the positional embedding in front of every block,
+  // src/models/pix4point.py:254-255) - the sum is what the block normalises AND what its residual carries, so it is written back.
+  // out_f32 != null: the (affine) normalised rows also leave in fp32 (the final norm of PointViT.forward, line 256).
   const int lane = threadIdx.x & 31;
   const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2;
   if (row0 >= M) return;
@@ -59,13 +63,17 @@ ln_rows_kernel(float* __restrict__ x, int64_t M, int D, float eps, const float* 
     for (int i = 0; i < NV4; ++i) {
       const int j = lane + 32 * i;
       v[r][i] = j < nv ? xr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (add && j < nv) {
+        const float4 a4 = reinterpret_cast<const float4*>(add + (row0 + (two ? r : 0)) * D)[j];
+        v[r][i].x += a4.x; v[r][i].y += a4.y; v[r][i].z += a4.z; v[r][i].w += a4.w;
+      }
     }
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
 #pragma unroll
     for (int i = 0; i < NV4; ++i) s[r] += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
-    if (rescale != 1.f && (r == 0 || two)) {   // the residual stream leaves this kernel multiplied (the layer's "2 x")
+    if ((rescale != 1.f || add) && (r == 0 || two)) {   // the residual stream leaves this kernel multiplied (the layer's "2 x") / shifted
       float4* xr = reinterpret_cast<float4*>(x + (row0 + r) * D);
 #pragma unroll
       for (int i = 0; i < NV4; ++i) {
@@ -112,9 +120,12 @@ ln_rows_kernel(float* __restrict__ x, int64_t M, int D, float eps, const float* 
           const float4 ww = reinterpret_cast<const float4*>(w)[j], bb = reinterpret_cast<const float4*>(bvec)[j];
           a = fmaf(a, ww.x, bb.x); b = fmaf(b, ww.y, bb.y); c = fmaf(c, ww.z, bb.z); d = fmaf(d, ww.w, bb.w);
         }
-        __nv_bfloat162 lo = __floats2bfloat162_rn(a, b);
-        __nv_bfloat162 hi = __floats2bfloat162_rn(c, d);
-        reinterpret_cast<uint2*>(orow)[j] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        if (out_f32) reinterpret_cast<float4*>(out_f32 + (row0 + r) * D)[j] = make_float4(a, b, c, d);
+        if (out) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(a, b);
+          __nv_bfloat162 hi = __floats2bfloat162_rn(c, d);
+          reinterpret_cast<uint2*>(orow)[j] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        }
       }
     }
   }
@@ -123,15 +134,15 @@ ln_rows_kernel(float* __restrict__ x, int64_t M, int D, float eps, const float* 
 // w == nullptr: plain normalisation (the affine lives in the consuming GEMM's weights)
 // rescale != 1: x is also multiplied in place (x <- rescale * x) after it has been read
 static int layernorm_bf16(float* x, int64_t M, int D, float eps, const float* w, const float* b, __nv_bfloat16* out,
-                          float rescale, cudaStream_t s) {
+                          float rescale, cudaStream_t s, const float* add = nullptr, float* out_f32 = nullptr) {
   P3_REQUIRE(D % 4 == 0 && D > 0 && D <= 128 * LN_MAX_V4, P3TOK_ERR_UNSUPPORTED, "layernorm: D=%d must be a multiple of 4, <= %d", D,
              128 * LN_MAX_V4);
-  P3_REQUIRE(x && out && (!w == !b), P3TOK_ERR_INVALID, "layernorm: null pointer");
+  P3_REQUIRE(x && (out || out_f32) && (!w == !b), P3TOK_ERR_INVALID, "layernorm: null pointer");
   if (M == 0) return P3TOK_OK;
   const unsigned blocks = (unsigned)((M + 15) / 16);   // 8 warps x 2 rows
-  if (D <= 384) ln_rows_kernel<3><<<blocks, 256, 0, s>>>(x, M, D, eps, w, b, out, rescale);
-  else if (D <= 768) ln_rows_kernel<6><<<blocks, 256, 0, s>>>(x, M, D, eps, w, b, out, rescale);
-  else ln_rows_kernel<LN_MAX_V4><<<blocks, 256, 0, s>>>(x, M, D, eps, w, b, out, rescale);
+  if (D <= 384) ln_rows_kernel<3><<<blocks, 256, 0, s>>>(x, M, D, eps, w, b, out, rescale, add, out_f32);
+  else if (D <= 768) ln_rows_kernel<6><<<blocks, 256, 0, s>>>(x, M, D, eps, w, b, out, rescale, add, out_f32);
+  else ln_rows_kernel<LN_MAX_V4><<<blocks, 256, 0, s>>>(x, M, D, eps, w, b, out, rescale, add, out_f32);
   P3_LAUNCH_CHECK("ln_rows_kernel");
   return P3TOK_OK;
 }
@@ -139,7 +150,7 @@ static int layernorm_bf16(float* x, int64_t M, int D, float eps, const float* w,
 // encoder_norm + max over the tokens of a cloud (apf.py:364-366).  One CTA per cloud, warp per token row.
 __global__ void __launch_bounds__(256)
 norm_max_kernel(const float* __restrict__ x, int G, int D, float eps, const float* __restrict__ w, const float* __restrict__ b,
-                float* __restrict__ pooled) {
+                float* __restrict__ pooled, int skip) {   // skip: leading rows of every sequence left out of the max (a cls token)
   __shared__ float4 red[8][32 * LN_MAX_V4];   // [warp][D/4], 32 KB
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = D >> 2;
@@ -147,7 +158,7 @@ norm_max_kernel(const float* __restrict__ x, int G, int D, float eps, const floa
   float4 mx[LN_MAX_V4];
 #pragma unroll
   for (int i = 0; i < LN_MAX_V4; ++i) mx[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-  for (int r = warp; r < G; r += 8) {
+  for (int r = warp + skip; r < G; r += 8) {
     const float4* xr = reinterpret_cast<const float4*>(xb + (size_t)r * D);
     float4 v[LN_MAX_V4];
     float s = 0.f;
@@ -572,7 +583,7 @@ static int linear_wide(const __nv_bfloat16* A, int64_t M, int K, const __nv_bflo
 using namespace p3tok;
 
 extern "C" int64_t p3tok_apf_vit_workspace_bytes(int64_t B, int64_t G, int64_t D, int64_t H, int64_t R) {
-  if (B < 0 || G < 0 || D <= 0 || H <= 0 || R <= 0) return -1;
+  if (B < 0 || G < 0 || D <= 0 || H <= 0 || R < 0) return -1;
   return apf_vit_workspace(B, G, D, H, R);
 }
 
@@ -608,38 +619,42 @@ extern "C" int p3tok_linear_bf16_ex(const void* A, int64_t M, int64_t K, const v
                       (__nv_bfloat16*)out_bf16, out_f32, as_stream(stream));
 }
 
-extern "C" int p3tok_apf_vit_forward(float* x, int64_t B, int64_t G, int64_t D, int64_t heads, int64_t H, int64_t R,
-                                     const p3tok_vit_layer* layers, int64_t n_layers, const float* final_norm_w,
-                                     const float* final_norm_b, float ln_eps, float* pooled_out, void* workspace,
-                                     int64_t workspace_bytes, void* stream) {
-  P3_REQUIRE(B >= 0 && G >= 0 && D > 0 && H > 0 && R > 0 && heads > 0 && n_layers >= 0, P3TOK_ERR_INVALID, "apf_vit: bad shape");
-  P3_REQUIRE(D % 8 == 0 && H % 64 == 0 && R % 8 == 0, P3TOK_ERR_UNSUPPORTED, "apf_vit: D, R must be multiples of 8, H of 64");
-  P3_REQUIRE(D <= 128 * LN_MAX_V4, P3TOK_ERR_UNSUPPORTED, "apf_vit: D=%lld > %d", (long long)D, 128 * LN_MAX_V4);
+// The block stack in its two flavours:
+//   APFViTLayer (apf_utils.py:236-293): R > 0 adapter columns ride in the fc1 / fc2 GEMMs, the layer output carries 2 x
+//   timm Block (pix4point.py:254-255 `feats = blk(feats + pos_embed)`; timm 1.0.16 vision_transformer.Block, the dependency the
+//              reference pins in requirements.txt): R = 0, plain residuals, the positional embedding re-added in front of
+//              every block (fused into the block's first normalisation pass), a cls row at the head of every sequence.
+static int vit_forward(float* x, int64_t B, int64_t G, int64_t D, int64_t heads, int64_t H, int64_t R, const p3tok_vit_layer* layers,
+                       int64_t n_layers, const float* pos, float res_mul, const float* final_norm_w, const float* final_norm_b,
+                       float eps, float* out_norm, float* pooled_out, int pool_skip, void* workspace, int64_t workspace_bytes,
+                       cudaStream_t s) {
+  P3_REQUIRE(B >= 0 && G >= 0 && D > 0 && H > 0 && R >= 0 && heads > 0 && n_layers >= 0, P3TOK_ERR_INVALID, "vit: bad shape");
+  P3_REQUIRE(D % 8 == 0 && H % 64 == 0 && R % 8 == 0, P3TOK_ERR_UNSUPPORTED, "vit: D, R must be multiples of 8, H of 64");
+  P3_REQUIRE(D <= 128 * LN_MAX_V4, P3TOK_ERR_UNSUPPORTED, "vit: D=%lld > %d", (long long)D, 128 * LN_MAX_V4);
   P3_REQUIRE(D % heads == 0 && (D / heads == 32 || D / heads == 64), P3TOK_ERR_UNSUPPORTED,
-             "apf_vit: head dim %lld (supported: 32, 64)", (long long)(D / heads));
-  P3_REQUIRE(B * G < (1ll << 31) - 256, P3TOK_ERR_UNSUPPORTED, "apf_vit: too many token rows");
+             "vit: head dim %lld (supported: 32, 64)", (long long)(D / heads));
+  P3_REQUIRE(B * G < (1ll << 31) - 256, P3TOK_ERR_UNSUPPORTED, "vit: too many token rows");
+  P3_REQUIRE(eps > 0.f && eps < 1.f, P3TOK_ERR_INVALID, "vit: ln_eps %g", (double)eps);
+  P3_REQUIRE(pool_skip >= 0 && pool_skip < (G > 0 ? G : 1), P3TOK_ERR_INVALID, "vit: pool_skip %d", pool_skip);
   const int64_t M = B * G;
   if (M == 0) return P3TOK_OK;
-  P3_REQUIRE(x && workspace && (n_layers == 0 || layers), P3TOK_ERR_INVALID, "apf_vit: null pointer");
-  P3_REQUIRE(!pooled_out || (final_norm_w && final_norm_b), P3TOK_ERR_INVALID, "apf_vit: pooled output needs encoder_norm");
+  P3_REQUIRE(x && workspace && (n_layers == 0 || layers), P3TOK_ERR_INVALID, "vit: null pointer");
+  P3_REQUIRE((!pooled_out && !out_norm) || (final_norm_w && final_norm_b), P3TOK_ERR_INVALID, "vit: outputs need the final norm");
   const VitWs L = vit_layout(M, D, H, R);
-  P3_REQUIRE(workspace_bytes >= L.total, P3TOK_ERR_WORKSPACE, "apf_vit: workspace %lld < %lld bytes", (long long)workspace_bytes,
+  P3_REQUIRE(workspace_bytes >= L.total, P3TOK_ERR_WORKSPACE, "vit: workspace %lld < %lld bytes", (long long)workspace_bytes,
              (long long)L.total);
-  cudaStream_t s = as_stream(stream);
   uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
   __nv_bfloat16* a = reinterpret_cast<__nv_bfloat16*>(ws + L.a);
   __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(ws + L.qkv);
   __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(ws + L.h);
-  P3_REQUIRE(ln_eps > 0.f && ln_eps < 1.f, P3TOK_ERR_INVALID, "apf_vit: ln_eps %g", (double)ln_eps);
-  const float eps = ln_eps;
   const int HR = (int)(H + R);
   int rc;
   for (int64_t li = 0; li < n_layers; ++li) {
     const p3tok_vit_layer& w = layers[li];
     P3_REQUIRE(w.qkv_w && w.qkv_b && w.proj_w && w.proj_b && w.fc1d_w && w.fc1d_b && w.fc2u_w && w.fc2u_b, P3TOK_ERR_INVALID,
-               "apf_vit: layer %lld has a null parameter", (long long)li);
-    // attention branch: x += proj(attention(norm1(x)))                                    (apf_utils.py:279-283)
-    if ((rc = layernorm_bf16(x, M, (int)D, eps, nullptr, nullptr, a, 1.f, s))) return rc;
+               "vit: layer %lld has a null parameter", (long long)li);
+    // attention branch: x (+= pos) ; x += proj(attention(norm1(x)))                       (apf_utils.py:279-283)
+    if ((rc = layernorm_bf16(x, M, (int)D, eps, nullptr, nullptr, a, 1.f, s, pos))) return rc;
     if ((rc = linear_wide(a, M, (int)D, (const __nv_bfloat16*)w.qkv_w, (int)(3 * D), w.qkv_b, 0, 0, qkv, s))) return rc;
     if ((rc = attention_bf16(qkv, B, G, (int)D, (int)heads, a, s))) return rc;
     {
@@ -648,8 +663,9 @@ extern "C" int p3tok_apf_vit_forward(float* x, int64_t B, int64_t G, int64_t D, 
       if ((rc = tc_linear_ex(a, M, (int)D, (const __nv_bfloat16*)w.proj_w, (int)D, w.proj_b, 0, ex, nullptr, x, s))) return rc;
     }
     // adapter + MLP on the same x: out = mlp(norm2(x)) + [scale * up(relu(down(adapter_norm(x)))) + x] + x   (:284-292)
-    // the normalisation pass also leaves 2 x behind, so that the last GEMM, like proj, only ADDS into the stream
-    if ((rc = layernorm_bf16(x, M, (int)D, eps, nullptr, nullptr, a, 2.f, s))) return rc;
+    // the normalisation pass also leaves res_mul x behind (2 for APFViTLayer, 1 for a timm Block), so that the last GEMM,
+    // like proj, only ADDS into the stream
+    if ((rc = layernorm_bf16(x, M, (int)D, eps, nullptr, nullptr, a, res_mul, s))) return rc;
     if ((rc = linear_wide(a, M, (int)D, (const __nv_bfloat16*)w.fc1d_w, HR, w.fc1d_b, 1, (int)H, h, s))) return rc;
     {
       TcExtra ex;
@@ -657,9 +673,29 @@ extern "C" int p3tok_apf_vit_forward(float* x, int64_t B, int64_t G, int64_t D, 
       if ((rc = tc_linear_ex(h, M, HR, (const __nv_bfloat16*)w.fc2u_w, (int)D, w.fc2u_b, 0, ex, nullptr, x, s))) return rc;
     }
   }
+  if (out_norm) {
+    if ((rc = layernorm_bf16(x, M, (int)D, eps, final_norm_w, final_norm_b, nullptr, 1.f, s, nullptr, out_norm))) return rc;
+  }
   if (pooled_out) {
-    norm_max_kernel<<<(unsigned)B, 256, 0, s>>>(x, (int)G, (int)D, eps, final_norm_w, final_norm_b, pooled_out);
+    norm_max_kernel<<<(unsigned)B, 256, 0, s>>>(x, (int)G, (int)D, eps, final_norm_w, final_norm_b, pooled_out, pool_skip);
     P3_LAUNCH_CHECK("norm_max_kernel");
   }
   return P3TOK_OK;
+}
+
+extern "C" int p3tok_apf_vit_forward(float* x, int64_t B, int64_t G, int64_t D, int64_t heads, int64_t H, int64_t R,
+                                     const p3tok_vit_layer* layers, int64_t n_layers, const float* final_norm_w,
+                                     const float* final_norm_b, float ln_eps, float* pooled_out, void* workspace,
+                                     int64_t workspace_bytes, void* stream) {
+  P3_REQUIRE(R > 0, P3TOK_ERR_INVALID, "apf_vit: the adapter bottleneck R must be positive (use p3tok_vit_forward for plain blocks)");
+  return vit_forward(x, B, G, D, heads, H, R, layers, n_layers, nullptr, 2.f, final_norm_w, final_norm_b, ln_eps, nullptr, pooled_out, 0,
+                     workspace, workspace_bytes, as_stream(stream));
+}
+
+extern "C" int p3tok_vit_forward(float* x, int64_t B, int64_t S, int64_t D, int64_t heads, int64_t H, const p3tok_vit_layer* layers,
+                                 int64_t n_layers, const float* pos, const float* final_norm_w, const float* final_norm_b,
+                                 float ln_eps, float* out_norm, float* pooled_out, int64_t pool_skip, void* workspace,
+                                 int64_t workspace_bytes, void* stream) {
+  return vit_forward(x, B, S, D, heads, H, 0, layers, n_layers, pos, 1.f, final_norm_w, final_norm_b, ln_eps, out_norm, pooled_out,
+                     (int)pool_skip, workspace, workspace_bytes, as_stream(stream));
 }

@@ -673,6 +673,56 @@ def _(tokens, params, heads, bottleneck, final_w, final_b, ln_eps=1e-5):
     return tokens.new_empty(tokens.shape), tokens.new_empty((tokens.shape[0], tokens.shape[2]))
 
 
+@torch.library.custom_op("p3tok::vit_blocks", mutates_args=(), device_types="cuda")
+def vit_blocks(feats: torch.Tensor, pos: Optional[torch.Tensor], params: Sequence[torch.Tensor], heads: int, final_w: torch.Tensor,
+               final_b: torch.Tensor, ln_eps: float, pool_skip: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Plain pre-norm ViT blocks (timm `Block`, what Pix4Point runs): feats (B,S,D) f32 = [cls ; tokens], pos (B,S,D) or None
+    re-added in front of every block -> (LayerNorm(x) (B,S,D) f32, max over rows >= pool_skip (B,D) f32).  params: 8 tensors
+    per layer in VIT_LAYER_TENSORS order, folded by p4p_model.fold_timm_block (no adapter columns)."""
+    if len(params) % _NVT:
+        raise RuntimeError(f"p3tok::vit_blocks: expected {_NVT} tensors per layer")
+    nl = len(params) // _NVT
+    _need_cuda("vit_blocks", feats, pos, final_w, final_b, *params)
+    x = _f32c("vit_blocks", feats).clone()
+    B, S, D = (int(v) for v in x.shape)
+    p = _f32c("vit_blocks", pos) if pos is not None else None
+    if p is not None and tuple(p.shape) != (B, S, D):
+        raise RuntimeError("p3tok::vit_blocks: pos must have the shape of feats")
+    fw, fb = _f32c("vit_blocks", final_w), _f32c("vit_blocks", final_b)
+    keep = []
+    layers = (_lib.VitLayerStruct * max(nl, 1))()
+    H = 64
+    for li in range(nl):
+        for j, name in enumerate(VIT_LAYER_TENSORS):
+            t = params[li * _NVT + j]
+            want = torch.bfloat16 if name.endswith("_w") else torch.float32
+            if t.dtype != want:
+                raise RuntimeError(f"p3tok::vit_blocks: layer {li} {name} must be {want}, got {t.dtype}")
+            t = t.contiguous()
+            keep.append(t)
+            setattr(layers[li], name, t.data_ptr())
+        qkv, proj, fc1, fc2 = (params[li * _NVT + j] for j in (0, 2, 4, 6))
+        H = int(fc1.shape[0])
+        if tuple(qkv.shape) != (3 * D, D) or tuple(proj.shape) != (D, D) or fc1.shape[1] != D or tuple(fc2.shape) != (D, H):
+            raise RuntimeError("p3tok::vit_blocks: weight shapes do not match the token width")
+    out = torch.empty((B, S, D), dtype=torch.float32, device=x.device)
+    pooled = torch.empty((B, D), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        nbytes = int(_L().p3tok_apf_vit_workspace_bytes(B, S, D, H, 0))
+        ws = torch.empty((max(nbytes, 1024),), dtype=torch.uint8, device=x.device)
+        with _timed("vit_blocks"):
+            check(_L().p3tok_vit_forward(x.data_ptr(), B, S, D, int(heads), H, layers, nl, _ptr(p), fw.data_ptr(), fb.data_ptr(),
+                                         float(ln_eps), out.data_ptr(), pooled.data_ptr(), int(pool_skip), ws.data_ptr(), nbytes,
+                                         _stream()), "vit_blocks")
+    del keep
+    return out, pooled
+
+
+@vit_blocks.register_fake
+def _(feats, pos, params, heads, final_w, final_b, ln_eps, pool_skip):
+    return feats.new_empty(feats.shape), feats.new_empty((feats.shape[0], feats.shape[2]))
+
+
 @torch.library.custom_op("p3tok::layernorm_bf16", mutates_args=(), device_types="cuda")
 def layernorm_bf16(x: torch.Tensor, w: Optional[torch.Tensor], b: Optional[torch.Tensor], eps: float) -> torch.Tensor:
     """bf16(LayerNorm(x)) over the last dimension of x (M,D) f32; w = b = None: normalisation without affine."""

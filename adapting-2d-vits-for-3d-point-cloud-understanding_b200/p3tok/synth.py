@@ -215,6 +215,33 @@ def apf_vit_state(dim: int, depth: int, num_classes: int = 15, seed: int = 0, bo
     return sd
 
 
+def pointvit_state(dim: int, depth: int, seed: int = 0, mlp_ratio: int = 4) -> Dict[str, np.ndarray]:
+    """state_dict (numpy) of the timm ViT inside the reference's PointViT (src/models/pix4point.py:221-228): `vit.blocks.{i}.*`
+    with timm's Block layout (norm1, attn.qkv, attn.proj, norm2, mlp.fc1, mlp.fc2) and `vit.norm.*`."""
+    ws = _WeightStream(seed + 15485863)
+    sd: Dict[str, np.ndarray] = {}
+
+    def lin(name, cout, cin, scale=1.0):
+        bound = scale / math.sqrt(cin)
+        sd[name + ".weight"] = ws.uniform((cout, cin), -bound, bound)
+        sd[name + ".bias"] = ws.uniform((cout,), -bound, bound)
+
+    def ln(name):
+        sd[name + ".weight"] = ws.uniform((dim,), 0.5, 1.5)
+        sd[name + ".bias"] = ws.uniform((dim,), -0.1, 0.1)
+
+    for i in range(depth):
+        b = f"vit.blocks.{i}."
+        ln(b + "norm1")
+        lin(b + "attn.qkv", 3 * dim, dim, 2.0)
+        lin(b + "attn.proj", dim, dim)
+        ln(b + "norm2")
+        lin(b + "mlp.fc1", mlp_ratio * dim, dim)
+        lin(b + "mlp.fc2", dim, mlp_ratio * dim)
+    ln("vit.norm")
+    return sd
+
+
 def vit_tokens(B: int, G: int, D: int, seed: int) -> np.ndarray:
     """Synthetic (B,G,D) token batch in [-1,1) for the ViT block-stack cases."""
     u = uniform01(seed, B * G * D, 17).reshape(B, G, D)

@@ -253,6 +253,19 @@ P3TOK_API int p3tok_apf_vit_forward(float* x, int64_t B, int64_t G, int64_t D, i
                           const float* final_norm_b, float ln_eps, float* pooled_out, void* workspace,
                           int64_t workspace_bytes, void* stream);
 
+/* The same stack for plain pre-norm ViT blocks - the timm `Block`s Pix4Point runs (src/models/pix4point.py:248-256; timm
+ * 1.0.16 is the reference's pinned dependency, requirements.txt): x = x + proj(attn(norm1(x))); x = x + fc2(gelu(fc1(norm2(x)))).
+ * x (B,S,D) f32 = [cls ; tokens], updated in place.  pos (B,S,D) f32 or NULL: added to x in front of EVERY block (line 255
+ * `feats = blk(feats + pos_embed)`; fused into the block's first normalisation pass).  Layers use the same folded descriptor
+ * with no adapter columns: fc1d_w [H, D] = fc1.weight diag(g2), fc2u_w [D, H] = fc2.weight.
+ * out_norm (B,S,D) f32 or NULL: LayerNorm(x; final_norm) - what PointViT.forward returns (line 256);
+ * pooled_out (B,D) f32 or NULL: max over the rows s >= pool_skip of LayerNorm(x) (forward_cls_feat's 'max' feature over the
+ * tokens without the cls row: pool_skip = 1).  Workspace: p3tok_apf_vit_workspace_bytes(B, S, D, H, 0). */
+P3TOK_API int p3tok_vit_forward(float* x, int64_t B, int64_t S, int64_t D, int64_t heads, int64_t H,
+                      const p3tok_vit_layer* layers, int64_t n_layers, const float* pos, const float* final_norm_w,
+                      const float* final_norm_b, float ln_eps, float* out_norm, float* pooled_out, int64_t pool_skip,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Building blocks of the above, exported for tests.
  * p3tok_layernorm_bf16: out = bf16(LN(x; w, b)) over the rows of x (M,D) f32; w = b = NULL: normalisation only.
  * p3tok_attention_bf16: qkv (B*G, 3D) bf16 laid out as AttentionLayer's reshape(B,N,3,heads,hd) -> out (B*G, D) bf16. */

@@ -298,6 +298,38 @@ def apf_vit(sd: Dict[str, np.ndarray], tokens: np.ndarray, depth: int, heads: in
     return x, pooled, logits
 
 
+def timm_block(sd: Dict[str, np.ndarray], prefix: str, x: np.ndarray, heads: int, eps: float = 1e-6) -> np.ndarray:
+    """One pre-norm ViT block as Pix4Point runs it (src/models/pix4point.py:254-255 calls timm's `Block`; timm is absent from
+    the reference tree - pinned timm==1.0.16 in requirements.txt - so its published forward is restated:
+    x = x + proj(softmax(q k^T / sqrt(hd)) v) on norm1(x);  x = x + fc2(gelu(fc1(norm2(x)))), LayerNorm eps 1e-6, qkv with
+    bias, no LayerScale (`init_values=None` for vit_small_patch16_384), DropPath / dropout = identity in eval), float64."""
+    f = lambda k: np.asarray(sd[prefix + k], np.float64)
+    B, S, D = x.shape
+    hd = D // heads
+    a = _layer_norm(sd, prefix + "norm1", x, eps)
+    qkv = (a @ f("attn.qkv.weight").T + f("attn.qkv.bias")).reshape(B, S, 3, heads, hd).transpose(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    att = (q @ k.transpose(0, 1, 3, 2)) * hd ** -0.5
+    att = np.exp(att - att.max(-1, keepdims=True))
+    att = att / att.sum(-1, keepdims=True)
+    o = (att @ v).transpose(0, 2, 1, 3).reshape(B, S, D)
+    x = x + (o @ f("attn.proj.weight").T + f("attn.proj.bias"))
+    h = _layer_norm(sd, prefix + "norm2", x, eps) @ f("mlp.fc1.weight").T + f("mlp.fc1.bias")
+    h = 0.5 * h * (1.0 + _erf(h / np.sqrt(2.0)))
+    return x + (h @ f("mlp.fc2.weight").T + f("mlp.fc2.bias"))
+
+
+def pointvit_blocks(sd: Dict[str, np.ndarray], feats: np.ndarray, pos: np.ndarray, depth: int, heads: int, eps: float = 1e-6):
+    """The tail of PointViT.forward (pix4point.py:254-256) + forward_cls_feat (260-271, global_features 'max,cls'):
+    feats, pos (B,1+G,D) -> (normed (B,1+G,D), global (B,2D) = [max over the tokens without cls || cls])."""
+    x = feats.astype(np.float64)
+    p = pos.astype(np.float64)
+    for i in range(depth):
+        x = timm_block(sd, f"vit.blocks.{i}.", x + p, heads, eps)
+    x = _layer_norm(sd, "vit.norm", x, eps)
+    return x, np.concatenate([x[:, 1:].max(1), x[:, 0]], 1)
+
+
 # ----------------------------------------------------------------------------- comparison helpers
 
 def knn_tie_equivalent(idx_a: np.ndarray, idx_b: np.ndarray, dist_full: np.ndarray,

@@ -40,6 +40,13 @@ VIT_CASES = {
     "vit_s12": dict(B=1, G=128, D=384, heads=12, depth=12, classes=15, seed=53),    # ViT-S geometry of BASELINE config 2
 }
 
+P4P_VIT_CASES = {
+    # Pix4Point's ViT tail (pix4point.py:254-271): timm-style pre-norm blocks with the positional embedding re-added before every
+    # block, final norm, 'max,cls' features: dict(B, G, D, heads, depth, seed)  (sequence = 1 cls row + G tokens)
+    "p4p_vit": dict(B=2, G=20, D=128, heads=2, depth=3, seed=61),          # head dim 64, ragged sequence of 21
+    "p4p_vit_s": dict(B=1, G=64, D=384, heads=6, depth=12, seed=62),       # vit_small_patch16_384 geometry, BASELINE C1 token count
+}
+
 P4P_TRAIN_CASES = {
     # training-mode P3Embed (1 stage) through the reference's own forward + autograd: dict(B, N, k, W, seed)
     "p4p_train": dict(B=2, N=64, k=8, W=32, seed=96),

@@ -224,6 +224,51 @@ def vit_case(ref, name, c):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), x=x.numpy(), pooled=pooled.numpy(), logits=logits.numpy())
 
 
+def p4p_vit_inputs(c):
+    """(feats (B,1+G,D), pos (B,1+G,D), state) of a P4P_VIT_CASES entry (shared with the tests)."""
+    S = c["G"] + 1
+    feats = synth.vit_tokens(c["B"], S, c["D"], c["seed"])
+    pos = (0.3 * synth.vit_tokens(c["B"], S, c["D"], c["seed"] + 1000)).astype(np.float32)
+    return feats, pos, synth.pointvit_state(c["D"], c["depth"], c["seed"])
+
+
+def p4p_vit_case(name, c):
+    """Pix4Point's blocks are timm `Block`s (pix4point.py:221-228); timm is neither in the reference tree nor installed, so
+    the fixture comes from an INDEPENDENT implementation of the same published block - torch.nn.TransformerEncoderLayer
+    (norm_first, exact GELU, eps 1e-6, packed q/k/v projection in timm's order) - driven exactly as the reference drives its
+    blocks: `feats = blk(feats + pos_embed)` per block, final norm, 'max,cls' features (pix4point.py:254-271)."""
+    import torch.nn as nn
+    feats, pos, sd = p4p_vit_inputs(c)
+    tsd = synth.to_torch_state(sd)
+    D, H = c["D"], 4 * c["D"]
+    layers = []
+    for i in range(c["depth"]):
+        l = nn.TransformerEncoderLayer(D, c["heads"], H, dropout=0.0, activation="gelu", layer_norm_eps=1e-6, batch_first=True,
+                                       norm_first=True).eval()
+        b = f"vit.blocks.{i}."
+        l.load_state_dict({"self_attn.in_proj_weight": tsd[b + "attn.qkv.weight"], "self_attn.in_proj_bias": tsd[b + "attn.qkv.bias"],
+                           "self_attn.out_proj.weight": tsd[b + "attn.proj.weight"], "self_attn.out_proj.bias": tsd[b + "attn.proj.bias"],
+                           "linear1.weight": tsd[b + "mlp.fc1.weight"], "linear1.bias": tsd[b + "mlp.fc1.bias"],
+                           "linear2.weight": tsd[b + "mlp.fc2.weight"], "linear2.bias": tsd[b + "mlp.fc2.bias"],
+                           "norm1.weight": tsd[b + "norm1.weight"], "norm1.bias": tsd[b + "norm1.bias"],
+                           "norm2.weight": tsd[b + "norm2.weight"], "norm2.bias": tsd[b + "norm2.bias"]})
+        layers.append(l)
+    norm = nn.LayerNorm(D, eps=1e-6).eval()
+    norm.load_state_dict({"weight": tsd["vit.norm.weight"], "bias": tsd["vit.norm.bias"]})
+    with torch.no_grad():
+        x, p = torch.from_numpy(feats), torch.from_numpy(pos)
+        for l in layers:
+            x = l(x + p)
+        x = norm(x)
+        glob = torch.cat([x[:, 1:].max(1)[0], x[:, 0]], 1)
+    ox, og = oracle.pointvit_blocks(sd, feats, pos, c["depth"], c["heads"])
+    e1 = np.abs(ox - x.numpy()).max() / np.abs(x.numpy()).max()
+    e2 = np.abs(og - glob.numpy()).max() / np.abs(glob.numpy()).max()
+    print(f"{name}: oracle vs torch.nn.TransformerEncoderLayer stack: feats {e1:.2e}, global {e2:.2e}")
+    assert max(e1, e2) < 2e-5, name
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), feats=x.numpy(), glob=glob.numpy())
+
+
 def train_inputs(c):
     """(neigh (B,G,k,2C) f32, grad_tokens (B,G,E) f32, encoder state) of a TRAIN_CASES entry (shared with the tests)."""
     x = synth.make_cloud("uniform", c["B"], c["N"], c["seed"], c["C"])
@@ -361,6 +406,8 @@ def main():
         if want(name): head_case(name, c)
     for name, c in cases.VIT_CASES.items():
         if want(name): vit_case(ref, name, c)
+    for name, c in cases.P4P_VIT_CASES.items():
+        if want(name): p4p_vit_case(name, c)
     for name, c in cases.TRAIN_CASES.items():
         if want(name): train_case(ref, name, c)
     for name, c in cases.P4P_TRAIN_CASES.items():

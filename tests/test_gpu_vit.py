@@ -173,3 +173,54 @@ def test_vit_empty_batch():
     blocks, norm, _ = _stack(c, synth.apf_vit_state(64, 1, 15, 69))
     x, pooled = run_blocks(blocks, torch.zeros(0, 4, 64, device=dev()), norm)
     assert tuple(x.shape) == (0, 4, 64) and tuple(pooled.shape) == (0, 64)
+
+
+# ------------------------------------------------------------------ Pix4Point's block stack (timm Block variant of next #3)
+@pytest.mark.parametrize("name", list(cases.P4P_VIT_CASES))
+def test_pointvit_blocks_match_oracle_and_golden(golden_dir, name):
+    """p3tok_vit_forward: pre-norm blocks without adapter, the positional embedding re-added in front of every block
+    (pix4point.py:254-255), final norm, max over the tokens without the cls row - vs the float64 oracle and the
+    torch.nn.TransformerEncoderLayer fixture; bf16 GEMMs / fp32 residual stream: rtol 1e-2."""
+    import make_golden
+    from p3tok.p4p_model import PointViT, fold_timm_block
+    c = cases.P4P_VIT_CASES[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    feats, pos, sd = make_golden.p4p_vit_inputs(c)
+    m = PointViT(embed_dim=c["D"], depth=c["depth"], num_heads=c["heads"], k_neighbors=8).eval().to(dev())
+    missing = m.load_state_dict(synth.to_torch_state(sd), strict=False)
+    assert not missing.unexpected_keys
+    params = [t for blk in m.vit.blocks for t in fold_timm_block(blk)]
+    out, pooled = ops.vit_blocks(to_dev(feats), to_dev(pos), params, c["heads"], m.norm.weight.detach(), m.norm.bias.detach(), 1e-6, 1)
+    ox, og = oracle.pointvit_blocks(sd, feats, pos, c["depth"], c["heads"])
+    D = c["D"]
+    assert_tokens_close(out.cpu().numpy(), ox, 1e-2, f"{name} normed feats vs oracle")
+    assert_tokens_close(out.cpu().numpy(), g["feats"], 1e-2, f"{name} normed feats vs golden")
+    assert_tokens_close(pooled.cpu().numpy(), og[:, :D], 1e-2, f"{name} token max vs oracle")
+    assert_tokens_close(torch.cat([pooled, out[:, 0]], 1).cpu().numpy(), g["glob"], 1e-2, f"{name} 'max,cls' features vs golden")
+
+
+def test_pointvit_module_end_to_end():
+    """PointViT drop-in (P3Embed -> proj / pos_embed / cls -> blocks -> norm -> 'max,cls'), BASELINE C1 shapes at B = 2, against the
+    oracle chain p3embed -> token_head -> pointvit_blocks; state_dict carries the reference's key names."""
+    from p3tok.p4p_model import PointViT
+    B, N, k, E = 2, 1024, 32, 384
+    m = PointViT(embed_dim=E, k_neighbors=k, sample_ratio=1 / 16, precision="fp32").eval().to(dev())
+    sd_p = synth.p3embed_state(3, 1 / 16, 4, 4, 256, 7)
+    sd_h = synth.token_head_state(256, E, 7)
+    sd_v = synth.pointvit_state(E, 12, 7)
+    m.patch_embed.load_state_dict(synth.to_torch_state(sd_p), strict=True)
+    miss = m.load_state_dict({**synth.to_torch_state(sd_h), **synth.to_torch_state(sd_v)}, strict=False)
+    assert not miss.unexpected_keys
+    keys = set(m.state_dict())
+    assert {"vit.blocks.0.attn.qkv.weight", "vit_blocks.11.mlp.fc2.bias", "vit.norm.weight", "norm.bias", "cls_token", "vit.cls_token",
+            "cls_pos", "proj.weight", "pos_embed.2.bias", "patch_embed.convs.1.1.4.running_var"} <= keys
+    p = synth.make_cloud("uniform", B, N, 7, 3)
+    starts = [synth.start_indices(B, N, 7, 0), synth.start_indices(B, N // 4, 7, 1)]
+    glob = m.forward_cls_feat(to_dev(p), None, [to_dev(s) for s in starts])
+    p_list, x_list, feats = m(to_dev(p), None, [to_dev(s) for s in starts])
+    assert feats.shape == (B, 1 + N // 16, E) and glob.shape == (B, 2 * E)
+    op, of, _ = oracle.p3embed(sd_p, p, p.copy(), starts, k, 2)
+    hf, hp = oracle.token_head(sd_h, of[-1].astype(np.float32), op[-1])
+    ox, og = oracle.pointvit_blocks(sd_v, hf, hp, 12, 6)
+    assert_tokens_close(feats.cpu().numpy(), ox, 1e-2, "PointViT feats vs oracle")
+    assert_tokens_close(glob.cpu().numpy(), og, 1e-2, "PointViT 'max,cls' vs oracle")

@@ -194,3 +194,16 @@ def test_vit_backward_oracle(golden_dir, name):
     for mine, key in ((pooled, "pooled"), (dx, "grad_tokens"), (gn["encoder_norm.weight"], "grad_norm_w"),
                       (gn["encoder_norm.bias"], "grad_norm_b")):
         assert np.abs(mine - g[key]).max() <= 1e-5 * np.abs(g[key]).max(), key
+
+
+@pytest.mark.parametrize("name", list(cases.P4P_VIT_CASES))
+def test_pointvit_block_oracle_matches_golden(golden_dir, name):
+    """oracle.pointvit_blocks (timm Block restated, pix4point.py:254-271) against the fixture an independent implementation of the
+    same block (torch.nn.TransformerEncoderLayer) produced in make_golden.py."""
+    import make_golden
+    c = cases.P4P_VIT_CASES[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    feats, pos, sd = make_golden.p4p_vit_inputs(c)
+    ox, og = oracle.pointvit_blocks(sd, feats, pos, c["depth"], c["heads"])
+    assert np.abs(ox - g["feats"]).max() <= 2e-5 * np.abs(g["feats"]).max()
+    assert np.abs(og - g["glob"]).max() <= 2e-5 * np.abs(g["glob"]).max()
