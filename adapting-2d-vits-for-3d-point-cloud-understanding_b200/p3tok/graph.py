@@ -15,11 +15,15 @@ import torch
 
 
 class GraphedTokenizer:
-    def __init__(self, fn: Callable[..., torch.Tensor], example_inputs: Sequence[torch.Tensor], warmup: int = 3):
-        """fn(*inputs) -> tensor; example_inputs fix shapes/dtypes/device (their values seed the static buffers)."""
+    def __init__(self, fn: Callable[..., torch.Tensor], example_inputs: Sequence[torch.Tensor], warmup: int = 3,
+                 stream: "torch.cuda.Stream | None" = None):
+        """fn(*inputs) -> tensor; example_inputs fix shapes/dtypes/device (their values seed the static buffers).
+        stream: run `__call__` / `replay_on_stream` on this stream - two instances on two streams keep two steps in flight
+        (the index kernels of one step overlap the embedding of the other), what bench.py's device loop does."""
         if not example_inputs or not all(t.is_cuda for t in example_inputs):
             raise RuntimeError("GraphedTokenizer: CUDA example inputs required")
         self.device = example_inputs[0].device
+        self.stream = stream
         self.inputs = [t.clone() for t in example_inputs]
         self.graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(device=self.device)
@@ -38,6 +42,11 @@ class GraphedTokenizer:
         return self.output
 
     def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:
+        if self.stream is not None:
+            with torch.cuda.stream(self.stream):
+                for dst, src in zip(self.inputs, inputs):
+                    dst.copy_(src, non_blocking=True)
+                return self.replay()
         for dst, src in zip(self.inputs, inputs):
             dst.copy_(src, non_blocking=True)
         return self.replay()

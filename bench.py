@@ -306,9 +306,10 @@ def run_reference(args, w, rank, world):
 class Harness:
     """One workload on this rank's GPU: builds the model, the L2-defeating input pool and the graphs, and times windows."""
 
-    def __init__(self, w, B, precision, token_dtype, device, rank, world, kind, eager=False):
+    def __init__(self, w, B, precision, token_dtype, device, rank, world, kind, eager=False, streams=2):
         import torch.distributed as dist
         self.dist, self.w, self.B, self.device, self.rank, self.world, self.eager = dist, w, B, device, rank, world, eager
+        self.streams = streams
         self.net, self.run = build_gpu_model(w, precision, device, token_dtype)
         x_np, st_np = make_inputs(w, B, 1234 + rank, kind)
         self.x_host = torch.from_numpy(x_np).pin_memory()
@@ -333,7 +334,7 @@ class Harness:
     def step_dev(self, i):
         j = i % self.pool_n
         if self.gdev is not None:
-            return self.gdev(self.pool[j], *self.st_pool[j])
+            return self.gdev[i % len(self.gdev)](self.pool[j], *self.st_pool[j])
         return self.run(self.pool[j], self.st_pool[j])
 
     def prepare_device_loop(self, warmup):
@@ -350,9 +351,13 @@ class Harness:
             # wrapper); every step first copies its clouds and start indices from the HBM-resident pool into the graph's
             # input buffers (device-to-device, inside the timed region), then replays.  --eager times the Python-dispatched
             # module call instead (launch-bound for the small workloads).
+            # `streams` instances on as many streams keep that many steps in flight (default 2, like the e2e path): the index
+            # kernels of one step (FPS is a latency chain on <= 1 CTA per SM) overlap the embedding of the other.
             if not self.eager:
-                self.gdev = GraphedTokenizer(lambda x, *st: self.run(x, list(st)), [self.base] + self.st_pool[0])
-                for i in range(3):
+                self.dev_streams = [torch.cuda.Stream(device=self.device) for _ in range(self.streams)] if self.streams > 1 else [None]
+                self.gdev = [GraphedTokenizer(lambda x, *st: self.run(x, list(st)), [self.base] + self.st_pool[0], stream=s_)
+                             for s_ in self.dev_streams]
+                for i in range(2 * len(self.gdev)):
                     self.step_dev(i)
             torch.cuda.synchronize()
 
@@ -366,9 +371,17 @@ class Harness:
             while True:
                 self.barrier()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                main = torch.cuda.current_stream(self.device)
                 e0.record()
+                multi = self.gdev is not None and self.dev_streams[0] is not None
+                if multi:
+                    for s_ in self.dev_streams:
+                        s_.wait_stream(main)           # the step streams start after the start event ...
                 for i in range(steps):
                     self.step_dev(i + len(out))
+                if multi:
+                    for s_ in self.dev_streams:
+                        main.wait_stream(s_)           # ... and the end event is recorded after both have drained
                 e1.record()
                 self.barrier()
                 ms = self.reduce_max(e0.elapsed_time(e1))
@@ -454,7 +467,7 @@ def run_p3tok(args, w, rank, world, local_rank):
     B = per_gpu_clouds(w, world)
     kinds = ["uniform", "clustered"] if args.clouds == "both" else [args.clouds]
 
-    H = Harness(w, B, precision, tok_dtype, device, rank, world, kinds[0], args.eager)
+    H = Harness(w, B, precision, tok_dtype, device, rank, world, kinds[0], args.eager, args.streams)
     if args.ncu > 0:
         # profiling aid, not a measurement: `ncu --profile-from-start off ... bench.py --ncu 1` sees exactly N eager steps
         with torch.no_grad():
@@ -483,7 +496,9 @@ def run_p3tok(args, w, rank, world, local_rank):
         ref_out = H.run(H.x_host.to(device), [s.to(device) for s in H.st_host])
         assert torch.equal(H.graphs[0].host_output.to(device), ref_out), "e2e graph != eager"
         if H.gdev is not None:
-            assert torch.equal(H.gdev(H.pool[0], *H.st_pool[0]), H.run(H.pool[0], H.st_pool[0])), "graph replay != eager"
+            got = H.gdev[0](H.pool[0], *H.st_pool[0])
+            torch.cuda.synchronize()
+            assert torch.equal(got, H.run(H.pool[0], H.st_pool[0])), "graph replay != eager"
     copy_bw = H.copy_bandwidth()
 
     # ---- e2e with the reference's token dtype (f32) when the headline moved bf16 tokens, and with the token all-gather
@@ -584,7 +599,8 @@ def run_p3tok(args, w, rank, world, local_rank):
                    "parallelism": f"batch-shard x{world}, no collective on the path",
                    "l2": f"rotating pool of {H.pool_n} distinct input batches ({H.pool_n * H.in_bytes / 1e6:.0f} MB > L2)",
                    "embed_precision": precision, "token_dtype": "bf16" if tok_dtype is not None else "f32",
-                   "step": "eager module call" if args.eager else "CUDA-graph replay of the module call",
+                   "step": "eager module call" if args.eager else
+                           f"CUDA-graph replay of the module call, {args.streams} step(s) in flight on as many streams",
                    "host_cores_of_rank0": cores},
         "timing": {"windows": len(dev_windows), "steps_per_window": args.steps, "timed_device_s": sum(dev_windows) / 1e3,
                    "ms_per_step_min": min(dev_windows) / args.steps, "ms_per_step_max": max(dev_windows) / args.steps,
@@ -680,6 +696,7 @@ def main():
                     help="input kind of the headline numbers; 'both' = uniform headline + a short clustered run attached as other_clouds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the c5 strong-scaling probe attached to the default c2 line")
+    ap.add_argument("--streams", type=int, default=2, help="steps in flight in the device-resident loop (graphs replayed round-robin on as many streams)")
     ap.add_argument("--ncu", type=int, default=0, help="profiling aid: run N eager steps between cudaProfilerStart/Stop and exit (no timing)")
     ap.add_argument("--eager", action="store_true", help="time the Python-dispatched module call instead of the CUDA-graph replay")
     args = ap.parse_args()
