@@ -1352,7 +1352,7 @@ static BfLayout bf_layout(const p3tok_mlp* m, int64_t ngroups, int64_t k) {
   L.off_gbias = o; o += align_up(L.cg * m->mid_dim * 4, 1024);
   // fp32 scratch for the unfused max (k not a multiple of 32): one [rows, max(F,out)] matrix
   L.off_scratch_f32 = o; o += (k % 32 == 0) ? 0 : align_up(L.rows * wide * 4, 1024);
-  L.off_wpad = o; o += L.kpad0 ? align_up((int64_t)m->pre_dim[0] * L.kpad0 * 2, 1024) : 0;
+  L.off_wpad = o; o += L.kpad0 ? align_up((int64_t)m->pre_dim[0] * align_up(L.kpad0, 64) * 2, 1024) : 0;   // also the 64-padded form
   L.total = o + 1024;
   return L;
 }
@@ -1383,9 +1383,15 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
   // P3Embed rows with a float4-aligned feature width use the rotated [feats | xyz] column order
   const bool rot_rows = L.kpad0 && R->kind == 1 && R->D % 4 == 0 && R->D >= 4 &&
                         (reinterpret_cast<uintptr_t>(R->feats) & 15) == 0;
+  // P3Embed stage >= 1 (a single wide per-point layer): the gather runs inside the GEMM's producer (embed_gather.cu) and the
+  // row matrix never exists.  P3TOK_GATHER_FUSED=0 selects the round-1 path (gather kernel + tc_linear).
+  static int gfuse_on = -1;
+  if (gfuse_on < 0) { const char* e = getenv("P3TOK_GATHER_FUSED"); gfuse_on = e ? atoi(e) : 1; }
+  const bool gather_fused = gfuse_on && rot_rows && m->n_pre == 1 && m->pre_relu[0] == 1 && tc_gather_linear_supported(R, m->pre_dim[0], k);
+  const int64_t kpadw = gather_fused ? align_up(L.kpad0, 64) : L.kpad0;
   if (L.kpad0) {
-    pad_weight_kernel<<<grid_1d((int64_t)m->pre_dim[0] * L.kpad0, 256), 256, 0, s>>>(
-        (const __nv_bfloat16*)m->w_pre[0], m->pre_dim[0], m->cin, (int)L.kpad0, rot_rows ? 3 : 0, wpad);
+    pad_weight_kernel<<<grid_1d((int64_t)m->pre_dim[0] * kpadw, 256), 256, 0, s>>>(
+        (const __nv_bfloat16*)m->w_pre[0], m->pre_dim[0], m->cin, (int)kpadw, rot_rows ? 3 : 0, wpad);
     P3_LAUNCH_CHECK("pad_weight_kernel");
   }
 
@@ -1437,6 +1443,16 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
       P3_LAUNCH_CHECK("rows_first_layer_kernel");
       first_tc = 1;
       kin = m->pre_dim[0];
+    } else if (gather_fused) {
+      __nv_bfloat16* part_bf16 = reinterpret_cast<__nv_bfloat16*>(gmax_f32);
+      rc = tc_gather_linear(R, g0, rows, wpad, m->pre_dim[0], m->b_pre[0], 1, act[cur], parts == 1 ? gmax_bf16 : part_bf16, s);
+      if (rc) return rc;
+      if (parts > 1) {
+        partial_max_bf16_kernel<<<grid_1d(gc * L.F, 256), 256, 0, s>>>(part_bf16, gc, parts, (int)L.F, gmax_bf16);
+        P3_LAUNCH_CHECK("partial_max_bf16_kernel");
+      }
+      first_tc = m->n_pre;            // the block's only per-point layer is done, its patch max too
+      kin = m->pre_dim[0];
     } else if (rot_rows) {
       const unsigned blocks = grid_1d(rows * 32, 256);
       if (i64) rows_gather_p4p_bf16_kernel<int64_t><<<blocks, 256, 0, s>>>(*R, g0, rows, (int)L.kpad0, act[cur]);
@@ -1452,7 +1468,7 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
       kin = (int)L.kpad0;
     }
     // ---- remaining per-point layers on the tensor cores; the last one also emits the patch max
-    bool have_gmax = false;
+    bool have_gmax = gather_fused;
     static int fuse_on = -1;
     // Layer pairs go through tc_fused_kernel (embed_fused.cu): the hidden activation of each pair never reaches HBM.
     // P3TOK_FUSED=0 selects the layer-by-layer path.  History (same-box A/B, bench.py, ms per step): with 64-column

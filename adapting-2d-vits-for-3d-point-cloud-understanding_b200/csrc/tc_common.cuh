@@ -410,4 +410,9 @@ int tc_stage(const __nv_bfloat16* A0, int64_t M, int K0, const __nv_bfloat16* Wa
              const float* gbias, int rows_per_group, const __nv_bfloat16* Wb, int N2, const float* bias_b, float* out_max,
              __nv_bfloat16* out_max_bf16, int max_relu, cudaStream_t s);
 
+// embed_gather.cu
+bool tc_gather_linear_supported(const p3tok_rows* R, int N1, int64_t k);
+int tc_gather_linear(const p3tok_rows* R, int64_t g_begin, int64_t rows, const __nv_bfloat16* W, int N1, const float* bias, int relu,
+                     __nv_bfloat16* out_bf16, __nv_bfloat16* out_max_bf16, cudaStream_t s);
+
 }  // namespace p3tok
