@@ -43,6 +43,9 @@ constexpr int FU_CH_BYTES = 2 * 16384;       // one chunk operand: 128 rows x 12
 constexpr int FU_RA_BOX = 64 * 128;          // 8 KB: this CTA's 64 of the chunk's 128 rows of W_a x 64 k
 constexpr int FU_MAX_RA = 32, FU_MAX_RB = 16;
 constexpr int FU_SMEM = 227 * 1024;
+constexpr int FU_L1_WSTRIDE = 76;            // floats per lane: 32 rel + 32 ctr weights + 8 biases, padded so LDS.128 is conflict-free
+constexpr int FU_L1_STAGE = 128 * 16 + 4 * 16;   // per tile and CTA: 128 rel rows + 4 block centres (float4 each)
+constexpr int FU_L1_BYTES = 32 * FU_L1_WSTRIDE * 4 + 2 * FU_L1_STAGE;
 
 struct FusedParams {
   int M, K0, N1, N2;
@@ -62,6 +65,12 @@ struct FusedParams {
   __nv_bfloat16* out_max_bf16;      // same, bf16, or null
   int max_relu;
   unsigned long long* trace;        // debug (P3TOK_TC_TRACE=1): pair 0's timeline (leader MMA warp + one epilogue warp of each kind)
+  // ---- APF first layer produced in-kernel (K0 == 256): A0 = relu(W_rel . (nbr - ctr) + (W_ctr . ctr + bias)) written by the
+  // chunk-epilogue warps straight into the swizzled A0 tile; l1_rel == null: A0 comes from tmA as before
+  const float4* l1_rel;             // [rows padded to 256] (nbr - ctr) per row, fp32 (apf_rel_rows_kernel)
+  const float4* l1_ctr;             // [rows / 32] centre row of every 32-row block
+  const float* l1_w;                // [32 lanes][FU_L1_WSTRIDE]: lane l's 8 output channels, pair-packed (fused_l1_pack_kernel)
+  int l1_relu;
 };
 // trace[(it * 16 + j) * 16 + slot]; slots 0-7 MMA warp, 8-11 chunk-epilogue warp 2, 12-15 tile-epilogue warp 10 (leader CTA)
 __device__ __forceinline__ void fu_trace(const FusedParams& p, int it, int j, int slot, long long v) {
@@ -82,7 +91,10 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   float* sba = reinterpret_cast<float*>(sST + (p.store_out ? FU_OUT_WARPS * 4096 : 0));   // N1 floats
   float* sbb = sba + p.N1;                               // N2 floats
   float* sgb = sbb + p.N2;                               // chunk warps x 64 floats (group-bias slices)
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sgb + FU_CH_WARPS * 64) + 7) & ~(uintptr_t)7);
+  const bool L1 = p.l1_rel != nullptr;
+  float* sl1w = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sgb + FU_CH_WARPS * 64) + 15) & ~(uintptr_t)15);   // packed first-layer weights
+  uint8_t* sl1 = reinterpret_cast<uint8_t*>(sl1w + (L1 ? 32 * FU_L1_WSTRIDE : 0));                 // 2 x FU_L1_STAGE: rel rows + block centres
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sl1 + (L1 ? 2 * FU_L1_STAGE : 0)) + 7) & ~(uintptr_t)7);
   uint64_t* a0_full = bars;            // leader
   uint64_t* a0_empty = bars + 1;       // local, multicast commit
   uint64_t* acc3_full = bars + 2;      // local, multicast commit
@@ -95,7 +107,9 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* ra_empty = bars + 44;      // [32] local
   uint64_t* rb_full = bars + 76;       // [16] leader
   uint64_t* rb_empty = bars + 92;      // [16] local
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 108);
+  uint64_t* l1_full = bars + 108;      // [2] local, TMA bulk copy (tx bytes)
+  uint64_t* l1_empty = bars + 110;     // [2] local, FU_CH_WARPS arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 112);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -106,8 +120,9 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWa)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWb)) : "memory");
-    mbar_init(a0_full, 1);
+    mbar_init(a0_full, L1 ? 2 * FU_CH_WARPS : 1);      // L1: every chunk-epilogue warp of both CTAs publishes its 16 rows
     mbar_init(a0_empty, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&l1_full[b], 1); mbar_init(&l1_empty[b], FU_CH_WARPS); }
     mbar_init(acc3_full, 1);
     mbar_init(acc3_empty, 2 * FU_OUT_WARPS);
     for (int b = 0; b < 2; ++b) {
@@ -122,6 +137,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   for (int i = threadIdx.x; i < p.N1; i += FU_THREADS) sba[i] = p.bias_a ? p.bias_a[i] : 0.f;
   for (int i = threadIdx.x; i < p.N2; i += FU_THREADS) sbb[i] = p.bias_b ? p.bias_b[i] : 0.f;
+  if (L1) for (int i = threadIdx.x; i < 32 * FU_L1_WSTRIDE; i += FU_THREADS) sl1w[i] = p.l1_w[i];
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
@@ -140,12 +156,35 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int rs = 0;
     uint32_t rph = 0;
     int it = 0;
+    // L1: the first-layer inputs of tile `t` (128 rel rows + 4 block centres of this CTA, 2112 bytes) as two 1-D bulk copies
+    // into staging buffer t & 1; issued one tile ahead of the chunk-epilogue warps that turn them into A0
+    auto l1_load = [&](int t, int tp_t) {
+      const int sb = t & 1;
+      mbar_wait(&l1_empty[sb], ((uint32_t)(t >> 1) & 1) ^ 1);
+      if (issuer) {
+        const int64_t mt_t = 2 * (int64_t)tp_t + rank;
+        uint8_t* dst = sl1 + sb * FU_L1_STAGE;
+        mbar_expect_tx(&l1_full[sb], (uint32_t)FU_L1_STAGE);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                     "l"(reinterpret_cast<uint64_t>(p.l1_rel + mt_t * TC_BM)), "r"(128 * 16), "r"(smem_u32(&l1_full[sb]))
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst + 128 * 16)),
+                     "l"(reinterpret_cast<uint64_t>(p.l1_ctr + mt_t * (TC_BM / 32))), "r"(4 * 16), "r"(smem_u32(&l1_full[sb]))
+                     : "memory");
+      }
+      __syncwarp();
+    };
+    if (L1 && pair_id < p.num_pairs) l1_load(0, pair_id);
     for (int tp = pair_id; tp < p.num_pairs; tp += pair_stride, ++it) {
       const int mt = 2 * tp + rank;         // may be a dummy tile past the end: TMA zero-fills, stores are clipped
-      mbar_wait(a0_empty, (uint32_t)(it & 1) ^ 1);
-      if (issuer) {
-        if (rank == 0) mbar_expect_tx(a0_full, 2u * (uint32_t)KB0 * 16384u);
-        for (int kb = 0; kb < KB0; ++kb) tma_load_2d_pair(sA0 + kb * 16384, &tmA, a0_full, kb * 64, mt * TC_BM);
+      if (L1) {
+        if (tp + pair_stride < p.num_pairs) l1_load(it + 1, tp + pair_stride);
+      } else {
+        mbar_wait(a0_empty, (uint32_t)(it & 1) ^ 1);
+        if (issuer) {
+          if (rank == 0) mbar_expect_tx(a0_full, 2u * (uint32_t)KB0 * 16384u);
+          for (int kb = 0; kb < KB0; ++kb) tma_load_2d_pair(sA0 + kb * 16384, &tmA, a0_full, kb * 64, mt * TC_BM);
+        }
       }
       __syncwarp();
       for (int j = 0; j < NC; ++j) {
@@ -393,8 +432,74 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint8_t* stg = sST + ew * 4096;
     const int ngroups = p.N2 / 64;
     const int fcol = rows_max_frag_col(lane);
+    // L1: tile `t`'s A0 from the staged first-layer inputs, produced by THESE warps: they are idle from the end of their
+    // epilogue until the tile's last B-GEMM retires, and a0_empty fires a whole chunk period before that (after the last
+    // A-GEMM), so the next tile's first A-GEMM finds its operand waiting - like the TMA-loaded A0 (producing in the chunk-
+    // epilogue warps after the last chunk put ~2000 cycles per tile on the critical path: pair kernel 314 -> 370 us at c2).
+    // This warp owns rows ew*16 .. +15 of the CTA's 128 (half of one 32-row block, so one centre); lane l owns output
+    // channels 8l .. 8l+7 = 16-byte chunk l & 7 of k-block l >> 3.  Same fp32 operation order as
+    // rows_first_layer_apf_warp_kernel (base = bias + W_ctr.ctr, then the rel chain), two channels per FFMA2.
+    auto produce_a0 = [&](int t) {
+      const int sb = t & 1;
+      const float* wl = sl1w + lane * FU_L1_WSTRIDE;
+      float wr[32], base[8];
+      {
+        float wc[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          *reinterpret_cast<float4*>(&wr[4 * i]) = *reinterpret_cast<const float4*>(wl + 4 * i);
+          *reinterpret_cast<float4*>(&wc[4 * i]) = *reinterpret_cast<const float4*>(wl + 32 + 4 * i);
+        }
+        *reinterpret_cast<float4*>(&base[0]) = *reinterpret_cast<const float4*>(wl + 64);
+        *reinterpret_cast<float4*>(&base[4]) = *reinterpret_cast<const float4*>(wl + 68);
+        mbar_wait(&l1_full[sb], (uint32_t)(t >> 1) & 1);
+        const float4 cc = *reinterpret_cast<const float4*>(sl1 + sb * FU_L1_STAGE + 128 * 16 + (ew >> 1) * 16);
+        const float cv[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) fma2(base[j], base[j + 1], wc[c * 8 + j], wc[c * 8 + j + 1], cv[c], cv[c], base[j], base[j + 1]);
+        }
+      }
+      const float4* relp = reinterpret_cast<const float4*>(sl1 + sb * FU_L1_STAGE) + ew * 16;
+      const uint32_t dst0 = smem_u32(sA0) + (uint32_t)(lane >> 3) * 16384u;
+#pragma unroll
+      for (int r4 = 0; r4 < 16; r4 += 4) {
+        uint32_t pk[4][4];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const float4 xv = relp[r4 + rr];                 // warp-wide broadcast
+          const float xr[4] = {xv.x, xv.y, xv.z, xv.w};
+          float a[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = base[j];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) fma2(a[j], a[j + 1], wr[c * 8 + j], wr[c * 8 + j + 1], xr[c], xr[c], a[j], a[j + 1]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pk[rr][j] = p.l1_relu ? pack_bf16x2_relu(a[2 * j], a[2 * j + 1]) : pack_bf16x2(a[2 * j], a[2 * j + 1]);
+        }
+        if (r4 == 0) mbar_wait(a0_empty, (uint32_t)(t & 1) ^ 1);      // every MMA that read the previous tile's A0 is done
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const uint32_t trow_ = (uint32_t)(ew * 16 + r4 + rr);
+          const uint32_t dst = dst0 + trow_ * 128u + ((((uint32_t)lane & 7u) ^ (trow_ & 7u)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[rr][0]), "r"(pk[rr][1]), "r"(pk[rr][2]), "r"(pk[rr][3]) : "memory");
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&l1_empty[sb]);
+        mbar_arrive_cta(a0_full, 0);
+      }
+    };
+    if (L1 && pair_id < p.num_pairs) produce_a0(0);
     int it = 0;
     for (int tp = pair_id; tp < p.num_pairs; tp += pair_stride, ++it) {
+      if (L1 && tp + pair_stride < p.num_pairs) produce_a0(it + 1);   // gated by a0_empty: this tile's last A-GEMM has retired
       const int row0 = (2 * tp + rank) * TC_BM + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
@@ -514,11 +619,11 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // ------------------------------------------------------------------------------------------------ host
 // ring depths for these shapes: what is left of shared memory after the resident operands is split between the two weight
 // rings in proportion to the bytes a chunk needs from each (a chunk = K0/64 RA boxes and 2*nq RB boxes)
-static bool fused_rings_n(int K0, int N1, int N2, bool store_out, int nch, int& ra_slots, int& rb_slots, int& rb_box) {
+static bool fused_rings_n(int K0, int N1, int N2, bool store_out, int nch, bool l1, int& ra_slots, int& rb_slots, int& rb_box) {
   const int nq = N2 > 256 ? 2 : 1;
   rb_box = (N2 / nq / 2) * 128;
   const int fixed = (K0 / 64) * 16384 + nch * FU_CH_BYTES + (store_out ? FU_OUT_WARPS * 4096 : 0) +
-                    (N1 + N2 + FU_CH_WARPS * 64) * 4 + 112 * 8 + 64 + 1024;
+                    (N1 + N2 + FU_CH_WARPS * 64) * 4 + (l1 ? FU_L1_BYTES + 16 : 0) + 116 * 8 + 64 + 1024;
   const int left = FU_SMEM - fixed;
   const int chunk_a = (K0 / 64) * FU_RA_BOX, chunk_b = 2 * nq * rb_box;
   if (left < 2 * FU_RA_BOX + 2 * rb_box) return false;
@@ -534,11 +639,11 @@ static bool fused_rings_n(int K0, int N1, int N2, bool store_out, int nch, int& 
 // round trip is ~1000-1500 cycles and a 12 KB weight box is consumed in ~390, so rings of 2-3 slots starve the MMAs
 // (measured: chunk period 5200 cycles against 3100 of MMA work at E = 384).  When the rings would be that shallow the
 // second operand buffer (32 KB) goes to the rings instead.
-static bool fused_rings(int K0, int N1, int N2, bool store_out, int& nch, int& ra_slots, int& rb_slots, int& rb_box) {
+static bool fused_rings(int K0, int N1, int N2, bool store_out, bool l1, int& nch, int& ra_slots, int& rb_slots, int& rb_box) {
   nch = 2;
-  if (fused_rings_n(K0, N1, N2, store_out, 2, ra_slots, rb_slots, rb_box) && ra_slots >= 4 && rb_slots >= 3) return true;
+  if (fused_rings_n(K0, N1, N2, store_out, 2, l1, ra_slots, rb_slots, rb_box) && ra_slots >= 4 && rb_slots >= 3) return true;
   nch = 1;
-  return fused_rings_n(K0, N1, N2, store_out, 1, ra_slots, rb_slots, rb_box);
+  return fused_rings_n(K0, N1, N2, store_out, 1, l1, ra_slots, rb_slots, rb_box);
 }
 
 bool tc_fused_supported(int K0, int N1, int N2, int64_t rows_per_group, bool has_gbias) {
@@ -547,15 +652,43 @@ bool tc_fused_supported(int K0, int N1, int N2, int64_t rows_per_group, bool has
   if (N2 > 256 && (N2 / 2) % 16) return false;          // two B-MMAs of N2/2 columns each
   if (has_gbias && (rows_per_group % 32 != 0)) return false;
   int nch, ra, rb, box;
-  return fused_rings(K0, N1, N2, !has_gbias, nch, ra, rb, box);   // the "pre" pair (no group bias) also stores its output
+  return fused_rings(K0, N1, N2, !has_gbias, false, nch, ra, rb, box);   // the "pre" pair (no group bias) also stores its output
+}
+
+// ---- APF first layer inside the pair kernel: per-lane packed fp32 weights.  Lane l owns output channels 8l .. 8l+7:
+// floats [8c + j] = W[8l + j][c] (rel half, c < 4, zero beyond C), [32 + 8c + j] = W[8l + j][C + c] (centre half), [64 + j] = bias
+__global__ void fused_l1_pack_kernel(const __nv_bfloat16* __restrict__ W, const float* __restrict__ bias, int C, float* __restrict__ out) {
+  const int lane = blockIdx.x, i = threadIdx.x;            // 32 blocks x FU_L1_WSTRIDE threads
+  float v = 0.f;
+  if (i < 64) {
+    const int half = i >> 5, c = (i & 31) >> 3, j = i & 7;
+    if (c < C) v = __bfloat162float(W[(size_t)(8 * lane + j) * (2 * C) + half * C + c]);
+  } else if (i < 72) {
+    v = bias ? bias[8 * lane + (i - 64)] : 0.f;
+  }
+  out[lane * FU_L1_WSTRIDE + i] = v;
+}
+bool tc_fused_l1_supported(int N1, int N2) {
+  if (!tc_fused_supported(256, N1, N2, 32, false)) return false;
+  int nch, ra, rb, box;
+  return fused_rings(256, N1, N2, true, true, nch, ra, rb, box);
+}
+int64_t fused_l1_pack_bytes() { return 32 * FU_L1_WSTRIDE * 4; }
+int fused_l1_pack(const __nv_bfloat16* W, const float* bias, int C, float* packed, cudaStream_t s) {
+  P3_REQUIRE(C == 3 || C == 4, P3TOK_ERR_UNSUPPORTED, "fused_l1_pack: C must be 3 or 4");
+  fused_l1_pack_kernel<<<32, FU_L1_WSTRIDE, 0, s>>>(W, bias, C, packed);
+  P3_LAUNCH_CHECK("fused_l1_pack_kernel");
+  return P3TOK_OK;
 }
 
 // out = W_b relu(W_a A0 + bias_a + gbias) + bias_b.  A0 [M,K0] bf16, W_a [N1,K0], W_b [N2,N1] bf16.
 int tc_fused(const __nv_bfloat16* A0, int64_t M, int K0, const __nv_bfloat16* Wa, int N1, const float* bias_a,
              const float* gbias, int rows_per_group, const __nv_bfloat16* Wb, int N2, const float* bias_b,
-             __nv_bfloat16* out_bf16, float* out_max, __nv_bfloat16* out_max_bf16, int max_relu, cudaStream_t s) {
+             __nv_bfloat16* out_bf16, float* out_max, __nv_bfloat16* out_max_bf16, int max_relu, cudaStream_t s,
+             const FusedL1* l1) {
   P3_REQUIRE(tc_fused_supported(K0, N1, N2, rows_per_group, gbias != nullptr), P3TOK_ERR_UNSUPPORTED,
              "tc_fused: unsupported shape K0=%d N1=%d N2=%d", K0, N1, N2);
+  P3_REQUIRE(!l1 || (K0 == 256 && l1->rel && l1->ctr && l1->w), P3TOK_ERR_UNSUPPORTED, "tc_fused: the in-kernel first layer needs K0 == 256");
   P3_REQUIRE(M < (1ll << 31) - 512, P3TOK_ERR_UNSUPPORTED, "tc_fused: too many rows");
   if (M == 0) return P3TOK_OK;
   FusedParams p;
@@ -574,20 +707,25 @@ int tc_fused(const __nv_bfloat16* A0, int64_t M, int K0, const __nv_bfloat16* Wa
   if (xtile_on < 0) { const char* e = getenv("P3TOK_FUSED_XTILE"); xtile_on = e ? atoi(e) : 0; }
   p.xtile = xtile_on;
   p.rb_box = (p.nq_rows / 2) * 128;
-  P3_REQUIRE(fused_rings(K0, N1, N2, p.store_out != 0, p.nch, p.ra_slots, p.rb_slots, p.rb_box), P3TOK_ERR_UNSUPPORTED,
+  P3_REQUIRE(fused_rings(K0, N1, N2, p.store_out != 0, l1 != nullptr, p.nch, p.ra_slots, p.rb_slots, p.rb_box), P3TOK_ERR_UNSUPPORTED,
              "tc_fused: shapes do not fit shared memory");
+  p.l1_rel = l1 ? l1->rel : nullptr; p.l1_ctr = l1 ? l1->ctr : nullptr; p.l1_w = l1 ? l1->w : nullptr; p.l1_relu = l1 ? l1->relu : 0;
   CUtensorMap ta, twa, twb, tc;
-  int rc = make_map(&ta, A0, M, K0, TC_BM);
+  int rc = make_map(&twa, Wa, N1, K0, FU_CHUNK / 2);  // each CTA of the pair fetches 64 of a chunk's 128 rows
   if (rc) return rc;
-  rc = make_map(&twa, Wa, N1, K0, FU_CHUNK / 2);  // each CTA of the pair fetches 64 of a chunk's 128 rows
-  if (rc) return rc;
+  if (l1) {
+    ta = twa;                                     // unused: A0 is produced in the kernel
+  } else {
+    rc = make_map(&ta, A0, M, K0, TC_BM);
+    if (rc) return rc;
+  }
   rc = make_map(&twb, Wb, N2, N1, p.nq_rows / 2); // ... and half of the output rows of one B-MMA of W_b
   if (rc) return rc;
   if (out_bf16) {
     rc = make_map(&tc, out_bf16, M, N2, 32);
     if (rc) return rc;
   } else {
-    tc = ta;
+    tc = twa;
   }
   static thread_local bool configured[32] = {false};
   int dev = 0;

@@ -138,12 +138,7 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {   // explicit shared-
 // coefficient, so beyond the interval it only falls (q < -34 for t > 6.5, -inf for huge t: 2^q = 0, no clamp needed).
 // 7 FMAs + ONE MUFU (EX2) + FMNMX + FFMA per element: the epilogue of the fc1 GEMM is issue- and MUFU-bound (erff():
 // ~25 instructions; the A&S 7.1.26 form: 2 MUFUs).  Two elements per call: the Horner chain runs as packed FFMA2.
-__device__ __forceinline__ void fma2(float& o0, float& o1, float a0, float a1, float b0, float b1, float c0, float c1) {
-  asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; fma.rn.f32x2 rd, ra, rb, rc; "
-      "mov.b64 {%0,%1}, rd; }"
-      : "=f"(o0), "=f"(o1)
-      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
-}
+// (fma2: tc_common.cuh)
 __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
   const float t0 = fabsf(x0), t1 = fabsf(x1);
   float r0 = -1.808829734e-06f, r1 = -1.808829734e-06f;
@@ -1150,6 +1145,36 @@ rows_first_layer_apf_warp_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, c
   }
 }
 
+// Inputs of the APF first layer when it runs INSIDE the pair kernel (embed_fused.cu, FusedL1): rel[r] = neighbour - centre
+// (fp32, the reference's subtraction, apf.py:83-84) for every row of the chunk and the centre row of every 32-row block -
+// 16 bytes per row instead of the 512-byte bf16 first-layer row.  Rows in [nrows, nrows_pad) are zero-filled (the pair
+// kernel's last tile reads whole 128-row slices).
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+apf_rel_rows_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, int64_t nrows_pad, float4* __restrict__ rel, float4* __restrict__ ctr) {
+  const int C = R.C;
+  const IdxT* knn = reinterpret_cast<const IdxT*>(R.knn_idx);
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows_pad; r += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), c = v;
+    if (r < nrows) {
+      const int64_t bj = g_begin + r / R.k;                // output group (k % 32 == 0: the same for a whole 32-row block)
+      const int64_t b = bj / R.G;
+      const int64_t g = R.perm ? R.perm[bj] : (bj - b * R.G);
+      const float* crow = R.x + (b * R.N + R.ctr_idx[b * R.G + g]) * C;
+      c.x = crow[0]; c.y = crow[1]; c.z = crow[2];
+      if (C == 4) c.w = crow[3];
+      const int64_t ni = (int64_t)knn[(b * R.G + g) * R.k + (r % R.k)];
+      const float* prow = R.x + (b * R.N + ni) * C;
+      v.x = __fsub_rn(prow[0], c.x);
+      v.y = __fsub_rn(prow[1], c.y);
+      v.z = __fsub_rn(prow[2], c.z);
+      if (C == 4) v.w = __fsub_rn(prow[3], c.w);
+    }
+    rel[r] = v;
+    if ((r & 31) == 0) ctr[r >> 5] = c;
+  }
+}
+
 // Wide input: gather rows to bf16 [nrows, kpad], zero padded
 template <typename IdxT>
 __global__ void rows_gather_bf16_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, int cin, int kpad,
@@ -1330,8 +1355,14 @@ static int64_t chunk_groups(int64_t ngroups, int64_t k, int64_t wmax) {
 
 struct BfLayout {
   int64_t cg, rows, wmax, F, kpad0;
-  int64_t off_act0, off_act1, off_gmax_f32, off_gmax_bf16, off_gbias, off_scratch_f32, off_wpad, total;
+  int64_t off_act0, off_act1, off_gmax_f32, off_gmax_bf16, off_gbias, off_scratch_f32, off_wpad, off_l1, total;
+  int64_t l1_rows_pad;              // rows of the chunk padded to whole 256-row pair tiles (0: no in-kernel first layer)
 };
+
+// the first layer can run inside the "pre" pair kernel: APF-shaped block (coordinates in, 256 -> N1 -> F per-point layers)
+static bool l1_fusable_mlp(const p3tok_mlp* m, int64_t k) {
+  return m->cin <= 8 && m->n_pre == 3 && m->pre_dim[0] == 256 && m->pre_relu[0] == 1 && k % 32 == 0;
+}
 
 static BfLayout bf_layout(const p3tok_mlp* m, int64_t ngroups, int64_t k) {
   BfLayout L;
@@ -1353,6 +1384,9 @@ static BfLayout bf_layout(const p3tok_mlp* m, int64_t ngroups, int64_t k) {
   // fp32 scratch for the unfused max (k not a multiple of 32): one [rows, max(F,out)] matrix
   L.off_scratch_f32 = o; o += (k % 32 == 0) ? 0 : align_up(L.rows * wide * 4, 1024);
   L.off_wpad = o; o += L.kpad0 ? align_up((int64_t)m->pre_dim[0] * align_up(L.kpad0, 64) * 2, 1024) : 0;   // also the 64-padded form
+  L.l1_rows_pad = l1_fusable_mlp(m, k) ? align_up(L.rows, 256) : 0;
+  L.off_l1 = o;                     // packed first-layer weights | rel rows | block centres
+  o += L.l1_rows_pad ? align_up(fused_l1_pack_bytes(), 1024) + L.l1_rows_pad * 16 + align_up(L.l1_rows_pad / 32 * 16, 1024) : 0;
   L.total = o + 1024;
   return L;
 }
@@ -1403,7 +1437,32 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
     // ---- first layer: CUDA cores for narrow inputs, otherwise gather to bf16 rows for the tensor cores
     int first_tc = 0;
     int kin;
-    if (!L.kpad0) {
+    // APF blocks: the first layer runs inside the "pre" pair kernel (embed_fused.cu, FusedL1) - its 512-byte bf16 rows are
+    // never written; what the pair kernel reads instead is 16 bytes per row (neighbour - centre) + one centre per 32 rows.
+    // P3TOK_L1_FUSED=0 selects the separate first-layer kernel.
+    static int l1f_on = -1, fuse_on0 = -1;
+    if (l1f_on < 0) { const char* e = getenv("P3TOK_L1_FUSED"); l1f_on = e ? atoi(e) : 1; }
+    if (fuse_on0 < 0) { const char* e = getenv("P3TOK_FUSED"); fuse_on0 = e ? atoi(e) : 1; }
+    FusedL1 l1;
+    const bool l1_fused = l1f_on && fuse_on0 && L.l1_rows_pad && !L.kpad0 && R->kind == 0 && (R->C == 3 || R->C == 4) && fused_max &&
+                          m->pre_relu[1] == 1 && m->pre_relu[2] == 0 && tc_fused_l1_supported(m->pre_dim[1], m->pre_dim[2]);
+    if (l1_fused) {
+      char* l1b = base + L.off_l1;
+      float* packed = reinterpret_cast<float*>(l1b);
+      float4* rel = reinterpret_cast<float4*>(l1b + align_up(fused_l1_pack_bytes(), 1024));
+      float4* ctr = rel + L.l1_rows_pad;
+      if (g0 == 0) {
+        rc = fused_l1_pack((const __nv_bfloat16*)m->w_pre[0], m->b_pre[0], R->C, packed, s);
+        if (rc) return rc;
+      }
+      const int64_t rows_pad = align_up(rows, 256);
+      if (i64) apf_rel_rows_kernel<int64_t><<<grid_1d(rows_pad, 256), 256, 0, s>>>(*R, g0, rows, rows_pad, rel, ctr);
+      else apf_rel_rows_kernel<int32_t><<<grid_1d(rows_pad, 256), 256, 0, s>>>(*R, g0, rows, rows_pad, rel, ctr);
+      P3_LAUNCH_CHECK("apf_rel_rows_kernel");
+      l1.rel = rel; l1.ctr = ctr; l1.w = packed; l1.relu = 1;
+      first_tc = 1;
+      kin = m->pre_dim[0];
+    } else if (!L.kpad0) {
       const unsigned blocks = (unsigned)((rows + 31) / 32);
       // single per-point layer (P3Embed stage 0) with k = 32: the first-layer kernel also emits the patch max
       __nv_bfloat16* l1_gmax = (m->n_pre == 1 && k == 32 && m->pre_dim[0] % 2 == 0) ? gmax_bf16 : nullptr;
@@ -1478,6 +1537,7 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
     const bool fuse_pre = fuse_on && fused_max && (m->n_pre - first_tc == 2) && m->pre_relu[m->n_pre - 2] == 1 &&
                           m->pre_relu[m->n_pre - 1] == 0 &&
                           tc_fused_supported(kin, m->pre_dim[m->n_pre - 2], m->pre_dim[m->n_pre - 1], k, false);
+    P3_REQUIRE(fuse_pre || !l1_fused, P3TOK_ERR_UNSUPPORTED, "patch_embed(bf16): in-kernel first layer without the pair kernel");
     if (fuse_pre) {
       // both tensor-core per-point layers in one kernel: the (rows x pre_dim[n-2]) hidden activation stays on-chip
       const int i0 = m->n_pre - 2, i1 = m->n_pre - 1;
@@ -1486,7 +1546,7 @@ int patch_embed_bf16(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t 
       __nv_bfloat16* part_bf16 = reinterpret_cast<__nv_bfloat16*>(gmax_f32);
       rc = tc_fused(act[cur], rows, kin, (const __nv_bfloat16*)m->w_pre[i0], m->pre_dim[i0], m->b_pre[i0], nullptr, 32,
                     (const __nv_bfloat16*)m->w_pre[i1], m->pre_dim[i1], m->b_pre[i1], act[cur ^ 1],
-                    nullptr, parts == 1 ? gmax_bf16 : part_bf16, 0, s);
+                    nullptr, parts == 1 ? gmax_bf16 : part_bf16, 0, s, l1_fused ? &l1 : nullptr);
       if (rc) return rc;
       if (parts > 1) {
         partial_max_bf16_kernel<<<grid_1d(gc * L.F, 256), 256, 0, s>>>(part_bf16, gc, parts, (int)L.F, gmax_bf16);

@@ -322,6 +322,13 @@ __device__ __forceinline__ void add2(float& o0, float& o1, float a0, float a1, f
       : "=f"(o0), "=f"(o1)
       : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
+// (o0, o1) = (fma(a0, b0, c0), fma(a1, b1, c1)) as one packed FFMA2 (each half rounded like fmaf)
+__device__ __forceinline__ void fma2(float& o0, float& o1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; fma.rn.f32x2 rd, ra, rb, rc; "
+      "mov.b64 {%0,%1}, rd; }"
+      : "=f"(o0), "=f"(o1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
 // bf16x2 {lo = relu(a), hi = relu(b)}: ReLU fused into the conversion (F2FP.RELU.BF16.F32.PACK_AB)
 __device__ __forceinline__ uint32_t pack_bf16x2_relu(float a, float b) {
   uint32_t d;
@@ -400,9 +407,21 @@ static inline int num_sms() {
 
 // embed_fused.cu
 bool tc_fused_supported(int K0, int N1, int N2, int64_t rows_per_group, bool has_gbias);
+// l1 != null: A0 is not read - the kernel forms it from the APF first layer (K0 == 256; see FusedL1)
+struct FusedL1 {
+  const float4* rel;     // [rows padded to a multiple of 256] neighbour - centre per row (fp32; .w = height channel or 0)
+  const float4* ctr;     // [padded rows / 32] centre row of every 32-row block
+  const float* w;        // packed first-layer weights, fused_l1_pack()
+  int relu;
+};
+bool tc_fused_l1_supported(int N1, int N2);   // "pre" pair 256 -> N1 -> N2 with the first layer in-kernel
+int64_t fused_l1_pack_bytes();
+// W [256, 2C] bf16 (columns [rel | ctr]), bias [256] or null -> packed fp32 per-lane layout
+int fused_l1_pack(const __nv_bfloat16* W, const float* bias, int C, float* packed, cudaStream_t s);
 int tc_fused(const __nv_bfloat16* A0, int64_t M, int K0, const __nv_bfloat16* Wa, int N1, const float* bias_a,
              const float* gbias, int rows_per_group, const __nv_bfloat16* Wb, int N2, const float* bias_b,
-             __nv_bfloat16* out_bf16, float* out_max, __nv_bfloat16* out_max_bf16, int max_relu, cudaStream_t s);
+             __nv_bfloat16* out_bf16, float* out_max, __nv_bfloat16* out_max_bf16, int max_relu, cudaStream_t s,
+             const FusedL1* l1 = nullptr);
 
 // embed_stage.cu
 bool tc_stage_supported(int K0, int N1, int N2, int64_t rows_per_group);
