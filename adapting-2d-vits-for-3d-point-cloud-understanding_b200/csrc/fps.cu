@@ -12,9 +12,16 @@
 // ((dx*dx)+(dy*dy))+(dz*dz) (no FMA contraction), a thread-local strict-> argmax (lowest index
 // wins), two redux.sync per warp (max of the distance bits, then min index among the maxima),
 // one __syncthreads, a second redux over the per-warp winners.  Clouds larger than 8192 points
-// use a cluster of 2/4/8/16 CTAs: each CTA owns a contiguous slice, pushes its candidate
-// (distance, index, xyz) into every peer's shared memory through DSMEM and the cluster barrier
-// orders the exchange.
+// use a cluster of 2..16 CTAs: each CTA owns a contiguous slice and pushes its candidate
+// (distance, index, xyz) into every peer's shared memory through DSMEM (st.async + mbarrier).
+// Cluster CTAs carry FPS_EXTRA more points per thread whose coordinates stay in shared memory
+// (only their running minimum is a register): a slice may hold 10240 points, so the cluster size is
+// not forced to a power of two - it is chosen so that ALL clouds of the launch are resident at once
+// (cudaOccupancyMaxActiveClusters).  Found with profiles/microbench/fps_cluster_trace.cu: a B200 seats
+// only 15 clusters of 8 CTAs (a cluster must sit inside one GPC), so the 16 clouds of BASELINE
+// configs[3] ran as TWO waves (3.9 ms); as clusters of 7 (9363 points per CTA) they are one.
+#include <stdlib.h>
+
 #include <cooperative_groups.h>
 #include <cuda/ptx>
 
@@ -25,8 +32,23 @@ namespace cg = cooperative_groups;
 namespace p3tok {
 
 constexpr int FPS_PPT = 8;           // points per thread (registers)
+constexpr int FPS_EXTRA = 4;         // "wide slice" cluster CTAs: further points per thread, coordinates read from shared memory
 constexpr int FPS_MAX_THREADS = 1024;
-constexpr int FPS_SLICE = FPS_PPT * FPS_MAX_THREADS;  // 8192 points per CTA
+constexpr int FPS_SLICE = FPS_PPT * FPS_MAX_THREADS;  // 8192 points per CTA (single-CTA clouds)
+constexpr int FPS_SLICE_X = (FPS_PPT + FPS_EXTRA) * FPS_MAX_THREADS;   // 12288 points per wide-slice cluster CTA
+
+#ifdef P3TOK_FPS_TRACE     // profiles/microbench/fps_cluster_trace.cu: per-phase clock stamps of iteration 100 of cloud 0
+__device__ long long fps_trace_buf[16 * 32];
+#define FPS_T(slot)                                                                                       \
+  do {                                                                                                    \
+    if (g == 100 && cloud == 0 && lane == 0 && (warp == 0 || warp == 5))                                  \
+      fps_trace_buf[rank * 32 + (warp ? 16 : 0) + (slot)] = clock64();                                    \
+    if ((slot) == 0 && (g == 200 || g == 1200) && cloud == 0 && t == 0)                                   \
+      fps_trace_buf[rank * 32 + (g == 200 ? 8 : 9)] = clock64();                                          \
+  } while (0)
+#else
+#define FPS_T(slot) do { } while (0)
+#endif
 
 struct __align__(16) FpsCand {
   uint32_t key;   // float bits of the candidate's min-distance (>= 0 -> order preserving)
@@ -89,14 +111,18 @@ __device__ __forceinline__ void fps_mul2(float& o0, float& o1, float a0, float a
       : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 
-template <int CL>
+// CL = 1: one CTA per cloud.  CL > 1: a cluster of `ncta` <= CL CTAs per cloud (run-time size).  E: shared-memory points per
+// thread on top of the FPS_PPT register points (0, or FPS_EXTRA for slices beyond 8192 points: +~110 issue cycles per extra
+// point and iteration, so only where it saves a wave).
+template <int CL, int E = 0>
 __global__ void __launch_bounds__(FPS_MAX_THREADS, 1)
 fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __restrict__ start_idx,
-           int G, int64_t* __restrict__ out_idx, int slice) {
+           int G, int64_t* __restrict__ out_idx, int slice, int ncta) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // [rows: slice*pt_stride floats][mbarrier 8B][warp slots 2*32*8B][cluster cands 2*16*32B]
   float* rows = reinterpret_cast<float*>(smem_raw);
-  const int rows_bytes = ((slice * pt_stride * 4 + 127) / 128) * 128;
+  const int cap = E > 0 ? max(slice, (FPS_PPT + E) * (int)blockDim.x) : slice;   // points the staging buffer holds
+  const int rows_bytes = ((cap * pt_stride * 4 + 127) / 128) * 128;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + rows_bytes);
   uint2* wslot = reinterpret_cast<uint2*>(smem_raw + rows_bytes + 16);
   FpsCand* ccand = reinterpret_cast<FpsCand*>(smem_raw + rows_bytes + 16 + 2 * 32 * sizeof(uint2));
@@ -109,7 +135,7 @@ fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __r
   int cloud, rank;
   if constexpr (CL > 1) {
     rank = (int)cg::this_cluster().block_rank();
-    cloud = blockIdx.x / CL;
+    cloud = blockIdx.x / ncta;
   } else {
     rank = 0;
     cloud = blockIdx.x;
@@ -156,6 +182,19 @@ fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __r
       md[j] = -2.f;    // padding: never the maximum, never updated (fminf keeps -2)
     }
   }
+  // extra points (cluster CTAs): local index (FPS_PPT + e) * T + t, coordinates stay in `rows`
+  // (a padded slot keeps md = -2 whatever it reads - fminf(-2, anything) - so rows past the slice's points only have to lie
+  // inside the staging buffer: it is sized for (FPS_PPT + E) * T points)
+  static_assert(E % 2 == 0, "extra points are processed as packed pairs");
+  float mdx[E > 0 ? E : 1];
+  const int xstep = T * pt_stride;
+  const int xoff = (FPS_PPT * T + t) * pt_stride;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = (FPS_PPT + e) * T + t;
+    mdx[e] = i < np ? 1e10f : -2.f;
+  }
+  (void)xstep;
 
   int far = (int)start_idx[cloud];
   far = min(max(far, 0), N - 1);   // the C ABI cannot validate device data; an out-of-range start index is clamped
@@ -174,7 +213,7 @@ fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __r
       c.key = 0; c.idx = (uint32_t)far;
       c.x = rows[l * pt_stride]; c.y = rows[l * pt_stride + 1]; c.z = rows[l * pt_stride + 2];
       c.pad[0] = c.pad[1] = c.pad[2] = 0;
-      for (int r = 0; r < CL; ++r) *cluster.map_shared_rank(&ccand[0], r) = c;
+      for (int r = 0; r < ncta; ++r) *cluster.map_shared_rank(&ccand[0], r) = c;
     }
     cluster.sync();
     cx = ccand[0].x; cy = ccand[0].y; cz = ccand[0].z;
@@ -192,7 +231,21 @@ fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __r
     // fused square differs from the reference's ((dx*dx)+(dy*dy))+(dz*dz) in the last bit for ~19 % of the pairs
     // (profiles/microbench/f32x2_check.cu), which flips FPS picks on near-ties (found by the C3-shape parity test).  A
     // scalar add.rn is never contracted; build() checks that the kernel's SASS holds no FFMA2.
+    FPS_T(0);
     const float ncx = -cx, ncy = -cy, ncz = -cz;
+#pragma unroll
+    for (int e = 0; e + 1 < E; e += 2) {       // the shared-memory points, as packed pairs with the same arithmetic
+      const int o0 = xoff + e * xstep, o1 = o0 + xstep;
+      float dx0, dx1, dy0, dy1, dz0, dz1;
+      fps_add2(dx0, dx1, rows[o0], rows[o1], ncx, ncx);
+      fps_add2(dy0, dy1, rows[o0 + 1], rows[o1 + 1], ncy, ncy);
+      fps_add2(dz0, dz1, rows[o0 + 2], rows[o1 + 2], ncz, ncz);
+      fps_mul2(dx0, dx1, dx0, dx1, dx0, dx1);
+      fps_mul2(dy0, dy1, dy0, dy1, dy0, dy1);
+      fps_mul2(dz0, dz1, dz0, dz1, dz0, dz1);
+      mdx[e] = fminf(mdx[e], __fadd_rn(__fadd_rn(dx0, dy0), dz0));
+      mdx[e + 1] = fminf(mdx[e + 1], __fadd_rn(__fadd_rn(dx1, dy1), dz1));
+    }
 #pragma unroll
     for (int j = 0; j < FPS_PPT; j += 2) {
       float dx0, dx1, dy0, dy1, dz0, dz1;
@@ -212,22 +265,28 @@ fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __r
     float best = md[0];
 #pragma unroll
     for (int j = 1; j < FPS_PPT; ++j) best = fmaxf(best, md[j]);
+#pragma unroll
+    for (int e = 0; e < E; ++e) best = fmaxf(best, mdx[e]);
     uint32_t key = best >= 0.f ? __float_as_uint(best) : 0u;
     uint32_t idx = 0xffffffffu;
     {
       const uint32_t wmax = __reduce_max_sync(0xffffffffu, key);
       if (key == wmax && best >= 0.f) {
-        int besti = FPS_PPT - 1;
+        int besti = FPS_PPT + E - 1;
 #pragma unroll
-        for (int j = FPS_PPT - 2; j >= 0; --j) besti = (md[j] == best) ? j : besti;
+        for (int e = E - 2; e >= 0; --e) besti = (mdx[e] == best) ? FPS_PPT + e : besti;
+#pragma unroll
+        for (int j = FPS_PPT - 1; j >= 0; --j) besti = (md[j] == best) ? j : besti;
         idx = (uint32_t)(p0 + besti * T + t);
       }
       idx = __reduce_min_sync(0xffffffffu, idx);
       key = wmax;
     }
     const int buf = g & 1;
+    FPS_T(1);
     if (lane == 0) wslot[buf * 32 + warp] = make_uint2(key, idx);
     __syncthreads();
+    FPS_T(2);
     {
       const uint2 s = (lane < nwarps) ? wslot[buf * 32 + lane] : make_uint2(0u, 0xffffffffu);
       key = s.x; idx = s.y;
@@ -237,7 +296,7 @@ fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __r
       // Only warp 0 talks to the cluster (a cluster-scope acquire by all 1024 threads costs an L1 invalidate each);
       // it reduces the CL candidates and publishes the winner to the CTA through shared memory.
       if (warp == 0) {
-        if (lane < CL) {
+        if (lane < ncta) {
           FpsCand c;
           c.key = key; c.idx = idx;
           if (idx != 0xffffffffu) {
@@ -247,20 +306,24 @@ fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __r
             c.x = c.y = c.z = 0.f;
           }
           c.pad[0] = c.pad[1] = c.pad[2] = 0;
-          if (lane == 0) fps_expect_cands(&cbar[buf], (uint32_t)CL * 32u);
+          if (lane == 0) fps_expect_cands(&cbar[buf], (uint32_t)ncta * 32u);
           fps_push_cand(&ccand[buf * 16 + rank], &cbar[buf], (uint32_t)lane, c);
         }
         // buffer `buf` is reused every second iteration; a peer can be at most one iteration ahead (it needs this
         // CTA's candidate to finish an iteration), so two buffers and the barrier's phase parity are enough
+        FPS_T(3);
         fps_wait_cands(&cbar[buf], (uint32_t)(g >> 1) & 1);
-        uint32_t k2 = lane < CL ? ccand[buf * 16 + lane].key : 0u;
-        uint32_t i2 = lane < CL ? ccand[buf * 16 + lane].idx : 0xffffffffu;
+        FPS_T(4);
+        uint32_t k2 = lane < ncta ? ccand[buf * 16 + lane].key : 0u;
+        uint32_t i2 = lane < ncta ? ccand[buf * 16 + lane].idx : 0xffffffffu;
         const uint32_t mine = i2;
         warp_argmax(k2, i2);                                   // max key, lowest index among the maxima
-        const uint32_t src = __ffs(__ballot_sync(0xffffffffu, lane < CL && mine == i2)) - 1;
+        const uint32_t src = __ffs(__ballot_sync(0xffffffffu, lane < ncta && mine == i2)) - 1;
         if (lane == (int)src) cwin[buf] = ccand[buf * 16 + lane];
+        FPS_T(5);
       }
       __syncthreads();
+      FPS_T(6);
       far = (int)min(cwin[buf].idx, (uint32_t)(N - 1));   // no candidate anywhere (cannot happen for finite input): stay in range
       cx = cwin[buf].x; cy = cwin[buf].y; cz = cwin[buf].z;
     } else {
@@ -271,36 +334,68 @@ fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __r
   if constexpr (CL > 1) cg::this_cluster().sync();   // no CTA exits while peers may still write to it
 }
 
-static size_t fps_smem_bytes(int slice, int pt_stride) {
-  const size_t rows_bytes = (((size_t)slice * pt_stride * 4 + 127) / 128) * 128;
+static size_t fps_smem_bytes(int slice, int pt_stride, int threads = 0, int extra = 0) {
+  const int cap = extra > 0 && (FPS_PPT + extra) * threads > slice ? (FPS_PPT + extra) * threads : slice;
+  const size_t rows_bytes = (((size_t)cap * pt_stride * 4 + 127) / 128) * 128;
   return rows_bytes + 16 + 2 * 32 * sizeof(uint2) + 2 * 16 * sizeof(FpsCand) + 16 + 2 * sizeof(FpsCand);
 }
 
-template <int CL>
-static int fps_launch(const float* x, int B, int N, int pt_stride, const int64_t* start, int G,
-                      int64_t* out, int slice, int threads, cudaStream_t stream) {
-  const size_t smem = fps_smem_bytes(slice, pt_stride);
-  static thread_local size_t configured[32] = {0};   // per device (cudaFuncSetAttribute is per-device state)
+template <int CL, int E>
+static int fps_configure() {
+  static thread_local bool configured[32] = {false};   // per device (cudaFuncSetAttribute is per-device state)
   int dev = 0;
   P3_CUDA(cudaGetDevice(&dev));
-  if (dev < 32 && configured[dev] < smem) {
-    P3_CUDA(cudaFuncSetAttribute(fps_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    if (CL > 8) P3_CUDA(cudaFuncSetAttribute(fps_kernel<CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    configured[dev] = 227 * 1024;
+  if (dev < 32 && !configured[dev]) {
+    P3_CUDA((cudaFuncSetAttribute(fps_kernel<CL, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
+    if (CL > 8) P3_CUDA((cudaFuncSetAttribute(fps_kernel<CL, E>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)));
+    configured[dev] = true;
   }
+  return P3TOK_OK;
+}
+
+// clusters of `ncta` CTAs (threads each, smem bytes each) that can be resident at once on the current device; <= 0: unknown
+template <int CL, int E>
+static int fps_max_clusters(int ncta, int threads, size_t smem) {
+  if (fps_configure<CL, E>() != P3TOK_OK) return -1;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(B * CL));
+  cfg.gridDim = dim3((unsigned)(ncta * 64));
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)ncta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = -1;
+  if (cudaOccupancyMaxActiveClusters(&n, fps_kernel<CL, E>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return n;
+}
+
+template <int CL, int E>
+static int fps_launch(const float* x, int B, int N, int pt_stride, const int64_t* start, int G,
+                      int64_t* out, int slice, int threads, int ncta, cudaStream_t stream) {
+  const size_t smem = fps_smem_bytes(slice, pt_stride, threads, E);
+  int rc = fps_configure<CL, E>();
+  if (rc) return rc;
+  const int CLr = ncta;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(B * CLr));
   cfg.blockDim = dim3((unsigned)threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.x = (unsigned)CLr;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CL > 1 ? 1 : 0;
-  P3_CUDA(cudaLaunchKernelEx(&cfg, fps_kernel<CL>, x, N, pt_stride, start, G, out, slice));
+  P3_CUDA((cudaLaunchKernelEx(&cfg, fps_kernel<CL, E>, x, N, pt_stride, start, G, out, slice, ncta)));
   count_launch();
   return P3TOK_OK;
 }
@@ -321,18 +416,47 @@ extern "C" int p3tok_fps(const float* x, int64_t B, int64_t N, int64_t pt_stride
   P3_REQUIRE(N <= (int64_t)FPS_SLICE * 16, P3TOK_ERR_UNSUPPORTED, "fps: N=%lld exceeds 131072", (long long)N);
   P3_REQUIRE(B * 16 < (1ll << 31) && B * G < (1ll << 40), P3TOK_ERR_UNSUPPORTED, "fps: batch too large");
   cudaStream_t s = as_stream(stream);
-  int cl = 1;
-  while ((int64_t)cl * FPS_SLICE < N) cl *= 2;
-  const int slice = (int)((N + cl - 1) / cl);
-  int threads = ((slice + FPS_PPT - 1) / FPS_PPT + 31) / 32 * 32;
-  if (threads < 32) threads = 32;
-  // a slice must be fully covered by threads*PPT registers
-  P3_REQUIRE(threads <= FPS_MAX_THREADS, P3TOK_ERR_UNSUPPORTED, "fps: internal slice error");
-  switch (cl) {
-    case 1: return fps_launch<1>(x, (int)B, (int)N, (int)pt_stride, start_idx, (int)G, out_idx, slice, threads, s);
-    case 2: return fps_launch<2>(x, (int)B, (int)N, (int)pt_stride, start_idx, (int)G, out_idx, slice, threads, s);
-    case 4: return fps_launch<4>(x, (int)B, (int)N, (int)pt_stride, start_idx, (int)G, out_idx, slice, threads, s);
-    case 8: return fps_launch<8>(x, (int)B, (int)N, (int)pt_stride, start_idx, (int)G, out_idx, slice, threads, s);
-    default: return fps_launch<16>(x, (int)B, (int)N, (int)pt_stride, start_idx, (int)G, out_idx, slice, threads, s);
+  const int Bi = (int)B, Ni = (int)N, Gi = (int)G, ps = (int)pt_stride;
+  if (N <= FPS_SLICE) {           // one CTA per cloud, every point in registers
+    int threads = ((Ni + FPS_PPT - 1) / FPS_PPT + 31) / 32 * 32;
+    if (threads < 32) threads = 32;
+    return fps_launch<1, 0>(x, Bi, Ni, ps, start_idx, Gi, out_idx, Ni, threads, 1, s);
   }
+  // A cluster per cloud.  Candidate sizes: from the smallest that holds the cloud (12288 points per CTA with the shared-
+  // memory extras) up to 8 (16 beyond 8 x 8192 points).  How many clusters of a size the device seats at once is asked of
+  // the driver (once per size) - a cluster must sit inside one GPC, so it is NOT #SMs / size: a B200 seats 15 clusters of 8
+  // or 7, 22 of 6 - and the choice minimises  waves x cycles per iteration  (measured: ~1000 cycles of reduction / exchange
+  // chain + ~0.11 per point of the slice; profiles/microbench/fps_cluster_trace.cu).
+  const int lo = (Ni + FPS_SLICE_X - 1) / FPS_SLICE_X;
+  const int hi = (Ni + FPS_SLICE - 1) / FPS_SLICE <= 8 ? 8 : 16;
+  static thread_local int seats[32][17][33];  // [device][cluster size][warps per CTA]: 0 = not asked yet
+  int dev = 0;
+  P3_CUDA(cudaGetDevice(&dev));
+  static int cl_env = -1;                     // P3TOK_FPS_CLUSTER=n forces the cluster size (experiments)
+  if (cl_env < 0) { const char* e = getenv("P3TOK_FPS_CLUSTER"); cl_env = e ? atoi(e) : 0; }
+  int best_cl = 0, best_threads = 0, best_slice = 0;
+  double best_cost = 0;
+  for (int cl = hi; cl >= lo && cl >= 1; --cl) {
+    if (cl_env >= lo && cl_env <= hi && cl != cl_env) continue;
+    const int slice = (Ni + cl - 1) / cl;
+    const bool wide = slice > FPS_SLICE;
+    if (wide && cl > 8) continue;             // the 16-CTA instantiation has no extras
+    const int ppt = wide ? FPS_PPT + FPS_EXTRA : FPS_PPT;
+    const int threads = ((slice + ppt - 1) / ppt + 31) / 32 * 32;
+    if (threads > FPS_MAX_THREADS) continue;
+    int n = dev < 32 ? seats[dev][cl][threads / 32] : 0;
+    if (n == 0) {
+      const size_t sm = fps_smem_bytes(slice, ps, threads, wide ? FPS_EXTRA : 0);
+      n = cl > 8 ? fps_max_clusters<16, 0>(cl, threads, sm) : wide ? fps_max_clusters<8, FPS_EXTRA>(cl, threads, sm) : fps_max_clusters<8, 0>(cl, threads, sm);
+      if (n <= 0) n = -1;
+      if (dev < 32) seats[dev][cl][threads / 32] = n;
+    }
+    if (n < 0) n = 148 / cl;                  // the driver would not say: assume no placement loss
+    const double cost = (double)((Bi + n - 1) / n) * (1000.0 + 0.11 * slice);
+    if (best_cl == 0 || cost < best_cost) { best_cl = cl; best_cost = cost; best_threads = threads; best_slice = slice; }
+  }
+  P3_REQUIRE(best_cl > 0, P3TOK_ERR_UNSUPPORTED, "fps: no cluster size for N=%lld", (long long)N);
+  if (best_cl > 8) return fps_launch<16, 0>(x, Bi, Ni, ps, start_idx, Gi, out_idx, best_slice, best_threads, best_cl, s);
+  if (best_slice > FPS_SLICE) return fps_launch<8, FPS_EXTRA>(x, Bi, Ni, ps, start_idx, Gi, out_idx, best_slice, best_threads, best_cl, s);
+  return fps_launch<8, 0>(x, Bi, Ni, ps, start_idx, Gi, out_idx, best_slice, best_threads, best_cl, s);
 }

@@ -152,6 +152,26 @@ def test_full_size_properties_c2_and_c4():
         assert np.array_equal(idx[sub].cpu().numpy(), oracle.fps(x[sub], st[sub].cpu().numpy(), G))
 
 
+def test_fps_cluster_size_follows_the_batch():
+    """p3tok_fps picks the cluster size per launch so that all clouds are resident at once (csrc/fps.cu: a B200 seats only
+    15 clusters of 8 CTAs, so 16 clouds of 65536 points run as clusters of 6 with 10923-point slices - 8 register points +
+    4 shared-memory points per thread).  Whatever the decomposition, the picks are the oracle's, bit for bit: the same
+    clouds sampled alone (clusters of 8), in the full batch (wide slices), with 4-channel rows and with sizes around the
+    8192 / 12288-point slice limits, uniform / clustered / duplicated points."""
+    G = 96
+    for (B, N, C, kind) in ((16, 65536, 3, "clustered"), (18, 65536, 4, "uniform"), (3, 9000, 3, "duplicates"),
+                            (40, 12288, 3, "uniform"), (2, 12289, 4, "clustered"), (20, 50001, 3, "duplicates")):
+        x = synth.make_cloud(kind, B, N, 4321 + B, C)
+        st = synth.start_indices(B, N, 4321 + B)
+        xt, stt = to_dev(x), to_dev(st)
+        full = ops.fps(xt, stt, G).cpu().numpy()
+        sub = [0, B - 1]
+        assert np.array_equal(full[sub], oracle.fps(x[sub], st[sub], G)), (B, N, C, kind)
+        alone = ops.fps(xt[:2].contiguous(), stt[:2].contiguous(), G).cpu().numpy()      # 2 clouds: the widest cluster
+        assert np.array_equal(alone, full[:2]), (B, N, C, kind)
+        assert all(len(set(r.tolist())) == min(G, N) for r in full) or kind == "duplicates"
+
+
 def test_randomised_shapes_against_oracle():
     """Seeded sweep over ragged shapes (N, G, k not multiples of the tile sizes; 3- and 4-channel rows; all three
     cloud kinds): FPS, both kNN flavours, Morton order and APF grouping stay bit-exact against the oracle."""
