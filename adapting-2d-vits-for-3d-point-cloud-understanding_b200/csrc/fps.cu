@@ -14,12 +14,12 @@
 // one __syncthreads, a second redux over the per-warp winners.  Clouds larger than 8192 points
 // use a cluster of 2..16 CTAs: each CTA owns a contiguous slice and pushes its candidate
 // (distance, index, xyz) into every peer's shared memory through DSMEM (st.async + mbarrier).
-// Cluster CTAs carry FPS_EXTRA more points per thread whose coordinates stay in shared memory
-// (only their running minimum is a register): a slice may hold 10240 points, so the cluster size is
-// not forced to a power of two - it is chosen so that ALL clouds of the launch are resident at once
-// (cudaOccupancyMaxActiveClusters).  Found with profiles/microbench/fps_cluster_trace.cu: a B200 seats
-// only 15 clusters of 8 CTAs (a cluster must sit inside one GPC), so the 16 clouds of BASELINE
-// configs[3] ran as TWO waves (3.9 ms); as clusters of 7 (9363 points per CTA) they are one.
+// A cluster CTA may hold up to 12288 points ("wide slice": 24 points per thread x 512 threads), so the
+// cluster size is not forced to a power of two - it is chosen so that ALL clouds of the launch are
+// resident at once (cudaOccupancyMaxActiveClusters).  Found with profiles/microbench/
+// fps_cluster_trace.cu: a B200 seats only 15 clusters of 8 (or 7) CTAs - a cluster must sit inside one
+// GPC - so the 16 clouds of BASELINE configs[3] ran as TWO waves (3.9 ms); as clusters of 6 (10923
+// points per CTA; 22 seats) they are one (2.3 ms).
 #include <stdlib.h>
 
 #include <cooperative_groups.h>
@@ -32,10 +32,12 @@ namespace cg = cooperative_groups;
 namespace p3tok {
 
 constexpr int FPS_PPT = 8;           // points per thread (registers)
-constexpr int FPS_EXTRA = 4;         // "wide slice" cluster CTAs: further points per thread, coordinates read from shared memory
+constexpr int FPS_CL_PPT = 16;       // register points per thread of the cluster kernels (512 threads per 8192-point slice)
+constexpr int FPS_WIDE_PPT = 24;     // "wide slice" cluster CTAs: 24 points per thread x 512 threads (126 registers)
 constexpr int FPS_MAX_THREADS = 1024;
-constexpr int FPS_SLICE = FPS_PPT * FPS_MAX_THREADS;  // 8192 points per CTA (single-CTA clouds)
-constexpr int FPS_SLICE_X = (FPS_PPT + FPS_EXTRA) * FPS_MAX_THREADS;   // 12288 points per wide-slice cluster CTA
+constexpr int FPS_SLICE = FPS_PPT * FPS_MAX_THREADS;  // 8192 points per CTA (single-CTA clouds, regular cluster slices)
+constexpr int FPS_SLICE_X = FPS_WIDE_PPT * 512;       // 12288 points per wide-slice cluster CTA
+constexpr int fps_max_threads(int ppt) { return ppt == FPS_WIDE_PPT ? 512 : FPS_SLICE / ppt; }
 
 #ifdef P3TOK_FPS_TRACE     // profiles/microbench/fps_cluster_trace.cu: per-phase clock stamps of iteration 100 of cloud 0
 __device__ long long fps_trace_buf[16 * 32];
@@ -111,18 +113,25 @@ __device__ __forceinline__ void fps_mul2(float& o0, float& o1, float a0, float a
       : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 
-// CL = 1: one CTA per cloud.  CL > 1: a cluster of `ncta` <= CL CTAs per cloud (run-time size).  E: shared-memory points per
-// thread on top of the FPS_PPT register points (0, or FPS_EXTRA for slices beyond 8192 points: +~110 issue cycles per extra
-// point and iteration, so only where it saves a wave).
-template <int CL, int E = 0>
-__global__ void __launch_bounds__(FPS_MAX_THREADS, 1)
+// CL = 1: one CTA per cloud.  CL > 1: a cluster of `ncta` <= CL CTAs per cloud (run-time size).
+// PPT: register points per thread.  An iteration is ISSUE-bound (N = 8192: ~900 of 1270 cycles at 8 points per thread x 32
+// warps): each warp pays ~55 instructions of reduction / tie resolution / loop on top of 6 per point, so more points per
+// thread and fewer warps mean fewer instructions per iteration (measured: 16 beats 8 by 9-12 % from N = 1024 up, 32 is no
+// better than 16).
+// Measured and dropped: (a) a "two clouds per SM" form for 4096 < N <= 8192 (6 register + 10 shared-memory points per thread,
+// 512 threads, 64 registers, two CTAs per SM so that one cloud's reduction chain hides behind the other's distance pass) - 256
+// clouds x 8192 points: 2.54 ms against 2.56 ms for two waves of the register form, the SM is issue-bound either way;
+// (b) shared-memory "extra" points for the wide slices (+~110 issue cycles per point and iteration; registers hold 24);
+// (c) a flag-in-data candidate exchange (tagged 8-byte remote stores polled by warp 0, CTA-scope mbarriers instead of the
+// two __syncthreads): 2640 against 2330 cycles per iteration for the st.async form below.
+template <int CL, int PPT = FPS_PPT>
+__global__ void __launch_bounds__(fps_max_threads(PPT), 1)
 fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __restrict__ start_idx,
            int G, int64_t* __restrict__ out_idx, int slice, int ncta) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // [rows: slice*pt_stride floats][mbarrier 8B][warp slots 2*32*8B][cluster cands 2*16*32B]
   float* rows = reinterpret_cast<float*>(smem_raw);
-  const int cap = E > 0 ? max(slice, (FPS_PPT + E) * (int)blockDim.x) : slice;   // points the staging buffer holds
-  const int rows_bytes = ((cap * pt_stride * 4 + 127) / 128) * 128;
+  const int rows_bytes = ((slice * pt_stride * 4 + 127) / 128) * 128;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + rows_bytes);
   uint2* wslot = reinterpret_cast<uint2*>(smem_raw + rows_bytes + 16);
   FpsCand* ccand = reinterpret_cast<FpsCand*>(smem_raw + rows_bytes + 16 + 2 * 32 * sizeof(uint2));
@@ -168,9 +177,9 @@ fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __r
   }
 
   // ---- registers: PPT points per thread, local index j*T + t (so j ascending == index ascending)
-  float px[FPS_PPT], py[FPS_PPT], pz[FPS_PPT], md[FPS_PPT];
+  float px[PPT], py[PPT], pz[PPT], md[PPT];
 #pragma unroll
-  for (int j = 0; j < FPS_PPT; ++j) {
+  for (int j = 0; j < PPT; ++j) {
     const int i = j * T + t;
     if (i < np) {
       px[j] = rows[i * pt_stride + 0];
@@ -182,20 +191,6 @@ fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __r
       md[j] = -2.f;    // padding: never the maximum, never updated (fminf keeps -2)
     }
   }
-  // extra points (cluster CTAs): local index (FPS_PPT + e) * T + t, coordinates stay in `rows`
-  // (a padded slot keeps md = -2 whatever it reads - fminf(-2, anything) - so rows past the slice's points only have to lie
-  // inside the staging buffer: it is sized for (FPS_PPT + E) * T points)
-  static_assert(E % 2 == 0, "extra points are processed as packed pairs");
-  float mdx[E > 0 ? E : 1];
-  const int xstep = T * pt_stride;
-  const int xoff = (FPS_PPT * T + t) * pt_stride;
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    const int i = (FPS_PPT + e) * T + t;
-    mdx[e] = i < np ? 1e10f : -2.f;
-  }
-  (void)xstep;
-
   int far = (int)start_idx[cloud];
   far = min(max(far, 0), N - 1);   // the C ABI cannot validate device data; an out-of-range start index is clamped
   float cx, cy, cz;
@@ -234,20 +229,7 @@ fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __r
     FPS_T(0);
     const float ncx = -cx, ncy = -cy, ncz = -cz;
 #pragma unroll
-    for (int e = 0; e + 1 < E; e += 2) {       // the shared-memory points, as packed pairs with the same arithmetic
-      const int o0 = xoff + e * xstep, o1 = o0 + xstep;
-      float dx0, dx1, dy0, dy1, dz0, dz1;
-      fps_add2(dx0, dx1, rows[o0], rows[o1], ncx, ncx);
-      fps_add2(dy0, dy1, rows[o0 + 1], rows[o1 + 1], ncy, ncy);
-      fps_add2(dz0, dz1, rows[o0 + 2], rows[o1 + 2], ncz, ncz);
-      fps_mul2(dx0, dx1, dx0, dx1, dx0, dx1);
-      fps_mul2(dy0, dy1, dy0, dy1, dy0, dy1);
-      fps_mul2(dz0, dz1, dz0, dz1, dz0, dz1);
-      mdx[e] = fminf(mdx[e], __fadd_rn(__fadd_rn(dx0, dy0), dz0));
-      mdx[e + 1] = fminf(mdx[e + 1], __fadd_rn(__fadd_rn(dx1, dy1), dz1));
-    }
-#pragma unroll
-    for (int j = 0; j < FPS_PPT; j += 2) {
+    for (int j = 0; j < PPT; j += 2) {
       float dx0, dx1, dy0, dy1, dz0, dz1;
       fps_add2(dx0, dx1, px[j], px[j + 1], ncx, ncx);
       fps_add2(dy0, dy1, py[j], py[j + 1], ncy, ncy);
@@ -264,19 +246,15 @@ fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __r
     // maximum (usually one): lowest j == lowest point index inside a thread, lowest index wins across threads
     float best = md[0];
 #pragma unroll
-    for (int j = 1; j < FPS_PPT; ++j) best = fmaxf(best, md[j]);
-#pragma unroll
-    for (int e = 0; e < E; ++e) best = fmaxf(best, mdx[e]);
+    for (int j = 1; j < PPT; ++j) best = fmaxf(best, md[j]);
     uint32_t key = best >= 0.f ? __float_as_uint(best) : 0u;
     uint32_t idx = 0xffffffffu;
     {
       const uint32_t wmax = __reduce_max_sync(0xffffffffu, key);
       if (key == wmax && best >= 0.f) {
-        int besti = FPS_PPT + E - 1;
+        int besti = PPT - 1;
 #pragma unroll
-        for (int e = E - 2; e >= 0; --e) besti = (mdx[e] == best) ? FPS_PPT + e : besti;
-#pragma unroll
-        for (int j = FPS_PPT - 1; j >= 0; --j) besti = (md[j] == best) ? j : besti;
+        for (int j = PPT - 2; j >= 0; --j) besti = (md[j] == best) ? j : besti;
         idx = (uint32_t)(p0 + besti * T + t);
       }
       idx = __reduce_min_sync(0xffffffffu, idx);
@@ -334,29 +312,28 @@ fps_kernel(const float* __restrict__ x, int N, int pt_stride, const int64_t* __r
   if constexpr (CL > 1) cg::this_cluster().sync();   // no CTA exits while peers may still write to it
 }
 
-static size_t fps_smem_bytes(int slice, int pt_stride, int threads = 0, int extra = 0) {
-  const int cap = extra > 0 && (FPS_PPT + extra) * threads > slice ? (FPS_PPT + extra) * threads : slice;
-  const size_t rows_bytes = (((size_t)cap * pt_stride * 4 + 127) / 128) * 128;
+static size_t fps_smem_bytes(int slice, int pt_stride) {
+  const size_t rows_bytes = (((size_t)slice * pt_stride * 4 + 127) / 128) * 128;
   return rows_bytes + 16 + 2 * 32 * sizeof(uint2) + 2 * 16 * sizeof(FpsCand) + 16 + 2 * sizeof(FpsCand);
 }
 
-template <int CL, int E>
+template <int CL, int PPT>
 static int fps_configure() {
   static thread_local bool configured[32] = {false};   // per device (cudaFuncSetAttribute is per-device state)
   int dev = 0;
   P3_CUDA(cudaGetDevice(&dev));
   if (dev < 32 && !configured[dev]) {
-    P3_CUDA((cudaFuncSetAttribute(fps_kernel<CL, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
-    if (CL > 8) P3_CUDA((cudaFuncSetAttribute(fps_kernel<CL, E>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)));
+    P3_CUDA((cudaFuncSetAttribute(fps_kernel<CL, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
+    if (CL > 8) P3_CUDA((cudaFuncSetAttribute(fps_kernel<CL, PPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)));
     configured[dev] = true;
   }
   return P3TOK_OK;
 }
 
 // clusters of `ncta` CTAs (threads each, smem bytes each) that can be resident at once on the current device; <= 0: unknown
-template <int CL, int E>
+template <int CL, int PPT>
 static int fps_max_clusters(int ncta, int threads, size_t smem) {
-  if (fps_configure<CL, E>() != P3TOK_OK) return -1;
+  if (fps_configure<CL, PPT>() != P3TOK_OK) return -1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(ncta * 64));
   cfg.blockDim = dim3((unsigned)threads);
@@ -369,18 +346,18 @@ static int fps_max_clusters(int ncta, int threads, size_t smem) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = -1;
-  if (cudaOccupancyMaxActiveClusters(&n, fps_kernel<CL, E>, &cfg) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveClusters(&n, fps_kernel<CL, PPT>, &cfg) != cudaSuccess) {
     cudaGetLastError();
     return -1;
   }
   return n;
 }
 
-template <int CL, int E>
+template <int CL, int PPT>
 static int fps_launch(const float* x, int B, int N, int pt_stride, const int64_t* start, int G,
                       int64_t* out, int slice, int threads, int ncta, cudaStream_t stream) {
-  const size_t smem = fps_smem_bytes(slice, pt_stride, threads, E);
-  int rc = fps_configure<CL, E>();
+  const size_t smem = fps_smem_bytes(slice, pt_stride);
+  int rc = fps_configure<CL, PPT>();
   if (rc) return rc;
   const int CLr = ncta;
   cudaLaunchConfig_t cfg = {};
@@ -395,7 +372,7 @@ static int fps_launch(const float* x, int B, int N, int pt_stride, const int64_t
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CL > 1 ? 1 : 0;
-  P3_CUDA((cudaLaunchKernelEx(&cfg, fps_kernel<CL, E>, x, N, pt_stride, start, G, out, slice, ncta)));
+  P3_CUDA((cudaLaunchKernelEx(&cfg, fps_kernel<CL, PPT>, x, N, pt_stride, start, G, out, slice, ncta)));
   count_launch();
   return P3TOK_OK;
 }
@@ -418,12 +395,17 @@ extern "C" int p3tok_fps(const float* x, int64_t B, int64_t N, int64_t pt_stride
   cudaStream_t s = as_stream(stream);
   const int Bi = (int)B, Ni = (int)N, Gi = (int)G, ps = (int)pt_stride;
   if (N <= FPS_SLICE) {           // one CTA per cloud, every point in registers
-    int threads = ((Ni + FPS_PPT - 1) / FPS_PPT + 31) / 32 * 32;
+    static int ppt_env = -1;      // P3TOK_FPS_PPT=8|16|32 forces the points per thread (experiments)
+    if (ppt_env < 0) { const char* e = getenv("P3TOK_FPS_PPT"); ppt_env = e ? atoi(e) : 0; }
+    const int ppt = ppt_env ? ppt_env : (Ni >= 1024 ? 16 : 8);   // measured: 16 beats 8 by 9-12 % from N = 1024 up, 32 is no better
+    int threads = ((Ni + ppt - 1) / ppt + 31) / 32 * 32;
     if (threads < 32) threads = 32;
-    return fps_launch<1, 0>(x, Bi, Ni, ps, start_idx, Gi, out_idx, Ni, threads, 1, s);
+    if (ppt == 32) return fps_launch<1, 32>(x, Bi, Ni, ps, start_idx, Gi, out_idx, Ni, threads, 1, s);
+    if (ppt == 16) return fps_launch<1, 16>(x, Bi, Ni, ps, start_idx, Gi, out_idx, Ni, threads, 1, s);
+    return fps_launch<1, 8>(x, Bi, Ni, ps, start_idx, Gi, out_idx, Ni, threads, 1, s);
   }
-  // A cluster per cloud.  Candidate sizes: from the smallest that holds the cloud (12288 points per CTA with the shared-
-  // memory extras) up to 8 (16 beyond 8 x 8192 points).  How many clusters of a size the device seats at once is asked of
+  // A cluster per cloud.  Candidate sizes: from the smallest that holds the cloud (12288 points per CTA as wide slices)
+  // up to 8 (16 beyond 8 x 8192 points).  How many clusters of a size the device seats at once is asked of
   // the driver (once per size) - a cluster must sit inside one GPC, so it is NOT #SMs / size: a B200 seats 15 clusters of 8
   // or 7, 22 of 6 - and the choice minimises  waves x cycles per iteration  (measured: ~1000 cycles of reduction / exchange
   // chain + ~0.11 per point of the slice; profiles/microbench/fps_cluster_trace.cu).
@@ -440,14 +422,15 @@ extern "C" int p3tok_fps(const float* x, int64_t B, int64_t N, int64_t pt_stride
     if (cl_env >= lo && cl_env <= hi && cl != cl_env) continue;
     const int slice = (Ni + cl - 1) / cl;
     const bool wide = slice > FPS_SLICE;
-    if (wide && cl > 8) continue;             // the 16-CTA instantiation has no extras
-    const int ppt = wide ? FPS_PPT + FPS_EXTRA : FPS_PPT;
+    if (wide && cl > 8) continue;             // the 16-CTA instantiation holds regular slices only
+    const int ppt = wide ? FPS_WIDE_PPT : FPS_CL_PPT;
     const int threads = ((slice + ppt - 1) / ppt + 31) / 32 * 32;
-    if (threads > FPS_MAX_THREADS) continue;
+    if (threads > fps_max_threads(ppt)) continue;
     int n = dev < 32 ? seats[dev][cl][threads / 32] : 0;
     if (n == 0) {
-      const size_t sm = fps_smem_bytes(slice, ps, threads, wide ? FPS_EXTRA : 0);
-      n = cl > 8 ? fps_max_clusters<16, 0>(cl, threads, sm) : wide ? fps_max_clusters<8, FPS_EXTRA>(cl, threads, sm) : fps_max_clusters<8, 0>(cl, threads, sm);
+      const size_t sm = fps_smem_bytes(slice, ps);
+      n = cl > 8 ? fps_max_clusters<16, FPS_CL_PPT>(cl, threads, sm)
+                 : wide ? fps_max_clusters<8, FPS_WIDE_PPT>(cl, threads, sm) : fps_max_clusters<8, FPS_CL_PPT>(cl, threads, sm);
       if (n <= 0) n = -1;
       if (dev < 32) seats[dev][cl][threads / 32] = n;
     }
@@ -456,7 +439,8 @@ extern "C" int p3tok_fps(const float* x, int64_t B, int64_t N, int64_t pt_stride
     if (best_cl == 0 || cost < best_cost) { best_cl = cl; best_cost = cost; best_threads = threads; best_slice = slice; }
   }
   P3_REQUIRE(best_cl > 0, P3TOK_ERR_UNSUPPORTED, "fps: no cluster size for N=%lld", (long long)N);
-  if (best_cl > 8) return fps_launch<16, 0>(x, Bi, Ni, ps, start_idx, Gi, out_idx, best_slice, best_threads, best_cl, s);
-  if (best_slice > FPS_SLICE) return fps_launch<8, FPS_EXTRA>(x, Bi, Ni, ps, start_idx, Gi, out_idx, best_slice, best_threads, best_cl, s);
-  return fps_launch<8, 0>(x, Bi, Ni, ps, start_idx, Gi, out_idx, best_slice, best_threads, best_cl, s);
+  if (best_cl > 8) return fps_launch<16, FPS_CL_PPT>(x, Bi, Ni, ps, start_idx, Gi, out_idx, best_slice, best_threads, best_cl, s);
+  if (best_slice > FPS_SLICE)
+    return fps_launch<8, FPS_WIDE_PPT>(x, Bi, Ni, ps, start_idx, Gi, out_idx, best_slice, best_threads, best_cl, s);
+  return fps_launch<8, FPS_CL_PPT>(x, Bi, Ni, ps, start_idx, Gi, out_idx, best_slice, best_threads, best_cl, s);
 }
