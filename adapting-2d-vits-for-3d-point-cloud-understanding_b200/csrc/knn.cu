@@ -261,21 +261,30 @@ static int knn_launch(const float* x, int B, int N, int pt_stride, const float* 
 // bound minus a margin far above the rounding error of the expansion formula) exceeds the current k-th distance, and
 // because points no longer arrive in index order the filter is non-strict (<=): ties at the k-th distance reach the
 // merge, which orders by (distance, index).
-constexpr int KNS_MAX_N = 8192;
+// Clouds beyond 8192 points (one CTA's shared-memory sort) are handled as S = ceil(N / 8192) SEGMENTS of consecutive points,
+// each sorted on its own (its own Z-order frame, block boxes and cell table); a query walks the segments one after the
+// other, seeding from each.  A segment is a random 1/S sample of the cloud, so its blocks are ~S^(1/3) times wider than a
+// global sort's - at N = 65536 a centre still evaluates only ~2-3 % of the cloud instead of all of it (sweep kernel).
+constexpr int KNS_MAX_N = 8192;                // points per segment
+constexpr int KNS_MAX_SEG = 16;                // N <= 131072
 constexpr int KNS_CELLS = 512;                 // coarse Z-order cells (top 9 bits of the 30-bit code) for the start position
 
 struct KnsLayout {
+  int64_t S, seg, nblk_seg;                     // segments per cloud, points per segment (the last may be shorter), blocks per segment
   int64_t off_pts, off_ids, off_bb, off_lut, off_meta, total;
 };
 static KnsLayout kns_layout(int64_t B, int64_t N) {
   KnsLayout L;
-  const int64_t nblk = (N + 31) / 32;
+  L.S = (N + KNS_MAX_N - 1) / KNS_MAX_N;
+  L.seg = (N + L.S - 1) / L.S;
+  L.nblk_seg = (L.seg + 31) / 32;
+  const int64_t nblk = L.S * L.nblk_seg;
   int64_t o = 0;
   L.off_pts = o; o += B * nblk * 32 * 16;       // float4 {x,y,z,|p|^2}, sorted, padded to whole blocks
   L.off_ids = o; o += B * nblk * 32 * 4;        // int32 original index
   L.off_bb = o; o += B * nblk * 32;             // 8 floats per block: min xyz, max xyz, -, -
-  L.off_lut = o; o += B * (KNS_CELLS + 1) * 4;  // int32 first sorted position of each coarse cell
-  L.off_meta = o; o += B * 32;                  // 8 floats per cloud: min xyz, 1/(max-min) * 1023 xyz, max |p|^2, -
+  L.off_lut = o; o += B * L.S * (KNS_CELLS + 1) * 4;  // int32 first sorted position of each coarse cell (per segment)
+  L.off_meta = o; o += B * L.S * 32;            // 8 floats per segment: min xyz, 1/(max-min) * 1023 xyz, max |p|^2, -
   L.total = o + 256;
   return L;
 }
@@ -296,16 +305,19 @@ __device__ __forceinline__ uint32_t kns_code(float x, float y, float z, const fl
 }
 
 // one CTA per cloud: bounding box, Z-order keys, bitonic sort in shared memory, sorted copies + block boxes + cell table
+// (Ntot points per cloud in S segments of `seg` points; this CTA = segment blockIdx.x % S of cloud blockIdx.x / S;
+//  b below numbers the (cloud, segment) pairs, N is THIS segment's point count, id0 its first original index)
 __global__ void __launch_bounds__(1024)
-knn_prep_kernel(const float* __restrict__ x, int N, int pt_stride, int P2, float4* __restrict__ pts, int* __restrict__ ids,
-                float* __restrict__ bb, int* __restrict__ lut, float* __restrict__ meta_out) {
+knn_prep_kernel(const float* __restrict__ x, int Ntot, int S, int seg, int nblk, int pt_stride, int P2, float4* __restrict__ pts,
+                int* __restrict__ ids, float* __restrict__ bb, int* __restrict__ lut, float* __restrict__ meta_out) {
   extern __shared__ uint64_t keys[];
   __shared__ float red[7][32];
   __shared__ float meta[8];
   __shared__ int slut[KNS_CELLS + 1];
   const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5, T = blockDim.x;
-  const float* P = x + (size_t)b * N * pt_stride;
-  const int nblk = (N + 31) / 32;
+  const int cloud = b / S, id0 = (b - cloud * S) * seg;
+  const int N = min(seg, Ntot - id0);
+  const float* P = x + ((size_t)cloud * Ntot + id0) * pt_stride;
   float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f}, wmax = 0.f;
   for (int i = t; i < N; i += T) {
     const float px = P[(size_t)i * pt_stride], py = P[(size_t)i * pt_stride + 1], pz = P[(size_t)i * pt_stride + 2];
@@ -399,7 +411,7 @@ knn_prep_kernel(const float* __restrict__ x, int N, int pt_stride, int P2, float
       if (cell != prev) slut[cell] = j;
     }
     pts[((size_t)b * nblk) * 32 + j] = pt;
-    ids[((size_t)b * nblk) * 32 + j] = id;
+    ids[((size_t)b * nblk) * 32 + j] = id < 0 ? id : id + id0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -424,26 +436,19 @@ knn_prep_kernel(const float* __restrict__ x, int N, int pt_stride, int P2, float
 template <int KPL, int MODE>
 __global__ void __launch_bounds__(KNN_WARPS * 32)
 knn_sorted_kernel(const float4* __restrict__ pts, const int* __restrict__ ids, const float* __restrict__ bb,
-                  const int* __restrict__ lut, const float* __restrict__ meta_all, int N, const float* __restrict__ centres,
+                  const int* __restrict__ lut, const float* __restrict__ meta_all, int S, int nblk, const float* __restrict__ centres,
                   int G, int64_t total, int k, void* __restrict__ idx_out, int idx_is_i64, float* __restrict__ dist_out) {
   __shared__ uint64_t queue[KNN_WARPS][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t cw = (int64_t)blockIdx.x * KNN_WARPS + warp;      // this warp's centre
   if (cw >= total) return;
   const int b = (int)(cw / G);
-  const int nblk = (N + 31) / 32;
-  const float* meta = meta_all + (size_t)b * 8;
-  const float4* P4 = pts + (size_t)b * nblk * 32;
-  const int* ID = ids + (size_t)b * nblk * 32;
-  const float* BB = bb + (size_t)b * nblk * 8;
   const float* cp = centres + (size_t)cw * 3;
   const float cx = cp[0], cy = cp[1], cz = cp[2];
   const float cn = sq3(cx, cy, cz);
   float c0, c1, c2;
   if (MODE == P3TOK_KNN_APF_SQ) { c0 = cx; c1 = cy; c2 = cz; }
   else { c0 = __fmul_rn(-2.f, cx); c1 = __fmul_rn(-2.f, cy); c2 = __fmul_rn(-2.f, cz); }
-  // margin of the block test: the expansion formula's rounding error is a few ulp of (|c|^2 + |p|^2 + 2|c||p|) <= 2(|c|^2+|p|^2)
-  const float margin = 1e-5f * (cn + meta[6]) + 1e-30f;
 
   uint64_t L[KPL];
 #pragma unroll
@@ -510,9 +515,17 @@ knn_sorted_kernel(const float4* __restrict__ pts, const int* __restrict__ ids, c
     }
   };
 
-  // ---- seed: the blocks around the centre's own position on the curve
+  for (int sg = 0; sg < S; ++sg) {              // segments of the cloud (one for N <= 8192), each sorted on its own
+  const size_t bs = (size_t)b * S + sg;
+  const float* meta = meta_all + bs * 8;
+  const float4* P4 = pts + bs * nblk * 32;
+  const int* ID = ids + bs * nblk * 32;
+  const float* BB = bb + bs * nblk * 8;
+  // margin of the block test: the expansion formula's rounding error is a few ulp of (|c|^2 + |p|^2 + 2|c||p|) <= 2(|c|^2+|p|^2)
+  const float margin = 1e-5f * (cn + meta[6]) + 1e-30f;
+  // ---- seed: the blocks around the centre's own position on the segment's curve
   const int cell = (int)(kns_code(cx, cy, cz, meta) >> 21);
-  const int pos = lut[(size_t)b * (KNS_CELLS + 1) + cell];
+  const int pos = lut[bs * (KNS_CELLS + 1) + cell];
   int s0 = (pos >> 5) - 1;
   s0 = max(0, min(s0, nblk - 3));
   const int s1 = min(nblk, s0 + 3);
@@ -556,6 +569,7 @@ knn_sorted_kernel(const float4* __restrict__ pts, const int* __restrict__ ids, c
       process(P4[bk * 32 + lane], ID[bk * 32 + lane]);
     }
   }
+  }   // segments
   if (qn > 0) merge(qn);
   const int g = (int)(cw - (int64_t)b * G);
   const size_t o = ((size_t)b * G + g) * k;
@@ -572,14 +586,14 @@ knn_sorted_kernel(const float4* __restrict__ pts, const int* __restrict__ ids, c
 }
 
 template <int KPL>
-static int knn_sorted_launch(const float4* pts, const int* ids, const float* bb, const int* lut, const float* meta, int N,
+static int knn_sorted_launch(const float4* pts, const int* ids, const float* bb, const int* lut, const float* meta, int S, int nblk,
                              const float* centres, int G, int64_t total, int k, int mode, void* idx_out, int i64, float* dist_out,
                              cudaStream_t s) {
   const unsigned grid = (unsigned)((total + KNN_WARPS - 1) / KNN_WARPS);
   if (mode == P3TOK_KNN_APF_SQ)
-    knn_sorted_kernel<KPL, P3TOK_KNN_APF_SQ><<<grid, KNN_WARPS * 32, 0, s>>>(pts, ids, bb, lut, meta, N, centres, G, total, k, idx_out, i64, dist_out);
+    knn_sorted_kernel<KPL, P3TOK_KNN_APF_SQ><<<grid, KNN_WARPS * 32, 0, s>>>(pts, ids, bb, lut, meta, S, nblk, centres, G, total, k, idx_out, i64, dist_out);
   else
-    knn_sorted_kernel<KPL, P3TOK_KNN_P4P_CDIST><<<grid, KNN_WARPS * 32, 0, s>>>(pts, ids, bb, lut, meta, N, centres, G, total, k, idx_out, i64, dist_out);
+    knn_sorted_kernel<KPL, P3TOK_KNN_P4P_CDIST><<<grid, KNN_WARPS * 32, 0, s>>>(pts, ids, bb, lut, meta, S, nblk, centres, G, total, k, idx_out, i64, dist_out);
   P3_LAUNCH_CHECK("knn_sorted_kernel");
   return P3TOK_OK;
 }
@@ -608,7 +622,7 @@ extern "C" int p3tok_knn(const float* x, int64_t B, int64_t N, int64_t pt_stride
 }
 
 extern "C" int64_t p3tok_knn_workspace_bytes(int64_t B, int64_t N) {
-  if (B < 0 || N <= 0 || N > KNS_MAX_N) return 0;       // 0: the sorted variant does not apply, use p3tok_knn
+  if (B < 0 || N <= 0 || N > (int64_t)KNS_MAX_N * KNS_MAX_SEG) return 0;       // 0: the sorted variant does not apply, use p3tok_knn
   return kns_layout(B, N).total;
 }
 
@@ -645,15 +659,17 @@ int kns_workspace_views(const void* workspace, int64_t workspace_bytes, int64_t 
 extern "C" int p3tok_knn_prepare(const float* x, int64_t B, int64_t N, int64_t pt_stride, void* workspace, int64_t workspace_bytes,
                                  void* stream) {
   P3_REQUIRE(B >= 0 && N > 0 && pt_stride >= 3, P3TOK_ERR_INVALID, "knn_prepare: bad shape");
-  P3_REQUIRE(N <= KNS_MAX_N, P3TOK_ERR_UNSUPPORTED, "knn_prepare: N=%lld > %d (use p3tok_knn)", (long long)N, KNS_MAX_N);
+  P3_REQUIRE(N <= (int64_t)KNS_MAX_N * KNS_MAX_SEG, P3TOK_ERR_UNSUPPORTED, "knn_prepare: N=%lld > %d (use p3tok_knn)", (long long)N,
+             KNS_MAX_N * KNS_MAX_SEG);
   P3_REQUIRE(B < 65536, P3TOK_ERR_UNSUPPORTED, "knn_prepare: B too large");
   if (B == 0) return P3TOK_OK;
   P3_REQUIRE(x && workspace, P3TOK_ERR_INVALID, "knn_prepare: null pointer");
   P3_REQUIRE(workspace_bytes >= kns_layout(B, N).total, P3TOK_ERR_WORKSPACE, "knn_prepare: workspace %lld < %lld bytes",
              (long long)workspace_bytes, (long long)kns_layout(B, N).total);
   const KnsPtrs w = kns_ptrs(workspace, B, N);
+  const KnsLayout L = kns_layout(B, N);
   int P2 = 32;
-  while (P2 < N) P2 <<= 1;
+  while (P2 < L.seg) P2 <<= 1;
   const int threads = P2 > 1024 ? 1024 : P2;
   const size_t smem = (size_t)P2 * 8;
   static thread_local bool configured[32] = {false};
@@ -663,7 +679,8 @@ extern "C" int p3tok_knn_prepare(const float* x, int64_t B, int64_t N, int64_t p
     P3_CUDA(cudaFuncSetAttribute(knn_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KNS_MAX_N * 8));
     configured[dev] = true;
   }
-  knn_prep_kernel<<<(unsigned)B, threads, smem, as_stream(stream)>>>(x, (int)N, (int)pt_stride, P2, w.pts, w.ids, w.bb, w.lut, w.meta);
+  knn_prep_kernel<<<(unsigned)(B * L.S), threads, smem, as_stream(stream)>>>(x, (int)N, (int)L.S, (int)L.seg, (int)L.nblk_seg, (int)pt_stride,
+                                                                              P2, w.pts, w.ids, w.bb, w.lut, w.meta);
   P3_LAUNCH_CHECK("knn_prep_kernel");
   return P3TOK_OK;
 }
@@ -676,7 +693,8 @@ extern "C" int p3tok_knn_query(const void* workspace, int64_t workspace_bytes, i
   P3_REQUIRE(idx_dtype == P3TOK_I64 || idx_dtype == P3TOK_I32, P3TOK_ERR_INVALID, "knn_query: idx dtype must be i32/i64");
   P3_REQUIRE(k >= 1 && k <= N, P3TOK_ERR_INVALID, "knn_query: k=%lld out of range for N=%lld", (long long)k, (long long)N);
   P3_REQUIRE(k <= 128, P3TOK_ERR_UNSUPPORTED, "knn_query: k=%lld > 128", (long long)k);
-  P3_REQUIRE(N <= KNS_MAX_N, P3TOK_ERR_UNSUPPORTED, "knn_query: N=%lld > %d (use p3tok_knn)", (long long)N, KNS_MAX_N);
+  P3_REQUIRE(N <= (int64_t)KNS_MAX_N * KNS_MAX_SEG, P3TOK_ERR_UNSUPPORTED, "knn_query: N=%lld > %d (use p3tok_knn)", (long long)N,
+             KNS_MAX_N * KNS_MAX_SEG);
   if (B == 0 || G == 0) return P3TOK_OK;
   P3_REQUIRE(centres && idx_out && workspace, P3TOK_ERR_INVALID, "knn_query: null pointer");
   P3_REQUIRE(workspace_bytes >= kns_layout(B, N).total, P3TOK_ERR_WORKSPACE, "knn_query: workspace %lld < %lld bytes",
@@ -685,9 +703,11 @@ extern "C" int p3tok_knn_query(const void* workspace, int64_t workspace_bytes, i
   cudaStream_t s = as_stream(stream);
   const int i64 = idx_dtype == P3TOK_I64;
   const int64_t total = B * G;
-  if (k <= 32) return knn_sorted_launch<1>(w.pts, w.ids, w.bb, w.lut, w.meta, (int)N, centres, (int)G, total, (int)k, mode, idx_out, i64, dist_out, s);
-  if (k <= 64) return knn_sorted_launch<2>(w.pts, w.ids, w.bb, w.lut, w.meta, (int)N, centres, (int)G, total, (int)k, mode, idx_out, i64, dist_out, s);
-  return knn_sorted_launch<4>(w.pts, w.ids, w.bb, w.lut, w.meta, (int)N, centres, (int)G, total, (int)k, mode, idx_out, i64, dist_out, s);
+  const KnsLayout L = kns_layout(B, N);
+  const int S = (int)L.S, nb = (int)L.nblk_seg;
+  if (k <= 32) return knn_sorted_launch<1>(w.pts, w.ids, w.bb, w.lut, w.meta, S, nb, centres, (int)G, total, (int)k, mode, idx_out, i64, dist_out, s);
+  if (k <= 64) return knn_sorted_launch<2>(w.pts, w.ids, w.bb, w.lut, w.meta, S, nb, centres, (int)G, total, (int)k, mode, idx_out, i64, dist_out, s);
+  return knn_sorted_launch<4>(w.pts, w.ids, w.bb, w.lut, w.meta, S, nb, centres, (int)G, total, (int)k, mode, idx_out, i64, dist_out, s);
 }
 
 extern "C" int p3tok_knn_sorted(const float* x, int64_t B, int64_t N, int64_t pt_stride, const float* centres, int64_t G,

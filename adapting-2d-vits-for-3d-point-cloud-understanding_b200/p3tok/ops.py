@@ -110,7 +110,7 @@ _FPS_CULLED_MIN_N = int(os.environ.get("P3TOK_FPS_CULLED_MIN_N", "4096"))
 
 
 def _use_culled_fps(B: int, N: int, npoint: int) -> bool:
-    return (_FPS_CULLED and _KNN_SORTED and B > 0 and npoint >= 8 and N >= _FPS_CULLED_MIN_N
+    return (_FPS_CULLED and _KNN_SORTED and B > 0 and npoint >= 8 and _FPS_CULLED_MIN_N <= N <= 8192
             and int(_L().p3tok_knn_workspace_bytes(B, N)) > 0)
 
 
@@ -193,7 +193,8 @@ def knn(x: torch.Tensor, centres: torch.Tensor, k: int, mode: int, int32_out: bo
         raise RuntimeError(f"p3tok::knn: selected index k out of range (k={k} > N={N})")
     idx = torch.empty((B, G, k), dtype=torch.int32 if int32_out else torch.int64, device=x.device)
     dist = torch.empty((B, G, k) if return_dist else (0,), dtype=torch.float32, device=x.device)
-    # clouds of up to 8192 points: Z-order sorted blocks + bounding-box culling (same results bit for bit);
+    # Z-order sorted blocks + bounding-box culling (same results bit for bit; clouds beyond 8192 points as segments of
+    # 8192, up to 131072);
     # P3TOK_KNN_SORTED=0 forces the plain sweep
     ws_bytes = int(_L().p3tok_knn_workspace_bytes(B, N)) if _KNN_SORTED and B * G > 0 else 0
     with torch.cuda.device(x.device), _timed("knn"):
@@ -219,7 +220,7 @@ def _(x, centres, k, mode, int32_out, return_dist):
 @torch.library.custom_op("p3tok::knn_prepare", mutates_args=(), device_types="cuda")
 def knn_prepare(x: torch.Tensor) -> torch.Tensor:
     """The centre-independent half of the sorted kNN (Z-order sort + block boxes of every cloud) -> workspace bytes;
-    empty when the sorted variant does not apply (N > 8192 or P3TOK_KNN_SORTED=0).  Enqueued on the CURRENT stream:
+    empty when the sorted variant does not apply (N > 131072 or P3TOK_KNN_SORTED=0).  Enqueued on the CURRENT stream:
     modules run it on a side stream next to FPS."""
     _need_cuda("knn_prepare", x)
     x_in = x

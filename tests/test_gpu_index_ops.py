@@ -260,6 +260,8 @@ def _knn_both(x, ctr, k, mode, i32):
 @pytest.mark.parametrize("B,N,G,k,kind", [
     (3, 1000, 77, 32, "uniform"), (2, 8192, 300, 32, "clustered"), (2, 2048, 128, 64, "duplicates"),
     (4, 100, 100, 100, "uniform"), (2, 33, 5, 16, "clustered"), (1, 4096, 64, 128, "duplicates"),
+    # beyond 8192 points: the cloud is sorted as segments of <= 8192 points and a query walks them (csrc/knn.cu)
+    (2, 8193, 50, 32, "uniform"), (2, 20011, 130, 64, "duplicates"), (1, 65536, 96, 64, "clustered"), (1, 131072, 40, 17, "uniform"),
 ])
 def test_sorted_knn_is_bit_identical_to_the_sweep(mode, B, N, G, k, kind):
     """The culled variant must return exactly the sweep's (distance, index) lists: ragged N, k = N, duplicated points
@@ -278,7 +280,8 @@ def test_sorted_knn_is_bit_identical_to_the_sweep(mode, B, N, G, k, kind):
 
 def test_sorted_knn_workspace_contract():
     L = ops._L()
-    assert int(L.p3tok_knn_workspace_bytes(4, 8193)) == 0          # too many points: use the sweep
+    assert int(L.p3tok_knn_workspace_bytes(4, 8193)) > 0           # two segments
+    assert int(L.p3tok_knn_workspace_bytes(4, 131073)) == 0        # too many points: use the sweep
     x = to_dev(synth.make_cloud("uniform", 1, 64, 1, 3))
     idx = torch.empty((1, 4, 8), dtype=torch.int64, device=dev())
     ws = torch.empty(16, dtype=torch.uint8, device=dev())
@@ -301,11 +304,15 @@ def test_knn_prepare_query_split_and_stream_overlap(mode):
     ref = ops.knn(x, ctr, k, mode, mode == oracle.KNN_P4P_CDIST, False)[0]
     assert torch.equal(got, ref)
     assert np.array_equal(got.cpu().numpy().astype(np.int64), oracle.knn(x.cpu().numpy(), ctr.cpu().numpy(), k, mode))
-    big = to_dev(synth.make_cloud("uniform", 1, 9000, 92, 3))          # N > 8192: empty workspace, the sweep answers
+    big = to_dev(synth.make_cloud("uniform", 1, 9000, 92, 3))          # 8192 < N <= 131072: two sorted segments
     ws2 = ops.knn_prepare(big)
-    assert ws2.numel() == 0
+    assert ws2.numel() > 0
     c2 = big[:, :10].contiguous()
-    assert torch.equal(ops.knn_query(big, ws2, c2, 8, mode, False), ops.knn(big, c2, 8, mode, False, False)[0])
+    got2 = ops.knn_query(big, ws2, c2, 8, mode, False)
+    assert torch.equal(got2, ops.knn(big, c2, 8, mode, False, False)[0])
+    assert np.array_equal(got2.cpu().numpy().astype(np.int64), oracle.knn(big.cpu().numpy(), c2.cpu().numpy(), 8, mode))
+    huge = torch.zeros((1, 131073, 3), device=dev())                   # beyond the segmented limit: empty workspace, the sweep answers
+    assert ops.knn_prepare(huge).numel() == 0
 
 
 # ------------------------------------------------------------------ round-1 advisor findings
