@@ -29,6 +29,13 @@
 // Barriers the leader's MMA warp waits on live in the leader CTA (TMA loads of both CTAs signal them, epilogue warps
 // of the peer arrive remotely); barriers producers / epilogue warps wait on are local and are released by
 // multicast tcgen05.commit.
+// Measured and dropped (round 2): forming a0 INSIDE this kernel - the output-epilogue warps computing the 6 -> 128 first
+// layer from 32 bytes of gathered inputs per row straight into the swizzled a0 stage, like the APF first layer in
+// embed_fused.cu - so that rows_first_layer_narrow_kernel only has to emit the patch max.  Bit-identical tokens, but slower:
+// c5w 2.02 -> 2.24 ms, c3 10.65 -> 11.65 ms per step.  A tile of this kernel is only ~3650 cycles and already bound by shared-
+// memory bandwidth and by the hidden epilogue's issue slots; ~4300 more warp instructions per tile (30 % of the issue slots
+// of its 3650 cycles) cost more than the 148 us / 2^21 rows of the separate first-layer kernel they replace.  (The pair
+// kernel absorbs its first layer because ITS tile is 10-25 k cycles.)
 #include "tc_common.cuh"
 
 namespace p3tok {
