@@ -62,7 +62,9 @@ P3TOK_API int64_t p3tok_kernel_launches(void);
  * an (B,N,4) xyz+height tensor is read in place, no .contiguous() copy).
  * start_idx: (B) int64, first pick per cloud (the reference draws torch.randint, sampler.py:20).
  * out_idx: (B,G) int64.  dist = ((dx*dx)+(dy*dy))+(dz*dz) unfused; argmax keeps the lowest index.
- * N <= 131072.  G > N repeats index 0 once the cloud is exhausted, like the reference. */
+ * N <= 131072.  G > N repeats index 0 once the cloud is exhausted, like the reference.
+ * One CTA per cloud up to 8192 points, a thread-block cluster per cloud beyond; the cluster size (<= 12288 points per
+ * CTA) is chosen per launch so that all B clouds are resident at once (cudaOccupancyMaxActiveClusters). */
 P3TOK_API int p3tok_fps(const float* x, int64_t B, int64_t N, int64_t pt_stride, const int64_t* start_idx,
               int64_t G, int64_t* out_idx, void* stream);
 
@@ -90,10 +92,11 @@ P3TOK_API int p3tok_knn(const float* x, int64_t B, int64_t N, int64_t pt_stride,
               int64_t G, int64_t k, int mode, void* idx_out, int idx_dtype, float* dist_out,
               void* stream);
 
-/* Spatially sorted variant of p3tok_knn for clouds of at most 8192 points (same contract, same results bit for bit):
- * a preparation kernel sorts every cloud along a Z-order curve into `workspace`, then one warp per centre evaluates only
- * the 32-point blocks whose bounding box can still contain one of the k nearest neighbours.
- * p3tok_knn_workspace_bytes returns the scratch size in bytes, or 0 when the variant does not apply (N > 8192). */
+/* Spatially sorted variant of p3tok_knn for clouds of at most 131072 points (same contract, same results bit for bit):
+ * a preparation kernel sorts every cloud along a Z-order curve into `workspace` (clouds beyond 8192 points as segments of
+ * <= 8192 consecutive points, each sorted on its own), then one warp per centre evaluates only the 32-point blocks whose
+ * bounding box can still contain one of the k nearest neighbours.
+ * p3tok_knn_workspace_bytes returns the scratch size in bytes, or 0 when the variant does not apply (N > 131072). */
 P3TOK_API int64_t p3tok_knn_workspace_bytes(int64_t B, int64_t N);
 P3TOK_API int p3tok_knn_sorted(const float* x, int64_t B, int64_t N, int64_t pt_stride, const float* centres,
                      int64_t G, int64_t k, int mode, void* idx_out, int idx_dtype, float* dist_out,

@@ -56,7 +56,7 @@ def full(path):
                 print(f"  {w:70s} {r[i]:>14s} {units[i]}")
 
 
-EMBED_KERNELS = ("tc_", "rows_", "pad_weight", "partial_max", "group_max", "sgemm", "build_rows", "embed_")
+EMBED_KERNELS = ("tc_", "rows_", "pad_weight", "partial_max", "group_max", "sgemm", "build_rows", "embed_", "apf_rel_rows", "fused_l1_pack")
 
 
 def traffic(path, key, steps):
