@@ -21,6 +21,8 @@
 // Measured and rejected: direct per-candidate insertion (0.196 vs 0.12 ms at C2); two points per lane with packed
 // f32x2 distance arithmetic (FFMA2/FADD2: c3 6.1 -> 7.7 ms, c5 0.59 -> 0.97 ms - twice the votes per active step and a
 // vote is true twice as often; the queue merges, not the distance arithmetic, are what the kernel spends its time on).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace p3tok {
@@ -265,6 +267,9 @@ static int knn_launch(const float* x, int B, int N, int pt_stride, const float* 
 // each sorted on its own (its own Z-order frame, block boxes and cell table); a query walks the segments one after the
 // other, seeding from each.  A segment is a random 1/S sample of the cloud, so its blocks are ~S^(1/3) times wider than a
 // global sort's - at N = 65536 a centre still evaluates only ~2-3 % of the cloud instead of all of it (sweep kernel).
+#ifndef KNS_MIN_BLOCKS
+#define KNS_MIN_BLOCKS 5                       // k <= 32: 48 registers, 40 resident warps per SM (64 registers / 32 warps before)
+#endif
 constexpr int KNS_MAX_N = 8192;                // points per segment
 constexpr int KNS_MAX_SEG = 16;                // N <= 131072
 constexpr int KNS_CELLS = 512;                 // coarse Z-order cells (top 9 bits of the 30-bit code) for the start position
@@ -434,10 +439,10 @@ knn_prep_kernel(const float* __restrict__ x, int Ntot, int S, int seg, int nblk,
 }
 
 template <int KPL, int MODE>
-__global__ void __launch_bounds__(KNN_WARPS * 32)
+__global__ void __launch_bounds__(KNN_WARPS * 32, KPL == 1 ? KNS_MIN_BLOCKS : 4)
 knn_sorted_kernel(const float4* __restrict__ pts, const int* __restrict__ ids, const float* __restrict__ bb,
                   const int* __restrict__ lut, const float* __restrict__ meta_all, int S, int nblk, const float* __restrict__ centres,
-                  int G, int64_t total, int k, void* __restrict__ idx_out, int idx_is_i64, float* __restrict__ dist_out) {
+                  int G, int64_t total, int k, void* __restrict__ idx_out, int idx_is_i64, float* __restrict__ dist_out, int best_first) {
   __shared__ uint64_t queue[KNN_WARPS][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t cw = (int64_t)blockIdx.x * KNN_WARPS + warp;      // this warp's centre
@@ -523,6 +528,48 @@ knn_sorted_kernel(const float4* __restrict__ pts, const int* __restrict__ ids, c
   const float* BB = bb + bs * nblk * 8;
   // margin of the block test: the expansion formula's rounding error is a few ulp of (|c|^2 + |p|^2 + 2|c||p|) <= 2(|c|^2+|p|^2)
   const float margin = 1e-5f * (cn + meta[6]) + 1e-30f;
+  // ---- best-first walk over the segment's blocks: every lane keeps the lower bounds of 8 blocks (256 blocks per round,
+  // one round for a segment of 8192 points) as 32-bit keys (lower bound's float bits, low 8 bits replaced by the block's
+  // number in the round - rounding the bound DOWN, which is the safe side); one redux.sync.min picks the nearest unvisited
+  // block, and the walk stops as soon as that bound exceeds the running k-th distance.  Nearest-first means the threshold
+  // is tight after the first 2-3 blocks (the genuinely nearest ~96 points), so far fewer candidates pass the filter and
+  // reach the queue merges that bound this kernel than in curve order (round 1: seed from the curve position, then all
+  // blocks in index order - ~10 merges per centre at N = 8192, k = 32).
+  if (best_first && nblk >= 128) {     // (measured: neutral on uniform clouds, +6 % on clustered ones at N = 8192; below
+                                       //  4096 points the 8-keys-per-lane bookkeeping costs more than it saves)
+    for (int r0 = 0; r0 < nblk; r0 += 256) {
+      uint32_t key[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int blk = r0 + u * 32 + lane;
+        key[u] = 0xffffffffu;
+        if (blk < nblk) {
+          const float4 lo = *reinterpret_cast<const float4*>(BB + (size_t)blk * 8);       // min x,y,z, max x
+          const float4 hi = *reinterpret_cast<const float4*>(BB + (size_t)blk * 8 + 4);   // max y,z
+          const float dx = fmaxf(fmaxf(lo.x - cx, cx - lo.w), 0.f);
+          const float dy = fmaxf(fmaxf(lo.y - cy, cy - hi.x), 0.f);
+          const float dz = fmaxf(fmaxf(lo.z - cz, cz - hi.y), 0.f);
+          const float lb = fmaxf((dx * dx + dy * dy + dz * dz) * 0.999999f - margin, 0.f);
+          if (lb <= thr) key[u] = (__float_as_uint(lb) & 0xffffff00u) | (uint32_t)(u * 32 + lane);   // (padding blocks: lb = +inf)
+        }
+      }
+      while (true) {
+        uint32_t m = key[0];
+#pragma unroll
+        for (int u = 1; u < 8; ++u) m = min(m, key[u]);
+        const uint32_t w = __reduce_min_sync(0xffffffffu, m);
+        if (w == 0xffffffffu) break;
+        if (__uint_as_float(w & 0xffffff00u) > thr) break;       // every unvisited block of the round is farther still
+        const int id = (int)(w & 0xffu);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (u == (id >> 5) && lane == (id & 31)) key[u] = 0xffffffffu;
+        const int bk = r0 + id;
+        process(P4[bk * 32 + lane], ID[bk * 32 + lane]);
+      }
+    }
+    continue;
+  }
   // ---- seed: the blocks around the centre's own position on the segment's curve
   const int cell = (int)(kns_code(cx, cy, cz, meta) >> 21);
   const int pos = lut[bs * (KNS_CELLS + 1) + cell];
@@ -590,10 +637,12 @@ static int knn_sorted_launch(const float4* pts, const int* ids, const float* bb,
                              const float* centres, int G, int64_t total, int k, int mode, void* idx_out, int i64, float* dist_out,
                              cudaStream_t s) {
   const unsigned grid = (unsigned)((total + KNN_WARPS - 1) / KNN_WARPS);
+  static int bf = -1;          // P3TOK_KNN_BEST_FIRST=0: the round-1 traversal (seed from the curve position, then index order)
+  if (bf < 0) { const char* e = getenv("P3TOK_KNN_BEST_FIRST"); bf = e ? atoi(e) : 1; }
   if (mode == P3TOK_KNN_APF_SQ)
-    knn_sorted_kernel<KPL, P3TOK_KNN_APF_SQ><<<grid, KNN_WARPS * 32, 0, s>>>(pts, ids, bb, lut, meta, S, nblk, centres, G, total, k, idx_out, i64, dist_out);
+    knn_sorted_kernel<KPL, P3TOK_KNN_APF_SQ><<<grid, KNN_WARPS * 32, 0, s>>>(pts, ids, bb, lut, meta, S, nblk, centres, G, total, k, idx_out, i64, dist_out, bf);
   else
-    knn_sorted_kernel<KPL, P3TOK_KNN_P4P_CDIST><<<grid, KNN_WARPS * 32, 0, s>>>(pts, ids, bb, lut, meta, S, nblk, centres, G, total, k, idx_out, i64, dist_out);
+    knn_sorted_kernel<KPL, P3TOK_KNN_P4P_CDIST><<<grid, KNN_WARPS * 32, 0, s>>>(pts, ids, bb, lut, meta, S, nblk, centres, G, total, k, idx_out, i64, dist_out, bf);
   P3_LAUNCH_CHECK("knn_sorted_kernel");
   return P3TOK_OK;
 }
