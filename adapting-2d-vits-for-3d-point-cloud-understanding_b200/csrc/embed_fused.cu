@@ -45,7 +45,8 @@ constexpr int FU_MAX_RA = 32, FU_MAX_RB = 16;
 constexpr int FU_SMEM = 227 * 1024;
 constexpr int FU_L1_WSTRIDE = 76;            // floats per lane: 32 rel + 32 ctr weights + 8 biases, padded so LDS.128 is conflict-free
 constexpr int FU_L1_STAGE = 128 * 16 + 4 * 16;   // per tile and CTA: 128 rel rows + 4 block centres (float4 each)
-constexpr int FU_L1_BYTES = 32 * FU_L1_WSTRIDE * 4 + 2 * FU_L1_STAGE;
+constexpr int FU_L1_BYTES = 2 * FU_L1_STAGE;      // (the packed weights, 9.5 KB, are read through L1 once per tile: the shared
+                                                  //  memory they would take is a ring slot)
 
 struct FusedParams {
   int M, K0, N1, N2;
@@ -92,8 +93,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   float* sbb = sba + p.N1;                               // N2 floats
   float* sgb = sbb + p.N2;                               // chunk warps x 64 floats (group-bias slices)
   const bool L1 = p.l1_rel != nullptr;
-  float* sl1w = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sgb + FU_CH_WARPS * 64) + 15) & ~(uintptr_t)15);   // packed first-layer weights
-  uint8_t* sl1 = reinterpret_cast<uint8_t*>(sl1w + (L1 ? 32 * FU_L1_WSTRIDE : 0));                 // 2 x FU_L1_STAGE: rel rows + block centres
+  uint8_t* sl1 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sgb + FU_CH_WARPS * 64) + 15) & ~(uintptr_t)15);   // 2 x FU_L1_STAGE: rel rows + block centres
   uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sl1 + (L1 ? 2 * FU_L1_STAGE : 0)) + 7) & ~(uintptr_t)7);
   uint64_t* a0_full = bars;            // leader
   uint64_t* a0_empty = bars + 1;       // local, multicast commit
@@ -137,7 +137,6 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   for (int i = threadIdx.x; i < p.N1; i += FU_THREADS) sba[i] = p.bias_a ? p.bias_a[i] : 0.f;
   for (int i = threadIdx.x; i < p.N2; i += FU_THREADS) sbb[i] = p.bias_b ? p.bias_b[i] : 0.f;
-  if (L1) for (int i = threadIdx.x; i < 32 * FU_L1_WSTRIDE; i += FU_THREADS) sl1w[i] = p.l1_w[i];
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
@@ -441,17 +440,17 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // rows_first_layer_apf_warp_kernel (base = bias + W_ctr.ctr, then the rel chain), two channels per FFMA2.
     auto produce_a0 = [&](int t) {
       const int sb = t & 1;
-      const float* wl = sl1w + lane * FU_L1_WSTRIDE;
+      const float4* wl = reinterpret_cast<const float4*>(p.l1_w + lane * FU_L1_WSTRIDE);
       float wr[32], base[8];
       {
         float wc[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          *reinterpret_cast<float4*>(&wr[4 * i]) = *reinterpret_cast<const float4*>(wl + 4 * i);
-          *reinterpret_cast<float4*>(&wc[4 * i]) = *reinterpret_cast<const float4*>(wl + 32 + 4 * i);
+          *reinterpret_cast<float4*>(&wr[4 * i]) = __ldg(wl + i);
+          *reinterpret_cast<float4*>(&wc[4 * i]) = __ldg(wl + 8 + i);
         }
-        *reinterpret_cast<float4*>(&base[0]) = *reinterpret_cast<const float4*>(wl + 64);
-        *reinterpret_cast<float4*>(&base[4]) = *reinterpret_cast<const float4*>(wl + 68);
+        *reinterpret_cast<float4*>(&base[0]) = __ldg(wl + 16);
+        *reinterpret_cast<float4*>(&base[4]) = __ldg(wl + 17);
         mbar_wait(&l1_full[sb], (uint32_t)(t >> 1) & 1);
         const float4 cc = *reinterpret_cast<const float4*>(sl1 + sb * FU_L1_STAGE + 128 * 16 + (ew >> 1) * 16);
         const float cv[4] = {cc.x, cc.y, cc.z, cc.w};
@@ -625,8 +624,11 @@ static bool fused_rings_n(int K0, int N1, int N2, bool store_out, int nch, bool 
   const int fixed = (K0 / 64) * 16384 + nch * FU_CH_BYTES + (store_out ? FU_OUT_WARPS * 4096 : 0) +
                     (N1 + N2 + FU_CH_WARPS * 64) * 4 + (l1 ? FU_L1_BYTES + 16 : 0) + 116 * 8 + 64 + 1024;
   const int left = FU_SMEM - fixed;
-  const int chunk_a = (K0 / 64) * FU_RA_BOX, chunk_b = 2 * nq * rb_box;
   if (left < 2 * FU_RA_BOX + 2 * rb_box) return false;
+  // split in proportion to the bytes a chunk needs from each ring.  (Measured and dropped: "the smaller ring as large as
+  // possible" - the pre pair at E = 384 with 5 + 3 instead of 3 + 4 slots: c2 0.943 -> 0.975 ms, c4 5.31 -> 5.48 ms; the
+  // B-GEMM's paired W_b boxes need the depth more than the A-GEMM does.)
+  const int chunk_a = (K0 / 64) * FU_RA_BOX, chunk_b = 2 * nq * rb_box;
   ra_slots = (int)((int64_t)left * chunk_a / (chunk_a + chunk_b)) / FU_RA_BOX;
   if (ra_slots < 2) ra_slots = 2;
   if (ra_slots > FU_MAX_RA) ra_slots = FU_MAX_RA;
