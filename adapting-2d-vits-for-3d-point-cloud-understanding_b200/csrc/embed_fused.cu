@@ -136,13 +136,18 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < p.N1; i += FU_THREADS) sba[i] = p.bias_a ? p.bias_a[i] : 0.f;
-  for (int i = threadIdx.x; i < p.N2; i += FU_THREADS) sbb[i] = p.bias_b ? p.bias_b[i] : 0.f;
+  int bb_nonzero = 0;
+  for (int i = threadIdx.x; i < p.N2; i += FU_THREADS) {
+    const float b = p.bias_b ? p.bias_b[i] : 0.f;
+    sbb[i] = b;
+    bb_nonzero |= (b != 0.f);
+  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
   }
   tc_fence_before();
-  __syncthreads();
+  const bool has_bb = __syncthreads_or(bb_nonzero) != 0;   // an all-zero output bias (folded away on the host) is not added
   cluster_sync_all();                       // the peer's barriers exist before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
@@ -385,10 +390,12 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t sb = smem_u32(sba + c0 + 32 * half), sg = smem_u32(my_sgb + 32 * half);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            float4 b4;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(sb + 16 * i));
-            add2(v[4 * i], v[4 * i + 1], v[4 * i], v[4 * i + 1], b4.x, b4.y);
-            add2(v[4 * i + 2], v[4 * i + 3], v[4 * i + 2], v[4 * i + 3], b4.z, b4.w);
+            if (p.bias_a) {      // (null when the layer's bias travels inside the group bias: the "post" pair)
+              float4 b4;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(sb + 16 * i));
+              add2(v[4 * i], v[4 * i + 1], v[4 * i], v[4 * i + 1], b4.x, b4.y);
+              add2(v[4 * i + 2], v[4 * i + 3], v[4 * i + 2], v[4 * i + 3], b4.z, b4.w);
+            }
             if (gb_row) {
               float4 g4;
               asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g4.x), "=f"(g4.y), "=f"(g4.z), "=f"(g4.w) : "r"(sg + 16 * i));
@@ -552,10 +559,12 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               if (tr) fu_trace(p, it, 0, 14, clock64());
               released = true;
             }
+            if (has_bb) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b4 = *reinterpret_cast<const float4*>(sbb + n0 + half * 32 + 4 * i);
-              v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+              for (int i = 0; i < 8; ++i) {
+                const float4 b4 = *reinterpret_cast<const float4*>(sbb + n0 + half * 32 + 4 * i);
+                v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+              }
             }
             if (half == 0) {   // the previous box of this warp has left shared memory
               if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");

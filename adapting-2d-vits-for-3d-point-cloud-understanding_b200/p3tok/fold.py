@@ -126,6 +126,12 @@ def fold_apf_encoder(sd: Dict[str, torch.Tensor], eps: Optional[Dict[str, float]
     bo = _bias(sd, "second_conv.3", Wo.shape[0])
     E = W3.shape[0]
     assert Wm.shape == (2 * E, 2 * E) and Wo.shape == (E, 2 * E)
+    # first_conv.6 has no BN / activation behind it (apf.py:136), so its bias passes linearly through the max over k and the
+    # concat (apf.py:160-163) into second_conv.0:  Wm [g + b3 || f + b3] + bm = Wm [g || f] + (bm + (Wm_g + Wm_f) b3).  Folding
+    # it there (float64) leaves the layer that WRITES the rows x E feature tensor without a bias: its epilogue is the critical
+    # path between two row tiles of the pair kernel (csrc/embed_fused.cu), and a bias costs it 8 LDS + 32 FADD per 32 columns.
+    bm = bm + (Wm[:, :E] + Wm[:, E:]) @ b3
+    b3 = torch.zeros_like(b3)
     f = lambda t: t.float().contiguous()
     return PatchMLP(cin=W1.shape[1], pre_dims=[W1.shape[0], W2.shape[0], E], pre_relu=[1, 1, 0],
                     mid_dim=2 * E, out_dim=E, out_relu=0,
