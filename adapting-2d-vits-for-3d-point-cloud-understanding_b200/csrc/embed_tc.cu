@@ -45,6 +45,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace p3tok {
@@ -965,33 +967,43 @@ rows_first_layer_narrow_kernel(p3tok_rows R, int64_t g_begin, int64_t nrows, con
     float m[NPL];
 #pragma unroll
     for (int j = 0; j < NPL; ++j) m[j] = -3.0e38f;
+    // The kernel is ISSUE-bound (ncu: 71 % issue-active, DRAM 41 %; 54 warp instructions per row in round 1), so: two output
+    // channels per FFMA2, only the cin channels that exist (the zero-padded ones added +0), ReLU folded into the bf16
+    // conversion and applied to the patch max once per block (max relu = relu max).
+    auto row_loop = [&](auto cin_tag) {
+    constexpr int CIN = decltype(cin_tag)::value;
 #pragma unroll 4
     for (int row = 0; row < nr; ++row) {
       const float4 x0 = *reinterpret_cast<const float4*>(&xin[row][0]);   // warp-wide broadcasts
       const float4 x1 = *reinterpret_cast<const float4*>(&xin[row][4]);
+      const float xr[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
       float a[NPL];
 #pragma unroll
-      for (int j = 0; j < NPL; ++j) {
-        float t = fmaf(w[j][0], x0.x, b[j]);
-        t = fmaf(w[j][1], x0.y, t); t = fmaf(w[j][2], x0.z, t); t = fmaf(w[j][3], x0.w, t);
-        t = fmaf(w[j][4], x1.x, t); t = fmaf(w[j][5], x1.y, t); t = fmaf(w[j][6], x1.z, t); t = fmaf(w[j][7], x1.w, t);
-        if (relu) t = fmaxf(t, 0.f);
-        a[j] = t;
-        m[j] = fmaxf(m[j], t);
+      for (int j = 0; j < NPL; ++j) a[j] = b[j];
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) {
+#pragma unroll
+        for (int j = 0; j < NPL; j += 2) fma2(a[j], a[j + 1], w[j][c], w[j + 1][c], xr[c], xr[c], a[j], a[j + 1]);
       }
+#pragma unroll
+      for (int j = 0; j < NPL; ++j) m[j] = fmaxf(m[j], a[j]);
       uint32_t pk[NPL / 2];
 #pragma unroll
-      for (int j = 0; j < NPL / 2; ++j) pk[j] = pack_bf16x2(a[2 * j], a[2 * j + 1]);
+      for (int j = 0; j < NPL / 2; ++j) pk[j] = relu ? pack_bf16x2_relu(a[2 * j], a[2 * j + 1]) : pack_bf16x2(a[2 * j], a[2 * j + 1]);
       __nv_bfloat16* o = out + (r0 + row) * NOUT + lane * NPL;
       if (NPL == 2) *reinterpret_cast<uint32_t*>(o) = pk[0];
       else if (NPL == 4) *reinterpret_cast<uint2*>(o) = make_uint2(pk[0], pk[1 % (NPL / 2)]);
       else *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1 % (NPL / 2)], pk[2 % (NPL / 2)], pk[3 % (NPL / 2)]);
     }
+    };
+    if (cin == 6) row_loop(std::integral_constant<int, 6>{});
+    else if (cin <= 4) row_loop(std::integral_constant<int, 4>{});
+    else row_loop(std::integral_constant<int, 8>{});
     if (gmax32) {
       // bf16 rounding is monotonic: rounding the fp32 max equals the max of the rounded activations the next GEMM reads
       uint32_t pm[NPL / 2];
 #pragma unroll
-      for (int j = 0; j < NPL / 2; ++j) pm[j] = pack_bf16x2(m[2 * j], m[2 * j + 1]);
+      for (int j = 0; j < NPL / 2; ++j) pm[j] = relu ? pack_bf16x2_relu(m[2 * j], m[2 * j + 1]) : pack_bf16x2(m[2 * j], m[2 * j + 1]);
       __nv_bfloat16* o = gmax32 + blk * NOUT + lane * NPL;
       if (NPL == 2) *reinterpret_cast<uint32_t*>(o) = pm[0];
       else if (NPL == 4) *reinterpret_cast<uint2*>(o) = make_uint2(pm[0], pm[1 % (NPL / 2)]);
