@@ -30,6 +30,36 @@ def test_library_exports_every_declared_symbol(built):
     assert L.p3tok_abi_version() == 2             # host-only call, no GPU needed
 
 
+def test_host_only_size_queries(built):
+    """Size queries are host computations (no GPU): the sorted-kNN scratch follows the segment layout of csrc/knn.cu -
+    21 bytes per point plus per-segment tables, segments of at most 8192 points, nothing beyond 131072 points."""
+    L = ctypes.CDLL(built)
+    L.p3tok_knn_workspace_bytes.restype = ctypes.c_int64
+    L.p3tok_knn_workspace_bytes.argtypes = [ctypes.c_int64, ctypes.c_int64]
+    ws = L.p3tok_knn_workspace_bytes
+    assert ws(0, 1024) > 0 and ws(4, 0) == 0 and ws(-1, 8) == 0
+    one, two = ws(1, 8192), ws(1, 8193)
+    assert 8192 * 21 <= one <= 8192 * 21 + 4096             # pts 16 B + ids 4 B + boxes 1 B per point, cell table, meta
+    assert two > one and two - one < 2 * (32 * 21) + 4096    # a second segment: two more padded blocks and a second table
+    assert ws(16, 65536) >= 16 * 65536 * 21 and ws(1, 131072) > 0 and ws(1, 131073) == 0
+    assert ws(7, 20011) - ws(6, 20011) == ws(3, 20011) - ws(2, 20011)   # linear in the number of clouds
+
+
+def test_apf_fold_moves_the_feature_bias_into_the_concat_layer():
+    """fold_apf_encoder (p3tok/fold.py): first_conv.6's bias is folded through the max and the concat into second_conv.0 -
+    the folded feature layer carries a zero bias and the folded network still equals the oracle (checked above); here: the
+    moved term is exactly (Wm_g + Wm_f) b3."""
+    sd = synth.to_torch_state(synth.apf_encoder_state(64, 6, 3))
+    m = fold.fold_apf_encoder(sd)
+    assert float(m.b_pre[2].abs().max()) == 0.0
+    sd0 = {k: v.clone() for k, v in sd.items()}
+    sd0["first_conv.6.bias"] = torch.zeros_like(sd0["first_conv.6.bias"])
+    m0 = fold.fold_apf_encoder(sd0)
+    b3 = sd["first_conv.6.bias"].double()
+    moved = (m0.w_mid_g.double() + m0.w_mid_f.double()) @ b3
+    assert torch.allclose(m.b_mid.double() - m0.b_mid.double(), moved, rtol=1e-5, atol=1e-6)
+
+
 def test_struct_layouts_match_header(tmp_path, built):
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "p3tok.h"\nint main(){printf("%zu %zu %zu %zu\\n",'
