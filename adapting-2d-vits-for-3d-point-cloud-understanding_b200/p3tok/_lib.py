@@ -19,6 +19,7 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, 1, 2, 3, 4
 KNN_APF_SQ, KNN_P4P_CDIST = 0, 1
 F32, BF16, I32, I64, BF16X3 = 0, 1, 2, 3, 4
 ROWS_APF, ROWS_P4P, ROWS_DIRECT = 0, 1, 2
+EW_AXPBY, EW_MUL, EW_GELU, EW_GELU_BWD, EW_RELU, EW_RELU_BWD = 0, 1, 2, 3, 4, 5
 
 _i32, _i64, _vp, _int = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int
 
@@ -80,6 +81,12 @@ _SIGNATURES = {
     "p3tok_group_sum_f32": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "p3tok_scatter_rows_add_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     "p3tok_build_rows_f32": (_int, [ctypes.POINTER(RowsStruct), _vp, _vp]),
+    "p3tok_ln_fwd_f32": (_int, [_vp, _i64, _i64, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),
+    "p3tok_ln_bwd_f32": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _int, _vp, _vp]),
+    "p3tok_ln_param_grad_f32": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "p3tok_attn_fwd_f32": (_int, [_vp, _i64, _i64, _i64, _i64, _f32, _vp, _vp, _vp]),
+    "p3tok_attn_bwd_f32": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _vp, _vp]),
+    "p3tok_ew_f32": (_int, [_int, _vp, _vp, _f32, _f32, _i64, _i64, _vp, _vp]),
     "p3tok_apf_vit_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64, _i64]),
     "p3tok_apf_vit_forward": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, ctypes.POINTER(VitLayerStruct), _i64, _vp, _vp,
                                      _f32, _vp, _vp, _i64, _vp]),

@@ -5,10 +5,13 @@
 
 Same constructor arguments, attribute names and state_dict keys (`blocks.{i}.norm1`, `.attention.qkv`, `.mlp.fc1`,
 `.adapter.down_proj`, `encoder_norm`, `point_encoder.encoder.first_conv.0`, `head.mlp_head.0`, ...), so a reference
-checkpoint loads with strict=True.  The torch submodules are parameter containers; forward runs the sm_100a kernels
-(`p3tok::apf_vit`: LayerNorm -> tcgen05 GEMMs with GELU / residual epilogues -> attention, fp32 residual stream) and is
-eval-mode only (DropPath, dropout = identity; BatchNorm of the head folded).  Differences from the reference
-constructor: no timm / no network here, so `pretrained=True` raises - load a state_dict instead.
+checkpoint loads with strict=True.  The torch submodules are parameter containers.  Serving (eval mode, no gradient
+wanted): forward runs `p3tok::apf_vit` - LayerNorm -> tcgen05 GEMMs with GELU / residual epilogues -> attention, fp32
+residual stream, the head's BatchNorms folded.  Training (`.train()`, or a gradient is wanted through eval-mode blocks):
+the fp32 autograd path of p3tok/train_vit.py - dropout / DropPath as keep masks, BatchNorm batch statistics, gradients
+for the tokens and for every parameter that requires one (the reference keeps point_encoder / encoder_norm / head
+trainable, apf.py:335-346).  Differences from the reference constructor: no timm / no network here, so
+`pretrained=True` raises - load a state_dict instead.
 """
 from __future__ import annotations
 
@@ -67,7 +70,8 @@ class APFViTLayer(nn.Module):
         super().__init__()
         self.norm1 = nn.LayerNorm(dim)
         self.norm2 = nn.LayerNorm(dim)
-        self.drop_path = nn.Identity()                     # eval mode: DropPath is the identity
+        self.drop_path = nn.Identity()                     # parameter-free; the rate below drives the train-mode keep masks
+        self.drop_path_rate = float(drop_path)             # apf_utils.py:258 (timm DropPath, scale_by_keep)
         self.mlp = _Mlp(dim, dim * 4)
         self.attention = AttentionLayer(dim=dim, num_heads=num_heads)
         self.adapter = AdapterLayer(model_dimension=dim, dropout=dropout)
@@ -114,11 +118,21 @@ def _layer_params(layer: "APFViTLayer", cache: dict) -> List[torch.Tensor]:
     return hit[1]
 
 
+def _wants_autograd(layers, x: torch.Tensor, final_norm: Optional[nn.LayerNorm]) -> bool:
+    """The fp32 autograd path (train_vit) instead of the serving kernels: any layer in train mode, or a gradient is wanted
+    for the input (frozen eval-mode blocks still pass the tokenizer's gradient through, apf.py:335-346).  Eval-mode modules on
+    an input without gradient always take the serving path, whatever `requires_grad` their parameters carry."""
+    if any(l.training for l in layers) or (final_norm is not None and final_norm.training):
+        return True
+    return torch.is_grad_enabled() and x.requires_grad
+
+
 def run_blocks(layers, x: torch.Tensor, final_norm: Optional[nn.LayerNorm], cache: Optional[dict] = None):
     """(x after the last layer, pooled = max over tokens of final_norm(x) or None)."""
     layers = list(layers)
-    if any(l.training for l in layers):
-        raise RuntimeError("APFViTLayer: p3tok implements the eval-mode forward only; call .eval() first")
+    if _wants_autograd(layers, x, final_norm):
+        from . import train_vit
+        return train_vit.blocks_train(layers, x, final_norm)
     cache = {} if cache is None else cache
     params: List[torch.Tensor] = []
     for l in layers:
@@ -160,7 +174,8 @@ class ClassificationHead(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.training:
-            raise RuntimeError("ClassificationHead: eval-mode forward only; call .eval() first")
+            from . import train_vit
+            return train_vit.head_train(self, x, sync=bool(getattr(self, "sync_bn", False)))
         m = self.mlp_head
         x = x.float().contiguous()
         for lin, bn, relu in ((m[0], m[1], True), (m[4], m[5], True), (m[8], None, False)):
@@ -183,20 +198,32 @@ class AdaptPointFormer(nn.Module):
                                "load_state_dict() a reference checkpoint (keys are identical)")
         in_channels = in_channels * 2                      # apf.py:293: [rel || centre] concat
         depth = 12
+        dpr = [v.item() for v in torch.linspace(0, dropout_path_rate, depth)]      # apf.py:298: deeper layers drop more
         self.dropout = nn.Dropout(dropout_rate)
         self.encoder_norm = nn.LayerNorm(embedding_dim)
         self.point_encoder = PointNet(embedding_dim, npoint, nsample, in_channels, precision=precision)
         self.head = ClassificationHead(in_channels=embedding_dim, num_classes=num_classes)
-        self.blocks = nn.Sequential(*[APFViTLayer(dim=embedding_dim, num_heads=12, drop_path=0.0, dropout=dropout_rate)
-                                      for _ in range(depth)])
+        self.blocks = nn.Sequential(*[APFViTLayer(dim=embedding_dim, num_heads=12, drop_path=dpr[i], dropout=dropout_rate)
+                                      for i in range(depth)])
 
     def features(self, x: torch.Tensor, start_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
         """(B,D) pooled features: everything before the classification head (apf.py:358-366)."""
-        if self.training:
-            raise RuntimeError("AdaptPointFormer: eval-mode forward only; call .eval() first")
         tok = self.point_encoder(x, start_idx)
         cache = self.__dict__.setdefault("_vit_cache", {})
         return run_blocks(self.blocks, tok, self.encoder_norm, cache)[1]
 
+    def _freeze(self) -> None:
+        """apf.py:335-346 verbatim in effect: everything frozen except parameters whose name contains 'adaptmlp', 'head',
+        'enc_norm' or 'encoder' (point_encoder.*, encoder_norm.*, head.*; the adapters are named `adapter` and stay frozen)."""
+        for param in self.parameters():
+            param.requires_grad_(False)
+        for name, param in self.named_parameters():
+            if "adaptmlp" in name or "head" in name or "enc_norm" in name or "encoder" in name:
+                param.requires_grad = True
+
     def forward(self, x: torch.Tensor, start_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
-        return self.head(self.features(x, start_idx))
+        feats = self.features(x, start_idx)
+        if self.dropout.training and self.dropout.p > 0:                          # apf.py:368
+            from . import train_vit
+            feats = train_vit.dropout(feats, float(self.dropout.p), True)
+        return self.head(feats)

@@ -1,0 +1,381 @@
+"""Training mode of the APF token consumer: the APFViTLayer stack, encoder_norm, the max over tokens and the
+ClassificationHead as torch.autograd.Functions over the C ABI (csrc/train_vit.cu + csrc/train.cu).
+
+Why it exists: the reference freezes the pre-trained blocks but keeps point_encoder.*, encoder_norm.* and head.* trainable
+(reference src/models/apf.py:335-346), so the tokenizer's gradient arrives THROUGH the twelve layers
+(src/models/apf_utils.py:268-293).  `BlocksTrainFn` carries dL/dpooled back to the tokens and produces the gradient of every
+block / norm parameter that asks for one (`requires_grad`; the frozen ones cost nothing); `HeadTrainFn` is the head with
+nn.BatchNorm1d in TRAIN mode (apf.py:219-252).  Stochastic regularisers - the adapter's dropout (apf_utils.py:223), the two
+DropPath draws of a layer (apf_utils.py:277, 289), the dropout in front of and inside the head (apf.py:368, 237-242) - are keep
+masks drawn with torch's generator (scaled by 1 / keep probability) and applied by the element-wise kernel; a caller may pass
+the masks in (tests do, to compare against a reference evaluation under the same masks).
+
+fp32 on CUDA cores (GEMMs: p3tok_linear_f32 / p3tok_linear_tn_f32); CUDA tensors only, no fallback.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check
+from .train import _L, _f32, _s, _t, bn_backward, bn_forward, colstats, colsum, group_max_arg, group_max_bwd, linear, linear_tn
+
+# parameter order of one APFViTLayer (state_dict names relative to the layer)
+LAYER_PARAMS = ("norm1.weight", "norm1.bias", "attention.qkv.weight", "attention.qkv.bias", "attention.proj.weight",
+                "attention.proj.bias", "adapter.adapter_norm.weight", "adapter.adapter_norm.bias", "adapter.scale",
+                "adapter.down_proj.weight", "adapter.down_proj.bias", "adapter.up_proj.weight", "adapter.up_proj.bias",
+                "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias")
+NP = len(LAYER_PARAMS)
+
+
+# ------------------------------------------------------------------------------------------------ kernel wrappers
+def ln_fwd(x: torch.Tensor, w: Optional[torch.Tensor], b: Optional[torch.Tensor], eps: float, want_y: bool = True):
+    """x (M,D) -> (y or None, mean (M,), rstd (M,))  (p3tok_ln_fwd_f32)."""
+    x = _f32(x)
+    M, D = x.shape
+    y = torch.empty_like(x) if want_y else None
+    mean = torch.empty(M, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(M, dtype=torch.float32, device=x.device)
+    wf = _f32(w) if w is not None else None
+    bf = _f32(b) if b is not None else None
+    with torch.cuda.device(x.device):
+        check(_L().p3tok_ln_fwd_f32(x.data_ptr(), M, D, wf.data_ptr() if wf is not None else None,
+                                    bf.data_ptr() if bf is not None else None, float(eps), y.data_ptr() if y is not None else None,
+                                    mean.data_ptr(), rstd.data_ptr(), _s()), "ln_fwd_f32")
+    return y, mean, rstd
+
+
+def ln_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, w: Optional[torch.Tensor],
+           into: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx of LayerNorm; `into` (M,D) is accumulated into (and returned) when given."""
+    dy, x = _f32(dy), _f32(x)
+    M, D = x.shape
+    dx = into if into is not None else torch.empty_like(x)
+    wf = _f32(w) if w is not None else None
+    with torch.cuda.device(x.device):
+        check(_L().p3tok_ln_bwd_f32(dy.data_ptr(), x.data_ptr(), M, D, mean.data_ptr(), rstd.data_ptr(),
+                                    wf.data_ptr() if wf is not None else None, 1 if into is not None else 0, dx.data_ptr(), _s()),
+              "ln_bwd_f32")
+    return dx
+
+
+def ln_param_grad(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    dy, x = _f32(dy), _f32(x)
+    M, D = x.shape
+    g = torch.empty(2 * D, dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_L().p3tok_ln_param_grad_f32(dy.data_ptr(), x.data_ptr(), M, D, mean.data_ptr(), rstd.data_ptr(), g.data_ptr(),
+                                           g.data_ptr() + 8 * D, _s()), "ln_param_grad_f32")
+    return g[:D].float(), g[D:].float()
+
+
+def attn_fwd(qkv: torch.Tensor, B: int, G: int, heads: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """qkv (B*G, 3D) -> (o (B*G, D), P (B*heads, G, G)); scale = head_dim ** -0.5 (apf_utils.py:126)."""
+    qkv = _f32(qkv)
+    D = qkv.shape[1] // 3
+    hd = D // heads
+    o = torch.empty((B * G, D), dtype=torch.float32, device=qkv.device)
+    P = torch.empty((B * heads, G, G), dtype=torch.float32, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        check(_L().p3tok_attn_fwd_f32(qkv.data_ptr(), B, G, heads, hd, float(hd) ** -0.5, o.data_ptr(), P.data_ptr(), _s()), "attn_fwd_f32")
+    return o, P
+
+
+def attn_bwd(qkv: torch.Tensor, P: torch.Tensor, do: torch.Tensor, B: int, G: int, heads: int) -> torch.Tensor:
+    qkv, do = _f32(qkv), _f32(do)
+    D = qkv.shape[1] // 3
+    hd = D // heads
+    dqkv = torch.empty_like(qkv)
+    scratch = torch.empty((2, B * heads, G, G), dtype=torch.float32, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        check(_L().p3tok_attn_bwd_f32(qkv.data_ptr(), P.data_ptr(), do.data_ptr(), B, G, heads, hd, float(hd) ** -0.5,
+                                      scratch.data_ptr(), dqkv.data_ptr(), _s()), "attn_bwd_f32")
+    return dqkv
+
+
+def ew(op: int, a: torch.Tensor, b: Optional[torch.Tensor] = None, alpha: float = 1.0, beta: float = 1.0, bdiv: int = 1,
+       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """p3tok_ew_f32: out = f(a, b) element-wise (out may be a or b)."""
+    a = _f32(a)
+    bb = _f32(b) if b is not None else None
+    if out is None:
+        out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        check(_L().p3tok_ew_f32(int(op), a.data_ptr(), bb.data_ptr() if bb is not None else None, float(alpha), float(beta), a.numel(),
+                                int(bdiv), out.data_ptr(), _s()), "ew_f32")
+    return out
+
+
+def axpby(alpha: float, a: torch.Tensor, beta: float, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return ew(_lib.EW_AXPBY, a, b, alpha, beta, out=out)
+
+
+def mask_mul(a: torch.Tensor, mask: Optional[torch.Tensor], per: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a * mask[e // per] (mask already scaled by 1 / keep probability); identity when mask is None."""
+    if mask is None:
+        return a
+    return ew(_lib.EW_MUL, a, mask, 1.0, 0.0, per, out=out)
+
+
+def keep_mask(shape: Sequence[int], p: float, device, generator: Optional[torch.Generator] = None) -> Optional[torch.Tensor]:
+    """Bernoulli(1 - p) keep mask scaled by 1 / (1 - p) (nn.functional.dropout / timm DropPath); None when p == 0."""
+    if p <= 0.0:
+        return None
+    if p >= 1.0:
+        return torch.zeros(tuple(shape), dtype=torch.float32, device=device)
+    keep = torch.rand(tuple(shape), dtype=torch.float32, device=device, generator=generator) >= p
+    return keep.to(torch.float32) / (1.0 - p)
+
+
+# ------------------------------------------------------------------------------------------------ the block stack
+class BlocksTrainFn(torch.autograd.Function):
+    """tokens (B,G,D) -> APFViTLayer x depth -> [final LayerNorm -> max over tokens].
+
+    apply(tokens, heads, eps, masks, has_final, *params): params = depth x LAYER_PARAMS tensors (+ final norm weight, bias);
+    eps = (per layer (norm1, adapter_norm, norm2) ..., final); masks = per layer (drop_path_attn (B,), adapter dropout (M,R),
+    drop_path_mlp (B,)) entries or None.  Returns (x after the last layer (B,G,D), pooled (B,D)) - pooled is a zero-size
+    tensor without a final norm."""
+
+    @staticmethod
+    def forward(ctx, tokens, heads, eps, masks, has_final, *params):
+        B, G, D = tokens.shape
+        M = B * G
+        depth = (len(params) - (2 if has_final else 0)) // NP
+        x = _f32(tokens).reshape(M, D)
+        saved: List[torch.Tensor] = []
+        meta = []
+        for li in range(depth):
+            (n1w, n1b, Wq, bq, Wp, bp, naw, nab, sc, Wd, bd, Wu, bu, n2w, n2b, W1, b1, W2, b2) = params[li * NP:(li + 1) * NP]
+            e1, ea, e2 = eps[li]
+            dp1, dmask, dp2 = masks[li] if masks is not None else (None, None, None)
+            a, mu1, rs1 = ln_fwd(x, n1w, n1b, e1)                                   # apf_utils.py:275
+            qkv = linear(a, Wq, bq)
+            o, P = attn_fwd(qkv, B, G, heads)
+            att = mask_mul(linear(o, Wp, bp), dp1, G * D)                           # attention + drop_path (276-277)
+            x1 = axpby(1.0, x, 1.0, att, out=att)                                   # 278
+            an, mua, rsa = ln_fwd(x1, naw, nab, ea)                                 # adapter (apf_utils.py:214-233)
+            zd = linear(an, Wd, bd)
+            dn = mask_mul(ew(_lib.EW_RELU, zd), dmask)
+            up = linear(dn, Wu, bu)
+            n2, mu2, rs2 = ln_fwd(x1, n2w, n2b, e2)                                 # MLP (286-289)
+            z1 = linear(n2, W1, b1)
+            m = mask_mul(linear(ew(_lib.EW_GELU, z1), W2, b2), dp2, G * D)
+            scv = float(sc.detach().reshape(-1)[0].item()) if sc.numel() else 1.0
+            y = axpby(1.0, m, scv, up, out=m)                                       # x_mlp + (up * scale + x1) + x1  (291)
+            y = axpby(1.0, y, 2.0, x1, out=y)
+            saved += [x, mu1, rs1, qkv, P, o, x1, mua, rsa, zd, mu2, rs2, z1]
+            meta.append((scv, dp1, dmask, dp2))
+            x = y
+        if has_final:
+            fw, fb = params[-2], params[-1]
+            yn, muf, rsf = ln_fwd(x, fw, fb, eps[depth])                            # apf.py:364
+            pooled, arg = group_max_arg(yn, G)                                      # apf.py:366 (first maximum)
+            saved += [x, muf, rsf, arg]
+        else:
+            pooled = x.new_zeros((0,))
+        ctx.save_for_backward(*saved, *[p for p in params])
+        ctx.n_saved = len(saved)
+        ctx.dims = (B, G, D, depth, heads, has_final)
+        ctx.meta = meta
+        ctx.eps = eps
+        return x.reshape(B, G, D), pooled
+
+    @staticmethod
+    def backward(ctx, gx, gpooled):
+        B, G, D, depth, heads, has_final = ctx.dims
+        M = B * G
+        saved, params = ctx.saved_tensors[:ctx.n_saved], ctx.saved_tensors[ctx.n_saved:]
+        need = ctx.needs_input_grad[5:]
+        grads: List[Optional[torch.Tensor]] = [None] * len(params)
+        dx = _f32(gx).reshape(M, D).clone() if gx is not None else torch.zeros((M, D), dtype=torch.float32, device=params[0].device)
+        if has_final and gpooled is not None and gpooled.numel():
+            xl, muf, rsf, arg = saved[13 * depth:13 * depth + 4]
+            dyn = group_max_bwd(gpooled, arg, G)
+            if need[-2] or need[-1]:
+                gw, gb = ln_param_grad(dyn, xl, muf, rsf)
+                grads[-2], grads[-1] = (gw if need[-2] else None), (gb if need[-1] else None)
+            ln_bwd(dyn, xl, muf, rsf, params[-2], into=dx)
+        for li in reversed(range(depth)):
+            (n1w, n1b, Wq, bq, Wp, bp, naw, nab, sc, Wd, bd, Wu, bu, n2w, n2b, W1, b1, W2, b2) = params[li * NP:(li + 1) * NP]
+            nd = need[li * NP:(li + 1) * NP]
+            x, mu1, rs1, qkv, P, o, x1, mua, rsa, zd, mu2, rs2, z1 = saved[13 * li:13 * li + 13]
+            scv, dp1, dmask, dp2 = ctx.meta[li]
+            e1, ea, e2 = ctx.eps[li]
+            g = [None] * NP
+            dy = dx
+            # ---- MLP branch: y = drop_path(fc2(gelu(fc1(norm2(x1))))) + ...
+            dm = mask_mul(dy, dp2, G * D)
+            if nd[17] or nd[18]:
+                h = ew(_lib.EW_GELU, z1)
+                g[17], g[18] = (linear_tn(dm, h) if nd[17] else None), (colsum(dm) if nd[18] else None)
+                del h
+            dz1 = ew(_lib.EW_GELU_BWD, z1, linear(dm, _t(_f32(W2))))
+            if nd[15] or nd[16]:
+                n2 = ln_fwd(x1, n2w, n2b, e2)[0]
+                g[15], g[16] = (linear_tn(dz1, n2) if nd[15] else None), (colsum(dz1) if nd[16] else None)
+                del n2
+            dn2 = linear(dz1, _t(_f32(W1)))
+            del dz1
+            if nd[13] or nd[14]:
+                g[13], g[14] = ln_param_grad(dn2, x1, mu2, rs2)
+            dx1 = axpby(2.0, dy, 0.0, dy)                                           # adapter's "+ residual" and the layer's
+            ln_bwd(dn2, x1, mu2, rs2, n2w, into=dx1)
+            del dn2
+            # ---- adapter branch: (up_proj(dropout(relu(down_proj(adapter_norm(x1))))) * scale
+            if nd[8] or nd[11] or nd[12] or nd[9] or nd[10] or nd[6] or nd[7]:
+                an = ln_fwd(x1, naw, nab, ea)[0]
+                dn = mask_mul(ew(_lib.EW_RELU, zd), dmask)
+            if nd[8]:
+                up = linear(dn, Wu, bu)
+                g[8] = colstats(ew(_lib.EW_MUL, dy, up, 1.0, 0.0, 1))[0].sum().float().reshape(sc.shape)
+            if nd[11]:
+                g[11] = linear_tn(dy, dn) * scv
+            if nd[12]:
+                g[12] = colsum(dy) * scv
+            ddn = mask_mul(linear(dy, _t(_f32(Wu)) * scv), dmask)
+            dzd = ew(_lib.EW_RELU_BWD, zd, ddn, out=ddn)
+            if nd[9] or nd[10]:
+                g[9], g[10] = (linear_tn(dzd, an) if nd[9] else None), (colsum(dzd) if nd[10] else None)
+            dan = linear(dzd, _t(_f32(Wd)))
+            if nd[6] or nd[7]:
+                g[6], g[7] = ln_param_grad(dan, x1, mua, rsa)
+            ln_bwd(dan, x1, mua, rsa, naw, into=dx1)
+            # ---- attention branch: x1 = x + drop_path(proj(attention(qkv(norm1(x)))))
+            datt = mask_mul(dx1, dp1, G * D)
+            if nd[4] or nd[5]:
+                g[4], g[5] = (linear_tn(datt, o) if nd[4] else None), (colsum(datt) if nd[5] else None)
+            dqkv = attn_bwd(qkv, P, linear(datt, _t(_f32(Wp))), B, G, heads)
+            if nd[2] or nd[3]:
+                a = ln_fwd(x, n1w, n1b, e1)[0]
+                g[2], g[3] = (linear_tn(dqkv, a) if nd[2] else None), (colsum(dqkv) if nd[3] else None)
+                del a
+            da = linear(dqkv, _t(_f32(Wq)))
+            if nd[0] or nd[1]:
+                g[0], g[1] = ln_param_grad(da, x, mu1, rs1)
+            dx = ln_bwd(da, x, mu1, rs1, n1w, into=dx1)
+            for i in range(NP):
+                if g[i] is not None and nd[i]:
+                    grads[li * NP + i] = g[i].reshape(params[li * NP + i].shape)
+        gtok = dx.reshape(B, G, D) if ctx.needs_input_grad[0] else None
+        return (gtok, None, None, None, None, *grads)
+
+
+def layer_params(layer) -> List[torch.Tensor]:
+    sd = dict(layer.named_parameters())
+    return [sd[n] for n in LAYER_PARAMS]
+
+
+def draw_masks(layers, B: int, G: int, device, generator: Optional[torch.Generator] = None):
+    """One (drop_path_attn, adapter dropout, drop_path_mlp) triple per layer, in the order the reference draws them
+    (apf_utils.py:277 attention DropPath, 223 adapter dropout, 289 MLP DropPath); None when every rate is 0."""
+    out = []
+    any_mask = False
+    for l in layers:
+        dpr = float(getattr(l, "drop_path_rate", 0.0)) if l.training else 0.0
+        pdrop = float(l.adapter.dropout) if l.training else 0.0
+        t = (keep_mask((B,), dpr, device, generator), keep_mask((B * G, l.adapter.down_size), pdrop, device, generator),
+             keep_mask((B,), dpr, device, generator))
+        any_mask = any_mask or any(m is not None for m in t)
+        out.append(t)
+    return out if any_mask else None
+
+
+def blocks_train(layers, x: torch.Tensor, final_norm=None, masks=None, generator: Optional[torch.Generator] = None):
+    """Train-mode evaluation of a stack of APFViTLayers (+ encoder_norm and the max over tokens) under autograd:
+    -> (x after the last layer (B,G,D), pooled (B,D) or None)."""
+    layers = list(layers)
+    if not x.is_cuda:
+        raise RuntimeError("p3tok training path: CUDA tensors only (no CPU fallback)")
+    B, G, _ = x.shape
+    if masks is None:
+        masks = draw_masks(layers, B, G, x.device, generator)
+    params: List[torch.Tensor] = []
+    eps = []
+    for l in layers:
+        params += layer_params(l)
+        eps.append((float(l.norm1.eps), float(l.adapter.adapter_norm.eps), float(l.norm2.eps)))
+    if final_norm is not None:
+        params += [final_norm.weight, final_norm.bias]
+        eps.append(float(final_norm.eps))
+    y, pooled = BlocksTrainFn.apply(x, int(layers[0].attention.num_heads), tuple(eps), masks, final_norm is not None, *params)
+    return y, (pooled if final_norm is not None else None)
+
+
+# ------------------------------------------------------------------------------------------------ dropout on a tensor
+class MaskMulFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mask):
+        ctx.save_for_backward(mask)
+        return mask_mul(x, mask).reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        return mask_mul(g, mask).reshape(g.shape), None
+
+
+def dropout(x: torch.Tensor, p: float, training: bool, mask: Optional[torch.Tensor] = None,
+            generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """nn.Dropout on a CUDA tensor (apf.py:368) through the element-wise kernel."""
+    if mask is None:
+        mask = keep_mask(x.shape, p if training else 0.0, x.device, generator)
+    return x if mask is None else MaskMulFn.apply(x, mask)
+
+
+# ------------------------------------------------------------------------------------------------ classification head
+class HeadTrainFn(torch.autograd.Function):
+    """ClassificationHead in train mode (apf.py:230-252): Linear -> BN1d -> ReLU -> Dropout, twice, -> Linear.
+    apply(x (B,E), eps (2), sync, masks (2 or None), W1, b1, g1, be1, W2, b2, g2, be2, W3, b3) ->
+    (logits, batch mean / unbiased variance of both BatchNorms for the running-estimate update)."""
+
+    @staticmethod
+    def forward(ctx, x, eps, sync, masks, W1, b1, g1, be1, W2, b2, g2, be2, W3, b3):
+        x = _f32(x)
+        m1, m2 = masks if masks is not None else (None, None)
+        z1 = linear(x, W1, b1)
+        h1, s1 = bn_forward(z1, g1, be1, eps[0], True, sync)
+        h1 = mask_mul(h1, m1)
+        z2 = linear(h1, W2, b2)
+        h2, s2 = bn_forward(z2, g2, be2, eps[1], True, sync)
+        h2 = mask_mul(h2, m2)
+        out = linear(h2, W3, b3)
+        ctx.sync, ctx.stats, ctx.masks = sync, (s1, s2), (m1, m2)
+        ctx.save_for_backward(x, z1, h1, z2, h2, W1, W2, W3, g1, be1, g2, be2)
+        outs = [out, s1.mean64.float(), s1.var_unbiased.float(), s2.mean64.float(), s2.var_unbiased.float()]
+        ctx.mark_non_differentiable(*outs[1:])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g, *_unused):
+        x, z1, h1, z2, h2, W1, W2, W3, g1, be1, g2, be2 = ctx.saved_tensors
+        s1, s2 = ctx.stats
+        m1, m2 = ctx.masks
+        g = _f32(g)
+        dW3, db3 = linear_tn(g, h2), colsum(g)
+        dh2 = mask_mul(linear(g, _t(_f32(W3))), m2)
+        dz2, dg2, dbe2 = bn_backward(dh2, z2, s2, g2, be2, True, ctx.sync)
+        dW2, db2 = linear_tn(dz2, h1), colsum(dz2)
+        dh1 = mask_mul(linear(dz2, _t(_f32(W2))), m1)
+        dz1, dg1, dbe1 = bn_backward(dh1, z1, s1, g1, be1, True, ctx.sync)
+        dW1, db1 = linear_tn(dz1, x), colsum(dz1)
+        dx = linear(dz1, _t(_f32(W1))) if ctx.needs_input_grad[0] else None
+        return (dx, None, None, None, dW1, db1, dg1, dbe1, dW2, db2, dg2, dbe2, dW3, db3)
+
+
+def head_train(head, x: torch.Tensor, masks=None, sync: bool = False, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """Train-mode ClassificationHead.forward on x (B,E); updates the BatchNorm buffers like nn.BatchNorm1d does."""
+    from .train import update_running
+    m = head.mlp_head
+    if masks is None:
+        p1, p2 = float(m[3].p), float(m[7].p)
+        masks = (keep_mask((x.shape[0], m[0].out_features), p1, x.device, generator),
+                 keep_mask((x.shape[0], m[4].out_features), p2, x.device, generator))
+        if masks[0] is None and masks[1] is None:
+            masks = None
+    outs = HeadTrainFn.apply(x, (float(m[1].eps), float(m[5].eps)), bool(sync), masks, m[0].weight, m[0].bias, m[1].weight, m[1].bias,
+                             m[4].weight, m[4].bias, m[5].weight, m[5].bias, m[8].weight, m[8].bias)
+    update_running(m[1], outs[1], outs[2])
+    update_running(m[5], outs[3], outs[4])
+    return outs[0]

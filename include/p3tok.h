@@ -321,6 +321,35 @@ P3TOK_API int p3tok_scatter_rows_add_f32(const float* dRows, const int32_t* idx,
  * input (the inference path never materialises it). */
 P3TOK_API int p3tok_build_rows_f32(const p3tok_rows* rows, float* X, void* stream);
 
+/* ---- training through the ViT block stack (SURVEY 8f "next" #4 on top of #3) -------------------------------------------
+ * The reference keeps the blocks frozen but trains point_encoder / encoder_norm / head (src/models/apf.py:335-346), so a
+ * training step differentiates APFViTLayer x depth (src/models/apf_utils.py:268-293) -> encoder_norm -> max over tokens ->
+ * ClassificationHead (apf.py:219-252, 358-371) with respect to the tokens.  GEMMs: p3tok_linear_f32 / p3tok_linear_tn_f32;
+ * below are the pieces that are not GEMMs.  fp32 on CUDA cores; host side p3tok/train_vit.py. */
+/* nn.LayerNorm over the last axis of X (M,D): Y = xhat * gamma + beta (gamma / beta may be NULL = no affine; Y may be NULL
+ * when only the row statistics are wanted), mean[m], rstd[m] = 1/sqrt(biased variance + eps) kept for the backward. */
+P3TOK_API int p3tok_ln_fwd_f32(const float* X, int64_t M, int64_t D, const float* gamma, const float* beta, float eps, float* Y,
+                     float* mean, float* rstd, void* stream);
+/* dX (+)= rstd (g dY - mean_c(g dY) - xhat mean_c(g dY xhat)), g = gamma (NULL = 1); accumulate = 0 overwrites. */
+P3TOK_API int p3tok_ln_bwd_f32(const float* dY, const float* X, int64_t M, int64_t D, const float* mean, const float* rstd,
+                     const float* gamma, int accumulate, float* dX, void* stream);
+/* dgamma[c] = sum_m dY xhat, dbeta[c] = sum_m dY (fp64, overwritten). */
+P3TOK_API int p3tok_ln_param_grad_f32(const float* dY, const float* X, int64_t M, int64_t D, const float* mean, const float* rstd,
+                            double* dgamma, double* dbeta, void* stream);
+/* AttentionLayer.forward between qkv and proj (apf_utils.py:141-153): qkv (B*G, 3*heads*hd) = [q | k | v] ->
+ * O (B*G, heads*hd) = softmax(q k^T scale) v per (cloud, head); P (B*heads, G, G) = the probabilities, kept for the backward. */
+P3TOK_API int p3tok_attn_fwd_f32(const float* qkv, int64_t B, int64_t G, int64_t heads, int64_t hd, float scale, float* O, float* P,
+                       void* stream);
+/* its backward: dO (B*G, heads*hd) -> dqkv (B*G, 3*heads*hd); scratch: 2 * B*heads*G*G floats. */
+P3TOK_API int p3tok_attn_bwd_f32(const float* qkv, const float* P, const float* dO, int64_t B, int64_t G, int64_t heads, int64_t hd,
+                       float scale, float* scratch, float* dqkv, void* stream);
+/* out[e] = f(A[e], B[e]) over `total` elements (out may alias A or B):
+ *   op 0  alpha A + beta B                   op 1  alpha A B[e / bdiv]  (dropout mask, bdiv = 1; DropPath per cloud, bdiv = G*D)
+ *   op 2  gelu(A) (exact erf)                op 3  B gelu'(A)
+ *   op 4  relu(A)                            op 5  B [A > 0] */
+P3TOK_API int p3tok_ew_f32(int op, const float* A, const float* B, float alpha, float beta, int64_t total, int64_t bdiv, float* out,
+                 void* stream);
+
 /* out[g, c] = max over r < k of in[(g*k + r), c]   (torch.max(..., dim=k-axis)) */
 P3TOK_API int p3tok_group_max(const float* in, int64_t ngroups, int64_t k, int64_t C, float* out, void* stream);
 

@@ -4,8 +4,8 @@ Groundwork for the next row: float64 numpy forward with batch-statistics BatchNo
 train mode: nn.BatchNorm1d, eps 1e-5, momentum 0.1, biased variance for the normalisation, unbiased for the running
 estimate) and the backward of the whole mini-PointNet through both max-pools and the concat (apf.py:145-169), i.e. what
 autograd computes for `Encoder.forward`.  Pinned against the reference module's own autograd by tests/golden/make_golden.py
-(tests/golden/apf_train.npz) and re-checked against those fixtures by tests/test_oracle_vs_golden.py.  No kernel consumes
-this yet (next #4 "oracle pinned, kernels not started").
+(tests/golden/apf_train.npz) and re-checked against those fixtures by tests/test_oracle_vs_golden.py.  The kernels held to
+it: csrc/train.cu + p3tok/train.py (tokenizer), csrc/train_vit.cu + p3tok/train_vit.py (block stack, encoder_norm, head).
 """
 from __future__ import annotations
 
@@ -206,11 +206,17 @@ def _ln_bwd(dy, w, cache):
     return dx, (dy * xhat).reshape(-1, xhat.shape[-1]).sum(0), dy.reshape(-1, xhat.shape[-1]).sum(0)
 
 
-def apf_vit_layer_fwd_bwd(sd: Dict[str, np.ndarray], p: str, x: np.ndarray, heads: int):
-    """Forward of one APFViTLayer (apf_utils.py:268-293, dropout 0) returning the output and a closure dY -> dX."""
+def apf_vit_layer_fwd_bwd(sd: Dict[str, np.ndarray], p: str, x: np.ndarray, heads: int, masks=None, grads: Dict[str, np.ndarray] = None):
+    """Forward of one APFViTLayer (apf_utils.py:268-293) returning the output and a closure dY -> dX.
+    masks = (drop_path_attn (B,), adapter dropout (B*G, R), drop_path_mlp (B,)) keep masks already scaled by 1 / keep
+    probability (None entries = no dropout: the reference's eval mode or rate 0).  When `grads` is a dict the closure also
+    fills it with the gradient of every parameter of the layer (state_dict names)."""
     f = lambda k: np.asarray(sd[p + k], np.float64)
     B, G, D = x.shape
     hd = D // heads
+    dp1, dmask, dp2 = masks if masks is not None else (None, None, None)
+    bc = lambda m: 1.0 if m is None else np.asarray(m, np.float64).reshape(B, 1, 1)
+    dm3 = 1.0 if dmask is None else np.asarray(dmask, np.float64).reshape(B, G, -1)
     a, c_n1 = _ln_fwd(x, f("norm1.weight"), f("norm1.bias"))
     Wq, bq, Wp, bp = f("attention.qkv.weight"), f("attention.qkv.bias"), f("attention.proj.weight"), f("attention.proj.bias")
     qkv = (a @ Wq.T + bq).reshape(B, G, 3, heads, hd).transpose(2, 0, 3, 1, 4)
@@ -219,45 +225,68 @@ def apf_vit_layer_fwd_bwd(sd: Dict[str, np.ndarray], p: str, x: np.ndarray, head
     e = np.exp(s - s.max(-1, keepdims=True))
     P = e / e.sum(-1, keepdims=True)
     o = (P @ v).transpose(0, 2, 1, 3).reshape(B, G, D)
-    x1 = x + (o @ Wp.T + bp)
+    x1 = x + (o @ Wp.T + bp) * bc(dp1)
     an, c_an = _ln_fwd(x1, f("adapter.adapter_norm.weight"), f("adapter.adapter_norm.bias"))
     Wd, bd, Wu, bu = f("adapter.down_proj.weight"), f("adapter.down_proj.bias"), f("adapter.up_proj.weight"), f("adapter.up_proj.bias")
     sc = float(np.asarray(sd[p + "adapter.scale"]).reshape(-1)[0])
     zd = an @ Wd.T + bd
-    dn = np.maximum(zd, 0)
+    dn = np.maximum(zd, 0) * dm3
+    up = dn @ Wu.T + bu
     n2, c_n2 = _ln_fwd(x1, f("norm2.weight"), f("norm2.bias"))
     W1, b1, W2, b2 = f("mlp.fc1.weight"), f("mlp.fc1.bias"), f("mlp.fc2.weight"), f("mlp.fc2.bias")
     z1 = n2 @ W1.T + b1
     cdf = 0.5 * (1.0 + _erf(z1 / np.sqrt(2.0)))
     h = z1 * cdf
-    y = (h @ W2.T + b2) + ((dn @ Wu.T + bu) * sc + x1) + x1
+    y = (h @ W2.T + b2) * bc(dp2) + (up * sc + x1) + x1
 
     def backward(dy):
+        r2 = lambda t: t.reshape(-1, t.shape[-1])
+        put = (lambda name, val: grads.__setitem__(p + name, val)) if grads is not None else (lambda name, val: None)
         dx1 = 2.0 * dy                                                    # adapter's "+ x" and the layer's
-        dh = dy @ W2
+        dmm = dy * bc(dp2)
+        put("mlp.fc2.weight", r2(dmm).T @ r2(h)); put("mlp.fc2.bias", r2(dmm).sum(0))
+        dh = dmm @ W2
         dz1 = dh * (cdf + z1 * np.exp(-0.5 * z1 * z1) / np.sqrt(2.0 * np.pi))
-        dx1 = dx1 + _ln_bwd(dz1 @ W1, f("norm2.weight"), c_n2)[0]
-        dzd = ((dy * sc) @ Wu) * (zd > 0)
-        dx1 = dx1 + _ln_bwd(dzd @ Wd, f("adapter.adapter_norm.weight"), c_an)[0]
-        do = (dx1 @ Wp).reshape(B, G, heads, hd).transpose(0, 2, 1, 3)    # (B,h,G,hd)
+        put("mlp.fc1.weight", r2(dz1).T @ r2(n2)); put("mlp.fc1.bias", r2(dz1).sum(0))
+        d, gw, gb = _ln_bwd(dz1 @ W1, f("norm2.weight"), c_n2)
+        put("norm2.weight", gw); put("norm2.bias", gb)
+        dx1 = dx1 + d
+        put("adapter.scale", np.array([(dy * up).sum()]))
+        put("adapter.up_proj.weight", sc * (r2(dy).T @ r2(dn))); put("adapter.up_proj.bias", sc * r2(dy).sum(0))
+        dzd = ((dy * sc) @ Wu) * dm3 * (zd > 0)
+        put("adapter.down_proj.weight", r2(dzd).T @ r2(an)); put("adapter.down_proj.bias", r2(dzd).sum(0))
+        d, gw, gb = _ln_bwd(dzd @ Wd, f("adapter.adapter_norm.weight"), c_an)
+        put("adapter.adapter_norm.weight", gw); put("adapter.adapter_norm.bias", gb)
+        dx1 = dx1 + d
+        datt = dx1 * bc(dp1)
+        put("attention.proj.weight", r2(datt).T @ r2(o)); put("attention.proj.bias", r2(datt).sum(0))
+        do = (datt @ Wp).reshape(B, G, heads, hd).transpose(0, 2, 1, 3)   # (B,h,G,hd)
         dP = do @ v.transpose(0, 1, 3, 2)
         dv = P.transpose(0, 1, 3, 2) @ do
         ds = P * (dP - (dP * P).sum(-1, keepdims=True)) * hd ** -0.5
         dq = ds @ k
         dk = ds.transpose(0, 1, 3, 2) @ q
         dqkv = np.stack([dq, dk, dv], 0).transpose(1, 3, 0, 2, 4).reshape(B, G, 3 * D)
-        return dx1 + _ln_bwd(dqkv @ Wq, f("norm1.weight"), c_n1)[0]
+        put("attention.qkv.weight", r2(dqkv).T @ r2(a)); put("attention.qkv.bias", r2(dqkv).sum(0))
+        d, gw, gb = _ln_bwd(dqkv @ Wq, f("norm1.weight"), c_n1)
+        put("norm1.weight", gw); put("norm1.bias", gb)
+        return dx1 + d
 
     return y, backward
 
 
-def apf_vit_backward(sd: Dict[str, np.ndarray], tokens: np.ndarray, depth: int, heads: int, grad_pooled: np.ndarray):
-    """Blocks (frozen) -> encoder_norm (trainable) -> max over tokens (apf.py:361-366): returns (pooled (B,D), d tokens (B,G,D),
-    {"encoder_norm.weight": ..., "encoder_norm.bias": ...}) for dL/dpooled = grad_pooled."""
+def apf_vit_backward(sd: Dict[str, np.ndarray], tokens: np.ndarray, depth: int, heads: int, grad_pooled: np.ndarray, masks=None,
+                     param_grads: bool = False):
+    """Blocks -> encoder_norm -> max over tokens (apf.py:361-366): returns (pooled (B,D), d tokens (B,G,D), gradients) for
+    dL/dpooled = grad_pooled.  gradients: encoder_norm.* (trainable in the reference) and, with param_grads, every block
+    parameter too (frozen in the reference, apf.py:335-346 - for users who unfreeze them).  masks: per layer, see
+    apf_vit_layer_fwd_bwd."""
     x = tokens.astype(np.float64)
     backs = []
+    grads: Dict[str, np.ndarray] = {}
     for i in range(depth):
-        x, bw = apf_vit_layer_fwd_bwd(sd, f"blocks.{i}.", x, heads)
+        x, bw = apf_vit_layer_fwd_bwd(sd, f"blocks.{i}.", x, heads, masks[i] if masks is not None else None,
+                                      grads if param_grads else None)
         backs.append(bw)
     w, b = np.asarray(sd["encoder_norm.weight"], np.float64), np.asarray(sd["encoder_norm.bias"], np.float64)
     yn, c = _ln_fwd(x, w, b)
@@ -268,4 +297,34 @@ def apf_vit_backward(sd: Dict[str, np.ndarray], tokens: np.ndarray, depth: int, 
     dx, dw, db = _ln_bwd(dyn, w, c)
     for bw in reversed(backs):
         dx = bw(dx)
-    return pooled, dx, {"encoder_norm.weight": dw, "encoder_norm.bias": db}
+    grads["encoder_norm.weight"], grads["encoder_norm.bias"] = dw, db
+    return pooled, dx, grads
+
+
+def head_train(sd: Dict[str, np.ndarray], x: np.ndarray, grad_logits: np.ndarray, masks=None, prefix: str = "head.mlp_head."):
+    """ClassificationHead in TRAIN mode (apf.py:230-252: Linear, BatchNorm1d with batch statistics, ReLU, Dropout, twice, then
+    Linear) and its backward: returns (logits, {"input": dx, parameter gradients by state_dict name}, {running_mean / running_var
+    after one momentum update}).  masks = (keep mask (B,512), keep mask (B,256)) scaled by 1 / keep, None = dropout off."""
+    f = lambda k: np.asarray(sd[prefix + k], np.float64)
+    x = x.astype(np.float64)
+    m1, m2 = (1.0 if m is None else np.asarray(m, np.float64) for m in (masks if masks is not None else (None, None)))
+    z1 = x @ f("0.weight").T + f("0.bias")
+    y1, c1 = _bn_fwd(z1, f("1.weight"), f("1.bias"))
+    h1 = np.maximum(y1, 0) * m1
+    z2 = h1 @ f("4.weight").T + f("4.bias")
+    y2, c2 = _bn_fwd(z2, f("5.weight"), f("5.bias"))
+    h2 = np.maximum(y2, 0) * m2
+    out = h2 @ f("8.weight").T + f("8.bias")
+    g = grad_logits.astype(np.float64)
+    grads = {prefix + "8.weight": g.T @ h2, prefix + "8.bias": g.sum(0)}
+    dz2, grads[prefix + "5.weight"], grads[prefix + "5.bias"] = _bn_bwd((g @ f("8.weight")) * m2 * (y2 > 0), f("5.weight"), c2)
+    grads[prefix + "4.weight"], grads[prefix + "4.bias"] = dz2.T @ h1, dz2.sum(0)
+    dz1, grads[prefix + "1.weight"], grads[prefix + "1.bias"] = _bn_bwd((dz2 @ f("4.weight")) * m1 * (y1 > 0), f("1.weight"), c1)
+    grads[prefix + "0.weight"], grads[prefix + "0.bias"] = dz1.T @ x, dz1.sum(0)
+    grads["input"] = dz1 @ f("0.weight")
+    n = x.shape[0]
+    running = {}
+    for name, (xhat, var, mu) in (("1", c1), ("5", c2)):
+        running[prefix + name + ".running_mean"] = (1 - BN_MOMENTUM) * f(name + ".running_mean") + BN_MOMENTUM * mu
+        running[prefix + name + ".running_var"] = (1 - BN_MOMENTUM) * f(name + ".running_var") + BN_MOMENTUM * var * n / max(n - 1, 1)
+    return out, grads, running

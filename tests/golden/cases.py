@@ -57,6 +57,14 @@ VIT_TRAIN_CASES = {
     "vit_train": dict(B=2, G=20, D=64, heads=2, depth=2, seed=97),
 }
 
+VIT_FULL_TRAIN_CASES = {
+    # the whole token consumer in TRAIN mode under autograd - blocks (every parameter asks for a gradient), encoder_norm, max
+    # over tokens, dropout, ClassificationHead with batch-statistics BatchNorm1d: dict(B, G, D, heads, depth, classes, seed,
+    # p_adapter, p_pool, p_head) - the dropout rates become forced keep masks (0 = dropout off)
+    "vit_train_full": dict(B=4, G=12, D=64, heads=2, depth=2, classes=15, seed=131, p_adapter=0.0, p_pool=0.0, p_head=0.0),
+    "vit_train_masked": dict(B=6, G=9, D=64, heads=4, depth=2, classes=7, seed=137, p_adapter=0.25, p_pool=0.1, p_head=0.4),
+}
+
 TRAIN_CASES = {
     # training-mode APF Encoder (batch-statistics BN) + autograd through both max-pools: dict(B, N, C, G, k, E, seed)
     "apf_train": dict(B=2, N=128, C=3, G=6, k=8, E=32, seed=95),

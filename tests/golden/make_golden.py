@@ -389,6 +389,107 @@ def vit_train_case(ref, name, c):
                         grad_norm_w=norm.weight.grad.numpy(), grad_norm_b=norm.bias.grad.numpy())
 
 
+def vit_full_train_inputs(c):
+    """(state, tokens (B,G,D), grad_logits (B,classes), masks) of a VIT_FULL_TRAIN_CASES entry (shared with the tests).
+    masks = dict(adapter=[(B*G, 64) per layer], pool=(B,D), head=((B,512), (B,256))) keep masks scaled by 1 / keep, or None."""
+    sd = synth.apf_vit_state(c["D"], c["depth"], c["classes"], c["seed"])
+    tok = synth.vit_tokens(c["B"], c["G"], c["D"], c["seed"])
+    gl = (synth.uniform01(c["seed"], c["B"] * c["classes"], 37).reshape(c["B"], c["classes"]) - 0.5).astype(np.float32)
+
+    def keep(shape, p, stream):
+        if p <= 0:
+            return None
+        u = synth.uniform01(c["seed"], int(np.prod(shape)), stream).reshape(shape)
+        return ((u >= p).astype(np.float32) / np.float32(1.0 - p)).astype(np.float32)
+
+    masks = dict(adapter=[keep((c["B"] * c["G"], 64), c["p_adapter"], 41 + i) for i in range(c["depth"])],
+                 pool=keep((c["B"], c["D"]), c["p_pool"], 61), head=(keep((c["B"], 512), c["p_head"], 62), keep((c["B"], 256), c["p_head"], 63)))
+    return sd, tok, gl, masks
+
+
+@contextlib.contextmanager
+def forced_dropout(masks):
+    """torch.nn.functional.dropout (what nn.Dropout and the reference's adapter call, apf_utils.py:223) multiplies by the next
+    forced keep mask instead of drawing one; a None entry means "dropout off" for that call."""
+    import torch.nn.functional as F
+    real = F.dropout
+    it = iter(masks)
+
+    def fake(input, p=0.5, training=True, inplace=False):
+        m = next(it)
+        if m is None:
+            return input
+        return input * torch.from_numpy(np.asarray(m)).reshape(input.shape)
+
+    F.dropout = fake
+    try:
+        yield
+    finally:
+        F.dropout = real
+
+
+def vit_full_train_case(ref, name, c):
+    """The reference's APFViTLayer stack + nn.LayerNorm + max over tokens + nn.Dropout + ClassificationHead (apf.py:219-252,
+    358-371) in TRAIN mode under autograd, every parameter asking for a gradient; dropout draws replaced by forced keep masks
+    (DropPath is a timm class, absent here - its masks are exercised against the oracle only)."""
+    import torch.nn as nn
+    from oracle import train
+    sd, tok, gl, masks = vit_full_train_inputs(c)
+    tsd = synth.to_torch_state(sd)
+    blocks = nn.Sequential(*[ref.apf_utils.APFViTLayer(dim=c["D"], num_heads=c["heads"], drop_path=0.0, dropout=max(c["p_adapter"], 0.0))
+                             for _ in range(c["depth"])]).train()
+    blocks.load_state_dict({k[len("blocks."):]: v for k, v in tsd.items() if k.startswith("blocks.")})
+    norm = nn.LayerNorm(c["D"]).train()
+    norm.load_state_dict({"weight": tsd["encoder_norm.weight"], "bias": tsd["encoder_norm.bias"]})
+    drop = nn.Dropout(0.1).train()
+    head = ref.apf.ClassificationHead(c["D"], c["classes"]).train()
+    head.load_state_dict({k[len("head."):]: v for k, v in tsd.items() if k.startswith("head.")})
+    x = torch.from_numpy(tok).requires_grad_(True)
+    order = list(masks["adapter"]) + [masks["pool"], masks["head"][0], masks["head"][1]]
+    with forced_dropout(order):
+        h = x
+        for i in range(c["depth"]):
+            h = blocks[i](h)
+        pooled = norm(h).max(-2)[0]
+        logits = head(drop(pooled))
+    (logits * torch.from_numpy(gl)).sum().backward()
+    out = {"logits": logits.detach().numpy(), "pooled": pooled.detach().numpy(), "grad.tokens": x.grad.numpy()}
+    for n, p_ in blocks.named_parameters():
+        out["grad.blocks." + n] = p_.grad.numpy()
+    for n, p_ in norm.named_parameters():
+        out["grad.encoder_norm." + n] = p_.grad.numpy()
+    for n, p_ in head.named_parameters():
+        out["grad.head." + n] = p_.grad.numpy()
+    for n, b in head.named_buffers():
+        if "num_batches" not in n:
+            out["running.head." + n] = b.numpy()
+    # the oracle, held to the reference
+    lm = [(None, masks["adapter"][i], None) for i in range(c["depth"])]
+    po, _, _ = train.apf_vit_backward(sd, tok, c["depth"], c["heads"], np.zeros((c["B"], c["D"])), lm)
+    pin = po * (1.0 if masks["pool"] is None else masks["pool"])
+    lo, hg, run = train.head_train(sd, pin, gl, masks["head"])
+    dpool = hg.pop("input") * (1.0 if masks["pool"] is None else masks["pool"])
+    _, dx, bg = train.apf_vit_backward(sd, tok, c["depth"], c["heads"], dpool, lm, param_grads=True)
+    rel = lambda a, b: np.abs(np.asarray(a).reshape(b.shape) - b).max() / max(np.abs(b).max(), 1e-30)
+    worst = max(rel(lo, out["logits"]), rel(po, out["pooled"]), rel(dx, out["grad.tokens"]))
+    scale = max(np.abs(v).max() for k_, v in out.items() if k_.startswith("grad.") and k_.endswith("weight") and v.ndim == 2)
+    for n, v in list(bg.items()) + list(hg.items()):
+        worst = max(worst, np.abs(v.reshape(out["grad." + n].shape) - out["grad." + n]).max() / scale)
+    for n, v in run.items():
+        worst = max(worst, rel(v, out["running." + n]))
+    print(f"{name}: oracle/train.py vs reference autograd (blocks + encoder_norm + head, train mode): worst error {worst:.2e}")
+    assert worst < 1e-5, name
+    small = {}
+    for k_, v in out.items():                      # matrices above 5 k elements are stored as their row sums and column sums
+        if v.size > 5000:
+            m = v.reshape(v.shape[0], -1)
+            small[k_ + "#rowsum"] = m.sum(1)
+            small[k_ + "#colsum"] = m.sum(0)
+        else:
+            small[k_] = v
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **small)
+
+
 def main():
     """python tests/golden/make_golden.py [case names ...]  (no names: every case)."""
     assert ref_loader.available(), "reference tree not present"
@@ -414,6 +515,8 @@ def main():
         if want(name): p4p_train_case(ref, name, c)
     for name, c in cases.VIT_TRAIN_CASES.items():
         if want(name): vit_train_case(ref, name, c)
+    for name, c in cases.VIT_FULL_TRAIN_CASES.items():
+        if want(name): vit_full_train_case(ref, name, c)
 
 
 if __name__ == "__main__":

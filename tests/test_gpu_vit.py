@@ -150,7 +150,7 @@ def test_vit_errors():
     with pytest.raises(RuntimeError, match="head dim"):
         blk(torch.zeros(1, 4, 48, device=dev()))
     with pytest.raises(RuntimeError):
-        APFViTLayer(64, 2).train().to(dev())(torch.zeros(1, 4, 64, device=dev()))
+        APFViTLayer(64, 2).train()(torch.zeros(1, 4, 64))    # train mode (p3tok/train_vit.py) is CUDA-only too
     with pytest.raises(RuntimeError):
         ops.attention_bf16(torch.zeros(8, 192), 2, 4, 2)     # CPU tensor: no fallback
 

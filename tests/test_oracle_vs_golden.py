@@ -196,6 +196,35 @@ def test_vit_backward_oracle(golden_dir, name):
         assert np.abs(mine - g[key]).max() <= 1e-5 * np.abs(g[key]).max(), key
 
 
+@pytest.mark.parametrize("name", list(cases.VIT_FULL_TRAIN_CASES))
+def test_full_consumer_train_oracle(golden_dir, name):
+    """oracle/train.py - block stack with EVERY parameter gradient, forced dropout masks, encoder_norm, token max and the
+    train-mode ClassificationHead (batch-statistics BatchNorm1d) - against the reference modules' autograd."""
+    import make_golden
+    from oracle import train
+    c = cases.VIT_FULL_TRAIN_CASES[name]
+    g = _load(golden_dir, name)
+    sd, tok, gl, masks = make_golden.vit_full_train_inputs(c)
+    lm = [(None, masks["adapter"][i], None) for i in range(c["depth"])]
+    pm = 1.0 if masks["pool"] is None else masks["pool"]
+    po, _, _ = train.apf_vit_backward(sd, tok, c["depth"], c["heads"], np.zeros((c["B"], c["D"])), lm)
+    lo, hg, run = train.head_train(sd, po * pm, gl, masks["head"])
+    _, dx, bg = train.apf_vit_backward(sd, tok, c["depth"], c["heads"], hg.pop("input") * pm, lm, param_grads=True)
+    rel = lambda a, b: np.abs(np.asarray(a).reshape(b.shape) - b).max() / max(np.abs(b).max(), 1e-30)
+    assert rel(lo, g["logits"]) <= 1e-5 and rel(po, g["pooled"]) <= 1e-5 and rel(dx, g["grad.tokens"]) <= 1e-5
+    scale = max(np.abs(g[k]).max() for k in g.files if k.startswith("grad.") and k.endswith("weight") and g[k].ndim == 2)
+    for n, v in list(bg.items()) + list(hg.items()):
+        key = "grad." + n
+        if key in g.files:
+            assert np.abs(v.reshape(g[key].shape) - g[key]).max() <= 1e-5 * scale, n
+        else:
+            m = v.reshape(v.shape[0], -1)
+            assert np.abs(m.sum(1) - g[key + "#rowsum"]).max() <= 1e-5 * scale * m.shape[1] ** 0.5, n
+            assert np.abs(m.sum(0) - g[key + "#colsum"]).max() <= 1e-5 * scale * m.shape[0] ** 0.5, n
+    for n, v in run.items():
+        assert rel(v, g["running." + n]) <= 1e-5, n
+
+
 @pytest.mark.parametrize("name", list(cases.P4P_VIT_CASES))
 def test_pointvit_block_oracle_matches_golden(golden_dir, name):
     """oracle.pointvit_blocks (timm Block restated, pix4point.py:254-271) against the fixture an independent implementation of the
