@@ -301,7 +301,11 @@ class PointViTTokens(nn.Module):
             x = p.transpose(1, 2)                          # pix4point.py:237-238: features := coordinates
         p_list, x_list = self.patch_embed(p, x, start_idx)
         tokens = x_list[-1].transpose(1, 2)                # channel-last view of the kernel's native layout
-        d = lambda t: t.detach()                           # inference-only op: parameters enter as plain tensors
+        if self.training or (torch.is_grad_enabled() and tokens.requires_grad):
+            from . import train_vit                        # autograd path: gradients for proj / pos_embed / cls and the tokens
+            feats, pos = train_vit.token_head_train(self, tokens, p_list[-1])
+            return p_list, x_list, feats, pos
+        d = lambda t: t.detach()                           # serving op: parameters enter as plain tensors
         feats, pos = ops.token_head(tokens, p_list[-1], d(self.proj.weight), d(self.proj.bias),
                                     d(self.pos_embed[0].weight), d(self.pos_embed[0].bias), d(self.pos_embed[2].weight),
                                     d(self.pos_embed[2].bias), d(self.cls_token), d(self.cls_pos))

@@ -6,7 +6,9 @@ The reference takes its blocks from `timm.create_model(...)` (pix4point.py:221-2
 parameter layout (`vit.blocks.{i}.norm1 / attn.qkv / attn.proj / norm2 / mlp.fc1 / mlp.fc2`, `vit.norm`, `vit.cls_token`,
 `vit.pos_embed`) - a PointViT checkpoint loads with strict=False (timm's own unused patch embedding / head are skipped).
 forward runs the sm_100a kernels (`p3tok::vit_blocks`: the APF block-stack kernels without the adapter columns, the
-positional add fused into each block's first normalisation pass); eval mode only.
+positional add fused into each block's first normalisation pass) in eval mode; `.train()` - or a gradient wanted through
+eval-mode blocks - takes the fp32 autograd path of p3tok/train_vit.py (Pix4Point trains everything, or everything but `vit.*`
+with frozen=True, pix4point.py:229-233).
 """
 from __future__ import annotations
 
@@ -93,6 +95,10 @@ class PointViT(nn.Module):
         self.cls_pos = nn.Parameter(torch.zeros(1, 1, embed_dim))
         self.__dict__["_tok"] = tok                          # not a registered submodule: its parameters are the ones above
         tok.cls_token, tok.cls_pos = self.cls_token, self.cls_pos
+        if frozen:                                           # pix4point.py:229-233
+            for name, param in self.named_parameters():
+                if "vit" in name:
+                    param.requires_grad = False
 
     def _folded(self) -> List[torch.Tensor]:
         ver = tuple((t._version, t.data_ptr()) for t in self.vit.blocks.parameters())
@@ -103,10 +109,13 @@ class PointViT(nn.Module):
         return cache["params"]
 
     def _run(self, p: torch.Tensor, x: Optional[torch.Tensor], start_idx=None):
-        if self.training:
-            raise RuntimeError("PointViT: p3tok implements the eval-mode forward of the block stack only; call .eval() first")
         tok = self.__dict__["_tok"]
+        tok.train(self.training)                             # not a registered submodule: follow the owner's mode
         p_list, x_list, feats, pos = tok(p, x, start_idx)
+        if self.training or (torch.is_grad_enabled() and (feats.requires_grad or pos.requires_grad)):
+            from . import train_vit
+            out = train_vit.timm_blocks_train(self.vit.blocks, self.norm, feats, pos)
+            return p_list, x_list, out, train_vit.TokenMaxFn.apply(out, 1)
         eps = {float(n.eps) for blk in self.vit.blocks for n in (blk.norm1, blk.norm2)} | {float(self.norm.eps)}
         if len(eps) != 1:
             raise RuntimeError(f"PointViT: all LayerNorms must share one eps, got {sorted(eps)}")

@@ -379,3 +379,172 @@ def head_train(head, x: torch.Tensor, masks=None, sync: bool = False, generator:
     update_running(m[1], outs[1], outs[2])
     update_running(m[5], outs[3], outs[4])
     return outs[0]
+
+
+# ------------------------------------------------------------------------------------------------ Pix4Point (PointViT)
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) on rows (nn.Linear, optionally followed by the exact GELU of pix4point.py:215-217); act: 0 none, 2 GELU."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, act):
+        shape = x.shape
+        x2 = _f32(x).reshape(-1, shape[-1])
+        z = linear(x2, W, b)
+        ctx.save_for_backward(x2, _f32(W), z if act == 2 else x2.new_zeros(0))
+        ctx.act, ctx.shape, ctx.has_bias = act, shape, b is not None
+        y = ew(_lib.EW_GELU, z) if act == 2 else z
+        return y.reshape(*shape[:-1], W.shape[0])
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, W, z = ctx.saved_tensors
+        g2 = _f32(g).reshape(-1, W.shape[0])
+        if ctx.act == 2:
+            g2 = ew(_lib.EW_GELU_BWD, z, g2)
+        dW = linear_tn(g2, x2) if ctx.needs_input_grad[1] else None
+        db = colsum(g2) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        dx = linear(g2, _t(W)).reshape(ctx.shape) if ctx.needs_input_grad[0] else None
+        return dx, dW, db, None
+
+
+class TokenMaxFn(torch.autograd.Function):
+    """torch.max over the tokens after the first `skip` rows of every cloud (pix4point.py:262-268): (B,S,D) -> (B,D)."""
+
+    @staticmethod
+    def forward(ctx, x, skip):
+        B, S, D = x.shape
+        body = _f32(x)[:, skip:, :].contiguous().reshape(B * (S - skip), D)
+        out, arg = group_max_arg(body, S - skip)
+        ctx.save_for_backward(arg)
+        ctx.dims = (B, S, D, skip)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (arg,) = ctx.saved_tensors
+        B, S, D, skip = ctx.dims
+        dx = torch.zeros((B, S, D), dtype=torch.float32, device=g.device)
+        dx[:, skip:, :] = group_max_bwd(g, arg, S - skip).reshape(B, S - skip, D)
+        return dx, None
+
+
+TIMM_BLOCK_PARAMS = ("norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.qkv.bias", "attn.proj.weight", "attn.proj.bias",
+                     "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias")
+NTP = len(TIMM_BLOCK_PARAMS)
+
+
+class TimmBlocksTrainFn(torch.autograd.Function):
+    """PointViT's block loop and final norm (pix4point.py:254-256): for blk: feats = blk(feats + pos_embed); feats = norm(feats),
+    blk = timm's pre-norm Block (x + attn(norm1(x)), then x + mlp(norm2(x)); drop rates 0 as timm.create_model builds them).
+    apply(feats (B,S,D), pos (B,S,D), heads, eps, *params): params = depth x TIMM_BLOCK_PARAMS + (norm.weight, norm.bias);
+    eps = ((norm1, norm2) per block ..., final)."""
+
+    @staticmethod
+    def forward(ctx, feats, pos, heads, eps, *params):
+        B, S, D = feats.shape
+        M = B * S
+        depth = (len(params) - 2) // NTP
+        x = _f32(feats).reshape(M, D)
+        pe = _f32(pos).reshape(M, D)
+        saved: List[torch.Tensor] = []
+        for li in range(depth):
+            n1w, n1b, Wq, bq, Wp, bp, n2w, n2b, W1, b1, W2, b2 = params[li * NTP:(li + 1) * NTP]
+            e1, e2 = eps[li]
+            xin = axpby(1.0, x, 1.0, pe)
+            a, mu1, rs1 = ln_fwd(xin, n1w, n1b, e1)
+            qkv = linear(a, Wq, bq)
+            o, P = attn_fwd(qkv, B, S, heads)
+            att = linear(o, Wp, bp)
+            x1 = axpby(1.0, xin, 1.0, att, out=att)
+            n2, mu2, rs2 = ln_fwd(x1, n2w, n2b, e2)
+            z1 = linear(n2, W1, b1)
+            m = linear(ew(_lib.EW_GELU, z1), W2, b2)
+            x = axpby(1.0, x1, 1.0, m, out=m)
+            saved += [xin, mu1, rs1, qkv, P, o, x1, mu2, rs2, z1]
+        yn, muf, rsf = ln_fwd(x, params[-2], params[-1], eps[depth])
+        saved += [x, muf, rsf]
+        ctx.save_for_backward(*saved, *params)
+        ctx.n_saved = len(saved)
+        ctx.dims = (B, S, D, depth, heads)
+        ctx.eps = eps
+        return yn.reshape(B, S, D)
+
+    @staticmethod
+    def backward(ctx, gout):
+        B, S, D, depth, heads = ctx.dims
+        M = B * S
+        saved, params = ctx.saved_tensors[:ctx.n_saved], ctx.saved_tensors[ctx.n_saved:]
+        need = ctx.needs_input_grad[4:]
+        grads: List[Optional[torch.Tensor]] = [None] * len(params)
+        g = _f32(gout).reshape(M, D)
+        xl, muf, rsf = saved[10 * depth:10 * depth + 3]
+        if need[-2] or need[-1]:
+            gw, gb = ln_param_grad(g, xl, muf, rsf)
+            grads[-2], grads[-1] = (gw if need[-2] else None), (gb if need[-1] else None)
+        dx = ln_bwd(g, xl, muf, rsf, params[-2])
+        dpos = torch.zeros((M, D), dtype=torch.float32, device=dx.device)
+        for li in reversed(range(depth)):
+            n1w, n1b, Wq, bq, Wp, bp, n2w, n2b, W1, b1, W2, b2 = params[li * NTP:(li + 1) * NTP]
+            nd = need[li * NTP:(li + 1) * NTP]
+            xin, mu1, rs1, qkv, P, o, x1, mu2, rs2, z1 = saved[10 * li:10 * li + 10]
+            e1, e2 = ctx.eps[li]
+            gp = [None] * NTP
+            if nd[10] or nd[11]:
+                h = ew(_lib.EW_GELU, z1)
+                gp[10], gp[11] = (linear_tn(dx, h) if nd[10] else None), (colsum(dx) if nd[11] else None)
+                del h
+            dz1 = ew(_lib.EW_GELU_BWD, z1, linear(dx, _t(_f32(W2))))
+            if nd[8] or nd[9]:
+                n2 = ln_fwd(x1, n2w, n2b, e2)[0]
+                gp[8], gp[9] = (linear_tn(dz1, n2) if nd[8] else None), (colsum(dz1) if nd[9] else None)
+                del n2
+            dn2 = linear(dz1, _t(_f32(W1)))
+            del dz1
+            if nd[6] or nd[7]:
+                gp[6], gp[7] = ln_param_grad(dn2, x1, mu2, rs2)
+            dx1 = ln_bwd(dn2, x1, mu2, rs2, n2w, into=dx)          # dx (the block's output gradient) + the MLP branch
+            if nd[4] or nd[5]:
+                gp[4], gp[5] = (linear_tn(dx1, o) if nd[4] else None), (colsum(dx1) if nd[5] else None)
+            dqkv = attn_bwd(qkv, P, linear(dx1, _t(_f32(Wp))), B, S, heads)
+            if nd[2] or nd[3]:
+                a = ln_fwd(xin, n1w, n1b, e1)[0]
+                gp[2], gp[3] = (linear_tn(dqkv, a) if nd[2] else None), (colsum(dqkv) if nd[3] else None)
+                del a
+            da = linear(dqkv, _t(_f32(Wq)))
+            if nd[0] or nd[1]:
+                gp[0], gp[1] = ln_param_grad(da, xin, mu1, rs1)
+            dx = ln_bwd(da, xin, mu1, rs1, n1w, into=dx1)          # = d(feats + pos_embed) of this block
+            axpby(1.0, dpos, 1.0, dx, out=dpos)
+            for i in range(NTP):
+                if gp[i] is not None and nd[i]:
+                    grads[li * NTP + i] = gp[i].reshape(params[li * NTP + i].shape)
+        return (dx.reshape(B, S, D) if ctx.needs_input_grad[0] else None, dpos.reshape(B, S, D) if ctx.needs_input_grad[1] else None,
+                None, None, *grads)
+
+
+def timm_blocks_train(blocks, norm, feats: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
+    """Train-mode / gradient-carrying evaluation of PointViT's block loop + final norm: -> (B,S,D)."""
+    blocks = list(blocks)
+    if not feats.is_cuda:
+        raise RuntimeError("p3tok training path: CUDA tensors only (no CPU fallback)")
+    params: List[torch.Tensor] = []
+    eps = []
+    for blk in blocks:
+        sd = dict(blk.named_parameters())
+        params += [sd[n] for n in TIMM_BLOCK_PARAMS]
+        eps.append((float(blk.norm1.eps), float(blk.norm2.eps)))
+    params += [norm.weight, norm.bias]
+    eps.append(float(norm.eps))
+    return TimmBlocksTrainFn.apply(feats, pos, int(blocks[0].attn.num_heads), tuple(eps), *params)
+
+
+def token_head_train(tok_mod, tokens: torch.Tensor, centers: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """proj / pos_embed / cls concat of PointViT.forward (pix4point.py:245-252) under autograd: tokens (B,G,W), centers (B,G,3)
+    -> (feats (B,1+G,E), pos (B,1+G,E))."""
+    B = tokens.shape[0]
+    x = LinearFn.apply(tokens, tok_mod.proj.weight, tok_mod.proj.bias, 0)
+    pe = LinearFn.apply(centers, tok_mod.pos_embed[0].weight, tok_mod.pos_embed[0].bias, 2)
+    pe = LinearFn.apply(pe, tok_mod.pos_embed[2].weight, tok_mod.pos_embed[2].bias, 0)
+    feats = torch.cat([tok_mod.cls_token.float().expand(B, -1, -1), x], dim=1)
+    pos = torch.cat([tok_mod.cls_pos.float().expand(B, -1, -1), pe], dim=1)
+    return feats, pos

@@ -328,3 +328,68 @@ def head_train(sd: Dict[str, np.ndarray], x: np.ndarray, grad_logits: np.ndarray
         running[prefix + name + ".running_mean"] = (1 - BN_MOMENTUM) * f(name + ".running_mean") + BN_MOMENTUM * mu
         running[prefix + name + ".running_var"] = (1 - BN_MOMENTUM) * f(name + ".running_var") + BN_MOMENTUM * var * n / max(n - 1, 1)
     return out, grads, running
+
+
+# Backward through Pix4Point's block loop (src/models/pix4point.py:254-271): timm pre-norm Blocks with `feats + pos_embed`
+# re-added in front of every block, final norm, 'max,cls' global features.  Pix4Point trains everything (or everything but
+# `vit.*` with frozen=True, pix4point.py:229-233), so feats, pos and every parameter receive a gradient.  timm is absent from the
+# reference tree (pinned timm==1.0.16): the published Block is restated (oracle.timm_block) and the fixture comes from
+# torch.nn.TransformerEncoderLayer(norm_first=True) under autograd (tests/golden/p4p_vit_train.npz).
+
+def pointvit_backward(sd: Dict[str, np.ndarray], feats: np.ndarray, pos: np.ndarray, depth: int, heads: int, grad_glob: np.ndarray,
+                      eps: float = 1e-6):
+    """-> (global features (B,2D) = [max over tokens 1.. || cls], d feats, d pos, {parameter gradients by state_dict name}) for
+    dL/dglobal = grad_glob."""
+    x = feats.astype(np.float64)
+    pe = pos.astype(np.float64)
+    B, S, D = x.shape
+    hd = D // heads
+    r2 = lambda t: t.reshape(-1, t.shape[-1])
+    tape = []
+    for i in range(depth):
+        p = f"vit.blocks.{i}."
+        f = lambda k, p=p: np.asarray(sd[p + k], np.float64)
+        xin = x + pe
+        a, c1 = _ln_fwd(xin, f("norm1.weight"), f("norm1.bias"), eps)
+        qkv = (a @ f("attn.qkv.weight").T + f("attn.qkv.bias")).reshape(B, S, 3, heads, hd).transpose(2, 0, 3, 1, 4)
+        q, k, v = qkv[0], qkv[1], qkv[2]
+        s = (q @ k.transpose(0, 1, 3, 2)) * hd ** -0.5
+        e = np.exp(s - s.max(-1, keepdims=True))
+        P = e / e.sum(-1, keepdims=True)
+        o = (P @ v).transpose(0, 2, 1, 3).reshape(B, S, D)
+        x1 = xin + (o @ f("attn.proj.weight").T + f("attn.proj.bias"))
+        n2, c2 = _ln_fwd(x1, f("norm2.weight"), f("norm2.bias"), eps)
+        z1 = n2 @ f("mlp.fc1.weight").T + f("mlp.fc1.bias")
+        cdf = 0.5 * (1.0 + _erf(z1 / np.sqrt(2.0)))
+        h = z1 * cdf
+        x = x1 + (h @ f("mlp.fc2.weight").T + f("mlp.fc2.bias"))
+        tape.append((p, f, a, c1, q, k, v, P, o, n2, c2, z1, cdf, h))
+    w, b = np.asarray(sd["vit.norm.weight"], np.float64), np.asarray(sd["vit.norm.bias"], np.float64)
+    yn, cf = _ln_fwd(x, w, b, eps)
+    body = yn[:, 1:]
+    arg = body.argmax(1)
+    glob = np.concatenate([np.take_along_axis(body, arg[:, None, :], 1)[:, 0], yn[:, 0]], 1)
+    g = grad_glob.astype(np.float64)
+    dyn = np.zeros_like(yn)
+    np.put_along_axis(dyn[:, 1:], arg[:, None, :], g[:, None, :D], 1)
+    dyn[:, 0] += g[:, D:]
+    grads: Dict[str, np.ndarray] = {}
+    dx, grads["vit.norm.weight"], grads["vit.norm.bias"] = _ln_bwd(dyn, w, cf)
+    dpos = np.zeros_like(pe)
+    for (p, f, a, c1, q, k, v, P, o, n2, c2, z1, cdf, h) in reversed(tape):
+        grads[p + "mlp.fc2.weight"], grads[p + "mlp.fc2.bias"] = r2(dx).T @ r2(h), r2(dx).sum(0)
+        dz1 = (dx @ f("mlp.fc2.weight")) * (cdf + z1 * np.exp(-0.5 * z1 * z1) / np.sqrt(2.0 * np.pi))
+        grads[p + "mlp.fc1.weight"], grads[p + "mlp.fc1.bias"] = r2(dz1).T @ r2(n2), r2(dz1).sum(0)
+        d, grads[p + "norm2.weight"], grads[p + "norm2.bias"] = _ln_bwd(dz1 @ f("mlp.fc1.weight"), f("norm2.weight"), c2)
+        dx1 = dx + d
+        grads[p + "attn.proj.weight"], grads[p + "attn.proj.bias"] = r2(dx1).T @ r2(o), r2(dx1).sum(0)
+        do = (dx1 @ f("attn.proj.weight")).reshape(B, S, heads, hd).transpose(0, 2, 1, 3)
+        dP = do @ v.transpose(0, 1, 3, 2)
+        dv = P.transpose(0, 1, 3, 2) @ do
+        ds = P * (dP - (dP * P).sum(-1, keepdims=True)) * hd ** -0.5
+        dqkv = np.stack([ds @ k, ds.transpose(0, 1, 3, 2) @ q, dv], 0).transpose(1, 3, 0, 2, 4).reshape(B, S, 3 * D)
+        grads[p + "attn.qkv.weight"], grads[p + "attn.qkv.bias"] = r2(dqkv).T @ r2(a), r2(dqkv).sum(0)
+        d, grads[p + "norm1.weight"], grads[p + "norm1.bias"] = _ln_bwd(dqkv @ f("attn.qkv.weight"), f("norm1.weight"), c1)
+        dx = dx1 + d
+        dpos = dpos + dx
+    return glob, dx, dpos, grads

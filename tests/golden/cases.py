@@ -57,6 +57,11 @@ VIT_TRAIN_CASES = {
     "vit_train": dict(B=2, G=20, D=64, heads=2, depth=2, seed=97),
 }
 
+P4P_VIT_TRAIN_CASES = {
+    # Pix4Point's block loop + final norm + 'max,cls' features under autograd, every parameter, feats and pos asking for a gradient
+    "p4p_vit_train": dict(B=3, G=9, D=64, heads=2, depth=2, seed=151),
+}
+
 VIT_FULL_TRAIN_CASES = {
     # the whole token consumer in TRAIN mode under autograd - blocks (every parameter asks for a gradient), encoder_norm, max
     # over tokens, dropout, ClassificationHead with batch-statistics BatchNorm1d: dict(B, G, D, heads, depth, classes, seed,

@@ -269,6 +269,59 @@ def p4p_vit_case(name, c):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), feats=x.numpy(), glob=glob.numpy())
 
 
+def p4p_vit_train_case(name, c):
+    """torch.nn.TransformerEncoderLayer stack (the independent implementation of timm's Block used by p4p_vit_case) in TRAIN mode
+    (dropout 0) under autograd, driven as pix4point.py:254-271: loss = sum(global_features * grad_glob)."""
+    import torch.nn as nn
+    from oracle import train
+    feats, pos, sd = p4p_vit_inputs(c)
+    tsd = synth.to_torch_state(sd)
+    D, H = c["D"], 4 * c["D"]
+    gg = (synth.uniform01(c["seed"], c["B"] * 2 * D, 39).reshape(c["B"], 2 * D) - 0.5).astype(np.float32)
+    names = {"self_attn.in_proj_weight": "attn.qkv.weight", "self_attn.in_proj_bias": "attn.qkv.bias",
+             "self_attn.out_proj.weight": "attn.proj.weight", "self_attn.out_proj.bias": "attn.proj.bias",
+             "linear1.weight": "mlp.fc1.weight", "linear1.bias": "mlp.fc1.bias", "linear2.weight": "mlp.fc2.weight",
+             "linear2.bias": "mlp.fc2.bias", "norm1.weight": "norm1.weight", "norm1.bias": "norm1.bias",
+             "norm2.weight": "norm2.weight", "norm2.bias": "norm2.bias"}
+    layers = []
+    for i in range(c["depth"]):
+        l = nn.TransformerEncoderLayer(D, c["heads"], H, dropout=0.0, activation="gelu", layer_norm_eps=1e-6, batch_first=True,
+                                       norm_first=True).train()
+        l.load_state_dict({k: tsd[f"vit.blocks.{i}." + v] for k, v in names.items()})
+        layers.append(l)
+    norm = nn.LayerNorm(D, eps=1e-6).train()
+    norm.load_state_dict({"weight": tsd["vit.norm.weight"], "bias": tsd["vit.norm.bias"]})
+    x0, p0 = torch.from_numpy(feats).requires_grad_(True), torch.from_numpy(pos).requires_grad_(True)
+    x = x0
+    for l in layers:
+        x = l(x + p0)
+    x = norm(x)
+    glob = torch.cat([x[:, 1:].max(1)[0], x[:, 0]], 1)
+    (glob * torch.from_numpy(gg)).sum().backward()
+    out = {"glob": glob.detach().numpy(), "grad.feats": x0.grad.numpy(), "grad.pos": p0.grad.numpy(),
+           "grad.vit.norm.weight": norm.weight.grad.numpy(), "grad.vit.norm.bias": norm.bias.grad.numpy()}
+    for i, l in enumerate(layers):
+        for k, v in names.items():
+            out[f"grad.vit.blocks.{i}.{v}"] = dict(l.named_parameters())[k].grad.numpy()
+    og, dx, dp, grads = train.pointvit_backward(sd, feats, pos, c["depth"], c["heads"], gg)
+    rel = lambda a, b: np.abs(np.asarray(a).reshape(b.shape) - b).max() / max(np.abs(b).max(), 1e-30)
+    worst = max(rel(og, out["glob"]), rel(dx, out["grad.feats"]), rel(dp, out["grad.pos"]))
+    scale = max(np.abs(v).max() for k_, v in out.items() if k_.endswith("weight") and v.ndim == 2)
+    for n, v in grads.items():
+        worst = max(worst, np.abs(v.reshape(out["grad." + n].shape) - out["grad." + n]).max() / scale)
+    print(f"{name}: oracle/train.py pointvit_backward vs torch.nn.TransformerEncoderLayer autograd: worst error {worst:.2e}")
+    assert worst < 1e-5, name
+    small = {}
+    for k_, v in out.items():
+        if v.size > 5000:
+            m = v.reshape(v.shape[0], -1)
+            small[k_ + "#rowsum"] = m.sum(1)
+            small[k_ + "#colsum"] = m.sum(0)
+        else:
+            small[k_] = v
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **small)
+
+
 def train_inputs(c):
     """(neigh (B,G,k,2C) f32, grad_tokens (B,G,E) f32, encoder state) of a TRAIN_CASES entry (shared with the tests)."""
     x = synth.make_cloud("uniform", c["B"], c["N"], c["seed"], c["C"])
@@ -517,6 +570,8 @@ def main():
         if want(name): vit_train_case(ref, name, c)
     for name, c in cases.VIT_FULL_TRAIN_CASES.items():
         if want(name): vit_full_train_case(ref, name, c)
+    for name, c in cases.P4P_VIT_TRAIN_CASES.items():
+        if want(name): p4p_vit_train_case(name, c)
 
 
 if __name__ == "__main__":

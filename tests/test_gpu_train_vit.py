@@ -257,3 +257,95 @@ def test_adaptpointformer_training_step():
     m2.eval()
     with torch.no_grad():
         assert torch.isfinite(m2(x, st)).all()
+
+
+def test_pix4point_block_loop_train_matches_oracle_and_fixture(golden_dir):
+    """PointViT's block loop + final norm + 'max,cls' features under autograd (pix4point.py:254-271): feats, pos and every
+    parameter against the float64 oracle and the torch.nn.TransformerEncoderLayer-autograd fixture."""
+    from p3tok.p4p_model import TimmBlock
+    c = cases.P4P_VIT_TRAIN_CASES["p4p_vit_train"]
+    g = np.load(os.path.join(golden_dir, "p4p_vit_train.npz"))
+    feats, pos, sd = make_golden.p4p_vit_inputs(c)
+    D = c["D"]
+    gg = (synth.uniform01(c["seed"], c["B"] * 2 * D, 39).reshape(c["B"], 2 * D) - 0.5).astype(np.float32)
+    tsd = synth.to_torch_state(sd)
+    blocks = []
+    for i in range(c["depth"]):
+        b = TimmBlock(D, c["heads"])
+        b.load_state_dict({k[len(f"vit.blocks.{i}."):]: v for k, v in tsd.items() if k.startswith(f"vit.blocks.{i}.")}, strict=True)
+        blocks.append(b.to(dev()).train())
+    norm = torch.nn.LayerNorm(D, eps=1e-6)
+    norm.load_state_dict({"weight": tsd["vit.norm.weight"], "bias": tsd["vit.norm.bias"]})
+    norm = norm.to(dev()).train()
+    x, p = to_dev(feats).requires_grad_(True), to_dev(pos).requires_grad_(True)
+    out = train_vit.timm_blocks_train(blocks, norm, x, p)
+    glob = torch.cat([train_vit.TokenMaxFn.apply(out, 1), out[:, 0, :]], 1)
+    (glob * to_dev(gg)).sum().backward()
+    og, dx, dp, grads = otrain.pointvit_backward(sd, feats, pos, c["depth"], c["heads"], gg)
+    _close(glob.detach().cpu().numpy(), og, "global features vs oracle")
+    _close(glob.detach().cpu().numpy(), g["glob"], "global features vs fixture")
+    _close(x.grad.cpu().numpy(), dx, "d feats vs oracle")
+    _close(p.grad.cpu().numpy(), dp, "d pos vs oracle")
+    _golden_close(x.grad.cpu().numpy(), g, "grad.feats", "d feats")
+    _golden_close(p.grad.cpu().numpy(), g, "grad.pos", "d pos")
+    scale = max(np.abs(v).max() for k_, v in grads.items() if k_.endswith("weight") and v.ndim == 2)
+    for i, b in enumerate(blocks):
+        for n, q in b.named_parameters():
+            _close(q.grad.cpu().numpy().reshape(-1), grads[f"vit.blocks.{i}.{n}"].reshape(-1), f"grad vit.blocks.{i}.{n} vs oracle", TOL, scale)
+            _golden_close(q.grad.cpu().numpy(), g, f"grad.vit.blocks.{i}.{n}", f"grad vit.blocks.{i}.{n}", scale)
+    for n, q in norm.named_parameters():
+        _close(q.grad.cpu().numpy(), grads["vit.norm." + n], "grad vit.norm." + n + " vs oracle", TOL, scale)
+
+
+def test_pointvit_training_step():
+    """PointViT.train(): P3Embed (batch-statistics BatchNorm) -> proj / pos_embed / cls concat -> block loop -> global features,
+    loss, backward: every parameter the reference trains receives a finite gradient; frozen=True leaves `vit.*` without one
+    (pix4point.py:229-233); the token head's gradients agree with the plain PyTorch evaluation of the same layers."""
+    from p3tok.p4p_model import PointViT
+    B, N = 3, 256
+    x = to_dev(synth.make_cloud("uniform", B, N, 23, 3))
+    st = [to_dev(synth.start_indices(B, N, 23))]
+    for frozen in (False, True):
+        torch.manual_seed(1)
+        m = PointViT(embed_dim=64, depth=2, num_heads=2, k_neighbors=8, frozen=frozen, precision="fp32").to(dev()).train()
+        with torch.no_grad():
+            for q in (m.cls_token, m.cls_pos):
+                q.normal_(0, 0.02)
+        gf = m.forward_cls_feat(x, None, st)
+        assert gf.shape == (B, 128)
+        (gf * torch.linspace(-1, 1, 128, device=dev())).sum().backward()
+        for n, q in m.named_parameters():
+            if n == "vit.pos_embed":
+                continue                                     # timm's own position table: PointViT reads only its first row, at construction
+            want = q.requires_grad
+            assert want == (not (frozen and "vit" in n)), n
+            assert (q.grad is not None) == want, n
+            if want:
+                assert torch.isfinite(q.grad).all() and float(q.grad.abs().max()) > 0, n
+        assert int(m.patch_embed.convs[0][0][2].num_batches_tracked) == 1
+    # token head against torch on the device
+    tokm = m.__dict__["_tok"]
+    tk = torch.randn(B, 16, m.patch_embed.out_channels, device=dev(), requires_grad=True)
+    ctr = torch.rand(B, 16, 3, device=dev())
+    for q in m.parameters():
+        q.requires_grad_(True)
+        q.grad = None
+    feats, pos = train_vit.token_head_train(tokm, tk, ctr)
+    w1 = torch.randn_like(feats)
+    ((feats + 0.5 * pos) * w1).sum().backward()
+    got = {n: q.grad.clone() for n, q in (("proj.weight", m.proj.weight), ("pos0.weight", m.pos_embed[0].weight), ("pos2.bias", m.pos_embed[2].bias),
+                                          ("cls_token", m.cls_token), ("cls_pos", m.cls_pos), ("tokens", tk))}
+    for q in list(m.parameters()) + [tk]:
+        q.grad = None
+    F = torch.nn.functional
+    xr = F.linear(tk, m.proj.weight, m.proj.bias)
+    pr = F.linear(F.gelu(F.linear(ctr, m.pos_embed[0].weight, m.pos_embed[0].bias)), m.pos_embed[2].weight, m.pos_embed[2].bias)
+    fr = torch.cat([m.cls_token.expand(B, -1, -1), xr], 1)
+    prr = torch.cat([m.cls_pos.expand(B, -1, -1), pr], 1)
+    ((fr + 0.5 * prr) * w1).sum().backward()
+    _close(feats.detach().cpu().numpy(), fr.detach().cpu().numpy(), "token head feats vs torch", 1e-5)
+    _close(pos.detach().cpu().numpy(), prr.detach().cpu().numpy(), "token head pos vs torch", 1e-5)
+    ref = {"proj.weight": m.proj.weight.grad, "pos0.weight": m.pos_embed[0].weight.grad, "pos2.bias": m.pos_embed[2].bias.grad,
+           "cls_token": m.cls_token.grad, "cls_pos": m.cls_pos.grad, "tokens": tk.grad}
+    for n in got:
+        _close(got[n].cpu().numpy(), ref[n].cpu().numpy(), "token head grad " + n + " vs torch", 2e-5)

@@ -225,6 +225,31 @@ def test_full_consumer_train_oracle(golden_dir, name):
         assert rel(v, g["running." + n]) <= 1e-5, n
 
 
+@pytest.mark.parametrize("name", list(cases.P4P_VIT_TRAIN_CASES))
+def test_pointvit_backward_oracle(golden_dir, name):
+    """oracle/train.py::pointvit_backward (Pix4Point's block loop under autograd: feats, pos, every parameter) against the
+    torch.nn.TransformerEncoderLayer-autograd fixture."""
+    import make_golden
+    from oracle import train
+    c = cases.P4P_VIT_TRAIN_CASES[name]
+    g = _load(golden_dir, name)
+    feats, pos, sd = make_golden.p4p_vit_inputs(c)
+    gg = (synth.uniform01(c["seed"], c["B"] * 2 * c["D"], 39).reshape(c["B"], 2 * c["D"]) - 0.5).astype(np.float32)
+    og, dx, dp, grads = train.pointvit_backward(sd, feats, pos, c["depth"], c["heads"], gg)
+    rel = lambda a, b: np.abs(np.asarray(a).reshape(b.shape) - b).max() / max(np.abs(b).max(), 1e-30)
+    assert rel(og, g["glob"]) <= 1e-5
+    scale = max(np.abs(v).max() for k, v in grads.items() if k.endswith("weight") and v.ndim == 2)
+    for n, v in list(grads.items()) + [("feats", dx), ("pos", dp)]:
+        key = "grad." + n
+        sc = scale if n not in ("feats", "pos") else np.abs(v).max()
+        if key in g.files:
+            assert np.abs(v.reshape(g[key].shape) - g[key]).max() <= 1e-5 * sc, n
+        else:
+            m = v.reshape(v.shape[0], -1)
+            assert np.abs(m.sum(1) - g[key + "#rowsum"]).max() <= 1e-5 * sc * m.shape[1] ** 0.5, n
+            assert np.abs(m.sum(0) - g[key + "#colsum"]).max() <= 1e-5 * sc * m.shape[0] ** 0.5, n
+
+
 @pytest.mark.parametrize("name", list(cases.P4P_VIT_CASES))
 def test_pointvit_block_oracle_matches_golden(golden_dir, name):
     """oracle.pointvit_blocks (timm Block restated, pix4point.py:254-271) against the fixture an independent implementation of the
