@@ -137,3 +137,85 @@ class PointViT(nn.Module):
             if "max" in token_type:
                 feats.append(pooled)
         return torch.cat(feats, dim=1)
+
+
+class ClsHead(nn.Module):
+    """pix4point.py:295-325: (Linear -> BatchNorm1d -> ReLU -> Dropout) per hidden width, then Linear; attribute `head`, same
+    state_dict keys.  eval: BatchNorm folded into the linears (p3tok::linear_f32); train: p3tok/train_vit.py (batch statistics,
+    dropout keep masks, gradients)."""
+
+    def __init__(self, in_channels: int = 768, num_classes: int = 15, mlps: Optional[List[int]] = None, dropout: float = 0.5,
+                 point_dim: int = 2):
+        super().__init__()
+        self.point_dim = point_dim
+        widths = [in_channels] + list(mlps if mlps is not None else [256, 256]) + [num_classes]
+        layers: List[nn.Module] = []
+        for i in range(len(widths) - 2):
+            layers += [nn.Linear(widths[i], widths[i + 1], True), nn.BatchNorm1d(widths[i + 1]), nn.ReLU(), nn.Dropout(dropout)]
+        layers += [nn.Linear(widths[-2], widths[-1], True)]
+        self.head = nn.Sequential(*layers)
+
+    def forward(self, end_points: torch.Tensor) -> torch.Tensor:
+        from . import train_vit
+        if self.training:
+            return train_vit.head_train(self, end_points)
+        blocks, last = train_vit.mlp_head_blocks(self.head)
+        x = end_points.float().contiguous()
+        for lin, bn, _ in blocks:
+            s = bn.weight.detach().double() / torch.sqrt(bn.running_var.double() + bn.eps)
+            w = (lin.weight.detach().double() * s[:, None]).float().contiguous()
+            b = ((lin.bias.detach().double() - bn.running_mean.double()) * s + bn.bias.detach().double()).float().contiguous()
+            x = ops.linear_f32(x, w, b, True)
+        return ops.linear_f32(x, last.weight.detach().float().contiguous(), last.bias.detach().float().contiguous(), False)
+
+
+class Pix4Point(nn.Module):
+    """pix4point.py:328-437: PointViT encoder (`model`) + ClsHead on its 'max,cls' global features (`cls_head`, 2 * embed_dim
+    inputs).  Same constructor arguments (plus the PointViT geometry, since timm cannot supply it here), same initialisation
+    (xavier linears, zero biases, unit BatchNorm; cls token / position ~ N(0, 0.02) when not pretrained), same helpers."""
+
+    def __init__(self, num_classes: int = 15, embed_dim: int = 768, pretrained_model: str = "vit_small_patch16_384.augreg_in21k_ft_in1k",
+                 pretrained: bool = False, frozen: bool = False, k_neighbors: int = 16, **pointvit_kwargs):
+        super().__init__()
+        self.pretrained = pretrained
+        self.model = PointViT(pretrained_model=pretrained_model, pretrained=pretrained, embed_dim=embed_dim, k_neighbors=k_neighbors,
+                              frozen=frozen, **pointvit_kwargs)
+        self.cls_head = ClsHead(in_channels=2 * embed_dim, num_classes=num_classes)
+        self.initialize_weights()
+
+    def initialize_weights(self):
+        if not self.pretrained:
+            torch.nn.init.normal_(self.model.cls_token, std=.02)
+            torch.nn.init.normal_(self.model.cls_pos, std=.02)
+        for name, module in self.named_modules():
+            if name.startswith("vit") and self.pretrained:
+                continue
+            self._init_weights(module)
+
+    @staticmethod
+    def _init_weights(m):
+        if isinstance(m, nn.Linear):
+            torch.nn.init.xavier_uniform_(m.weight)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    def get_param_groups(self):
+        """pix4point.py:388-401: weight decay for everything but cls token / position, biases and norms."""
+        decay, no_decay = [], []
+        for name, param in self.named_parameters():
+            if not param.requires_grad:
+                continue
+            if "cls_token" in name or "cls_pos" in name or name.endswith(".bias") or "norm" in name:
+                no_decay.append(param)
+            else:
+                decay.append(param)
+        return [{"params": decay}, {"params": no_decay, "weight_decay": 0.0}]
+
+    def get_trainable_params(self):
+        return filter(lambda p: p.requires_grad, self.model.parameters())
+
+    def forward(self, points: torch.Tensor, start_idx=None) -> torch.Tensor:
+        return self.cls_head(self.model.forward_cls_feat(points, None, start_idx))

@@ -324,60 +324,75 @@ def dropout(x: torch.Tensor, p: float, training: bool, mask: Optional[torch.Tens
     return x if mask is None else MaskMulFn.apply(x, mask)
 
 
-# ------------------------------------------------------------------------------------------------ classification head
+# ------------------------------------------------------------------------------------------------ classification heads
 class HeadTrainFn(torch.autograd.Function):
-    """ClassificationHead in train mode (apf.py:230-252): Linear -> BN1d -> ReLU -> Dropout, twice, -> Linear.
-    apply(x (B,E), eps (2), sync, masks (2 or None), W1, b1, g1, be1, W2, b2, g2, be2, W3, b3) ->
-    (logits, batch mean / unbiased variance of both BatchNorms for the running-estimate update)."""
+    """An MLP head in train mode: (Linear -> BatchNorm1d (batch statistics) -> ReLU -> Dropout) x n -> Linear - the reference's
+    ClassificationHead (apf.py:230-252, n = 2) and ClsHead (pix4point.py:295-325).
+    apply(x (B,E), eps (n), sync, masks (n entries or None), W1, b1, g1, be1, ..., Wn, bn, gn, ben, Wout, bout) ->
+    (logits, batch mean / unbiased variance of every BatchNorm for the running-estimate update)."""
 
     @staticmethod
-    def forward(ctx, x, eps, sync, masks, W1, b1, g1, be1, W2, b2, g2, be2, W3, b3):
-        x = _f32(x)
-        m1, m2 = masks if masks is not None else (None, None)
-        z1 = linear(x, W1, b1)
-        h1, s1 = bn_forward(z1, g1, be1, eps[0], True, sync)
-        h1 = mask_mul(h1, m1)
-        z2 = linear(h1, W2, b2)
-        h2, s2 = bn_forward(z2, g2, be2, eps[1], True, sync)
-        h2 = mask_mul(h2, m2)
-        out = linear(h2, W3, b3)
-        ctx.sync, ctx.stats, ctx.masks = sync, (s1, s2), (m1, m2)
-        ctx.save_for_backward(x, z1, h1, z2, h2, W1, W2, W3, g1, be1, g2, be2)
-        outs = [out, s1.mean64.float(), s1.var_unbiased.float(), s2.mean64.float(), s2.var_unbiased.float()]
+    def forward(ctx, x, eps, sync, masks, *params):
+        n = (len(params) - 2) // 4
+        h = _f32(x)
+        masks = tuple(masks) if masks is not None else (None,) * n
+        saved, stats = [], []
+        for i in range(n):
+            W, b, g, be = params[4 * i:4 * i + 4]
+            z = linear(h, W, b)
+            y, st = bn_forward(z, g, be, eps[i], True, sync)
+            saved += [h, z]
+            stats.append(st)
+            h = mask_mul(y, masks[i])
+        out = linear(h, params[-2], params[-1])
+        ctx.sync, ctx.stats, ctx.masks, ctx.n = sync, stats, masks, n
+        ctx.save_for_backward(*saved, h, *params)
+        outs = [out]
+        for st in stats:
+            outs += [st.mean64.float(), st.var_unbiased.float()]
         ctx.mark_non_differentiable(*outs[1:])
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, g, *_unused):
-        x, z1, h1, z2, h2, W1, W2, W3, g1, be1, g2, be2 = ctx.saved_tensors
-        s1, s2 = ctx.stats
-        m1, m2 = ctx.masks
+        n = ctx.n
+        saved, params = ctx.saved_tensors[:2 * n + 1], ctx.saved_tensors[2 * n + 1:]
+        grads = [None] * len(params)
         g = _f32(g)
-        dW3, db3 = linear_tn(g, h2), colsum(g)
-        dh2 = mask_mul(linear(g, _t(_f32(W3))), m2)
-        dz2, dg2, dbe2 = bn_backward(dh2, z2, s2, g2, be2, True, ctx.sync)
-        dW2, db2 = linear_tn(dz2, h1), colsum(dz2)
-        dh1 = mask_mul(linear(dz2, _t(_f32(W2))), m1)
-        dz1, dg1, dbe1 = bn_backward(dh1, z1, s1, g1, be1, True, ctx.sync)
-        dW1, db1 = linear_tn(dz1, x), colsum(dz1)
-        dx = linear(dz1, _t(_f32(W1))) if ctx.needs_input_grad[0] else None
-        return (dx, None, None, None, dW1, db1, dg1, dbe1, dW2, db2, dg2, dbe2, dW3, db3)
+        grads[-2], grads[-1] = linear_tn(g, saved[2 * n]), colsum(g)
+        d = linear(g, _t(_f32(params[-2])))
+        for i in reversed(range(n)):
+            W, b, gam, be = params[4 * i:4 * i + 4]
+            hin, z = saved[2 * i], saved[2 * i + 1]
+            dz, dgam, dbe = bn_backward(mask_mul(d, ctx.masks[i]), z, ctx.stats[i], gam, be, True, ctx.sync)
+            grads[4 * i:4 * i + 4] = [linear_tn(dz, hin), colsum(dz), dgam, dbe]
+            if i > 0 or ctx.needs_input_grad[0]:
+                d = linear(dz, _t(_f32(W)))
+        return (d if ctx.needs_input_grad[0] else None, None, None, None, *grads)
+
+
+def mlp_head_blocks(seq):
+    """[(Linear, BatchNorm1d, Dropout), ...], final Linear of an nn.Sequential laid out (Linear, BN, ReLU, Dropout) x n, Linear."""
+    mods = list(seq)
+    n = (len(mods) - 1) // 4
+    return [(mods[4 * i], mods[4 * i + 1], mods[4 * i + 3]) for i in range(n)], mods[-1]
 
 
 def head_train(head, x: torch.Tensor, masks=None, sync: bool = False, generator: Optional[torch.Generator] = None) -> torch.Tensor:
-    """Train-mode ClassificationHead.forward on x (B,E); updates the BatchNorm buffers like nn.BatchNorm1d does."""
+    """Train-mode forward of an MLP head module (attribute `mlp_head` or `head`) on x (B,E); updates the BatchNorm buffers like
+    nn.BatchNorm1d does."""
     from .train import update_running
-    m = head.mlp_head
+    blocks, last = mlp_head_blocks(head.mlp_head if hasattr(head, "mlp_head") else head.head)
     if masks is None:
-        p1, p2 = float(m[3].p), float(m[7].p)
-        masks = (keep_mask((x.shape[0], m[0].out_features), p1, x.device, generator),
-                 keep_mask((x.shape[0], m[4].out_features), p2, x.device, generator))
-        if masks[0] is None and masks[1] is None:
+        masks = tuple(keep_mask((x.shape[0], lin.out_features), float(dr.p), x.device, generator) for lin, _, dr in blocks)
+        if all(m is None for m in masks):
             masks = None
-    outs = HeadTrainFn.apply(x, (float(m[1].eps), float(m[5].eps)), bool(sync), masks, m[0].weight, m[0].bias, m[1].weight, m[1].bias,
-                             m[4].weight, m[4].bias, m[5].weight, m[5].bias, m[8].weight, m[8].bias)
-    update_running(m[1], outs[1], outs[2])
-    update_running(m[5], outs[3], outs[4])
+    params = []
+    for lin, bn, _ in blocks:
+        params += [lin.weight, lin.bias, bn.weight, bn.bias]
+    outs = HeadTrainFn.apply(x, tuple(float(bn.eps) for _, bn, _ in blocks), bool(sync), masks, *params, last.weight, last.bias)
+    for i, (_, bn, _) in enumerate(blocks):
+        update_running(bn, outs[1 + 2 * i], outs[2 + 2 * i])
     return outs[0]
 
 

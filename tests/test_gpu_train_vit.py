@@ -349,3 +349,44 @@ def test_pointvit_training_step():
            "cls_token": m.cls_token.grad, "cls_pos": m.cls_pos.grad, "tokens": tk.grad}
     for n in got:
         _close(got[n].cpu().numpy(), ref[n].cpu().numpy(), "token head grad " + n + " vs torch", 2e-5)
+
+
+def test_clshead_and_pix4point_model():
+    """ClsHead (pix4point.py:295-325) eval / train against the plain PyTorch evaluation of its own nn.Sequential container, and
+    a full Pix4Point training step (pix4point.py:328-437) on the kernels."""
+    import copy
+    from p3tok.p4p_model import ClsHead, Pix4Point
+    torch.manual_seed(7)
+    head = ClsHead(in_channels=96, num_classes=11, mlps=[64, 48, 32], dropout=0.0).to(dev())
+    with torch.no_grad():
+        for mod in head.head:
+            if isinstance(mod, torch.nn.BatchNorm1d):
+                mod.running_mean.normal_(0, 0.2); mod.running_var.uniform_(0.5, 1.5); mod.weight.uniform_(0.5, 1.5); mod.bias.normal_(0, 0.1)
+    ref = copy.deepcopy(head.head)
+    x = torch.randn(10, 96, device=dev())
+    _close(head.eval()(x).cpu().numpy(), ref.eval()(x).detach().cpu().numpy(), "ClsHead eval vs torch", 1e-5)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    w = torch.randn(10, 11, device=dev())
+    (head.train()(xa) * w).sum().backward()
+    (ref.train()(xb) * w).sum().backward()
+    _close(xa.grad.cpu().numpy(), xb.grad.cpu().numpy(), "ClsHead train d input vs torch")
+    scale = max(float(q.grad.abs().max()) for q in ref.parameters() if q.ndim == 2)
+    for (n, q), (_, r) in zip(head.head.named_parameters(), ref.named_parameters()):
+        _close(q.grad.cpu().numpy(), r.grad.cpu().numpy(), "ClsHead train grad " + n + " vs torch", TOL, scale)
+    for (n, q), (_, r) in zip(head.head.named_buffers(), ref.named_buffers()):
+        _close(q.float().cpu().numpy(), r.float().cpu().numpy(), "ClsHead running " + n + " vs torch", 1e-5)
+    # the whole model: a training step, then serving
+    B, N = 4, 256
+    pts = to_dev(synth.make_cloud("clustered", B, N, 29, 3))
+    st = [to_dev(synth.start_indices(B, N, 29))]
+    m = Pix4Point(num_classes=5, embed_dim=64, depth=2, num_heads=2, k_neighbors=8, precision="fp32").to(dev()).train()
+    opt = torch.optim.AdamW(m.get_param_groups(), lr=1e-3, weight_decay=0.05)
+    before = m.cls_head.head[0].weight.detach().clone()
+    logits = m(pts, st)
+    assert logits.shape == (B, 5)
+    torch.nn.functional.cross_entropy(logits, torch.arange(B, device=dev()) % 5).backward()
+    opt.step()
+    assert not torch.equal(before, m.cls_head.head[0].weight)
+    assert all(torch.isfinite(q.grad).all() for q in m.parameters() if q.grad is not None)
+    with torch.no_grad():
+        assert torch.isfinite(m.eval()(pts, st)).all()
