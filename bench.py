@@ -399,15 +399,16 @@ class Harness:
 
     # ---- e2e: host buffers in, host tokens out, through the public serving API (p3tok.graph.GraphedHostTokenizer):
     # one CUDA graph per step = pinned-host -> device copies of the clouds and start indices, the captured module call,
-    # device -> pinned-host copy of the tokens.  Two instances on two streams are replayed alternately, so the copies of
-    # step i+1 overlap the kernels of step i; the host pays one graph launch per step.
+    # device -> pinned-host copy of the tokens.  As many instances as the device-resident loop has steps in flight (>= 2) are
+    # replayed round-robin on their own streams, so the copies of step i+1 overlap the kernels of step i; the host pays one
+    # graph launch per step.
     def prepare_e2e(self):
         from p3tok.graph import GraphedHostTokenizer
         with torch.no_grad():
             self.graphs = [GraphedHostTokenizer(lambda x, *st: self.run(x, list(st)), [self.x_host] + self.st_host, self.device)
-                           for _ in range(2)]
-            for i in range(4):
-                self.graphs[i & 1].replay()
+                           for _ in range(max(2, self.streams))]
+            for i in range(2 * len(self.graphs)):
+                self.graphs[i % len(self.graphs)].replay()
             for g in self.graphs:
                 g.synchronize()
         self.h2d_bytes = self.in_bytes + sum(s.numel() * 8 for s in self.st_host)
@@ -423,7 +424,7 @@ class Harness:
             self.barrier()
             t0 = time.perf_counter()
             for i in range(steps):
-                g = self.graphs[i & 1]
+                g = self.graphs[i % len(self.graphs)]
                 g.replay()
                 if gather is not None:
                     gather(g)
@@ -467,6 +468,12 @@ def run_p3tok(args, w, rank, world, local_rank):
     B = per_gpu_clouds(w, world)
     kinds = ["uniform", "clustered"] if args.clouds == "both" else [args.clouds]
 
+    if args.streams <= 0:
+        # auto: FPS / kNN are one CTA (or cluster) per cloud, so a batch of B clouds leaves SMs idle during the index half of a
+        # step when B is well below the SM count; up to 4 steps in flight fill them (c1, B = 32: 152 k -> 194 k clouds/s on the
+        # same box with 4; c2 / c5w, B >= 128: no gain beyond 2)
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        args.streams = 2 if 2 * B > sms else min(4, max(2, sms // B))
     H = Harness(w, B, precision, tok_dtype, device, rank, world, kinds[0], args.eager, args.streams)
     if args.ncu > 0:
         # profiling aid, not a measurement: `ncu --profile-from-start off ... bench.py --ncu 1` sees exactly N eager steps
@@ -696,7 +703,7 @@ def main():
                     help="input kind of the headline numbers; 'both' = uniform headline + a short clustered run attached as other_clouds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the c5 strong-scaling probe attached to the default c2 line")
-    ap.add_argument("--streams", type=int, default=2, help="steps in flight in the device-resident loop (graphs replayed round-robin on as many streams)")
+    ap.add_argument("--streams", type=int, default=0, help="steps in flight (graphs replayed round-robin on as many streams) in the device-resident and e2e loops; 0 = auto: 2, up to 4 when the batch is well below the SM count")
     ap.add_argument("--ncu", type=int, default=0, help="profiling aid: run N eager steps between cudaProfilerStart/Stop and exit (no timing)")
     ap.add_argument("--eager", action="store_true", help="time the Python-dispatched module call instead of the CUDA-graph replay")
     args = ap.parse_args()
