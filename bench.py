@@ -472,8 +472,10 @@ def run_p3tok(args, w, rank, world, local_rank):
         # auto: FPS / kNN are one CTA (or cluster) per cloud, so a batch of B clouds leaves SMs idle during the index half of a
         # step when B is well below the SM count; up to 4 steps in flight fill them (c1, B = 32: 152 k -> 194 k clouds/s on the
         # same box with 4; c2 / c5w, B >= 128: no gain beyond 2)
+        # (c4, B = 16 x 65536 points, runs FPS as one CLUSTER per cloud and fills the device: 2 stays best, 3052 vs 3018)
         sms = torch.cuda.get_device_properties(device).multi_processor_count
-        args.streams = 2 if 2 * B > sms else min(4, max(2, sms // B))
+        ctas = B * max(1, -(-int(w["N"]) // 8192))          # index-kernel CTAs of one step: one per cloud, a cluster beyond 8192 points
+        args.streams = 2 if 2 * ctas > sms else min(4, max(2, sms // ctas))
     H = Harness(w, B, precision, tok_dtype, device, rank, world, kinds[0], args.eager, args.streams)
     if args.ncu > 0:
         # profiling aid, not a measurement: `ncu --profile-from-start off ... bench.py --ncu 1` sees exactly N eager steps
@@ -511,7 +513,7 @@ def run_p3tok(args, w, rank, world, local_rank):
     # ---- e2e with the reference's token dtype (f32) when the headline moved bf16 tokens, and with the token all-gather
     e2e_f32 = None
     if tok_dtype is not None:
-        H32 = Harness(w, B, precision, None, device, rank, world, kinds[0])
+        H32 = Harness(w, B, precision, None, device, rank, world, kinds[0], False, args.streams)
         with torch.no_grad():
             for i in range(3):
                 H32.run(H32.pool[0], H32.st_pool[0])
@@ -544,7 +546,7 @@ def run_p3tok(args, w, rank, world, local_rank):
     # ---- the other input kind (north star: uniform AND clustered clouds), shorter windows
     other = None
     if len(kinds) > 1:
-        H2 = Harness(w, B, precision, tok_dtype, device, rank, world, kinds[1])
+        H2 = Harness(w, B, precision, tok_dtype, device, rank, world, kinds[1], args.eager, args.streams)
         H2.prepare_device_loop(3)
         win = H2.time_device_windows(args.steps, min_s=0.3)
         H2.prepare_e2e()
