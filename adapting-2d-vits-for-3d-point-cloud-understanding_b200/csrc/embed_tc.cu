@@ -1897,9 +1897,59 @@ int patch_embed_x3(const p3tok_rows* R, const p3tok_mlp* m, void* ws, int64_t ws
   return P3TOK_OK;
 }
 
+// fp32 [R, C] -> bf16 [R, 3 cpad] = [hi | hi | lo], zero padded: the weight operand of the bf16x3 product
+__global__ void split_w3_kernel(const float* __restrict__ in, int64_t R_, int C, int cpad, __nv_bfloat16* __restrict__ out) {
+  const int64_t total = R_ * cpad;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % cpad);
+    const int64_t r = e / cpad;
+    const float v = c < C ? in[r * C + c] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    __nv_bfloat16* o = out + r * 3 * cpad + c;
+    o[0] = hi;
+    o[cpad] = hi;
+    o[2 * cpad] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
+// C = act(A W^T + bias + gbias) for fp32 operands through the bf16x3 tensor-core product (the training path's GEMMs when
+// P3TOK_TRAIN_TC=1): both operands are split on the fly into the caller's workspace.
+int linear_x3_f32(const float* A, int64_t M, int K, const float* W, int N, const float* bias, const float* gbias, int rows_per_group,
+                  int relu, float* C, void* ws, int64_t ws_bytes, cudaStream_t s) {
+  const int64_t kp = pad64(K);
+  const int64_t a_bytes = align_up(M * 2 * kp * 2, 1024), w_bytes = align_up((int64_t)N * 3 * kp * 2, 1024);
+  P3_REQUIRE(ws_bytes >= a_bytes + w_bytes + 1024, P3TOK_ERR_WORKSPACE, "linear_x3_f32: workspace %lld < %lld bytes", (long long)ws_bytes,
+             (long long)(a_bytes + w_bytes + 1024));
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) / 1024 * 1024);
+  __nv_bfloat16* sa = reinterpret_cast<__nv_bfloat16*>(base);
+  __nv_bfloat16* sw = reinterpret_cast<__nv_bfloat16*>(base + a_bytes);
+  split_rows_kernel<<<grid_1d(M * kp, 256), 256, 0, s>>>(A, M, K, (int)kp, sa);
+  P3_LAUNCH_CHECK("split_rows_kernel");
+  split_w3_kernel<<<grid_1d((int64_t)N * kp, 256), 256, 0, s>>>(W, N, K, (int)kp, sw);
+  P3_LAUNCH_CHECK("split_w3_kernel");
+  TcExtra ex;
+  ex.x3 = 1;
+  return tc_linear(sa, M, (int)(3 * kp), sw, N, bias, gbias, rows_per_group, relu, nullptr, C, nullptr, nullptr, 0, s, &ex);
+}
+
 }  // namespace p3tok
 
 using namespace p3tok;
+
+extern "C" int64_t p3tok_linear_x3_workspace_bytes(int64_t M, int64_t K, int64_t N) {
+  if (M < 0 || K <= 0 || N <= 0) return -1;
+  const int64_t kp = (K + 63) / 64 * 64;
+  return align_up(M * 2 * kp * 2, 1024) + align_up(N * 3 * kp * 2, 1024) + 1024;
+}
+
+extern "C" int p3tok_linear_x3_f32(const float* A, int64_t M, int64_t K, const float* W, int64_t N, const float* bias, const float* gbias,
+                                   int64_t rows_per_group, int relu, float* C, void* workspace, int64_t workspace_bytes, void* stream) {
+  P3_REQUIRE(M >= 0 && K > 0 && N > 0 && K < (1 << 22) && N < (1 << 24), P3TOK_ERR_INVALID, "linear_x3_f32: bad shape");
+  if (M == 0) return P3TOK_OK;
+  P3_REQUIRE(A && W && C && workspace, P3TOK_ERR_INVALID, "linear_x3_f32: null pointer");
+  P3_REQUIRE(relu == 0 || relu == 1, P3TOK_ERR_UNSUPPORTED, "linear_x3_f32: activation %d", relu);
+  return linear_x3_f32(A, M, (int)K, W, (int)N, bias, gbias, (int)rows_per_group, relu, C, workspace, workspace_bytes, as_stream(stream));
+}
 
 extern "C" int p3tok_linear_bf16(const void* A, int64_t M, int64_t K, const void* W, int64_t N, const float* bias,
                                  const float* gbias, int64_t rows_per_group, int relu, void* out_bf16, float* out_f32,

@@ -68,6 +68,8 @@ _SIGNATURES = {
     "p3tok_patch_embed_workspace_bytes": (_i64, [ctypes.POINTER(MlpStruct), _i64, _i64, _int]),
     "p3tok_patch_embed": (_int, [ctypes.POINTER(RowsStruct), ctypes.POINTER(MlpStruct), _int, _int, _vp, _i64, _vp, _vp]),
     "p3tok_linear_f32": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _int, _vp, _vp]),
+    "p3tok_linear_x3_workspace_bytes": (_i64, [_i64, _i64, _i64]),
+    "p3tok_linear_x3_f32": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _int, _vp, _vp, _i64, _vp]),
     "p3tok_linear_bf16": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp]),
     "p3tok_token_head_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64] + [_vp] * 12),
     "p3tok_group_max": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),

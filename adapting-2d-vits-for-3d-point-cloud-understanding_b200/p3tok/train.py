@@ -13,11 +13,15 @@ sum x, sum x^2, row count; backward: sum dy, sum dy*xhat) are all-reduced - the 
 on the module, torch.distributed initialised).  Weight gradients are per-rank partial sums, reduced by the caller (DDP).
 
 fp32 on CUDA cores; per-channel sums in fp64.  The eval-mode (serving) path is the tensor-core one; this path exists so that
-the kernels can replace the reference inside its trainers.
+the kernels can replace the reference inside its trainers.  Opt-in: P3TOK_TRAIN_TC=1 (or `set_tensor_core_gemms(1)`) sends the
+forward and dX products through the fp32-accurate bf16x3 tensor-core GEMM (`p3tok_linear_x3_f32`: operands split into bf16
+hi + lo, three partial products in one tcgen05 GEMM, fp32 accumulate, ~1e-5 of max); the weight-gradient products stay on CUDA
+cores.  The fp32 CUDA-core SGEMMs stay the default: they are what the 1e-4 parity tests pin.
 """
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -40,16 +44,45 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
     return t.detach().float().contiguous()
 
 
-# ------------------------------------------------------------------------------------------------ kernel wrappers
-def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, gbias: Optional[torch.Tensor] = None,
-           rows_per_group: int = 1) -> torch.Tensor:
-    """a (M,K) w (N,K) -> a w^T + bias + gbias[m // rows_per_group]  (p3tok_linear_f32)."""
-    a, w = _f32(a), _f32(w)
+_TC_LEVEL = int(os.environ.get("P3TOK_TRAIN_TC", "0") or 0)
+_TC_MIN_ROWS = 1024          # below this the split + ramp of the tensor-core GEMM costs more than the SGEMM
+
+
+def set_tensor_core_gemms(level: int) -> int:
+    """0: fp32 SGEMMs on CUDA cores (default); 1: forward / dX products (a w^T with >= 1024 rows) on the tensor cores
+    (bf16x3, fp32-accurate).  The weight-gradient products dY^T X stay on CUDA cores: their output is a small matrix and their
+    reduction axis is the row count, so without a split-K schedule a tensor-core tile walk keeps only a handful of SMs busy.
+    Returns the previous level."""
+    global _TC_LEVEL
+    prev, _TC_LEVEL = _TC_LEVEL, int(level)
+    return prev
+
+
+def _linear_x3(a: torch.Tensor, w: torch.Tensor, b, g, rows_per_group: int) -> torch.Tensor:
     M, K = a.shape
     N = w.shape[0]
     out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    L = _L()
+    ws = torch.empty(int(L.p3tok_linear_x3_workspace_bytes(M, K, N)), dtype=torch.uint8, device=a.device)
+    with torch.cuda.device(a.device):
+        check(L.p3tok_linear_x3_f32(a.data_ptr(), M, K, w.data_ptr(), N, b.data_ptr() if b is not None else None,
+                                    g.data_ptr() if g is not None else None, int(rows_per_group), 0, out.data_ptr(), ws.data_ptr(),
+                                    ws.numel(), _s()), "linear_x3_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ kernel wrappers
+def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, gbias: Optional[torch.Tensor] = None,
+           rows_per_group: int = 1) -> torch.Tensor:
+    """a (M,K) w (N,K) -> a w^T + bias + gbias[m // rows_per_group]  (p3tok_linear_f32; P3TOK_TRAIN_TC: p3tok_linear_x3_f32)."""
+    a, w = _f32(a), _f32(w)
+    M, K = a.shape
+    N = w.shape[0]
     b = _f32(bias) if bias is not None else None
     g = _f32(gbias) if gbias is not None else None
+    if _TC_LEVEL >= 1 and M >= _TC_MIN_ROWS and N % 8 == 0 and N <= 2048 and K >= 16:
+        return _linear_x3(a, w, b, g, rows_per_group)
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
         check(_L().p3tok_linear_f32(a.data_ptr(), M, K, w.data_ptr(), N, b.data_ptr() if b is not None else None,
                                     g.data_ptr() if g is not None else None, int(rows_per_group), 0, out.data_ptr(), _s()), "linear_f32")

@@ -210,6 +210,15 @@ P3TOK_API int p3tok_linear_bf16(const void* A, int64_t M, int64_t K, const void*
                       const float* gbias, int64_t rows_per_group, int relu, void* out_bf16,
                       float* out_f32, float* out_max32, void* stream);
 
+/* fp32 in, fp32 out, on the tensor cores: C[M,N] = act(A[M,K] W[N,K]^T + bias + gbias) with both operands split on the fly
+ * into hi = bf16(v), lo = bf16(v - hi) and a w = a_hi w_hi + a_lo w_hi + a_hi w_lo evaluated as ONE tcgen05 GEMM over the
+ * three-fold reduction length (fp32 accumulate; ~1e-5 of max against float64).  N % 8 == 0, N <= 2048; relu 0 / 1.
+ * workspace >= p3tok_linear_x3_workspace_bytes(M, K, N).  Used by the training path when P3TOK_TRAIN_TC=1. */
+P3TOK_API int64_t p3tok_linear_x3_workspace_bytes(int64_t M, int64_t K, int64_t N);
+P3TOK_API int p3tok_linear_x3_f32(const float* A, int64_t M, int64_t K, const float* W, int64_t N, const float* bias,
+                        const float* gbias, int64_t rows_per_group, int relu, float* C, void* workspace,
+                        int64_t workspace_bytes, void* stream);
+
 /* ---- "next" row 1: Pix4Point token head, src/models/pix4point.py:213-218 and 245-252 -----------
  * feats_out (B,1+G,E): row 0 = cls_token, rows 1.. = proj(tokens) with proj = Linear(W->E);
  * pos_out   (B,1+G,E): row 0 = cls_pos,   rows 1.. = Linear(H->E)(GELU(Linear(3->H)(centres))) (exact erf GELU).

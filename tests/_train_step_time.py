@@ -41,6 +41,7 @@ for _ in range(iters):
     loss = step()
 e1.record()
 torch.cuda.synchronize()
-print(f"APF training step B={B} N={N} G={G} k={k} E={E} depth=12: {e0.elapsed_time(e1) / iters:.1f} ms/step (device), "
+import os
+print(f"[P3TOK_TRAIN_TC={os.environ.get('P3TOK_TRAIN_TC', '0')}] APF training step B={B} N={N} G={G} k={k} E={E} depth=12: {e0.elapsed_time(e1) / iters:.1f} ms/step (device), "
       f"{(time.perf_counter() - t0) / iters * 1e3:.1f} ms wall, {B / (e0.elapsed_time(e1) / iters) * 1e3:.0f} clouds/s, "
       f"{(ops.kernel_launches() - n0) // iters} p3tok launches, loss {float(loss):.4f}, peak memory {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB")

@@ -390,3 +390,67 @@ def test_clshead_and_pix4point_model():
     assert all(torch.isfinite(q.grad).all() for q in m.parameters() if q.grad is not None)
     with torch.no_grad():
         assert torch.isfinite(m.eval()(pts, st)).all()
+
+
+def test_tensor_core_training_gemms():
+    """P3TOK_TRAIN_TC / set_tensor_core_gemms(1): the forward and dX products of the training path through the bf16x3 tensor-core
+    GEMM (p3tok_linear_x3_f32).  The product itself against float64, then a train-mode Encoder step against the oracle (tokens
+    1e-4 of max; gradients in aggregate, see below)."""
+    from p3tok import train
+    from p3tok.modules import Encoder
+    gen = torch.Generator(device="cpu").manual_seed(11)
+    for M, K, N in ((4096, 384, 1152), (1500, 6, 256), (2048, 1600, 384), (1024, 131, 64)):
+        a = torch.randn(M, K, generator=gen).to(dev())
+        w = (torch.randn(N, K, generator=gen) / K ** 0.5).to(dev())
+        b = torch.randn(N, generator=gen).to(dev())
+        prev = train.set_tensor_core_gemms(1)
+        try:
+            got = train.linear(a, w, b)
+        finally:
+            train.set_tensor_core_gemms(prev)
+        ref = a.double() @ w.double().t() + b.double()
+        _close(got.cpu().numpy(), ref.cpu().numpy(), f"bf16x3 linear {M}x{K}x{N} vs float64", 3e-5)
+    # 2048 rows (>= the 1024-row threshold below which the SGEMM is kept), ragged against the 256-row tiles of the GEMM
+    from oracle import oracle
+    B, N, C, G, k, E = 3, 512, 3, 43, 16, 64
+    xs = synth.make_cloud("uniform", B, N, 77, C)
+    neigh = oracle.group_apf(xs, synth.start_indices(B, N, 77), G, k)["neigh"].astype(np.float32)
+    sd = synth.apf_encoder_state(E, 2 * C, 77)
+    gt = (synth.uniform01(77, B * G * E, 31).reshape(B, G, E) - 0.5).astype(np.float32)
+    enc = Encoder(E, 2 * C).to(dev()).train()
+    enc.load_state_dict(synth.to_torch_state(sd))
+    x = to_dev(neigh).requires_grad_(True)
+    from p3tok import ops
+    prev = train.set_tensor_core_gemms(1)
+    n0 = ops.kernel_launches()
+    try:
+        tok = enc(x)
+        (tok * to_dev(gt)).sum().backward()
+    finally:
+        train.set_tensor_core_gemms(prev)
+    launches_tc = ops.kernel_launches() - n0
+    otok, ograds, _ = otrain.apf_encoder_train(sd, neigh, gt)
+    _close(tok.detach().cpu().numpy(), otok, "tensor-core training: tokens vs oracle", 1e-4)
+    # Gradients are ROUTED by the two arg-max pools (8256 picks each here): tokens that differ by 1e-5 pick another row of a
+    # near-tie in a handful of places, and one moved pick changes a weight gradient by ~1 % in the Frobenius norm (measured:
+    # every bf16x3 product of this step is within 7e-6 of float64 on its real operands, tests/_dbg_tc_train.py, while the
+    # gradients differ from the fp32-SGEMM run by 1-3 % - and the fp32-SGEMM run itself moves by 0.7-1.6 % when one layer's
+    # weights are perturbed by 1e-5: the sensitivity is the function's, not the GEMM's).  So gradients are held to an aggregate
+    # bound here; the element-wise 1e-4 contract is the CUDA-core default's.
+    def fro(a, b):
+        a, b = np.asarray(a, np.float64).reshape(-1), np.asarray(b, np.float64).reshape(-1)
+        return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+    e = fro(x.grad.cpu().numpy(), ograds["input"])
+    print(f"[train parity] tensor-core training: grad input vs oracle: relative Frobenius error {e:.2e}")
+    assert e <= 6e-2, e
+    for name, p_ in enc.named_parameters():
+        if name.endswith("weight"):
+            e = fro(p_.grad.cpu().numpy(), ograds[name])
+            print(f"[train parity] tensor-core training: grad {name} vs oracle: relative Frobenius error {e:.2e}")
+            assert e <= 6e-2, (name, e)
+    # the tensor-core path really ran: every bf16x3 product adds two split kernels to the launch count of the SGEMM path
+    for p_ in enc.parameters():
+        p_.grad = None
+    n0 = ops.kernel_launches()
+    (enc(x.detach().requires_grad_(True)) * to_dev(gt)).sum().backward()
+    assert launches_tc > ops.kernel_launches() - n0
