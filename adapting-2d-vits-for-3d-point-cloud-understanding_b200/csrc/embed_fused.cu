@@ -268,6 +268,13 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // accumulator (~4600 of 24700 cycles per tile at E = 384).  Measured on the same box: c2 0.977 vs 0.947 ms per step
       // WITHOUT it - the early A(0) delays the last B-GEMM and with it the tile epilogue that the next B(0) waits for.
       // Off by default.
+      // Also measured and dropped (round 2, last session): the issuing thread POLLING the A and B streams' barriers
+      // (mbarrier.test_wait) and issuing whichever k-block / K step has its operands, instead of parking inside A(j+1) on
+      // the weight box the 5-slot A ring cannot hold yet while B(j) is ready (the "Anext" stamps of
+      // profiles/r02_fused_trace_after.txt).  Bit-identical tokens, no stall - and c2 0.91 -> 1.41 ms per step whichever
+      // stream has priority: one thread walking a state machine with 4-6 barrier probes (a shared-memory round trip each)
+      // per step needs longer per k-block than the 260 cycles its four MMAs take, so the tensor pipe starves on ISSUE.
+      // The blocking walk costs ~15 instructions per k-block.
       auto first_A = [&](int tile_it) {
         if (issuer) fu_trace(p, tile_it, 0, 4, clock64());        // tile start
         mbar_wait(a0_full, (uint32_t)(tile_it & 1));
