@@ -15,7 +15,7 @@ INCLUDE = os.path.join(_ROOT, "include")
 LIB_PATH = os.path.join(_PKG, "libp3tok.so")
 OBJ_DIR = os.path.join(CSRC, "_obj")
 
-SOURCES = ["capi.cu", "fps.cu", "fps_culled.cu", "knn.cu", "group.cu", "mlp_f32.cu", "embed_tc.cu", "embed_fused.cu", "embed_stage.cu", "embed_gather.cu", "vit.cu", "train.cu", "train_vit.cu"]
+SOURCES = ["capi.cu", "fps.cu", "fps_culled.cu", "fps_nd.cu", "sqdist.cu", "knn.cu", "group.cu", "mlp_f32.cu", "embed_tc.cu", "embed_fused.cu", "embed_stage.cu", "embed_gather.cu", "vit.cu", "train.cu", "train_vit.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",

@@ -56,6 +56,8 @@ _SIGNATURES = {
     "p3tok_kernel_launches": (_i64, []),
     "p3tok_fps": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
     "p3tok_fps_sorted": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "p3tok_fps_nd": (_int, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "p3tok_square_distance": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp]),
     "p3tok_gather_points": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
     "p3tok_knn": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _int, _vp, _int, _vp, _vp]),
     "p3tok_knn_workspace_bytes": (_i64, [_i64, _i64]),

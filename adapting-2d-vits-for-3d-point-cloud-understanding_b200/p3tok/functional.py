@@ -37,17 +37,27 @@ def furthest_point_sample(xyz: torch.Tensor, npoint: int, start_idx: Optional[to
 def farthest_point_sampling(points: torch.Tensor, n_samples: int,
                             start_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
     """pix4point.py:8-53: clamps n_samples to N (line 23); distances sum over ALL D coordinates (line 44).
-    D = 3 (and D = 4 rows whose 4th channel is not a coordinate never reach this function in the reference) runs
-    the kernel in place; D < 3 is zero-padded to 3 columns - adding (0 - 0)^2 = +0 terms leaves every fp32 sum
-    bit-identical; D > 3 is outside the kernel's envelope (the reference only ever passes xyz, pix4point.py:175)."""
+    D = 3 - the reference's only call site passes xyz (pix4point.py:175) - runs the register / cluster kernel in place
+    (p3tok_fps); any other D <= 16 runs the general-D kernel (p3tok_fps_nd), which adds the D squares in the order
+    torch's CPU sum adds them, so the picks are the reference's for every D."""
     D = int(points.shape[-1])
-    if D > 3:
-        raise RuntimeError("p3tok farthest_point_sampling: D > 3 coordinates are not supported (the reference's only "
-                           "call site passes xyz, pix4point.py:175)")
+    if D > 16:
+        raise RuntimeError(f"p3tok farthest_point_sampling: D = {D} > 16 coordinates are not supported")
     start = _start(points, start_idx, device_draw=True)
-    if D < 3:
-        points = torch.cat([points.float(), points.new_zeros((*points.shape[:2], 3 - D), dtype=torch.float32)], -1)
-    return ops.fps(points, start, min(int(n_samples), int(points.shape[1])))
+    n = min(int(n_samples), int(points.shape[1]))
+    if D != 3:
+        return ops.fps_nd(points, start, n)
+    return ops.fps(points, start, n)
+
+
+def square_distance(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """sampler.py:47-62 `_square_distance`: (B,N,3), (B,M,3) -> (B,N,M), bit-exact restatement of the reference's
+    -2*matmul + |src|^2 + |dst|^2 (may be slightly negative).  knn_point never materialises it; this is for callers
+    that use the matrix itself."""
+    return ops.square_distance(src, dst)
+
+
+_square_distance = square_distance     # the reference's (private) name
 
 
 def index_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:

@@ -152,6 +152,54 @@ def _(x, start_idx, npoint):
     return x.new_empty((x.shape[0], npoint), dtype=torch.int64)
 
 
+@torch.library.custom_op("p3tok::fps_nd", mutates_args=(), device_types="cuda")
+def fps_nd(points: torch.Tensor, start_idx: torch.Tensor, npoint: int) -> torch.Tensor:
+    """(B,npoint) int64 FPS indices of D-dimensional points (B,N,D), 1 <= D <= 16: farthest_point_sampling's distance over
+    ALL coordinates (pix4point.py:44), summed in torch's CPU order (csrc/fps_nd.cu).  The xyz case runs on p3tok::fps."""
+    _need_cuda("fps_nd", points, start_idx)
+    if points.dim() != 3:
+        raise RuntimeError(f"p3tok::fps_nd: expected (B,N,D) points, got {tuple(points.shape)}")
+    x = (points if points.dtype == torch.float32 else points.float()).contiguous()
+    B, N, D = (int(v) for v in x.shape)
+    start = start_idx.to(torch.int64).contiguous()
+    if start.shape != (B,):
+        raise RuntimeError(f"p3tok::fps_nd: start_idx must have shape ({B},)")
+    out = torch.empty((B, npoint), dtype=torch.int64, device=x.device)
+    ws = torch.empty((B, N), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device), _timed("fps"):
+        check(_L().p3tok_fps_nd(x.data_ptr(), B, N, D, D, start.data_ptr(), npoint, out.data_ptr(), ws.data_ptr(), _stream()),
+              "fps_nd")
+    return out
+
+
+@fps_nd.register_fake
+def _(points, start_idx, npoint):
+    return points.new_empty((points.shape[0], npoint), dtype=torch.int64)
+
+
+@torch.library.custom_op("p3tok::square_distance", mutates_args=(), device_types="cuda")
+def square_distance(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """_square_distance (sampler.py:47-62): src (B,S,3), dst (B,N,3) -> (B,S,N) f32, the kNN kernels' APF arithmetic."""
+    _need_cuda("square_distance", src, dst)
+    if src.dim() != 3 or dst.dim() != 3 or src.shape[0] != dst.shape[0] or src.shape[-1] != 3 or dst.shape[-1] != 3:
+        raise RuntimeError(f"p3tok::square_distance: expected (B,S,3) and (B,N,3), got {tuple(src.shape)} and {tuple(dst.shape)}")
+    if dst.dtype != torch.float32:
+        raise RuntimeError(f"p3tok::square_distance: expected float32, got {dst.dtype}")
+    c = _f32c("square_distance", src)
+    d, stride = _point_stride(dst)          # a [:, :, :3] view of (B,N,4) rows is read in place
+    B, S, N = int(c.shape[0]), int(c.shape[1]), int(d.shape[1])
+    out = torch.empty((B, S, N), dtype=torch.float32, device=c.device)
+    with torch.cuda.device(c.device), _timed("sqdist"):
+        check(_L().p3tok_square_distance(c.data_ptr(), B, S, d.data_ptr(), N, stride, out.data_ptr(), _stream()),
+              "square_distance")
+    return out
+
+
+@square_distance.register_fake
+def _(src, dst):
+    return src.new_empty((src.shape[0], src.shape[1], dst.shape[1]), dtype=torch.float32)
+
+
 # ------------------------------------------------------------------------------------------- gather
 @torch.library.custom_op("p3tok::gather_points", mutates_args=(), device_types="cuda")
 def gather_points(x: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:

@@ -79,6 +79,15 @@ def make_cloud(kind: str, B: int, N: int, seed: int, channels: int = 3) -> np.nd
     raise ValueError("channels must be 3 or 4")
 
 
+def make_points_nd(B: int, N: int, D: int, seed: int) -> np.ndarray:
+    """(B,N,D) float32 points uniform in [-1,1)^D for the general-D FPS (farthest_point_sampling, pix4point.py:8-53);
+    the second quarter of every cloud repeats the first, so exact distance ties (lowest index wins) are exercised."""
+    pts = (uniform01(seed, B * N * D, 7 + D) * np.float32(2) - np.float32(1)).reshape(B, N, D)
+    q = N // 4
+    pts[:, q:2 * q] = pts[:, :q]
+    return np.ascontiguousarray(pts, dtype=np.float32)
+
+
 def start_indices(B: int, N: int, seed: int, stage: int = 0) -> np.ndarray:
     """FPS start index per cloud (stands in for torch.randint(0,N,(B,)), sampler.py:20)."""
     return randint(seed, B, N, 100 + stage)

@@ -76,6 +76,16 @@ P3TOK_API int p3tok_fps(const float* x, int64_t B, int64_t N, int64_t pt_stride,
 P3TOK_API int p3tok_fps_sorted(const void* workspace, int64_t workspace_bytes, int64_t B, int64_t N,
                      const int64_t* start_idx, int64_t G, int64_t* out_idx, void* stream);
 
+/* farthest_point_sampling (src/models/pix4point.py:8-53) on D-dimensional points, 1 <= D <= 16: the reference sums the
+ * squared differences over ALL D coordinates (line 44, torch.sum(..., dim=2)).  x: point p of cloud b at
+ * x[(b*N+p)*pt_stride + 0..D-1] (pt_stride >= D).  The D squares are added in the order torch's CPU sum kernel adds a
+ * contiguous last dimension (four interleaved partial sums below 8 elements, 8 vector lanes from 8 on - spelled out in
+ * csrc/fps_nd.cu and oracle/p3tok_oracle.c, checked bit for bit against torch.sum), so the picks equal the reference's for
+ * every D; for D <= 3 they equal p3tok_fps's.  min_dist_ws: (B,N) f32 scratch owned by the caller (the running minima;
+ * contents on entry are ignored).  One CTA per cloud, any N < 2^31; the xyz case belongs on p3tok_fps. */
+P3TOK_API int p3tok_fps_nd(const float* x, int64_t B, int64_t N, int64_t D, int64_t pt_stride, const int64_t* start_idx,
+                 int64_t G, int64_t* out_idx, float* min_dist_ws, void* stream);
+
 /* ---- a5: index_points (src/data/sampler.py:77-94) / torch.gather of centres (pix4point.py:176)
  * x (B,N,C) f32, idx (B,S) int64 -> out (B,S,C).  S may be G or G*k. */
 P3TOK_API int p3tok_gather_points(const float* x, int64_t B, int64_t N, int64_t C, const int64_t* idx,
@@ -110,6 +120,13 @@ P3TOK_API int p3tok_knn_prepare(const float* x, int64_t B, int64_t N, int64_t pt
                       int64_t workspace_bytes, void* stream);
 P3TOK_API int p3tok_knn_query(const void* workspace, int64_t workspace_bytes, int64_t B, int64_t N, const float* centres,
                     int64_t G, int64_t k, int mode, void* idx_out, int idx_dtype, float* dist_out, void* stream);
+
+/* _square_distance materialised (src/data/sampler.py:47-62): src (B,S,3) contiguous, dst: point n of cloud b at
+ * dst[(b*N+n)*dst_stride + 0..2] -> out (B,S,N) f32 = ((-2*dot) + |src|^2) + |dst|^2 with the K=3 FMA chain of
+ * P3TOK_KNN_APF_SQ (bit-exact restatement of the reference's matmul form; values may be slightly negative, no clamp).
+ * The tokenizer itself never materialises this matrix (p3tok_knn*); B*S*N < 2^40. */
+P3TOK_API int p3tok_square_distance(const float* src, int64_t B, int64_t S, const float* dst, int64_t N,
+                          int64_t dst_stride, float* out, void* stream);
 
 /* ---- a7: Morton order of the centres (src/models/apf_utils.py:66-104, resolution 1024) -------
  * centres (B,G,3) -> perm (B,G) int64 = stable ascending argsort of the 30-bit Z-order code;

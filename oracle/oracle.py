@@ -48,11 +48,14 @@ def lib():
         L = ctypes.CDLL(_LIB_PATH)
         i64, fp, ip, vp = ctypes.c_int64, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p
         L.orc_fps.argtypes = [fp, i64, i64, i64, ip, i64, ip]
+        L.orc_fps_nd.argtypes = [fp, i64, i64, i64, i64, ip, i64, ip]
+        L.orc_torch_row_sum.argtypes = [fp, i64, i64, fp]
+        L.orc_torch_row_sum.restype = ctypes.c_int
         L.orc_knn.argtypes = [fp, i64, fp, i64, i64, i64, i64, ctypes.c_int, ip, vp]
         L.orc_pair_dist.argtypes = [fp, i64, fp, i64, i64, i64, ctypes.c_int, fp]
         L.orc_morton.argtypes = [fp, i64, i64, ip, vp]
         L.orc_group_apf.argtypes = [fp, i64, i64, i64, ip, ip, vp, i64, i64, fp, fp]
-        for f in (L.orc_fps, L.orc_knn, L.orc_pair_dist, L.orc_morton, L.orc_group_apf):
+        for f in (L.orc_fps, L.orc_fps_nd, L.orc_knn, L.orc_pair_dist, L.orc_morton, L.orc_group_apf):
             f.restype = ctypes.c_int
         _lib = L
     return _lib
@@ -81,6 +84,25 @@ def fps(x: np.ndarray, start: np.ndarray, G: int) -> np.ndarray:
     start = np.ascontiguousarray(start, dtype=np.int64)
     out = np.empty((B, G), dtype=np.int64)
     _check(lib().orc_fps(_f(x), B, N, C, _i(start), G, _i(out)), "fps")
+    return out
+
+
+def fps_nd(points: np.ndarray, start: np.ndarray, G: int) -> np.ndarray:
+    """pix4point.py:8-53 on D-dimensional points (B,N,D), 1 <= D <= 32: the distance sums over ALL D coordinates in
+    torch's CPU summation order (p3tok_oracle.c: torch_cpu_row_sum).  No clamp of G.  Returns (B,G) int64."""
+    points = np.ascontiguousarray(points, dtype=np.float32)
+    B, N, D = points.shape
+    start = np.ascontiguousarray(start, dtype=np.int64)
+    out = np.empty((B, G), dtype=np.int64)
+    _check(lib().orc_fps_nd(_f(points), B, N, D, D, _i(start), G, _i(out)), "fps_nd")
+    return out
+
+
+def torch_row_sum(q: np.ndarray) -> np.ndarray:
+    """(rows, D) float32 -> the row sums in the order torch.sum(q, -1) adds them on the CPU (D <= 32)."""
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    out = np.empty((q.shape[0],), dtype=np.float32)
+    _check(lib().orc_torch_row_sum(_f(q), q.shape[0], q.shape[1], _f(out)), "torch_row_sum")
     return out
 
 

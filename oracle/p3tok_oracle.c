@@ -79,6 +79,83 @@ int orc_fps(const float* xyz, int64_t B, int64_t N, int64_t pt_stride, const int
   return err ? ORC_EINVAL : ORC_OK;
 }
 
+/* torch.sum(v, -1) over a CONTIGUOUS last dimension of D fp32 values on the CPU, restated (torch's cascade_sum,
+ * aten/src/ATen/native/cpu/SumKernel.cpp; third-party, not under /root/reference).  Vector width 8 (the AVX2 kernel, also
+ * what an AVX-512 host dispatches to).  D < 8 is the scalar row sum with four interleaved partial sums: p[j] = v[j] for
+ * j < 4 when D >= 4, the elements from 4*(D/4) on are added to p[0], then p[0] += p[1], p[2], p[3].  D >= 8: lane k of the
+ * vector accumulator = v[k] + v[8+k] + ... over the D/8 whole vectors, the tail elements are summed first (from 0), then
+ * the 8 lanes are added in order.  D <= 4 and D = 8 come out as the plain left-to-right sum.  Checked bit for bit against
+ * torch.sum for every D in 1..32 (tests/test_oracle_vs_reference.py::test_fps_nd).  q: D values; D <= 32. */
+static float torch_cpu_row_sum(const float* q, int D) {
+  if (D < 8) {
+    float p[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    int done = 0;
+    if (D >= 4) {
+      for (int j = 0; j < 4; ++j) p[j] = p[j] + q[j];
+      done = 4;
+    }
+    for (int i = done; i < D; ++i) p[0] = p[0] + q[i];
+    for (int j = 1; j < 4; ++j) p[0] = p[0] + p[j];
+    return p[0];
+  }
+  const int nvec = D / 8;
+  float lane[8];
+  for (int k = 0; k < 8; ++k) lane[k] = 0.0f + q[k];
+  for (int v = 1; v < nvec; ++v)
+    for (int k = 0; k < 8; ++k) lane[k] = lane[k] + q[8 * v + k];
+  float f = 0.0f;
+  for (int i = nvec * 8; i < D; ++i) f = f + q[i];
+  for (int k = 0; k < 8; ++k) f = f + lane[k];
+  return f;
+}
+
+/* rows x D values -> the row sums in torch's CPU order (test hook: compared with torch.sum bit for bit) */
+int orc_torch_row_sum(const float* q, int64_t rows, int64_t D, float* out) {
+  if (D < 1 || D > 32) return ORC_EINVAL;
+  for (int64_t r = 0; r < rows; ++r) out[r] = torch_cpu_row_sum(q + r * D, (int)D);
+  return ORC_OK;
+}
+
+/* pix4point.py:8-53 farthest_point_sampling on D-dimensional points (the distance sums over ALL D coordinates, line 44:
+ * torch.sum((points - centroid) ** 2, -1)), 1 <= D <= 32; point p of cloud b at pts[(b*N+p)*pt_stride + 0..D-1].
+ * The squared differences are summed in torch's CPU order (torch_cpu_row_sum).  The running distance starts at 1e10
+ * (pix4point.py:27); update where dist < distance (47-48); torch.max keeps the first (lowest) index of the maximum (51).
+ * D = 3 gives orc_fps's picks (the tests cross-check).  No clamp of G here (min(n_samples, N), line 23: callers). */
+int orc_fps_nd(const float* pts, int64_t B, int64_t N, int64_t D, int64_t pt_stride, const int64_t* start,
+               int64_t G, int64_t* out) {
+  if (B < 0 || N <= 0 || G < 0 || D < 1 || D > 32 || pt_stride < D) return ORC_EINVAL;
+  int err = 0;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t b = 0; b < B; ++b) {
+    const float* P = pts + b * N * pt_stride;
+    float* mind = (float*)malloc(sizeof(float) * (size_t)N);
+    if (!mind) { err = 1; continue; }
+    for (int64_t i = 0; i < N; ++i) mind[i] = 1e10f;
+    int64_t far = start[b];
+    if (far < 0 || far >= N) { err = 1; free(mind); continue; }
+    for (int64_t g = 0; g < G; ++g) {
+      out[b * G + g] = far;
+      const float* c = P + far * pt_stride;
+      float best = -1.0f;
+      int64_t besti = 0;
+      for (int64_t i = 0; i < N; ++i) {
+        float q[32];
+        for (int64_t a = 0; a < D; ++a) {
+          float df = P[i * pt_stride + a] - c[a];
+          q[a] = df * df;
+        }
+        float d = torch_cpu_row_sum(q, (int)D);
+        float m = mind[i];
+        if (d < m) { m = d; mind[i] = m; }
+        if (m > best) { best = m; besti = i; } /* strict >: first (lowest) index wins */
+      }
+      far = besti;
+    }
+    free(mind);
+  }
+  return err ? ORC_EINVAL : ORC_OK;
+}
+
 static inline uint32_t f2ord(float f) {
   uint32_t b;
   memcpy(&b, &f, 4);

@@ -28,6 +28,12 @@ INDEX_CASES = {
     "idx_dups": dict(kind="duplicates", B=2, N=512, G=64, k=16, seed=33),
 }
 
+FPS_ND_CASES = {
+    # farthest_point_sampling on D-dimensional points (pix4point.py:8-53 sums over ALL D coordinates): dict(B, N, G, dims, seed);
+    # one index array per D; the dims cover both branches of torch's CPU summation order (below 8 elements / 8 lanes + tail)
+    "fps_nd": dict(B=2, N=600, G=80, dims=[1, 2, 4, 5, 6, 7, 8, 9, 11, 12, 15, 16], seed=71),
+}
+
 HEAD_CASES = {
     # Pix4Point token head (proj + pos_embed + cls concat): name: dict(B, G, W, E, seed)
     "p4p_head": dict(B=2, G=16, W=64, E=96, seed=41),

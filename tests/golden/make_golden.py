@@ -169,6 +169,23 @@ def index_case(ref, name, c):
                         morton_perm=mperm.numpy().astype(np.int32))
 
 
+def fps_nd_case(ref, name, c):
+    """farthest_point_sampling (pix4point.py:8-53) of the UNMODIFIED reference on (B,N,D) points for every D in c['dims']."""
+    out = {}
+    start = synth.start_indices(c["B"], c["N"], c["seed"])
+    for D in c["dims"]:
+        pts = synth.make_points_nd(c["B"], c["N"], D, c["seed"])
+        with torch.no_grad(), forced_randint([start]):
+            r = ref.farthest_point_sampling(torch.from_numpy(pts), c["G"]).numpy()
+        assert np.array_equal(oracle.fps_nd(pts, start, c["G"]), r), (name, D)
+        sq = np.square(pts - pts[:, :1])
+        assert np.array_equal(oracle.torch_row_sum(sq.reshape(-1, D)),
+                              torch.sum(torch.from_numpy(sq), -1).numpy().reshape(-1)), (name, D)
+        out[f"idx_D{D}"] = r.astype(np.int32)
+    print(f"{name}: oracle.fps_nd == reference for D in {c['dims']}; row sums bit-equal to torch.sum")
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+
+
 def head_case(name, c):
     """The reference builds these layers with plain torch.nn (pix4point.py:213-218) and applies them at 245-252; PointViT
     itself cannot be constructed here (timm.create_model), so the same torch.nn modules are evaluated directly."""
@@ -552,6 +569,8 @@ def main():
     want = lambda name: not only or name in only
     for name, c in cases.INDEX_CASES.items():
         if want(name): index_case(ref, name, c)
+    for name, c in cases.FPS_ND_CASES.items():
+        if want(name): fps_nd_case(ref, name, c)
     for name, c in cases.APF_CASES.items():
         if want(name): apf_case(ref, name, c)
     for name, c in cases.P4P_CASES.items():

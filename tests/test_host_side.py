@@ -231,6 +231,30 @@ def test_fps_kernel_sass_has_no_fused_multiply_add(built):
     assert entry.fps_fused_multiply_adds(built) == 0
 
 
+def test_general_d_fps_and_square_distance_validate_on_the_host(built):
+    """p3tok_fps_nd / p3tok_square_distance: argument validation and the empty cases return before any CUDA call, so the
+    error behaviour of the C ABI is checkable without a GPU (status codes of include/p3tok.h, text from p3tok_last_error)."""
+    L = _lib.lib()
+    assert L.p3tok_fps_nd(None, 0, 16, 5, 5, None, 4, None, None, None) == _lib.OK            # no clouds: nothing to do
+    assert L.p3tok_fps_nd(None, 2, 16, 5, 5, None, 0, None, None, None) == _lib.OK            # no samples asked for
+    assert L.p3tok_fps_nd(None, 2, 16, 17, 17, None, 4, None, None, None) == _lib.ERR_UNSUPPORTED
+    assert b"D=17" in L.p3tok_last_error()
+    assert L.p3tok_fps_nd(None, 2, 16, 5, 4, None, 4, None, None, None) == _lib.ERR_INVALID   # rows shorter than D
+    assert L.p3tok_fps_nd(None, 2, 0, 5, 5, None, 4, None, None, None) == _lib.ERR_INVALID    # empty clouds cannot be sampled
+    assert L.p3tok_fps_nd(None, 2, 16, 5, 5, None, 4, None, None, None) == _lib.ERR_INVALID   # null pointers
+    assert L.p3tok_square_distance(None, 2, 0, None, 16, 3, None, None) == _lib.OK            # empty matrix
+    assert L.p3tok_square_distance(None, 2, 4, None, 16, 2, None, None) == _lib.ERR_INVALID   # dst rows shorter than xyz
+    assert L.p3tok_square_distance(None, 2, 4, None, 16, 3, None, None) == _lib.ERR_INVALID   # null pointers
+    assert L.p3tok_square_distance(None, 1 << 14, 1 << 14, None, 1 << 14, 3, None, None) == _lib.ERR_INVALID  # nulls first
+    from p3tok import functional as F
+    with pytest.raises(RuntimeError, match="16"):
+        F.farthest_point_sampling(torch.zeros(1, 8, 17), 4, torch.zeros(1, dtype=torch.long))
+    with pytest.raises((NotImplementedError, RuntimeError)):                                  # CPU tensors: no fallback
+        F.farthest_point_sampling(torch.zeros(1, 8, 5), 4, torch.zeros(1, dtype=torch.long))
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        F.square_distance(torch.zeros(1, 2, 3), torch.zeros(1, 8, 3))
+
+
 def test_bn_statistics_combination_matches_batchnorm():
     """Host logic of the train-mode BatchNorm (p3tok.train.combine_stats): (sum, sum of squares, rows) -> mean, rstd and the
     unbiased variance nn.BatchNorm1d puts into running_var; summing the per-shard triples first (SyncBN) gives the same."""

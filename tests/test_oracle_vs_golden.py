@@ -36,6 +36,41 @@ def test_index_cases(golden_dir, name):
     assert np.array_equal(np.take_along_axis(codes, ref_perm, 1), np.take_along_axis(codes, perm, 1))
 
 
+@pytest.mark.parametrize("name", list(cases.FPS_ND_CASES))
+def test_fps_nd_cases(golden_dir, name):
+    """General-D farthest_point_sampling (pix4point.py:8-53): the oracle reproduces the reference's picks for every D of
+    the fixture, and for D = 3 the general restatement equals the xyz one."""
+    c = cases.FPS_ND_CASES[name]
+    g = _load(golden_dir, name)
+    start = synth.start_indices(c["B"], c["N"], c["seed"])
+    for D in c["dims"]:
+        pts = synth.make_points_nd(c["B"], c["N"], D, c["seed"])
+        assert np.array_equal(oracle.fps_nd(pts, start, c["G"]), g[f"idx_D{D}"]), D
+    p3 = synth.make_points_nd(c["B"], c["N"], 3, c["seed"])
+    assert np.array_equal(oracle.fps_nd(p3, start, c["G"]), oracle.fps(p3, start, c["G"]))
+
+
+def test_torch_row_sum_is_torchs_cpu_order():
+    """The summation order the general-D FPS is held to (p3tok_oracle.c: torch_cpu_row_sum) IS torch.sum's on this host,
+    bit for bit, for every D up to 32 - and it is NOT the left-to-right sum from D = 5 on (except D = 8), which is why the
+    kernel spells the order out."""
+    import torch
+    if torch.backends.cpu.get_cpu_capability() not in ("AVX2", "AVX512"):
+        pytest.skip("torch's CPU sum kernel has another vector width on this host")
+    rng = np.random.default_rng(5)
+    differs = []
+    for D in range(1, 33):
+        q = np.square(rng.standard_normal((4096, D)).astype(np.float32))
+        mine = oracle.torch_row_sum(q)
+        assert np.array_equal(mine, torch.sum(torch.from_numpy(q), -1).numpy()), D
+        seq = q[:, 0].copy()
+        for a in range(1, D):
+            seq = (seq + q[:, a]).astype(np.float32)
+        if not np.array_equal(seq, mine):
+            differs.append(D)
+    assert differs == [d for d in range(5, 33) if d != 8]
+
+
 @pytest.mark.parametrize("name", list(cases.APF_CASES))
 def test_apf_cases(golden_dir, name):
     c = cases.APF_CASES[name]

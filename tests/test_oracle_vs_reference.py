@@ -40,6 +40,20 @@ def test_index_ops(ref, B, N, G, k, seed):
     assert np.array_equal(np.square(d_orc.astype(np.float64)).round(3) >= 0, np.ones_like(d_orc, bool))
 
 
+@pytest.mark.parametrize("D", list(range(1, 33)))
+def test_fps_nd(ref, D):
+    """farthest_point_sampling on D-dimensional points (pix4point.py:8-53, distance over ALL coordinates): the oracle's
+    restatement of torch's CPU summation order gives the live reference's picks for every D, exact ties included."""
+    B, N, G = 3, 500, 70
+    pts = synth.make_points_nd(B, N, D, 40 + D)
+    st = synth.start_indices(B, N, 40 + D)
+    with _forced([st]), torch.no_grad():
+        r = ref.farthest_point_sampling(torch.from_numpy(pts), G)
+    assert np.array_equal(oracle.fps_nd(pts, st, G), r.numpy())
+    sq = np.square(pts - pts[:, 3:4])
+    assert np.array_equal(oracle.torch_row_sum(sq.reshape(-1, D)), torch.sum(torch.from_numpy(sq), -1).numpy().reshape(-1))
+
+
 def test_p3embed_port_matches_reference(ref):
     B, N, k = 2, 512, 16
     x = synth.make_cloud("uniform", B, N, 9)
