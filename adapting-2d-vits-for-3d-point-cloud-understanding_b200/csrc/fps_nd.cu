@@ -13,15 +13,15 @@
 //           then p[0] += p[1]; p[0] += p[2]; p[0] += p[3].          (D <= 4: the plain left-to-right sum)
 //   D >= 8: lane[k] = q[k] + q[8+k] + ... over the D/8 whole vectors; f = sum of the tail elements (left to right, from 0);
 //           then f += lane[0], ..., lane[7].                         (D = 8: the plain left-to-right sum)
-// For D <= 3 this is ((dx*dx)+(dy*dy))+(dz*dz): the picks equal fps_kernel's (tests/test_gpu_zz_fps_nd.py cross-checks).
+// For D <= 3 this is ((dx*dx)+(dy*dy))+(dz*dz): the picks equal fps_kernel's (tests/test_gpu_xtra_index.py cross-checks).
 // Running distance starts at 1e10 (pix4point.py:27), update where dist < distance (47-48), argmax keeps the LOWEST index of
 // the maximum (torch.max, 51).
 //
 // Design: one CTA per cloud; the running minima live in a caller-provided (B,N) fp32 scratch (coalesced, L2-resident), the
 // points are read in place from global memory every iteration (N*D*4 bytes per iteration and cloud from L2), the argmax is
 // thread-local -> redux.sync per warp -> one shared-memory slot per warp -> every warp reduces the slots redundantly, so an
-// iteration has ONE __syncthreads (slots double-buffered by iteration parity).  Bound: L2 bandwidth / latency; not tuned -
-// no BASELINE config reaches it.
+// iteration has ONE __syncthreads (slots double-buffered by iteration parity).  Bound: L2 latency / bandwidth (a thread
+// loads several points - 128-bit loads when the rows allow - before it evaluates any); no BASELINE config reaches this path.
 #include "common.cuh"
 
 namespace p3tok {
@@ -59,10 +59,28 @@ __device__ __forceinline__ float torch_row_sum(const float (&q)[D]) {
   }
 }
 
-template <int D>
+// one point's D coordinates -> registers; V4: rows are 16-byte aligned (D % 4 == 0, stride % 4 == 0): 128-bit loads
+template <int D, bool V4>
+__device__ __forceinline__ void load_point(const float* __restrict__ pr, float (&v)[D]) {
+  if constexpr (V4) {
+#pragma unroll
+    for (int a = 0; a < D; a += 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(pr + a));
+      v[a] = t.x; v[a + 1] = t.y; v[a + 2] = t.z; v[a + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int a = 0; a < D; ++a) v[a] = __ldg(pr + a);
+  }
+}
+
+// U points per thread are loaded before any of them is evaluated (an iteration is a chain of dependent L2 round trips
+// otherwise: N = 8192, D = 8 measured 9.4 us per iteration with one point at a time): 4 for D <= 4, 2 for D <= 8, else 1
+template <int D, bool V4>
 __global__ void __launch_bounds__(1024)
 fps_nd_kernel(const float* __restrict__ x, int N, int64_t pt_stride, const int64_t* __restrict__ start_idx, int G,
               int64_t* __restrict__ out_idx, float* __restrict__ min_dist) {
+  constexpr int U = D <= 4 ? 4 : (D <= 8 ? 2 : 1);
   __shared__ uint2 wslot[2][32];
   const int cloud = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -78,23 +96,36 @@ fps_nd_kernel(const float* __restrict__ x, int N, int64_t pt_stride, const int64
   for (int g = 0; g < G; ++g) {
     if (tid == 0) out[g] = far;
     float c[D];
-#pragma unroll
-    for (int a = 0; a < D; ++a) c[a] = __ldg(P + (int64_t)far * pt_stride + a);
+    load_point<D, V4>(P + (int64_t)far * pt_stride, c);
 
     float bm = -1.f;
     uint32_t bi = 0xffffffffu;
-    for (int i = tid; i < N; i += nthreads) {
-      const float* pr = P + (int64_t)i * pt_stride;
-      float q[D];
+    for (int i0 = tid; i0 < N; i0 += U * nthreads) {
+      float v[U][D], m[U];
 #pragma unroll
-      for (int a = 0; a < D; ++a) {
-        const float df = __fsub_rn(__ldg(pr + a), c[a]);
-        q[a] = __fmul_rn(df, df);
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * nthreads;
+        if (i < N) {
+          load_point<D, V4>(P + (int64_t)i * pt_stride, v[u]);
+          m[u] = md[i];
+        }
       }
-      const float d = torch_row_sum<D>(q);
-      float m = md[i];
-      if (d < m) { m = d; md[i] = m; }
-      if (m > bm) { bm = m; bi = (uint32_t)i; }             // ascending i, strict >: the thread keeps its lowest index
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * nthreads;
+        if (i < N) {
+          float q[D];
+#pragma unroll
+          for (int a = 0; a < D; ++a) {
+            const float df = __fsub_rn(v[u][a], c[a]);
+            q[a] = __fmul_rn(df, df);
+          }
+          const float d = torch_row_sum<D>(q);
+          float mm = m[u];
+          if (d < mm) { mm = d; md[i] = mm; }
+          if (mm > bm) { bm = mm; bi = (uint32_t)i; }         // ascending i, strict >: the thread keeps its lowest index
+        }
+      }
     }
     // a thread without a pick (no point, or only NaN minima) never wins: key 0 is below f2ord of any value >= -1
     const uint32_t key = bi != 0xffffffffu ? f2ord(bm) : 0u;
@@ -115,7 +146,14 @@ static int fps_nd_launch(const float* x, int B, int N, int64_t pt_stride, const 
                          float* min_dist, cudaStream_t s) {
   int threads = N >= 4096 ? 1024 : ((N + 3) / 4 + 31) / 32 * 32;
   if (threads < 32) threads = 32;
-  fps_nd_kernel<D><<<B, threads, 0, s>>>(x, N, pt_stride, start, G, out, min_dist);
+  if constexpr (D % 4 == 0) {
+    if (pt_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+      fps_nd_kernel<D, true><<<B, threads, 0, s>>>(x, N, pt_stride, start, G, out, min_dist);
+      P3_LAUNCH_CHECK("fps_nd_kernel");
+      return P3TOK_OK;
+    }
+  }
+  fps_nd_kernel<D, false><<<B, threads, 0, s>>>(x, N, pt_stride, start, G, out, min_dist);
   P3_LAUNCH_CHECK("fps_nd_kernel");
   return P3TOK_OK;
 }
@@ -132,7 +170,7 @@ extern "C" int p3tok_fps_nd(const float* x, int64_t B, int64_t N, int64_t D, int
   P3_REQUIRE(D <= 16, P3TOK_ERR_UNSUPPORTED, "fps_nd: D=%lld > 16", (long long)D);
   if (B == 0 || G == 0) return P3TOK_OK;
   P3_REQUIRE(x && start_idx && out_idx && min_dist_ws, P3TOK_ERR_INVALID, "fps_nd: null pointer");
-  P3_REQUIRE(N < (1ll << 31) - 1024 && B < (1ll << 31) && G < (1ll << 31), P3TOK_ERR_UNSUPPORTED, "fps_nd: shape too large");
+  P3_REQUIRE(N < (1ll << 31) - 8192 && B < (1ll << 31) && G < (1ll << 31), P3TOK_ERR_UNSUPPORTED, "fps_nd: shape too large");
   cudaStream_t s = as_stream(stream);
   const int Bi = (int)B, Ni = (int)N, Gi = (int)G;
   switch ((int)D) {

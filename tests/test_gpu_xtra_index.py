@@ -112,6 +112,16 @@ def test_square_distance_matches_the_oracle_bit_for_bit():
     assert tuple(F.square_distance(to_dev(ctr[:, :0]), to_dev(x)).shape) == (B, 0, N)
 
 
+@pytest.mark.parametrize("B,S,N", [(1, 700, 1027), (3, 5, 33), (1, 2000, 4096), (2, 300, 1024), (5, 1, 1), (2, 257, 2050)])
+def test_square_distance_shapes(B, S, N):
+    """N off the 4-point quads and the 1024-point tiles (scalar stores), several 256-row passes, src rows split over
+    gridDim.y when the (tile, cloud) grid alone is small."""
+    x = synth.make_cloud("uniform", B, max(N, S), 29, 3)
+    pts, ctr = np.ascontiguousarray(x[:, :N]), np.ascontiguousarray(x[:, ::-1][:, :S])
+    got = F.square_distance(to_dev(ctr), to_dev(pts)).cpu().numpy()
+    assert np.array_equal(got, oracle.pair_dist(pts, ctr, oracle.KNN_APF_SQ))
+
+
 def test_square_distance_is_the_knn_kernels_distance():
     """The matrix entry at every selected neighbour equals the distance the kNN kernel reports for it, and the selected
     set is the k smallest (distance, index) pairs of the row."""
