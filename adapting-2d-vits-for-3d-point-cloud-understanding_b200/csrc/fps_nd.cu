@@ -20,8 +20,8 @@
 // Design: one CTA per cloud; the running minima live in a caller-provided (B,N) fp32 scratch (coalesced, L2-resident), the
 // points are read in place from global memory every iteration (N*D*4 bytes per iteration and cloud from L2), the argmax is
 // thread-local -> redux.sync per warp -> one shared-memory slot per warp -> every warp reduces the slots redundantly, so an
-// iteration has ONE __syncthreads (slots double-buffered by iteration parity).  Bound: L2 latency / bandwidth (a thread
-// loads several points - 128-bit loads when the rows allow - before it evaluates any); no BASELINE config reaches this path.
+// iteration has ONE __syncthreads (slots double-buffered by iteration parity).  Bound: the chain of L2 round trips of an
+// iteration (0.7-1.3 us; the xyz kernel with everything in registers: 0.3-0.6); no BASELINE config reaches this path.
 #include "common.cuh"
 
 namespace p3tok {
@@ -74,9 +74,13 @@ __device__ __forceinline__ void load_point(const float* __restrict__ pr, float (
   }
 }
 
-// U points per thread are loaded before any of them is evaluated (an iteration is a chain of dependent L2 round trips
-// otherwise: N = 8192, D = 8 measured 9.4 us per iteration with one point at a time): 4 for D <= 4, 2 for D <= 8, else 1
-template <int D, bool V4>
+// Two bodies for the pass over the points, chosen by the launch from the measured cross-over (B200, profiles/
+// r02_xtra_time*.txt).  STAGED = false: one point at a time - 0.74 us per iteration at N = 1024 (D = 4), 1.11 at N = 2048
+// (D = 6), where the whole iteration is one chain of L2 round trips (centroid, minima) and nothing is gained by staging
+// (the staged body measured 0.96 / 1.32 there).  STAGED = true, beyond 4 points per thread: U points (4 for D <= 4, 2 for
+// D <= 8, else 1) are loaded - 128-bit loads when the rows allow - before any of them is evaluated, so their round trips
+// overlap: N = 8192, D = 8: 9.44 -> 4.04 us per iteration.
+template <int D, bool V4, bool STAGED>
 __global__ void __launch_bounds__(1024)
 fps_nd_kernel(const float* __restrict__ x, int N, int64_t pt_stride, const int64_t* __restrict__ start_idx, int G,
               int64_t* __restrict__ out_idx, float* __restrict__ min_dist) {
@@ -100,30 +104,46 @@ fps_nd_kernel(const float* __restrict__ x, int N, int64_t pt_stride, const int64
 
     float bm = -1.f;
     uint32_t bi = 0xffffffffu;
-    for (int i0 = tid; i0 < N; i0 += U * nthreads) {
-      float v[U][D], m[U];
+    if constexpr (!STAGED) {
+      for (int i = tid; i < N; i += nthreads) {
+        const float* pr = P + (int64_t)i * pt_stride;
+        float q[D];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = i0 + u * nthreads;
-        if (i < N) {
-          load_point<D, V4>(P + (int64_t)i * pt_stride, v[u]);
-          m[u] = md[i];
+        for (int a = 0; a < D; ++a) {
+          const float df = __fsub_rn(__ldg(pr + a), c[a]);
+          q[a] = __fmul_rn(df, df);
         }
+        const float d = torch_row_sum<D>(q);
+        float m = md[i];
+        if (d < m) { m = d; md[i] = m; }
+        if (m > bm) { bm = m; bi = (uint32_t)i; }             // ascending i, strict >: the thread keeps its lowest index
       }
+    } else {
+      for (int i0 = tid; i0 < N; i0 += U * nthreads) {
+        float v[U][D], m[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = i0 + u * nthreads;
-        if (i < N) {
-          float q[D];
-#pragma unroll
-          for (int a = 0; a < D; ++a) {
-            const float df = __fsub_rn(v[u][a], c[a]);
-            q[a] = __fmul_rn(df, df);
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * nthreads;
+          if (i < N) {
+            load_point<D, V4>(P + (int64_t)i * pt_stride, v[u]);
+            m[u] = md[i];
           }
-          const float d = torch_row_sum<D>(q);
-          float mm = m[u];
-          if (d < mm) { mm = d; md[i] = mm; }
-          if (mm > bm) { bm = mm; bi = (uint32_t)i; }         // ascending i, strict >: the thread keeps its lowest index
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * nthreads;
+          if (i < N) {
+            float q[D];
+#pragma unroll
+            for (int a = 0; a < D; ++a) {
+              const float df = __fsub_rn(v[u][a], c[a]);
+              q[a] = __fmul_rn(df, df);
+            }
+            const float d = torch_row_sum<D>(q);
+            float mm = m[u];
+            if (d < mm) { mm = d; md[i] = mm; }
+            if (mm > bm) { bm = mm; bi = (uint32_t)i; }       // ascending i, strict >: the thread keeps its lowest index
+          }
         }
       }
     }
@@ -144,16 +164,16 @@ fps_nd_kernel(const float* __restrict__ x, int N, int64_t pt_stride, const int64
 template <int D>
 static int fps_nd_launch(const float* x, int B, int N, int64_t pt_stride, const int64_t* start, int G, int64_t* out,
                          float* min_dist, cudaStream_t s) {
-  int threads = N >= 4096 ? 1024 : ((N + 3) / 4 + 31) / 32 * 32;
+  int threads = ((N + 3) / 4 + 31) / 32 * 32;             // 4 points per thread up to 1024 threads (1 or 2 measured no better)
+  if (threads > 1024) threads = 1024;
   if (threads < 32) threads = 32;
-  if constexpr (D % 4 == 0) {
-    if (pt_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-      fps_nd_kernel<D, true><<<B, threads, 0, s>>>(x, N, pt_stride, start, G, out, min_dist);
-      P3_LAUNCH_CHECK("fps_nd_kernel");
-      return P3TOK_OK;
-    }
+  if (N <= 4 * 1024) {
+    fps_nd_kernel<D, false, false><<<B, threads, 0, s>>>(x, N, pt_stride, start, G, out, min_dist);
+  } else if (D % 4 == 0 && pt_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    fps_nd_kernel<D, D % 4 == 0, true><<<B, threads, 0, s>>>(x, N, pt_stride, start, G, out, min_dist);
+  } else {
+    fps_nd_kernel<D, false, true><<<B, threads, 0, s>>>(x, N, pt_stride, start, G, out, min_dist);
   }
-  fps_nd_kernel<D, false><<<B, threads, 0, s>>>(x, N, pt_stride, start, G, out, min_dist);
   P3_LAUNCH_CHECK("fps_nd_kernel");
   return P3TOK_OK;
 }

@@ -38,12 +38,13 @@ def test_fps_nd_matches_the_reference_fixture(golden_dir, name):
         assert np.array_equal(got, g[f"idx_D{D}"]), D        # == the reference's picks
 
 
+@pytest.mark.parametrize("N", [1500, 6000])     # one point at a time / several points staged per thread (csrc/fps_nd.cu)
 @pytest.mark.parametrize("D", list(range(1, 17)))
-def test_fps_nd_distance_bits_follow_torchs_summation_order(D):
+def test_fps_nd_distance_bits_follow_torchs_summation_order(D, N):
     """After ONE iteration the caller's scratch holds every point's distance to the start point: the kernel's arithmetic
     itself, compared bit for bit with the oracle's restatement of torch.sum((p - c) ** 2, -1) (which the CPU suite pins
     against torch) - index equality alone would not notice a different summation order."""
-    B, N = 2, 1500
+    B = 2
     pts = synth.make_points_nd(B, N, D, 300 + D)
     st = synth.start_indices(B, N, 300 + D)
     x, s = to_dev(pts), to_dev(st)
@@ -117,7 +118,7 @@ def test_square_distance_shapes(B, S, N):
     """N off the 4-point quads and the 1024-point tiles (scalar stores), several 256-row passes, src rows split over
     gridDim.y when the (tile, cloud) grid alone is small."""
     x = synth.make_cloud("uniform", B, max(N, S), 29, 3)
-    pts, ctr = np.ascontiguousarray(x[:, :N]), np.ascontiguousarray(x[:, ::-1][:, :S])
+    pts, ctr = np.ascontiguousarray(x[:, :N]), np.ascontiguousarray(x[:, ::-1][:, :S]).copy()
     got = F.square_distance(to_dev(ctr), to_dev(pts)).cpu().numpy()
     assert np.array_equal(got, oracle.pair_dist(pts, ctr, oracle.KNN_APF_SQ))
 
