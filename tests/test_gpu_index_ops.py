@@ -370,14 +370,16 @@ def test_knn_query_rejects_a_foreign_workspace():
 
 
 def test_farthest_point_sampling_fewer_than_three_coordinates():
-    """pix4point.py:44 sums over all D coordinates; D < 3 runs zero-padded (adds exact +0 terms)."""
+    """pix4point.py:44 sums over all D coordinates; D < 3 (the general-D kernel) equals the zero-padded xyz sampling:
+    the padding only adds exact +0 terms.  D > 3: tests/test_gpu_xtra_index.py."""
     p2 = synth.make_cloud("uniform", 2, 300, 5, 3)[..., :2].copy()
     st = synth.start_indices(2, 300, 5)
     got = F.farthest_point_sampling(to_dev(p2), 40, to_dev(st)).cpu().numpy()
     ref = oracle.fps(np.concatenate([p2, np.zeros((2, 300, 1), np.float32)], -1), st, 40)
     assert np.array_equal(got, ref)
-    with pytest.raises(RuntimeError, match="D > 3"):
-        F.farthest_point_sampling(torch.zeros(1, 8, 5, device=dev()), 2)
+    assert np.array_equal(got, oracle.fps_nd(p2, st, 40))
+    with pytest.raises(RuntimeError, match="16"):
+        F.farthest_point_sampling(torch.zeros(1, 8, 17, device=dev()), 2)
 
 
 def test_seeded_draw_reproduces_reference_semantics():
