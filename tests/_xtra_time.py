@@ -24,6 +24,13 @@ def timed(fn, reps=5):
 
 
 dev = torch.device("cuda:0")
+if len(sys.argv) > 1 and sys.argv[1] == "ncu":     # one launch of each kernel for `ncu --set full` (no timing)
+    x = torch.from_numpy(synth.make_cloud("uniform", 16, 65536, 2, 3)).to(dev)
+    ops.square_distance(x[:, :512].contiguous(), x)
+    p = torch.from_numpy(synth.make_points_nd(32, 8192, 8, 1)).to(dev)
+    ops.fps_nd(p, torch.zeros(32, dtype=torch.long, device=dev), 512)
+    torch.cuda.synchronize()
+    sys.exit(0)
 a = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16)
 for _ in range(200):                       # ~0.3 s of tensor work: clocks up before anything is timed
     a @ a
