@@ -49,3 +49,30 @@ def test_apf_pointnet_wide_clouds(C, prec, rtol):
     tok = net(to_dev(x), to_dev(st)).cpu().numpy()
     otok, grp = oracle.pointnet_apf(sd, x, st, G, k)
     assert_tokens_close(tok, otok, rtol, f"APF C={C} {prec}")
+
+
+@pytest.mark.parametrize("prec,rtol", [("fp32", 1e-4), ("bf16", 1e-2)])
+@pytest.mark.parametrize("k", [1, 5, 24, 48, 128])
+def test_group_sizes_beside_the_baseline(k, prec, rtol):
+    """Neighbourhood sizes that are not 8 / 16 / 32 / 64: one neighbour, sizes that do not divide the 32-row pooling blocks
+    or the 256-row tiles, and the kNN kernels' maximum (128) - APF at E = 384 (the fused pair kernels' widths) and a
+    two-stage P3Embed at 128 / 256."""
+    B, N, G, E = 2, 512, 20, 384
+    x = synth.make_cloud("clustered", B, N, 90 + k, 3)
+    st = synth.start_indices(B, N, 90 + k)
+    sd = synth.apf_encoder_state(E, 6, 90 + k)
+    net = PointNet(E, G, k, 6, precision=prec).eval().to(dev())
+    net.encoder.load_state_dict(synth.to_torch_state(sd))
+    tok = net(to_dev(x), to_dev(st)).cpu().numpy()
+    otok, _ = oracle.pointnet_apf(sd, x, st, G, k)
+    assert_tokens_close(tok, otok, rtol, f"APF k={k} {prec}")
+
+    sd2 = synth.p3embed_state(3, 1 / 16, 4, 4, 256, 190 + k)
+    mod = P3Embed(sample_ratio=1 / 16, k=k, embed_dim=256, precision=prec).eval().to(dev())
+    mod.load_state_dict(synth.to_torch_state(sd2), strict=True)
+    starts = [synth.start_indices(B, N, 190 + k, 0), synth.start_indices(B, N // 4, 190 + k, 1)]
+    ps, fs = mod(to_dev(x), to_dev(x).transpose(1, 2).contiguous(), [to_dev(s) for s in starts])
+    op, of, _ = oracle.p3embed(sd2, x, x.copy(), starts, k, 2)
+    for s in (1, 2):
+        assert np.array_equal(ps[s].cpu().numpy(), op[s])
+        assert_tokens_close(fs[s].transpose(1, 2).cpu().numpy(), of[s], rtol * s, f"P3Embed k={k} {prec} stage {s - 1}")
