@@ -21,5 +21,8 @@ for prec in ("fp32", "bf16"):
     m = P3Embed(sample_ratio=1 / 16, k=16, embed_dim=128, precision=prec).eval().to(dev)
     m.load_state_dict(synth.to_torch_state(synth.p3embed_state(3, 1 / 16, 4, 4, 128, 2)))
     ps, fs = m(x, x.transpose(1, 2).contiguous(), [st, t(synth.start_indices(3, 128, 1, 1))])
+pn = t(synth.make_points_nd(2, 5000, 6, 4))                      # general-D FPS (both loop bodies) and the squared-distance matrix
+ops.fps_nd(pn, t(synth.start_indices(2, 5000, 4)), 12); ops.fps_nd(pn[:, :300].contiguous(), t(synth.start_indices(2, 300, 4)), 12)
+ops.square_distance(x[:, :37].contiguous(), x); ops.square_distance(x[:, :5, :3].contiguous(), x[:, :301].contiguous())
 torch.cuda.synchronize()
 print("sanitize-run ok", float(out.abs().sum()), float(fs[-1].abs().sum()))
