@@ -1,5 +1,6 @@
 """Timing of the general-D FPS and the squared-distance matrix (scratch driver, not a test):
-python tests/_xtra_time.py  ->  one line per case, CUDA events, after warm-up."""
+python tests/_xtra_time.py      ->  one line per case, CUDA events, after a clock warm-up (profiles/r02_xtra_time.txt)
+python tests/_xtra_time.py ncu  ->  one launch of each kernel, for `ncu --set full` (profiles/r02_xtra_ncu_full.txt)"""
 import os
 import sys
 
@@ -35,15 +36,14 @@ a = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16)
 for _ in range(200):                       # ~0.3 s of tensor work: clocks up before anything is timed
     a @ a
 torch.cuda.synchronize()
-for _ in (0,):
-    for B, N, D, G in ((32, 1024, 4, 256), (128, 2048, 6, 128), (32, 8192, 8, 512), (256, 512, 5, 128), (128, 2048, 3, 128)):
-        x = torch.from_numpy(synth.make_points_nd(B, N, D, 1)).to(dev)
-        st = torch.zeros(B, dtype=torch.long, device=dev)
-        ms = timed(lambda: ops.fps_nd(x, st, G), reps=20)
-        line = f"fps_nd B={B} N={N} D={D} G={G}: {ms:.3f} ms ({ms * 1e3 / G:.2f} us/iteration)"
-        if D == 3:
-            line += f"; fps_kernel (xyz path) {timed(lambda: ops.fps_sweep(x, st, G), reps=20):.3f} ms"
-        print(line)
+for B, N, D, G in ((32, 1024, 4, 256), (128, 2048, 6, 128), (32, 8192, 8, 512), (256, 512, 5, 128), (128, 2048, 3, 128)):
+    x = torch.from_numpy(synth.make_points_nd(B, N, D, 1)).to(dev)
+    st = torch.zeros(B, dtype=torch.long, device=dev)
+    ms = timed(lambda: ops.fps_nd(x, st, G), reps=20)
+    line = f"fps_nd B={B} N={N} D={D} G={G}: {ms:.3f} ms ({ms * 1e3 / G:.2f} us/iteration)"
+    if D == 3:
+        line += f"; fps_kernel (xyz path) {timed(lambda: ops.fps_sweep(x, st, G), reps=20):.3f} ms"
+    print(line)
 for B, S, N in ((128, 128, 2048), (16, 2048, 65536)):
     x = torch.from_numpy(synth.make_cloud("uniform", B, N, 2, 3)).to(dev)
     c = x[:, :S].contiguous()
